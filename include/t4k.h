@@ -1,0 +1,191 @@
+/*
+ * t4k.h — C-ABI of libt4k.so: the B200-native (sm_100a) replacement of tensorForth's
+ * tensor-op hot path.  Plain pointers and sizes, no C++/torch types.
+ *
+ * The reference has no plugin/FFI layer; its seam is source level: the __KERN__ prototypes
+ * of src/t4math.h:138-184 and src/nn/nmath.h:41-112 as launched through the FORK* macros
+ * (src/t4base.h:129-159) by src/mu/tensor.cu, src/nn/forward.cu, backprop.cu, gradient.cu.
+ * Each entry point below names the reference launch site(s) it replaces (file:line relative
+ * to the reference tree).  INTEGRATION.md shows the shim a maintainer adds on the reference
+ * side (the bodies of Tensor::xxx / Model::_fxxx/_bxxx re-expressed on these calls).
+ *
+ * Conventions
+ *  - All tensor data is FP32, NHWC; Tensor.shape = {H,W,C,N} (src/mu/tensor.h:53,109-112).
+ *  - Every pointer is a DEVICE pointer (cudaMalloc or cudaMallocManaged) owned by the caller
+ *    (MMU arena, src/mu/mmu.cu:199-209).  The library never allocates or frees user-visible
+ *    memory; its private workspace (reduction partials, split planes, TMA descriptors) is
+ *    internal, per device, grown on demand.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is what
+ *    the reference uses: FORK* pass no stream).  Calls are STREAM-ORDERED and ASYNCHRONOUS:
+ *    no cudaDeviceSynchronize() inside (the reference syncs after every launch via GPU_CHK,
+ *    src/ten4_types.h:192).  Scalar results are written to a device float the caller reads
+ *    (reference: Tensor::_tmp = &data[numel], src/mu/tensor.cu:231-233); use t4k_sync() or
+ *    a stream-ordered cudaMemcpy at the host-read points.
+ *  - Return value: 0 on success; a positive cudaError_t if a launch failed; negative T4K_E*
+ *    for argument errors (the reference prints and returns the output untouched,
+ *    src/mu/tensor.cu:35-38, src/nn/forward.cu:147-150).  Nothing is printed, nothing
+ *    calls cudaDeviceReset().
+ *  - There is NO CPU fallback: without a CUDA device every compute call returns an error.
+ */
+#ifndef T4K_H
+#define T4K_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T4K_VERSION 100                /* 1.00 */
+#define T4K_EINVAL  (-1)               /* bad argument / unsupported shape */
+#define T4K_ENOSUP  (-2)               /* configuration the reference also rejects (e.g. conv K,S,P) */
+#define T4K_ENOMEM  (-3)               /* workspace allocation failed */
+
+typedef void *t4k_stream_t;            /* cudaStream_t */
+
+/* math_op — identical numbering to src/t4math.h:25-56 */
+enum t4k_math_op {
+    T4K_ABS = 0, T4K_NEG, T4K_EXP, T4K_LN, T4K_LOG, T4K_TANH, T4K_RELU, T4K_SIGM, T4K_SQRT,
+    T4K_RCP, T4K_SAT, T4K_IDEN, T4K_FILL, T4K_GFILL, T4K_SCALE, T4K_POW,
+    T4K_ADD, T4K_SUB, T4K_MUL, T4K_DIV, T4K_MOD, T4K_MAX, T4K_MIN
+};
+/* t4_layer — identical numbering to src/nn/ntypes.h:16-36 */
+enum t4k_layer {
+    T4K_L_NONE = 0, T4K_L_CONV, T4K_L_LINEAR, T4K_L_FLATTEN, T4K_L_RELU, T4K_L_TANH,
+    T4K_L_SIGMOID, T4K_L_SELU, T4K_L_LEAKYRL, T4K_L_ELU, T4K_L_DROPOUT, T4K_L_SOFTMAX,
+    T4K_L_LOGSMAX, T4K_L_AVGPOOL, T4K_L_MAXPOOL, T4K_L_MINPOOL, T4K_L_BATCHNM,
+    T4K_L_USAMPLE, T4K_L_DCONV
+};
+/* t4_loss — src/nn/ntypes.h:38-43 */
+enum t4k_loss { T4K_LOSS_MSE = 0, T4K_LOSS_BCE, T4K_LOSS_CE, T4K_LOSS_NLL };
+/* rand_opt — src/util.h (UNIFORM, NORMAL) */
+enum t4k_rand_opt { T4K_UNIFORM = 0, T4K_NORMAL = 1 };
+/* GEMM engine selection for t4k_gemm_ex (0 = automatic) */
+enum t4k_gemm_engine { T4K_GEMM_AUTO = 0, T4K_GEMM_SIMT = 1, T4K_GEMM_TC = 2 };
+
+/* ---- library / device ------------------------------------------------------------- */
+int         t4k_version(void);
+const char *t4k_strerror(int rc);
+int         t4k_device_count(void);                    /* 0 when no CUDA device/driver */
+int         t4k_sm_count(void);                        /* SMs of the current device    */
+int         t4k_sync(t4k_stream_t stream);             /* cudaStreamSynchronize        */
+long        t4k_launch_count(void);                    /* kernels launched by this library so far */
+
+/* ---- elementwise: src/t4math.cu:134-234 ------------------------------------------- */
+/* k_math via Tensor::map (src/mu/tensor.cu:566-571): in-place A[j] = op(A[j], v) */
+int t4k_map(int op, float *A, float v, int64_t n, t4k_stream_t s);
+/* k_ts_op via Tensor::ten_op(A,v,O) (src/mu/tensor.cu:17-23): O = A op v, op in ADD..DIV */
+int t4k_ts_op(int op, const float *A, float v, float *O, int64_t n, t4k_stream_t s);
+/* k_tt_op via Tensor::ten_op(A,B,O) (src/mu/tensor.cu:29-53): O[n] = A[Na==1?0:n] op B[Nb==1?0:n],
+ * each slice `hwc` floats, N = max(Na,Nb) slices (the reference loops over n on the host) */
+int t4k_tt_op(int op, const float *A, const float *B, float *O, int64_t hwc, int Na, int Nb, t4k_stream_t s);
+/* k_copy via Tensor::copy (src/mu/tensor.cu:204-208) */
+int t4k_copy(const float *src, float *dst, int64_t n, t4k_stream_t s);
+/* k_transpose via Tensor::transpose (src/mu/tensor.cu:210-219): per sample, per channel 2-D transpose */
+int t4k_transpose(const float *A, float *T, int N, int H, int W, int C, t4k_stream_t s);
+/* k_identity via Tensor::identity (src/mu/tensor.cu:548-555) */
+int t4k_identity(float *T, int N, int H, int W, int C, t4k_stream_t s);
+
+/* ---- reductions: src/t4math.cu:23-131,248-365; results OVERWRITE *out (no pre-zero) --- */
+int t4k_sum(const float *A, int64_t n, float *out, t4k_stream_t s);                 /* k_sum  tensor.cu:225-236 */
+int t4k_nvar(const float *A, float avg, int64_t n, float *out, t4k_stream_t s);     /* k_nvar tensor.cu:244-259 */
+int t4k_minmax(const float *A, int64_t n, int find_max, float *out, t4k_stream_t s);/* k_max  tensor.cu:261-277 */
+/* mean and the reference's std = sqrt(Σ(x-μ)²)/n (src/mu/tensor.cu:238-251) in one call: out[0]=avg, out[1]=std */
+int t4k_avg_std(const float *A, int64_t n, float *out2, t4k_stream_t s);
+/* k_dot via Tensor::dot (src/mu/tensor.cu:61-72,279-287): O[n,c] = alpha*Σ_k A[n,k,c]B[n,k,c] + beta*O[n,c] */
+int t4k_dot(const float *A, const float *B, float *O, float alpha, float beta,
+            int K, int C, int Na, int Nb, t4k_stream_t s);
+/* Tensor::loss (src/mu/tensor.cu:289-325, k_bce src/t4math.cu:248-274), NON-destructive on `out`
+ * (the reference works on a duplicate, src/nn/loss.cpp:129-132): *loss = loss_kind(out,tgt)/N */
+int t4k_loss(int kind, const float *out, const float *tgt, int64_t numel, int N, float *loss, t4k_stream_t s);
+/* k_nan_inf via Tensor::has_nan (src/mu/tensor.cu:326-333): *cnt = #NaN + #Inf */
+int t4k_nan_inf(const float *A, int64_t n, int *cnt, t4k_stream_t s);
+
+/* ---- GEMM: src/t4math.cu:370-734 via Tensor::mm/linear/gemm1-4 (src/mu/tensor.cu:74-201) --
+ * O[b][M,N,C] = alpha * op(A[b]) @ op(B[b]) + beta * O[b], channel interleaved (stride C),
+ * op(A) = tA ? A[K,M,C] : A[M,K,C];  op(B) = tB ? B[N,K,C] : B[K,N,C].
+ * batch slices are strideA/strideB/strideO floats apart (0 = broadcast, tensor.cu:175-177).
+ * FP32 in, FP32 out.  Engine: tcgen05 3xTF32 (error-compensated split, FP32 accumulate in
+ * TMEM) for large aligned C==1 problems, FP32-FMA SIMT otherwise. */
+int t4k_gemm(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
+             int M, int N, int K, int C, int batch, int64_t strideA, int64_t strideB, int64_t strideO,
+             t4k_stream_t s);
+int t4k_gemm_ex(int engine, const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
+             int M, int N, int K, int C, int batch, int64_t strideA, int64_t strideB, int64_t strideO,
+             t4k_stream_t s);
+
+/* ---- NN forward: src/nn/forward.cu + src/nn/nmath.cu/.tcu ---------------------------- */
+/* k_bias (nmath.cu:27-35, forward.cu:195): Y[n,e] += B[e] */
+int t4k_bias(const float *B, float *Y, int N, int E0, t4k_stream_t s);
+/* Model::_flinear (forward.cu:158-198): Y[N,E0] = X[N,E1] @ W[E0,E1]^T + B[E0]  (GEMM + fused bias) */
+int t4k_linear_fwd(const float *X, const float *W, const float *B, float *Y, int N, int E0, int E1, t4k_stream_t s);
+/* k_activate (nmath.cu:37-70, forward.cu:201-209): writes O and the saved derivative/mask F.
+ * layer in RELU,TANH,SIGMOID,SELU,LEAKYRL,ELU,DROPOUT; for DROPOUT F holds U(0,1] on entry. */
+int t4k_activate_fwd(int layer, const float *I, float *O, float *F, float alpha, int64_t n, t4k_stream_t s);
+/* k_softmax_small/k_softmax (nmath.cu:74-169, forward.cu:231-243): row softmax, rows of C */
+int t4k_softmax_fwd(const float *I, float *O, int N, int C, t4k_stream_t s);
+/* Model::_flogsoftmax AS CODED (forward.cu:246-259): O = exp(I) - log10(max(Σ_row exp(I),1e-6)) */
+int t4k_logsoftmax_fwd(const float *I, float *O, int N, int C, t4k_stream_t s);
+/* k_conv2d<TS,KS,S,P> (nmath.tcu:34-104, forward.cu:126-155).  F is [C1,KS,KS,C0], B is [C0].
+ * Writes EVERY element of O (no pre-zero needed, unlike forward.cu:138).
+ * (KS,S,P) in {(1,1,0),(3,1,1),(4,2,1),(5,1,2)} as in the reference, else T4K_ENOSUP. */
+int t4k_conv2d_fwd(const float *I, const float *F, const float *B, float *O,
+                   int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, t4k_stream_t s);
+/* k_pool<KS> (nmath.tcu:122-186, forward.cu:212-228; also upsample-backward backprop.cu:285-300)
+ * layer in AVGPOOL,MAXPOOL,MINPOOL,USAMPLE; KS in {2,3}; stride == KS */
+int t4k_pool_fwd(int layer, const float *I, float *O, int N, int H1, int W1, int H0, int W0, int C, int KS, t4k_stream_t s);
+/* k_batchnorm_1/2/3 (nmath.cu:177-264, forward.cu:264-309).  scratch3C = mtum[4] layout:
+ * [0,C) rvar = 1/(sqrt(max(var,0))+1e-6), [C,2C) mean, [2C,3C) unused in forward. */
+int t4k_batchnorm_fwd(const float *I, float *O, float *XH, const float *gamma, const float *beta,
+                      float *scratch3C, int N, int HW, int C, t4k_stream_t s);
+
+/* ---- NN backward: src/nn/backprop.cu ------------------------------------------------- */
+/* k_dlinear_db (nmath.cu:274-280, backprop.cu:239): dB[e] += Σ_n dY[n,e] */
+int t4k_dbias(const float *dY, float *dB, int N, int E0, t4k_stream_t s);
+/* Model::_blinear (backprop.cu:194-254): if train { dB += ΣdY; dW += dY^T@X }; dX = dY@W.
+ * dX may alias X's buffer?  NO — dW needs X; pass distinct buffers or dX==X (handled: dW first). */
+int t4k_linear_bwd(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
+                   int N, int E0, int E1, int train, t4k_stream_t s);
+/* Model::_bactivate (backprop.cu:257-263): dX = dY * F */
+int t4k_activate_bwd(const float *dY, const float *F, float *dX, int64_t n, t4k_stream_t s);
+/* k_dconv2d (nmath.tcu:211-338, backprop.cu:153-191): dX written in full (no pre-zero needed),
+ * uses the reference's 180°-FLIPPED filter taps for dX (nmath.tcu:304); if train: dF += , dB += . */
+int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, float *dX, float *dF, float *dB,
+                   int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P,
+                   int train, t4k_stream_t s);
+/* k_dpool<KS> (nmath.tcu:475-568, backprop.cu:266-280; also upsample-forward forward.cu:314-329):
+ * IN PLACE on the forward input I: max/min → zero window, dO at first strict max/min. */
+int t4k_pool_bwd(int layer, float *I, const float *dO, int N, int H1, int W1, int H0, int W0, int C, int KS, t4k_stream_t s);
+/* k_dbatchnorm_1/2/3 (nmath.cu:295-414, backprop.cu:312-370): scratch3C as in forward
+ * ([C,2C) and [2C,3C) receive mean(dy), mean(dy*xhat)); if train: dgamma += mean(dy*xhat), dbeta += mean(dy) */
+int t4k_batchnorm_bwd(const float *dO, const float *XH, float *dX, const float *gamma,
+                      float *dgamma, float *dbeta, float *scratch3C, int N, int HW, int C, int train, t4k_stream_t s);
+
+/* ---- optimizers: src/nn/gradient.cu:133-169 + nmath.cu:419-472 ------------------------ */
+int t4k_sgd(float *G, float *DG, float *M, int Nw, float lr, float b, int64_t n, t4k_stream_t s);
+int t4k_adam(float *G, float *DG, float *M, float *V, float lr, float b1, float b2, int64_t n, t4k_stream_t s);
+int t4k_adamw(float *G, float *DG, float *M, float *V, float lr, float b1, float b2, float wd, int64_t n, t4k_stream_t s);
+/* one launch for a whole model: `seg` is a DEVICE array of nseg segments over flat arenas
+ * G/DG/M/V (same offsets in each); kind 0=sgd 1=adam 2=adamw.  Replaces the per-tensor launch
+ * loop of Model::gradient (gradient.cu:99-121). */
+typedef struct { int64_t off; int64_t len; int32_t Nw; int32_t pad; } t4k_seg_t;
+int t4k_optim_multi(int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
+                    int64_t total, float lr, float b1, float b2, float wd, t4k_stream_t s);
+
+/* ---- RNG: src/util.cu:35-70 via System::rand (src/sys.cpp:77-95) ---------------------- */
+/* d[i] = scale * (bias + x), x ~ U(0,1] or N(0,1).  Counter-based Philox4x32-10 keyed by
+ * (seed, element index): reproducible and independent of grid size / GPU count (the reference's
+ * XORWOW stream is seeded with time(), so bit parity is not defined). */
+int t4k_rand_seed(uint64_t seed);
+int t4k_rand(float *d, int64_t n, int opt, float bias, float scale, t4k_stream_t s);
+int t4k_rand_at(float *d, int64_t n, int opt, float bias, float scale, uint64_t seed, uint64_t offset, t4k_stream_t s);
+
+/* ---- loss-side host loops moved on device: src/nn/loss.cpp:47-107 ---------------------- */
+/* Model::onehot(Dataset&): hot[n, label<E ? label : 0] = 1, everything else 0; labels are device int32 */
+int t4k_onehot(const int32_t *label, float *hot, int N, int E, t4k_stream_t s);
+/* Model::hit: *cnt = Σ_n (int)hot[n, argmax_first(out[n])] */
+int t4k_hit(const float *out, const float *hot, int N, int E, int *cnt, t4k_stream_t s);
+/* fused softmax-output step: p - y in place (Model::_bprep, backprop.cu:97-103) is t4k_tt_op(SUB) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T4K_H */

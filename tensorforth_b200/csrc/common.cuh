@@ -1,0 +1,65 @@
+// common.cuh — shared device/host helpers for libt4k (sm_100a only)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+#include "../../include/t4k.h"
+
+#define T4K_SMS          148                  // B200: 148 SMs (grid sizing; real count read at runtime)
+#define T4K_THREADS      256
+#define DU_EPS           1.0e-6f              // src/ten4_types.h:85
+#define DU_LNX           1.0e-12f             // src/t4math.cu:172
+
+namespace t4k {
+
+extern long g_launches;                       // counted kernel launches (t4k_launch_count)
+int  sm_count();                              // cached cudaDevAttrMultiProcessorCount
+int  check_launch();                          // cudaGetLastError() → rc, ++g_launches
+void *workspace(size_t bytes, int slot);      // library-owned per-device scratch (grown on demand)
+float *reduce_slot(cudaStream_t st);          // 4 KiB partials + counter, ring of slots, zeroed counter
+
+static inline cudaStream_t STRM(t4k_stream_t s) { return (cudaStream_t)s; }
+
+// persistent-ish grid for HBM streaming kernels: enough CTAs to cover n items at `per_thread`
+// each, capped at 8 resident CTAs of 256 threads per SM (148 x 8 = 1184).
+static inline int stream_grid(int64_t n_items, int per_thread = 1) {
+    int64_t need = (n_items + (int64_t)T4K_THREADS * per_thread - 1) / ((int64_t)T4K_THREADS * per_thread);
+    int64_t cap  = (int64_t)sm_count() * 8;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+static inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide sum of `v` (blockDim.x multiple of 32, <= 1024); result valid in thread 0
+__device__ __forceinline__ float block_sum(float v, float *sm32) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sm32[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (lane < (int)(blockDim.x >> 5)) ? sm32[lane] : 0.0f;
+        v = warp_sum(v);
+    }
+    __syncthreads();
+    return v;
+}
+// 128-bit streaming global access
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void   stg4(float *p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+} // namespace t4k

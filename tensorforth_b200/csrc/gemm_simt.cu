@@ -1,0 +1,169 @@
+// gemm_simt.cu — general FP32-FMA GEMM (CUDA cores): every (tA,tB), channel-interleaved C>1,
+// batch/broadcast, arbitrary M,N,K, deterministic split-K for skinny problems.
+//   replaces k_gemm / k_gemm_claude / k_gemm_tile_claude(_x2) (src/t4math.cu:370-734) for the
+//   shapes the tcgen05 engine (gemm_tc.cu) does not take: small / unaligned / C>1.
+// Tile 64x64x16, 256 threads, 4x4 register micro-tile, register-staged double buffering.
+// Bound: FP32 FMA pipe (128 FMA/clk/SM); used where launch latency, not math, dominates.
+#include "common.cuh"
+
+namespace t4k {
+
+#define SBM 64
+#define SBN 64
+#define SBK 16
+
+struct GemmP {
+    const float *A, *B; float *O;
+    float alpha, beta;
+    int M, N, K, C;
+    int64_t sA, sB, sO;          // batch strides (floats), 0 = broadcast
+    int splits, kchunk;          // split-K: kchunk = K range per split (multiple of SBK)
+    float *part;                 // split-K partials [batch*C][splits][M*N] (nullptr when splits==1)
+};
+
+template<bool TA, bool TB>
+__global__ void __launch_bounds__(256) k_gemm_simt(GemmP p) {
+    __shared__ float sA[2][SBK][SBM + 4];
+    __shared__ float sB[2][SBK][SBN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int zc = blockIdx.z % p.C;                          // channel
+    const int zs = (blockIdx.z / p.C) % p.splits;             // k-split
+    const int zb = blockIdx.z / (p.C * p.splits);             // batch
+    const int C = p.C, M = p.M, N = p.N, K = p.K;
+    const float *A = p.A + zb * p.sA + zc;
+    const float *B = p.B + zb * p.sB + zc;
+    const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+    const int kbeg = zs * p.kchunk, kend = min(K, kbeg + p.kchunk);
+
+    // loader coordinates: contiguous global dimension on the fast thread index
+    // A normal  [M,K]: (m = tid/16 + 16*i, k = tid%16)     A^T [K,M]: (k = tid/64 + 4*i, m = tid%64)
+    // B normal  [K,N]: (k = tid/64 + 4*i, n = tid%64)      B^T [N,K]: (n = tid/16 + 16*i, k = tid%16)
+    float ra[4], rb[4];
+    auto load = [&](int k0) {
+        #pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int m, k;
+            if (TA) { k = (tid >> 6) + 4 * i; m = tid & 63; } else { m = (tid >> 4) + 16 * i; k = tid & 15; }
+            const int gm = m0 + m, gk = k0 + k;
+            ra[i] = (gm < M && gk < kend) ? __ldg(A + (TA ? ((int64_t)gk * M + gm) : ((int64_t)gm * K + gk)) * C) : 0.0f;
+            int n, kb;
+            if (TB) { n = (tid >> 4) + 16 * i; kb = tid & 15; } else { kb = (tid >> 6) + 4 * i; n = tid & 63; }
+            const int gn = n0 + n, gkb = k0 + kb;
+            rb[i] = (gn < N && gkb < kend) ? __ldg(B + (TB ? ((int64_t)gn * K + gkb) : ((int64_t)gkb * N + gn)) * C) : 0.0f;
+        }
+    };
+    auto store = [&](int buf) {
+        #pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int m, k;
+            if (TA) { k = (tid >> 6) + 4 * i; m = tid & 63; } else { m = (tid >> 4) + 16 * i; k = tid & 15; }
+            sA[buf][k][m] = ra[i];
+            int n, kb;
+            if (TB) { n = (tid >> 4) + 16 * i; kb = tid & 15; } else { kb = (tid >> 6) + 4 * i; n = tid & 63; }
+            sB[buf][kb][n] = rb[i];
+        }
+    };
+
+    float acc[4][4] = {};
+    int buf = 0;
+    if (kbeg < kend) { load(kbeg); store(0); }
+    __syncthreads();
+    for (int k0 = kbeg; k0 < kend; k0 += SBK) {
+        const bool more = (k0 + SBK) < kend;
+        if (more) load(k0 + SBK);
+        #pragma unroll
+        for (int k = 0; k < SBK; k++) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&sA[buf][k][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&sB[buf][k][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+            #pragma unroll
+            for (int i = 0; i < 4; i++)
+                #pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (more) { store(buf ^ 1); }
+        __syncthreads();
+        buf ^= 1;
+    }
+    if (p.splits == 1) {
+        float *O = p.O + zb * p.sO + zc;
+        #pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int gm = m0 + ty * 4 + i;
+            if (gm >= M) continue;
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int gn = n0 + tx * 4 + j;
+                if (gn >= N) continue;
+                const int64_t z = ((int64_t)gm * N + gn) * C;
+                O[z] = (p.beta == 0.0f) ? acc[i][j] * p.alpha : acc[i][j] * p.alpha + O[z] * p.beta;
+            }
+        }
+    } else {
+        float *P = p.part + ((int64_t)(zb * C + zc) * p.splits + zs) * ((int64_t)M * N);
+        #pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int gm = m0 + ty * 4 + i;
+            if (gm >= M) continue;
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int gn = n0 + tx * 4 + j;
+                if (gn < N) P[(int64_t)gm * N + gn] = acc[i][j];
+            }
+        }
+    }
+}
+
+// split-K epilogue: O = alpha * Σ_s part[s] + beta * O   (fixed order → deterministic)
+__global__ void __launch_bounds__(T4K_THREADS) k_splitk_fin(GemmP p, int batch) {
+    const int64_t MN = (int64_t)p.M * p.N, total = MN * p.C * batch;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = t % MN; const int bc = (int)(t / MN); const int b = bc / p.C, c = bc % p.C;
+        const float *P = p.part + (int64_t)bc * p.splits * MN + e;
+        float s = 0.0f;
+        for (int k = 0; k < p.splits; k++) s += P[(int64_t)k * MN];
+        float *o = p.O + b * p.sO + e * p.C + c;
+        *o = (p.beta == 0.0f) ? s * p.alpha : s * p.alpha + *o * p.beta;
+    }
+}
+
+int gemm_simt(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
+              int M, int N, int K, int C, int batch, int64_t sA, int64_t sB, int64_t sO, cudaStream_t st) {
+    GemmP p{A, B, O, alpha, beta, M, N, K, C, sA, sB, sO, 1, K, nullptr};
+    const int gx = (N + SBN - 1) / SBN, gy = (M + SBM - 1) / SBM;
+    const int64_t ctas = (int64_t)gx * gy * C * batch;
+    // split K when the output grid cannot fill the machine and K is deep
+    int splits = 1;
+    const int sms = sm_count();
+    if (ctas < sms && K >= 8 * SBK) {
+        splits = (int)((2 * sms + ctas - 1) / ctas);
+        const int maxs = K / (4 * SBK);
+        if (splits > maxs) splits = maxs;
+        if (splits > 64) splits = 64;
+        if (splits < 1) splits = 1;
+    }
+    if (splits > 1) {
+        int kchunk = (K + splits - 1) / splits;
+        kchunk = (kchunk + SBK - 1) / SBK * SBK;
+        splits = (K + kchunk - 1) / kchunk;
+        p.kchunk = kchunk;
+    }
+    p.splits = splits;
+    if (splits > 1) {
+        p.part = (float*)workspace((size_t)batch * C * splits * M * N * sizeof(float), 0);
+        if (!p.part) return T4K_ENOMEM;
+    }
+    if ((int64_t)C * splits * batch > 65535) return T4K_EINVAL;
+    dim3 g(gx, gy, C * splits * batch);
+    if (K == 0) { p.splits = 1; }
+    if (tA) { if (tB) k_gemm_simt<true, true ><<<g, 256, 0, st>>>(p); else k_gemm_simt<true, false><<<g, 256, 0, st>>>(p); }
+    else    { if (tB) k_gemm_simt<false, true><<<g, 256, 0, st>>>(p); else k_gemm_simt<false, false><<<g, 256, 0, st>>>(p); }
+    int rc = check_launch();
+    if (rc || p.splits == 1) return rc;
+    const int64_t total = (int64_t)M * N * C * batch;
+    k_splitk_fin<<<stream_grid(total), T4K_THREADS, 0, st>>>(p, batch);
+    return check_launch();
+}
+
+} // namespace t4k

@@ -1,0 +1,384 @@
+// gemm_tc.cu — FP32 GEMM on the 5th-gen tensor cores (tcgen05, sm_100a), "3xTF32":
+//     a = a_hi + a_lo   (a_hi = rn_tf32(a), a_lo = rn_tf32(a - a_hi))
+//     A·B ≈ A_hi·B_hi + A_hi·B_lo + A_lo·B_hi        (FP32 accumulate in TMEM)
+//   → relative error per product ~2^-21, i.e. FP32-grade (tensor-core TF32 alone is ~2^-11 and
+//     would violate the 1e-4 parity bar against the reference's FP32-FMA k_gemm_tile_claude,
+//     src/t4math.cu:478-583).
+//
+// Pipeline (one 128 x BN output tile per CTA, optional split-K over gridDim.z):
+//   k_pack_tf32   : op(A) / op(B) (any tA/tB, any strides) → hi/lo planes, K-major, zero padded,
+//                   stored as ready-made 128x32 SWIZZLE_128B shared-memory tile images
+//   k_gemm_tc     : warp 0  — producer: cp.async.bulk (TMA engine, UBLKCP) global→smem, mbarrier tx
+//                   warp 1  — tcgen05.mma issuer (1 elected lane), TMEM alloc/dealloc
+//                   warps 2-5 — epilogue: tcgen05.ld TMEM→regs, alpha/beta, store
+//   k_splitk_fin  : (gemm_simt.cu) deterministic split-K reduction
+// Bound: tensor pipe (3 MMAs per k-step); roofline denominators in DESIGN.md.
+#include "common.cuh"
+
+namespace t4k {
+
+constexpr int TBM = 128;          // tile rows (UMMA M)
+constexpr int TBK = 32;           // k per stage = one 128-byte swizzle row of tf32
+constexpr int UK  = 8;            // UMMA K for tf32 (32 bytes)
+constexpr int PLANE_FLTS = TBM * TBK;            // 4096 floats = 16 KiB per (hi|lo) plane of a packed tile
+constexpr int TILE_FLTS  = 2 * PLANE_FLTS;       // hi + lo
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t cnt) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(cnt));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;"  ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+//  start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major, canonical 1) | SBO>>4 [32,46) = 1024B (8 rows x 128B)
+//  version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
+// A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// ------------------------------------------------------------------ pack: op(X) → tile images
+// X(r,k) = X[r*sr + k*sk]  (r in [0,R) is the M or N index, k in [0,K)); output tile (rt,kt):
+//   P[(rt*KT + kt)*TILE_FLTS + plane*PLANE_FLTS + r*32 + (((k>>2) ^ (r&7))<<2) + (k&3)]
+// i.e. exactly what the UMMA SWIZZLE_128B K-major descriptor expects once bulk-copied to smem.
+__global__ void __launch_bounds__(256) k_pack_tf32(const float *__restrict__ X, float *__restrict__ P,
+                                                   int R, int K, int64_t sr, int64_t sk, int KT) {
+    __shared__ float tile[TBK][TBM + 1];
+    const int rt = blockIdx.y, kt = blockIdx.x;
+    const int r0 = rt * TBM, k0 = kt * TBK;
+    const int tid = threadIdx.x;
+    float *out = P + ((int64_t)rt * KT + kt) * TILE_FLTS;
+    if (sk == 1) {
+        // rows have contiguous k: 8 threads x float4 per row, 32 rows per pass
+        const bool v4 = ((sr & 3) == 0) && ((((uintptr_t)X) & 15) == 0);
+        #pragma unroll
+        for (int pass = 0; pass < 4; pass++) {
+            const int r = pass * 32 + (tid >> 3), c = tid & 7;
+            const int gr = r0 + r, gk = k0 + c * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < R) {
+                const float *src = X + (int64_t)gr * sr + gk;
+                if (v4 && gk + 3 < K) v = ldg4(src);
+                else { if (gk < K) v.x = src[0]; if (gk + 1 < K) v.y = src[1]; if (gk + 2 < K) v.z = src[2]; if (gk + 3 < K) v.w = src[3]; }
+            }
+            float4 hi, lo;
+            hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
+            lo.x = to_tf32(v.x - hi.x); lo.y = to_tf32(v.y - hi.y); lo.z = to_tf32(v.z - hi.z); lo.w = to_tf32(v.w - hi.w);
+            const int o = r * 32 + ((c ^ (r & 7)) << 2);
+            stg4(out + o, hi); stg4(out + PLANE_FLTS + o, lo);
+        }
+    } else {
+        // contiguous (or strided) r: read coalesced along r into smem, then emit k-chunks
+        #pragma unroll
+        for (int pass = 0; pass < 16; pass++) {
+            const int k = pass * 2 + (tid >> 7), r = tid & 127;
+            const int gr = r0 + r, gk = k0 + k;
+            tile[k][r] = (gr < R && gk < K) ? __ldg(X + (int64_t)gr * sr + (int64_t)gk * sk) : 0.0f;
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int pass = 0; pass < 4; pass++) {
+            const int r = pass * 32 + (tid >> 3), c = tid & 7;
+            float4 v = make_float4(tile[c * 4][r], tile[c * 4 + 1][r], tile[c * 4 + 2][r], tile[c * 4 + 3][r]);
+            float4 hi, lo;
+            hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
+            lo.x = to_tf32(v.x - hi.x); lo.y = to_tf32(v.y - hi.y); lo.z = to_tf32(v.z - hi.z); lo.w = to_tf32(v.w - hi.w);
+            const int o = r * 32 + ((c ^ (r & 7)) << 2);
+            stg4(out + o, hi); stg4(out + PLANE_FLTS + o, lo);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ the tensor-core kernel
+struct TcP {
+    const float *PA, *PB;        // packed planes
+    float *O;                    // output [M,N] row-major (C==1) or split-K partials
+    float alpha, beta;
+    int M, N;
+    int KT;                      // number of 32-wide k blocks (padded K / 32)
+    int kt_per_split;            // k blocks per gridDim.z slice
+    int splits;
+    float *part;                 // partials [splits][M*N] when splits > 1
+};
+
+template<int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1) k_gemm_tc(TcP p) {
+    constexpr uint32_t A_BYTES = TILE_FLTS * 4;                  // 32 KiB (hi+lo)
+    constexpr uint32_t B_BYTES = (BN / TBM) * TILE_FLTS * 4;     // 32 or 64 KiB
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t PLANE_B = PLANE_FLTS * 4;                 // 16 KiB
+    constexpr uint32_t B_PLANE_B = (BN / TBM) * PLANE_B;         // bytes of the B hi (or lo) plane in smem
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte aligned tiles
+    uint8_t *smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);   // full[STAGES], empty[STAGES], tmem_full
+    uint32_t *tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.y, nt = blockIdx.x, zs = blockIdx.z;
+    const int kt0 = zs * p.kt_per_split;
+    const int kt1 = min(p.KT, kt0 + p.kt_per_split);
+    const int nkb = kt1 - kt0;
+
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                    // TMEM: BN fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer: bulk async copies (TMA engine) of ready-made tile images =====
+        if (lane == 0) {
+            for (int i = 0; i < nkb; i++) {
+                const int s = i % STAGES, it = i / STAGES;
+                mbar_wait(empty0 + 8 * s, (it & 1) ^ 1);
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t sb = sa + A_BYTES;
+                mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+                const int kt = kt0 + i;
+                bulk_g2s(sa, p.PA + ((int64_t)mt * p.KT + kt) * TILE_FLTS, A_BYTES, full0 + 8 * s);
+                #pragma unroll
+                for (int j = 0; j < BN / TBM; j++) {
+                    const float *src = p.PB + ((int64_t)(nt * (BN / TBM) + j) * p.KT + kt) * TILE_FLTS;
+                    bulk_g2s(sb + j * PLANE_B,             src,              PLANE_B, full0 + 8 * s);   // hi rows [128j,128j+128)
+                    bulk_g2s(sb + B_PLANE_B + j * PLANE_B, src + PLANE_FLTS, PLANE_B, full0 + 8 * s);   // lo
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = idesc_tf32(TBM, BN);
+        for (int i = 0; i < nkb; i++) {
+            const int s = i % STAGES, it = i / STAGES;
+            mbar_wait(full0 + 8 * s, it & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint32_t sb = sa + A_BYTES;
+                const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + PLANE_B);
+                const uint64_t b_hi = smem_desc_sw128(sb), b_lo = smem_desc_sw128(sb + B_PLANE_B);
+                #pragma unroll
+                for (int k = 0; k < TBK / UK; k++) {
+                    const uint64_t ko = (uint64_t)((k * UK * 4) >> 4);      // advance start address inside the swizzle row
+                    tc_mma_tf32(tmem_base, a_lo + ko, b_hi + ko, idesc, (i | k) ? 1u : 0u);
+                    tc_mma_tf32(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
+                    tc_mma_tf32(tmem_base, a_hi + ko, b_hi + ko, idesc, 1u);
+                }
+            }
+            __syncwarp();
+            if (elect_one()) {
+                tc_commit(empty0 + 8 * s);                   // frees the smem stage when the MMAs above retire
+                if (i == nkb - 1) tc_commit(tfull);          // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        const int q = warp & 3;
+        const int row = mt * TBM + q * 32 + lane;
+        float *dst; float alpha = p.alpha, beta = p.beta;
+        if (p.splits > 1) { dst = p.part + (int64_t)zs * p.M * p.N; alpha = 1.0f; beta = 0.0f; }
+        else dst = p.O;
+        if (nkb > 0) { mbar_wait(tfull, 0); tc_fence_after(); }
+        const bool n_vec = ((p.N & 3) == 0) && ((((uintptr_t)dst) & 15) == 0);
+        #pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            if (nkb > 0) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+                #pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = 0u;
+            }
+            const int col0 = nt * BN + c0;
+            if (row < p.M && col0 < p.N) {
+                float *o = dst + (int64_t)row * p.N + col0;
+                if (n_vec && col0 + 32 <= p.N) {
+                    #pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 r = make_float4(__uint_as_float(v[j]) * alpha, __uint_as_float(v[j + 1]) * alpha,
+                                               __uint_as_float(v[j + 2]) * alpha, __uint_as_float(v[j + 3]) * alpha);
+                        if (beta != 0.0f) {
+                            const float4 old = *reinterpret_cast<const float4*>(o + j);
+                            r.x += old.x * beta; r.y += old.y * beta; r.z += old.z * beta; r.w += old.w * beta;
+                        }
+                        stg4(o + j, r);
+                    }
+                } else {
+                    #pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        if (col0 + j < p.N) {
+                            float r = __uint_as_float(v[j]) * alpha;
+                            if (beta != 0.0f) r += o[j] * beta;
+                            o[j] = r;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)BN));
+    }
+}
+
+int gemm_simt(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
+              int M, int N, int K, int C, int batch, int64_t sA, int64_t sB, int64_t sO, cudaStream_t st);
+__global__ void k_splitk_fin_tc(const float *part, float *O, float alpha, float beta, int64_t MN, int splits);
+
+__global__ void __launch_bounds__(T4K_THREADS) k_splitk_fin_tc(const float *__restrict__ part, float *O,
+                                                               float alpha, float beta, int64_t MN, int splits) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < MN; e += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.0f;
+        for (int k = 0; k < splits; k++) s += part[(int64_t)k * MN + e];
+        O[e] = (beta == 0.0f) ? s * alpha : s * alpha + O[e] * beta;
+    }
+}
+
+template<int BN, int STAGES> static int launch_tc(const TcP &p, dim3 grid, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * ((size_t)TILE_FLTS * 4 + (size_t)(BN / TBM) * TILE_FLTS * 4) + 1024 + 256;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    k_gemm_tc<BN, STAGES><<<grid, 192, smem, st>>>(p);
+    return check_launch();
+}
+
+// C == 1, single matrix (the caller loops the batch).  Returns T4K_EINVAL if the shape is not
+// worth / not eligible for the tensor path (caller falls back to the SIMT engine).
+int gemm_tc(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
+            int M, int N, int K, cudaStream_t st) {
+    if (M < 1 || N < 1 || K < 1) return T4K_EINVAL;
+    const int MT = (M + TBM - 1) / TBM, KT = (K + TBK - 1) / TBK;
+    const int BN = (N > 128) ? 256 : 128;
+    const int NT128 = (N + BN - 1) / BN * (BN / TBM);           // 128-row packed tiles of B
+    const size_t a_flts = (size_t)MT * KT * TILE_FLTS, b_flts = (size_t)NT128 * KT * TILE_FLTS;
+    float *PA = (float*)workspace(a_flts * 4, 1);
+    float *PB = (float*)workspace(b_flts * 4, 2);
+    if (!PA || !PB) return T4K_ENOMEM;
+    // pack op(A): rows = M index, k = K index
+    {
+        const int64_t sr = tA ? 1 : K, sk = tA ? M : 1;
+        k_pack_tf32<<<dim3(KT, MT), 256, 0, st>>>(A, PA, M, K, sr, sk, KT);
+        int rc = check_launch(); if (rc) return rc;
+    }
+    {   // pack op(B)^T: rows = N index, k = K index;  B normal is [K,N] → sr=1, sk=N;  B^T stored [N,K] → sr=K, sk=1
+        const int64_t sr = tB ? K : 1, sk = tB ? 1 : N;
+        k_pack_tf32<<<dim3(KT, NT128), 256, 0, st>>>(B, PB, N, K, sr, sk, KT);
+        int rc = check_launch(); if (rc) return rc;
+    }
+    const int gx = (N + BN - 1) / BN, gy = MT;
+    int splits = 1;
+    const int sms = sm_count();
+    if (gx * gy < sms && KT >= 8) {
+        splits = (sms + gx * gy - 1) / (gx * gy);
+        if (splits > KT / 4) splits = KT / 4;
+        if (splits > 32) splits = 32;
+        if (splits < 1) splits = 1;
+    }
+    int kt_per = (KT + splits - 1) / splits;
+    splits = (KT + kt_per - 1) / kt_per;
+    TcP p{PA, PB, O, alpha, beta, M, N, KT, kt_per, splits, nullptr};
+    if (splits > 1) {
+        p.part = (float*)workspace((size_t)splits * M * N * 4, 3);
+        if (!p.part) return T4K_ENOMEM;
+    }
+    dim3 grid(gx, gy, splits);
+    int rc = (BN == 256) ? launch_tc<256, 2>(p, grid, st) : launch_tc<128, 3>(p, grid, st);
+    if (rc || splits == 1) return rc;
+    const int64_t MN = (int64_t)M * N;
+    k_splitk_fin_tc<<<stream_grid(MN), T4K_THREADS, 0, st>>>(p.part, O, alpha, beta, MN, splits);
+    return check_launch();
+}
+
+} // namespace t4k
+using namespace t4k;
+
+// ====================================================================== C ABI
+extern "C" int t4k_gemm_ex(int engine, const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
+                           int M, int N, int K, int C, int batch, int64_t sA, int64_t sB, int64_t sO, t4k_stream_t s) {
+    if (!A || !B || !O || M < 1 || N < 1 || K < 0 || C < 1 || batch < 1) return T4K_EINVAL;
+    bool tc = false;
+    if (engine == T4K_GEMM_TC) { if (C != 1 || K < 1) return T4K_EINVAL; tc = true; }
+    else if (engine == T4K_GEMM_AUTO) {
+        // tensor path pays two pack passes + a 128-wide tile: take it when there is real math
+        tc = (C == 1) && K >= 64 && (double)M * N * K >= 2.0e8 && M >= 64 && N >= 32;
+    }
+    for (int b = 0; tc && b < batch; b++) {
+        int rc = gemm_tc(A + b * sA, B + b * sB, O + b * sO, alpha, beta, tA, tB, M, N, K, STRM(s));
+        if (rc) return rc;
+    }
+    if (tc) return 0;
+    return gemm_simt(A, B, O, alpha, beta, tA, tB, M, N, K, C, batch, sA, sB, sO, STRM(s));
+}
+extern "C" int t4k_gemm(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
+                        int M, int N, int K, int C, int batch, int64_t sA, int64_t sB, int64_t sO, t4k_stream_t s) {
+    return t4k_gemm_ex(T4K_GEMM_AUTO, A, B, O, alpha, beta, tA, tB, M, N, K, C, batch, sA, sB, sO, s);
+}

@@ -1,0 +1,65 @@
+// rand.cu — counter-based RNG (Philox4x32-10), full-grid
+//   replaces k_rand_init / k_rand (src/util.cu:46-70: 1024 XORWOW states in ONE block, serial over
+//   pages) behind System::rand (src/sys.cpp:77-95).  d[i] = scale * (bias + x),
+//   x ~ U(0,1] (curand_uniform convention) or N(0,1) (Box-Muller).
+// Element i depends only on (seed, offset + i): independent of grid size and of how a tensor is
+// sharded across GPUs.  Bit parity with the reference is undefined (it seeds with time()).
+#include "common.cuh"
+
+namespace t4k {
+
+static uint64_t g_seed = 0x243F6A8885A308D3ull, g_offset = 0;
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    #pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)x * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }  // (0,1]
+
+__global__ void __launch_bounds__(T4K_THREADS)
+k_rand(float *d, int64_t n, int opt, float bias, float scale, uint64_t seed, uint64_t offset) {
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const int64_t nq = (n + 3) >> 2;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        // counter = absolute quad index; unaligned offsets are handled by drawing per element below
+        float r[4];
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint64_t e = offset + (uint64_t)(4 * q + k);
+            const uint4 x = philox4x32_10(make_uint4((uint32_t)(e >> 2), (uint32_t)(e >> 34), 0u, 0u), key);
+            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+            if (opt == T4K_NORMAL) {
+                // Box-Muller on the pair (2*(e&1)) of this counter's 4 words: element parity picks cos/sin
+                const uint32_t a = w[(e & 2)], b = w[(e & 2) + 1];
+                const float u1 = u01(a), u2 = u01(b);
+                const float m = sqrtf(-2.0f * logf(u1));
+                r[k] = (e & 1) ? m * sinf(6.2831853071795865f * u2) : m * cosf(6.2831853071795865f * u2);
+            } else {
+                r[k] = u01(w[e & 3]);
+            }
+        }
+        #pragma unroll
+        for (int k = 0; k < 4; k++) { const int64_t i = 4 * q + k; if (i < n) d[i] = scale * (bias + r[k]); }
+    }
+}
+} // namespace t4k
+using namespace t4k;
+
+extern "C" int t4k_rand_seed(uint64_t seed) { g_seed = seed; g_offset = 0; return 0; }
+extern "C" int t4k_rand_at(float *d, int64_t n, int opt, float bias, float scale, uint64_t seed, uint64_t offset, t4k_stream_t s) {
+    if (!d || n < 0 || (opt != T4K_UNIFORM && opt != T4K_NORMAL)) return T4K_EINVAL;
+    if (n == 0) return 0;
+    k_rand<<<stream_grid((n + 3) / 4), T4K_THREADS, 0, STRM(s)>>>(d, n, opt, bias, scale, seed, offset);
+    return check_launch();
+}
+extern "C" int t4k_rand(float *d, int64_t n, int opt, float bias, float scale, t4k_stream_t s) {
+    int rc = t4k_rand_at(d, n, opt, bias, scale, g_seed, g_offset, s);
+    g_offset += (uint64_t)((n + 3) & ~3ll);        // successive calls draw disjoint counters
+    return rc;
+}

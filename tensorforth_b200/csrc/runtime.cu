@@ -1,0 +1,105 @@
+// runtime.cu — library state: device attributes, workspace, launch accounting, error strings
+#include "common.cuh"
+#include <mutex>
+#include <cstdio>
+
+namespace t4k {
+
+long g_launches = 0;
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = 0;
+            return T4K_SMS;
+        }
+    }
+    return n;
+}
+
+int check_launch() {
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    return (int)e;
+}
+
+// Library-owned scratch, one growing buffer per (device, slot).  Ownership rule of the boundary
+// (SURVEY.md §8b): user-visible tensors belong to the caller's arena, workspace lives here.
+// Regrowth frees the old block with cudaFree (implicit device sync) — only happens when a
+// larger problem than ever before arrives.
+#define MAX_DEV  16
+#define MAX_SLOT 8
+static void  *g_ws[MAX_DEV][MAX_SLOT];
+static size_t g_ws_sz[MAX_DEV][MAX_SLOT];
+static std::mutex g_mu;
+
+void *workspace(size_t bytes, int slot) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= MAX_DEV || slot >= MAX_SLOT) return nullptr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ws_sz[dev][slot] < bytes) {
+        if (g_ws[dev][slot]) cudaFree(g_ws[dev][slot]);
+        size_t want = bytes + (bytes >> 2);
+        want = (want + 255) & ~(size_t)255;
+        void *p = nullptr;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); g_ws[dev][slot] = nullptr; g_ws_sz[dev][slot] = 0; return nullptr; }
+        g_ws[dev][slot] = p; g_ws_sz[dev][slot] = want;
+    }
+    return g_ws[dev][slot];
+}
+
+// Reduction scratch: ring of 64 slots x (1024 partial floats + 8 control words), control words
+// are zero on entry and re-zeroed by the finishing block, so no memset per call.
+#define RSLOTS      64
+#define RSLOT_FLTS  (2048 + 8)
+static float *g_red[MAX_DEV];
+static unsigned g_red_next[MAX_DEV];
+
+float *reduce_slot(cudaStream_t) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= MAX_DEV) return nullptr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_red[dev]) {
+        void *p = nullptr;
+        size_t sz = (size_t)RSLOTS * RSLOT_FLTS * sizeof(float);
+        if (cudaMalloc(&p, sz) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        cudaMemset(p, 0, sz);
+        g_red[dev] = (float*)p;
+    }
+    unsigned k = g_red_next[dev]++ % RSLOTS;
+    return g_red[dev] + (size_t)k * RSLOT_FLTS;
+}
+
+} // namespace t4k
+
+extern "C" {
+
+int t4k_version(void) { return T4K_VERSION; }
+
+const char *t4k_strerror(int rc) {
+    switch (rc) {
+    case 0:          return "ok";
+    case T4K_EINVAL: return "t4k: invalid argument / unsupported shape";
+    case T4K_ENOSUP: return "t4k: configuration not supported (as in the reference)";
+    case T4K_ENOMEM: return "t4k: workspace allocation failed";
+    default:         return rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "t4k: unknown error";
+    }
+}
+
+int t4k_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int t4k_sm_count(void) { return t4k::sm_count(); }
+
+int t4k_sync(t4k_stream_t s) { return (int)cudaStreamSynchronize((cudaStream_t)s); }
+
+long t4k_launch_count(void) { return t4k::g_launches; }
+
+} // extern "C"

@@ -1,0 +1,437 @@
+"""
+-m gpu parity tests: every entry point of include/t4k.h, called through the C-ABI on cuda:0,
+against the CPU oracle (oracle/) on the same seeded inputs.  Bar (north star): bit-exact for
+index / reshape / routing work, <= 1e-4 relative for FP32 math (tolerance written per test).
+Edge cases follow the reference's own: ragged (non tile-multiple) sizes, n == 0, N-broadcast,
+unaligned slices, the four conv (K,S,P) configs, pool K in {2,3}, ties in max-pool routing.
+"""
+import ctypes as C
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tensorforth_b200 import lib as t4
+from gpu_util import lib, dev, zeros, ptr, host, ok, assert_close, assert_exact
+
+pytestmark = pytest.mark.gpu
+RNG = np.random.default_rng(1234)
+
+
+def rnd(*shape, lo=-1.0, hi=1.0):
+    return (RNG.random(shape, dtype=np.float32) * (hi - lo) + lo).astype(np.float32)
+
+
+# ------------------------------------------------------------------ elementwise
+MAP_OPS = [(t4.ABS, 0), (t4.NEG, 0), (t4.EXP, 0), (t4.LN, 0), (t4.LOG, 0), (t4.TANH, 0), (t4.RELU, 0),
+           (t4.SIGM, 0), (t4.SQRT, 0), (t4.RCP, 0), (t4.SAT, 0), (t4.FILL, 3.25), (t4.GFILL, 2.0),
+           (t4.SCALE, 1.5), (t4.POW, 2.5), (t4.ADD, 0.75), (t4.SUB, 0.75), (t4.MUL, -3.0), (t4.DIV, 7.0)]
+
+
+@pytest.mark.parametrize("op,v", MAP_OPS)
+@pytest.mark.parametrize("n,off", [(1, 0), (1027, 0), (4096, 1), (300001, 0)])
+def test_map(op, v, n, off):
+    a = rnd(n + off, lo=-2, hi=2)
+    if op in (t4.POW, t4.RCP):
+        a = np.abs(a) + 0.1
+    d = dev(a)
+    ok(lib().t4k_map(op, ptr(d, off), v, n, None))
+    ref = orc.map_(op, a[off:], v)
+    got = host(d)[off:]
+    if op in (t4.ABS, t4.NEG, t4.RELU, t4.SAT, t4.FILL, t4.SCALE, t4.ADD, t4.SUB, t4.MUL, t4.DIV, t4.SQRT, t4.RCP):
+        assert_exact(got, ref, "map %d" % op)           # IEEE ops: bit exact
+    else:
+        assert_close(got, ref, rtol=1e-5, atol=1e-6, what="map %d" % op)   # __expf/__logf/__powf vs libm
+    if off:
+        assert host(d)[0] == a[0]                        # neighbours untouched
+
+
+def test_map_empty_and_bad():
+    d = zeros(4)
+    assert lib().t4k_map(t4.ABS, ptr(d), 0.0, 0, None) == 0
+    assert lib().t4k_map(t4.IDEN, ptr(d), 0.0, 4, None) != 0      # not a k_math op (t4math.cu:199)
+    assert lib().t4k_map(t4.ABS, None, 0.0, 4, None) != 0
+
+
+@pytest.mark.parametrize("op", [t4.ADD, t4.SUB, t4.MUL, t4.DIV])
+def test_ts_tt_ops(op):
+    a, b = rnd(5, 333), rnd(5, 333, lo=0.5, hi=2)
+    da, db, do = dev(a), dev(b), zeros(5, 333)
+    ok(lib().t4k_ts_op(op, ptr(da), 1.7, ptr(do), a.size, None))
+    assert_exact(host(do), orc.ts_op(op, a, 1.7))
+    ok(lib().t4k_tt_op(op, ptr(da), ptr(db), ptr(do), 333, 5, 5, None))
+    assert_exact(host(do), orc.tt_op(op, a, b))
+    # N-broadcast of B (tensor.cu:39-46) and of A
+    b1 = b[:1]
+    ok(lib().t4k_tt_op(op, ptr(da), ptr(dev(b1)), ptr(do), 333, 5, 1, None))
+    assert_exact(host(do), orc.tt_op(op, a, b1.reshape(333)))
+    ok(lib().t4k_tt_op(op, ptr(dev(b1)), ptr(da), ptr(do), 333, 1, 5, None))
+    assert_exact(host(do), orc.tt_op(op, b1.reshape(333), a))
+    # vectorised broadcast path (hwc % 4 == 0)
+    a4, b4 = rnd(3, 64), rnd(1, 64, lo=0.5, hi=2)
+    o4 = zeros(3, 64)
+    ok(lib().t4k_tt_op(op, ptr(dev(a4)), ptr(dev(b4)), ptr(o4), 64, 3, 1, None))
+    assert_exact(host(o4), orc.tt_op(op, a4, b4.reshape(64)))
+    assert lib().t4k_tt_op(op, ptr(da), ptr(db), ptr(do), 333, 5, 2, None) != 0     # N mismatch (tensor.cu:35-38)
+
+
+@pytest.mark.parametrize("n,off", [(0, 0), (3, 0), (1 << 20, 0), (77777, 3)])
+def test_copy(n, off):
+    a = rnd(n + off + 8)
+    d, o = dev(a), zeros(n + off + 8)
+    ok(lib().t4k_copy(ptr(d, off), ptr(o, off), n, None))
+    assert_exact(host(o)[off:off + n], a[off:off + n])
+    assert not host(o)[off + n:].any()
+
+
+@pytest.mark.parametrize("N,H,W,Cc", [(1, 2, 3, 1), (2, 70, 33, 1), (1, 512, 1024, 1), (2, 5, 7, 3)])
+def test_transpose_identity(N, H, W, Cc):
+    a = rnd(N, H, W, Cc)
+    o = zeros(N, W, H, Cc)
+    ok(lib().t4k_transpose(ptr(dev(a)), ptr(o), N, H, W, Cc, None))
+    ref = np.stack([orc.transpose(a[n], Cc) for n in range(N)])
+    assert_exact(host(o), ref)
+    e = zeros(N, H, W, Cc)
+    ok(lib().t4k_identity(ptr(e), N, H, W, Cc, None))
+    assert_exact(host(e), np.stack([orc.identity(H, W, Cc) for _ in range(N)]))
+
+
+# ------------------------------------------------------------------ reductions / losses
+@pytest.mark.parametrize("n,off", [(1, 0), (15, 0), (1000, 1), (1 << 22, 0)])
+def test_reductions(n, off):
+    a = rnd(n + off)
+    d, out = dev(a), zeros(4)
+    x = a[off:]
+    ok(lib().t4k_sum(ptr(d, off), n, ptr(out), None))
+    assert_close(host(out)[0], orc.tsum(x), rtol=1e-5, atol=1e-5 * np.sqrt(n))
+    ok(lib().t4k_nvar(ptr(d, off), 0.25, n, ptr(out), None))
+    assert_close(host(out)[0], float(orc.lib().orc_nvar(orc._p(orc.f32(x)), 0.25, n)), rtol=1e-5)
+    ok(lib().t4k_minmax(ptr(d, off), n, 1, ptr(out), None))
+    assert host(out)[0] == orc.tmax(x)
+    ok(lib().t4k_minmax(ptr(d, off), n, 0, ptr(out), None))
+    assert host(out)[0] == orc.tmin(x)
+    ok(lib().t4k_avg_std(ptr(d, off), n, ptr(out), None))
+    assert_close(host(out)[0], orc.avg(x), rtol=1e-4, atol=1e-6)
+    assert_close(host(out)[1], orc.std(x), rtol=1e-4, atol=1e-9)       # reference's std = sqrt(Σ(x-μ)²)/n
+    # repeatability: no float atomics → identical bits run to run
+    ok(lib().t4k_sum(ptr(d, off), n, ptr(out), None)); s1 = host(out)[0].copy()
+    ok(lib().t4k_sum(ptr(d, off), n, ptr(out), None)); s2 = host(out)[0].copy()
+    assert s1.tobytes() == s2.tobytes()
+
+
+def test_dot():
+    K, Cc, N = 1000, 3, 4
+    a, b = rnd(N, K, Cc), rnd(N, K, Cc)
+    o0 = rnd(N, Cc)
+    o = dev(o0)
+    ok(lib().t4k_dot(ptr(dev(a)), ptr(dev(b)), ptr(o), 0.5, 2.0, K, Cc, N, N, None))
+    ref = np.stack([orc.dot(a[n], b[n], o0[n], 0.5, 2.0, Cc) for n in range(N)])
+    assert_close(host(o), ref, rtol=1e-5)
+    v1, v2 = rnd(100003), rnd(100003)
+    o = dev(np.array([3.0], np.float32))
+    ok(lib().t4k_dot(ptr(dev(v1)), ptr(dev(v2)), ptr(o), 1.0, 0.0, v1.size, 1, 1, 1, None))
+    assert_close(host(o)[0], np.dot(v1.astype(np.float64), v2.astype(np.float64)), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("kind", [t4.LOSS_MSE, t4.LOSS_BCE, t4.LOSS_CE, t4.LOSS_NLL])
+@pytest.mark.parametrize("N,E", [(1, 2), (3, 2), (512, 10), (1024, 1)])
+def test_loss(kind, N, E):
+    out = rnd(N, E, lo=0.01, hi=0.99)
+    tgt = orc.onehot(RNG.integers(0, E, N), E) if kind != t4.LOSS_MSE else rnd(N, E)
+    do = dev(out)
+    l = zeros(1)
+    ok(lib().t4k_loss(kind, ptr(do), ptr(dev(tgt)), out.size, N, ptr(l), None))
+    assert_close(host(l)[0], orc.loss(kind, out, tgt, N), rtol=1e-5, atol=1e-6)
+    assert_exact(host(do), out)                          # non-destructive (works on no copy at all)
+
+
+def test_nan_inf():
+    a = rnd(100000)
+    a[[5, 77, 9999]] = [np.nan, np.inf, -np.inf]
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ok(lib().t4k_nan_inf(ptr(dev(a)), a.size, C.c_void_p(cnt.data_ptr()), None))
+    assert int(cnt.cpu()[0]) == 3
+
+
+# ------------------------------------------------------------------ GEMM
+def gemm_ref64(A, B, O, alpha, beta, tA, tB):
+    a = A.astype(np.float64).T if tA else A.astype(np.float64)
+    b = B.astype(np.float64).T if tB else B.astype(np.float64)
+    return alpha * (a @ b) + beta * O.astype(np.float64)
+
+
+@pytest.mark.parametrize("engine", [t4.GEMM_SIMT, t4.GEMM_TC])
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(2, 2, 3), (64, 64, 64), (128, 128, 32), (200, 100, 70), (130, 260, 513), (512, 100, 1960)])
+def test_gemm_engines(engine, tA, tB, M, N, K):
+    A = rnd(K, M) if tA else rnd(M, K)
+    B = rnd(N, K) if tB else rnd(K, N)
+    O0 = rnd(M, N)
+    o = dev(O0)
+    ok(lib().t4k_gemm_ex(engine, ptr(dev(A)), ptr(dev(B)), ptr(o), 0.5, 2.0, tA, tB, M, N, K, 1, 1, 0, 0, 0, None), "gemm")
+    got = host(o)
+    ref = orc.gemm(A, B, O0, 0.5, 2.0, bool(tA), bool(tB), M, N, K, 1)      # oracle: FP32 FMA, k ascending (t4math.cu:554-564)
+    assert_close(got, ref, rtol=1e-4, what="gemm vs oracle")                 # the north-star bar
+    assert_close(got, gemm_ref64(A, B, O0, 0.5, 2.0, tA, tB), rtol=2e-5, what="gemm vs f64")   # and FP32-grade vs exact
+
+
+def test_gemm_beta0_ignores_garbage():
+    M = N = K = 96
+    A, B = rnd(M, K), rnd(K, N)
+    for eng in (t4.GEMM_SIMT, t4.GEMM_TC):
+        o = dev(np.full((M, N), np.nan, np.float32))
+        ok(lib().t4k_gemm_ex(eng, ptr(dev(A)), ptr(dev(B)), ptr(o), 1.0, 0.0, 0, 0, M, N, K, 1, 1, 0, 0, 0, None))
+        assert_close(host(o), gemm_ref64(A, B, np.zeros((M, N)), 1, 0, 0, 0), rtol=2e-5)
+
+
+def test_gemm_channels_and_batch_broadcast():
+    # rank-4 `@`: per-channel, per-sample GEMM with channel stride C; N-broadcast of B (tensor.cu:162-180)
+    Nb, M, N, K, Cc = 3, 20, 17, 33, 2
+    A, B = rnd(Nb, M, K, Cc), rnd(1, K, N, Cc)
+    o = zeros(Nb, M, N, Cc)
+    ok(lib().t4k_gemm(ptr(dev(A)), ptr(dev(B)), ptr(o), 1.0, 0.0, 0, 0, M, N, K, Cc, Nb, M * K * Cc, 0, M * N * Cc, None))
+    ref = np.stack([orc.gemm(A[n], B[0], None, 1.0, 0.0, False, False, M, N, K, Cc) for n in range(Nb)])
+    assert_close(host(o), ref, rtol=1e-5)
+
+
+def test_gemm_tc_large_vs_f64():
+    # 1024^3 on the tcgen05 engine vs exact (float64) product; zero-mean data is the hard case for TF32
+    M = N = K = 1024
+    A, B = rnd(M, K), rnd(K, N)
+    o = zeros(M, N)
+    ok(lib().t4k_gemm_ex(t4.GEMM_TC, ptr(dev(A)), ptr(dev(B)), ptr(o), 1.0, 0.0, 0, 0, M, N, K, 1, 1, 0, 0, 0, None))
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    got = host(o)
+    assert_close(got, ref, rtol=1e-5, what="3xTF32 1024^3")
+    rel = np.abs(got - ref).max() / np.abs(ref).max()
+    assert rel < 2e-6, rel                                # FP32-grade: plain TF32 would be ~5e-4
+
+
+def test_gemm_4096_property():
+    # BASELINE size (config 2): size-independent checks — linearity in alpha and the row-sum identity
+    # (A@B)·1 = A·(B·1), evaluated in float64 on the host in O(n^2).
+    n = 4096
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A = torch.rand(n, n, device="cuda", generator=g) * 2 - 1
+    B = torch.rand(n, n, device="cuda", generator=g) * 2 - 1
+    o1, o2 = zeros(n, n), zeros(n, n)
+    ok(lib().t4k_gemm(ptr(A), ptr(B), ptr(o1), 1.0, 0.0, 0, 0, n, n, n, 1, 1, 0, 0, 0, None))
+    ok(lib().t4k_gemm(ptr(A), ptr(B), ptr(o2), 2.0, 0.0, 0, 0, n, n, n, 1, 1, 0, 0, 0, None))
+    assert torch.equal(o2, 2 * o1)                        # exact: scaling by 2 commutes with rounding
+    rs = o1.double().sum(1).cpu().numpy()
+    ref = (A.double() @ B.double().sum(1)).cpu().numpy()
+    assert_close(rs, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+    # spot-check 64 full rows against float64
+    idx = torch.arange(0, n, 64, device="cuda")
+    ref_rows = (A[idx].double() @ B.double()).cpu().numpy()
+    assert_close(o1[idx].cpu().numpy(), ref_rows, rtol=1e-5, what="4096 rows")
+
+
+# ------------------------------------------------------------------ linear / activation / softmax
+@pytest.mark.parametrize("N,E0,E1", [(1, 3, 2), (3, 2, 2), (512, 100, 1960), (512, 10, 100), (1024, 512, 784)])
+def test_linear_fwd_bwd(N, E0, E1):
+    X, W, Bv, dY = rnd(N, E1), rnd(E0, E1), rnd(E0), rnd(N, E0)
+    y = zeros(N, E0)
+    ok(lib().t4k_linear_fwd(ptr(dev(X)), ptr(dev(W)), ptr(dev(Bv)), ptr(y), N, E0, E1, None))
+    ref = orc.gemm(X, W, tB=True); orc.lib().orc_bias(orc._p(Bv), orc._p(ref), N, E0)
+    assert_close(host(y), ref, rtol=1e-4, what="linear fwd")
+    dW0, dB0 = rnd(E0, E1), rnd(E0)
+    dx, dw, db = zeros(N, E1), dev(dW0), dev(dB0)
+    ok(lib().t4k_linear_bwd(ptr(dev(X)), ptr(dev(W)), ptr(dev(dY)), ptr(dx), ptr(dw), ptr(db), N, E0, E1, 1, None))
+    rdb = dB0.copy(); orc.lib().orc_dlinear_db(orc._p(dY), orc._p(rdb), N, E0)
+    assert_close(host(db), rdb, rtol=1e-4, what="dB")
+    assert_close(host(dw), orc.gemm(dY, X, O=dW0, alpha=1.0, beta=1.0, tA=True), rtol=1e-4, what="dW")
+    assert_close(host(dx), orc.gemm(dY, W), rtol=1e-4, what="dX")
+    # train == 0: parameters' gradients untouched
+    dw2, db2 = dev(dW0), dev(dB0)
+    ok(lib().t4k_linear_bwd(ptr(dev(X)), ptr(dev(W)), ptr(dev(dY)), ptr(dx), ptr(dw2), ptr(db2), N, E0, E1, 0, None))
+    assert_exact(host(dw2), dW0); assert_exact(host(db2), dB0)
+
+
+ACTS = [(t4.L_RELU, 0.0), (t4.L_TANH, 0.0), (t4.L_SIGMOID, 0.0), (t4.L_SELU, 0.0), (t4.L_LEAKYRL, 0.2),
+        (t4.L_ELU, 1.0), (t4.L_DROPOUT, 0.3)]
+
+
+@pytest.mark.parametrize("layer,alpha", ACTS)
+@pytest.mark.parametrize("n", [7, 4096, 100352])
+def test_activate(layer, alpha, n):
+    x = rnd(n, lo=-3, hi=3)
+    x[:3] = [0.0, -0.0, 1e-30]
+    u = RNG.random(n, dtype=np.float32)
+    o, f = zeros(n), dev(u)
+    ok(lib().t4k_activate_fwd(layer, ptr(dev(x)), ptr(o), ptr(f), alpha, n, None))
+    ro, rf = orc.activate(layer, x, alpha, mask=u)
+    if layer in (t4.L_RELU, t4.L_LEAKYRL, t4.L_DROPOUT):
+        assert_exact(host(o), ro); assert_exact(host(f), rf)               # routing / mask: bit exact
+    else:
+        assert_close(host(o), ro, rtol=1e-5, atol=1e-6); assert_close(host(f), rf, rtol=1e-5, atol=1e-6)
+    dy, dx = rnd(n), zeros(n)
+    ok(lib().t4k_activate_bwd(ptr(dev(dy)), ptr(f), ptr(dx), n, None))
+    assert_exact(host(dx), orc.tt_op(orc.MUL, dy, host(f)))
+
+
+@pytest.mark.parametrize("N,Cc", [(1, 2), (512, 10), (33, 300), (4, 1000)])
+def test_softmax_logsoftmax(N, Cc):
+    x = rnd(N, Cc, lo=-4, hi=4)
+    o = zeros(N, Cc)
+    ok(lib().t4k_softmax_fwd(ptr(dev(x)), ptr(o), N, Cc, None))
+    assert_close(host(o), orc.softmax(x, N), rtol=1e-5, atol=1e-7)
+    ok(lib().t4k_logsoftmax_fwd(ptr(dev(x)), ptr(o), N, Cc, None))
+    assert_close(host(o), orc.logsoftmax(x, N), rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------ conv / pool / batchnorm
+CONV_CASES = [  # N,H,W,C1,C0,K,S,P
+    (2, 16, 16, 1, 2, 3, 1, 1),          # t4_30d.4th toy CNN, small-channel path
+    (4, 28, 28, 1, 10, 3, 1, 1),         # MNIST first layer (config 3)
+    (3, 12, 12, 3, 5, 5, 1, 2),
+    (2, 9, 9, 2, 4, 1, 1, 0),
+    (2, 14, 14, 2, 6, 4, 2, 1),          # the 4x4 stride-2 config
+    (2, 14, 14, 16, 32, 3, 1, 1),        # general implicit-GEMM path
+    (1, 10, 10, 20, 70, 5, 1, 2),
+    (2, 8, 8, 24, 24, 4, 2, 1),
+    (1, 56, 56, 64, 64, 3, 1, 1),        # one sample of config 5
+]
+
+
+@pytest.mark.parametrize("N,H,W,C1,C0,K,S,P", CONV_CASES)
+def test_conv2d_fwd_bwd(N, H, W, C1, C0, K, S, P):
+    I, F, Bv = rnd(N, H, W, C1), rnd(C1, K, K, C0, lo=-.3, hi=.3), rnd(C0)
+    H0, W0 = orc.conv_out_dims(H, W, K, S, P)
+    o = dev(np.full((N, H0, W0, C0), np.nan, np.float32))                    # must not need pre-zeroing
+    ok(lib().t4k_conv2d_fwd(ptr(dev(I)), ptr(dev(F)), ptr(dev(Bv)), ptr(o), N, H, W, C1, H0, W0, C0, K, S, P, None))
+    assert_close(host(o), orc.conv2d(I, F, Bv, K, S, P), rtol=1e-4, what="conv fwd")
+    dO = rnd(N, H0, W0, C0)
+    dF0, dB0 = rnd(C1, K, K, C0), rnd(C0)
+    dx, df, db = dev(np.full(I.shape, np.nan, np.float32)), dev(dF0), dev(dB0)
+    ok(lib().t4k_conv2d_bwd(ptr(dev(I)), ptr(dev(dO)), ptr(dev(F)), ptr(dx), ptr(df), ptr(db),
+                            N, H, W, C1, H0, W0, C0, K, S, P, 1, None))
+    rdx, rdf, rdb = orc.dconv2d(I, dO, F, K, S, P, dF0, dB0, True)
+    assert_close(host(dx), rdx, rtol=1e-4, what="conv dX (flipped taps)")
+    assert_close(host(df), rdf, rtol=1e-4, what="conv dF")
+    assert_close(host(db), rdb, rtol=1e-4, what="conv dB")
+    df2, db2 = dev(dF0), dev(dB0)
+    ok(lib().t4k_conv2d_bwd(ptr(dev(I)), ptr(dev(dO)), ptr(dev(F)), ptr(dx), ptr(df2), ptr(db2),
+                            N, H, W, C1, H0, W0, C0, K, S, P, 0, None))
+    assert_exact(host(df2), dF0); assert_exact(host(db2), dB0)               # train == 0
+    assert lib().t4k_conv2d_fwd(ptr(dev(I)), ptr(dev(F)), ptr(dev(Bv)), ptr(o), N, H, W, C1, H0, W0, C0, 7, 1, 3, None) == -2
+
+
+@pytest.mark.parametrize("layer", [t4.L_MAXPOOL, t4.L_AVGPOOL, t4.L_MINPOOL, t4.L_USAMPLE])
+@pytest.mark.parametrize("N,H,W,Cc,K", [(2, 4, 4, 1, 2), (512, 28, 28, 10, 2), (3, 9, 12, 5, 3), (2, 6, 6, 33, 2)])
+def test_pool_fwd_bwd(layer, N, H, W, Cc, K):
+    x = rnd(N, H, W, Cc)
+    x[0, :K, :K, 0] = 0.5                                                    # a full tie: first element must win
+    o = zeros(N, H // K, W // K, Cc)
+    ok(lib().t4k_pool_fwd(layer, ptr(dev(x)), ptr(o), N, H, W, H // K, W // K, Cc, K, None))
+    ref = orc.pool(layer, x, K)
+    (assert_exact if layer in (t4.L_MAXPOOL, t4.L_MINPOOL) else assert_close)(host(o), ref)
+    dy = rnd(N, H // K, W // K, Cc)
+    xi = dev(x)
+    ok(lib().t4k_pool_bwd(layer, ptr(xi), ptr(dev(dy)), N, H, W, H // K, W // K, Cc, K, None))
+    rb = orc.dpool(layer, x, dy, K)
+    (assert_close if layer == t4.L_AVGPOOL else assert_exact)(host(xi), rb)  # routing is exact
+
+
+@pytest.mark.parametrize("N,HW,Cc", [(2, 16, 3), (8, 49, 10), (4, 100, 64), (3, 7, 300)])
+def test_batchnorm_fwd_bwd(N, HW, Cc):
+    x = rnd(N, HW, Cc, lo=-2, hi=3)
+    g, b = rnd(Cc, lo=.5, hi=1.5), rnd(Cc)
+    o, xh, scr = zeros(N, HW, Cc), zeros(N, HW, Cc), zeros(3 * Cc)
+    ok(lib().t4k_batchnorm_fwd(ptr(dev(x)), ptr(o), ptr(xh), ptr(dev(g)), ptr(dev(b)), ptr(scr), N, HW, Cc, None))
+    ro, rxh, ravg, rrvar = orc.batchnorm(x, g, b)
+    assert_close(host(o), ro, rtol=1e-4, what="bn out"); assert_close(host(xh), rxh, rtol=1e-4, what="bn xhat")
+    assert_close(host(scr)[:Cc], rrvar, rtol=1e-4); assert_close(host(scr)[Cc:2 * Cc], ravg, rtol=1e-4, atol=1e-6)
+    dy = rnd(N, HW, Cc)
+    dW0, dB0 = rnd(Cc), rnd(Cc)
+    dx, dw, db = zeros(N, HW, Cc), dev(dW0), dev(dB0)
+    ok(lib().t4k_batchnorm_bwd(ptr(dev(dy)), ptr(xh), ptr(dx), ptr(dev(g)), ptr(dw), ptr(db), ptr(scr), N, HW, Cc, 1, None))
+    rdx, rdw, rdb = orc.dbatchnorm(dy, rxh, g, rrvar, dW0, dB0, True)
+    assert_close(host(dx), rdx, rtol=1e-4, what="bn dX")
+    assert_close(host(dw), rdw, rtol=1e-4, atol=1e-6); assert_close(host(db), rdb, rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------ optimizers / onehot / hit / rand
+@pytest.mark.parametrize("n", [5, 1000, 196000])
+def test_optimizers(n):
+    g0, dg0, m0, v0 = rnd(n), rnd(n), rnd(n, lo=-.1, hi=.1), rnd(n, lo=0, hi=.1)
+    for kind in ("sgd0", "sgdm", "adam", "adamw"):
+        g, dg, m, v = dev(g0), dev(dg0), dev(m0), dev(v0)
+        rg, rdg, rm, rv = g0.copy(), dg0.copy(), m0.copy(), v0.copy()
+        P = orc._p
+        if kind == "sgd0":
+            ok(lib().t4k_sgd(ptr(g), ptr(dg), ptr(m), 3, 0.5, 0.0, n, None)); orc.lib().orc_sgd(P(rg), P(rdg), P(rm), 3, 0.5, 0.0, n)
+        elif kind == "sgdm":
+            ok(lib().t4k_sgd(ptr(g), ptr(dg), ptr(m), 1, 0.5, 0.9, n, None)); orc.lib().orc_sgd(P(rg), P(rdg), P(rm), 1, 0.5, 0.9, n)
+        elif kind == "adam":
+            ok(lib().t4k_adam(ptr(g), ptr(dg), ptr(m), ptr(v), 1e-3, 0.9, 0.999, n, None)); orc.lib().orc_adam(P(rg), P(rdg), P(rm), P(rv), 1e-3, 0.9, 0.999, n)
+        else:
+            ok(lib().t4k_adamw(ptr(g), ptr(dg), ptr(m), ptr(v), 1e-3, 0.9, 0.999, 0.01, n, None)); orc.lib().orc_adamw(P(rg), P(rdg), P(rm), P(rv), 1e-3, 0.9, 0.999, 0.01, n)
+        assert_close(host(g), rg, rtol=1e-5, atol=1e-7, what=kind)
+        assert not host(dg).any()                                            # dG zeroed (nmath.cu:434,452)
+        assert_close(host(m), rm, rtol=1e-5, atol=1e-8, what=kind + " m")
+        if kind.startswith("adam"):
+            assert_close(host(v), rv, rtol=1e-5, atol=1e-9, what=kind + " v")
+
+
+def test_optim_multi_matches_per_tensor():
+    lens, nws = [90, 10, 196000, 100, 1000, 10], [1, 1, 1, 1, 1, 1]
+    nws[0] = 3
+    offs = np.concatenate([[0], np.cumsum([(l + 3) // 4 * 4 for l in lens])]).astype(np.int64)
+    total = int(offs[-1])
+    g0, dg0 = rnd(total), rnd(total)
+    seg = np.zeros(len(lens), dtype=[("off", "<i8"), ("len", "<i8"), ("Nw", "<i4"), ("pad", "<i4")])
+    seg["off"], seg["len"], seg["Nw"] = offs[:-1], [(l + 3) // 4 * 4 for l in lens], nws
+    dseg = torch.from_numpy(seg.view(np.uint8)).cuda()
+    for kind in (0, 1, 2):
+        g, dg, m, v = dev(g0), dev(dg0), zeros(total), zeros(total)
+        ok(lib().t4k_optim_multi(kind, ptr(g), ptr(dg), ptr(m), ptr(v), C.c_void_p(dseg.data_ptr()), len(lens), total, 0.01, 0.9 if kind else 0.0, 0.999, 0.01, None))
+        g2, dg2, m2, v2 = dev(g0), dev(dg0), zeros(total), zeros(total)
+        for k in range(len(lens)):
+            o, ln = int(seg["off"][k]), int(seg["len"][k])
+            if kind == 0: ok(lib().t4k_sgd(ptr(g2, o), ptr(dg2, o), ptr(m2, o), int(seg["Nw"][k]), 0.01, 0.0, ln, None))
+            elif kind == 1: ok(lib().t4k_adam(ptr(g2, o), ptr(dg2, o), ptr(m2, o), ptr(v2, o), 0.01, 0.9, 0.999, ln, None))
+            else: ok(lib().t4k_adamw(ptr(g2, o), ptr(dg2, o), ptr(m2, o), ptr(v2, o), 0.01, 0.9, 0.999, 0.01, ln, None))
+        assert_exact(host(g), host(g2)); assert_exact(host(m), host(m2)); assert_exact(host(v), host(v2))
+
+
+def test_onehot_hit():
+    N, E = 512, 10
+    lab = RNG.integers(0, 12, N).astype(np.int32)            # labels >= E map to class 0 (loss.cpp:66)
+    hot = zeros(N, E)
+    dl = torch.from_numpy(lab).cuda()
+    ok(lib().t4k_onehot(C.c_void_p(dl.data_ptr()), ptr(hot), N, E, None))
+    rh = orc.onehot(lab, E)
+    assert_exact(host(hot), rh)
+    out = rnd(N, E)
+    out[3, :] = 0.25                                          # tie → first index
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ok(lib().t4k_hit(ptr(dev(out)), ptr(hot), N, E, C.c_void_p(cnt.data_ptr()), None))
+    assert int(cnt.cpu()[0]) == orc.hit(out, rh)
+
+
+def test_rand_statistics_and_reproducibility():
+    n = 1 << 20
+    a, b = zeros(n), zeros(n)
+    ok(lib().t4k_rand_at(ptr(a), n, t4.UNIFORM, 0.0, 1.0, 42, 0, None))
+    ok(lib().t4k_rand_at(ptr(b), n, t4.UNIFORM, 0.0, 1.0, 42, 0, None))
+    ha = host(a)
+    assert np.array_equal(ha, host(b))
+    assert ha.min() > 0.0 and ha.max() <= 1.0 and abs(ha.mean() - 0.5) < 2e-3 and abs(ha.var() - 1 / 12) < 2e-3
+    # sharding independence: element i only depends on (seed, offset+i)
+    ok(lib().t4k_rand_at(ptr(b), n // 2, t4.UNIFORM, 0.0, 1.0, 42, n // 2, None))
+    assert np.array_equal(host(b)[: n // 2], ha[n // 2:])
+    ok(lib().t4k_rand_at(ptr(a), n, t4.NORMAL, 0.0, 1.0, 7, 0, None))
+    hn = host(a)
+    assert abs(hn.mean()) < 5e-3 and abs(hn.std() - 1.0) < 5e-3
+    # weight-init convention of Model::RAND: scale*2*(-0.5+U) in [-k, k)  (model.cpp:74-79)
+    ok(lib().t4k_rand_at(ptr(a), n, t4.UNIFORM, -0.5, 2 * 0.1, 1, 0, None))
+    hw = host(a)
+    assert hw.min() > -0.1 - 1e-7 and hw.max() <= 0.1 + 1e-7
+
+
+def test_launches_are_counted():
+    before = lib().t4k_launch_count()
+    d = zeros(1024)
+    ok(lib().t4k_map(t4.FILL, ptr(d), 1.0, 1024, None))
+    assert lib().t4k_launch_count() == before + 1
