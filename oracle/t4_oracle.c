@@ -321,6 +321,19 @@ void orc_conv2d(const float *I, const float *F, const float *B, float *O,
  * dX is pre-zeroed by the caller (src/nn/backprop.cu:169); oracle zeroes it here.
  * dF/dB ACCUMULATE into the caller's buffers.
  * ------------------------------------------------------------------------- */
+/* Flush multiplicity of dF taps — src/nn/nmath.tcu:332-336 flushes _df[t] once per thread whose
+ * load_id = ty*TS + tx equals t, with (tx,ty) in [0,16)^2 and TS = (16-KS+S)/S (backprop.cu:144).
+ * For KS=1,3 every t < KS*KS has exactly one such thread; for (KS,S)=(5,1) taps 12..15,24 are
+ * flushed twice and for (4,2) taps 7..13 twice, 14..15 three times.  Reference behaviour
+ * (verified against the reference kernels on a B200, tests/golden) → replicated. */
+static int dconv_flush_mult(int KS, int S, int t)
+{
+    const int TS = (16 - KS + S) / S;
+    int m = 0;
+    for (int ty = 0; ty < 16; ty++)
+        for (int tx = 0; tx < 16; tx++) if (ty * TS + tx == t) m++;
+    return m;
+}
 void orc_dconv2d(const float *I, const float *dO, const float *F,
                  float *dX, float *dF, float *dB,
                  int N, int H1, int W1, int C1, int H0, int W0, int C0,
@@ -378,7 +391,7 @@ void orc_dconv2d(const float *I, const float *dO, const float *F,
                             }
                         }
                     }
-                    dF[(((long)c1 * KS + ky) * KS + kx) * C0 + c0] += (float)s;
+                    dF[(((long)c1 * KS + ky) * KS + kx) * C0 + c0] += (float)(s * dconv_flush_mult(KS, S, ky * KS + kx));
                 }
 }
 /* ---------------------------------------------------------------------------

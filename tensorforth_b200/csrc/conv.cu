@@ -149,15 +149,28 @@ __global__ void __launch_bounds__(T4K_THREADS) k_conv_wgrad_small(ConvP p, float
         part[(int64_t)blockIdx.x * (nF + C0) + t] = acc;
     }
 }
+// Reference quirk (nmath.tcu:332-336): the per-tile _df[tap] is flushed once per thread whose
+// load_id = ty*TS + tx equals tap, (tx,ty) in [0,16)^2, TS = (16-KS+S)/S.  Exactly one thread for
+// KS = 1,3; but taps 12..15,24 of the 5x5/s1 config are flushed twice and taps 7..13 / 14..15 of
+// the 4x4/s2 config two / three times.  Verified on the reference kernels (tests/golden); replicated.
+__host__ __device__ __forceinline__ int dconv_flush_mult(int KS, int S, int tap) {
+    const int TS = (16 - KS + S) / S;
+    int m = 0;
+    for (int ty = 0; ty < 16; ty++) { const int tx = tap - ty * TS; if (tx >= 0 && tx < 16) m++; }
+    return m;
+}
 // dF[t] += Σ_cta part[cta][t] (t < nF) ; dB[t-nF] += ... ; ordered → deterministic
 __global__ void __launch_bounds__(T4K_THREADS) k_wgrad_fin(const float *__restrict__ part, float *dF, float *dB,
-                                                           int nF, int C0, int nparts) {
+                                                           int nF, int C0, int nparts, int KS, int S) {
     __shared__ float red[T4K_THREADS / 32];
     const int t = blockIdx.x;                                      // one output element per CTA
     float v = 0.0f;
     for (int c = threadIdx.x; c < nparts; c += blockDim.x) v += part[(int64_t)c * (nF + C0) + t];
     v = block_sum(v, red);
-    if (threadIdx.x == 0) { if (t < nF) dF[t] += v; else dB[t - nF] += v; }
+    if (threadIdx.x == 0) {
+        if (t < nF) dF[t] += v * (float)dconv_flush_mult(KS, S, (t / C0) % (KS * KS));
+        else dB[t - nF] += v;
+    }
 }
 
 // ====================================================================== general implicit GEMM (CUDA cores)
@@ -272,11 +285,11 @@ __global__ void __launch_bounds__(256) k_conv_igemm(ConvP p, float *part, int kc
     }
 }
 // dF[(c1,ky,kx),c0] += Σ_z part[z][...]   (MODE 2 finalize; part row m=(c1,ky,kx) matches dF's layout)
-__global__ void __launch_bounds__(T4K_THREADS) k_igemm_wgrad_fin(const float *__restrict__ part, float *dF, int64_t nF, int splits) {
+__global__ void __launch_bounds__(T4K_THREADS) k_igemm_wgrad_fin(const float *__restrict__ part, float *dF, int64_t nF, int splits, int C0, int KS, int S) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nF; t += (int64_t)gridDim.x * blockDim.x) {
         float s = 0.0f;
         for (int z = 0; z < splits; z++) s += part[(int64_t)z * nF + t];
-        dF[t] += s;
+        dF[t] += s * (float)dconv_flush_mult(KS, S, (int)((t / C0) % (KS * KS)));
     }
 }
 // dB[c0] += Σ_pix dO[pix,c0] : two-phase column reduce (CTA partials, ordered finalize)
@@ -379,7 +392,7 @@ extern "C" int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, f
                                     k_conv_wgrad_small<K_><<<ctas, T4K_THREADS, smem_small, st>>>(p, part, strips); }
             switch (KS) { case 1: WG_LAUNCH(1) break; case 3: WG_LAUNCH(3) break; case 4: WG_LAUNCH(4) break; default: WG_LAUNCH(5) break; }
             rc = check_launch(); if (rc) return rc;
-            k_wgrad_fin<<<nF + C0, T4K_THREADS, 0, st>>>(part, dF, dB, nF, C0, ctas);
+            k_wgrad_fin<<<nF + C0, T4K_THREADS, 0, st>>>(part, dF, dB, nF, C0, ctas, KS, S);
             rc = check_launch(); if (rc) return rc;
         } else {
             const int64_t Kg = (int64_t)N * H0 * W0;
@@ -395,7 +408,7 @@ extern "C" int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, f
             if (!part) return T4K_ENOMEM;
             k_conv_igemm<2><<<dim3(gx, gy, splits), 256, 0, st>>>(p, part, (int)kchunk);
             rc = check_launch(); if (rc) return rc;
-            k_igemm_wgrad_fin<<<stream_grid(nF), T4K_THREADS, 0, st>>>(part, dF, nF, splits);
+            k_igemm_wgrad_fin<<<stream_grid(nF), T4K_THREADS, 0, st>>>(part, dF, nF, splits, C0, KS, S);
             rc = check_launch(); if (rc) return rc;
             // dB
             int nparts = 4 * sm_count();

@@ -5,6 +5,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 
 def pytest_configure(config):
@@ -24,3 +25,13 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _release_device_buffers():
+    yield
+    try:
+        import gpu_util
+        gpu_util.release()
+    except Exception:
+        pass

@@ -15,13 +15,25 @@ def lib():
     return L
 
 
+_KEEP = []          # keeps device buffers alive while asynchronous kernels use their raw pointers
+
+
 def dev(a, dtype=np.float32):
-    """numpy → CUDA tensor (contiguous)"""
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).cuda()
+    """numpy → CUDA tensor (contiguous); kept alive until release() (the C-ABI sees raw pointers only)"""
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).cuda()
+    _KEEP.append(t)
+    return t
+
+
+def release():
+    torch.cuda.synchronize()
+    _KEEP.clear()
 
 
 def zeros(*shape):
-    return torch.zeros(*shape, dtype=torch.float32, device="cuda")
+    t = torch.zeros(*shape, dtype=torch.float32, device="cuda")
+    _KEEP.append(t)
+    return t
 
 
 def ptr(t, off=0):
