@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""
+bench.py — the measurement contract (task §④).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's own legacy CUDA build (oracle/_ref/ten4)
+
+Metric (BASELINE.json): MNIST-CNN training samples/s — the CNN of examples/t4_40a.4th:10-13 at N=512 per GPU
+(weak scaling), one step = forward + loss.ce + backprop + nn.adam on synthetic 28x28x1 data — plus, at N=1, the two
+other headline numbers as `extras`: GEMM 4096^3 FP32 TFLOP/s and conv2d 3x3 64->64 @56x56 HBM GB/s, each against its
+roofline (MEASURED_PEAKS.json).  One JSON line on stdout (rank 0).
+
+`value`   : device-timed (CUDA events on the launching stream, max over ranks), inputs resident in HBM.
+`e2e`     : same step through the public host API with the batch copied from pinned host memory and the loss read
+            back every step.
+`roofline`: the dominant kernel of the step, timed live (K launches between two events on its stream).
+`cpu_baseline`: the C oracle (oracle/, "port") timed on the host cores on a bounded sample — reported, not a target.
+tensorForth has no CPU tensor path; the reference arm therefore times the reference's GPU build.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 512                       # per GPU (BASELINE config 3)
+REF_TEN4 = os.path.join(ROOT, "oracle", "_ref", "ten4")
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+        p["src"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True); self.t.start(); return self
+
+    def __exit__(self, *a):
+        self.stop.set(); self.t.join(timeout=3)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = max([int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def ref_script(kind, warm, steps, batch):
+    """Forth text both builds could run (SURVEY.md §8d 'synthetic step script')"""
+    if kind == "mnist":
+        return "\n".join([
+            "0 trace", "%d constant N" % batch,
+            "N 28 28 1 nn.model 0.5 10 conv2d 2 maxpool relu flatten 100 linear relu 10 linear softmax constant md0",
+            "N 28 28 1 tensor rand 2 *= 1 -= constant X", "N 1 10 1 tensor rand constant Y",
+            ": step ( M -- M ) X forward Y loss.ce drop Y backprop 0.001 nn.adam ;",
+            ": bench ( M n -- M ) clock >r for step next clock r> - . ;",
+            "md0 %d bench cr" % max(warm - 1, 0), "%d bench cr" % (steps - 1), "bye", ""])
+    if kind == "gemm":
+        return "\n".join([
+            "0 trace", "4096 4096 matrix rand", "4096 4096 matrix rand",
+            ": mx ( A B n -- A B ) clock >r for @ drop next clock r> - . ;",
+            "%d mx cr" % max(warm - 1, 0), "%d mx cr" % (steps - 1), "bye", ""])
+    raise ValueError(kind)
+
+
+def run_ref(kind, warm, steps, batch=BATCH, timeout=900):
+    """run the reference's own CUDA build; returns ms for `steps` iterations (its own `clock` word, syncs included)"""
+    if not os.path.exists(REF_TEN4):
+        return None, "oracle/_ref/ten4 not built"
+    env = dict(os.environ)
+    try:
+        p = subprocess.run([REF_TEN4], input=ref_script(kind, warm, steps, batch), capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+    except Exception as e:
+        return None, "ten4 failed: %r" % (e,)
+    nums = [float(x) for x in re.findall(r"^(-?\d+(?:\.\d+)?)\s*$", p.stdout, flags=re.M)]
+    if len(nums) < 2:
+        return None, "could not parse ten4 output: %s" % p.stdout[-300:].replace("\n", " | ")
+    return nums[-1], None
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    ms, why = run_ref("mnist", args.warmup, args.steps)
+    line = {"impl": "reference", "metric": "mnist_cnn_train_samples_per_sec", "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MNIST CNN (t4_40a.4th:10-13) N=%d fwd+loss.ce+backprop+nn.adam" % BATCH,
+                       "note": "reference = chochain/tensorForth's own CUDA kernels, unmodified, built for sm_100 (oracle/ref/build_ref.sh), "
+                               "1 GPU (it has no multi-GPU and no CPU tensor path); timed with its own `clock` word incl. its per-kernel syncs"}}
+    if ms is None:
+        # no reference binary on this box: fall back to the CPU oracle port (bounded sample)
+        v, cores, sample = cpu_port_baseline(max(2, min(args.steps, 10)))
+        line.update({"value": v, "ms_per_step": BATCH / v * 1e3, "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+                     "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "reference_unavailable": why})
+    else:
+        v = BATCH * args.steps / (ms / 1e3) if ms > 0 else float("inf")
+        line.update({"value": v, "ms_per_step": ms / args.steps,
+                     "cpu_baseline": {"value": v, "unit": "samples/s", "cores": 1, "kind": "reference",
+                                      "sample": "%d steps of N=%d on GPU 0 through oracle/_ref/ten4 (one host thread drives the GPU)" % (args.steps, BATCH)},
+                     "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        if not args.no_extras:
+            gms, gwhy = run_ref("gemm", 3, 10)
+            line["extras"] = {"gemm4096": ({"ms": gms / 10, "tflops": 2 * 4096 ** 3 / (gms / 10) / 1e9} if gms else {"unavailable": gwhy})}
+    line["wall_s"] = round(time.time() - t0, 2)
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- CPU oracle baseline
+def cpu_port_baseline(steps=4, batch=BATCH):
+    """the oracle's Model restatement (C kernels, OpenMP) on the host cores: bounded sample of the same workload"""
+    import numpy as np
+    from oracle import oracle as orc
+    om = orc.OracleModel(batch, 28, 28, 1, seed=1)
+    om.add(orc.L_CONV, 10, 0.5, [3, 1, 1, 1]).add(orc.L_MAXPOOL, 2).add(orc.L_RELU).add(orc.L_FLATTEN)
+    om.add(orc.L_LINEAR, 100, 1.0).add(orc.L_RELU).add(orc.L_LINEAR, 10, 1.0).add(orc.L_SOFTMAX)
+    rng = np.random.default_rng(0)
+    x = (rng.random((batch, 28, 28, 1), dtype=np.float32) * 2 - 1).astype(np.float32)
+    y = orc.onehot(rng.integers(0, 10, batch), 10)
+
+    def step():
+        om.forward(x); om.loss(orc.LOSS_CE, y); om.backprop(y); om.adam(0.001)
+    step()
+    t0 = time.time()
+    n = 0
+    while n < steps or (time.time() - t0 < 10.0 and n < 200):
+        step(); n += 1
+    dt = time.time() - t0
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return batch * n / dt, cores, "%d train steps of N=%d (%.1f s) with the C oracle, OpenMP" % (n, batch, dt)
+
+
+# --------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="no CUDA-graph capture of the step")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    from tensorforth_b200 import lib as t4
+    from tensorforth_b200 import host as th
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product has no CPU path"
+    torch.cuda.set_device(local)
+    th.init(local)
+    L, H = t4.load(), th.load()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib_stream = torch.cuda.ExternalStream(th.stream(), device=local)       # events/NCCL ordered with the library's stream
+    torch.cuda.set_stream(lib_stream)
+    pk = peaks()
+
+    # ---- model + synthetic data of BASELINE config 3 (weights: the model's own Philox init, per-rank identical seed)
+    L.t4k_rand_seed(1234)
+    m = th.mnist_cnn(BATCH)
+    rng = np.random.default_rng(100 + rank)
+    xh = torch.from_numpy((rng.random((BATCH, 28, 28, 1), dtype=np.float32) * 2 - 1).astype(np.float32)).pin_memory()
+    yh = torch.from_numpy(np.eye(10, dtype=np.float32)[rng.integers(0, 10, BATCH)]).pin_memory()
+    X, Y = th.Tensor.tensor(BATCH, 28, 28, 1), th.Tensor.tensor(BATCH, 1, 10, 1)
+    H.t4h_tensor_h2d(X.h, C.c_void_p(xh.data_ptr()), xh.numel()); H.t4h_tensor_h2d(Y.h, C.c_void_p(yh.data_ptr()), yh.numel())
+    loss_dev = torch.zeros(8, device="cuda")
+    lossp = C.c_void_p(loss_dev.data_ptr())
+    LR = 1e-3
+
+    dg_view = None
+
+    def step():
+        if world == 1 and not args.eager:
+            t4.check(m.step_graph(X, Y, t4.LOSS_CE, lossp, optimizer=2, lr=LR), "step_graph")
+        else:
+            m.forward(X); m.loss_async(t4.LOSS_CE, Y, lossp); m.backprop(Y)
+            if world > 1:
+                dist.all_reduce(dg_view)                       # gradient sum over ranks (reference gradients are batch SUMS)
+            m.adam(LR)
+
+    # first step eagerly: builds the flat parameter arenas and sizes every workspace
+    n0 = L.t4k_launch_count()
+    m.forward(X); m.loss_async(t4.LOSS_CE, Y, lossp); m.backprop(Y); m.adam(LR)
+    launches_per_step = L.t4k_launch_count() - n0
+    if world > 1:
+        g, dg, total = m.arena()
+
+        class _Cai:                                            # zero-copy torch view of the DG arena
+            __cuda_array_interface__ = {"shape": (total,), "typestr": "<f4", "data": (dg, False), "version": 3}
+        dg_view = torch.as_tensor(_Cai(), device="cuda")
+
+        class _CaiG:
+            __cuda_array_interface__ = {"shape": (total,), "typestr": "<f4", "data": (g, False), "version": 3}
+        dist.broadcast(torch.as_tensor(_CaiG(), device="cuda"), 0)          # identical replicas
+    th.sync()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as cs:
+        e0.record(lib_stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(lib_stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if ms < 600:                                           # keep the GPU under the same load so nvidia-smi sees clocks under load
+            t_end = time.time() + 0.8
+            while time.time() < t_end:
+                step()
+            torch.cuda.synchronize()
+    final_loss = float(loss_dev[0].cpu())
+    if world > 1:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.cpu()[0])
+    value = BATCH * world * args.steps / (ms / 1e3)
+
+    # ---- e2e: batch from pinned host memory every step, loss read back every step
+    lh = torch.zeros(1).pin_memory()
+    barrier()
+    e0.record(lib_stream)
+    for _ in range(args.steps):
+        H.t4h_tensor_h2d(X.h, C.c_void_p(xh.data_ptr()), xh.numel()); H.t4h_tensor_h2d(Y.h, C.c_void_p(yh.data_ptr()), yh.numel())
+        step()
+        lh.copy_(loss_dev[:1], non_blocking=True); lib_stream.synchronize()
+    e1.record(lib_stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_e2e = float(t.cpu()[0])
+    e2e = {"value": BATCH * world * args.steps / (ms_e2e / 1e3), "unit": "samples/s",
+           "h2d_bytes_per_step": int(xh.numel() * 4 + yh.numel() * 4), "d2h_bytes_per_step": 4}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel live timing of the step's kernels at the step's shapes → roofline of the dominant one
+    def kt(fn, iters=50):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); a.record(lib_stream)
+        for _ in range(iters):
+            fn()
+        b.record(lib_stream); torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters * 1e3                 # us
+
+    N = BATCH
+    f32 = lambda *s: torch.empty(*s, device="cuda").uniform_(-1, 1)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(th.stream())
+    I, F, Bv, O = f32(N, 28, 28, 1), f32(1, 3, 3, 10), f32(10), f32(N, 28, 28, 10)
+    Pl, dPl, Fl, dW1 = f32(N, 14, 14, 10), f32(N, 14, 14, 10), f32(N, 1960), f32(100, 1960)
+    W1, Y1, dY1, dF, dB, dX = f32(100, 1960), f32(N, 100), f32(N, 100), f32(1, 3, 3, 10), f32(10), f32(N, 28, 28, 1)
+    B100 = f32(100)
+    MB = 1e6
+    kernels = [
+        ("conv2d_fwd 1->10 3x3",  lambda: L.t4k_conv2d_fwd(p(I), p(F), p(Bv), p(O), N, 28, 28, 1, 28, 28, 10, 3, 1, 1, st), (I.numel() + O.numel()) * 4),
+        ("maxpool2_fwd",          lambda: L.t4k_pool_fwd(t4.L_MAXPOOL, p(O), p(Pl), N, 28, 28, 14, 14, 10, 2, st), (O.numel() + Pl.numel()) * 4),
+        ("relu_fwd(+mask)",       lambda: L.t4k_activate_fwd(t4.L_RELU, p(Pl), p(dPl), p(Fl), 0.0, Pl.numel(), st), 3 * Pl.numel() * 4),
+        ("flatten copy",          lambda: L.t4k_copy(p(Pl), p(Fl), Pl.numel(), st), 2 * Pl.numel() * 4),
+        ("linear1_fwd 1960->100", lambda: L.t4k_linear_fwd(p(Fl), p(W1), p(B100), p(Y1), N, 100, 1960, st), (Fl.numel() + W1.numel() + Y1.numel()) * 4),
+        ("linear1_bwd (dB,dW,dX)", lambda: L.t4k_linear_bwd(p(Fl), p(W1), p(dY1), p(dPl), p(dW1), p(Y1), N, 100, 1960, 1, st), (2 * Fl.numel() + 3 * W1.numel() + dY1.numel()) * 4),
+        ("relu_bwd (dY*mask)",    lambda: L.t4k_activate_bwd(p(Pl), p(Fl), p(dPl), Pl.numel(), st), 3 * Pl.numel() * 4),
+        ("maxpool2_bwd in place", lambda: L.t4k_pool_bwd(t4.L_MAXPOOL, p(O), p(Pl), N, 28, 28, 14, 14, 10, 2, st), (2 * O.numel() + Pl.numel()) * 4),
+        ("conv2d_bwd (dF,dB,dX)", lambda: L.t4k_conv2d_bwd(p(I), p(O), p(F), p(dX), p(dF), p(dB), N, 28, 28, 1, 28, 28, 10, 3, 1, 1, 1, st), (2 * I.numel() + 2 * O.numel()) * 4),
+    ]
+    ktab = []
+    for name, fn, nbytes in kernels:
+        us = kt(fn)
+        ktab.append({"kernel": name, "us": round(us, 2), "alg_MB": round(nbytes / MB, 2), "GBps": round(nbytes / us / 1e3, 1)})
+    dom = max(ktab, key=lambda r: r["us"])
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": round(dom["GBps"] / pk["hbm_gbs"], 4), "traffic": None, "peak_src": pk["src"],
+                "step_kernel_sum_us": round(sum(r["us"] for r in ktab), 1)}
+
+    out = {"metric": "mnist_cnn_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "MNIST CNN (examples/t4_40a.4th:10-13) conv3x3(1->10)+maxpool2+relu+flatten+linear100+relu+linear10+softmax, "
+                                  "N=%d per GPU, step = forward + loss.ce + backprop + nn.adam(lr=1e-3)" % BATCH,
+                      "global_batch": BATCH * world, "parallelism": "dp%d" % world if world > 1 else "single",
+                      "cuda_graph": bool(world == 1 and not args.eager),
+                      "l2": "working set per step ~190 MB > 126 MB L2; no explicit flush (back-to-back steps is the workload)"},
+           "clocks": cs.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+           "launches_per_step": int(launches_per_step), "final_loss": final_loss,
+           "roofline": roofline, "kernels": ktab}
+
+    # ---- extras: the other two headline numbers of BASELINE.json (1 GPU only)
+    if world == 1 and not args.no_extras:
+        ex = {}
+        n = 4096
+        A, B_, Oo = f32(n, n), f32(n, n), f32(n, n)
+        us = kt(lambda: L.t4k_gemm(p(A), p(B_), p(Oo), 1.0, 0.0, 0, 0, n, n, n, 1, 1, 0, 0, 0, st), iters=20)
+        tf = 2 * n ** 3 / us / 1e6
+        tf32_peak = pk["bf16_tflops"] / 2                      # TF32 dense = 1/2 BF16
+        ex["gemm4096"] = {"ms": round(us / 1e3, 4), "tflops": round(tf, 1), "engine": "tcgen05 3xTF32 (pack + mma)",
+                          "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": round(tf32_peak / 3, 1), "unit": "TFLOP/s",
+                                       "frac": round(tf / (tf32_peak / 3), 4),
+                                       "note": "peak = measured BF16 %.0f /2 (TF32) /3 (3 MMAs per product for FP32-grade accuracy); "
+                                               "vs plain TF32 peak: %.3f" % (pk["bf16_tflops"], tf / tf32_peak)}}
+        del A, B_, Oo
+        cn = 64                                                # samples of config 5 per launch in this quick probe
+        Ic, Fc, Bc, Oc = f32(cn, 56, 56, 64), f32(64, 3, 3, 64), f32(64), f32(cn, 56, 56, 64)
+        dXc, dFc, dBc = f32(cn, 56, 56, 64), f32(64, 3, 3, 64), f32(64)
+        usf = kt(lambda: L.t4k_conv2d_fwd(p(Ic), p(Fc), p(Bc), p(Oc), cn, 56, 56, 64, 56, 56, 64, 3, 1, 1, st), iters=5)
+        usb = kt(lambda: L.t4k_conv2d_bwd(p(Ic), p(Oc), p(Fc), p(dXc), p(dFc), p(dBc), cn, 56, 56, 64, 56, 56, 64, 3, 1, 1, 1, st), iters=5)
+        fb = (2 * Ic.numel() + Fc.numel()) * 4
+        bb = (3 * Ic.numel() + 2 * Fc.numel()) * 4
+        fl = 2.0 * cn * 56 * 56 * 64 * 64 * 9
+        ex["conv2d_3x3_64"] = {"samples": cn, "fwd_ms": round(usf / 1e3, 3), "bwd_ms": round(usb / 1e3, 3),
+                               "fwd_GBps": round(fb / usf / 1e3, 1), "bwd_GBps": round(bb / usb / 1e3, 1),
+                               "fwd_tflops": round(fl / usf / 1e6, 2), "bwd_tflops": round(2 * fl / usb / 1e6, 2),
+                               "roofline": {"bound": "hbm", "achieved": round(fb / usf / 1e3, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                            "frac": round(fb / usf / 1e3 / pk["hbm_gbs"], 4)},
+                               "note": "NHWC, N=%d of the 8192-sample config per launch (per-sample cost is size independent)" % cn}
+        out["extras"] = ex
+    if not args.no_cpu_baseline:
+        v, cores, sample = cpu_port_baseline()
+        out["cpu_baseline"] = {"value": round(v, 1), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

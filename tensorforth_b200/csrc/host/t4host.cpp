@@ -1,0 +1,653 @@
+// t4host.cpp — bodies of t4::Tensor / t4::Model on top of the kernel C-ABI (include/t4k.h), plus the
+// flat C interface of include/t4host.h.  Reference citations are file:line in the reference tree.
+#include "t4host.hpp"
+#include "../../../include/t4host.h"
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <cfloat>
+
+namespace t4 {
+
+// =============================================================================== Runtime
+static cudaStream_t g_stream = nullptr;
+static bool  g_init = false;
+static char  g_err[512] = "";
+
+int Runtime::init(int device) {
+    if (g_init) return 0;
+    if (cudaSetDevice(device) != cudaSuccess) { error("cudaSetDevice(%d) failed: no CUDA device (there is no CPU fallback)", device); cudaGetLastError(); return T4K_EINVAL; }
+    if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) { error("cudaStreamCreate failed"); return T4K_EINVAL; }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;                     // keep freed blocks cached: alloc/free in `for @ drop next` loops stay cheap
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    g_init = true;
+    return 0;
+}
+void *Runtime::stream() { return (void*)g_stream; }
+int   Runtime::sync()   { return (int)cudaStreamSynchronize(g_stream); }
+void  Runtime::error(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+const char *Runtime::last_error() { return g_err; }
+void *Runtime::alloc(size_t bytes) {
+    if (!g_init && init(0)) return nullptr;
+    void *p = nullptr;
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (cudaMallocAsync(&p, bytes, g_stream) != cudaSuccess) { cudaGetLastError(); error("device allocation of %zu bytes failed", bytes); return nullptr; }
+    return p;
+}
+void Runtime::free(void *p) { if (p) cudaFreeAsync(p, g_stream); }
+
+#define ST         (Runtime::stream())
+#define KCHK(call) do { int _rc = (call); if (_rc) Runtime::error("%s -> %d (%s)", #call, _rc, t4k_strerror(_rc)); } while (0)
+static inline DU SCALAR(DU v) { uint32_t u; memcpy(&u, &v, 4); u &= ~1u; memcpy(&v, &u, 4); return v; }   // src/t4base.h:33 (object tag bit cleared)
+
+// =============================================================================== Tensor
+Tensor &Tensor::reset(void *mem, U64 sz, t4_layer fn) {                 // tensor.cu:461-484
+    numel = sz; rank = 1; train = false; err = false; iparm = 0; xparm = 0;
+    const U64 GB = 1ull << 30;
+    const U16 s[4] = {1, 1, 1, 1};
+    const U32 h[4] = {(U32)(sz > GB ? (sz >> 30) : sz), (U32)(sz > GB ? GB : 1), 1, 1};
+    data = (DU*)mem; grad_fn = fn;
+    memcpy(stride, s, sizeof(s)); memcpy(shape, h, sizeof(h));
+    for (int i = 0; i < 5; i++) grad[i] = mtum[i] = nullptr;
+    _tmp = data ? &data[numel] : nullptr;
+    return *this;
+}
+static Tensor &alloc_tensor(U64 sz) {
+    Tensor *t = new Tensor();
+    void *mem = Runtime::alloc((sz + 4) * sizeof(DU));                   // numel + scratch (MMU::talloc: numel+1, mmu.cu:202)
+    t->reset(mem, sz);
+    return *t;
+}
+Tensor &Tensor::create(U64 sz)                    { return alloc_tensor(sz); }
+Tensor &Tensor::create(U32 h, U32 w)              { return alloc_tensor((U64)h * w).reshape(h, w); }
+Tensor &Tensor::create(U32 n, U32 h, U32 w, U32 c){ return alloc_tensor((U64)n * h * w * c).reshape(n, h, w, c); }
+Tensor &Tensor::create_like(Tensor &t)            { return create(t.N(), t.H(), t.W(), t.C()); }
+Tensor &Tensor::copy_of(Tensor &t) {                                     // MMU::copy, mmu.cu:274-295
+    Tensor &o = alloc_tensor(t.numel);
+    o.rank = t.rank; memcpy(o.shape, t.shape, sizeof(o.shape)); memcpy(o.stride, t.stride, sizeof(o.stride));
+    o.xparm = t.xparm; o.iparm = t.iparm;
+    copy(t, o);
+    return o;
+}
+void Tensor::destroy(Tensor &t) {
+    if (t.owns) Runtime::free(t.data);
+    delete &t;
+}
+bool Tensor::is_same_shape(Tensor &t) { return memcmp(shape, t.shape, sizeof(shape)) == 0; }
+
+Tensor &Tensor::reshape(U64 sz) {                                        // tensor.cu:487-497
+    if (sz == numel) { DU *d = data; t4_layer fn = grad_fn; Tensor *g[5], *m[5]; memcpy(g, grad, sizeof(g)); memcpy(m, mtum, sizeof(m));
+                       reset(d, numel, fn); memcpy(grad, g, sizeof(g)); memcpy(mtum, m, sizeof(m)); }
+    else Runtime::error("  tensor#reshape sz != numel (%ld != %ld)\n", (long)sz, (long)numel);
+    return *this;
+}
+Tensor &Tensor::reshape(U32 h, U32 w) {                                  // tensor.cu:499-514
+    if ((U64)h * w == numel) { rank = 2; const U16 s[4] = {1, 1, 1, 1}; const U32 t[4] = {h, w, 1, 1}; memcpy(stride, s, sizeof(s)); memcpy(shape, t, sizeof(t)); }
+    else Runtime::error("  tensor#reshape sz != numel (%ld != %ld)\n", (long)((U64)h * w), (long)numel);
+    return *this;
+}
+Tensor &Tensor::reshape(U32 n, U32 h, U32 w, U32 c) {                    // tensor.cu:516-531
+    if ((U64)n * h * w * c == numel) { rank = 4; const U16 s[4] = {1, 1, 1, 1}; const U32 t[4] = {h, w, c, n}; memcpy(stride, s, sizeof(s)); memcpy(shape, t, sizeof(t)); }
+    else Runtime::error("  tensor#reshape sz != numel (%ld != %ld)\n", (long)((U64)n * h * w * c), (long)numel);
+    return *this;
+}
+Tensor &Tensor::identity() { KCHK(t4k_identity(data, N(), H(), W(), C(), ST)); return *this; }      // tensor.cu:548-555
+Tensor &Tensor::zeros()    { cudaMemsetAsync(data, 0, sizeof(DU) * numel, (cudaStream_t)ST); return *this; }   // tensor.cu:557-562
+Tensor &Tensor::map(math_op op, DU v) { KCHK(t4k_map(op, data, v, numel, ST)); return *this; }       // tensor.cu:564-571
+Tensor &Tensor::normalize(DU avg, DU std) {                              // tensor.cu:573-578
+    KCHK(t4k_ts_op(T4K_SUB, data, avg, data, numel, ST)); KCHK(t4k_ts_op(T4K_DIV, data, std, data, numel, ST)); return *this;
+}
+Tensor &Tensor::ten_op(math_op op, Tensor &A, DU v, Tensor &O) {         // tensor.cu:17-23
+    KCHK(t4k_ts_op(op, A.data, v, O.data, A.numel, ST)); return O;
+}
+Tensor &Tensor::ten_op(math_op op, Tensor &A, Tensor &B, Tensor &O) {    // tensor.cu:29-53
+    const U32 Na = A.N(), Nb = B.N();
+    if (A.HWC() != B.HWC() || (Na == 1 ? B.numel : A.numel) != O.numel) {
+        Runtime::error("  tensor#ten_op A.HWC(%ld)!=B.HWC(%ld) or N, C diff\n", (long)A.HWC(), (long)B.HWC());
+        return O;
+    }
+    KCHK(t4k_tt_op(op, A.data, B.data, O.data, A.HWC(), Na, Nb, ST));
+    return O;
+}
+Tensor &Tensor::dot(Tensor &A, Tensor &B, Tensor &O, DU alpha, DU beta) { // tensor.cu:61-72
+    KCHK(t4k_dot(A.data, B.data, O.data, alpha, beta, A.W(), A.C(), A.N(), B.N(), ST)); return O;
+}
+Tensor &Tensor::mm(Tensor &A, Tensor &B, Tensor &O, bool inc, bool tA, bool tB) {   // tensor.cu:74-77
+    return gemm3(A, B, O, 1.0f, inc ? 1.0f : 0.0f, tA, tB);
+}
+Tensor &Tensor::linear(Tensor &A, Tensor &B, Tensor &O, int H, int W, int K, DU alpha, DU beta, bool tA, bool tB) { // tensor.cu:80-87
+    KCHK(t4k_gemm(A.data, B.data, O.data, alpha, beta, tA, tB, H, W, K, 1, 1, 0, 0, 0, ST)); return O;
+}
+Tensor &Tensor::_gemm(int engine, Tensor &A, Tensor &B, Tensor &O, DU alpha, DU beta, bool tA, bool tB, const char *nm) {
+    U32 H  = tA ? A.W() : A.H(), W  = tB ? B.H() : B.W();               // tensor.cu:162-180
+    U32 Ka = tA ? A.H() : A.W(), Kb = tB ? B.W() : B.H();
+    U32 Na = A.N(), Nb = B.N(), C = B.C();
+    U32 N  = std::max(Na, Nb);
+    if (Ka != Kb || N != O.N() || C != O.C()) { Runtime::error("  tensor#%s ka(%d)!=kb(%d) or N, C diff\n", nm, Ka, Kb); return O; }
+    KCHK(t4k_gemm_ex(engine, A.data, B.data, O.data, alpha, beta, tA, tB, H, W, Ka, C, N,
+                     Na == 1 && N > 1 ? 0 : (int64_t)A.HWC(), Nb == 1 && N > 1 ? 0 : (int64_t)B.HWC(), (int64_t)O.HWC(), ST));
+    return O;
+}
+// gemm1/gemm2 are the reference's naive / 16x16-tiled kernels (double accumulator); all four words map
+// onto the same engines here and stay as aliases
+Tensor &Tensor::gemm1(Tensor &A, Tensor &B, Tensor &O, DU a, DU b, bool tA, bool tB) { return A._gemm(T4K_GEMM_SIMT, A, B, O, a, b, tA, tB, "gemm1"); }
+Tensor &Tensor::gemm2(Tensor &A, Tensor &B, Tensor &O, DU a, DU b, bool tA, bool tB) { return A._gemm(T4K_GEMM_SIMT, A, B, O, a, b, tA, tB, "gemm2"); }
+Tensor &Tensor::gemm3(Tensor &A, Tensor &B, Tensor &O, DU a, DU b, bool tA, bool tB) { return A._gemm(T4K_GEMM_AUTO, A, B, O, a, b, tA, tB, "gemm3"); }
+Tensor &Tensor::gemm4(Tensor &A, Tensor &B, Tensor &O, DU a, DU b, bool tA, bool tB) { return A._gemm(T4K_GEMM_AUTO, A, B, O, a, b, tA, tB, "gemm4"); }
+Tensor &Tensor::copy(Tensor &A, Tensor &O) { KCHK(t4k_copy(A.data, O.data, A.numel, ST)); return O; }          // tensor.cu:204-208
+Tensor &Tensor::transpose(Tensor &A, Tensor &T) { KCHK(t4k_transpose(A.data, T.data, A.N(), A.H(), A.W(), A.C(), ST)); return T; } // :210-219
+
+static DU read_scalar(DU *dev) { DU v = 0; cudaMemcpyAsync(&v, dev, sizeof(DU), cudaMemcpyDeviceToHost, (cudaStream_t)ST); Runtime::sync(); return v; }
+DU Tensor::sum()  { KCHK(t4k_sum(data, numel, _tmp, ST)); return SCALAR(read_scalar(_tmp)); }                  // tensor.cu:225-236
+DU Tensor::avg()  { DU v = sum() / numel; return SCALAR(v); }                                                  // :238-242
+DU Tensor::std()  { KCHK(t4k_avg_std(data, numel, _tmp, ST)); return SCALAR(read_scalar(_tmp + 1)); }          // :244-251 (sqrt(Σ(x-μ)²)/n)
+DU Tensor::norm() { KCHK(t4k_nvar(data, 0.0f, numel, _tmp, ST)); return SCALAR(sqrtf(read_scalar(_tmp))); }    // :253-259
+DU Tensor::max()  { KCHK(t4k_minmax(data, numel, 1, _tmp, ST)); return SCALAR(read_scalar(_tmp)); }            // :261-268
+DU Tensor::min()  { KCHK(t4k_minmax(data, numel, 0, _tmp, ST)); return SCALAR(read_scalar(_tmp)); }            // :269-277
+DU Tensor::dot(Tensor &B) {                                                                                   // :279-287
+    if (rank == 1 && B.rank == 1 && numel == B.numel) KCHK(t4k_dot(data, B.data, _tmp, 1.0f, 0.0f, (int)numel, 1, 1, 1, ST));
+    else Runtime::error("A.dot(B) dim? %ld != %ld)\n", (long)numel, (long)B.numel);
+    return SCALAR(read_scalar(_tmp));
+}
+DU Tensor::loss(t4_loss op, Tensor &tgt) {                                                                    // :289-325
+    KCHK(t4k_loss(op, data, tgt.data, numel, N(), _tmp, ST));
+    return SCALAR(read_scalar(_tmp));
+}
+U32 Tensor::has_nan() {
+    KCHK(t4k_nan_inf(data, numel, (int*)_tmp, ST));
+    int cnt = 0; cudaMemcpyAsync(&cnt, _tmp, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)ST); Runtime::sync(); return cnt;
+}
+int Tensor::h2d(const DU *h, U64 n) { return (int)cudaMemcpyAsync(data, h, sizeof(DU) * (n ? n : numel), cudaMemcpyHostToDevice, (cudaStream_t)ST); }
+int Tensor::d2h(DU *h, U64 n) { cudaMemcpyAsync(h, data, sizeof(DU) * (n ? n : numel), cudaMemcpyDeviceToHost, (cudaStream_t)ST); return Runtime::sync(); }
+
+// =============================================================================== Model
+Model::Model(U32 n, U32 h, U32 w, U32 c) { _layers.push_back(&Tensor::create(n, h, w, c)); }
+Model::~Model() {
+    Runtime::sync();
+    for (Tensor *t : _layers) {
+        for (int i = 0; i < 5; i++) { if (t->grad[i]) Tensor::destroy(*t->grad[i]); if (t->mtum[i]) Tensor::destroy(*t->mtum[i]); }
+        Tensor::destroy(*t);
+    }
+    if (_own_hot && _hot) Tensor::destroy(*_hot);
+    Runtime::free(_G); Runtime::free(_DG); Runtime::free(_M); Runtime::free(_V); Runtime::free(_seg_dev); Runtime::free(_cnt_dev);
+    if (_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)_graph_exec);
+}
+Tensor &Model::operator[](S32 i) { return *_layers[(i < 0) ? (S32)_layers.size() + i : i]; }     // model.cpp:47-49
+int Model::batch_size() { return _layers.empty() ? 1 : (int)_layers[0]->N(); }
+void Model::_RAND(Tensor &t, DU scale) {                                  // model.cpp:74-79: [-scale, scale)
+    KCHK(t4k_rand(t.data, t.numel, T4K_UNIFORM, -0.5f, scale * 2.0f, ST));
+}
+// ---- layer factory (model.cpp:83-117)
+Model &Model::add(t4_layer fn, U32 n, DU bias, U16 *opt) {
+    Tensor &in = (*this)[-1];
+    if (in.grad_fn != T4K_L_NONE) return *this;
+    for (int i = 0; i < 5; i++) in.grad[i] = in.mtum[i] = nullptr;
+    U16 dflt[4] = {3, 1, 0, 1};
+    size_t before = _layers.size();
+    switch (fn) {
+    case T4K_L_CONV:    _iconv(in, n, bias, opt ? opt : dflt); break;
+    case T4K_L_LINEAR:  _ilinear(in, n, bias);                 break;
+    case T4K_L_FLATTEN: _iflatten(in);                         break;
+    case T4K_L_RELU: case T4K_L_TANH: case T4K_L_SIGMOID: case T4K_L_SELU:
+    case T4K_L_LEAKYRL: case T4K_L_ELU: case T4K_L_DROPOUT: _iactivate(in, bias); break;
+    case T4K_L_SOFTMAX: case T4K_L_LOGSMAX: _isoftmax(in);     break;
+    case T4K_L_AVGPOOL: case T4K_L_MAXPOOL: case T4K_L_MINPOOL: _ipool(in, (U16)n); break;
+    case T4K_L_BATCHNM: _ibatchnorm(in, bias);                 break;
+    case T4K_L_USAMPLE: _iup(in, (U16)n, bias);                break;
+    default: Runtime::error("Model#add layer %d not supported\n", fn); err = true; return *this;   // L_DCONV: SURVEY §8f row 4
+    }
+    if (_layers.size() > before) in.grad_fn = fn;
+    return *this;
+}
+void Model::_iconv(Tensor &in, U32 C0, DU bias, U16 *opt) {               // model.cpp:122-180
+    U32 N1 = in.N(), H1 = in.H(), W1 = in.W(), C1 = in.C();
+    U16 Kx = opt[0], Ky = opt[0], S = opt[1];
+    U16 P  = (Kx > 1 && opt[2]) ? opt[2] : (Kx - 1) / 2;
+    U16 H0 = (H1 - Kx + P * 2) / S + 1;
+    U16 W0 = (H1 - Ky + P * 2) / S + 1;                                   // sic: W0 from H1 (model.cpp:137)
+    (void)W1;
+    if (Kx != 1 && Kx != 3 && Kx != 5) { Runtime::error("nn#iconv conv2d f=[%d,%d]? 1x1, 3x3, 4x4, and 5x5 supported only.\n", Kx, Ky); err = true; return; }
+    in.stride[0] = in.stride[1] = S; in.stride[2] = in.stride[3] = P; in.xparm = bias;
+    Tensor *f = in.grad[0] = &Tensor::create(C1, Kx, Ky, C0);
+    Tensor *b = in.grad[1] = &Tensor::create((U64)C0);
+    in.grad[2] = &Tensor::create(C1, Kx, Ky, C0).zeros();
+    in.grad[3] = &Tensor::create((U64)C0).zeros();
+    in.grad[4] = &Tensor::create(N1, H1, in.W(), C1).zeros();
+    DU k = sqrtf(6.0f / (Kx * Ky * C1));
+    _RAND(*f, k); _RAND(*b, bias);
+    _layers.push_back(&Tensor::create(N1, H0, W0, C0));
+}
+void Model::_ilinear(Tensor &in, U32 E0, DU bias) {                       // model.cpp:183-226
+    U32 N1 = in.N(); U64 E1 = in.HWC();
+    Tensor *w = in.grad[0] = &Tensor::create(1, E0, (U32)E1, 1);
+    Tensor *b = in.grad[1] = &Tensor::create((U64)E0);
+    in.grad[2] = &Tensor::create(1, E0, (U32)E1, 1).zeros();
+    in.grad[3] = &Tensor::create((U64)E0).zeros();
+    in.xparm = bias;
+    DU k = sqrtf(1.0f / (E0 + E1));
+    _RAND(*w, k); _RAND(*b, bias);
+    _layers.push_back(&Tensor::create(N1, 1, E0, 1));
+}
+void Model::_iflatten(Tensor &in) { _layers.push_back(&Tensor::create(in.N(), 1, (U32)in.HWC(), 1)); }          // model.cpp:227-233
+void Model::_isoftmax(Tensor &in) { in.grad[4] = &Tensor::create(1, in.H(), in.W(), in.C()); _layers.push_back(&Tensor::create_like(in)); } // :237-245
+void Model::_iactivate(Tensor &in, DU alpha) { in.grad[4] = &Tensor::create_like(in); in.xparm = alpha; _layers.push_back(&Tensor::create_like(in)); } // :247-256
+void Model::_ipool(Tensor &in, U16 k) {                                   // model.cpp:260-274
+    if (k != 2 && k != 3) { Runtime::error("nn#ipool k=%dx%d? 2x2 and 3x3 supported only\n", k, k); err = true; return; }
+    U32 H0 = (in.H() + k - 1) / k, W0 = (in.W() + k - 1) / k;
+    U16 s[4] = {k, 1, 1, 0}; memcpy(in.stride, s, sizeof(s));
+    _layers.push_back(&Tensor::create(in.N(), H0, W0, in.C()));
+}
+void Model::_ibatchnorm(Tensor &in, DU m) {                               // model.cpp:276-292
+    const U32 C = in.C();
+    in.grad[0] = &Tensor::create((U64)C).map(T4K_FILL, 1.0f);
+    in.grad[2] = &Tensor::create((U64)C).zeros();     // reference leaves d_gamma/d_beta uninitialised (model.cpp:281,283); zero is the value a fresh arena has
+    in.grad[1] = &Tensor::create((U64)C).zeros();
+    in.grad[3] = &Tensor::create((U64)C).zeros();
+    in.grad[4] = &Tensor::create_like(in);
+    in.mtum[4] = &Tensor::create((U64)C * 3);
+    in.xparm = m;
+    _layers.push_back(&Tensor::create_like(in));
+}
+void Model::_iup(Tensor &in, U16 k, DU method) {                          // model.cpp:294-310
+    if (k != 2 && k != 3) { Runtime::error("nn#iup k=%dx%d? only 2x2 and 3x3 supported\n", k, k); err = true; return; }
+    in.iparm = (U32)method;
+    U16 s[4] = {k, 1, 1, 1}; memcpy(in.stride, s, sizeof(s));
+    _layers.push_back(&Tensor::create(in.N(), in.H() * k, in.W() * k, in.C()));
+}
+// ---- forward (forward.cu:29-113)
+Model &Model::forward(Tensor &input) {
+    Tensor &n0 = (*this)[0];
+    if (input.numel != n0.numel) {
+        Runtime::error("nn#forward dataset wrong shape[%d,%d,%d,%d] != model input[%d,%d,%d,%d]\n",
+                       input.N(), input.H(), input.W(), input.C(), n0.N(), n0.H(), n0.W(), n0.C());
+        return *this;
+    }
+    if (input.data != n0.data) n0 = input;
+    for (size_t i = 0; i + 1 < _layers.size(); i++) _fstep(*_layers[i], *_layers[i + 1]);
+    return *this;
+}
+void Model::_fstep(Tensor &in, Tensor &out) {                             // forward.cu:83-113
+    t4_layer fn = in.grad_fn;
+    switch (fn) {
+    case T4K_L_CONV:    _fconv(in, out);   break;
+    case T4K_L_LINEAR:  _flinear(in, out); break;
+    case T4K_L_FLATTEN: out = in;          break;
+    case T4K_L_RELU: case T4K_L_TANH: case T4K_L_SIGMOID: case T4K_L_SELU:
+    case T4K_L_LEAKYRL: case T4K_L_ELU: _factivate(in, out, fn); break;
+    case T4K_L_DROPOUT: {
+        Tensor &t = *in.grad[4];
+        KCHK(t4k_rand(t.data, t.numel, T4K_UNIFORM, 0.0f, 1.0f, ST));     // fresh mask every forward (forward.cu:98-102)
+        _factivate(in, out, fn);
+    } break;
+    case T4K_L_SOFTMAX: _fsoftmax(in, out);    break;
+    case T4K_L_LOGSMAX: _flogsoftmax(in, out); break;
+    case T4K_L_AVGPOOL: case T4K_L_MAXPOOL: case T4K_L_MINPOOL: _fpool(in, out, fn); break;
+    case T4K_L_BATCHNM: _fbatchnorm(in, out);  break;
+    case T4K_L_USAMPLE: _fupsample(in, out);   break;
+    default: Runtime::error("nn#fstep layer=%d not supported\n", fn);
+    }
+}
+int Model::_fconv(Tensor &in, Tensor &out) {                              // forward.cu:126-155
+    Tensor &f = *in.grad[0], &b = *in.grad[1];
+    int rc = t4k_conv2d_fwd(in.data, f.data, b.data, out.data, out.N(), in.H(), in.W(), in.C(), out.H(), out.W(), out.C(),
+                            f.H(), in.stride[0], in.stride[2], ST);
+    if (rc == T4K_ENOSUP) { Runtime::error("nn#fconv kernel_size=%d stride=%d padding=%d not supported\n", f.H(), in.stride[0], in.stride[2]); return -1; }
+    KCHK(rc);
+    return 0;
+}
+int Model::_flinear(Tensor &in, Tensor &out) {                            // forward.cu:158-198
+    KCHK(t4k_linear_fwd(in.data, in.grad[0]->data, in.grad[1]->data, out.data, out.N(), (int)out.HWC(), (int)in.HWC(), ST));
+    return 0;
+}
+int Model::_factivate(Tensor &in, Tensor &out, t4_layer fn) {             // forward.cu:201-209
+    KCHK(t4k_activate_fwd(fn, in.data, out.data, in.grad[4]->data, in.xparm, in.numel, ST)); return 0;
+}
+int Model::_fpool(Tensor &in, Tensor &out, t4_layer fn) {                 // forward.cu:212-228
+    int rc = t4k_pool_fwd(fn, in.data, out.data, out.N(), in.H(), in.W(), out.H(), out.W(), out.C(), in.stride[0], ST);
+    if (rc == T4K_ENOSUP) { Runtime::error("nn#fpool kernel_size=%d not supported\n", in.stride[0]); return -1; }
+    KCHK(rc); return 0;
+}
+int Model::_fsoftmax(Tensor &in, Tensor &out)    { KCHK(t4k_softmax_fwd(in.data, out.data, in.N(), (int)in.HWC(), ST)); return 0; }     // forward.cu:231-243
+int Model::_flogsoftmax(Tensor &in, Tensor &out) { KCHK(t4k_logsoftmax_fwd(in.data, out.data, in.N(), (int)in.HWC(), ST)); return 0; }  // forward.cu:246-259
+int Model::_fbatchnorm(Tensor &in, Tensor &out) {                         // forward.cu:264-309
+    KCHK(t4k_batchnorm_fwd(in.data, out.data, in.grad[4]->data, in.grad[0]->data, in.grad[1]->data, in.mtum[4]->data,
+                           out.N(), out.H() * out.W(), out.C(), ST));
+    return 0;
+}
+int Model::_fupsample(Tensor &in, Tensor &out) {                          // forward.cu:314-329 (nearest: every cell of the KxK block = in)
+    KCHK(t4k_pool_bwd(T4K_L_USAMPLE, out.data, in.data, in.N(), out.H(), out.W(), in.H(), in.W(), in.C(), in.stride[0], ST)); return 0;
+}
+// ---- backprop (backprop.cu:40-140)
+Model &Model::backprop() {
+    if (_hot) return backprop(*_hot);
+    Runtime::error("nn#backprop missing onehot vector?\n");
+    return *this;
+}
+Model &Model::backprop(Tensor &tgt) {
+    if (_bprep(tgt)) return *this;
+    for (int i = (int)_layers.size() - 2, j = 0; i >= 0; i--, j++) _bstep(*_layers[i], *_layers[i + 1], j == 0);
+    return *this;
+}
+int Model::_bprep(Tensor &tgt) {                                          // backprop.cu:76-109
+    Tensor &out = (*this)[-1];
+    if (out.numel != tgt.numel) {
+        Runtime::error("Model#bprep: Onehot wrong shape[%d,%d,%d,%d] != [%d,%d,%d,%d], numel=%ld,%ld ",
+                       tgt.N(), tgt.H(), tgt.W(), tgt.C(), out.N(), out.H(), out.W(), out.C(), (long)tgt.numel, (long)out.numel);
+        return 1;
+    }
+    switch ((*this)[-2].grad_fn) {
+    case T4K_L_LINEAR: case T4K_L_SIGMOID: case T4K_L_SOFTMAX: case T4K_L_LOGSMAX:
+        KCHK(t4k_tt_op(T4K_SUB, out.data, tgt.data, out.data, out.numel, 1, 1, ST)); break;       // out -= tgt  (p - y, not divided by N)
+    default: out = tgt; break;
+    }
+    return 0;
+}
+void Model::_bstep(Tensor &in, Tensor &out, bool last_layer) {            // backprop.cu:112-140
+    t4_layer fn = in.grad_fn;
+    switch (fn) {
+    case T4K_L_CONV:    _bconv(in, out); break;
+    case T4K_L_LINEAR:  if (last_layer) in = out; else _blinear(in, out); break;
+    case T4K_L_FLATTEN: in = out; break;
+    case T4K_L_RELU: case T4K_L_TANH: case T4K_L_SELU: case T4K_L_LEAKYRL: case T4K_L_ELU:
+    case T4K_L_DROPOUT: _bactivate(in, out); break;
+    case T4K_L_SIGMOID: case T4K_L_SOFTMAX: case T4K_L_LOGSMAX: in = out; break;   // pass-through, also for hidden sigmoids (backprop.cu:129-131)
+    case T4K_L_MAXPOOL: case T4K_L_AVGPOOL: case T4K_L_MINPOOL: _bpool(in, out, fn); break;
+    case T4K_L_BATCHNM: _bbatchnorm(in, out); break;
+    case T4K_L_USAMPLE: _bupsample(in, out, fn); break;
+    default: Runtime::error("nn#bstep layer=%d not supported\n", fn);
+    }
+}
+int Model::_bconv(Tensor &in, Tensor &out) {                              // backprop.cu:153-191
+    Tensor &f = *in.grad[0], &df = *in.grad[2], &db = *in.grad[3], &dx = *in.grad[4];
+    int rc = t4k_conv2d_bwd(in.data, out.data, f.data, dx.data, df.data, db.data, in.N(), in.H(), in.W(), in.C(),
+                            out.H(), out.W(), out.C(), f.H(), in.stride[0], in.stride[2], train, ST);
+    if (rc == T4K_ENOSUP) { Runtime::error("nn#bconv kernel_size=%d stride=%d padding=%d not supported\n", f.H(), in.stride[0], in.stride[2]); return -1; }
+    KCHK(rc);
+    in = dx;                                                               // x = dX (overwrite)
+    return 0;
+}
+int Model::_blinear(Tensor &in, Tensor &out) {                            // backprop.cu:194-254
+    Tensor &w = *in.grad[0], &dw = *in.grad[2], &db = *in.grad[3];
+    // dX overwrites the layer input in place; dW needs X first → t4k_linear_bwd orders dW before dX,
+    // and dX = dY@W does not read X, so in.data may be both X and dX.
+    KCHK(t4k_linear_bwd(in.data, w.data, out.data, in.data, dw.data, db.data, in.N(), (int)out.HWC(), (int)in.HWC(), train, ST));
+    return 0;
+}
+int Model::_bactivate(Tensor &in, Tensor &out) { KCHK(t4k_activate_bwd(out.data, in.grad[4]->data, in.data, in.numel, ST)); return 0; } // backprop.cu:257-263
+int Model::_bpool(Tensor &in, Tensor &out, t4_layer fn) {                 // backprop.cu:266-280
+    int rc = t4k_pool_bwd(fn, in.data, out.data, out.N(), in.H(), in.W(), out.H(), out.W(), out.C(), in.stride[0], ST);
+    if (rc == T4K_ENOSUP) { Runtime::error("nn#bpool kernel_size=%d not supported\n", in.stride[0]); return -1; }
+    KCHK(rc); return 0;
+}
+int Model::_bupsample(Tensor &in, Tensor &out, t4_layer fn) {             // backprop.cu:285-300 (k_pool USAMPLE = Σ/K²)
+    (void)fn;
+    KCHK(t4k_pool_fwd(T4K_L_USAMPLE, out.data, in.data, in.N(), out.H(), out.W(), in.H(), in.W(), in.C(), in.stride[0], ST)); return 0;
+}
+int Model::_bbatchnorm(Tensor &in, Tensor &out) {                         // backprop.cu:312-370
+    KCHK(t4k_batchnorm_bwd(out.data, in.grad[4]->data, in.data, in.grad[0]->data, in.grad[2]->data, in.grad[3]->data,
+                           in.mtum[4]->data, in.N(), in.H() * in.W(), in.C(), train, ST));
+    return 0;
+}
+// ---- loss / onehot / hit (loss.cpp:16-136)
+Tensor &Model::onehot() {
+    if (_hot) return *_hot;
+    Runtime::error("Model.onehot not provided by dataset, use nn.onehot= to setup!\n");
+    return (*this)[-1];
+}
+Tensor &Model::onehot(Tensor &t) {                                        // loss.cpp:26-43
+    Tensor &out = (*this)[-1];
+    if (_hot) { if (_own_hot) Tensor::destroy(*_hot); _hot = nullptr; }
+    else if (t.N() != out.N() || (U32)t.HWC() != (U32)out.HWC()) { Runtime::error("Model.onehot dimension is not [%d,1,%d,1]\n", out.N(), (U32)out.HWC()); return t; }
+    _hot = &t; _own_hot = false;
+    _hit = hit(true);
+    return *_hot;
+}
+Tensor &Model::onehot_labels(const int32_t *labels_dev) {                 // loss.cpp:47-72, on device
+    Tensor &out = (*this)[-1];
+    if (!_hot) { _hot = &Tensor::create(out.N(), 1, (U32)out.HWC(), 1); _own_hot = true; }
+    KCHK(t4k_onehot(labels_dev, _hot->data, out.N(), (int)out.HWC(), ST));
+    return *_hot;
+}
+int Model::hit(bool recalc) {                                             // loss.cpp:75-107
+    if (!recalc) return _hit;
+    if (!_hot) return 0;
+    Tensor &out = (*this)[-1];
+    if (!_cnt_dev) _cnt_dev = (int*)Runtime::alloc(256);
+    KCHK(t4k_hit(out.data, _hot->data, out.N(), (int)out.HWC(), _cnt_dev, ST));
+    int cnt = 0; cudaMemcpyAsync(&cnt, _cnt_dev, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)ST); Runtime::sync();
+    return _hit = cnt;
+}
+DU Model::loss(t4_loss op) { return _hot ? loss(op, *_hot) : 0.0f; }
+DU Model::loss(t4_loss op, Tensor &tgt) {                                 // loss.cpp:119-136 (non-destructive: no _loss duplicate needed)
+    Tensor &out = (*this)[-1];
+    if (out.numel != tgt.numel) {
+        Runtime::error("nn::loss model output shape[%d,%d,%d,%d] != tgt[%d,%d,%d,%d]\n",
+                       out.N(), out.H(), out.W(), out.C(), tgt.N(), tgt.H(), tgt.W(), tgt.C());
+        return 0.0f;
+    }
+    return out.loss(op, tgt);
+}
+int Model::loss_async(t4_loss op, Tensor &tgt, DU *loss_dev) {
+    Tensor &out = (*this)[-1];
+    if (out.numel != tgt.numel) return T4K_EINVAL;
+    return t4k_loss(op, out.data, tgt.data, out.numel, out.N(), loss_dev, ST);
+}
+// ---- optimizers (gradient.cu:20-169)
+Model &Model::grad_alloc(t4_optimizer op) {
+    // Reference: per-tensor m / v tensors (gradient.cu:20-59).  Here: every (w,dw),(b,db) pair moves into flat
+    // arenas G / DG (+ M, V, zero filled) at identical offsets, the Tensor objects become views; one
+    // t4k_optim_multi launch then updates the whole model and DG is one contiguous all-reduce payload.
+    struct Seg { Tensor *g, *dg; int Nw; };
+    std::vector<Seg> segs;
+    for (size_t i = 0; i + 1 < _layers.size(); i++) {
+        Tensor &in = *_layers[i];
+        if (in.grad[0] && in.grad[2]) segs.push_back({in.grad[0], in.grad[2], (int)in.grad[0]->N()});   // Nw = parameter tensor's N() (gradient.cu:137)
+        if (in.grad[1] && in.grad[3]) segs.push_back({in.grad[1], in.grad[3], (int)in.grad[1]->N()});
+    }
+    _arena_opt = op;
+    if (segs.empty()) return *this;
+    std::vector<t4k_seg_t> table;
+    U64 off = 0;
+    for (auto &s : segs) { U64 len = (s.g->numel + 3) & ~3ull; table.push_back({(int64_t)off, (int64_t)len, s.Nw, 0}); off += len; }
+    _total = off; _nseg = (int)segs.size();
+    _G = (DU*)Runtime::alloc(_total * 4); _DG = (DU*)Runtime::alloc(_total * 4);
+    _M = (DU*)Runtime::alloc(_total * 4); _V  = (DU*)Runtime::alloc(_total * 4);
+    _seg_dev = Runtime::alloc(4096 + 256 + sizeof(t4k_seg_t) * table.size());
+    cudaStream_t st = (cudaStream_t)ST;
+    cudaMemsetAsync(_G, 0, _total * 4, st); cudaMemsetAsync(_DG, 0, _total * 4, st);
+    cudaMemsetAsync(_M, 0, _total * 4, st); cudaMemsetAsync(_V, 0, _total * 4, st);
+    cudaMemcpyAsync(_seg_dev, table.data(), sizeof(t4k_seg_t) * table.size(), cudaMemcpyHostToDevice, st);
+    for (size_t k = 0; k < segs.size(); k++) {
+        Tensor *g = segs[k].g, *dg = segs[k].dg;
+        KCHK(t4k_copy(g->data, _G + table[k].off, g->numel, ST)); KCHK(t4k_copy(dg->data, _DG + table[k].off, dg->numel, ST));
+        if (g->owns) Runtime::free(g->data);
+        if (dg->owns) Runtime::free(dg->data);
+        g->data = _G + table[k].off;  g->owns = false;  g->_tmp = (DU*)_seg_dev + 1024;     // views share a scratch past the segment table
+        dg->data = _DG + table[k].off; dg->owns = false; dg->_tmp = (DU*)_seg_dev + 1024;
+    }
+    Runtime::sync();                      // `table` is host memory read by the async copy
+    return *this;
+}
+Model &Model::_gradient(t4_optimizer op, DU lr, DU b1, DU b2, DU wd) {     // gradient.cu:64-126
+    if (_iter++ == 0 && epoch == 0 && !_G) grad_alloc(op);
+    if (!train || !_G) return *this;
+    const int kind = (op == OPTI_SGD || op == OPTI_SGDM) ? 0 : (op == OPTI_ADAM ? 1 : 2);
+    KCHK(t4k_optim_multi(kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, (int64_t)_total, lr, b1, b2, wd, ST));
+    return *this;
+}
+Model &Model::sgd(DU lr, DU b) {                                           // gradient.cu:133-143: momentum forced to 0 on the first call
+    DU beta = _iter ? b : 0.0f;
+    return _gradient(fabsf(b) < DU_EPS_H ? OPTI_SGD : OPTI_SGDM, lr, beta, 0.0f, 0.0f);
+}
+Model &Model::adam(DU lr, DU b1, DU b2)         { return _gradient(OPTI_ADAM, lr, b1, b2, 0.0f); }     // gradient.cu:145-157 (no bias correction)
+Model &Model::adamw(DU lr, DU wd, DU b1, DU b2) { return _gradient(OPTI_ADAMW, lr, b1, b2, wd); }      // gradient.cu:159-169
+int Model::arena(DU **G, DU **DG, int64_t *total) {
+    if (!_G) grad_alloc(OPTI_ADAM);
+    if (G) *G = _G; if (DG) *DG = _DG; if (total) *total = (int64_t)_total;
+    return _G ? 0 : T4K_EINVAL;
+}
+// ---- one train step as a CUDA graph: forward + loss + backprop + optimizer
+int Model::step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd) {
+    auto run = [&]() {
+        forward(input);
+        if (loss_dev) loss_async(lop, tgt, loss_dev);
+        backprop(tgt);
+        switch (op) { case OPTI_SGD: case OPTI_SGDM: sgd(lr, b1); break; case OPTI_ADAM: adam(lr, b1, b2); break; default: adamw(lr, wd, b1, b2); }
+    };
+    bool has_dropout = false;
+    for (Tensor *t : _layers) if (t->grad_fn == T4K_L_DROPOUT) has_dropout = true;
+    U64 key[8]; float f4[4] = {lr, b1, b2, wd};
+    key[0] = (U64)input.data; key[1] = (U64)tgt.data; key[2] = (U64)lop; key[3] = (U64)loss_dev; key[4] = (U64)op;
+    memcpy(&key[5], f4, 16); key[7] = (U64)train;
+    // SGD's first call forces momentum 0 (host state) and the first optimizer call builds the arenas: run those eagerly
+    if (has_dropout || !_G || _iter == 0) { run(); return 0; }
+    cudaStream_t st = (cudaStream_t)ST;
+    if (!_graph_exec || memcmp(key, _graph_key, sizeof(key)) != 0) {
+        if (_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)_graph_exec); _graph_exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); run(); return 0; }
+        const int it = _iter;
+        run();
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (e != cudaSuccess || !graph) { cudaGetLastError(); _iter = it; Runtime::error("graph capture failed: %s", cudaGetErrorString(e)); run(); return 0; }
+        cudaGraphExec_t ex = nullptr;
+        e = cudaGraphInstantiate(&ex, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { cudaGetLastError(); _iter = it; run(); return 0; }
+        _graph_exec = ex; memcpy(_graph_key, key, sizeof(key));
+        _iter = it;                                   // the captured run did not execute; the launch below is the step
+    }
+    _iter++;
+    return (int)cudaGraphLaunch((cudaGraphExec_t)_graph_exec, st);
+}
+
+} // namespace t4
+
+// =============================================================================== flat C interface
+using namespace t4;
+#define TT(x) (*(Tensor*)(x))
+#define MM(x) (*(Model*)(x))
+extern "C" {
+const char *t4h_last_error(void) { return Runtime::last_error(); }
+int   t4h_init(int device) { return Runtime::init(device); }
+void *t4h_stream(void) { return Runtime::stream(); }
+int   t4h_sync(void) { return Runtime::sync(); }
+long  t4h_launch_count(void) { return t4k_launch_count(); }
+
+t4h_tensor t4h_tensor_new(int rank, uint32_t n, uint32_t h, uint32_t w, uint32_t c) {
+    if (Runtime::init(0)) return nullptr;
+    Tensor *t = rank == 1 ? &Tensor::create((U64)h) : rank == 2 ? &Tensor::create(h, w) : &Tensor::create(n, h, w, c);
+    if (!t->data) { delete t; return nullptr; }
+    return (t4h_tensor)t;
+}
+void  t4h_tensor_free(t4h_tensor t) { if (t) Tensor::destroy(TT(t)); }
+float *t4h_tensor_data(t4h_tensor t) { return TT(t).data; }
+int   t4h_tensor_shape(t4h_tensor t, uint32_t nhwc[4]) { nhwc[0] = TT(t).N(); nhwc[1] = TT(t).H(); nhwc[2] = TT(t).W(); nhwc[3] = TT(t).C(); return 0; }
+int64_t t4h_tensor_numel(t4h_tensor t) { return (int64_t)TT(t).numel; }
+int   t4h_tensor_rank(t4h_tensor t) { return (int)TT(t).rank; }
+int   t4h_tensor_h2d(t4h_tensor t, const float *src, int64_t n) { return TT(t).h2d(src, n); }
+int   t4h_tensor_d2h(t4h_tensor t, float *dst, int64_t n) { return TT(t).d2h(dst, n); }
+int   t4h_tensor_reshape(t4h_tensor t, int rank, uint32_t n, uint32_t h, uint32_t w, uint32_t c) {
+    Tensor &x = TT(t); const U64 want = rank == 1 ? h : rank == 2 ? (U64)h * w : (U64)n * h * w * c;
+    if (want != x.numel) { if (rank == 1) x.reshape((U64)h); else if (rank == 2) x.reshape(h, w); else x.reshape(n, h, w, c); return T4K_EINVAL; }
+    if (rank == 1) x.reshape((U64)h); else if (rank == 2) x.reshape(h, w); else x.reshape(n, h, w, c);
+    return 0;
+}
+t4h_tensor t4h_tensor_copy(t4h_tensor t) { return (t4h_tensor)&Tensor::copy_of(TT(t)); }
+int   t4h_tensor_map(t4h_tensor t, int op, float v) { return t4k_map(op, TT(t).data, v, TT(t).numel, Runtime::stream()); }
+int   t4h_tensor_identity(t4h_tensor t) { TT(t).identity(); return 0; }
+int   t4h_tensor_rand(t4h_tensor t, int opt) { return t4k_rand(TT(t).data, TT(t).numel, opt, 0.0f, 1.0f, Runtime::stream()); }
+int   t4h_ten_op_s(int op, t4h_tensor A, float v, t4h_tensor O) { return t4k_ts_op(op, TT(A).data, v, TT(O).data, TT(A).numel, Runtime::stream()); }
+int   t4h_ten_op_t(int op, t4h_tensor A, t4h_tensor B, t4h_tensor O) {
+    Tensor &a = TT(A), &b = TT(B), &o = TT(O);
+    if (a.HWC() != b.HWC() || (a.N() == 1 ? b.numel : a.numel) != o.numel) { Tensor::ten_op((math_op)op, a, b, o); return T4K_EINVAL; }
+    return t4k_tt_op(op, a.data, b.data, o.data, a.HWC(), a.N(), b.N(), Runtime::stream());
+}
+int   t4h_mm(t4h_tensor A, t4h_tensor B, t4h_tensor O, int inc, int tA, int tB) { Tensor::mm(TT(A), TT(B), TT(O), inc, tA, tB); return 0; }
+int   t4h_gemm(int variant, t4h_tensor A, t4h_tensor B, t4h_tensor O, float alpha, float beta, int tA, int tB) {
+    switch (variant) { case 1: Tensor::gemm1(TT(A), TT(B), TT(O), alpha, beta, tA, tB); break; case 2: Tensor::gemm2(TT(A), TT(B), TT(O), alpha, beta, tA, tB); break;
+                       case 4: Tensor::gemm4(TT(A), TT(B), TT(O), alpha, beta, tA, tB); break; default: Tensor::gemm3(TT(A), TT(B), TT(O), alpha, beta, tA, tB); }
+    return 0;
+}
+t4h_tensor t4h_matmul(t4h_tensor A_, t4h_tensor B_) {                     // TensorVM::_tdot, tenvm.cpp:329-367
+    Tensor &A = TT(A_), &B = TT(B_);
+    U32 Na = A.N(), Ha = A.H(), Wa = A.W(), Ca = A.C(), Nb = B.N(), Hb = B.H(), Wb = B.W(), Cb = B.C();
+    if (B.rank == 1 && A.rank != 1 && Wa == B.numel) { Tensor &C = Tensor::create((U64)Ha); Tensor::mm(A, B, C); return (t4h_tensor)&C; }
+    if (A.rank == 2 && B.rank == 2 && Wa == Hb)       { Tensor &C = Tensor::create(Ha, Wb); Tensor::mm(A, B, C); return (t4h_tensor)&C; }
+    if ((Na == 1 || Nb == 1) && Na != Nb && Ca == Cb && Wa == Hb) {
+        Tensor &C = Tensor::create(std::max(Na, Nb), Ha, Wb, Ca); Tensor::mm(A, B, C); return (t4h_tensor)&C;
+    }
+    Runtime::error("A.W != B.H dim?");
+    return nullptr;
+}
+t4h_tensor t4h_transpose(t4h_tensor A_) {                                 // blas1(T_XPOS), tenvm.cpp:128-130
+    Tensor &A = TT(A_); Tensor &T = Tensor::copy_of(A);
+    if (A.rank == 2) T.reshape(A.W(), A.H()); else T.reshape(A.N(), A.W(), A.H(), A.C());
+    Tensor::transpose(A, T); return (t4h_tensor)&T;
+}
+float t4h_tensor_sum(t4h_tensor t)  { return TT(t).sum(); }
+float t4h_tensor_avg(t4h_tensor t)  { return TT(t).avg(); }
+float t4h_tensor_std(t4h_tensor t)  { return TT(t).std(); }
+float t4h_tensor_norm(t4h_tensor t) { return TT(t).norm(); }
+float t4h_tensor_max(t4h_tensor t)  { return TT(t).max(); }
+float t4h_tensor_min(t4h_tensor t)  { return TT(t).min(); }
+float t4h_tensor_dot(t4h_tensor A, t4h_tensor B) { return TT(A).dot(TT(B)); }
+float t4h_tensor_loss(t4h_tensor o, int op, t4h_tensor tgt) { return TT(o).loss((t4_loss)op, TT(tgt)); }
+
+t4h_model t4h_model_new(uint32_t n, uint32_t h, uint32_t w, uint32_t c) { if (Runtime::init(0)) return nullptr; return (t4h_model) new Model(n, h, w, c); }
+void  t4h_model_free(t4h_model m) { delete (Model*)m; }
+int   t4h_model_add(t4h_model m, int layer, uint32_t n, float bias, const uint16_t *opt) {
+    U16 o[4]; if (opt) memcpy(o, opt, sizeof(o));
+    const U64 before = MM(m).numel();
+    MM(m).add((t4_layer)layer, n, bias, opt ? o : nullptr);
+    return MM(m).numel() > before ? 0 : T4K_ENOSUP;
+}
+int   t4h_model_numel(t4h_model m) { return (int)MM(m).numel(); }
+t4h_tensor t4h_model_layer(t4h_model m, int i) {
+    const int n = (int)MM(m).numel(); const int k = i < 0 ? n + i : i;
+    return (k < 0 || k >= n) ? nullptr : (t4h_tensor)&MM(m)[i];
+}
+t4h_tensor t4h_model_param(t4h_model m, int i, int which) {              // NetVM::_get_parm, netvm.cpp:153-166
+    t4h_tensor L = t4h_model_layer(m, i);
+    if (!L || which < 0 || which > 4) return nullptr;
+    Tensor &t = TT(L);
+    Tensor *p = which ? t.grad[which] : (t.grad[0] ? t.grad[0] : t.grad[4]);
+    return (t4h_tensor)p;
+}
+int   t4h_model_set_param(t4h_model m, int i, int which, t4h_tensor src) {   // NetVM::_set_parm, netvm.cpp:171-193
+    Tensor *p = (Tensor*)t4h_model_param(m, i, which);
+    if (!p || !src || TT(src).numel != p->numel) { Runtime::error("Tensor and model parameter is not the same shape"); return T4K_EINVAL; }
+    Tensor::copy(TT(src), *p);
+    return 0;
+}
+int   t4h_model_train(t4h_model m, int on) { MM(m).train = on != 0; return 0; }
+int   t4h_model_forward(t4h_model m, t4h_tensor input) {
+    Tensor &n0 = MM(m)[0];
+    if (TT(input).numel != n0.numel) { MM(m).forward(TT(input)); return T4K_EINVAL; }
+    MM(m).forward(TT(input)); return 0;
+}
+int   t4h_model_backprop(t4h_model m, t4h_tensor tgt) {
+    if (!tgt) { MM(m).backprop(); return 0; }
+    if (TT(tgt).numel != MM(m)[-1].numel) { MM(m).backprop(TT(tgt)); return T4K_EINVAL; }
+    MM(m).backprop(TT(tgt)); return 0;
+}
+float t4h_model_loss(t4h_model m, int op, t4h_tensor tgt) { return tgt ? MM(m).loss((t4_loss)op, TT(tgt)) : MM(m).loss((t4_loss)op); }
+int   t4h_model_loss_async(t4h_model m, int op, t4h_tensor tgt, float *loss_dev) { return MM(m).loss_async((t4_loss)op, TT(tgt), loss_dev); }
+int   t4h_model_onehot_labels(t4h_model m, const int32_t *labels_dev) { MM(m).onehot_labels(labels_dev); return 0; }
+int   t4h_model_onehot_set(t4h_model m, t4h_tensor hot) { MM(m).onehot(TT(hot)); return 0; }
+int   t4h_model_hit(t4h_model m, int recalc) { return MM(m).hit(recalc != 0); }
+int   t4h_model_sgd(t4h_model m, float lr, float b) { MM(m).sgd(lr, b); return 0; }
+int   t4h_model_adam(t4h_model m, float lr, float b1, float b2) { MM(m).adam(lr, b1, b2); return 0; }
+int   t4h_model_adamw(t4h_model m, float lr, float wd, float b1, float b2) { MM(m).adamw(lr, wd, b1, b2); return 0; }
+int   t4h_model_arena(t4h_model m, float **G, float **DG, int64_t *total) { return MM(m).arena(G, DG, total); }
+int   t4h_model_step_graph(t4h_model m, t4h_tensor input, t4h_tensor tgt, int lop, float *loss_dev, int optimizer, float lr, float b1, float b2, float wd) {
+    return MM(m).step_graph(TT(input), TT(tgt), (t4_loss)lop, loss_dev, (t4_optimizer)optimizer, lr, b1, b2, wd);
+}
+} // extern "C"

@@ -1,0 +1,198 @@
+// t4host.hpp — host-side mirror of the reference's Tensor / Model class surface
+//   t4::Tensor  ←→  src/mu/tensor.h:51-190   (struct Tensor : T4Base)
+//   t4::Model   ←→  src/nn/model.h:36-164    (class Model : T4Base)
+// Same method names, argument order and meaning; the bodies call the kernel C-ABI (include/t4k.h)
+// instead of launching FORK*() kernels + cudaDeviceSynchronize().  Everything above this file in the
+// reference (Forth VMs, MMU/TLSF, IO, TensorBoard) is a caller of exactly these methods.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+#include "../../../include/t4k.h"
+
+namespace t4 {
+
+typedef float    DU;
+typedef uint64_t U64;
+typedef uint32_t U32;
+typedef uint16_t U16;
+typedef int32_t  S32;
+
+typedef enum t4k_math_op math_op;
+typedef enum t4k_layer   t4_layer;
+typedef enum t4k_loss    t4_loss;      // `enum` tag: t4k_loss is also the C-ABI function name
+typedef enum { OPTI_SGD = 0, OPTI_SGDM, OPTI_ADAM, OPTI_ADAMW } t4_optimizer;   // src/nn/ntypes.h:57-62
+
+#define T4_DIM_SZ 16
+#define DU_EPS_H  1.0e-6f
+
+// process-wide runtime: device, stream, error slot (src/ten4.cu:125-176 keeps these in TensorForth)
+struct Runtime {
+    static int   init(int device);
+    static void *stream();
+    static int   sync();
+    static void  error(const char *fmt, ...);          // ERROR(...) of src/ten4_types.h:25
+    static const char *last_error();
+    static void *alloc(size_t bytes);                  // stream-ordered pool (replaces MMU::talloc)
+    static void  free(void *p);
+};
+
+struct Tensor {
+    // ---- T4Base (src/t4base.h:50-115)
+    U64      numel = 0;
+    U32      rank  = 0;
+    U32      iparm = 0;
+    bool     train = false, err = false;
+    DU       xparm = 0;
+    DU      *data  = nullptr;          ///< device memory (numel + 1 floats: _tmp scratch at data[numel])
+    // ---- Tensor (src/mu/tensor.h:52-58)
+    U16      stride[4] = {1, 1, 1, 1}; ///< [strideH, strideW, paddingH, paddingW]
+    U32      shape[4]  = {1, 1, 1, 1}; ///< HWCN
+    t4_layer grad_fn   = T4K_L_NONE;
+    Tensor  *grad[5]   = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    Tensor  *mtum[5]   = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    DU      *_tmp      = nullptr;
+    bool     owns      = true;         ///< false for views into a parameter arena
+
+    // life cycle (MMU::tensor / MMU::free, src/mu/mmu.cu:211-268)
+    static Tensor &create(U64 sz);
+    static Tensor &create(U32 h, U32 w);
+    static Tensor &create(U32 n, U32 h, U32 w, U32 c);
+    static Tensor &create_like(Tensor &t);
+    static Tensor &copy_of(Tensor &t);                 ///< MMU::copy (hard copy)
+    static void    destroy(Tensor &t);
+
+    // static ops — result tensor is the last parameter and is returned (tensor.h:59-80)
+    static Tensor &ten_op(math_op op, Tensor &A, DU v, Tensor &O);
+    static Tensor &ten_op(math_op op, Tensor &A, Tensor &B, Tensor &O);
+    static Tensor &dot(Tensor &A, Tensor &B, Tensor &O, DU alpha, DU beta);
+    static Tensor &mm(Tensor &A, Tensor &B, Tensor &O, bool inc = 0, bool tA = 0, bool tB = 0);
+    static Tensor &linear(Tensor &A, Tensor &B, Tensor &O, int H, int W, int K, DU alpha, DU beta, bool tA = 0, bool tB = 0);
+    static Tensor &gemm1(Tensor &A, Tensor &B, Tensor &O, DU alpha, DU beta, bool tA = 0, bool tB = 0);
+    static Tensor &gemm2(Tensor &A, Tensor &B, Tensor &O, DU alpha, DU beta, bool tA = 0, bool tB = 0);
+    static Tensor &gemm3(Tensor &A, Tensor &B, Tensor &O, DU alpha, DU beta, bool tA = 0, bool tB = 0);
+    static Tensor &gemm4(Tensor &A, Tensor &B, Tensor &O, DU alpha, DU beta, bool tA = 0, bool tB = 0);
+    static Tensor &copy(Tensor &A, Tensor &O);
+    static Tensor &transpose(Tensor &A, Tensor &T);
+
+    // attributes (tensor.h:106-122)
+    U32 &N() { return shape[3]; }
+    U32 &H() { return shape[0]; }
+    U32 &W() { return shape[1]; }
+    U32 &C() { return shape[2]; }
+    U64  HWC() { return (U64)shape[0] * shape[1] * shape[2]; }
+    U64  size() { return HWC() * N(); }
+    DU  *slice(int n) { return &data[HWC() * n]; }
+    bool is_same_shape(Tensor &t);
+
+    // arithmetics (tensor.h:126-135); host scalars → these synchronise
+    DU  sum();  DU avg();  DU std();  DU norm();  DU max();  DU min();
+    DU  dot(Tensor &B);
+    DU  loss(t4_loss op, Tensor &tgt);
+    U32 has_nan();
+
+    // life-cycle ops (tensor.h:144-153)
+    Tensor &reset(void *mem, U64 sz, t4_layer fn = T4K_L_NONE);
+    Tensor &reshape(U64 sz);
+    Tensor &reshape(U32 h, U32 w);
+    Tensor &reshape(U32 n, U32 h, U32 w, U32 c);
+    Tensor &identity();
+    Tensor &zeros();
+    Tensor &map(math_op op, DU v = 0.0f);
+    Tensor &normalize(DU avg, DU std);
+
+    // operators (tensor.h:166-180)
+    Tensor &operator=(DU v)       { return map(T4K_FILL, v); }
+    Tensor &operator+=(DU v)      { return map(T4K_ADD, v); }
+    Tensor &operator-=(DU v)      { return map(T4K_SUB, v); }
+    Tensor &operator*=(DU v)      { return map(T4K_MUL, v); }
+    Tensor &operator=(Tensor &t)  { copy(t, *this); return *this; }
+    Tensor &operator+=(Tensor &t) { return ten_op(T4K_ADD, *this, t, *this); }
+    Tensor &operator-=(Tensor &t) { return ten_op(T4K_SUB, *this, t, *this); }
+    Tensor &operator*=(Tensor &t) { return ten_op(T4K_MUL, *this, t, *this); }
+
+    // host <-> device (replaces the VM's direct pokes into managed memory, tenvm.cpp:535-541)
+    int h2d(const DU *h, U64 n = 0);
+    int d2h(DU *h, U64 n = 0);
+private:
+    Tensor &_gemm(int engine, Tensor &A, Tensor &B, Tensor &O, DU alpha, DU beta, bool tA, bool tB, const char *nm);
+};
+
+class Model {
+    int     _hit  = 0;
+    int     _iter = 0;
+    Tensor *_hot  = nullptr;           ///< cached one-hot vector
+    bool    _own_hot = false;
+    int    *_cnt_dev = nullptr;        ///< device int for hit()
+    // flat parameter arenas (B200-first: one optimizer launch / one all-reduce for the whole model)
+    DU     *_G = nullptr, *_DG = nullptr, *_M = nullptr, *_V = nullptr;
+    U64     _total = 0;
+    void   *_seg_dev = nullptr; int _nseg = 0;
+    t4_optimizer _arena_opt = OPTI_SGD;
+    // captured train step
+    void   *_graph_exec = nullptr; U64 _graph_key[8] = {0};
+    std::vector<Tensor*> _layers;      ///< layer i holds that layer's INPUT; last = output
+public:
+    int  epoch    = 0;
+    DU   max_norm = 0;
+    bool train    = true;
+    bool err      = false;
+    U64  numel() { return _layers.size(); }
+
+    Model(U32 n, U32 h, U32 w, U32 c);                       ///< `nn.model` (netvm.cpp:301-311)
+    ~Model();
+    void tick() { epoch++; _iter = 0; }
+    Tensor &operator[](S32 i);
+    int     batch_size();
+    // main NN methods (model.h:85-91)
+    Model &add(t4_layer fn, U32 n = 0, DU alpha = 0.0f, U16 *opt = nullptr);
+    Model &forward(Tensor &input);
+    Model &backprop();
+    Model &backprop(Tensor &tgt);
+    // loss functions (model.h:95-100)
+    Tensor &onehot();
+    Tensor &onehot(Tensor &t);
+    Tensor &onehot_labels(const int32_t *labels_dev);        ///< Model::onehot(Dataset&) with device labels
+    int     hit(bool recalc = true);
+    DU      loss(t4_loss op);
+    DU      loss(t4_loss op, Tensor &tgt);
+    int     loss_async(t4_loss op, Tensor &tgt, DU *loss_dev);
+    // gradient descent (model.h:103-111)
+    Model &grad_zero() { _iter = _hit = 0; return *this; }
+    Model &grad_alloc(t4_optimizer op);
+    Model &sgd(DU lr, DU b = 0.9f);
+    Model &adam(DU lr, DU b1 = 0.9f, DU b2 = 0.999f);
+    Model &adamw(DU lr, DU wd = 0.001f, DU b1 = 0.9f, DU b2 = 0.999f);
+    int    arena(DU **G, DU **DG, int64_t *total);
+    int    step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd);
+private:
+    void _iconv(Tensor &in, U32 c, DU bias, U16 *opt);
+    void _ilinear(Tensor &in, U32 n, DU bias);
+    void _iflatten(Tensor &in);
+    void _isoftmax(Tensor &in);
+    void _iactivate(Tensor &in, DU alpha);
+    void _ipool(Tensor &in, U16 f);
+    void _ibatchnorm(Tensor &in, DU m);
+    void _iup(Tensor &in, U16 f, DU m);
+    void _fstep(Tensor &in, Tensor &out);
+    int  _fconv(Tensor &in, Tensor &out);
+    int  _flinear(Tensor &in, Tensor &out);
+    int  _factivate(Tensor &in, Tensor &out, t4_layer fn);
+    int  _fpool(Tensor &in, Tensor &out, t4_layer fn);
+    int  _fsoftmax(Tensor &in, Tensor &out);
+    int  _flogsoftmax(Tensor &in, Tensor &out);
+    int  _fbatchnorm(Tensor &in, Tensor &out);
+    int  _fupsample(Tensor &in, Tensor &out);
+    int  _bprep(Tensor &tgt);
+    void _bstep(Tensor &in, Tensor &out, bool last_layer);
+    int  _bconv(Tensor &in, Tensor &out);
+    int  _blinear(Tensor &in, Tensor &out);
+    int  _bactivate(Tensor &in, Tensor &out);
+    int  _bpool(Tensor &in, Tensor &out, t4_layer fn);
+    int  _bupsample(Tensor &in, Tensor &out, t4_layer fn);
+    int  _bbatchnorm(Tensor &in, Tensor &out);
+    Model &_gradient(t4_optimizer op, DU lr, DU b1, DU b2, DU wd);
+    void _RAND(Tensor &t, DU scale);
+};
+
+} // namespace t4

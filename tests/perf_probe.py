@@ -1,0 +1,57 @@
+"""quick device-timed probes of individual C-ABI calls (development aid; bench.py is the contract)"""
+import ctypes as C
+import sys
+import torch
+from tensorforth_b200 import lib as t4
+
+L = t4.load()
+
+
+def p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def gemm(n, engine=t4.GEMM_AUTO):
+    A = torch.rand(n, n, device="cuda") - 0.5
+    B = torch.rand(n, n, device="cuda") - 0.5
+    O = torch.zeros(n, n, device="cuda")
+    ms = timeit(lambda: t4.check(L.t4k_gemm_ex(engine, p(A), p(B), p(O), 1.0, 0.0, 0, 0, n, n, n, 1, 1, 0, 0, 0, None)))
+    print("gemm %d^3 engine=%d: %.3f ms  %.1f TFLOP/s" % (n, engine, ms, 2 * n ** 3 / ms / 1e9))
+    ms = timeit(lambda: torch.matmul(A, B, out=O))
+    print("   torch fp32 matmul (cuBLAS, reference point only): %.3f ms  %.1f TFLOP/s" % (ms, 2 * n ** 3 / ms / 1e9))
+
+
+def stream(n=1 << 28):
+    a = torch.rand(n, device="cuda"); b = torch.empty_like(a)
+    ms = timeit(lambda: t4.check(L.t4k_copy(p(a), p(b), n, None)))
+    print("copy %d MiB: %.3f ms  %.0f GB/s" % (n * 4 >> 20, ms, 2 * n * 4 / ms / 1e6))
+    ms = timeit(lambda: t4.check(L.t4k_map(t4.RELU, p(a), 0.0, n, None)))
+    print("map relu in place: %.3f ms  %.0f GB/s" % (ms, 2 * n * 4 / ms / 1e6))
+    o = torch.zeros(4, device="cuda")
+    ms = timeit(lambda: t4.check(L.t4k_sum(p(a), n, p(o), None)))
+    print("sum: %.3f ms  %.0f GB/s" % (ms, n * 4 / ms / 1e6))
+    ms = timeit(lambda: b.copy_(a))
+    print("   torch copy_: %.3f ms  %.0f GB/s" % (ms, 2 * n * 4 / ms / 1e6))
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("all", "gemm"):
+        for n in (1024, 2048, 4096, 8192):
+            gemm(n, t4.GEMM_TC)
+        gemm(1024, t4.GEMM_SIMT); gemm(4096, t4.GEMM_SIMT)
+    if what in ("all", "stream"):
+        stream()

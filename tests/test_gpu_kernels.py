@@ -220,7 +220,9 @@ def test_gemm_4096_property():
     assert torch.equal(o2, 2 * o1)                        # exact: scaling by 2 commutes with rounding
     rs = o1.double().sum(1).cpu().numpy()
     ref = (A.double() @ B.double().sum(1)).cpu().numpy()
-    assert_close(rs, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+    # a row sum adds 4096 elements whose FP32-grade errors (~2e-6 rel, tensor-core accumulation
+    # truncates toward zero so they do not cancel) → 1e-4 of the largest row sum
+    assert_close(rs, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
     # spot-check 64 full rows against float64
     idx = torch.arange(0, n, 64, device="cuda")
     ref_rows = (A[idx].double() @ B.double()).cpu().numpy()

@@ -1,0 +1,263 @@
+"""
+-m gpu Model-level parity: the host mirror (libt4host.so: t4::Tensor / t4::Model) driven exactly as
+the reference's example scripts drive the VM, checked against (a) the scripts' own `verify`
+numbers and (b) the oracle's Model restatement on the same injected weights (the
+reference's RNG is time-seeded, so parity tests inject parameters with nn.w= / nn.b=, as
+examples/t4_30b.4th:11-20 does).
+"""
+import ctypes as C
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tensorforth_b200 import lib as t4
+from tensorforth_b200 import host as th
+from gpu_util import assert_close
+
+pytestmark = pytest.mark.gpu
+A4 = 6e-5            # half-ulp of the reference's %+.4f print
+
+
+def close4(a, b, atol=A4):
+    np.testing.assert_allclose(np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel(), rtol=0, atol=atol)
+
+
+# ------------------------------------------------------------------ examples/t4_20a.4th (tensor words)
+def test_t4_20a_tensor_words():
+    A = th.Tensor.matrix(2, 3, [1, 2, 3, 4, 5, 6])
+    B = th.Tensor.matrix(3, 2).ones()
+    close4((A @ B).numpy(), [[6, 6], [15, 15]], 0)                           # :2-9
+    R = th.Tensor.matrix(512, 1024).rand()
+    O = R @ th.Tensor.matrix(1024, 256).ones()
+    O /= 1024.0                                                               # :12-16
+    r = R.numpy().astype(np.float64).mean(1)
+    assert_close(O.numpy(), np.repeat(r[:, None], 256, 1), rtol=1e-5)
+    X = th.Tensor.matrix(2, 3, [1, 2, 3, 4, 5, 6]); Y = th.Tensor.matrix(2, 3).ones()
+    X += Y; close4(X.numpy(), [[2, 3, 4], [5, 6, 7]], 0)                      # :45-51
+    X -= Y; X -= Y; close4(X.numpy(), [[0, 1, 2], [3, 4, 5]], 0)              # :53-55
+    P = th.Tensor.matrix(2, 3, [1, 2, 3, 0, 4, 5]) @ th.Tensor.matrix(3, 2).ones()
+    close4(P.numpy(), [[6, 6], [9, 9]], 0)                                    # :57-62
+    Hh = th.Tensor.matrix(2, 2).ones(); Hh *= 0.5; P *= Hh
+    close4(P.numpy(), [[3, 3], [4.5, 4.5]], 0)                                # :64-68
+    with pytest.raises(t4.T4KError):
+        th.Tensor.matrix(2, 3) @ th.Tensor.matrix(2, 3)                       # "A.W != B.H dim?"
+
+
+def test_tensor_reductions_and_words():
+    a = np.random.default_rng(3).random(5000, dtype=np.float32) - 0.5
+    T = th.Tensor.vector(a.size, a)
+    assert_close(T.sum(), orc.tsum(a), rtol=1e-4, atol=1e-3)
+    assert_close(T.avg(), orc.avg(a), rtol=1e-4, atol=1e-6)
+    assert_close(T.std(), orc.std(a), rtol=1e-4)
+    assert_close(T.norm(), orc.norm(a), rtol=1e-4)
+    assert abs(T.max() - a.max()) <= abs(a.max()) * 2e-7 and abs(T.min() - a.min()) <= abs(a.min()) * 2e-7   # SCALAR() clears bit 0
+    assert_close(T.dot(T), float(np.dot(a.astype(np.float64), a.astype(np.float64))), rtol=1e-4)
+    M = th.Tensor.matrix(3, 5, np.arange(15)); Mt = M.transpose()
+    assert Mt.shape[1:3] == (5, 3) and np.array_equal(Mt.numpy(), np.arange(15, dtype=np.float32).reshape(3, 5).T)
+    E = th.Tensor.matrix(4, 4).eye()
+    assert np.array_equal(E.numpy(), np.eye(4, dtype=np.float32))
+    G = th.gemm(3, M, Mt, th.Tensor.matrix(3, 3).ones(), 2.0, 0.5)
+    m = np.arange(15, dtype=np.float64).reshape(3, 5)
+    assert_close(G.numpy(), 2 * m @ m.T + 0.5, rtol=1e-5)
+
+
+# ------------------------------------------------------------------ examples/t4_30a.4th
+def test_t4_30a_linear_forward():
+    nn = th.Model(1, 1, 2, 1).linear(3)
+    nn.set_w(0, 0.1 * np.array([[1, 2], [3, 4], [5, 6]], np.float32)).set_b(0, [1, 2, 3])
+    close4(nn.w(0).numpy(), 0.1 * np.array([1, 2, 3, 4, 5, 6]), 1e-7)
+    nn.forward(th.Tensor.vector(2, [10, 20]))
+    close4(nn.layer(-1).numpy(), [6, 13, 20], 1e-5)
+
+
+# ------------------------------------------------------------------ examples/t4_30b.4th / t4_30c.4th
+def mazur(N, hidden):
+    return th.Model(N, 1, 2, 1).linear(hidden).sigmoid().linear(2).sigmoid()
+
+
+def test_t4_30b_mazur_n1():
+    nn = mazur(1, 3)
+    nn.set_w(0, [0.15, 0.2, 0.25, 0.3, 0.2, 0.15]).set_b(0, [0.35] * 3)
+    nn.set_w(2, [0.4, 0.45, 0.5, 0.55, 0.5, 0.45]).set_b(2, [0.6] * 2)
+    nn.forward(th.Tensor.vector(2, [0.05, 0.1]))
+    close4(nn.layer(1).numpy(), [0.3775, 0.3925, 0.3750])
+    close4(nn.w(1).numpy(), [0.2413, 0.2406, 0.2414])                        # `1 nn.w` on a sigmoid layer → its filter grad[4]
+    close4(nn.layer(2).numpy(), [0.5933, 0.5969, 0.5927])
+    close4(nn.layer(3).numpy(), [1.4022, 1.4914])
+    close4(nn.w(3).numpy(), [0.1585, 0.1500])
+    close4(nn.layer(4).numpy(), [0.8025, 0.8163])
+    tgt = th.Tensor.vector(2, [0.01, 0.99])
+    close4(nn.loss(t4.LOSS_MSE, tgt), 0.658292, 2e-6)
+    nn.backprop(tgt)
+    close4(nn.layer(4).numpy(), [0.7925, -0.1737]); close4(nn.layer(3).numpy(), [0.7925, -0.1737])
+    close4(nn.db(2).numpy(), [0.7925, -0.1737])
+    close4(nn.dw(2).numpy(), [0.4702, 0.4731, 0.4697, -0.1031, -0.1037, -0.1029])
+    close4(nn.layer(2).numpy(), [0.2215, 0.2698, 0.3181]); close4(nn.layer(1).numpy(), [0.2215, 0.2698, 0.3181])
+    close4(nn.db(0).numpy(), [0.2215, 0.2698, 0.3181])
+    close4(nn.dw(0).numpy(), [0.0111, 0.0221, 0.0135, 0.0270, 0.0159, 0.0318])
+    close4(nn.layer(0).numpy(), [0.1643, 0.1729])
+    nn.sgd(0.5, 0.0)
+    close4(nn.w(2).numpy(), [0.1649, 0.2135, 0.2651, 0.6015, 0.5518, 0.5015])
+    close4(nn.b(2).numpy(), [0.2037, 0.6869])
+    assert not nn.dw(2).numpy().any() and not nn.db(2).numpy().any()
+    close4(nn.w(0).numpy(), [0.1445, 0.1889, 0.2433, 0.2865, 0.1920, 0.1341])      # the script's `verify` line
+    close4(nn.b(0).numpy(), [0.2393, 0.2151, 0.1909])
+
+
+def test_t4_30c_mazur_n3():
+    nn = mazur(3, 2)
+    nn.set_w(0, [0.15, 0.2, 0.25, 0.3]).set_b(0, [0.35] * 2).set_w(2, [0.4, 0.45, 0.5, 0.55]).set_b(2, [0.6] * 2)
+    nn.forward(th.Tensor.vector(6, [0.05, 0.1] * 3))                          # auto-reshaped: numel check only
+    close4(nn.layer(4).numpy(), [0.7514, 0.7729] * 3)
+    tgt = th.Tensor.vector(6, [0.01, 0.99] * 3).reshape(3, 1, 2, 1)
+    close4(nn.loss(t4.LOSS_MSE, tgt), 0.596742, 2e-6)
+    nn.backprop(tgt)
+    close4(nn.db(0).numpy(), [0.5640, 0.6427]); close4(nn.dw(0).numpy(), [0.0282, 0.0564, 0.0321, 0.0643])
+    close4(nn.layer(0).numpy(), [0.0818, 0.1019] * 3)
+    nn.sgd(0.5, 0.0)
+    close4(nn.w(0).numpy(), [0.1359, 0.1718, 0.2339, 0.2679]); close4(nn.b(0).numpy(), [0.0680, 0.0287])
+
+
+# ------------------------------------------------------------------ model vs oracle with injected parameters
+def inject(gm, om):
+    """copy the oracle model's (seeded) parameters into the GPU model with nn.w= / nn.b="""
+    for i, L in enumerate(om.layers[:-1]):
+        if L.w is not None and L.dw is not None:
+            gm.set_w(i, L.w.ravel()); gm.set_b(i, L.b.ravel())
+
+
+def compare_layers(gm, om, what, rtol=1e-4):
+    for i, L in enumerate(om.layers):
+        assert_close(gm.layer(i).numpy(), L.data, rtol=rtol, what="%s layer %d" % (what, i))
+
+
+def compare_params(gm, om, what, grads=True, rtol=1e-4, w_atol=0.0):
+    """w_atol: absolute slack on weights after an Adam step.  Adam without bias correction
+    (nmath.cu:438-454) moves a weight by lr*m/(sqrt(v)+1e-6); for |dg| ~ 1e-5 that quotient has
+    slope 1e5 in dg, so FP32 summation-order noise of 1e-8 in a gradient shows up as lr*1e-3 in w.
+    Gradients whose exact value is 0 (conv bias in front of a batch-norm) are pure rounding noise:
+    compared with an absolute floor tied to the layer's weight-gradient scale."""
+    for i, L in enumerate(om.layers[:-1]):
+        if L.w is not None and L.dw is not None:
+            rw = np.sqrt(np.mean(L.w.astype(np.float64) ** 2))
+            assert_close(gm.w(i).numpy(), L.w, rtol=rtol, atol=rtol * rw + w_atol, what="%s w%d" % (what, i))
+            assert_close(gm.b(i).numpy(), L.b, rtol=rtol, atol=rtol * rw + w_atol, what="%s b%d" % (what, i))
+            if grads:
+                floor = 1e-5 * (np.sqrt(np.mean(L.dw.astype(np.float64) ** 2)) + 1e-3)
+                assert_close(gm.dw(i).numpy(), L.dw, rtol=rtol, what="%s dw%d" % (what, i))
+                rb = np.sqrt(np.mean(L.db.astype(np.float64) ** 2))
+                assert_close(gm.db(i).numpy(), L.db, rtol=rtol, atol=rtol * rb + floor, what="%s db%d" % (what, i))
+
+
+def build_pair(kind, N):
+    if kind == "mnist":               # examples/t4_40a.4th:10-13
+        gm = th.mnist_cnn(N)
+        om = orc.OracleModel(N, 28, 28, 1, seed=5)
+        om.add(orc.L_CONV, 10, 0.5, [3, 1, 1, 1]).add(orc.L_MAXPOOL, 2).add(orc.L_RELU).add(orc.L_FLATTEN)
+        om.add(orc.L_LINEAR, 100, 1.0).add(orc.L_RELU).add(orc.L_LINEAR, 10, 1.0).add(orc.L_SOFTMAX)
+        shape, E, lop = (N, 28, 28, 1), 10, t4.LOSS_CE
+    elif kind == "toycnn":            # examples/t4_30d.4th:3-24 without dropout (RNG is not parity-comparable)
+        gm = (th.Model(N, 16, 16, 1).conv2d(0.5, 2).maxpool(2).relu().conv2d(0.5, 2).maxpool(2).relu()
+              .flatten().linear(16, 0.0).linear(4, 0.0).softmax())
+        om = orc.OracleModel(N, 16, 16, 1, seed=6)
+        om.add(orc.L_CONV, 2, 0.5, [3, 1, 1, 1]).add(orc.L_MAXPOOL, 2).add(orc.L_RELU)
+        om.add(orc.L_CONV, 2, 0.5, [3, 1, 1, 1]).add(orc.L_MAXPOOL, 2).add(orc.L_RELU)
+        om.add(orc.L_FLATTEN).add(orc.L_LINEAR, 16, 0.0).add(orc.L_LINEAR, 4, 0.0).add(orc.L_SOFTMAX)
+        shape, E, lop = (N, 16, 16, 1), 4, t4.LOSS_CE
+    elif kind == "gan_g":             # examples/t4_40b.4th:44-48
+        gm = th.gan_generator(N)
+        om = orc.OracleModel(N, 128, 1, 1, seed=7)
+        om.add(orc.L_LINEAR, 256, 1.0).add(orc.L_LEAKYRL, 0, 0.2).add(orc.L_LINEAR, 512, 1.0).add(orc.L_LEAKYRL, 0, 0.2)
+        om.add(orc.L_LINEAR, 784, 1.0).add(orc.L_TANH)
+        shape, E, lop = (N, 128, 1, 1), 784, t4.LOSS_MSE
+    elif kind == "bn":                # conv + batchnorm block as in examples/t4_30e.4th:28-31
+        gm = (th.Model(N, 8, 8, 3).conv2d(0.5, 6).batchnorm().relu().avgpool(2).flatten().linear(5).sigmoid())
+        om = orc.OracleModel(N, 8, 8, 3, seed=8)
+        om.add(orc.L_CONV, 6, 0.5, [3, 1, 1, 1]).add(orc.L_BATCHNM, 0, 0.1).add(orc.L_RELU).add(orc.L_AVGPOOL, 2)
+        om.add(orc.L_FLATTEN).add(orc.L_LINEAR, 5, 1.0).add(orc.L_SIGMOID)
+        shape, E, lop = (N, 8, 8, 3), 5, t4.LOSS_BCE
+    inject(gm, om)
+    return gm, om, shape, E, lop
+
+
+@pytest.mark.parametrize("kind,N", [("mnist", 8), ("mnist", 64), ("toycnn", 2), ("gan_g", 16), ("bn", 4)])
+@pytest.mark.parametrize("opt", ["sgd", "adam", "adamw"])
+def test_model_train_steps_vs_oracle(kind, N, opt):
+    rng = np.random.default_rng(11)
+    gm, om, shape, E, lop = build_pair(kind, N)
+    assert len(gm) == len(om.layers)
+    for step in range(3):
+        x = (rng.random(shape, dtype=np.float32) * 2 - 1).astype(np.float32)
+        if lop == t4.LOSS_MSE:
+            y = (rng.random((N, E), dtype=np.float32) * 2 - 1).astype(np.float32)
+        else:
+            y = orc.onehot(rng.integers(0, E, N), E)
+        X, Y = th.Tensor.from_numpy(x), th.Tensor.tensor(N, 1, E, 1, y)
+        gm.forward(X); om.forward(x)
+        compare_layers(gm, om, "%s fwd step %d" % (kind, step))
+        assert_close(gm.loss(lop, Y), om.loss(lop, y), rtol=1e-4, atol=1e-6, what="loss")    # north star: <= 1e-4 loss deviation
+        gm.backprop(Y); om.backprop(y)
+        compare_layers(gm, om, "%s bwd step %d" % (kind, step))
+        compare_params(gm, om, "%s bwd step %d" % (kind, step))
+        if opt == "sgd":
+            gm.sgd(0.05, 0.9); om.sgd(0.05, 0.9)              # momentum is forced to 0 on the first call (gradient.cu:139)
+        elif opt == "adam":
+            gm.adam(0.001); om.adam(0.001)
+        else:
+            gm.adamw(0.001, 0.01); om.adamw(0.001, 0.01)
+        compare_params(gm, om, "%s %s step %d" % (kind, opt, step), grads=False, w_atol=0.0 if opt == "sgd" else 0.05 * 0.001)
+        for i, L in enumerate(om.layers[:-1]):
+            if L.dw is not None and L.w is not None:
+                assert not gm.dw(i).numpy().any() and not gm.db(i).numpy().any()     # optimizers zero dG
+                # next step starts from identical parameters (Adam's 1/(sqrt(v)+eps) amplifies rounding noise, see compare_params)
+                L.w[...] = gm.w(i).numpy().reshape(L.w.shape); L.b[...] = gm.b(i).numpy().reshape(L.b.shape)
+
+
+def test_trainable_off_and_hit():
+    N = 16
+    gm, om, shape, E, lop = build_pair("mnist", N)
+    rng = np.random.default_rng(2)
+    x = rng.random(shape, dtype=np.float32); lab = rng.integers(0, E, N).astype(np.int32)
+    y = orc.onehot(lab, E)
+    gm.trainable(False); om.train = False
+    gm.forward(th.Tensor.from_numpy(x)); om.forward(x)
+    dl = torch.from_numpy(lab).cuda()
+    gm.onehot_labels(C.c_void_p(dl.data_ptr()))
+    assert gm.hit() == orc.hit(om.output().reshape(N, E), y)
+    assert_close(gm.loss(lop), om.loss(lop, y), rtol=1e-4)
+    gm.backprop(); om.backprop(y)
+    gm.adam(0.001); om.adam(0.001)
+    compare_params(gm, om, "not trainable")                   # dW stays 0, weights unchanged
+    compare_layers(gm, om, "not trainable bwd")
+
+
+def test_errors_mirror_reference():
+    nn = th.mnist_cnn(4)
+    with pytest.raises(t4.T4KError, match="wrong shape"):
+        nn.forward(th.Tensor.tensor(4, 28, 28, 2))            # forward.cu:33-38
+    with pytest.raises(t4.T4KError, match="Onehot wrong shape"):
+        nn.backprop(th.Tensor.vector(7))                      # backprop.cu:78-83
+    with pytest.raises(t4.T4KError):
+        th.Model(2, 8, 8, 1).maxpool(4)                       # model.cpp:262-265
+    with pytest.raises(t4.T4KError):
+        th.Model(2, 8, 8, 1).conv2d(0.5, 4, k=7)              # model.cpp:144-149
+
+
+def test_step_graph_equals_eager():
+    N = 32
+    rng = np.random.default_rng(4)
+    x = (rng.random((N, 28, 28, 1), dtype=np.float32) * 2 - 1).astype(np.float32); y = orc.onehot(rng.integers(0, 10, N), 10)
+    ga, om, *_ = build_pair("mnist", N)
+    gb, _, *_ = build_pair("mnist", N)
+    X, Y = th.Tensor.from_numpy(x), th.Tensor.tensor(N, 1, 10, 1, y)
+    la, lb = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    losses_a, losses_b = [], []
+    for step in range(5):
+        ga.forward(X); ga.loss_async(t4.LOSS_CE, Y, C.c_void_p(la.data_ptr())); ga.backprop(Y); ga.adam(0.001)
+        th.sync(); losses_a.append(float(la.cpu()[0]))
+        assert gb.step_graph(X, Y, t4.LOSS_CE, C.c_void_p(lb.data_ptr()), optimizer=2, lr=0.001) == 0
+        th.sync(); losses_b.append(float(lb.cpu()[0]))
+    assert losses_a == losses_b, (losses_a, losses_b)          # same kernels, same order → same bits
+    for i in (0, 4, 6):
+        assert np.array_equal(ga.w(i).numpy(), gb.w(i).numpy())
