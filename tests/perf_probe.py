@@ -1,7 +1,9 @@
 """quick device-timed probes of individual C-ABI calls (development aid; bench.py is the contract)"""
 import ctypes as C
 import sys
+import os
 import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tensorforth_b200 import lib as t4
 
 L = t4.load()
