@@ -129,6 +129,10 @@ int t4k_logsoftmax_fwd(const float *I, float *O, int N, int C, t4k_stream_t s);
  * (KS,S,P) in {(1,1,0),(3,1,1),(4,2,1),(5,1,2)} as in the reference, else T4K_ENOSUP. */
 int t4k_conv2d_fwd(const float *I, const float *F, const float *B, float *O,
                    int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, t4k_stream_t s);
+/* engine selection for conv2d fwd/bwd (tests, benchmarks): T4K_GEMM_AUTO (default: tcgen05 implicit GEMM when the
+ * shape is GEMM-sized — stride 1, "same" padding, C1 % 32 == 0, 16 <= C0 <= 128, C0 % 16 == 0 — else CUDA cores),
+ * T4K_GEMM_SIMT (never the tensor path), T4K_GEMM_TC (tensor path or T4K_EINVAL) */
+int t4k_set_conv_engine(int engine);
 /* k_pool<KS> (nmath.tcu:122-186, forward.cu:212-228; also upsample-backward backprop.cu:285-300)
  * layer in AVGPOOL,MAXPOOL,MINPOOL,USAMPLE; KS in {2,3}; stride == KS */
 int t4k_pool_fwd(int layer, const float *I, float *O, int N, int H1, int W1, int H0, int W0, int C, int KS, t4k_stream_t s);

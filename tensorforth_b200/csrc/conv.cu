@@ -328,6 +328,14 @@ __global__ void __launch_bounds__(T4K_THREADS) k_colsum_part_c(const float *__re
     }
 }
 
+bool conv_tc_ok(int H1, int W1, int CI, int H0, int W0, int CO, int KS, int S, int P);
+int  conv_tc(const float *X, const float *F, const float *bias, float *Y, int N, int H, int W, int C1, int C0,
+             int KS, int P, int mode, cudaStream_t st);
+int  conv_wgrad_tc(const float *I, const float *dO, float *dF, float *dB, int N, int H, int W, int C1, int C0,
+                   int KS, int P, cudaStream_t st);
+bool conv_wgrad_tc_ok(int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P);
+static int g_conv_engine = T4K_GEMM_AUTO;                 // t4k_set_conv_engine: AUTO / SIMT / TC
+
 static bool conv_cfg_ok(int KS, int S, int P) {           // forward.cu:142-151
     return (KS == 1 && S == 1 && P == 0) || (KS == 3 && S == 1 && P == 1) ||
            (KS == 4 && S == 2 && P == 1) || (KS == 5 && S == 1 && P == 2);
@@ -337,6 +345,10 @@ static bool conv_cfg_ok(int KS, int S, int P) {           // forward.cu:142-151
 using namespace t4k;
 
 // ====================================================================== C ABI
+extern "C" int t4k_set_conv_engine(int engine) {
+    if (engine < T4K_GEMM_AUTO || engine > T4K_GEMM_TC) return T4K_EINVAL;
+    g_conv_engine = engine; return 0;
+}
 extern "C" int t4k_conv2d_fwd(const float *I, const float *F, const float *B, float *O,
                               int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, t4k_stream_t s) {
     if (!I || !F || !B || !O || N < 1 || H1 < 1 || W1 < 1 || C1 < 1 || H0 < 1 || W0 < 1 || C0 < 1) return T4K_EINVAL;
@@ -355,6 +367,9 @@ extern "C" int t4k_conv2d_fwd(const float *I, const float *F, const float *B, fl
         }
         return check_launch();
     }
+    if (g_conv_engine != T4K_GEMM_SIMT && conv_tc_ok(H1, W1, C1, H0, W0, C0, KS, S, P))
+        return conv_tc(I, F, B, O, N, H1, W1, C1, C0, KS, P, 0, st);
+    if (g_conv_engine == T4K_GEMM_TC) return T4K_EINVAL;
     // gridDim.y <= 65535: launch per group of samples so each launch has at most 65535 pixel tiles
     const int64_t pix_per_n = (int64_t)H0 * W0;
     int n_per = (int)((65535LL * CBM) / pix_per_n); if (n_per < 1) return T4K_EINVAL;
@@ -436,6 +451,8 @@ extern "C" int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, f
         }
         return check_launch();
     }
+    if (g_conv_engine != T4K_GEMM_SIMT && conv_tc_ok(H0, W0, C0, H1, W1, C1, KS, S, P))
+        return conv_tc(dO, F, nullptr, dX, N, H1, W1, C1, C0, KS, P, 1, st);
     const int64_t pix_per_n = (int64_t)H1 * W1;
     int n_per = (int)((65535LL * CBM) / pix_per_n); if (n_per < 1) return T4K_EINVAL;
     if (n_per > N) n_per = N;

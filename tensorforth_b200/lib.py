@@ -49,6 +49,7 @@ PROTOTYPES = {
     "t4k_softmax_fwd": (_i, [_p, _p, _i, _i, _p]),
     "t4k_logsoftmax_fwd": (_i, [_p, _p, _i, _i, _p]),
     "t4k_conv2d_fwd": (_i, [_p, _p, _p, _p] + [_i] * 10 + [_p]),
+    "t4k_set_conv_engine": (_i, [_i]),
     "t4k_pool_fwd": (_i, [_i, _p, _p] + [_i] * 7 + [_p]),
     "t4k_batchnorm_fwd": (_i, [_p] * 6 + [_i] * 3 + [_p]),
     "t4k_dbias": (_i, [_p, _p, _i, _i, _p]),

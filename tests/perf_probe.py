@@ -49,11 +49,32 @@ def stream(n=1 << 28):
     print("   torch copy_: %.3f ms  %.0f GB/s" % (ms, 2 * n * 4 / ms / 1e6))
 
 
+def conv(n=256, c=64, hw=56, engine=t4.GEMM_AUTO):
+    I = torch.rand(n, hw, hw, c, device="cuda") - 0.5
+    F = (torch.rand(c, 3, 3, c, device="cuda") - 0.5) * 0.2
+    B = torch.rand(c, device="cuda")
+    O = torch.empty(n, hw, hw, c, device="cuda"); dX = torch.empty_like(I)
+    dF = torch.zeros_like(F); dB = torch.zeros_like(B)
+    L.t4k_set_conv_engine(engine)
+    fl = 2.0 * n * hw * hw * c * c * 9
+    by = 2 * I.numel() * 4
+    ms = timeit(lambda: t4.check(L.t4k_conv2d_fwd(p(I), p(F), p(B), p(O), n, hw, hw, c, hw, hw, c, 3, 1, 1, None)), iters=5)
+    print("conv fwd N=%d engine=%d: %.3f ms  %.1f TFLOP/s  %.0f GB/s" % (n, engine, ms, fl / ms / 1e9, by / ms / 1e6))
+    ms = timeit(lambda: t4.check(L.t4k_conv2d_bwd(p(I), p(O), p(F), p(dX), None, None, n, hw, hw, c, hw, hw, c, 3, 1, 1, 0, None)), iters=5)
+    print("conv dX  N=%d engine=%d: %.3f ms  %.1f TFLOP/s  %.0f GB/s" % (n, engine, ms, fl / ms / 1e9, by / ms / 1e6))
+    ms = timeit(lambda: t4.check(L.t4k_conv2d_bwd(p(I), p(O), p(F), p(dX), p(dF), p(dB), n, hw, hw, c, hw, hw, c, 3, 1, 1, 1, None)), iters=5)
+    print("conv bwd (dF,dB,dX) N=%d engine=%d: %.3f ms  %.1f TFLOP/s" % (n, engine, ms, 2 * fl / ms / 1e9))
+    L.t4k_set_conv_engine(t4.GEMM_AUTO)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "gemm"):
         for n in (1024, 2048, 4096, 8192):
             gemm(n, t4.GEMM_TC)
         gemm(1024, t4.GEMM_SIMT); gemm(4096, t4.GEMM_SIMT)
+    if what in ("all", "conv"):
+        conv(256)
+        conv(64, engine=t4.GEMM_SIMT)
     if what in ("all", "stream"):
         stream()

@@ -319,6 +319,40 @@ def test_conv2d_fwd_bwd(N, H, W, C1, C0, K, S, P):
     assert lib().t4k_conv2d_fwd(ptr(dev(I)), ptr(dev(F)), ptr(dev(Bv)), ptr(o), N, H, W, C1, H0, W0, C0, 7, 1, 3, None) == -2
 
 
+CONV_TC_CASES = [  # N,H,W,C1,C0,K,P  (stride 1, "same"): tcgen05 implicit-GEMM engine
+    (2, 12, 12, 32, 16, 3, 1),           # CK=32, smallest N
+    (3, 9, 9, 64, 64, 3, 1),             # 243 pixels: ragged last tile
+    (1, 16, 16, 64, 128, 5, 2),          # 5x5, C0=128 → single accumulator buffer
+    (2, 10, 10, 96, 48, 1, 0),           # 1x1, three 32-channel chunks
+    (5, 28, 28, 64, 32, 3, 1),           # 31 tiles → several per CTA? (no: one each) exercises tile loop bounds
+    (40, 56, 56, 64, 64, 3, 1),          # 980 tiles on 148 CTAs: persistent loop, double-buffered accumulators
+]
+
+
+@pytest.mark.parametrize("N,H,W,C1,C0,K,P", CONV_TC_CASES)
+def test_conv2d_tc_engine(N, H, W, C1, C0, K, P):
+    """fwd + dX on the tensor-core engine: vs the oracle where it finishes in seconds, vs the CUDA-core engine always"""
+    I, F, Bv, dO = rnd(N, H, W, C1), rnd(C1, K, K, C0, lo=-.3, hi=.3), rnd(C0), rnd(N, H, W, C0)
+    Id, Fd, Bd, dOd = dev(I), dev(F), dev(Bv), dev(dO)
+    o_tc, o_si = dev(np.full((N, H, W, C0), np.nan, np.float32)), zeros(N, H, W, C0)
+    dx_tc, dx_si = dev(np.full((N, H, W, C1), np.nan, np.float32)), zeros(N, H, W, C1)
+    try:
+        ok(lib().t4k_set_conv_engine(t4.GEMM_TC))
+        ok(lib().t4k_conv2d_fwd(ptr(Id), ptr(Fd), ptr(Bd), ptr(o_tc), N, H, W, C1, H, W, C0, K, 1, P, None), "conv fwd tc")
+        ok(lib().t4k_conv2d_bwd(ptr(Id), ptr(dOd), ptr(Fd), ptr(dx_tc), None, None, N, H, W, C1, H, W, C0, K, 1, P, 0, None), "conv dX tc")
+        ok(lib().t4k_set_conv_engine(t4.GEMM_SIMT))
+        ok(lib().t4k_conv2d_fwd(ptr(Id), ptr(Fd), ptr(Bd), ptr(o_si), N, H, W, C1, H, W, C0, K, 1, P, None))
+        ok(lib().t4k_conv2d_bwd(ptr(Id), ptr(dOd), ptr(Fd), ptr(dx_si), None, None, N, H, W, C1, H, W, C0, K, 1, P, 0, None))
+    finally:
+        lib().t4k_set_conv_engine(t4.GEMM_AUTO)
+    assert_close(host(o_tc), host(o_si), rtol=2e-5, what="conv fwd tc vs simt")
+    assert_close(host(dx_tc), host(dx_si), rtol=2e-5, what="conv dX tc vs simt")
+    if N * H * W <= 4096:
+        assert_close(host(o_tc), orc.conv2d(I, F, Bv, K, 1, P), rtol=1e-4, what="conv fwd tc vs oracle")
+        rdx, _, _ = orc.dconv2d(I, dO, F, K, 1, P, np.zeros_like(F), np.zeros_like(Bv), False)
+        assert_close(host(dx_tc), rdx, rtol=1e-4, what="conv dX tc vs oracle")
+
+
 @pytest.mark.parametrize("layer", [t4.L_MAXPOOL, t4.L_AVGPOOL, t4.L_MINPOOL, t4.L_USAMPLE])
 @pytest.mark.parametrize("N,H,W,Cc,K", [(2, 4, 4, 1, 2), (512, 28, 28, 10, 2), (3, 9, 12, 5, 3), (2, 6, 6, 33, 2)])
 def test_pool_fwd_bwd(layer, N, H, W, Cc, K):
