@@ -397,7 +397,10 @@ extern "C" int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, f
     // ---- weight + bias gradient first (dX may alias nothing, but keep I intact until wgrad has read it)
     if (train) {
         const size_t smem_small = ((size_t)WG_ROWS * W0 * C0 + (size_t)((WG_ROWS - 1) * S + KS) * W1 * C1) * sizeof(float);
-        if (nF + C0 <= 4096 && smem_small <= 96 * 1024 && C0 <= 16) {
+        if (g_conv_engine != T4K_GEMM_SIMT && conv_wgrad_tc_ok(H1, W1, C1, H0, W0, C0, KS, S, P)) {
+            rc = conv_wgrad_tc(I, dO, dF, dB, N, H1, W1, C1, C0, KS, P, st);
+            if (rc) return rc;
+        } else if (nF + C0 <= 4096 && smem_small <= 96 * 1024 && C0 <= 16) {
             const int strips = (H0 + WG_ROWS - 1) / WG_ROWS;
             const int ctas = N * strips;
             float *part = (float*)workspace((size_t)ctas * (nF + C0) * sizeof(float), 4);

@@ -324,6 +324,9 @@ CONV_TC_CASES = [  # N,H,W,C1,C0,K,P  (stride 1, "same"): tcgen05 implicit-GEMM 
     (3, 9, 9, 64, 64, 3, 1),             # 243 pixels: ragged last tile
     (1, 16, 16, 64, 128, 5, 2),          # 5x5, C0=128 → single accumulator buffer
     (2, 10, 10, 96, 48, 1, 0),           # 1x1, three 32-channel chunks
+    (3, 12, 12, 32, 64, 3, 1),           # wgrad: 4 taps per M-tile
+    (2, 20, 20, 64, 32, 1, 0),           # wgrad 1x1
+    (9, 16, 16, 64, 64, 3, 1),           # wgrad: 36 k-blocks
     (5, 28, 28, 64, 32, 3, 1),           # 31 tiles → several per CTA? (no: one each) exercises tile loop bounds
     (40, 56, 56, 64, 64, 3, 1),          # 980 tiles on 148 CTAs: persistent loop, double-buffered accumulators
 ]
@@ -345,6 +348,22 @@ def test_conv2d_tc_engine(N, H, W, C1, C0, K, P):
         ok(lib().t4k_conv2d_bwd(ptr(Id), ptr(dOd), ptr(Fd), ptr(dx_si), None, None, N, H, W, C1, H, W, C0, K, 1, P, 0, None))
     finally:
         lib().t4k_set_conv_engine(t4.GEMM_AUTO)
+    if (C1 in (32, 64)) and (C0 in (32, 64)) and K in (1, 3):                 # tensor-core weight gradient
+        dF0, dB0 = rnd(C1, K, K, C0), rnd(C0)
+        df_tc, db_tc, df_si, db_si = dev(dF0), dev(dB0), dev(dF0), dev(dB0)
+        try:
+            ok(lib().t4k_set_conv_engine(t4.GEMM_TC))
+            ok(lib().t4k_conv2d_bwd(ptr(Id), ptr(dOd), ptr(Fd), ptr(dx_tc), ptr(df_tc), ptr(db_tc), N, H, W, C1, H, W, C0, K, 1, P, 1, None), "conv bwd tc")
+            ok(lib().t4k_set_conv_engine(t4.GEMM_SIMT))
+            ok(lib().t4k_conv2d_bwd(ptr(Id), ptr(dOd), ptr(Fd), ptr(dx_si), ptr(df_si), ptr(db_si), N, H, W, C1, H, W, C0, K, 1, P, 1, None))
+        finally:
+            lib().t4k_set_conv_engine(t4.GEMM_AUTO)
+        assert_close(host(df_tc), host(df_si), rtol=2e-5, what="conv dF tc vs simt")
+        assert_close(host(db_tc), host(db_si), rtol=2e-5, what="conv dB tc vs simt")
+        if N * H * W <= 4096:
+            _, rdf, rdb = orc.dconv2d(I, dO, F, K, 1, P, dF0, dB0, True)
+            assert_close(host(df_tc), rdf, rtol=1e-4, what="conv dF tc vs oracle")
+            assert_close(host(db_tc), rdb, rtol=1e-4, what="conv dB tc vs oracle")
     assert_close(host(o_tc), host(o_si), rtol=2e-5, what="conv fwd tc vs simt")
     assert_close(host(dx_tc), host(dx_si), rtol=2e-5, what="conv dX tc vs simt")
     if N * H * W <= 4096:
