@@ -68,6 +68,7 @@ t4h_tensor t4h_model_layer(t4h_model m, int i);                      /* `n@` (ne
 t4h_tensor t4h_model_param(t4h_model m, int i, int which);           /* `nn.w nn.b nn.dw nn.db nn.ex` which=0..4; borrowed */
 int   t4h_model_set_param(t4h_model m, int i, int which, t4h_tensor t);   /* `nn.w=` `nn.b=` (copies t) */
 int   t4h_model_train(t4h_model m, int on);                          /* `trainable` */
+int   t4h_model_fuse(t4h_model m, int on);                           /* multi-layer fused kernels on (default) / off: same tensors either way */
 int   t4h_model_forward(t4h_model m, t4h_tensor input);              /* `forward` */
 int   t4h_model_backprop(t4h_model m, t4h_tensor tgt);               /* `backprop` (tgt NULL → cached one-hot) */
 float t4h_model_loss(t4h_model m, int loss_op, t4h_tensor tgt);      /* `loss.mse|bce|ce|nll` (syncs) */

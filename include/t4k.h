@@ -163,6 +163,19 @@ int t4k_pool_bwd(int layer, float *I, const float *dO, int N, int H1, int W1, in
 int t4k_batchnorm_bwd(const float *dO, const float *XH, float *dX, const float *gamma,
                       float *dgamma, float *dbeta, float *scratch3C, int N, int HW, int C, int train, t4k_stream_t s);
 
+/* ---- fused CNN block: conv2d → maxpool(2) → relu (→ flatten), the layer group of examples/t4_40a.4th:11-12.
+ * One launch each way; writes exactly the layer tensors the per-layer calls write (forward.cu:83-155,201-228;
+ * backprop.cu:112-191,257-280).  Eligible: C1 <= 4, C0 <= 16, even H0/W0, sample fits in shared memory; otherwise
+ * T4K_ENOSUP and the caller issues the per-layer calls.  flatO may be NULL (no flatten layer).
+ * backward: dY = gradient at the block output (the flatten output tensor, or actO itself when there is no flatten);
+ * actO <- dY, poolO <- dY*actF, convO (forward conv output) <- max-pool routed gradient in place,
+ * Iio (conv input) <- dX and dXbuf <- dX (Model::_bconv: `in = dx`), dF/dB += when train. */
+int t4k_conv_pool_relu_fwd(const float *I, const float *F, const float *B, float *convO, float *poolO, float *actO, float *actF,
+                           float *flatO, int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, t4k_stream_t s);
+int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,
+                           const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
+                           int KS, int S, int P, int train, t4k_stream_t s);
+
 /* ---- optimizers: src/nn/gradient.cu:133-169 + nmath.cu:419-472 ------------------------ */
 int t4k_sgd(float *G, float *DG, float *M, int Nw, float lr, float b, int64_t n, t4k_stream_t s);
 int t4k_adam(float *G, float *DG, float *M, float *V, float lr, float b1, float b2, int64_t n, t4k_stream_t s);

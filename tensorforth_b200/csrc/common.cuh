@@ -28,7 +28,7 @@ static inline int stream_grid(int64_t n_items, int per_thread = 1) {
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
 }
-static inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
+__host__ __device__ static inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 
 __device__ __forceinline__ float warp_sum(float v) {
     #pragma unroll

@@ -341,6 +341,179 @@ static bool conv_cfg_ok(int KS, int S, int P) {           // forward.cu:142-151
            (KS == 4 && S == 2 && P == 1) || (KS == 5 && S == 1 && P == 2);
 }
 
+
+// ====================================================================== fused conv → maxpool(2) → relu (→ flatten)
+// The canonical block of the reference's CNN examples ("0.5 10 conv2d 2 maxpool relu [flatten]",
+// examples/t4_40a.4th:11-12, t4_30e.4th:15-21).  One CTA per sample keeps the whole conv output of
+// that sample in shared memory, so the block costs ONE launch each way and touches HBM once per
+// layer tensor — every tensor the per-layer path writes is still written (n@ shows the same values).
+//   forward : _fconv + _fpool + _factivate (+ flatten copy)      src/nn/forward.cu:83-155,201-228
+//   backward: flatten copy + _bactivate + _bpool + _bconv         src/nn/backprop.cu:112-191,257-280
+// Arithmetic order is identical to the per-layer kernels above for O/dX/pool routing (bit-equal);
+// dF/dB use per-sample partials + the same ordered finalize.
+struct CprP {
+    const float *I, *F, *B;
+    float *convO, *poolO, *actO, *actF, *flatO;     // forward outputs (flatO may be null)
+    const float *dY;                                 // backward: gradient arriving at the block output
+    float *Iio, *dXbuf, *part;                       // backward: conv input (overwritten with dX), grad[4] copy, wgrad partials
+    int H1, W1, C1, H0, W0, C0, S, P, train;
+};
+template<int KS, int C0MAX>
+__global__ void __launch_bounds__(T4K_THREADS) k_cpr_fwd(CprP p) {
+    extern __shared__ float sm[];
+    const int C0 = p.C0, C1 = p.C1, S = p.S, P = p.P, H0 = p.H0, W0 = p.W0, H1 = p.H1, W1 = p.W1;
+    const int nF = C1 * KS * KS * C0, nI = H1 * W1 * C1, nO = H0 * W0 * C0;
+    float *sF = sm, *sI = sm + ((nF + C0 + 3) & ~3), *sO = sI + ((nI + 3) & ~3);
+    const int n = blockIdx.x;
+    const float *gI = p.I + (int64_t)n * nI;
+    for (int t = threadIdx.x; t < nF; t += blockDim.x) sF[t] = __ldg(p.F + t);
+    for (int t = threadIdx.x; t < C0; t += blockDim.x) sF[nF + t] = __ldg(p.B + t);
+    for (int t = threadIdx.x; t < nI; t += blockDim.x) sI[t] = __ldg(gI + t);
+    __syncthreads();
+    for (int pix = threadIdx.x; pix < H0 * W0; pix += blockDim.x) {
+        const int j = pix % W0, i = pix / W0;
+        float acc[C0MAX];
+        #pragma unroll
+        for (int c = 0; c < C0MAX; c++) acc[c] = (c < C0) ? sF[nF + c] : 0.0f;
+        #pragma unroll
+        for (int y = 0; y < KS; y++) {
+            const int gi = i * S + y - P;
+            if (gi < 0 || gi >= H1) continue;
+            #pragma unroll
+            for (int x = 0; x < KS; x++) {
+                const int gj = j * S + x - P;
+                if (gj < 0 || gj >= W1) continue;
+                const float *px = sI + (W1 * gi + gj) * C1;
+                for (int c1 = 0; c1 < C1; c1++) {
+                    const float v = px[c1];
+                    const float *f = sF + ((c1 * KS + y) * KS + x) * C0;
+                    #pragma unroll
+                    for (int c = 0; c < C0MAX; c++) if (c < C0) acc[c] = fmaf(f[c], v, acc[c]);
+                }
+            }
+        }
+        #pragma unroll
+        for (int c = 0; c < C0MAX; c++) if (c < C0) sO[pix * C0 + c] = acc[c];
+    }
+    __syncthreads();
+    float *gO = p.convO + (int64_t)n * nO;
+    if (((nO & 3) == 0) && aligned16(p.convO)) { for (int t = threadIdx.x; t < (nO >> 2); t += blockDim.x) stg4(gO + 4 * t, *reinterpret_cast<const float4*>(sO + 4 * t)); }
+    else for (int t = threadIdx.x; t < nO; t += blockDim.x) gO[t] = sO[t];
+    const int Hp = H0 / 2, Wp = W0 / 2, nP = Hp * Wp * C0;
+    const int64_t gp = (int64_t)n * nP;
+    for (int t = threadIdx.x; t < nP; t += blockDim.x) {
+        const int c = t % C0; int r = t / C0; const int j0 = r % Wp, i0 = r / Wp;
+        const float *ix = sO + ((i0 * 2) * W0 + j0 * 2) * C0 + c;
+        float v = ix[0];
+        v = fmaxf(ix[C0], v); v = fmaxf(ix[W0 * C0], v); v = fmaxf(ix[(W0 + 1) * C0], v);      // k_pool<2> order
+        p.poolO[gp + t] = v;
+        float o, f;
+        if (v > 0.0f) { f = 1.0f; o = v; } else { f = 0.0f; o = 0.0f; }                       // k_activate RELU
+        p.actO[gp + t] = o; p.actF[gp + t] = f;
+        if (p.flatO) p.flatO[gp + t] = o;
+    }
+}
+template<int KS>
+__global__ void __launch_bounds__(T4K_THREADS) k_cpr_bwd(CprP p) {
+    extern __shared__ float sm[];
+    __shared__ float sred[2 * 512];
+    const int C0 = p.C0, C1 = p.C1, S = p.S, P = p.P, H0 = p.H0, W0 = p.W0, H1 = p.H1, W1 = p.W1;
+    const int nF = C1 * KS * KS * C0, nI = H1 * W1 * C1, nO = H0 * W0 * C0;
+    float *sF = sm, *sI = sm + ((nF + 3) & ~3), *sO = sI + ((nI + 3) & ~3);
+    const int n = blockIdx.x;
+    float *gO = p.convO + (int64_t)n * nO;
+    float *gI = p.Iio + (int64_t)n * nI;
+    for (int t = threadIdx.x; t < nF; t += blockDim.x) sF[t] = __ldg(p.F + t);
+    for (int t = threadIdx.x; t < nI; t += blockDim.x) sI[t] = gI[t];
+    if (((nO & 3) == 0) && aligned16(p.convO)) { for (int t = threadIdx.x; t < (nO >> 2); t += blockDim.x) *reinterpret_cast<float4*>(sO + 4 * t) = *reinterpret_cast<const float4*>(gO + 4 * t); }
+    else for (int t = threadIdx.x; t < nO; t += blockDim.x) sO[t] = gO[t];
+    __syncthreads();
+    // flatten copy, relu backward, max-pool routing (first strict max in y,x order), in shared memory
+    const int Hp = H0 / 2, Wp = W0 / 2, nP = Hp * Wp * C0;
+    const int64_t gp = (int64_t)n * nP;
+    for (int t = threadIdx.x; t < nP; t += blockDim.x) {
+        const float d = p.dY[gp + t];
+        if (p.actO != p.dY) p.actO[gp + t] = d;                      // flatten backward: in = out
+        const float g = __fmul_rn(d, p.actF[gp + t]);                // _bactivate: in = out * mask
+        p.poolO[gp + t] = g;
+        const int c = t % C0; int r = t / C0; const int j0 = r % Wp, i0 = r / Wp;
+        float *ix = sO + ((i0 * 2) * W0 + j0 * 2) * C0 + c;
+        const float t0 = ix[0], t1 = ix[C0], t2 = ix[W0 * C0], t3 = ix[(W0 + 1) * C0];
+        float best = t0; int arg = 0;
+        if (t1 > best) { best = t1; arg = 1; }
+        if (t2 > best) { best = t2; arg = 2; }
+        if (t3 > best) { best = t3; arg = 3; }
+        ix[0] = (arg == 0) ? g : 0.0f; ix[C0] = (arg == 1) ? g : 0.0f;
+        ix[W0 * C0] = (arg == 2) ? g : 0.0f; ix[(W0 + 1) * C0] = (arg == 3) ? g : 0.0f;
+    }
+    __syncthreads();
+    if (((nO & 3) == 0) && aligned16(p.convO)) { for (int t = threadIdx.x; t < (nO >> 2); t += blockDim.x) stg4(gO + 4 * t, *reinterpret_cast<const float4*>(sO + 4 * t)); }
+    else for (int t = threadIdx.x; t < nO; t += blockDim.x) gO[t] = sO[t];
+    // weight / bias gradient partials of this sample: 2 threads per element (output-row halves)
+    if (p.train) {
+        const int nE = nF + C0;
+        for (int u = threadIdx.x; u < 2 * nE; u += blockDim.x) {
+            const int half = u / nE, t = u - half * nE;
+            const int ia = half ? H0 / 2 : 0, ib = half ? H0 : H0 / 2;
+            float acc = 0.0f;
+            if (t < nF) {
+                const int c0 = t % C0; int r = t / C0;
+                const int kx = r % KS; r /= KS; const int ky = r % KS; const int c1 = r / KS;
+                for (int i = ia; i < ib; i++) {
+                    const int gi = i * S + ky - P;
+                    if (gi < 0 || gi >= H1) continue;
+                    const float *irow = sI + gi * W1 * C1 + c1;
+                    const float *orow = sO + i * W0 * C0 + c0;
+                    for (int j = 0; j < W0; j++) {
+                        const int gj = j * S + kx - P;
+                        if (gj >= 0 && gj < W1) acc = fmaf(irow[gj * C1], orow[j * C0], acc);
+                    }
+                }
+            } else {
+                const int c0 = t - nF;
+                for (int q = ia * W0; q < ib * W0; q++) acc += sO[q * C0 + c0];
+            }
+            sred[u] = acc;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < nE; t += blockDim.x) p.part[(int64_t)n * nE + t] = sred[t] + sred[nE + t];
+    }
+    // input gradient (flipped taps, k_conv_dgrad_small order) → conv input tensor and grad[4]
+    for (int pix = threadIdx.x; pix < H1 * W1; pix += blockDim.x) {
+        const int x = pix % W1, y = pix / W1;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        #pragma unroll
+        for (int ky = 0; ky < KS; ky++) {
+            const int ti = y + P - ky;
+            if (ti < 0 || (ti % S) != 0) continue;
+            const int i = ti / S;
+            if (i >= H0) continue;
+            #pragma unroll
+            for (int kx = 0; kx < KS; kx++) {
+                const int tj = x + P - kx;
+                if (tj < 0 || (tj % S) != 0) continue;
+                const int j = tj / S;
+                if (j >= W0) continue;
+                const float *d = sO + (W0 * i + j) * C0;
+                for (int c0 = 0; c0 < C0; c0++) {
+                    const float dv = d[c0];
+                    #pragma unroll
+                    for (int c1 = 0; c1 < 4; c1++)
+                        if (c1 < C1) acc[c1] = fmaf(sF[((c1 * KS + (KS - 1 - ky)) * KS + (KS - 1 - kx)) * C0 + c0], dv, acc[c1]);
+                }
+            }
+        }
+        #pragma unroll
+        for (int c1 = 0; c1 < 4; c1++) if (c1 < C1) { gI[pix * C1 + c1] = acc[c1]; p.dXbuf[(int64_t)n * nI + pix * C1 + c1] = acc[c1]; }
+    }
+}
+static bool cpr_ok(int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, size_t *smem) {
+    if (!conv_cfg_ok(KS, S, P) || C1 > 4 || C0 > 16 || (H0 & 1) || (W0 & 1)) return false;
+    const size_t nF = (size_t)C1 * KS * KS * C0, nI = (size_t)H1 * W1 * C1, nO = (size_t)H0 * W0 * C0;
+    if (2 * (nF + C0) > 1024) return false;
+    *smem = (((nF + C0 + 3) & ~(size_t)3) + ((nI + 3) & ~(size_t)3) + nO) * sizeof(float);
+    return *smem <= 100 * 1024;
+}
 } // namespace t4k
 using namespace t4k;
 
@@ -467,4 +640,37 @@ extern "C" int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, f
         rc = check_launch(); if (rc) return rc;
     }
     return 0;
+}
+
+// ---- fused conv → maxpool(2) → relu (→ flatten) block; T4K_ENOSUP when the shape is not eligible (caller: per-layer calls)
+extern "C" int t4k_conv_pool_relu_fwd(const float *I, const float *F, const float *B, float *convO, float *poolO, float *actO, float *actF,
+                                      float *flatO, int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, t4k_stream_t s) {
+    if (!I || !F || !B || !convO || !poolO || !actO || !actF || N < 1) return T4K_EINVAL;
+    size_t smem = 0;
+    if (!cpr_ok(H1, W1, C1, H0, W0, C0, KS, S, P, &smem)) return T4K_ENOSUP;
+    CprP p{}; p.I = I; p.F = F; p.B = B; p.convO = convO; p.poolO = poolO; p.actO = actO; p.actF = actF; p.flatO = flatO;
+    p.H1 = H1; p.W1 = W1; p.C1 = C1; p.H0 = H0; p.W0 = W0; p.C0 = C0; p.S = S; p.P = P;
+    static bool attr[6] = {false};
+    #define CPRF(K_) { if (!attr[K_] && smem > 48 * 1024) { cudaFuncSetAttribute(k_cpr_fwd<K_, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr[K_] = true; } \
+                       k_cpr_fwd<K_, 16><<<N, T4K_THREADS, smem, STRM(s)>>>(p); }
+    switch (KS) { case 1: CPRF(1) break; case 3: CPRF(3) break; case 4: CPRF(4) break; default: CPRF(5) break; }
+    return check_launch();
+}
+extern "C" int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,
+                                      const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
+                                      int KS, int S, int P, int train, t4k_stream_t s) {
+    if (!dY || !actO || !actF || !poolO || !convO || !Iio || !dXbuf || !F || N < 1 || (train && (!dF || !dB))) return T4K_EINVAL;
+    size_t smem = 0;
+    if (!cpr_ok(H1, W1, C1, H0, W0, C0, KS, S, P, &smem)) return T4K_ENOSUP;
+    const int nF = C1 * KS * KS * C0;
+    CprP p{}; p.F = F; p.convO = convO; p.poolO = poolO; p.actO = actO; p.actF = (float*)actF; p.dY = dY; p.Iio = Iio; p.dXbuf = dXbuf;
+    p.H1 = H1; p.W1 = W1; p.C1 = C1; p.H0 = H0; p.W0 = W0; p.C0 = C0; p.S = S; p.P = P; p.train = train;
+    if (train) { p.part = (float*)workspace((size_t)N * (nF + C0) * sizeof(float), 4); if (!p.part) return T4K_ENOMEM; }
+    static bool attr[6] = {false};
+    #define CPRB(K_) { if (!attr[K_] && smem > 40 * 1024) { cudaFuncSetAttribute(k_cpr_bwd<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr[K_] = true; } \
+                       k_cpr_bwd<K_><<<N, T4K_THREADS, smem, STRM(s)>>>(p); }
+    switch (KS) { case 1: CPRB(1) break; case 3: CPRB(3) break; case 4: CPRB(4) break; default: CPRB(5) break; }
+    int rc = check_launch(); if (rc || !train) return rc;
+    k_wgrad_fin<<<nF + C0, T4K_THREADS, 0, STRM(s)>>>(p.part, dF, dB, nF, C0, N, KS, S);
+    return check_launch();
 }

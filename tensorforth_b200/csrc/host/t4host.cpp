@@ -270,8 +270,42 @@ Model &Model::forward(Tensor &input) {
         return *this;
     }
     if (input.data != n0.data) n0 = input;
-    for (size_t i = 0; i + 1 < _layers.size(); i++) _fstep(*_layers[i], *_layers[i + 1]);
+    for (size_t i = 0; i + 1 < _layers.size(); ) {
+        const int adv = _ffused(i);                        // conv → maxpool(2) → relu (→ flatten) in one launch
+        if (adv) { i += adv; continue; }
+        _fstep(*_layers[i], *_layers[i + 1]); i++;
+    }
     return *this;
+}
+// The canonical CNN block of the reference's examples ("conv2d 2 maxpool relu [flatten]", t4_40a.4th:11-12):
+// same layer tensors written as the per-layer path (forward.cu:83-113), one kernel.  Returns layers consumed.
+int Model::_ffused(size_t i) {
+    const size_t n = _layers.size();
+    if (!fuse || i + 3 >= n) return 0;
+    Tensor &in = *_layers[i], &co = *_layers[i + 1], &po = *_layers[i + 2], &ao = *_layers[i + 3];
+    if (in.grad_fn != T4K_L_CONV || co.grad_fn != T4K_L_MAXPOOL || co.stride[0] != 2 || po.grad_fn != T4K_L_RELU) return 0;
+    Tensor *fl = (ao.grad_fn == T4K_L_FLATTEN && i + 4 < n) ? _layers[i + 4] : nullptr;
+    Tensor &f = *in.grad[0], &b = *in.grad[1];
+    int rc = t4k_conv_pool_relu_fwd(in.data, f.data, b.data, co.data, po.data, ao.data, po.grad[4]->data, fl ? fl->data : nullptr,
+                                    co.N(), in.H(), in.W(), in.C(), co.H(), co.W(), co.C(), f.H(), in.stride[0], in.stride[2], ST);
+    if (rc == T4K_ENOSUP) return 0;
+    KCHK(rc);
+    return fl ? 4 : 3;
+}
+int Model::_bfused(int i) {                                // i = index of the block's LAST layer (relu or flatten); returns layers consumed
+    if (!fuse) return 0;
+    const bool flat = _layers[i]->grad_fn == T4K_L_FLATTEN;
+    const int ir = flat ? i - 1 : i;                       // relu layer index
+    if (ir < 2) return 0;
+    Tensor &in = *_layers[ir - 2], &co = *_layers[ir - 1], &po = *_layers[ir], &ao = *_layers[ir + 1];
+    if (po.grad_fn != T4K_L_RELU || co.grad_fn != T4K_L_MAXPOOL || co.stride[0] != 2 || in.grad_fn != T4K_L_CONV) return 0;
+    Tensor &dy = *_layers[i + 1];                          // gradient arriving at the block output
+    Tensor &f = *in.grad[0], &df = *in.grad[2], &db = *in.grad[3], &dx = *in.grad[4];
+    int rc = t4k_conv_pool_relu_bwd(dy.data, ao.data, po.grad[4]->data, po.data, co.data, in.data, dx.data, f.data, df.data, db.data,
+                                    in.N(), in.H(), in.W(), in.C(), co.H(), co.W(), co.C(), f.H(), in.stride[0], in.stride[2], train, ST);
+    if (rc == T4K_ENOSUP) return 0;
+    KCHK(rc);
+    return flat ? 4 : 3;
 }
 void Model::_fstep(Tensor &in, Tensor &out) {                             // forward.cu:83-113
     t4_layer fn = in.grad_fn;
@@ -332,7 +366,12 @@ Model &Model::backprop() {
 }
 Model &Model::backprop(Tensor &tgt) {
     if (_bprep(tgt)) return *this;
-    for (int i = (int)_layers.size() - 2, j = 0; i >= 0; i--, j++) _bstep(*_layers[i], *_layers[i + 1], j == 0);
+    for (int i = (int)_layers.size() - 2, j = 0; i >= 0; j++) {
+        const t4_layer fn = _layers[i]->grad_fn;
+        const int adv = (j > 0 && (fn == T4K_L_FLATTEN || fn == T4K_L_RELU)) ? _bfused(i) : 0;
+        if (adv) { i -= adv; continue; }
+        _bstep(*_layers[i], *_layers[i + 1], j == 0); i--;
+    }
     return *this;
 }
 int Model::_bprep(Tensor &tgt) {                                          // backprop.cu:76-109
@@ -628,6 +667,7 @@ int   t4h_model_set_param(t4h_model m, int i, int which, t4h_tensor src) {   // 
     return 0;
 }
 int   t4h_model_train(t4h_model m, int on) { MM(m).train = on != 0; return 0; }
+int   t4h_model_fuse(t4h_model m, int on) { MM(m).fuse = on != 0; return 0; }
 int   t4h_model_forward(t4h_model m, t4h_tensor input) {
     Tensor &n0 = MM(m)[0];
     if (TT(input).numel != n0.numel) { MM(m).forward(TT(input)); return T4K_EINVAL; }

@@ -137,6 +137,7 @@ public:
     DU   max_norm = 0;
     bool train    = true;
     bool err      = false;
+    bool fuse     = true;              ///< allow multi-layer fused kernels (same tensors written; off = strict per-layer launches)
     U64  numel() { return _layers.size(); }
 
     Model(U32 n, U32 h, U32 w, U32 c);                       ///< `nn.model` (netvm.cpp:301-311)
@@ -175,6 +176,8 @@ private:
     void _ibatchnorm(Tensor &in, DU m);
     void _iup(Tensor &in, U16 f, DU m);
     void _fstep(Tensor &in, Tensor &out);
+    int  _ffused(size_t i);
+    int  _bfused(int i);
     int  _fconv(Tensor &in, Tensor &out);
     int  _flinear(Tensor &in, Tensor &out);
     int  _factivate(Tensor &in, Tensor &out, t4_layer fn);

@@ -33,7 +33,7 @@ PROTOTYPES = {
     "t4h_model_new": (_p, [_u, _u, _u, _u]), "t4h_model_free": (None, [_p]),
     "t4h_model_add": (_i, [_p, _i, _u, _f, C.POINTER(C.c_uint16)]), "t4h_model_numel": (_i, [_p]),
     "t4h_model_layer": (_p, [_p, _i]), "t4h_model_param": (_p, [_p, _i, _i]), "t4h_model_set_param": (_i, [_p, _i, _i, _p]),
-    "t4h_model_train": (_i, [_p, _i]), "t4h_model_forward": (_i, [_p, _p]), "t4h_model_backprop": (_i, [_p, _p]),
+    "t4h_model_train": (_i, [_p, _i]), "t4h_model_fuse": (_i, [_p, _i]), "t4h_model_forward": (_i, [_p, _p]), "t4h_model_backprop": (_i, [_p, _p]),
     "t4h_model_loss": (_f, [_p, _i, _p]), "t4h_model_loss_async": (_i, [_p, _i, _p, _p]),
     "t4h_model_onehot_labels": (_i, [_p, _p]), "t4h_model_onehot_set": (_i, [_p, _p]), "t4h_model_hit": (_i, [_p, _i]),
     "t4h_model_sgd": (_i, [_p, _f, _f]), "t4h_model_adam": (_i, [_p, _f, _f, _f]), "t4h_model_adamw": (_i, [_p, _f, _f, _f, _f]),
@@ -249,6 +249,7 @@ class Model:
         return self
 
     def trainable(self, on): load().t4h_model_train(self.h, int(on)); return self
+    def fuse(self, on): load().t4h_model_fuse(self.h, int(on)); return self
 
     def forward(self, x):
         if load().t4h_model_forward(self.h, x.h): raise T4KError(_err())

@@ -261,3 +261,27 @@ def test_step_graph_equals_eager():
     assert losses_a == losses_b, (losses_a, losses_b)          # same kernels, same order → same bits
     for i in (0, 4, 6):
         assert np.array_equal(ga.w(i).numpy(), gb.w(i).numpy())
+
+
+@pytest.mark.parametrize("kind,N", [("mnist", 32), ("toycnn", 3)])
+def test_fused_block_equals_per_layer(kind, N):
+    """conv → maxpool(2) → relu (→ flatten) fused kernels write the same layer tensors as the per-layer launches:
+    bit-equal activations / routed gradients / dX (same arithmetic order), dF/dB within summation-order noise"""
+    rng = np.random.default_rng(21)
+    ga, om, shape, E, lop = build_pair(kind, N)
+    gb, _, *_ = build_pair(kind, N)
+    gb.fuse(False)
+    x = (rng.random(shape, dtype=np.float32) * 2 - 1).astype(np.float32); y = orc.onehot(rng.integers(0, E, N), E)
+    X, Y = th.Tensor.from_numpy(x), th.Tensor.tensor(N, 1, E, 1, y)
+    n0 = t4.load().t4k_launch_count()
+    ga.forward(X); ga.backprop(Y)
+    n1 = t4.load().t4k_launch_count()
+    gb.forward(X); gb.backprop(Y)
+    n2 = t4.load().t4k_launch_count()
+    assert n1 - n0 < n2 - n1                                   # fewer launches
+    for i in range(len(ga)):
+        assert np.array_equal(ga.layer(i).numpy(), gb.layer(i).numpy()), "layer %d" % i
+    for i in range(len(ga) - 1):
+        if ga.dw(i) is not None and ga.w(i) is not None and ga.db(i) is not None:
+            assert_close(ga.dw(i).numpy(), gb.dw(i).numpy(), rtol=1e-5, what="dw%d" % i)
+            assert_close(ga.db(i).numpy(), gb.db(i).numpy(), rtol=1e-5, what="db%d" % i)
