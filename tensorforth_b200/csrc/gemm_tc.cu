@@ -10,7 +10,7 @@
 //                   stored as ready-made 128x32 SWIZZLE_128B shared-memory tile images
 //   k_gemm_tc     : warp 0  — producer: cp.async.bulk (TMA engine, UBLKCP) global→smem, mbarrier tx
 //                   warp 1  — tcgen05.mma issuer (1 elected lane), TMEM alloc/dealloc
-//                   warps 2-5 — epilogue: tcgen05.ld TMEM→regs, alpha/beta, store
+//                   warps 2-9 — epilogue: tcgen05.ld TMEM→regs every DRAIN_KB k-blocks (RN add), alpha/beta, store
 //   k_splitk_fin  : (gemm_simt.cu) deterministic split-K reduction
 // Bound: tensor pipe (3 MMAs per k-step); roofline denominators in DESIGN.md.
 #include "tc_ptx.cuh"
@@ -87,34 +87,45 @@ struct TcP {
     float *part;                 // partials [splits][M*N] when splits > 1
 };
 
+// Accumulation accuracy: the tensor core's FP32 accumulator add TRUNCATES (round toward zero), so a chain of n MMAs
+// into one TMEM accumulator carries a one-sided bias of ~n/2 ulp (measured: 1536 MMAs at K=4096 → 1.4e-4 of the
+// result's rms — over the 1e-4 parity bar).  The k loop is therefore cut into chunks of DRAIN_KB k-blocks
+// (DRAIN_KB*4*3 = 96 MMAs): chunks alternate between two TMEM accumulators and the epilogue warps drain each finished
+// chunk into FP32 REGISTERS with a round-to-nearest add while the MMAs of the next chunk run on the other accumulator.
+constexpr int DRAIN_KB = 8;       // k-blocks (of 32) per accumulator chain
+
 template<int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1) k_gemm_tc(TcP p) {
+__global__ void __launch_bounds__(320, 1) k_gemm_tc(TcP p) {
     constexpr uint32_t A_BYTES = TILE_FLTS * 4;                  // 32 KiB (hi+lo)
     constexpr uint32_t B_BYTES = (BN / TBM) * TILE_FLTS * 4;     // 32 or 64 KiB
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t PLANE_B = PLANE_FLTS * 4;                 // 16 KiB
     constexpr uint32_t B_PLANE_B = (BN / TBM) * PLANE_B;         // bytes of the B hi (or lo) plane in smem
+    constexpr int NEPI = 8;                                      // epilogue warps
+    constexpr int CW = BN / 2;                                   // accumulator columns per epilogue thread
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned tiles
     uint8_t *smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);   // full[STAGES], empty[STAGES], tmem_full
-    uint32_t *tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+    uint64_t *bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);   // full[STAGES], empty[STAGES], acc_full[2], acc_empty[2]
+    uint32_t *tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = blockIdx.y, nt = blockIdx.x, zs = blockIdx.z;
     const int kt0 = zs * p.kt_per_split;
     const int kt1 = min(p.KT, kt0 + p.kt_per_split);
     const int nkb = kt1 - kt0;
+    const int nchunk = (nkb + DRAIN_KB - 1) / DRAIN_KB;
 
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const uint32_t afull0 = smem_u32(bars + 2 * STAGES), aempty0 = smem_u32(bars + 2 * STAGES + 2);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        mbar_init(tfull, 1);
+        for (int b = 0; b < 2; b++) { mbar_init(afull0 + 8 * b, 1); mbar_init(aempty0 + 8 * b, NEPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {                                    // TMEM: BN fp32 columns x 128 lanes
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)BN));
+    if (warp == 1) {                                    // TMEM: two accumulators of BN fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -146,9 +157,12 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(TcP p) {
         constexpr uint32_t idesc = idesc_tf32(TBM, BN);
         for (int i = 0; i < nkb; i++) {
             const int s = i % STAGES, it = i / STAGES;
+            const int c = i / DRAIN_KB, ib = i % DRAIN_KB, b = c & 1;
+            if (ib == 0 && c >= 2) { mbar_wait(aempty0 + 8 * b, ((c >> 1) - 1) & 1); tc_fence_after(); }   // chunk c-2 drained
             mbar_wait(full0 + 8 * s, it & 1);
             tc_fence_after();
             if (elect_one()) {
+                const uint32_t acc = tmem_base + (uint32_t)(b * BN);
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint32_t sb = sa + A_BYTES;
                 const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + PLANE_B);
@@ -156,32 +170,33 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(TcP p) {
                 #pragma unroll
                 for (int k = 0; k < TBK / UK; k++) {
                     const uint64_t ko = (uint64_t)((k * UK * 4) >> 4);      // advance start address inside the swizzle row
-                    tc_mma_tf32(tmem_base, a_lo + ko, b_hi + ko, idesc, (i | k) ? 1u : 0u);
-                    tc_mma_tf32(tmem_base, a_hi + ko, b_lo + ko, idesc, 1u);
-                    tc_mma_tf32(tmem_base, a_hi + ko, b_hi + ko, idesc, 1u);
+                    tc_mma_tf32(acc, a_lo + ko, b_hi + ko, idesc, (ib | k) ? 1u : 0u);
+                    tc_mma_tf32(acc, a_hi + ko, b_lo + ko, idesc, 1u);
+                    tc_mma_tf32(acc, a_hi + ko, b_hi + ko, idesc, 1u);
                 }
             }
             __syncwarp();
             if (elect_one()) {
-                tc_commit(empty0 + 8 * s);                   // frees the smem stage when the MMAs above retire
-                if (i == nkb - 1) tc_commit(tfull);          // accumulator complete
+                tc_commit(empty0 + 8 * s);                                   // frees the smem stage when the MMAs above retire
+                if (ib == DRAIN_KB - 1 || i == nkb - 1) tc_commit(afull0 + 8 * b);   // chunk complete
             }
             __syncwarp();
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
-        const int q = warp & 3;
+        // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+        const int q = warp & 3, h = (warp - 2) >> 2;
         const int row = mt * TBM + q * 32 + lane;
-        float *dst; float alpha = p.alpha, beta = p.beta;
-        if (p.splits > 1) { dst = p.part + (int64_t)zs * p.M * p.N; alpha = 1.0f; beta = 0.0f; }
-        else dst = p.O;
-        if (nkb > 0) { mbar_wait(tfull, 0); tc_fence_after(); }
-        const bool n_vec = ((p.N & 3) == 0) && ((((uintptr_t)dst) & 15) == 0);
-        #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            if (nkb > 0) {
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        float acc[CW];
+        #pragma unroll
+        for (int j = 0; j < CW; j++) acc[j] = 0.0f;
+        for (int c = 0; c < nchunk; c++) {
+            const int b = c & 1;
+            mbar_wait(afull0 + 8 * b, (c >> 1) & 1);
+            tc_fence_after();
+            #pragma unroll
+            for (int g = 0; g < CW / 32; g++) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + h * CW + g * 32);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -192,18 +207,27 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(TcP p) {
                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            } else {
                 #pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = 0u;
+                for (int j = 0; j < 32; j++) acc[g * 32 + j] += __uint_as_float(v[j]);
             }
-            const int col0 = nt * BN + c0;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(aempty0 + 8 * b);                     // this warp's slice of accumulator b is free again
+        }
+        float *dst; float alpha = p.alpha, beta = p.beta;
+        if (p.splits > 1) { dst = p.part + (int64_t)zs * p.M * p.N; alpha = 1.0f; beta = 0.0f; }
+        else dst = p.O;
+        const bool n_vec = ((p.N & 3) == 0) && ((((uintptr_t)dst) & 15) == 0);
+        #pragma unroll
+        for (int g = 0; g < CW / 32; g++) {
+            const int col0 = nt * BN + h * CW + g * 32;
             if (row < p.M && col0 < p.N) {
                 float *o = dst + (int64_t)row * p.N + col0;
                 if (n_vec && col0 + 32 <= p.N) {
                     #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 r = make_float4(__uint_as_float(v[j]) * alpha, __uint_as_float(v[j + 1]) * alpha,
-                                               __uint_as_float(v[j + 2]) * alpha, __uint_as_float(v[j + 3]) * alpha);
+                        float4 r = make_float4(acc[g * 32 + j] * alpha, acc[g * 32 + j + 1] * alpha,
+                                               acc[g * 32 + j + 2] * alpha, acc[g * 32 + j + 3] * alpha);
                         if (beta != 0.0f) {
                             const float4 old = *reinterpret_cast<const float4*>(o + j);
                             r.x += old.x * beta; r.y += old.y * beta; r.z += old.z * beta; r.w += old.w * beta;
@@ -214,7 +238,7 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(TcP p) {
                     #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         if (col0 + j < p.N) {
-                            float r = __uint_as_float(v[j]) * alpha;
+                            float r = acc[g * 32 + j] * alpha;
                             if (beta != 0.0f) r += o[j] * beta;
                             o[j] = r;
                         }
@@ -227,7 +251,7 @@ __global__ void __launch_bounds__(192, 1) k_gemm_tc(TcP p) {
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)(2 * BN)));
     }
 }
 
@@ -252,7 +276,7 @@ template<int BN, int STAGES> static int launch_tc(const TcP &p, dim3 grid, cudaS
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
-    k_gemm_tc<BN, STAGES><<<grid, 192, smem, st>>>(p);
+    k_gemm_tc<BN, STAGES><<<grid, 320, smem, st>>>(p);
     return check_launch();
 }
 
