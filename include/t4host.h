@@ -82,7 +82,8 @@ int   t4h_model_adamw(t4h_model m, float lr, float wd, float b1, float b2);
 /* flat parameter arenas (built at the first optimizer call): pointers + float count; DG is what a
  * data-parallel caller sum-allreduces between backprop and the optimizer */
 int   t4h_model_arena(t4h_model m, float **G, float **DG, int64_t *total);
-/* capture forward+loss+backprop+optimizer into one CUDA graph and replay it (launch-bound regime) */
+/* capture forward+loss+backprop+optimizer into one CUDA graph and replay it (launch-bound regime);
+ * optimizer: 0 sgd, 1 sgd+momentum, 2 adam, 3 adamw, -1 none (data parallel: all-reduce DG, then call the optimizer) */
 int   t4h_model_step_graph(t4h_model m, t4h_tensor input, t4h_tensor tgt, int loss_op, float *loss_dev,
                            int optimizer, float lr, float b1, float b2, float wd);
 

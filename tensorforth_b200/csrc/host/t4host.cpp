@@ -529,7 +529,9 @@ Model &Model::adam(DU lr, DU b1, DU b2)         { return _gradient(OPTI_ADAM, lr
 Model &Model::adamw(DU lr, DU wd, DU b1, DU b2) { return _gradient(OPTI_ADAMW, lr, b1, b2, wd); }      // gradient.cu:159-169
 int Model::arena(DU **G, DU **DG, int64_t *total) {
     if (!_G) grad_alloc(OPTI_ADAM);
-    if (G) *G = _G; if (DG) *DG = _DG; if (total) *total = (int64_t)_total;
+    if (G) *G = _G;
+    if (DG) *DG = _DG;
+    if (total) *total = (int64_t)_total;
     return _G ? 0 : T4K_EINVAL;
 }
 // ---- one train step as a CUDA graph: forward + loss + backprop + optimizer
@@ -538,6 +540,7 @@ int Model::step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_
         forward(input);
         if (loss_dev) loss_async(lop, tgt, loss_dev);
         backprop(tgt);
+        if ((int)op < 0) return;                          // data parallel: the caller all-reduces DG, then calls the optimizer
         switch (op) { case OPTI_SGD: case OPTI_SGDM: sgd(lr, b1); break; case OPTI_ADAM: adam(lr, b1, b2); break; default: adamw(lr, wd, b1, b2); }
     };
     bool has_dropout = false;
@@ -546,7 +549,7 @@ int Model::step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_
     key[0] = (U64)input.data; key[1] = (U64)tgt.data; key[2] = (U64)lop; key[3] = (U64)loss_dev; key[4] = (U64)op;
     memcpy(&key[5], f4, 16); key[7] = (U64)train;
     // SGD's first call forces momentum 0 (host state) and the first optimizer call builds the arenas: run those eagerly
-    if (has_dropout || !_G || _iter == 0) { run(); return 0; }
+    if (has_dropout || !_G || (_iter == 0 && (int)op >= 0)) { run(); return 0; }
     cudaStream_t st = (cudaStream_t)ST;
     if (!_graph_exec || memcmp(key, _graph_key, sizeof(key)) != 0) {
         if (_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)_graph_exec); _graph_exec = nullptr; }
@@ -563,7 +566,7 @@ int Model::step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_
         _graph_exec = ex; memcpy(_graph_key, key, sizeof(key));
         _iter = it;                                   // the captured run did not execute; the launch below is the step
     }
-    _iter++;
+    if ((int)op >= 0) _iter++;
     return (int)cudaGraphLaunch((cudaGraphExec_t)_graph_exec, st);
 }
 
