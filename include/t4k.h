@@ -166,12 +166,14 @@ int t4k_batchnorm_bwd(const float *dO, const float *XH, float *dX, const float *
 /* ---- fused CNN block: conv2d → maxpool(2) → relu (→ flatten), the layer group of examples/t4_40a.4th:11-12.
  * One launch each way; writes exactly the layer tensors the per-layer calls write (forward.cu:83-155,201-228;
  * backprop.cu:112-191,257-280).  Eligible: C1 <= 4, C0 <= 16, even H0/W0, sample fits in shared memory; otherwise
- * T4K_ENOSUP and the caller issues the per-layer calls.  flatO may be NULL (no flatten layer).
+ * T4K_ENOSUP and the caller issues the per-layer calls.  flatO may be NULL (no flatten layer).  Icopy (may be NULL or == I)
+ * receives a copy of I: the `n0 = input` of Model::forward (forward.cu:36-43) folded into the same launch.
  * backward: dY = gradient at the block output (the flatten output tensor, or actO itself when there is no flatten);
  * actO <- dY, poolO <- dY*actF, convO (forward conv output) <- max-pool routed gradient in place,
  * Iio (conv input) <- dX and dXbuf <- dX (Model::_bconv: `in = dx`), dF/dB += when train. */
-int t4k_conv_pool_relu_fwd(const float *I, const float *F, const float *B, float *convO, float *poolO, float *actO, float *actF,
-                           float *flatO, int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, t4k_stream_t s);
+int t4k_conv_pool_relu_fwd(const float *I, const float *F, const float *B, float *Icopy, float *convO, float *poolO, float *actO,
+                           float *actF, float *flatO, int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P,
+                           t4k_stream_t s);
 int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,
                            const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
                            int KS, int S, int P, int train, t4k_stream_t s);

@@ -1,0 +1,457 @@
+// cnn_block.cu — the fused "conv2d → maxpool(2) → relu (→ flatten)" layer group, second generation.
+//   forward : Model::_fconv + _fpool + _factivate (+ flatten copy) (+ the `n0 = input` copy of Model::forward)
+//             src/nn/forward.cu:29-43,83-155,201-228 ; kernels k_conv2d / k_pool / k_activate / k_copy
+//   backward: flatten copy + _bactivate + _bpool + _bconv            src/nn/backprop.cu:112-191,257-280
+// Every tensor the per-layer path writes is still written (n@ / nn.dw show the same values); what changes is
+// that each is touched ONCE: HBM-bound streaming kernels, roofline = algorithmic bytes / HBM bandwidth.
+//
+// Mapping (stride-1 "same" conv, C1 <= 4, C0 <= 16, even H0/W0): one CTA per sample, one THREAD PER 2x2 POOL
+// WINDOW.  A thread owns the window's 4 conv pixels x C0 channels in registers, so
+//   forward : conv (FMA order of k_conv_fwd_small: bias, then ky,kx,c1 — bit-equal), max-pool and relu never leave
+//             registers; the conv output is written as 2 x (2*C0) contiguous floats per thread (128-bit stores,
+//             neighbouring threads neighbouring addresses), pooled tensors as 64-bit stores;
+//   backward: (C1 == 1) the window's forward conv outputs are re-read into registers (128-bit loads) to redo the
+//             arg-max routing (first strict max in y,x order, nmath.tcu:535-549), the routed gradient goes back
+//             to HBM from registers and into a zero-haloed channel-major smem tile for the dX gather;
+//             dF/dB: per-thread partial over its window (3 taps x C0 per pass), reduced across the warp with a
+//             transposing butterfly (31 shuffles per 32 values), across warps in smem, per-sample partials are
+//             summed in sample order by k_wgrad_fin (deterministic; the reference uses atomics, nmath.tcu:307-336).
+// Shapes outside this envelope fall back to the first-generation kernels in conv.cu (same results).
+#include "common.cuh"
+
+namespace t4k {
+
+int cpr_v1_fwd(const float *I, const float *F, const float *B, float *convO, float *poolO, float *actO, float *actF,
+               float *flatO, int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, cudaStream_t st);
+int cpr_v1_bwd(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,
+               const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
+               int KS, int S, int P, int train, cudaStream_t st);
+int wgrad_fin_launch(const float *part, float *dF, float *dB, int nF, int C0, int nparts, int KS, int S, cudaStream_t st);
+
+struct Cpr2P {
+    const float *I, *F, *B, *dY, *actFc;
+    float *Icopy, *convO, *poolO, *actO, *actF, *flatO, *Iio, *dXbuf, *part;
+    int H, W, C1, C0, train;
+};
+
+// ------------------------------------------------------------------ forward
+// C0T = exact channel count known at compile time (static register indexing for the 128-bit stores), 0 = runtime C0 <= CP
+// Global traffic is kept at full-sector granularity: the sample's input arrives as 128-bit loads, the conv pixels
+// leave the registers as 128-bit stores of contiguous 2*C0 runs, the pooled values are staged in smem and the four
+// pooled tensors (pool, relu, mask, flatten) leave as contiguous 128-bit streams.
+template<int KS, int CP, int C0T>
+__global__ void __launch_bounds__(256, 3) k_cpr2_fwd(Cpr2P p) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int P = (KS - 1) / 2;
+    const int H = p.H, W = p.W, C1 = p.C1, C0 = C0T ? C0T : p.C0;
+    const int WP = W + 2 * P, HP = H + 2 * P;
+    const int nFp = KS * KS * C1 * CP;
+    const int Hp = H / 2, Wp = W / 2, nwin = Hp * Wp, nP = nwin * C0;
+    float *sF = sm;                         // [(ky*KS+kx)*C1 + c1][CP]   zero padded channels
+    float *sB = sF + nFp;                   // [CP]
+    float *sP = sB + CP;                    // [nwin][C0] pooled values (staging), 16-byte aligned
+    float *sI = sP + ((nP + 3) & ~3);       // [HP][WP][C1]               zero halo
+    const int n = blockIdx.x;
+    const int nI = H * W * C1;
+    const float *gI = p.I + (int64_t)n * nI;
+    for (int t = threadIdx.x; t < nFp; t += blockDim.x) {
+        const int c = t % CP; int r = t / CP; const int c1 = r % C1; r /= C1;        // r = ky*KS+kx
+        sF[t] = (c < C0) ? __ldg(p.F + ((int64_t)c1 * KS * KS + r) * C0 + c) : 0.0f;
+    }
+    for (int t = threadIdx.x; t < CP; t += blockDim.x) sB[t] = (t < C0) ? __ldg(p.B + t) : 0.0f;
+    // halo zeros, then the interior from 128-bit loads (W*C1 % 4 == 0 and aligned, else scalar)
+    for (int t = threadIdx.x; t < HP * WP * C1; t += blockDim.x) {
+        const int r = t / C1; const int x = r % WP - P, y = r / WP - P;
+        if (x < 0 || x >= W || y < 0 || y >= H) sI[t] = 0.0f;
+    }
+    const int rowf = W * C1;
+    if ((rowf & 3) == 0 && aligned16(p.I) && (!p.Icopy || aligned16(p.Icopy))) {
+        const int rq = rowf >> 2;
+        for (int t = threadIdx.x; t < H * rq; t += blockDim.x) {
+            const int y = t / rq, q = t - y * rq;
+            const float4 v = ldg4(gI + y * rowf + 4 * q);
+            if (p.Icopy) stg4(p.Icopy + (int64_t)n * nI + y * rowf + 4 * q, v);       // Model::forward: n0 = input
+            float *d = sI + ((y + P) * WP + P) * C1 + 4 * q;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    } else {
+        for (int t = threadIdx.x; t < nI; t += blockDim.x) {
+            const int y = t / rowf, q = t - y * rowf;
+            const float v = __ldg(gI + t);
+            if (p.Icopy) p.Icopy[(int64_t)n * nI + t] = v;
+            sI[((y + P) * WP + P) * C1 + q] = v;
+        }
+    }
+    __syncthreads();
+    float *gO = p.convO + (int64_t)n * H * W * C0;
+    constexpr bool VEC = C0T > 0 && (C0T & 1) == 0;        // host checks 16-byte alignment of the tensors
+    for (int w = threadIdx.x; w < nwin; w += blockDim.x) {
+        const int j0 = w % Wp, i0 = w / Wp;
+        float acc[4][CP];
+        #pragma unroll
+        for (int q = 0; q < 4; q++)
+            #pragma unroll
+            for (int c = 0; c < CP; c++) acc[q][c] = sB[c];
+        #pragma unroll
+        for (int ky = 0; ky < KS; ky++) {
+            #pragma unroll
+            for (int kx = 0; kx < KS; kx++) {
+                const float *px = sI + ((2 * i0 + ky) * WP + 2 * j0 + kx) * C1;
+                for (int c1 = 0; c1 < C1; c1++) {
+                    const float v0 = px[c1], v1 = px[C1 + c1], v2_ = px[WP * C1 + c1], v3 = px[(WP + 1) * C1 + c1];
+                    const float4 *f = reinterpret_cast<const float4*>(sF + ((ky * KS + kx) * C1 + c1) * CP);
+                    #pragma unroll
+                    for (int c4 = 0; c4 < CP / 4; c4++) {
+                        const float4 fv = f[c4];
+                        const float ff[4] = {fv.x, fv.y, fv.z, fv.w};
+                        #pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            acc[0][c4 * 4 + k] = fmaf(ff[k], v0, acc[0][c4 * 4 + k]);
+                            acc[1][c4 * 4 + k] = fmaf(ff[k], v1, acc[1][c4 * 4 + k]);
+                            acc[2][c4 * 4 + k] = fmaf(ff[k], v2_, acc[2][c4 * 4 + k]);
+                            acc[3][c4 * 4 + k] = fmaf(ff[k], v3, acc[3][c4 * 4 + k]);
+                        }
+                    }
+                }
+            }
+        }
+        // conv output: rows 2*i0, 2*i0+1; per row the pixel pair is 2*C0 contiguous floats
+        #pragma unroll
+        for (int dy = 0; dy < 2; dy++) {
+            float *o = gO + ((2 * i0 + dy) * W + 2 * j0) * C0;
+            if constexpr (VEC) {
+                // the pixel pair is a run of 2*C0T floats: element e = (pixel e / C0T, channel e % C0T)
+                #pragma unroll
+                for (int e = 0; e < 2 * C0T; e += 4) {
+                    float r[4];
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) r[k] = (e + k < C0T) ? acc[dy * 2][(e + k) % CP] : acc[dy * 2 + 1][(e + k >= C0T ? e + k - C0T : 0)];
+                    stg4(o + e, make_float4(r[0], r[1], r[2], r[3]));
+                }
+            } else {
+                #pragma unroll
+                for (int c = 0; c < CP; c++) if (c < C0) { o[c] = acc[dy * 2][c]; o[C0 + c] = acc[dy * 2 + 1][c]; }
+            }
+        }
+        // max-pool (k_pool<2> order) → staging
+        float *sp = sP + w * C0;
+        #pragma unroll
+        for (int c = 0; c < CP; c++) {
+            float v = acc[0][c];
+            v = fmaxf(acc[1][c], v); v = fmaxf(acc[2][c], v); v = fmaxf(acc[3][c], v);
+            if (c < C0) sp[c] = v;
+        }
+    }
+    __syncthreads();
+    // pooled tensors: pool value, relu (+mask, k_activate RELU), flatten copy — contiguous streams
+    const int64_t gp = (int64_t)n * nP;
+    const bool al = aligned16(p.poolO) && aligned16(p.actO) && aligned16(p.actF) && (!p.flatO || aligned16(p.flatO));
+    if ((nP & 3) == 0 && al) {
+        for (int t = threadIdx.x; t < (nP >> 2); t += blockDim.x) {
+            const float4 v = *reinterpret_cast<const float4*>(sP + 4 * t);
+            float4 a, f;
+            if (v.x > 0.0f) { f.x = 1.0f; a.x = v.x; } else { f.x = 0.0f; a.x = 0.0f; }
+            if (v.y > 0.0f) { f.y = 1.0f; a.y = v.y; } else { f.y = 0.0f; a.y = 0.0f; }
+            if (v.z > 0.0f) { f.z = 1.0f; a.z = v.z; } else { f.z = 0.0f; a.z = 0.0f; }
+            if (v.w > 0.0f) { f.w = 1.0f; a.w = v.w; } else { f.w = 0.0f; a.w = 0.0f; }
+            stg4(p.poolO + gp + 4 * t, v); stg4(p.actO + gp + 4 * t, a); stg4(p.actF + gp + 4 * t, f);
+            if (p.flatO) stg4(p.flatO + gp + 4 * t, a);
+        }
+    } else {
+        for (int t = threadIdx.x; t < nP; t += blockDim.x) {
+            const float v = sP[t];
+            float a, f;
+            if (v > 0.0f) { f = 1.0f; a = v; } else { f = 0.0f; a = 0.0f; }
+            p.poolO[gp + t] = v; p.actO[gp + t] = a; p.actF[gp + t] = f;
+            if (p.flatO) p.flatO[gp + t] = a;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ transposing warp reduction
+// v[0..32) per lane → lane l returns Σ_lanes v[l]   (16+8+4+2+1 = 31 shuffles instead of 32 x 5)
+__device__ __forceinline__ float warp_treduce32(float (&v)[32], int lane) {
+    #pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+        #pragma unroll
+        for (int i = 0; i < o; i++) {
+            const float send = up ? v[i] : v[i + o];
+            const float keep = up ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
+
+// ------------------------------------------------------------------ backward (C1 == 1, KS == 3)
+// CM = compile-time channel bound (multiple of 2): 10 or 16.   Partials: part[n][nF + C0], nF = 9*C0.
+// EXACT: C0 == CM (static register indexing, 128-bit global access)
+template<int CM, bool EXACT>
+__global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int KS = 3, P = 1;
+    constexpr int NG = (3 * CM + 31) / 32;              // 32-value groups per ky pass
+    const int H = p.H, W = p.W, C0 = EXACT ? CM : p.C0;
+    const int WP = W + 2, HP = H + 2;
+    const int RW = (WP + 1) & ~1;                       // even row stride → 8-byte aligned pairs
+    float *sF = sm;                                     // [9][CM] original taps (dX uses the flipped index)
+    float *sI = sF + ((9 * CM + 3) & ~3);               // [HP][WP] zero halo (forward input, C1 == 1)
+    float *sR = sI + ((HP * WP + 3) & ~3);              // [C0][HP][RW] routed gradient, zero halo
+    float *sRed = sR + (((size_t)C0 * HP * RW + 3) & ~(size_t)3);   // [nwarps][3*NG*32 + 32]
+    const int Hp = H / 2, Wp = W / 2, nwin = Hp * Wp, nP = nwin * C0;
+    float *sD = sRed + (size_t)(blockDim.x >> 5) * (3 * NG * 32 + 32);      // [nwin][C0] dY, overwritten with g = dY*mask
+    const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nI = H * W;
+    const int64_t gp = (int64_t)n * nP;
+    const bool alp = (nP & 3) == 0 && aligned16(p.dY) && aligned16(p.actFc) && aligned16(p.actO) && aligned16(p.poolO);
+    if (alp) {                                          // coalesced 128-bit streams of the pooled-size tensors
+        for (int t = threadIdx.x; t < (nP >> 2); t += blockDim.x) {
+            const float4 d = ldg4(p.dY + gp + 4 * t), m = ldg4(p.actFc + gp + 4 * t);
+            if (p.actO != p.dY) stg4(p.actO + gp + 4 * t, d);                         // flatten backward: in = out
+            const float4 g = make_float4(__fmul_rn(d.x, m.x), __fmul_rn(d.y, m.y), __fmul_rn(d.z, m.z), __fmul_rn(d.w, m.w));
+            stg4(p.poolO + gp + 4 * t, g);                                            // _bactivate: in = out * mask
+            *reinterpret_cast<float4*>(sD + 4 * t) = g;
+        }
+    } else {
+        for (int t = threadIdx.x; t < nP; t += blockDim.x) {
+            const float d = p.dY[gp + t];
+            if (p.actO != p.dY) p.actO[gp + t] = d;
+            const float g = __fmul_rn(d, p.actFc[gp + t]);
+            p.poolO[gp + t] = g; sD[t] = g;
+        }
+    }
+    float *gI = p.Iio + (int64_t)n * nI;
+    for (int t = threadIdx.x; t < 9 * CM; t += blockDim.x) { const int c = t % CM, tap = t / CM; sF[t] = (c < C0) ? __ldg(p.F + tap * C0 + c) : 0.0f; }
+    for (int t = threadIdx.x; t < HP * WP; t += blockDim.x) {
+        const int x = t % WP - 1, y = t / WP - 1;
+        sI[t] = (x >= 0 && x < W && y >= 0 && y < H) ? gI[y * W + x] : 0.0f;
+    }
+    for (int t = threadIdx.x; t < C0 * HP * RW; t += blockDim.x) {          // halo (and padding) zeros; interior is overwritten below
+        const int x = t % RW, y = (t / RW) % HP;
+        if (x == 0 || x >= W + 1 || y == 0 || y == H + 1) sR[t] = 0.0f;
+    }
+    __syncthreads();
+    float *gO = p.convO + (int64_t)n * H * W * C0;
+    constexpr bool VEC = EXACT && ((2 * CM) & 3) == 0;
+    const int RSTRIDE = 3 * NG * 32 + 32;
+    float accB[CM];
+    #pragma unroll
+    for (int c = 0; c < CM; c++) accB[c] = 0.0f;
+    float accF[NG * 32];                                  // current ky pass: [kx*CM + c]
+    // a thread may own several windows (nwin > blockDim): the routed values are recomputed per pass from smem
+    for (int ky = 0; ky < 3; ky++) {
+        #pragma unroll
+        for (int g = 0; g < NG * 32; g++) accF[g] = 0.0f;
+        for (int w = threadIdx.x; w < nwin; w += blockDim.x) {
+            const int j0 = w % Wp, i0 = w / Wp;
+            float r[4][CM];
+            if (ky == 0) {
+                // ---- phase A (once): flatten copy, relu backward, arg-max routing, write-back
+                float t_[4][CM];
+                #pragma unroll
+                for (int dy = 0; dy < 2; dy++) {
+                    const float *o = gO + ((2 * i0 + dy) * W + 2 * j0) * C0;
+                    if constexpr (VEC) {
+                        #pragma unroll
+                        for (int e = 0; e < 2 * CM; e += 4) {
+                            const float4 q = *reinterpret_cast<const float4*>(o + e);
+                            const float qq[4] = {q.x, q.y, q.z, q.w};
+                            #pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                if (e + k < CM) t_[dy * 2][(e + k) % CM] = qq[k];
+                                else            t_[dy * 2 + 1][(e + k) % CM] = qq[k];
+                            }
+                        }
+                    } else {
+                        #pragma unroll
+                        for (int c = 0; c < CM; c++) if (c < C0) { t_[dy * 2][c] = o[c]; t_[dy * 2 + 1][c] = o[C0 + c]; }
+                    }
+                }
+                const float *sg = sD + w * C0;
+                #pragma unroll
+                for (int c = 0; c < CM; c++) {
+                    if (c < C0) {
+                        const float g = sg[c];
+                        float best = t_[0][c]; int arg = 0;
+                        if (t_[1][c] > best) { best = t_[1][c]; arg = 1; }
+                        if (t_[2][c] > best) { best = t_[2][c]; arg = 2; }
+                        if (t_[3][c] > best) { best = t_[3][c]; arg = 3; }
+                        r[0][c] = (arg == 0) ? g : 0.0f; r[1][c] = (arg == 1) ? g : 0.0f;
+                        r[2][c] = (arg == 2) ? g : 0.0f; r[3][c] = (arg == 3) ? g : 0.0f;
+                        accB[c] += g;
+                        float *rr = sR + ((size_t)c * HP + 2 * i0 + 1) * RW + 2 * j0 + 1;
+                        rr[0] = r[0][c]; rr[1] = r[1][c]; rr[RW] = r[2][c]; rr[RW + 1] = r[3][c];
+                    } else { r[0][c] = r[1][c] = r[2][c] = r[3][c] = 0.0f; }
+                }
+                #pragma unroll
+                for (int dy = 0; dy < 2; dy++) {
+                    float *o = gO + ((2 * i0 + dy) * W + 2 * j0) * C0;
+                    if constexpr (VEC) {
+                        #pragma unroll
+                        for (int e = 0; e < 2 * CM; e += 4) {
+                            float q[4];
+                            #pragma unroll
+                            for (int k = 0; k < 4; k++) q[k] = (e + k < CM) ? r[dy * 2][(e + k) % CM] : r[dy * 2 + 1][(e + k) % CM];
+                            stg4(o + e, make_float4(q[0], q[1], q[2], q[3]));
+                        }
+                    } else {
+                        #pragma unroll
+                        for (int c = 0; c < CM; c++) if (c < C0) { o[c] = r[dy * 2][c]; o[C0 + c] = r[dy * 2 + 1][c]; }
+                    }
+                }
+            } else {
+                #pragma unroll
+                for (int c = 0; c < CM; c++) {
+                    if (c < C0) {
+                        const float *rr = sR + ((size_t)c * HP + 2 * i0 + 1) * RW + 2 * j0 + 1;
+                        r[0][c] = rr[0]; r[1][c] = rr[1]; r[2][c] = rr[RW]; r[3][c] = rr[RW + 1];
+                    } else { r[0][c] = r[1][c] = r[2][c] = r[3][c] = 0.0f; }
+                }
+            }
+            if (p.train) {
+                // dF[ky][kx][c] += Σ_{pixel (dy,dx) of the window} I[2*i0+dy+ky-1][2*j0+dx+kx-1] * r[dy*2+dx][c]
+                #pragma unroll
+                for (int kx = 0; kx < 3; kx++) {
+                    const float *ip = sI + (2 * i0 + ky) * WP + 2 * j0 + kx;
+                    const float i00 = ip[0], i01 = ip[1], i10 = ip[WP], i11 = ip[WP + 1];
+                    #pragma unroll
+                    for (int c = 0; c < CM; c++) {
+                        float a = accF[kx * CM + c];
+                        a = fmaf(i00, r[0][c], a); a = fmaf(i01, r[1][c], a);
+                        a = fmaf(i10, r[2][c], a); a = fmaf(i11, r[3][c], a);
+                        accF[kx * CM + c] = a;
+                    }
+                }
+            }
+        }
+        if (p.train) {
+            #pragma unroll
+            for (int g = 0; g < NG; g++) {
+                float v[32];
+                #pragma unroll
+                for (int k = 0; k < 32; k++) v[k] = accF[g * 32 + k];
+                const float s = warp_treduce32(v, lane);
+                sRed[warp * RSTRIDE + (ky * NG + g) * 32 + lane] = s;
+            }
+        }
+    }
+    if (p.train) {
+        float v[32];
+        #pragma unroll
+        for (int k = 0; k < 32; k++) v[k] = (k < CM) ? accB[k < CM ? k : 0] : 0.0f;
+        const float s = warp_treduce32(v, lane);
+        sRed[warp * RSTRIDE + 3 * NG * 32 + lane] = s;
+    }
+    __syncthreads();
+    if (p.train) {
+        const int nF = 9 * C0, nE = nF + C0;
+        for (int t = threadIdx.x; t < nE; t += blockDim.x) {
+            int slot;
+            if (t < nF) { const int c = t % C0, kx = (t / C0) % 3, ky = t / (3 * C0); slot = ky * NG * 32 + kx * CM + c; }
+            else slot = 3 * NG * 32 + (t - nF);
+            float s = 0.0f;
+            for (int wv = 0; wv < nwarps; wv++) s += sRed[wv * RSTRIDE + slot];
+            p.part[(int64_t)n * nE + t] = s;
+        }
+    }
+    // ---- dX (flipped taps, nmath.tcu:304): dX[y][x] = Σ_c Σ_{ky,kx} F[2-ky][2-kx][c] * R[y+1-ky][x+1-kx][c]
+    for (int w = threadIdx.x; w < nwin; w += blockDim.x) {
+        const int j0 = w % Wp, i0 = w / Wp;
+        float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+        for (int c = 0; c < C0; c++) {
+            // neighbourhood rows 2*i0 .. 2*i0+3, cols 2*j0 .. 2*j0+3 in halo coordinates
+            const float *rb = sR + ((size_t)c * HP + 2 * i0) * RW + 2 * j0;
+            float nb[4][4];
+            #pragma unroll
+            for (int rr = 0; rr < 4; rr++) {
+                const float2 u = *reinterpret_cast<const float2*>(rb + rr * RW);
+                const float2 v = *reinterpret_cast<const float2*>(rb + rr * RW + 2);
+                nb[rr][0] = u.x; nb[rr][1] = u.y; nb[rr][2] = v.x; nb[rr][3] = v.y;
+            }
+            #pragma unroll
+            for (int ky = 0; ky < 3; ky++) {
+                #pragma unroll
+                for (int kx = 0; kx < 3; kx++) {
+                    const float f = sF[((2 - ky) * 3 + (2 - kx)) * CM + c];
+                    // pixel (dy,dx): halo row = 2*i0+dy + 2 - ky → nb row dy + 2 - ky ; col dx + 2 - kx
+                    a00 = fmaf(f, nb[2 - ky][2 - kx], a00);
+                    a01 = fmaf(f, nb[2 - ky][3 - kx], a01);
+                    a10 = fmaf(f, nb[3 - ky][2 - kx], a10);
+                    a11 = fmaf(f, nb[3 - ky][3 - kx], a11);
+                }
+            }
+        }
+        float *o = gI + (2 * i0) * W + 2 * j0;
+        float *b = p.dXbuf + (int64_t)n * nI + (2 * i0) * W + 2 * j0;
+        *reinterpret_cast<float2*>(o) = make_float2(a00, a01); *reinterpret_cast<float2*>(o + W) = make_float2(a10, a11);
+        *reinterpret_cast<float2*>(b) = make_float2(a00, a01); *reinterpret_cast<float2*>(b + W) = make_float2(a10, a11);
+    }
+}
+
+static bool cpr2_fwd_ok(int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, int *CP, size_t *smem) {
+    if (!(KS == 3 || KS == 5) || S != 1 || P != (KS - 1) / 2 || H0 != H1 || W0 != W1) return false;
+    if (C1 > 4 || C0 > 16 || (H0 & 1) || (W0 & 1)) return false;
+    *CP = (C0 <= 4) ? 4 : (C0 <= 8) ? 8 : (C0 <= 12) ? 12 : 16;
+    const size_t nP = (size_t)(H0 / 2) * (W0 / 2) * C0;
+    *smem = ((size_t)KS * KS * C1 * *CP + *CP + ((nP + 3) & ~(size_t)3) + (size_t)(H1 + 2 * P) * (W1 + 2 * P) * C1) * sizeof(float);
+    return *smem <= 96 * 1024;
+}
+static bool cpr2_bwd_ok(int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, int *CM, size_t *smem, int threads) {
+    if (KS != 3 || S != 1 || P != 1 || H0 != H1 || W0 != W1 || C1 != 1 || C0 > 16 || (H0 & 1) || (W0 & 1)) return false;
+    *CM = (C0 <= 10) ? 10 : 16;
+    const int NG = (3 * *CM + 31) / 32;
+    const int HP = H1 + 2, WP = W1 + 2, RW = (WP + 1) & ~1;
+    const size_t nP = (size_t)(H0 / 2) * (W0 / 2) * C0;
+    *smem = ((size_t)((9 * *CM + 3) & ~3) + ((HP * WP + 3) & ~3) + (((size_t)C0 * HP * RW + 3) & ~(size_t)3) + (size_t)(threads / 32) * (3 * NG * 32 + 32) +
+             ((nP + 3) & ~(size_t)3)) * sizeof(float);
+    return *smem <= 100 * 1024 && (W1 & 1) == 0;
+}
+static int win_threads(int nwin) { int t = (nwin + 31) & ~31; return t > 256 ? 256 : (t < 32 ? 32 : t); }
+
+} // namespace t4k
+using namespace t4k;
+
+extern "C" int t4k_conv_pool_relu_fwd(const float *I, const float *F, const float *B, float *Icopy, float *convO, float *poolO,
+                                      float *actO, float *actF, float *flatO, int N, int H1, int W1, int C1, int H0, int W0,
+                                      int C0, int KS, int S, int P, t4k_stream_t s) {
+    if (!I || !F || !B || !convO || !poolO || !actO || !actF || N < 1) return T4K_EINVAL;
+    int CP = 0; size_t smem = 0;
+    if (!cpr2_fwd_ok(H1, W1, C1, H0, W0, C0, KS, S, P, &CP, &smem)) {
+        if (Icopy && Icopy != I) { int rc = t4k_copy(I, Icopy, (int64_t)N * H1 * W1 * C1, s); if (rc) return rc; }
+        return cpr_v1_fwd(I, F, B, convO, poolO, actO, actF, flatO, N, H1, W1, C1, H0, W0, C0, KS, S, P, STRM(s));
+    }
+    Cpr2P p{}; p.I = I; p.F = F; p.B = B; p.Icopy = (Icopy == I) ? nullptr : Icopy; p.convO = convO; p.poolO = poolO; p.actO = actO;
+    p.actF = actF; p.flatO = flatO; p.H = H1; p.W = W1; p.C1 = C1; p.C0 = C0;
+    const int threads = win_threads((H0 / 2) * (W0 / 2));
+    const bool al = aligned16(convO) && aligned16(poolO) && aligned16(actO) && aligned16(actF) && (!flatO || aligned16(flatO));
+    #define CPR2F(K_, CP_, CT_) { static bool attr = false; if (!attr && smem > 48 * 1024) { cudaFuncSetAttribute(k_cpr2_fwd<K_, CP_, CT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; } \
+                                  k_cpr2_fwd<K_, CP_, CT_><<<N, threads, smem, STRM(s)>>>(p); }
+    if (KS == 3) {
+        if (al && C0 == 10) CPR2F(3, 12, 10) else if (al && C0 == 16) CPR2F(3, 16, 16) else if (al && C0 == 8) CPR2F(3, 8, 8)
+        else switch (CP) { case 4: CPR2F(3, 4, 0) break; case 8: CPR2F(3, 8, 0) break; case 12: CPR2F(3, 12, 0) break; default: CPR2F(3, 16, 0) break; }
+    } else {
+        switch (CP) { case 4: CPR2F(5, 4, 0) break; case 8: CPR2F(5, 8, 0) break; case 12: CPR2F(5, 12, 0) break; default: CPR2F(5, 16, 0) break; }
+    }
+    return check_launch();
+}
+
+extern "C" int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,
+                                      const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
+                                      int KS, int S, int P, int train, t4k_stream_t s) {
+    if (!dY || !actO || !actF || !poolO || !convO || !Iio || !dXbuf || !F || N < 1 || (train && (!dF || !dB))) return T4K_EINVAL;
+    int CM = 0; size_t smem = 0;
+    const int threads = win_threads((H0 / 2) * (W0 / 2));
+    if (!cpr2_bwd_ok(H1, W1, C1, H0, W0, C0, KS, S, P, &CM, &smem, threads))
+        return cpr_v1_bwd(dY, actO, actF, poolO, convO, Iio, dXbuf, F, dF, dB, N, H1, W1, C1, H0, W0, C0, KS, S, P, train, STRM(s));
+    const int nF = 9 * C0;
+    Cpr2P p{}; p.F = F; p.dY = dY; p.actFc = actF; p.actO = actO; p.poolO = poolO; p.convO = convO; p.Iio = Iio; p.dXbuf = dXbuf;
+    p.H = H1; p.W = W1; p.C1 = 1; p.C0 = C0; p.train = train;
+    if (train) { p.part = (float*)workspace((size_t)N * (nF + C0) * sizeof(float), 4); if (!p.part) return T4K_ENOMEM; }
+    const bool ex = (C0 == CM) && aligned16(convO);
+    #define CPR2B(CM_, EX_) { static bool attr = false; if (!attr && smem > 48 * 1024) { cudaFuncSetAttribute(k_cpr2_bwd<CM_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+                              k_cpr2_bwd<CM_, EX_><<<N, threads, smem, STRM(s)>>>(p); }
+    if (CM == 10) { if (ex) CPR2B(10, true) else CPR2B(10, false) } else { if (ex) CPR2B(16, true) else CPR2B(16, false) }
+    int rc = check_launch(); if (rc || !train) return rc;
+    return wgrad_fin_launch(p.part, dF, dB, nF, C0, N, KS, S, STRM(s));
+}

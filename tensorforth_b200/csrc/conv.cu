@@ -643,8 +643,9 @@ extern "C" int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, f
 }
 
 // ---- fused conv → maxpool(2) → relu (→ flatten) block; T4K_ENOSUP when the shape is not eligible (caller: per-layer calls)
-extern "C" int t4k_conv_pool_relu_fwd(const float *I, const float *F, const float *B, float *convO, float *poolO, float *actO, float *actF,
-                                      float *flatO, int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, t4k_stream_t s) {
+namespace t4k {
+int cpr_v1_fwd(const float *I, const float *F, const float *B, float *convO, float *poolO, float *actO, float *actF,
+               float *flatO, int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, cudaStream_t s) {
     if (!I || !F || !B || !convO || !poolO || !actO || !actF || N < 1) return T4K_EINVAL;
     size_t smem = 0;
     if (!cpr_ok(H1, W1, C1, H0, W0, C0, KS, S, P, &smem)) return T4K_ENOSUP;
@@ -652,13 +653,13 @@ extern "C" int t4k_conv_pool_relu_fwd(const float *I, const float *F, const floa
     p.H1 = H1; p.W1 = W1; p.C1 = C1; p.H0 = H0; p.W0 = W0; p.C0 = C0; p.S = S; p.P = P;
     static bool attr[6] = {false};
     #define CPRF(K_) { if (!attr[K_] && smem > 48 * 1024) { cudaFuncSetAttribute(k_cpr_fwd<K_, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr[K_] = true; } \
-                       k_cpr_fwd<K_, 16><<<N, T4K_THREADS, smem, STRM(s)>>>(p); }
+                       k_cpr_fwd<K_, 16><<<N, T4K_THREADS, smem, s>>>(p); }
     switch (KS) { case 1: CPRF(1) break; case 3: CPRF(3) break; case 4: CPRF(4) break; default: CPRF(5) break; }
     return check_launch();
 }
-extern "C" int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,
-                                      const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
-                                      int KS, int S, int P, int train, t4k_stream_t s) {
+int cpr_v1_bwd(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,
+               const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
+               int KS, int S, int P, int train, cudaStream_t s) {
     if (!dY || !actO || !actF || !poolO || !convO || !Iio || !dXbuf || !F || N < 1 || (train && (!dF || !dB))) return T4K_EINVAL;
     size_t smem = 0;
     if (!cpr_ok(H1, W1, C1, H0, W0, C0, KS, S, P, &smem)) return T4K_ENOSUP;
@@ -668,9 +669,14 @@ extern "C" int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float 
     if (train) { p.part = (float*)workspace((size_t)N * (nF + C0) * sizeof(float), 4); if (!p.part) return T4K_ENOMEM; }
     static bool attr[6] = {false};
     #define CPRB(K_) { if (!attr[K_] && smem > 40 * 1024) { cudaFuncSetAttribute(k_cpr_bwd<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr[K_] = true; } \
-                       k_cpr_bwd<K_><<<N, T4K_THREADS, smem, STRM(s)>>>(p); }
+                       k_cpr_bwd<K_><<<N, T4K_THREADS, smem, s>>>(p); }
     switch (KS) { case 1: CPRB(1) break; case 3: CPRB(3) break; case 4: CPRB(4) break; default: CPRB(5) break; }
     int rc = check_launch(); if (rc || !train) return rc;
-    k_wgrad_fin<<<nF + C0, T4K_THREADS, 0, STRM(s)>>>(p.part, dF, dB, nF, C0, N, KS, S);
+    k_wgrad_fin<<<nF + C0, T4K_THREADS, 0, s>>>(p.part, dF, dB, nF, C0, N, KS, S);
     return check_launch();
 }
+int wgrad_fin_launch(const float *part, float *dF, float *dB, int nF, int C0, int nparts, int KS, int S, cudaStream_t st) {
+    k_wgrad_fin<<<nF + C0, T4K_THREADS, 0, st>>>(part, dF, dB, nF, C0, nparts, KS, S);
+    return check_launch();
+}
+} // namespace t4k

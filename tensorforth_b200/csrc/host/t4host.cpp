@@ -269,8 +269,12 @@ Model &Model::forward(Tensor &input) {
                        input.N(), input.H(), input.W(), input.C(), n0.N(), n0.H(), n0.W(), n0.C());
         return *this;
     }
-    if (input.data != n0.data) n0 = input;
-    for (size_t i = 0; i + 1 < _layers.size(); ) {
+    size_t i0 = 0;
+    if (input.data != n0.data) {
+        i0 = (size_t)_ffused(0, input.data);               // first block fused: the `n0 = input` copy rides in the same launch
+        if (!i0) n0 = input;
+    }
+    for (size_t i = i0; i + 1 < _layers.size(); ) {
         const int adv = _ffused(i);                        // conv → maxpool(2) → relu (→ flatten) in one launch
         if (adv) { i += adv; continue; }
         _fstep(*_layers[i], *_layers[i + 1]); i++;
@@ -279,14 +283,14 @@ Model &Model::forward(Tensor &input) {
 }
 // The canonical CNN block of the reference's examples ("conv2d 2 maxpool relu [flatten]", t4_40a.4th:11-12):
 // same layer tensors written as the per-layer path (forward.cu:83-113), one kernel.  Returns layers consumed.
-int Model::_ffused(size_t i) {
+int Model::_ffused(size_t i, const DU *src) {
     const size_t n = _layers.size();
     if (!fuse || i + 3 >= n) return 0;
     Tensor &in = *_layers[i], &co = *_layers[i + 1], &po = *_layers[i + 2], &ao = *_layers[i + 3];
     if (in.grad_fn != T4K_L_CONV || co.grad_fn != T4K_L_MAXPOOL || co.stride[0] != 2 || po.grad_fn != T4K_L_RELU) return 0;
     Tensor *fl = (ao.grad_fn == T4K_L_FLATTEN && i + 4 < n) ? _layers[i + 4] : nullptr;
     Tensor &f = *in.grad[0], &b = *in.grad[1];
-    int rc = t4k_conv_pool_relu_fwd(in.data, f.data, b.data, co.data, po.data, ao.data, po.grad[4]->data, fl ? fl->data : nullptr,
+    int rc = t4k_conv_pool_relu_fwd(src ? src : in.data, f.data, b.data, src ? in.data : nullptr, co.data, po.data, ao.data, po.grad[4]->data, fl ? fl->data : nullptr,
                                     co.N(), in.H(), in.W(), in.C(), co.H(), co.W(), co.C(), f.H(), in.stride[0], in.stride[2], ST);
     if (rc == T4K_ENOSUP) return 0;
     KCHK(rc);

@@ -176,7 +176,7 @@ private:
     void _ibatchnorm(Tensor &in, DU m);
     void _iup(Tensor &in, U16 f, DU m);
     void _fstep(Tensor &in, Tensor &out);
-    int  _ffused(size_t i);
+    int  _ffused(size_t i, const DU *src = nullptr);
     int  _bfused(int i);
     int  _fconv(Tensor &in, Tensor &out);
     int  _flinear(Tensor &in, Tensor &out);

@@ -67,6 +67,23 @@ def conv(n=256, c=64, hw=56, engine=t4.GEMM_AUTO):
     L.t4k_set_conv_engine(t4.GEMM_AUTO)
 
 
+def cpr(n=512, c0=10, hw=28):
+    f32 = lambda *s: torch.empty(*s, device="cuda").uniform_(-1, 1)
+    I, F, B = f32(n, hw, hw, 1), f32(1, 3, 3, c0), f32(c0)
+    I0 = torch.empty_like(I)
+    cO, pO, aO, aF, fO = f32(n, hw, hw, c0), f32(n, hw // 2, hw // 2, c0), f32(n, hw // 2, hw // 2, c0), f32(n, hw // 2, hw // 2, c0), f32(n, hw // 2, hw // 2, c0)
+    dY, dXb, dF, dB = f32(n, hw // 2, hw // 2, c0), torch.empty_like(I), torch.zeros_like(F), torch.zeros_like(B)
+    fwd = lambda: t4.check(L.t4k_conv_pool_relu_fwd(p(I), p(F), p(B), p(I0), p(cO), p(pO), p(aO), p(aF), p(fO), n, hw, hw, 1, hw, hw, c0, 3, 1, 1, None))
+    ms = timeit(fwd, iters=50)
+    by = (2 * I.numel() + cO.numel() + 4 * pO.numel()) * 4
+    print("cpr fwd N=%d: %.2f us  %.0f GB/s (alg %.1f MB)" % (n, ms * 1e3, by / ms / 1e6, by / 1e6))
+    def bwd():
+        t4.check(L.t4k_conv_pool_relu_bwd(p(dY), p(aO), p(aF), p(pO), p(cO), p(I0), p(dXb), p(F), p(dF), p(dB), n, hw, hw, 1, hw, hw, c0, 3, 1, 1, 1, None))
+    fwd(); ms = timeit(bwd, iters=50)
+    by = (dY.numel() * 4 + 2 * cO.numel() + 3 * I.numel()) * 4
+    print("cpr bwd N=%d: %.2f us  %.0f GB/s (alg %.1f MB)" % (n, ms * 1e3, by / ms / 1e6, by / 1e6))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "gemm"):
@@ -76,5 +93,7 @@ if __name__ == "__main__":
     if what in ("all", "conv"):
         conv(256)
         conv(64, engine=t4.GEMM_SIMT)
+    if what in ("all", "cpr"):
+        cpr()
     if what in ("all", "stream"):
         stream()

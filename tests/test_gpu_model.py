@@ -280,7 +280,10 @@ def test_fused_block_equals_per_layer(kind, N):
     n2 = t4.load().t4k_launch_count()
     assert n1 - n0 < n2 - n1                                   # fewer launches
     for i in range(len(ga)):
-        assert np.array_equal(ga.layer(i).numpy(), gb.layer(i).numpy()), "layer %d" % i
+        if i == 0:      # layer 0 holds dX after backprop: FP sums, the fused kernel gathers channel-outer (order differs)
+            assert_close(ga.layer(i).numpy(), gb.layer(i).numpy(), rtol=1e-5, what="dX")
+        else:           # activations, relu masks, arg-max routed gradients: bit-equal
+            assert np.array_equal(ga.layer(i).numpy(), gb.layer(i).numpy()), "layer %d" % i
     for i in range(len(ga) - 1):
         if ga.dw(i) is not None and ga.w(i) is not None and ga.db(i) is not None:
             assert_close(ga.dw(i).numpy(), gb.dw(i).numpy(), rtol=1e-5, what="dw%d" % i)
