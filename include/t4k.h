@@ -117,6 +117,13 @@ int t4k_gemm_ex(int engine, const float *A, const float *B, float *O, float alph
 int t4k_bias(const float *B, float *Y, int N, int E0, t4k_stream_t s);
 /* Model::_flinear (forward.cu:158-198): Y[N,E0] = X[N,E1] @ W[E0,E1]^T + B[E0]  (GEMM + fused bias) */
 int t4k_linear_fwd(const float *X, const float *W, const float *B, float *Y, int N, int E0, int E1, t4k_stream_t s);
+/* _flinear + the following _factivate in one pass (the bias, activation and mask ride in the GEMM's split-K finish):
+ * Y = X @ W^T + B (the linear layer's output tensor), A = act(Y), F = saved derivative / mask; layer as t4k_activate_fwd */
+int t4k_linear_act_fwd(int layer, const float *X, const float *W, const float *B, float *Y, float *A, float *F, float alpha,
+                       int N, int E0, int E1, t4k_stream_t s);
+/* classifier head, forward: small linear (E0 <= 32, W <= 40 KB) + bias + row softmax in one launch (forward.cu:158-198,231-243):
+ * Y = X @ W^T + B, P = softmax(Y).  T4K_ENOSUP when the head is not small (caller: t4k_linear_fwd + t4k_softmax_fwd) */
+int t4k_mlp_head_fwd(const float *X, const float *W, const float *B, float *Y, float *P, int N, int E0, int E1, t4k_stream_t s);
 /* k_activate (nmath.cu:37-70, forward.cu:201-209): writes O and the saved derivative/mask F.
  * layer in RELU,TANH,SIGMOID,SELU,LEAKYRL,ELU,DROPOUT; for DROPOUT F holds U(0,1] on entry. */
 int t4k_activate_fwd(int layer, const float *I, float *O, float *F, float alpha, int64_t n, t4k_stream_t s);
@@ -148,6 +155,16 @@ int t4k_dbias(const float *dY, float *dB, int N, int E0, t4k_stream_t s);
  * dX may alias X's buffer?  NO — dW needs X; pass distinct buffers or dX==X (handled: dW first). */
 int t4k_linear_bwd(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
                    int N, int E0, int E1, int train, t4k_stream_t s);
+/* as t4k_linear_bwd; skip_db != 0 leaves dB alone (it was accumulated by t4k_mlp_head_bwd) */
+int t4k_linear_bwd_ex(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
+                      int N, int E0, int E1, int train, int skip_db, t4k_stream_t s);
+/* classifier head, backward, one launch (backprop.cu:76-140,194-263), E0 <= 32, E1 <= 128 else T4K_ENOSUP:
+ *   P <- P - T (Model::_bprep), Ylin <- P - T (softmax backward is a copy), dB += Σ_n (P-T), dW += (P-T)^T @ X2,
+ *   X2 <- (P-T) @ W (in place: the small linear's input tensor receives its dX),
+ *   if F1: Y1 <- X2 * F1 (backward of the activation in front), dB1 (may be NULL) += Σ_n Y1 (bias gradient of the linear
+ *   in front of that activation; without F1 it accumulates Σ_n X2).  dW/dB/dB1 only when train. */
+int t4k_mlp_head_bwd(float *P, const float *T, float *Ylin, float *X2, const float *F1, float *Y1, const float *W,
+                     float *dW, float *dB, float *dB1, int N, int E0, int E1, int train, t4k_stream_t s);
 /* Model::_bactivate (backprop.cu:257-263): dX = dY * F */
 int t4k_activate_bwd(const float *dY, const float *F, float *dX, int64_t n, t4k_stream_t s);
 /* k_dconv2d (nmath.tcu:211-338, backprop.cu:153-191): dX written in full (no pre-zero needed),

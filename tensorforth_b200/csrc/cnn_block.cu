@@ -39,11 +39,11 @@ struct Cpr2P {
 // Global traffic is kept at full-sector granularity: the sample's input arrives as 128-bit loads, the conv pixels
 // leave the registers as 128-bit stores of contiguous 2*C0 runs, the pooled values are staged in smem and the four
 // pooled tensors (pool, relu, mask, flatten) leave as contiguous 128-bit streams.
-template<int KS, int CP, int C0T>
+template<int KS, int CP, int C0T, int C1T>
 __global__ void __launch_bounds__(256, 3) k_cpr2_fwd(Cpr2P p) {
     extern __shared__ __align__(16) float sm[];
     constexpr int P = (KS - 1) / 2;
-    const int H = p.H, W = p.W, C1 = p.C1, C0 = C0T ? C0T : p.C0;
+    const int H = p.H, W = p.W, C1 = C1T ? C1T : p.C1, C0 = C0T ? C0T : p.C0;
     const int WP = W + 2 * P, HP = H + 2 * P;
     const int nFp = KS * KS * C1 * CP;
     const int Hp = H / 2, Wp = W / 2, nwin = Hp * Wp, nP = nwin * C0;
@@ -59,10 +59,12 @@ __global__ void __launch_bounds__(256, 3) k_cpr2_fwd(Cpr2P p) {
         sF[t] = (c < C0) ? __ldg(p.F + ((int64_t)c1 * KS * KS + r) * C0 + c) : 0.0f;
     }
     for (int t = threadIdx.x; t < CP; t += blockDim.x) sB[t] = (t < C0) ? __ldg(p.B + t) : 0.0f;
-    // halo zeros, then the interior from 128-bit loads (W*C1 % 4 == 0 and aligned, else scalar)
-    for (int t = threadIdx.x; t < HP * WP * C1; t += blockDim.x) {
-        const int r = t / C1; const int x = r % WP - P, y = r / WP - P;
-        if (x < 0 || x >= W || y < 0 || y >= H) sI[t] = 0.0f;
+    // halo zeros (top/bottom rows, left/right columns), then the interior from 128-bit loads (else scalar)
+    const int rowp = WP * C1;
+    for (int t = threadIdx.x; t < P * rowp; t += blockDim.x) { sI[t] = 0.0f; sI[(HP - P) * rowp + t] = 0.0f; }
+    for (int t = threadIdx.x; t < H * P * C1; t += blockDim.x) {
+        const int y = t / (P * C1), q = t - y * (P * C1);
+        sI[(y + P) * rowp + q] = 0.0f; sI[(y + P) * rowp + (W + P) * C1 + q] = 0.0f;
     }
     const int rowf = W * C1;
     if ((rowf & 3) == 0 && aligned16(p.I) && (!p.Icopy || aligned16(p.Icopy))) {
@@ -97,7 +99,9 @@ __global__ void __launch_bounds__(256, 3) k_cpr2_fwd(Cpr2P p) {
             #pragma unroll
             for (int kx = 0; kx < KS; kx++) {
                 const float *px = sI + ((2 * i0 + ky) * WP + 2 * j0 + kx) * C1;
-                for (int c1 = 0; c1 < C1; c1++) {
+                #pragma unroll
+                for (int c1 = 0; c1 < (C1T ? C1T : 4); c1++) {
+                    if (c1 >= C1) break;
                     const float v0 = px[c1], v1 = px[C1 + c1], v2_ = px[WP * C1 + c1], v3 = px[(WP + 1) * C1 + c1];
                     const float4 *f = reinterpret_cast<const float4*>(sF + ((ky * KS + kx) * C1 + c1) * CP);
                     #pragma unroll
@@ -196,7 +200,8 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
     const int WP = W + 2, HP = H + 2;
     const int RW = (WP + 1) & ~1;                       // even row stride → 8-byte aligned pairs
     float *sF = sm;                                     // [9][CM] original taps (dX uses the flipped index)
-    float *sI = sF + ((9 * CM + 3) & ~3);               // [HP][WP] zero halo (forward input, C1 == 1)
+    float *sFx = sF + ((9 * CM + 3) & ~3);              // [CM][12] flipped taps, channel-major (dX gather: 3 x 128-bit per channel)
+    float *sI = sFx + 12 * CM;                          // [HP][WP] zero halo (forward input, C1 == 1)
     float *sR = sI + ((HP * WP + 3) & ~3);              // [C0][HP][RW] routed gradient, zero halo
     float *sRed = sR + (((size_t)C0 * HP * RW + 3) & ~(size_t)3);   // [nwarps][3*NG*32 + 32]
     const int Hp = H / 2, Wp = W / 2, nwin = Hp * Wp, nP = nwin * C0;
@@ -223,18 +228,29 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
     }
     float *gI = p.Iio + (int64_t)n * nI;
     for (int t = threadIdx.x; t < 9 * CM; t += blockDim.x) { const int c = t % CM, tap = t / CM; sF[t] = (c < C0) ? __ldg(p.F + tap * C0 + c) : 0.0f; }
-    for (int t = threadIdx.x; t < HP * WP; t += blockDim.x) {
-        const int x = t % WP - 1, y = t / WP - 1;
-        sI[t] = (x >= 0 && x < W && y >= 0 && y < H) ? gI[y * W + x] : 0.0f;
+    for (int t = threadIdx.x; t < 12 * CM; t += blockDim.x) { const int k = t % 12, c = t / 12; sFx[t] = (c < C0 && k < 9) ? __ldg(p.F + (8 - k) * C0 + c) : 0.0f; }
+    for (int t = threadIdx.x; t < WP; t += blockDim.x) { sI[t] = 0.0f; sI[(HP - 1) * WP + t] = 0.0f; }
+    for (int t = threadIdx.x; t < H; t += blockDim.x) { sI[(t + 1) * WP] = 0.0f; sI[(t + 1) * WP + W + 1] = 0.0f; }
+    if ((W & 3) == 0 && aligned16(p.Iio)) {
+        const int rq = W >> 2;
+        for (int t = threadIdx.x; t < H * rq; t += blockDim.x) {
+            const int y = t / rq, q = t - y * rq;
+            const float4 v = *reinterpret_cast<const float4*>(gI + y * W + 4 * q);
+            float *d = sI + (y + 1) * WP + 1 + 4 * q;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    } else {
+        for (int t = threadIdx.x; t < nI; t += blockDim.x) { const int y = t / W; sI[(y + 1) * WP + 1 + (t - y * W)] = gI[t]; }
     }
-    for (int t = threadIdx.x; t < C0 * HP * RW; t += blockDim.x) {          // halo (and padding) zeros; interior is overwritten below
-        const int x = t % RW, y = (t / RW) % HP;
-        if (x == 0 || x >= W + 1 || y == 0 || y == H + 1) sR[t] = 0.0f;
+    {   // zero the whole routed tile (halo + padding stay zero; the interior is overwritten in phase A after the barrier)
+        const int nq = (int)((((size_t)C0 * HP * RW + 3) & ~(size_t)3) >> 2);
+        for (int t = threadIdx.x; t < nq; t += blockDim.x) *reinterpret_cast<float4*>(sR + 4 * t) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
     float *gO = p.convO + (int64_t)n * H * W * C0;
     constexpr bool VEC = EXACT && ((2 * CM) & 3) == 0;
     const int RSTRIDE = 3 * NG * 32 + 32;
+    const int cs = HP * RW;                               // channel stride of the routed tile
     float accB[CM];
     #pragma unroll
     for (int c = 0; c < CM; c++) accB[c] = 0.0f;
@@ -245,6 +261,7 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
         for (int g = 0; g < NG * 32; g++) accF[g] = 0.0f;
         for (int w = threadIdx.x; w < nwin; w += blockDim.x) {
             const int j0 = w % Wp, i0 = w / Wp;
+            const int rb0 = 2 * i0 * RW + 2 * j0;          // window origin in the haloed routed tile (row 2*i0, col 2*j0)
             float r[4][CM];
             if (ky == 0) {
                 // ---- phase A (once): flatten copy, relu backward, arg-max routing, write-back
@@ -280,7 +297,7 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
                         r[0][c] = (arg == 0) ? g : 0.0f; r[1][c] = (arg == 1) ? g : 0.0f;
                         r[2][c] = (arg == 2) ? g : 0.0f; r[3][c] = (arg == 3) ? g : 0.0f;
                         accB[c] += g;
-                        float *rr = sR + ((size_t)c * HP + 2 * i0 + 1) * RW + 2 * j0 + 1;
+                        float *rr = sR + c * cs + rb0 + RW + 1;
                         rr[0] = r[0][c]; rr[1] = r[1][c]; rr[RW] = r[2][c]; rr[RW + 1] = r[3][c];
                     } else { r[0][c] = r[1][c] = r[2][c] = r[3][c] = 0.0f; }
                 }
@@ -304,7 +321,7 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
                 #pragma unroll
                 for (int c = 0; c < CM; c++) {
                     if (c < C0) {
-                        const float *rr = sR + ((size_t)c * HP + 2 * i0 + 1) * RW + 2 * j0 + 1;
+                        const float *rr = sR + c * cs + rb0 + RW + 1;
                         r[0][c] = rr[0]; r[1][c] = rr[1]; r[2][c] = rr[RW]; r[3][c] = rr[RW + 1];
                     } else { r[0][c] = r[1][c] = r[2][c] = r[3][c] = 0.0f; }
                 }
@@ -361,7 +378,7 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
         float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
         for (int c = 0; c < C0; c++) {
             // neighbourhood rows 2*i0 .. 2*i0+3, cols 2*j0 .. 2*j0+3 in halo coordinates
-            const float *rb = sR + ((size_t)c * HP + 2 * i0) * RW + 2 * j0;
+            const float *rb = sR + c * cs + 2 * i0 * RW + 2 * j0;
             float nb[4][4];
             #pragma unroll
             for (int rr = 0; rr < 4; rr++) {
@@ -369,11 +386,17 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
                 const float2 v = *reinterpret_cast<const float2*>(rb + rr * RW + 2);
                 nb[rr][0] = u.x; nb[rr][1] = u.y; nb[rr][2] = v.x; nb[rr][3] = v.y;
             }
+            float fx[12];
+            #pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const float4 fq = *reinterpret_cast<const float4*>(sFx + c * 12 + 4 * q);
+                fx[4 * q] = fq.x; fx[4 * q + 1] = fq.y; fx[4 * q + 2] = fq.z; fx[4 * q + 3] = fq.w;
+            }
             #pragma unroll
             for (int ky = 0; ky < 3; ky++) {
                 #pragma unroll
                 for (int kx = 0; kx < 3; kx++) {
-                    const float f = sF[((2 - ky) * 3 + (2 - kx)) * CM + c];
+                    const float f = fx[ky * 3 + kx];               // = F[2-ky][2-kx][c]
                     // pixel (dy,dx): halo row = 2*i0+dy + 2 - ky → nb row dy + 2 - ky ; col dx + 2 - kx
                     a00 = fmaf(f, nb[2 - ky][2 - kx], a00);
                     a01 = fmaf(f, nb[2 - ky][3 - kx], a01);
@@ -403,7 +426,7 @@ static bool cpr2_bwd_ok(int H1, int W1, int C1, int H0, int W0, int C0, int KS, 
     const int NG = (3 * *CM + 31) / 32;
     const int HP = H1 + 2, WP = W1 + 2, RW = (WP + 1) & ~1;
     const size_t nP = (size_t)(H0 / 2) * (W0 / 2) * C0;
-    *smem = ((size_t)((9 * *CM + 3) & ~3) + ((HP * WP + 3) & ~3) + (((size_t)C0 * HP * RW + 3) & ~(size_t)3) + (size_t)(threads / 32) * (3 * NG * 32 + 32) +
+    *smem = ((size_t)((9 * *CM + 3) & ~3) + 12 * *CM + ((HP * WP + 3) & ~3) + (((size_t)C0 * HP * RW + 3) & ~(size_t)3) + (size_t)(threads / 32) * (3 * NG * 32 + 32) +
              ((nP + 3) & ~(size_t)3)) * sizeof(float);
     return *smem <= 100 * 1024 && (W1 & 1) == 0;
 }
@@ -425,13 +448,13 @@ extern "C" int t4k_conv_pool_relu_fwd(const float *I, const float *F, const floa
     p.actF = actF; p.flatO = flatO; p.H = H1; p.W = W1; p.C1 = C1; p.C0 = C0;
     const int threads = win_threads((H0 / 2) * (W0 / 2));
     const bool al = aligned16(convO) && aligned16(poolO) && aligned16(actO) && aligned16(actF) && (!flatO || aligned16(flatO));
-    #define CPR2F(K_, CP_, CT_) { static bool attr = false; if (!attr && smem > 48 * 1024) { cudaFuncSetAttribute(k_cpr2_fwd<K_, CP_, CT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; } \
-                                  k_cpr2_fwd<K_, CP_, CT_><<<N, threads, smem, STRM(s)>>>(p); }
+    #define CPR2F(K_, CP_, CT_, C1_) { static bool attr = false; if (!attr && smem > 48 * 1024) { cudaFuncSetAttribute(k_cpr2_fwd<K_, CP_, CT_, C1_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; } \
+                                  k_cpr2_fwd<K_, CP_, CT_, C1_><<<N, threads, smem, STRM(s)>>>(p); }
     if (KS == 3) {
-        if (al && C0 == 10) CPR2F(3, 12, 10) else if (al && C0 == 16) CPR2F(3, 16, 16) else if (al && C0 == 8) CPR2F(3, 8, 8)
-        else switch (CP) { case 4: CPR2F(3, 4, 0) break; case 8: CPR2F(3, 8, 0) break; case 12: CPR2F(3, 12, 0) break; default: CPR2F(3, 16, 0) break; }
+        if (al && C1 == 1 && C0 == 10) CPR2F(3, 12, 10, 1) else if (al && C1 == 1 && C0 == 16) CPR2F(3, 16, 16, 1) else if (al && C1 == 1 && C0 == 8) CPR2F(3, 8, 8, 1)
+        else switch (CP) { case 4: CPR2F(3, 4, 0, 0) break; case 8: CPR2F(3, 8, 0, 0) break; case 12: CPR2F(3, 12, 0, 0) break; default: CPR2F(3, 16, 0, 0) break; }
     } else {
-        switch (CP) { case 4: CPR2F(5, 4, 0) break; case 8: CPR2F(5, 8, 0) break; case 12: CPR2F(5, 12, 0) break; default: CPR2F(5, 16, 0) break; }
+        switch (CP) { case 4: CPR2F(5, 4, 0, 0) break; case 8: CPR2F(5, 8, 0, 0) break; case 12: CPR2F(5, 12, 0, 0) break; default: CPR2F(5, 16, 0, 0) break; }
     }
     return check_launch();
 }
@@ -449,7 +472,7 @@ extern "C" int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float 
     p.H = H1; p.W = W1; p.C1 = 1; p.C0 = C0; p.train = train;
     if (train) { p.part = (float*)workspace((size_t)N * (nF + C0) * sizeof(float), 4); if (!p.part) return T4K_ENOMEM; }
     const bool ex = (C0 == CM) && aligned16(convO);
-    #define CPR2B(CM_, EX_) { static bool attr = false; if (!attr && smem > 48 * 1024) { cudaFuncSetAttribute(k_cpr2_bwd<CM_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+    #define CPR2B(CM_, EX_) { static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_cpr2_bwd<CM_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cudaFuncSetAttribute(k_cpr2_bwd<CM_, EX_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); attr = true; } \
                               k_cpr2_bwd<CM_, EX_><<<N, threads, smem, STRM(s)>>>(p); }
     if (CM == 10) { if (ex) CPR2B(10, true) else CPR2B(10, false) } else { if (ex) CPR2B(16, true) else CPR2B(16, false) }
     int rc = check_launch(); if (rc || !train) return rc;

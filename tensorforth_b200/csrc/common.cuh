@@ -18,6 +18,10 @@ int  check_launch();                          // cudaGetLastError() → rc, ++g_
 void *workspace(size_t bytes, int slot);      // library-owned per-device scratch (grown on demand)
 float *reduce_slot(cudaStream_t st);          // 4 KiB partials + counter, ring of slots, zeroed counter
 
+struct GemmDeferred { const float *part; int splits; };   // gemm_simt(..., defer): caller-side split-K finish
+int gemm_simt(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
+              int M, int N, int K, int C, int batch, int64_t sA, int64_t sB, int64_t sO, cudaStream_t st, GemmDeferred *defer = nullptr);
+
 static inline cudaStream_t STRM(t4k_stream_t s) { return (cudaStream_t)s; }
 
 // persistent-ish grid for HBM streaming kernels: enough CTAs to cover n items at `per_thread`

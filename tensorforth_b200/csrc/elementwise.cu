@@ -3,6 +3,7 @@
 //   k_bias / k_activate (src/nn/nmath.cu:27-70) and k_sgd / k_adam / k_adamw (src/nn/nmath.cu:419-472).
 // Roofline: all HBM-bound; algorithmic bytes per element are listed in DESIGN.md §kernels.
 #include "common.cuh"
+#include "act.cuh"
 
 namespace t4k {
 
@@ -163,19 +164,6 @@ __global__ void __launch_bounds__(T4K_THREADS) k_bias(const float *__restrict__ 
         Y[k] += __ldg(B + (k % E0));
 }
 
-// ------------------------------------------------------------------ activations (+ saved derivative / mask)
-#define SELU_L  1.0507
-#define SELU_LA 1.7581
-template<int L> __device__ __forceinline__ void act(float i, float alpha, float &o, float &f) {
-    if (L == T4K_L_RELU)         { if (i > 0.0f) { f = 1.0f; o = i; } else { f = 0.0f; o = 0.0f; } }
-    else if (L == T4K_L_TANH)    { o = tanhf(i); f = 1.0f - o * o; }
-    else if (L == T4K_L_SIGMOID) { o = 1.0f / (1.0f + expf(-i)); f = o * (1.0f - o); }
-    else if (L == T4K_L_SELU)    { if (i > 0.0f) { f = (float)SELU_L; o = i; }                // sic: no lambda on x (nmath.cu:56-58)
-                                   else { f = (float)(SELU_LA * (double)__expf(i)); o = (float)((double)f - SELU_LA); } }
-    else if (L == T4K_L_LEAKYRL) { if (i > 0.0f) { f = 1.0f; o = i; } else { f = alpha; o = alpha * i; } }
-    else if (L == T4K_L_ELU)     { if (i > 0.0f) { f = 1.0f; o = i; } else { f = alpha * __expf(i); o = f - alpha; } }
-    else /* DROPOUT */           { if (f > alpha) { f = 1.0f; o = i; } else { f = 0.0f; o = 0.0f; } }  // f holds U(0,1] on entry
-}
 template<int L, bool VEC>
 __global__ void __launch_bounds__(T4K_THREADS) k_activate(const float *I, float *O, float *F, float alpha, int64_t n) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

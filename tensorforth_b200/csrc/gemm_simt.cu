@@ -128,8 +128,10 @@ __global__ void __launch_bounds__(T4K_THREADS) k_splitk_fin(GemmP p, int batch) 
     }
 }
 
+// defer != nullptr: the caller runs its own split-K finish (fused epilogue): on return defer->part / defer->splits describe
+// the partials [splits][M*N] (C == 1, batch == 1); splits == 1 means O already holds alpha*A@B + beta*O.
 int gemm_simt(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
-              int M, int N, int K, int C, int batch, int64_t sA, int64_t sB, int64_t sO, cudaStream_t st) {
+              int M, int N, int K, int C, int batch, int64_t sA, int64_t sB, int64_t sO, cudaStream_t st, GemmDeferred *defer) {
     GemmP p{A, B, O, alpha, beta, M, N, K, C, sA, sB, sO, 1, K, nullptr};
     const int gx = (N + SBN - 1) / SBN, gy = (M + SBM - 1) / SBM;
     const int64_t ctas = (int64_t)gx * gy * C * batch;
@@ -160,6 +162,7 @@ int gemm_simt(const float *A, const float *B, float *O, float alpha, float beta,
     if (tA) { if (tB) k_gemm_simt<true, true ><<<g, 256, 0, st>>>(p); else k_gemm_simt<true, false><<<g, 256, 0, st>>>(p); }
     else    { if (tB) k_gemm_simt<false, true><<<g, 256, 0, st>>>(p); else k_gemm_simt<false, false><<<g, 256, 0, st>>>(p); }
     int rc = check_launch();
+    if (defer) { defer->part = p.splits > 1 ? p.part : O; defer->splits = p.splits; return rc; }
     if (rc || p.splits == 1) return rc;
     const int64_t total = (int64_t)M * N * C * batch;
     k_splitk_fin<<<stream_grid(total), T4K_THREADS, 0, st>>>(p, batch);

@@ -255,8 +255,6 @@ __global__ void __launch_bounds__(320, 1) k_gemm_tc(TcP p) {
     }
 }
 
-int gemm_simt(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
-              int M, int N, int K, int C, int batch, int64_t sA, int64_t sB, int64_t sO, cudaStream_t st);
 __global__ void k_splitk_fin_tc(const float *part, float *O, float alpha, float beta, int64_t MN, int splits);
 
 __global__ void __launch_bounds__(T4K_THREADS) k_splitk_fin_tc(const float *__restrict__ part, float *O,

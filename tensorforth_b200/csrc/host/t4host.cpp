@@ -275,7 +275,8 @@ Model &Model::forward(Tensor &input) {
         if (!i0) n0 = input;
     }
     for (size_t i = i0; i + 1 < _layers.size(); ) {
-        const int adv = _ffused(i);                        // conv → maxpool(2) → relu (→ flatten) in one launch
+        int adv = _ffused(i);                              // conv → maxpool(2) → relu (→ flatten) in one launch
+        if (!adv) adv = _ffused_linear(i);                 // linear → activation | linear → softmax
         if (adv) { i += adv; continue; }
         _fstep(*_layers[i], *_layers[i + 1]); i++;
     }
@@ -295,6 +296,47 @@ int Model::_ffused(size_t i, const DU *src) {
     if (rc == T4K_ENOSUP) return 0;
     KCHK(rc);
     return fl ? 4 : 3;
+}
+// linear → activation: bias + activation (+ mask) ride in the GEMM's split-K finish; linear → softmax (small head): one launch.
+// Same layer tensors as _flinear + _factivate / _fsoftmax (forward.cu:158-243).
+static bool mask_act(t4_layer fn) { return fn == T4K_L_RELU || fn == T4K_L_TANH || fn == T4K_L_SELU || fn == T4K_L_LEAKYRL || fn == T4K_L_ELU; }
+int Model::_ffused_linear(size_t i) {
+    const size_t n = _layers.size();
+    if (!fuse || i + 2 >= n) return 0;
+    Tensor &in = *_layers[i], &lo = *_layers[i + 1], &ao = *_layers[i + 2];
+    if (in.grad_fn != T4K_L_LINEAR) return 0;
+    const int N = (int)lo.N(), E0 = (int)lo.HWC(), E1 = (int)in.HWC();
+    const t4_layer fn = lo.grad_fn;
+    int rc;
+    if (fn == T4K_L_SOFTMAX) rc = t4k_mlp_head_fwd(in.data, in.grad[0]->data, in.grad[1]->data, lo.data, ao.data, N, E0, E1, ST);
+    else if (mask_act(fn) || fn == T4K_L_SIGMOID)
+        rc = t4k_linear_act_fwd(fn, in.data, in.grad[0]->data, in.grad[1]->data, lo.data, ao.data, lo.grad[4]->data, lo.xparm, N, E0, E1, ST);
+    else return 0;
+    if (rc == T4K_ENOSUP) return 0;
+    KCHK(rc);
+    return 2;
+}
+// tail of a classifier, backward: [linear →] activation → small linear → softmax with target y.  One launch does
+// _bprep (p - y), the softmax pass-through, the small linear's dB/dW/dX, the activation backward and the dB of the
+// linear in front (backprop.cu:76-140,194-263).  Returns the index of the next layer to process (-1: none left) or -2: not fused.
+int Model::_bfused_head(Tensor &tgt, bool *skip_db) {
+    const int n = (int)_layers.size();
+    *skip_db = false;
+    if (!fuse || n < 4) return -2;
+    Tensor &P = *_layers[n - 1], &yl = *_layers[n - 2], &x2 = *_layers[n - 3];
+    if (yl.grad_fn != T4K_L_SOFTMAX || x2.grad_fn != T4K_L_LINEAR) return -2;
+    const int N = (int)P.N(), E0 = (int)P.HWC(), E1 = (int)x2.HWC();
+    if (E0 > 32 || E1 > 128) return -2;
+    Tensor *act = (n >= 5 && (mask_act(_layers[n - 4]->grad_fn) || _layers[n - 4]->grad_fn == T4K_L_DROPOUT)) ? _layers[n - 4] : nullptr;
+    const int prev = act ? n - 5 : n - 4;
+    Tensor *lin1 = (prev >= 0 && _layers[prev]->grad_fn == T4K_L_LINEAR && train) ? _layers[prev] : nullptr;
+    int rc = t4k_mlp_head_bwd(P.data, tgt.data, yl.data, x2.data, act ? act->grad[4]->data : nullptr, act ? act->data : nullptr,
+                              x2.grad[0]->data, x2.grad[2]->data, x2.grad[3]->data, lin1 ? lin1->grad[3]->data : nullptr,
+                              N, E0, E1, train, ST);
+    if (rc == T4K_ENOSUP) return -2;
+    KCHK(rc);
+    *skip_db = lin1 != nullptr;
+    return prev;
 }
 int Model::_bfused(int i) {                                // i = index of the block's LAST layer (relu or flatten); returns layers consumed
     if (!fuse) return 0;
@@ -369,12 +411,19 @@ Model &Model::backprop() {
     return *this;
 }
 Model &Model::backprop(Tensor &tgt) {
-    if (_bprep(tgt)) return *this;
-    for (int i = (int)_layers.size() - 2, j = 0; i >= 0; j++) {
+    int i = (int)_layers.size() - 2, j = 0;
+    bool skip_db = false;
+    Tensor &out = (*this)[-1];
+    const int nxt = (out.numel == tgt.numel) ? _bfused_head(tgt, &skip_db) : -2;    // -2: head not fused
+    if (nxt == -2) { if (_bprep(tgt)) return *this; }
+    else { i = nxt; j = 1; }
+    for (; i >= 0; j++) {
         const t4_layer fn = _layers[i]->grad_fn;
         const int adv = (j > 0 && (fn == T4K_L_FLATTEN || fn == T4K_L_RELU)) ? _bfused(i) : 0;
         if (adv) { i -= adv; continue; }
-        _bstep(*_layers[i], *_layers[i + 1], j == 0); i--;
+        if (skip_db && fn == T4K_L_LINEAR) { _blinear(*_layers[i], *_layers[i + 1], true); skip_db = false; }
+        else _bstep(*_layers[i], *_layers[i + 1], j == 0);
+        i--;
     }
     return *this;
 }
@@ -416,11 +465,11 @@ int Model::_bconv(Tensor &in, Tensor &out) {                              // bac
     in = dx;                                                               // x = dX (overwrite)
     return 0;
 }
-int Model::_blinear(Tensor &in, Tensor &out) {                            // backprop.cu:194-254
+int Model::_blinear(Tensor &in, Tensor &out, bool skip_db) {              // backprop.cu:194-254
     Tensor &w = *in.grad[0], &dw = *in.grad[2], &db = *in.grad[3];
     // dX overwrites the layer input in place; dW needs X first → t4k_linear_bwd orders dW before dX,
     // and dX = dY@W does not read X, so in.data may be both X and dX.
-    KCHK(t4k_linear_bwd(in.data, w.data, out.data, in.data, dw.data, db.data, in.N(), (int)out.HWC(), (int)in.HWC(), train, ST));
+    KCHK(t4k_linear_bwd_ex(in.data, w.data, out.data, in.data, dw.data, db.data, in.N(), (int)out.HWC(), (int)in.HWC(), train, skip_db, ST));
     return 0;
 }
 int Model::_bactivate(Tensor &in, Tensor &out) { KCHK(t4k_activate_bwd(out.data, in.grad[4]->data, in.data, in.numel, ST)); return 0; } // backprop.cu:257-263

@@ -177,6 +177,8 @@ private:
     void _iup(Tensor &in, U16 f, DU m);
     void _fstep(Tensor &in, Tensor &out);
     int  _ffused(size_t i, const DU *src = nullptr);
+    int  _ffused_linear(size_t i);
+    int  _bfused_head(Tensor &tgt, bool *skip_db);
     int  _bfused(int i);
     int  _fconv(Tensor &in, Tensor &out);
     int  _flinear(Tensor &in, Tensor &out);
@@ -189,7 +191,7 @@ private:
     int  _bprep(Tensor &tgt);
     void _bstep(Tensor &in, Tensor &out, bool last_layer);
     int  _bconv(Tensor &in, Tensor &out);
-    int  _blinear(Tensor &in, Tensor &out);
+    int  _blinear(Tensor &in, Tensor &out, bool skip_db = false);
     int  _bactivate(Tensor &in, Tensor &out);
     int  _bpool(Tensor &in, Tensor &out, t4_layer fn);
     int  _bupsample(Tensor &in, Tensor &out, t4_layer fn);

@@ -1,24 +1,292 @@
-// nn.cu — linear layer forward/backward on top of the GEMM engines
+// nn.cu — linear layer forward/backward on top of the GEMM engines, with the layer-group fusions the launch-bound
+// MLP tails of the reference's examples need (examples/t4_40a.4th:12-13 "100 linear relu 10 linear softmax"):
 //   Model::_flinear (src/nn/forward.cu:158-198)  : Y = X @ W^T + B      (Tensor::linear tB=true, then k_bias)
+//   Model::_factivate (forward.cu:201-209)        : fused into the split-K finish of the GEMM (t4k_linear_act_fwd)
 //   Model::_blinear (src/nn/backprop.cu:194-254) : dB += ΣdY ; dW += dY^T @ X (beta=1) ; dX = dY @ W
-#include "common.cuh"
+//   head  forward  (t4k_mlp_head_fwd): small linear + bias + row softmax, one launch (forward.cu:158-198,231-243)
+//   head  backward (t4k_mlp_head_bwd): _bprep (p - y), softmax pass-through copy, small _blinear (dB, dW, dX),
+//                  the preceding _bactivate (dX * mask) and the dB of the linear before it, one launch
+//                  (backprop.cu:76-140,194-263)
+// Every layer tensor the per-layer path writes is still written with the same meaning.
+#include "act.cuh"
+
+namespace t4k {
+
+#define RCTRL 2048                       // control word offset inside a reduce_slot() block (runtime.cu)
+
+// ------------------------------------------------------------------ split-K finish + bias (+ activation)
+// part: [splits][MN] partial products (splits == 1: the finished product itself); Y = Σ part + bias; A,F = act(Y)
+template<int L>
+__global__ void __launch_bounds__(T4K_THREADS) k_linear_fin(const float *__restrict__ part, int splits, int64_t MN, int E0,
+                                                            const float *__restrict__ bias, float *Y, float *A, float *F, float alpha, int vec) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    if (vec) {
+        for (int64_t q = tid; q < (MN >> 2); q += nth) {
+            float4 s = ldg4(part + 4 * q);
+            for (int k = 1; k < splits; k++) { const float4 t = ldg4(part + (int64_t)k * MN + 4 * q); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+            const float4 b = ldg4(bias + (int)((4 * q) % E0));
+            s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+            stg4(Y + 4 * q, s);
+            if (L != T4K_L_NONE) {
+                float4 o, f;
+                if (L == T4K_L_DROPOUT) f = *reinterpret_cast<const float4*>(F + 4 * q);
+                act<L>(s.x, alpha, o.x, f.x); act<L>(s.y, alpha, o.y, f.y); act<L>(s.z, alpha, o.z, f.z); act<L>(s.w, alpha, o.w, f.w);
+                stg4(A + 4 * q, o); stg4(F + 4 * q, f);
+            }
+        }
+    } else {
+        for (int64_t e = tid; e < MN; e += nth) {
+            float s = part[e];
+            for (int k = 1; k < splits; k++) s += part[(int64_t)k * MN + e];
+            s += __ldg(bias + (int)(e % E0));
+            Y[e] = s;
+            if (L != T4K_L_NONE) { float o, f = (L == T4K_L_DROPOUT) ? F[e] : 0.0f; act<L>(s, alpha, o, f); A[e] = o; F[e] = f; }
+        }
+    }
+}
+template<int L> static int launch_fin(const GemmDeferred &d, int64_t MN, int E0, const float *B, float *Y, float *A, float *F, float alpha, cudaStream_t st) {
+    const int vec = ((E0 & 3) == 0) && aligned16(d.part) && aligned16(B) && aligned16(Y) && (L == T4K_L_NONE || (aligned16(A) && aligned16(F)));
+    k_linear_fin<L><<<stream_grid(MN, vec ? 4 : 1), T4K_THREADS, 0, st>>>(d.part, d.splits, MN, E0, B, Y, A, F, alpha, vec);
+    return check_launch();
+}
+static int linear_act_fwd(int layer, const float *X, const float *W, const float *B, float *Y, float *A, float *F, float alpha,
+                          int N, int E0, int E1, cudaStream_t st) {
+    GemmDeferred d{nullptr, 1};
+    int rc = gemm_simt(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, 1, 1, 0, 0, 0, st, &d);
+    if (rc) return rc;
+    const int64_t MN = (int64_t)N * E0;
+    switch (layer) {
+    case T4K_L_NONE:    return launch_fin<T4K_L_NONE>(d, MN, E0, B, Y, A, F, alpha, st);
+    case T4K_L_RELU:    return launch_fin<T4K_L_RELU>(d, MN, E0, B, Y, A, F, alpha, st);
+    case T4K_L_TANH:    return launch_fin<T4K_L_TANH>(d, MN, E0, B, Y, A, F, alpha, st);
+    case T4K_L_SIGMOID: return launch_fin<T4K_L_SIGMOID>(d, MN, E0, B, Y, A, F, alpha, st);
+    case T4K_L_SELU:    return launch_fin<T4K_L_SELU>(d, MN, E0, B, Y, A, F, alpha, st);
+    case T4K_L_LEAKYRL: return launch_fin<T4K_L_LEAKYRL>(d, MN, E0, B, Y, A, F, alpha, st);
+    case T4K_L_ELU:     return launch_fin<T4K_L_ELU>(d, MN, E0, B, Y, A, F, alpha, st);
+    case T4K_L_DROPOUT: return launch_fin<T4K_L_DROPOUT>(d, MN, E0, B, Y, A, F, alpha, st);
+    default:            return T4K_EINVAL;
+    }
+}
+
+// ------------------------------------------------------------------ transposing warp reduction (see cnn_block.cu)
+__device__ __forceinline__ float warp_treduce32(float (&v)[32], int lane) {
+    #pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+        #pragma unroll
+        for (int i = 0; i < o; i++) {
+            const float send = up ? v[i] : v[i + o];
+            const float keep = up ? v[i + o] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
+
+// ------------------------------------------------------------------ head forward: Y = X @ W^T + B ; P = softmax(Y)
+// warp per row, W (E0 x E1, E0 <= 32) in shared memory; lane k ends up owning class k.
+#define HEAD_JMAX 8                      // E1 <= 32 * HEAD_JMAX
+__global__ void __launch_bounds__(T4K_THREADS) k_head_fwd(const float *__restrict__ X, const float *__restrict__ W, const float *__restrict__ B,
+                                                          float *Y, float *P, int N, int E0, int E1) {
+    extern __shared__ float sW[];                      // [E0][E1]
+    for (int t = threadIdx.x; t < E0 * E1; t += blockDim.x) sW[t] = __ldg(W + t);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < N; row += nw) {
+        float acc[32];
+        #pragma unroll
+        for (int k = 0; k < 32; k++) acc[k] = 0.0f;
+        const float *x = X + (int64_t)row * E1;
+        for (int e = lane; e < E1; e += 32) {
+            const float xv = x[e];
+            #pragma unroll
+            for (int k = 0; k < 32; k++) if (k < E0) acc[k] = fmaf(xv, sW[k * E1 + e], acc[k]);
+        }
+        float y = warp_treduce32(acc, lane);           // lane k: Σ_e x[e] W[k][e]
+        const bool on = lane < E0;
+        if (on) y += __ldg(B + lane);
+        const float mx = warp_max(on ? y : -FLT_MAX);  // k_softmax_small (nmath.cu:74-118): exp(x - max) / Σ
+        const float ex = on ? __expf(y - mx) : 0.0f;
+        const float sm = warp_sum(ex);
+        if (on) { Y[(int64_t)row * E0 + lane] = y; P[(int64_t)row * E0 + lane] = ex / sm; }
+    }
+}
+
+// ------------------------------------------------------------------ head backward
+// per row n:  d = P - T  → P (in place, Model::_bprep) and → Ylin (softmax backward: in = out)
+//             dX2[e] = Σ_k d[k] W[k][e]                → X2 row (the small linear's input tensor, in place)
+//             dY1[e] = dX2[e] * F1[e]                   → Y1 row (the activation's input tensor)      [if F1]
+//  per CTA:   dW[k][e] += Σ_n d[k] x2[e],  dB[k] += Σ_n d[k],  dB1[e] += Σ_n dY1[e]   (x2 = X2 before overwrite)
+//  partials per CTA → global; the last CTA to finish adds them in CTA order into dW / dB / dB1 (deterministic).
+struct HeadB {
+    float *P; const float *T; float *Ylin, *X2; const float *F1; float *Y1; const float *W;
+    float *dW, *dB, *dB1, *part, *slot;
+    int N, E0, E1, train;
+};
+template<int KM>                                       // KM = compile-time bound on E0 (8, 16 or 32); E1 <= 128
+__global__ void __launch_bounds__(T4K_THREADS) k_head_bwd(HeadB p) {
+    extern __shared__ float sm[];
+    __shared__ bool last;
+    const int E0 = p.E0, E1 = p.E1, nE = E0 * E1 + E0 + E1;
+    float *sW = sm;                                    // [E0][E1]
+    float *sAcc = sm + ((E0 * E1 + 3) & ~3);           // [nwarps][nE]
+    for (int t = threadIdx.x; t < E0 * E1; t += blockDim.x) sW[t] = __ldg(p.W + t);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nw = gridDim.x * nwarps;
+    float accW[KM][4], accB1[4], accB = 0.0f;
+    #pragma unroll
+    for (int k = 0; k < KM; k++) { accW[k][0] = accW[k][1] = accW[k][2] = accW[k][3] = 0.0f; }
+    accB1[0] = accB1[1] = accB1[2] = accB1[3] = 0.0f;
+    for (int row = blockIdx.x * nwarps + warp; row < p.N; row += nw) {
+        float d = 0.0f;
+        if (lane < E0) {
+            const int64_t o = (int64_t)row * E0 + lane;
+            d = __fsub_rn(p.P[o], p.T[o]);
+            p.P[o] = d; p.Ylin[o] = d;
+            accB += d;
+        }
+        float x[4], dx[4];
+        #pragma unroll
+        for (int j = 0; j < 4; j++) { const int e = lane + 32 * j; x[j] = (e < E1) ? p.X2[(int64_t)row * E1 + e] : 0.0f; dx[j] = 0.0f; }
+        #pragma unroll
+        for (int k = 0; k < KM; k++) {
+            if (k < E0) {
+                const float dk = __shfl_sync(0xffffffffu, d, k);
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int e = lane + 32 * j;
+                    if (e < E1) dx[j] = fmaf(dk, sW[k * E1 + e], dx[j]);
+                    accW[k][j] = fmaf(dk, x[j], accW[k][j]);
+                }
+            }
+        }
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int e = lane + 32 * j;
+            if (e < E1) {
+                const int64_t o = (int64_t)row * E1 + e;
+                p.X2[o] = dx[j];
+                float g = dx[j];
+                if (p.F1) { g = __fmul_rn(dx[j], p.F1[o]); p.Y1[o] = g; }
+                accB1[j] += g;
+            }
+        }
+    }
+    if (!p.train) return;
+    // CTA reduction over warps (fixed order), then one partial per CTA
+    float *mine = sAcc + (size_t)warp * nE;
+    #pragma unroll
+    for (int k = 0; k < KM; k++) if (k < E0) {
+        #pragma unroll
+        for (int j = 0; j < 4; j++) { const int e = lane + 32 * j; if (e < E1) mine[k * E1 + e] = accW[k][j]; }
+    }
+    if (lane < E0) mine[E0 * E1 + lane] = accB;
+    #pragma unroll
+    for (int j = 0; j < 4; j++) { const int e = lane + 32 * j; if (e < E1) mine[E0 * E1 + E0 + e] = accB1[j]; }
+    __syncthreads();
+    float *gp = p.part + (size_t)blockIdx.x * nE;
+    for (int t = threadIdx.x; t < nE; t += blockDim.x) {
+        float s = 0.0f;
+        for (int w = 0; w < nwarps; w++) s += sAcc[(size_t)w * nE + t];
+        gp[t] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(p.slot + RCTRL), 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int t = threadIdx.x; t < nE; t += blockDim.x) {
+        float s = 0.0f;
+        for (int c = 0; c < (int)gridDim.x; c++) s += __ldcg(p.part + (size_t)c * nE + t);
+        if (t < E0 * E1) p.dW[t] += s;
+        else if (t < E0 * E1 + E0) p.dB[t - E0 * E1] += s;
+        else if (p.dB1) p.dB1[t - E0 * E1 - E0] += s;
+    }
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(p.slot + RCTRL) = 0u;       // re-arm the slot
+}
+
+} // namespace t4k
 using namespace t4k;
 
 extern "C" int t4k_linear_fwd(const float *X, const float *W, const float *B, float *Y, int N, int E0, int E1, t4k_stream_t s) {
     if (!X || !W || !B || !Y || N < 1 || E0 < 1 || E1 < 1) return T4K_EINVAL;
-    int rc = t4k_gemm(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, 1, 1, 0, 0, 0, s);
-    if (rc) return rc;
-    return t4k_bias(B, Y, N, E0, s);
+    if ((double)N * E0 * E1 >= 2.0e8 && N >= 64 && E0 >= 32 && E1 >= 64) {         // tensor-core sized: GEMM engine + bias pass
+        int rc = t4k_gemm(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, 1, 1, 0, 0, 0, s);
+        if (rc) return rc;
+        return t4k_bias(B, Y, N, E0, s);
+    }
+    return linear_act_fwd(T4K_L_NONE, X, W, B, Y, nullptr, nullptr, 0.0f, N, E0, E1, STRM(s));
 }
-extern "C" int t4k_linear_bwd(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
-                              int N, int E0, int E1, int train, t4k_stream_t s) {
+extern "C" int t4k_linear_act_fwd(int layer, const float *X, const float *W, const float *B, float *Y, float *A, float *F, float alpha,
+                                  int N, int E0, int E1, t4k_stream_t s) {
+    if (!X || !W || !B || !Y || !A || !F || N < 1 || E0 < 1 || E1 < 1) return T4K_EINVAL;
+    if (layer < T4K_L_RELU || layer > T4K_L_DROPOUT) return T4K_EINVAL;
+    if ((double)N * E0 * E1 >= 2.0e8 && N >= 64 && E0 >= 32 && E1 >= 64) {
+        int rc = t4k_gemm(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, 1, 1, 0, 0, 0, s);
+        if (rc) return rc;
+        GemmDeferred d{Y, 1};                                                       // bias + activation in one pass over Y
+        const int64_t MN = (int64_t)N * E0;
+        switch (layer) {
+        case T4K_L_RELU:    return launch_fin<T4K_L_RELU>(d, MN, E0, B, Y, A, F, alpha, STRM(s));
+        case T4K_L_TANH:    return launch_fin<T4K_L_TANH>(d, MN, E0, B, Y, A, F, alpha, STRM(s));
+        case T4K_L_SIGMOID: return launch_fin<T4K_L_SIGMOID>(d, MN, E0, B, Y, A, F, alpha, STRM(s));
+        case T4K_L_SELU:    return launch_fin<T4K_L_SELU>(d, MN, E0, B, Y, A, F, alpha, STRM(s));
+        case T4K_L_LEAKYRL: return launch_fin<T4K_L_LEAKYRL>(d, MN, E0, B, Y, A, F, alpha, STRM(s));
+        case T4K_L_ELU:     return launch_fin<T4K_L_ELU>(d, MN, E0, B, Y, A, F, alpha, STRM(s));
+        default:            return launch_fin<T4K_L_DROPOUT>(d, MN, E0, B, Y, A, F, alpha, STRM(s));
+        }
+    }
+    return linear_act_fwd(layer, X, W, B, Y, A, F, alpha, N, E0, E1, STRM(s));
+}
+extern "C" int t4k_linear_bwd_ex(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
+                                 int N, int E0, int E1, int train, int skip_db, t4k_stream_t s) {
     if (!X || !W || !dY || !dX || N < 1 || E0 < 1 || E1 < 1) return T4K_EINVAL;
     if (train) {
-        if (!dW || !dB) return T4K_EINVAL;
-        int rc = t4k_dbias(dY, dB, N, E0, s);                                        // dB[E0] += Σ_n dY
-        if (rc) return rc;
+        if (!dW || (!dB && !skip_db)) return T4K_EINVAL;
+        int rc = 0;
+        if (!skip_db) { rc = t4k_dbias(dY, dB, N, E0, s); if (rc) return rc; }       // dB[E0] += Σ_n dY
         rc = t4k_gemm(dY, X, dW, 1.0f, 1.0f, 1, 0, E0, E1, N, 1, 1, 0, 0, 0, s);      // dW[E0,E1] += dY^T[E0,N] @ X[N,E1]
         if (rc) return rc;
     }
     return t4k_gemm(dY, W, dX, 1.0f, 0.0f, 0, 0, N, E1, E0, 1, 1, 0, 0, 0, s);       // dX[N,E1] = dY[N,E0] @ W[E0,E1]
+}
+extern "C" int t4k_linear_bwd(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
+                              int N, int E0, int E1, int train, t4k_stream_t s) {
+    return t4k_linear_bwd_ex(X, W, dY, dX, dW, dB, N, E0, E1, train, 0, s);
+}
+
+extern "C" int t4k_mlp_head_fwd(const float *X, const float *W, const float *B, float *Y, float *P, int N, int E0, int E1, t4k_stream_t s) {
+    if (!X || !W || !B || !Y || !P || N < 1 || E0 < 1 || E1 < 1) return T4K_EINVAL;
+    if (E0 > 32 || (size_t)E0 * E1 * sizeof(float) > 40 * 1024) return T4K_ENOSUP;
+    const int rows_per_cta = T4K_THREADS / 32;
+    int g = (N + rows_per_cta - 1) / rows_per_cta;
+    if (g > 2 * sm_count()) g = 2 * sm_count();
+    k_head_fwd<<<g, T4K_THREADS, (size_t)E0 * E1 * sizeof(float), STRM(s)>>>(X, W, B, Y, P, N, E0, E1);
+    return check_launch();
+}
+extern "C" int t4k_mlp_head_bwd(float *P, const float *T, float *Ylin, float *X2, const float *F1, float *Y1, const float *W,
+                                float *dW, float *dB, float *dB1, int N, int E0, int E1, int train, t4k_stream_t s) {
+    if (!P || !T || !Ylin || !X2 || !W || N < 1 || E0 < 1 || E1 < 1 || (F1 && !Y1) || (train && (!dW || !dB))) return T4K_EINVAL;
+    if (E0 > 32 || E1 > 128) return T4K_ENOSUP;
+    const int nwarps = T4K_THREADS / 32, nE = E0 * E1 + E0 + E1;
+    int g = (N + 4 * nwarps - 1) / (4 * nwarps);                                    // ~4 rows per warp
+    if (g > sm_count()) g = sm_count();
+    if (g < 1) g = 1;
+    const size_t smem = ((size_t)((E0 * E1 + 3) & ~3) + (size_t)nwarps * nE) * sizeof(float);
+    if (smem > 96 * 1024) return T4K_ENOSUP;
+    HeadB p{P, T, Ylin, X2, F1, Y1, W, dW, dB, dB1, nullptr, nullptr, N, E0, E1, train};
+    if (train) {
+        p.part = (float*)workspace((size_t)g * nE * sizeof(float), 6);
+        p.slot = reduce_slot(STRM(s));
+        if (!p.part || !p.slot) return T4K_ENOMEM;
+    }
+    #define HEADB(KM_) { static bool attr = false; if (!attr && smem > 48 * 1024) { cudaFuncSetAttribute(k_head_bwd<KM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; } \
+                         k_head_bwd<KM_><<<g, T4K_THREADS, smem, STRM(s)>>>(p); }
+    if (E0 <= 8) HEADB(8) else if (E0 <= 16) HEADB(16) else HEADB(32)
+    return check_launch();
 }

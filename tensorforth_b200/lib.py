@@ -17,6 +17,7 @@ SO_PATH = os.path.join(_HERE, "libt4k.so")
 LOSS_MSE, LOSS_BCE, LOSS_CE, LOSS_NLL = range(4)
 UNIFORM, NORMAL = 0, 1
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = 0, 1, 2
+EINVAL, ENOSUP, ENOMEM = -1, -2, -3
 
 _p, _i, _f, _l, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
 
@@ -54,6 +55,10 @@ PROTOTYPES = {
     "t4k_batchnorm_fwd": (_i, [_p] * 6 + [_i] * 3 + [_p]),
     "t4k_dbias": (_i, [_p, _p, _i, _i, _p]),
     "t4k_linear_bwd": (_i, [_p] * 6 + [_i] * 4 + [_p]),
+    "t4k_linear_bwd_ex": (_i, [_p] * 6 + [_i] * 5 + [_p]),
+    "t4k_linear_act_fwd": (_i, [_i] + [_p] * 6 + [_f] + [_i] * 3 + [_p]),
+    "t4k_mlp_head_fwd": (_i, [_p] * 5 + [_i] * 3 + [_p]),
+    "t4k_mlp_head_bwd": (_i, [_p] * 10 + [_i] * 4 + [_p]),
     "t4k_activate_bwd": (_i, [_p, _p, _p, _l, _p]),
     "t4k_conv2d_bwd": (_i, [_p] * 6 + [_i] * 11 + [_p]),
     "t4k_pool_bwd": (_i, [_i, _p, _p] + [_i] * 7 + [_p]),

@@ -229,6 +229,61 @@ def test_gemm_4096_property():
     assert_close(o1[idx].cpu().numpy(), ref_rows, rtol=1e-5, what="4096 rows")
 
 
+# ------------------------------------------------------------------ fused linear epilogues / classifier head
+@pytest.mark.parametrize("layer,alpha", [(t4.L_RELU, 0.0), (t4.L_LEAKYRL, 0.2), (t4.L_TANH, 0.0), (t4.L_SIGMOID, 0.0), (t4.L_ELU, 1.0), (t4.L_SELU, 0.0)])
+@pytest.mark.parametrize("N,E0,E1", [(512, 100, 1960), (3, 5, 7), (1024, 512, 784)])
+def test_linear_act_fwd(layer, alpha, N, E0, E1):
+    X, W, Bv = rnd(N, E1), rnd(E0, E1) * 0.1, rnd(E0)
+    y, a, f = zeros(N, E0), zeros(N, E0), zeros(N, E0)
+    ok(lib().t4k_linear_act_fwd(layer, ptr(dev(X)), ptr(dev(W)), ptr(dev(Bv)), ptr(y), ptr(a), ptr(f), alpha, N, E0, E1, None))
+    ref = orc.gemm(X, W, tB=True); orc.lib().orc_bias(orc._p(Bv), orc._p(ref), N, E0)
+    assert_close(host(y), ref, rtol=1e-4, what="linear out")
+    ra, rf = orc.activate(layer, host(y), alpha)            # activation of OUR pre-activation: isolates the epilogue
+    assert_close(host(a), ra, rtol=1e-5, what="act out"); assert_close(host(f), rf, rtol=1e-5, what="act mask")
+
+
+@pytest.mark.parametrize("N,E0,E1", [(512, 10, 100), (7, 3, 5), (64, 32, 128), (33, 1, 256)])
+def test_mlp_head_fwd(N, E0, E1):
+    X, W, Bv = rnd(N, E1), rnd(E0, E1), rnd(E0)
+    y, pr = zeros(N, E0), zeros(N, E0)
+    ok(lib().t4k_mlp_head_fwd(ptr(dev(X)), ptr(dev(W)), ptr(dev(Bv)), ptr(y), ptr(pr), N, E0, E1, None))
+    ref = orc.gemm(X, W, tB=True); orc.lib().orc_bias(orc._p(Bv), orc._p(ref), N, E0)
+    assert_close(host(y), ref, rtol=1e-4, what="head linear")
+    assert_close(host(pr), orc.softmax(ref, N), rtol=1e-4, what="head softmax")
+    assert lib().t4k_mlp_head_fwd(ptr(dev(X)), ptr(dev(W)), ptr(dev(Bv)), ptr(y), ptr(pr), N, 33, E1, None) == t4.ENOSUP
+
+
+@pytest.mark.parametrize("N,E0,E1,act,prev", [(512, 10, 100, True, True), (5, 3, 7, True, False), (64, 32, 64, False, True), (40, 16, 128, True, True), (9, 2, 33, False, False)])
+def test_mlp_head_bwd(N, E0, E1, act, prev):
+    P, T, X2, W = np.abs(rnd(N, E0)), orc.onehot(np.arange(N) % E0, E0), rnd(N, E1), rnd(E0, E1)
+    F1 = (rnd(N, E1) > 0).astype(np.float32)
+    dW0, dB0, dB10 = rnd(E0, E1), rnd(E0), rnd(E1)
+    p, yl, x2, y1 = dev(P), zeros(N, E0), dev(X2), zeros(N, E1)
+    dw, db, db1 = dev(dW0), dev(dB0), dev(dB10)
+    for rep in range(2):                                    # twice: the arrival counter must re-arm itself
+        p, x2, dw, db, db1 = dev(P), dev(X2), dev(dW0), dev(dB0), dev(dB10)
+        ok(lib().t4k_mlp_head_bwd(ptr(p), ptr(dev(T)), ptr(yl), ptr(x2), ptr(dev(F1)) if act else None, ptr(y1) if act else None, ptr(dev(W)),
+                                  ptr(dw), ptr(db), ptr(db1) if prev else None, N, E0, E1, 1, None))
+        d = orc.tt_op(orc.SUB, P, T)
+        assert_exact(host(p), d); assert_exact(host(yl), d)
+        dx = orc.gemm(d, W)
+        assert_close(host(x2), dx, rtol=1e-4, what="head dX")
+        rdb = dB0.copy(); orc.lib().orc_dlinear_db(orc._p(d), orc._p(rdb), N, E0)
+        assert_close(host(db), rdb, rtol=1e-4, what="head dB")
+        assert_close(host(dw), orc.gemm(d, X2, O=dW0, alpha=1.0, beta=1.0, tA=True), rtol=1e-4, what="head dW")
+        g = host(x2) * F1 if act else host(x2)
+        if act:
+            assert_exact(host(y1), g)
+        if prev:
+            rdb1 = dB10.copy(); orc.lib().orc_dlinear_db(orc._p(np.ascontiguousarray(g)), orc._p(rdb1), N, E1)
+            assert_close(host(db1), rdb1, rtol=1e-4, what="dB of the linear in front")
+    # train == 0: parameter gradients untouched
+    p, x2, dw, db = dev(P), dev(X2), dev(dW0), dev(dB0)
+    ok(lib().t4k_mlp_head_bwd(ptr(p), ptr(dev(T)), ptr(yl), ptr(x2), None, None, ptr(dev(W)), ptr(dw), ptr(db), None, N, E0, E1, 0, None))
+    assert_exact(host(dw), dW0); assert_exact(host(db), dB0)
+    assert lib().t4k_mlp_head_bwd(ptr(p), ptr(dev(T)), ptr(yl), ptr(x2), None, None, ptr(dev(W)), ptr(dw), ptr(db), None, N, E0, 129, 0, None) == t4.ENOSUP
+
+
 # ------------------------------------------------------------------ linear / activation / softmax
 @pytest.mark.parametrize("N,E0,E1", [(1, 3, 2), (3, 2, 2), (512, 100, 1960), (512, 10, 100), (1024, 512, 784)])
 def test_linear_fwd_bwd(N, E0, E1):

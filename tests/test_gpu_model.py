@@ -273,6 +273,14 @@ def test_fused_block_equals_per_layer(kind, N):
     gb.fuse(False)
     x = (rng.random(shape, dtype=np.float32) * 2 - 1).astype(np.float32); y = orc.onehot(rng.integers(0, E, N), E)
     X, Y = th.Tensor.from_numpy(x), th.Tensor.tensor(N, 1, E, 1, y)
+    ga.forward(X); gb.forward(X)
+    first_fc = min(i for i, t in enumerate(om.layers) if t.fn == orc.L_LINEAR)
+    for i in range(len(ga)):
+        a, b = ga.layer(i).numpy(), gb.layer(i).numpy()
+        if i > first_fc:
+            assert_close(a, b, rtol=1e-5, what="fwd layer %d" % i)          # FC tail: split-K / dot-product summation order differs
+        else:
+            assert np.array_equal(a, b), "fwd layer %d" % i                  # conv blocks: same FMA order, pool routing, relu: bit-equal
     n0 = t4.load().t4k_launch_count()
     ga.forward(X); ga.backprop(Y)
     n1 = t4.load().t4k_launch_count()
@@ -280,10 +288,10 @@ def test_fused_block_equals_per_layer(kind, N):
     n2 = t4.load().t4k_launch_count()
     assert n1 - n0 < n2 - n1                                   # fewer launches
     for i in range(len(ga)):
-        if i == 0:      # layer 0 holds dX after backprop: FP sums, the fused kernel gathers channel-outer (order differs)
-            assert_close(ga.layer(i).numpy(), gb.layer(i).numpy(), rtol=1e-5, what="dX")
-        else:           # activations, relu masks, arg-max routed gradients: bit-equal
-            assert np.array_equal(ga.layer(i).numpy(), gb.layer(i).numpy()), "layer %d" % i
+        a, b = ga.layer(i).numpy(), gb.layer(i).numpy()
+        assert_close(a, b, rtol=2e-5, what="bwd layer %d" % i)
+        if i == 1:
+            assert np.array_equal(a == 0, b == 0), "arg-max routing pattern of the conv output gradient"
     for i in range(len(ga) - 1):
         if ga.dw(i) is not None and ga.w(i) is not None and ga.db(i) is not None:
             assert_close(ga.dw(i).numpy(), gb.dw(i).numpy(), rtol=1e-5, what="dw%d" % i)
