@@ -12,7 +12,6 @@
 
 namespace t4k {
 
-#define RCTRL 2048                       // control word offset inside a reduce_slot() block (runtime.cu)
 
 // ------------------------------------------------------------------ split-K finish + bias (+ activation)
 // part: [splits][MN] partial products (splits == 1: the finished product itself); Y = Σ part + bias; A,F = act(Y)
@@ -116,21 +115,35 @@ __global__ void __launch_bounds__(T4K_THREADS) k_head_fwd(const float *__restric
 // per row n:  d = P - T  → P (in place, Model::_bprep) and → Ylin (softmax backward: in = out)
 //             dX2[e] = Σ_k d[k] W[k][e]                → X2 row (the small linear's input tensor, in place)
 //             dY1[e] = dX2[e] * F1[e]                   → Y1 row (the activation's input tensor)      [if F1]
-//  per CTA:   dW[k][e] += Σ_n d[k] x2[e],  dB[k] += Σ_n d[k],  dB1[e] += Σ_n dY1[e]   (x2 = X2 before overwrite)
-//  partials per CTA → global; the last CTA to finish adds them in CTA order into dW / dB / dB1 (deterministic).
+//  gradients: dW[k][e] += Σ_n d[k] x2[e],  dB[k] += Σ_n d[k],  dB1[e] += Σ_n dY1[e]   (x2 = X2 before overwrite)
+// ONE THREAD-BLOCK CLUSTER (HB_CTAS CTAs, a warp per group of rows): per-warp register partials → per-CTA shared-memory
+// partial → cluster barrier → CTA r adds slice r of the HB_CTAS partials through DISTRIBUTED SHARED MEMORY in CTA order
+// and applies it.  No global partials, no atomics, no second launch; deterministic.
+#define HB_CTAS 16                                     // non-portable cluster size (opt-in attribute), 16 x 8 warps
+#define HB_ROWS 4                                      // rows per warp per trip (all their loads in flight together)
 struct HeadB {
     float *P; const float *T; float *Ylin, *X2; const float *F1; float *Y1; const float *W;
-    float *dW, *dB, *dB1, *part, *slot;
+    float *dW, *dB, *dB1;
     int N, E0, E1, train;
 };
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(const float *local, uint32_t rank) {       // the same smem offset in CTA `rank` of the cluster
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(local), r; float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(r) : "memory");
+    return v;
+}
 template<int KM>                                       // KM = compile-time bound on E0 (8, 16 or 32); E1 <= 128
-__global__ void __launch_bounds__(T4K_THREADS) k_head_bwd(HeadB p) {
+__global__ void __cluster_dims__(HB_CTAS, 1, 1) __launch_bounds__(T4K_THREADS) k_head_bwd(HeadB p) {
     extern __shared__ float sm[];
-    __shared__ bool last;
     const int E0 = p.E0, E1 = p.E1, nE = E0 * E1 + E0 + E1;
-    float *sW = sm;                                    // [E0][E1]
-    float *sAcc = sm + ((E0 * E1 + 3) & ~3);           // [nwarps][nE]
-    for (int t = threadIdx.x; t < E0 * E1; t += blockDim.x) sW[t] = __ldg(p.W + t);
+    float *sW = sm;                                    // [E0][128]       rows zero-padded: no column guards in the hot loop
+    float *sPart = sm + E0 * 128;                      // [nE]            this CTA's partial (read by the whole cluster)
+    float *sAcc = sPart + ((nE + 3) & ~3);             // [nwarps][nE]    per-warp partials
+    for (int t = threadIdx.x; t < E0 * 128; t += blockDim.x) { const int e = t & 127, k = t >> 7; sW[t] = (e < E1) ? __ldg(p.W + k * E1 + e) : 0.0f; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int nw = gridDim.x * nwarps;
@@ -138,43 +151,53 @@ __global__ void __launch_bounds__(T4K_THREADS) k_head_bwd(HeadB p) {
     #pragma unroll
     for (int k = 0; k < KM; k++) { accW[k][0] = accW[k][1] = accW[k][2] = accW[k][3] = 0.0f; }
     accB1[0] = accB1[1] = accB1[2] = accB1[3] = 0.0f;
-    for (int row = blockIdx.x * nwarps + warp; row < p.N; row += nw) {
-        float d = 0.0f;
-        if (lane < E0) {
-            const int64_t o = (int64_t)row * E0 + lane;
-            d = __fsub_rn(p.P[o], p.T[o]);
-            p.P[o] = d; p.Ylin[o] = d;
-            accB += d;
+    for (int row0 = (blockIdx.x * nwarps + warp) * HB_ROWS; row0 < p.N; row0 += nw * HB_ROWS) {
+        float d[HB_ROWS], x[HB_ROWS][4], f[HB_ROWS][4];
+        #pragma unroll
+        for (int r = 0; r < HB_ROWS; r++) {
+            const int row = row0 + r;
+            const bool rv = row < p.N;
+            d[r] = 0.0f;
+            if (rv && lane < E0) { const int64_t o = (int64_t)row * E0 + lane; d[r] = __fsub_rn(p.P[o], p.T[o]); }
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int e = lane + 32 * j;
+                const bool ev = rv && e < E1;
+                x[r][j] = ev ? p.X2[(int64_t)row * E1 + e] : 0.0f;
+                f[r][j] = (ev && p.F1) ? p.F1[(int64_t)row * E1 + e] : 1.0f;
+            }
         }
-        float x[4], dx[4];
         #pragma unroll
-        for (int j = 0; j < 4; j++) { const int e = lane + 32 * j; x[j] = (e < E1) ? p.X2[(int64_t)row * E1 + e] : 0.0f; dx[j] = 0.0f; }
-        #pragma unroll
-        for (int k = 0; k < KM; k++) {
-            if (k < E0) {
-                const float dk = __shfl_sync(0xffffffffu, d, k);
-                #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int e = lane + 32 * j;
-                    if (e < E1) dx[j] = fmaf(dk, sW[k * E1 + e], dx[j]);
-                    accW[k][j] = fmaf(dk, x[j], accW[k][j]);
+        for (int r = 0; r < HB_ROWS; r++) {
+            const int row = row0 + r;
+            if (row >= p.N) break;
+            if (lane < E0) { const int64_t o = (int64_t)row * E0 + lane; p.P[o] = d[r]; p.Ylin[o] = d[r]; accB += d[r]; }
+            float dx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            #pragma unroll
+            for (int k = 0; k < KM; k++) {
+                if (k < E0) {
+                    const float dk = __shfl_sync(0xffffffffu, d[r], k);
+                    #pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        dx[j] = fmaf(dk, sW[k * 128 + lane + 32 * j], dx[j]);
+                        accW[k][j] = fmaf(dk, x[r][j], accW[k][j]);
+                    }
+                }
+            }
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int e = lane + 32 * j;
+                if (e < E1) {
+                    const int64_t o = (int64_t)row * E1 + e;
+                    p.X2[o] = dx[j];
+                    float g = dx[j];
+                    if (p.F1) { g = __fmul_rn(dx[j], f[r][j]); p.Y1[o] = g; }
+                    accB1[j] += g;
                 }
             }
         }
-        #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int e = lane + 32 * j;
-            if (e < E1) {
-                const int64_t o = (int64_t)row * E1 + e;
-                p.X2[o] = dx[j];
-                float g = dx[j];
-                if (p.F1) { g = __fmul_rn(dx[j], p.F1[o]); p.Y1[o] = g; }
-                accB1[j] += g;
-            }
-        }
     }
-    if (!p.train) return;
-    // CTA reduction over warps (fixed order), then one partial per CTA
+    if (!p.train) return;                                                          // uniform over the cluster
     float *mine = sAcc + (size_t)warp * nE;
     #pragma unroll
     for (int k = 0; k < KM; k++) if (k < E0) {
@@ -185,29 +208,26 @@ __global__ void __launch_bounds__(T4K_THREADS) k_head_bwd(HeadB p) {
     #pragma unroll
     for (int j = 0; j < 4; j++) { const int e = lane + 32 * j; if (e < E1) mine[E0 * E1 + E0 + e] = accB1[j]; }
     __syncthreads();
-    float *gp = p.part + (size_t)blockIdx.x * nE;
     for (int t = threadIdx.x; t < nE; t += blockDim.x) {
         float s = 0.0f;
         for (int w = 0; w < nwarps; w++) s += sAcc[(size_t)w * nE + t];
-        gp[t] = s;
+        sPart[t] = s;
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(p.slot + RCTRL), 1u);
-        last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    for (int t = threadIdx.x; t < nE; t += blockDim.x) {
+    cluster_sync_all();                                                            // every CTA's sPart is complete and visible
+    const int rank = (int)cluster_rank();
+    const int chunk = (nE + HB_CTAS - 1) / HB_CTAS;
+    for (int t = rank * chunk + threadIdx.x; t < min(nE, (rank + 1) * chunk); t += blockDim.x) {
+        float v[HB_CTAS];
+        #pragma unroll
+        for (int c = 0; c < HB_CTAS; c++) v[c] = ld_dsmem(sPart + t, (uint32_t)c);
         float s = 0.0f;
-        for (int c = 0; c < (int)gridDim.x; c++) s += __ldcg(p.part + (size_t)c * nE + t);
+        #pragma unroll
+        for (int c = 0; c < HB_CTAS; c++) s += v[c];
         if (t < E0 * E1) p.dW[t] += s;
         else if (t < E0 * E1 + E0) p.dB[t - E0 * E1] += s;
         else if (p.dB1) p.dB1[t - E0 * E1 - E0] += s;
     }
-    if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(p.slot + RCTRL) = 0u;       // re-arm the slot
+    cluster_sync_all();                                                            // nobody leaves while its smem is still being read
 }
 
 } // namespace t4k
@@ -274,19 +294,12 @@ extern "C" int t4k_mlp_head_bwd(float *P, const float *T, float *Ylin, float *X2
     if (!P || !T || !Ylin || !X2 || !W || N < 1 || E0 < 1 || E1 < 1 || (F1 && !Y1) || (train && (!dW || !dB))) return T4K_EINVAL;
     if (E0 > 32 || E1 > 128) return T4K_ENOSUP;
     const int nwarps = T4K_THREADS / 32, nE = E0 * E1 + E0 + E1;
-    int g = (N + 4 * nwarps - 1) / (4 * nwarps);                                    // ~4 rows per warp
-    if (g > sm_count()) g = sm_count();
-    if (g < 1) g = 1;
-    const size_t smem = ((size_t)((E0 * E1 + 3) & ~3) + (size_t)nwarps * nE) * sizeof(float);
+    const size_t smem = ((size_t)E0 * 128 + ((nE + 3) & ~3) + (size_t)nwarps * nE) * sizeof(float);
     if (smem > 96 * 1024) return T4K_ENOSUP;
-    HeadB p{P, T, Ylin, X2, F1, Y1, W, dW, dB, dB1, nullptr, nullptr, N, E0, E1, train};
-    if (train) {
-        p.part = (float*)workspace((size_t)g * nE * sizeof(float), 6);
-        p.slot = reduce_slot(STRM(s));
-        if (!p.part || !p.slot) return T4K_ENOMEM;
-    }
-    #define HEADB(KM_) { static bool attr = false; if (!attr && smem > 48 * 1024) { cudaFuncSetAttribute(k_head_bwd<KM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; } \
-                         k_head_bwd<KM_><<<g, T4K_THREADS, smem, STRM(s)>>>(p); }
+    HeadB p{P, T, Ylin, X2, F1, Y1, W, dW, dB, dB1, N, E0, E1, train};
+    #define HEADB(KM_) { static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_head_bwd<KM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
+                                                                 cudaFuncSetAttribute(k_head_bwd<KM_>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); attr = true; } \
+                         k_head_bwd<KM_><<<HB_CTAS, T4K_THREADS, smem, STRM(s)>>>(p); }
     if (E0 <= 8) HEADB(8) else if (E0 <= 16) HEADB(16) else HEADB(32)
     return check_launch();
 }
