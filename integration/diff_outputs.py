@@ -1,0 +1,92 @@
+"""diff_outputs.py <ref dir> <new dir> [<ref2 dir>] — compare the text two tensorForth builds print for the same script.
+
+Token-wise: numeric tokens must agree within RTOL/ATOL (the printer is %+.4f, src/io/aio_tensor.cpp:141-163), every
+other token exactly.  Lines that carry memory statistics, pointers or the banner are skipped, and so are the
+elapsed-ms stamps of trace lines (`  0.00:  2> linear ...`): they differ between two runs of the SAME binary.
+<ref2 dir> holds a second run of the reference on the same scripts: where the reference disagrees with ITSELF
+(weights drawn by the wall-clock seeded rand, src/sys.cpp:77-95; float atomicAdd order feeding a chaotic
+trajectory) the token is held to 10x that spread instead of the fixed tolerance, and counted as `noisy`.
+Exit code 0 when every compared script matches."""
+import os
+import re
+import sys
+
+RTOL, ATOL = 1e-4, 2e-4
+NUM = re.compile(r'^[+-]?(\d+\.?\d*([eE][+-]?\d+)?|\.\d+|nan|inf)$')
+SKIP = re.compile(r'msec|mstat|obj#|0x[0-9a-f]{6,}|tensorForth|CUDA|GPU|\bms\b|\bsec\b|free|used|mmu|MMU|Mem|VM\[|dict|sizeof')
+STAMP = re.compile(r'^\d+\.\d+:$')
+
+
+def toks(line):
+    # numbers can be glued (" 0.05-0.21 0.07" in the trace dumps): split before a sign that follows a digit
+    line = re.sub(r'(?<=\d)(?=[+-]\d)', ' ', line)
+    return [t for t in re.findall(r'[^\s{}\[\](),=|]+|[{}\[\](),=|]', line) if not STAMP.match(t)]
+
+
+def lines(text):
+    return [l for l in text.splitlines() if l.strip() and not SKIP.search(l)]
+
+
+def compare(ref, new, ref2):
+    bad, nnum, noisy, worst = [], 0, 0, 0.0
+    lr, ln = lines(ref), lines(new)
+    l2 = lines(ref2) if ref2 is not None else None
+    if l2 is not None and len(l2) != len(lr):
+        l2 = None
+    if len(lr) != len(ln):
+        bad.append("line count %d vs %d" % (len(lr), len(ln)))
+    for i, (a, b) in enumerate(zip(lr, ln)):
+        ta, tb = toks(a), toks(b)
+        t2 = toks(l2[i]) if l2 is not None else None
+        if t2 is not None and len(t2) != len(ta):
+            t2 = None
+        if len(ta) != len(tb):
+            bad.append("line %d token count: %r | %r" % (i, a[:100], b[:100]))
+            continue
+        for k, (x, y) in enumerate(zip(ta, tb)):
+            if NUM.match(x) and NUM.match(y):
+                fx, fy = float(x), float(y)
+                nnum += 1
+                if fx != fx and fy != fy:
+                    continue
+                tol = ATOL + RTOL * abs(fx)
+                if t2 is not None and NUM.match(t2[k]) and float(t2[k]) != fx:
+                    spread = abs(float(t2[k]) - fx)
+                    noisy += 1
+                    tol = max(tol, 10 * spread)
+                    if spread > 0.05 * max(abs(fx), 1e-3):
+                        continue                      # the reference's own value is not reproducible (random draw)
+                d = abs(fx - fy)
+                if d <= tol:
+                    worst = max(worst, d / max(abs(fx), 1.0))
+                else:
+                    bad.append("line %d: %s vs %s  | %r" % (i, x, y, a[:100]))
+            elif x != y:
+                bad.append("line %d: %r vs %r | %r" % (i, x, y, a[:100]))
+    return bad, nnum, noisy, worst, len(lr)
+
+
+def main():
+    rd, nd = sys.argv[1], sys.argv[2]
+    r2 = sys.argv[3] if len(sys.argv) > 3 else None
+    fails = 0
+    for fn in sorted(os.listdir(rd)):
+        if not fn.endswith(".out"):
+            continue
+        name = fn[:-4]
+        p = os.path.join(nd, fn)
+        if not os.path.exists(p):
+            print("%-22s MISSING in %s" % (name, nd)); fails += 1; continue
+        rd_ = lambda q: open(q, errors="replace").read()
+        ref2 = rd_(os.path.join(r2, fn)) if r2 and os.path.exists(os.path.join(r2, fn)) else None
+        bad, nnum, noisy, worst, nl = compare(rd_(os.path.join(rd, fn)), rd_(p), ref2)
+        print("%-22s %s  lines=%d numbers=%d (reference-noisy %d) worst_rel_of_stable=%.2e" % (
+            name, "OK  " if not bad else "DIFF", nl, nnum, noisy, worst))
+        for b in bad[:12]:
+            print("      " + b)
+        fails += bool(bad)
+    return 1 if fails else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -28,5 +28,8 @@ for f in $R/io/aio*.cpp $R/vm/*.cpp $R/ld/*.cpp $R/nn/loss.cpp $R/nn/model.cpp $
 wait
 nvcc $ARCH -Xnvlink --suppress-stack-size-warning $(ls $O/*.o | grep -v refkern.o) -o $OUT/ten4
 nvcc $ARCH $O/refkern.o $O/t4math.o $O/nn_nmath.o -o $OUT/refkern
+# the reference's example scripts, staged beside the binaries for integration/run_side_by_side.sh
+# (oracle/_ref/ is git-ignored: they travel to the GPU box, they never enter this repository)
+mkdir -p $OUT/examples && cp $REF/examples/*.4th $OUT/examples/
 rm -rf $O
 ls -la $OUT
