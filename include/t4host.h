@@ -84,6 +84,9 @@ int   t4h_model_adamw(t4h_model m, float lr, float wd, float b1, float b2);
 int   t4h_model_arena(t4h_model m, float **G, float **DG, int64_t *total);
 /* capture forward+loss+backprop+optimizer into one CUDA graph and replay it (launch-bound regime);
  * optimizer: 0 sgd, 1 sgd+momentum, 2 adam, 3 adamw, -1 none (data parallel: all-reduce DG, then call the optimizer) */
+/* data parallel: attach a connected t4k_comm_t (include/t4k.h); from then on sgd/adam/adamw — also inside step_graph —
+ * sum the gradient arena over the ranks inside the optimizer kernel; scal[0..nscal) device floats ride along (summed) */
+int   t4h_model_dp_attach(t4h_model m, void *comm, float *scal, int nscal);
 int   t4h_model_step_graph(t4h_model m, t4h_tensor input, t4h_tensor tgt, int loss_op, float *loss_dev,
                            int optimizer, float lr, float b1, float b2, float wd);
 

@@ -206,6 +206,29 @@ typedef struct { int64_t off; int64_t len; int32_t Nw; int32_t pad; } t4k_seg_t;
 int t4k_optim_multi(int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
                     int64_t total, float lr, float b1, float b2, float wd, t4k_stream_t s);
 
+/* ---- data-parallel extras (SURVEY.md §8b "DP extras", §8e) --------------------------------
+ * The reference is single-GPU; Model::forward/backprop shard over the batch and the parameter gradients are batch
+ * sums (src/nn/backprop.cu:97-103), so a SUM all-reduce of the flat DG arena in front of the optimizer loop of
+ * Model::gradient (src/nn/gradient.cu:99-121) is the whole exchange.  One process per GPU; every rank creates a
+ * communicator (an exchange block in its own HBM, exported as a 64-byte cudaIpc handle), the host gathers the
+ * handles (torch.distributed / MPI / anything) and connects.  The exchange itself is one kernel per call over NVLink
+ * peer stores (tensorforth_b200/csrc/comm.cu), CUDA-graph capturable; sums are taken in rank order, so every rank
+ * holds bit-identical results.  Every rank must issue the same sequence of calls with the same lengths. */
+typedef struct t4k_comm *t4k_comm_t;
+#define T4K_COMM_HANDLE_BYTES 64
+int t4k_comm_create(int rank, int world, int64_t cap_floats, t4k_comm_t *out, void *handle64);
+int t4k_comm_connect(t4k_comm_t c, const void *handles /* world x T4K_COMM_HANDLE_BYTES, rank order */);
+int t4k_comm_connect_local(t4k_comm_t c, t4k_comm_t *all /* world communicators of THIS process, rank order */);
+int t4k_comm_destroy(t4k_comm_t c);
+int t4k_comm_status(t4k_comm_t c);      /* 0 healthy; k>0: a wait for rank k-1 timed out (~2 s without progress) */
+int64_t t4k_comm_capacity(t4k_comm_t c);
+/* buf[i] = sum over ranks of buf[i], in place, n <= capacity */
+int t4k_allreduce_sum(t4k_comm_t c, float *buf, int64_t n, t4k_stream_t s);
+/* t4k_optim_multi on the rank-summed gradient: DG is exchanged, summed and consumed (zeroed) by the same kernel;
+ * `scal[0..nscal)` (device, nscal <= 64: loss sums, hit counts) are sum-all-reduced in place in the same exchange */
+int t4k_optim_multi_dp(t4k_comm_t c, int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
+                       int64_t total, float lr, float b1, float b2, float wd, float *scal, int nscal, t4k_stream_t s);
+
 /* ---- RNG: src/util.cu:35-70 via System::rand (src/sys.cpp:77-95) ---------------------- */
 /* d[i] = scale * (bias + x), x ~ U(0,1] or N(0,1).  Counter-based Philox4x32-10 keyed by
  * (seed, element index): reproducible and independent of grid size / GPU count (the reference's

@@ -1,0 +1,286 @@
+// comm.cu — data-parallel exchange over NVLink / NVSwitch peer memory, fused with the optimizer step
+//
+// The reference is single-GPU.  Model::forward/backprop shard over the batch; parameter gradients are
+// batch SUMS (src/nn/backprop.cu:97-103, nmath.tcu:277,335), so one SUM all-reduce of the flat DG arena between backprop
+// and the optimizer (src/nn/gradient.cu:64-126) reproduces the single-GPU step.  That pair — a latency-bound 0.8 MB
+// all-reduce followed by a 2.8 us optimizer pass — is ONE kernel here:
+//
+//   push   every rank stores its chunk of DG into slot[parity][rank] of EVERY peer's exchange block (posted 128-bit
+//          stores over NVLink; no round trip), then one `fence.sys` per block + a store of the chunk's epoch flag to each peer
+//   wait   spin (acquire loads, local memory) until the chunk's flag from every rank has reached this epoch
+//   finish sum the `world` local slots in RANK ORDER (identical bits on every rank, so replicas never drift), run the
+//          optimizer step on G/M/V, write DG = 0
+//
+// Flags are per (rank, chunk): a chunk never waits for more than its own data, there is no grid-wide barrier, and the
+// chunk -> slot-range mapping depends only on the communicator's capacity, never on the call's length, so calls of any
+// length can be mixed.  Slot reuse is safe without a second barrier: parity p of a chunk is rewritten at that chunk's
+// epoch e+2; the writer has by then passed the chunk's wait at e+1, i.e. every peer had launched its e+1 kernel, which
+// stream order puts after the end of its epoch-e kernel (the reader of parity p).
+// Epoch counters live in device memory, so the kernel is CUDA-graph capturable (Model::step_graph captures the whole
+// data-parallel train step: forward + loss + backprop + exchange/optimizer, one graph launch per step).
+// One process per GPU: the exchange blocks are cudaMalloc'ed and exported with cudaIpc handles, which the host side
+// (tensorforth_b200/dp.py, torch.distributed) gathers.  A wait that sees no progress for ~2 s raises the communicator's
+// error word instead of hanging the GPU.
+#include "common.cuh"
+#include "optim.cuh"
+#include <cstring>
+#include <cstdlib>
+#include <new>
+
+#define COMM_MAXW   8            // ranks (one NVSwitch domain)
+#define COMM_MAXB   512          // chunks (= blocks) per call
+#define COMM_NSCAL  64           // extra scalars riding in the same exchange (loss sum, hit count …)
+#define COMM_FLAGB  (COMM_MAXW * COMM_MAXB * 4)
+#define COMM_SPIN_LIMIT (4000000000ll)       // clock64 ticks (~2 s)
+
+struct t4k_comm {
+    int rank, world, dev;
+    int64_t cap;                 // floats per slot (multiple of 4), scalar tail not included
+    int ch4;                     // float4s per chunk
+    char *base;                  // this rank's exchange block
+    char *peer[COMM_MAXW];       // every rank's block as mapped here (peer[rank] == base)
+    bool ipc[COMM_MAXW];
+    uint32_t *epoch;             // [COMM_MAXB] per-chunk epoch counters + [COMM_MAXB] error word (local)
+    size_t bytes;
+};
+
+namespace t4k {
+
+struct CommDev {
+    char *peer[COMM_MAXW];
+    uint32_t *epoch;
+    int64_t cap;
+    int rank, world, ch4;
+};
+struct DpOpt { float *G, *M, *V; const t4k_seg_t *seg; int nseg; bool mom; OptP p; };
+
+__device__ __forceinline__ float *slot_of(const CommDev &c, int where, int par, int r) {
+    return reinterpret_cast<float*>(c.peer[where] + COMM_FLAGB) + (int64_t)(par * c.world + r) * (c.cap + COMM_NSCAL);
+}
+__device__ __forceinline__ uint32_t *flag_of(const CommDev &c, int where, int r, int b) {
+    return reinterpret_cast<uint32_t*>(c.peer[where]) + r * COMM_MAXB + b;
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+// MODE 0: buf = Σ_r buf_r (in place).  MODE 1/2/3: sgd / adam / adamw on (G, Σ_r DG_r, M, V), DG = 0.
+template<int MODE, bool VEC>
+__global__ void __launch_bounds__(T4K_THREADS) k_dp_exchange(const __grid_constant__ CommDev c, float *buf, int64_t n, float *scal, int nscal, DpOpt o) {
+    __shared__ uint32_t s_ep;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) s_ep = c.epoch[b] + 1;
+    __syncthreads();
+    const uint32_t ep = s_ep;
+    const int par = (int)(ep & 1u);
+    const int64_t lo = (int64_t)b * c.ch4 * 4;
+    const int64_t hi = (lo + (int64_t)c.ch4 * 4 < n) ? lo + (int64_t)c.ch4 * 4 : n;
+    // ---- push this rank's chunk to every rank's slot[par][rank] (own slot last: it is the only local store)
+    if (VEC) {
+        for (int64_t i = lo + 4 * tid; i < hi; i += 4 * T4K_THREADS) {
+            const float4 v = *reinterpret_cast<const float4*>(buf + i);
+            #pragma unroll 1
+            for (int k = 1; k <= c.world; k++) {
+                const int p = (c.rank + k) % c.world;
+                *reinterpret_cast<float4*>(slot_of(c, p, par, c.rank) + i) = v;
+            }
+        }
+    } else {
+        for (int64_t i = lo + tid; i < hi; i += T4K_THREADS) {
+            const float v = buf[i];
+            for (int k = 1; k <= c.world; k++) slot_of(c, (c.rank + k) % c.world, par, c.rank)[i] = v;
+        }
+    }
+    if (b == 0 && tid < nscal) {
+        const float v = scal[tid];
+        for (int k = 1; k <= c.world; k++) slot_of(c, (c.rank + k) % c.world, par, c.rank)[c.cap + tid] = v;
+    }
+    __syncthreads();
+    // ---- signal every rank, then wait for every rank's signal for this chunk.  ONE fence.sys per block: the barrier orders the
+    // block's peer stores before thread 0's fence, and fences are cumulative, so the flag stores that follow publish all of
+    // them (measured on 2 B200s, 0.79 MB: a fence in every thread 17.7 us, this 9.9 us; NCCL 14.5 us).
+    if (tid == 0) {
+        __threadfence_system();
+        for (int k = 1; k <= c.world; k++) *reinterpret_cast<volatile uint32_t*>(flag_of(c, (c.rank + k) % c.world, c.rank, b)) = ep;
+    }
+    if (tid < c.world) {
+        const uint32_t *f = flag_of(c, c.rank, tid, b);
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(f) - ep) < 0)
+            if (clock64() - t0 > COMM_SPIN_LIMIT) { c.epoch[COMM_MAXB] = 1u + (uint32_t)tid; break; }
+    }
+    __syncthreads();
+    // ---- finish: rank-ordered sum of the local slots (+ optimizer)
+    const float *mine = slot_of(c, c.rank, par, 0);
+    const int64_t sstride = c.cap + COMM_NSCAL;
+    if (VEC) {
+        for (int64_t i = lo + 4 * tid; i < hi; i += 4 * T4K_THREADS) {
+            float4 s = __ldcg(reinterpret_cast<const float4*>(mine + i));
+            for (int r = 1; r < c.world; r++) {
+                const float4 t = __ldcg(reinterpret_cast<const float4*>(mine + r * sstride + i));
+                s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+            }
+            if (MODE == 0) { *reinterpret_cast<float4*>(buf + i) = s; }
+            else {
+                float4 g = *reinterpret_cast<const float4*>(o.G + i), m = make_float4(0, 0, 0, 0), v = m;
+                if (MODE == 1) {
+                    int l = 0, h = o.nseg - 1;                 // segment of element i (segments are 4-aligned: one lookup per float4)
+                    while (l < h) { int mid = (l + h + 1) >> 1; if (o.seg[mid].off <= i) l = mid; else h = mid - 1; }
+                    const float nw = (float)o.seg[l].Nw;
+                    s.x = s.x / nw; s.y = s.y / nw; s.z = s.z / nw; s.w = s.w / nw;
+                    if (o.mom) m = *reinterpret_cast<const float4*>(o.M + i);
+                } else { m = *reinterpret_cast<const float4*>(o.M + i); v = *reinterpret_cast<const float4*>(o.V + i); }
+                constexpr int K = MODE - 1;
+                opt_step<K>(g.x, s.x, m.x, v.x, 1.0f, o.mom, o.p); opt_step<K>(g.y, s.y, m.y, v.y, 1.0f, o.mom, o.p);
+                opt_step<K>(g.z, s.z, m.z, v.z, 1.0f, o.mom, o.p); opt_step<K>(g.w, s.w, m.w, v.w, 1.0f, o.mom, o.p);
+                *reinterpret_cast<float4*>(o.G + i) = g;
+                *reinterpret_cast<float4*>(buf + i) = make_float4(0, 0, 0, 0);
+                if (MODE == 1) { if (o.mom) *reinterpret_cast<float4*>(o.M + i) = m; }
+                else { *reinterpret_cast<float4*>(o.M + i) = m; *reinterpret_cast<float4*>(o.V + i) = v; }
+            }
+        }
+    } else {                                                   // MODE 0 only (see launcher)
+        for (int64_t i = lo + tid; i < hi; i += T4K_THREADS) {
+            float s = __ldcg(mine + i);
+            for (int r = 1; r < c.world; r++) s += __ldcg(mine + r * sstride + i);
+            buf[i] = s;
+        }
+    }
+    if (b == 0 && tid < nscal) {
+        float s = __ldcg(mine + c.cap + tid);
+        for (int r = 1; r < c.world; r++) s += __ldcg(mine + r * sstride + c.cap + tid);
+        scal[tid] = s;
+    }
+    if (tid == 0) c.epoch[b] = ep;
+}
+
+static CommDev devview(const t4k_comm *c) {
+    CommDev d;
+    for (int i = 0; i < COMM_MAXW; i++) d.peer[i] = c->peer[i];
+    d.epoch = c->epoch; d.cap = c->cap; d.rank = c->rank; d.world = c->world; d.ch4 = c->ch4;
+    return d;
+}
+static bool ready(const t4k_comm *c) {
+    if (!c || !c->base) return false;
+    for (int i = 0; i < c->world; i++) if (!c->peer[i]) return false;
+    return true;
+}
+
+} // namespace t4k
+using namespace t4k;
+
+extern "C" {
+
+int t4k_comm_create(int rank, int world, int64_t cap_floats, t4k_comm_t *out, void *handle64) {
+    if (!out || world < 1 || world > COMM_MAXW || rank < 0 || rank >= world || cap_floats < 1) return T4K_EINVAL;
+    t4k_comm *c = new (std::nothrow) t4k_comm();
+    if (!c) return T4K_ENOMEM;
+    memset(c, 0, sizeof(*c));
+    c->rank = rank; c->world = world;
+    c->cap = (cap_floats + 3) & ~(int64_t)3;
+    // chunking: a multiple of 32 float4s per chunk, about 2 chunks per SM, at most COMM_MAXB.  Peer-store throughput per SM is
+    // limited, so many small chunks win (0.79 MB, 2 GPUs: 296 chunks 9.9 us, 64: 18.6, 16: 53); T4K_COMM_CHUNKS overrides for tuning
+    const int64_t cap4 = c->cap / 4;
+    int64_t nb = cap4 / 256; int64_t want = 2 * (int64_t)sm_count();
+    if (const char *e = getenv("T4K_COMM_CHUNKS")) want = atoi(e) > 0 ? atoi(e) : want;
+    if (nb > want) nb = want; if (nb < 1) nb = 1; if (nb > COMM_MAXB) nb = COMM_MAXB;
+    int64_t ch4 = (cap4 + nb - 1) / nb; ch4 = (ch4 + 31) & ~(int64_t)31;
+    while ((cap4 + ch4 - 1) / ch4 > COMM_MAXB) ch4 += 32;
+    c->ch4 = (int)ch4;
+    if (cudaGetDevice(&c->dev) != cudaSuccess) { cudaGetLastError(); delete c; return T4K_EINVAL; }
+    c->bytes = (size_t)COMM_FLAGB + (size_t)2 * world * (size_t)(c->cap + COMM_NSCAL) * 4;
+    cudaError_t e = cudaMalloc((void**)&c->base, c->bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); delete c; return T4K_ENOMEM; }
+    e = cudaMalloc((void**)&c->epoch, (COMM_MAXB + 8) * 4);
+    if (e != cudaSuccess) { cudaGetLastError(); cudaFree(c->base); delete c; return T4K_ENOMEM; }
+    cudaMemset(c->base, 0, c->bytes);
+    cudaMemset(c->epoch, 0, (COMM_MAXB + 8) * 4);
+    cudaDeviceSynchronize();
+    c->peer[rank] = c->base;
+    if (handle64) {
+        cudaIpcMemHandle_t h;
+        static_assert(sizeof(h) <= T4K_COMM_HANDLE_BYTES, "handle size");
+        memset(handle64, 0, T4K_COMM_HANDLE_BYTES);
+        e = cudaIpcGetMemHandle(&h, c->base);
+        if (e != cudaSuccess) { cudaGetLastError(); if (world > 1) { cudaFree(c->base); cudaFree(c->epoch); delete c; return (int)e; } }
+        else memcpy(handle64, &h, sizeof(h));
+    }
+    *out = c;
+    return 0;
+}
+
+int t4k_comm_connect(t4k_comm_t c, const void *handles) {
+    if (!c || (!handles && c->world > 1)) return T4K_EINVAL;
+    for (int r = 0; r < c->world; r++) {
+        if (r == c->rank || c->peer[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * T4K_COMM_HANDLE_BYTES, sizeof(h));
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+        c->peer[r] = (char*)p; c->ipc[r] = true;
+    }
+    return 0;
+}
+
+/* same-process wiring (tests; several ranks of one process, on one or several devices with peer access enabled) */
+int t4k_comm_connect_local(t4k_comm_t c, t4k_comm_t *all) {
+    if (!c || !all) return T4K_EINVAL;
+    for (int r = 0; r < c->world; r++) {
+        if (!all[r] || all[r]->world != c->world || all[r]->rank != r || all[r]->cap != c->cap) return T4K_EINVAL;
+        c->peer[r] = all[r]->base;
+    }
+    return 0;
+}
+
+int t4k_comm_destroy(t4k_comm_t c) {
+    if (!c) return 0;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; r++) if (c->ipc[r] && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    if (c->base) cudaFree(c->base);
+    if (c->epoch) cudaFree(c->epoch);
+    cudaGetLastError();
+    delete c;
+    return 0;
+}
+
+/* 0 = healthy; k>0 = a wait for rank k-1 timed out (synchronises the device) */
+int t4k_comm_status(t4k_comm_t c) {
+    if (!c) return T4K_EINVAL;
+    uint32_t w = 0;
+    cudaError_t e = cudaMemcpy(&w, c->epoch + COMM_MAXB, 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return (int)e;
+    return (int)w;
+}
+
+int64_t t4k_comm_capacity(t4k_comm_t c) { return c ? c->cap : 0; }
+
+int t4k_allreduce_sum(t4k_comm_t c, float *buf, int64_t n, t4k_stream_t s) {
+    if (!ready(c) || !buf || n < 0 || n > c->cap) return T4K_EINVAL;
+    if (n == 0) return 0;
+    const int grid = (int)((((n + 3) / 4) + c->ch4 - 1) / c->ch4);
+    DpOpt o{};
+    if ((n & 3) == 0 && aligned16(buf)) k_dp_exchange<0, true ><<<grid, T4K_THREADS, 0, STRM(s)>>>(devview(c), buf, n, nullptr, 0, o);
+    else                                k_dp_exchange<0, false><<<grid, T4K_THREADS, 0, STRM(s)>>>(devview(c), buf, n, nullptr, 0, o);
+    return check_launch();
+}
+
+int t4k_optim_multi_dp(t4k_comm_t c, int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
+                       int64_t total, float lr, float b1, float b2, float wd, float *scal, int nscal, t4k_stream_t s) {
+    if (!ready(c) || !G || !DG || !seg || nseg < 1 || total < 0 || total > c->cap || (total & 3) || !aligned16(DG) || !aligned16(G) ||
+        nscal < 0 || nscal > COMM_NSCAL || (nscal && !scal)) return T4K_EINVAL;
+    if (total == 0) return 0;
+    const int grid = (int)(((total / 4) + c->ch4 - 1) / c->ch4);
+    DpOpt o{G, M, V, seg, nseg, true, OptP{lr, b1, b2, wd}};
+    CommDev d = devview(c);
+    switch (kind) {
+    case 0: o.mom = !(fabsf(b1) < DU_EPS); if (o.mom && !M) return T4K_EINVAL;
+            k_dp_exchange<1, true><<<grid, T4K_THREADS, 0, STRM(s)>>>(d, DG, total, scal, nscal, o); break;
+    case 1: if (!M || !V || !aligned16(M) || !aligned16(V)) return T4K_EINVAL;
+            k_dp_exchange<2, true><<<grid, T4K_THREADS, 0, STRM(s)>>>(d, DG, total, scal, nscal, o); break;
+    case 2: if (!M || !V || !aligned16(M) || !aligned16(V)) return T4K_EINVAL;
+            k_dp_exchange<3, true><<<grid, T4K_THREADS, 0, STRM(s)>>>(d, DG, total, scal, nscal, o); break;
+    default: return T4K_EINVAL;
+    }
+    return check_launch();
+}
+
+} // extern "C"

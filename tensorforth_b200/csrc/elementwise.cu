@@ -4,6 +4,7 @@
 // Roofline: all HBM-bound; algorithmic bytes per element are listed in DESIGN.md §kernels.
 #include "common.cuh"
 #include "act.cuh"
+#include "optim.cuh"
 
 namespace t4k {
 
@@ -182,21 +183,7 @@ __global__ void __launch_bounds__(T4K_THREADS) k_activate(const float *I, float 
     }
 }
 
-// ------------------------------------------------------------------ optimizers (one pass: read g,dg,m,v / write g,dg=0,m,v)
-struct OptP { float lr, b1, b2, wd; };
-template<int KIND> __device__ __forceinline__ void opt_step(float &g, float &dg, float &m, float &v, float invN, bool mom, OptP p) {
-    if (KIND == 0) {                                        // k_sgd (nmath.cu:419-436)
-        float d = dg * invN;                                // dg / Nw: Nw is a small power-of-two-free int; see launcher
-        if (!mom) g -= p.lr * d;
-        else { m = p.b1 * m + (1.0f - p.b1) * d; g -= p.lr * m; }
-    } else {                                                // k_adam / k_adamw (nmath.cu:438-472)
-        m = p.b1 * m + (1.0f - p.b1) * dg;
-        v = p.b2 * v + (1.0f - p.b2) * dg * dg;
-        if (KIND == 1) g -= p.lr * m / (__fsqrt_rn(v) + DU_EPS);
-        else           g -= p.lr * (m / (__fsqrt_rn(v) + DU_EPS) - p.wd * dg);
-    }
-    dg = 0.0f;
-}
+// ------------------------------------------------------------------ optimizers (one pass: read g,dg,m,v / write g,dg=0,m,v): optim.cuh
 // single tensor; SGD uses true division by Nw to match `DG[j] / N` bit for bit
 template<int KIND>
 __global__ void __launch_bounds__(T4K_THREADS) k_optim(float *G, float *DG, float *M, float *V, int Nw, bool mom, OptP p, int64_t n) {

@@ -571,7 +571,9 @@ Model &Model::_gradient(t4_optimizer op, DU lr, DU b1, DU b2, DU wd) {     // gr
     if (_iter++ == 0 && epoch == 0 && !_G) grad_alloc(op);
     if (!train || !_G) return *this;
     const int kind = (op == OPTI_SGD || op == OPTI_SGDM) ? 0 : (op == OPTI_ADAM ? 1 : 2);
-    KCHK(t4k_optim_multi(kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, (int64_t)_total, lr, b1, b2, wd, ST));
+    if (_comm) KCHK(t4k_optim_multi_dp((t4k_comm_t)_comm, kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, (int64_t)_total, lr, b1, b2, wd,
+                                       _dp_scal, _dp_nscal, ST));
+    else       KCHK(t4k_optim_multi(kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, (int64_t)_total, lr, b1, b2, wd, ST));
     return *this;
 }
 Model &Model::sgd(DU lr, DU b) {                                           // gradient.cu:133-143: momentum forced to 0 on the first call
@@ -586,6 +588,13 @@ int Model::arena(DU **G, DU **DG, int64_t *total) {
     if (DG) *DG = _DG;
     if (total) *total = (int64_t)_total;
     return _G ? 0 : T4K_EINVAL;
+}
+int Model::dp_attach(void *comm, DU *scal, int nscal) {
+    if (!_G) grad_alloc(OPTI_ADAM);
+    if (comm && (!_G || t4k_comm_capacity((t4k_comm_t)comm) < (int64_t)_total || nscal < 0 || nscal > 64)) return T4K_EINVAL;
+    _comm = comm; _dp_scal = scal; _dp_nscal = comm ? nscal : 0;
+    if (_graph_exec) { Runtime::sync(); cudaGraphExecDestroy((cudaGraphExec_t)_graph_exec); _graph_exec = nullptr; }   // the captured optimizer node changes
+    return 0;
 }
 // ---- one train step as a CUDA graph: forward + loss + backprop + optimizer
 int Model::step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd) {
@@ -743,6 +752,7 @@ int   t4h_model_sgd(t4h_model m, float lr, float b) { MM(m).sgd(lr, b); return 0
 int   t4h_model_adam(t4h_model m, float lr, float b1, float b2) { MM(m).adam(lr, b1, b2); return 0; }
 int   t4h_model_adamw(t4h_model m, float lr, float wd, float b1, float b2) { MM(m).adamw(lr, wd, b1, b2); return 0; }
 int   t4h_model_arena(t4h_model m, float **G, float **DG, int64_t *total) { return MM(m).arena(G, DG, total); }
+int   t4h_model_dp_attach(t4h_model m, void *comm, float *scal, int nscal) { return MM(m).dp_attach(comm, scal, nscal); }
 int   t4h_model_step_graph(t4h_model m, t4h_tensor input, t4h_tensor tgt, int lop, float *loss_dev, int optimizer, float lr, float b1, float b2, float wd) {
     return MM(m).step_graph(TT(input), TT(tgt), (t4_loss)lop, loss_dev, (t4_optimizer)optimizer, lr, b1, b2, wd);
 }

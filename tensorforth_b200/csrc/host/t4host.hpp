@@ -131,6 +131,7 @@ class Model {
     t4_optimizer _arena_opt = OPTI_SGD;
     // captured train step
     void   *_graph_exec = nullptr; U64 _graph_key[8] = {0};
+    void   *_comm = nullptr; DU *_dp_scal = nullptr; int _dp_nscal = 0;   // data parallel: t4k_comm_t + scalars riding in the exchange
     std::vector<Tensor*> _layers;      ///< layer i holds that layer's INPUT; last = output
 public:
     int  epoch    = 0;
@@ -165,6 +166,10 @@ public:
     Model &adam(DU lr, DU b1 = 0.9f, DU b2 = 0.999f);
     Model &adamw(DU lr, DU wd = 0.001f, DU b1 = 0.9f, DU b2 = 0.999f);
     int    arena(DU **G, DU **DG, int64_t *total);
+    // data parallel: with a communicator attached, the optimizer calls (sgd/adam/adamw, also inside step_graph)
+    // first SUM the gradient arena over the ranks — one fused exchange+optimizer kernel over NVLink peer memory (comm.cu);
+    // `scal[0..nscal)` device floats (this rank's loss sum …) are summed over the ranks in the same exchange
+    int    dp_attach(void *comm, DU *scal, int nscal);
     int    step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd);
 private:
     void _iconv(Tensor &in, U32 c, DU bias, U16 *opt);

@@ -67,6 +67,56 @@ def global_loss(local_loss, n_local, n_global, device="cpu"):
     return s / n_global
 
 
+def gather_bytes(payload, world=None):
+    """every rank contributes `payload` (bytes of one fixed length); returns the list in rank order.  Works on any
+    backend: the bytes travel as a uint8 tensor (on the current CUDA device under NCCL, on the host under gloo)."""
+    if not active():
+        return [bytes(payload)]
+    world = world or dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(payload), dtype=torch.uint8, device=dev)
+    outs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(outs, mine)
+    return [bytes(o.cpu().tolist()) for o in outs]
+
+
+class PeerComm:
+    """The exchange path of include/t4k.h's data-parallel extras: one exchange block per rank in its own HBM, mapped
+    into every peer with cudaIpc, written by NVLink peer stores from inside the kernels (csrc/comm.cu).  The only job of
+    the host is the rendezvous: create, gather the 64-byte handles (collective), connect."""
+
+    def __init__(self, cap_floats, rank=None, world=None):
+        import ctypes as C
+        from . import lib as _k
+        self._k, self._L = _k, _k.load()
+        self.rank = dist.get_rank() if rank is None and active() else (rank or 0)
+        self.world = dist.get_world_size() if world is None and active() else (world or 1)
+        h = C.c_void_p()
+        hb = (C.c_char * _k.COMM_HANDLE_BYTES)()
+        _k.check(self._L.t4k_comm_create(self.rank, self.world, int(cap_floats), C.byref(h), hb), "t4k_comm_create")
+        self.handle = h
+        allh = b"".join(gather_bytes(bytes(hb.raw), self.world))
+        _k.check(self._L.t4k_comm_connect(self.handle, allh), "t4k_comm_connect")
+        if active():
+            dist.barrier()                    # nobody pushes before every rank has mapped every block
+
+    def allreduce_sum_(self, flat):
+        """in-place SUM over the ranks of a float32 CUDA tensor, on the current torch stream"""
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous()
+        import ctypes as C
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self._k.check(self._L.t4k_allreduce_sum(self.handle, C.c_void_p(flat.data_ptr()), flat.numel(), st), "t4k_allreduce_sum")
+        return flat
+
+    def status(self):
+        return int(self._L.t4k_comm_status(self.handle))
+
+    def close(self):
+        if self.handle:
+            self._L.t4k_comm_destroy(self.handle)
+            self.handle = None
+
+
 class DataParallel:
     """Wraps a tensorforth_b200.host.Model that holds this rank's shard of the batch.
 
@@ -76,16 +126,29 @@ class DataParallel:
         model.adam(lr)                            # identical update on every rank
     """
 
-    def __init__(self, model, device, sync_params=True):
+    def __init__(self, model, device, sync_params=True, fused=False, scalars=None):
+        """fused=True: attach a PeerComm to the model — the SUM of the gradient arena over the ranks then happens inside
+        the optimizer kernel (model.adam()/sgd()/step_graph), over NVLink peer memory, and allreduce_grads() must not be
+        called; `scalars` (a float32 CUDA tensor of <= 64 elements, e.g. the loss sum) is summed in the same exchange.
+        fused=False: the gradient arena goes through torch.distributed (NCCL / gloo) in allreduce_grads()."""
         self.model, self.device = model, device
         g, dg, total = model.arena()              # builds the flat arenas on first use
-        self.params = device_view(g, total, device)
-        self.grads = device_view(dg, total, device)
+        self.params = device_view(g, total, device) if device.type == "cuda" else None
+        self.grads = device_view(dg, total, device) if device.type == "cuda" else None
         self.total = total
-        if sync_params:
+        self.comm = None
+        if sync_params and self.params is not None:
             broadcast_(self.params, 0)
+        if fused and active():
+            import ctypes as C
+            self.comm = PeerComm(total)
+            self._scalars = scalars               # keep alive
+            model.dp_attach(self.comm.handle, C.c_void_p(scalars.data_ptr()) if scalars is not None else None,
+                            scalars.numel() if scalars is not None else 0)
 
     def allreduce_grads(self):
+        if self.comm is not None:
+            raise RuntimeError("fused data parallel: the optimizer call does the exchange")
         return allreduce_sum_(self.grads)
 
     def hit(self):

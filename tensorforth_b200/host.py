@@ -39,6 +39,7 @@ PROTOTYPES = {
     "t4h_model_sgd": (_i, [_p, _f, _f]), "t4h_model_adam": (_i, [_p, _f, _f, _f]), "t4h_model_adamw": (_i, [_p, _f, _f, _f, _f]),
     "t4h_model_arena": (_i, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_l)]),
     "t4h_model_step_graph": (_i, [_p, _p, _p, _i, _p, _i, _f, _f, _f, _f]),
+    "t4h_model_dp_attach": (_i, [_p, _p, _p, _i]),
 }
 _lib = None
 
@@ -273,6 +274,12 @@ class Model:
         g, dg, n = _p(), _p(), _l()
         _k.check(load().t4h_model_arena(self.h, C.byref(g), C.byref(dg), C.byref(n)), "arena")
         return g.value, dg.value, n.value
+
+    def dp_attach(self, comm, scal_dev_ptr=None, nscal=0):
+        """data parallel: from now on the optimizer calls sum the gradient arena over the ranks of `comm` (a connected
+        t4k_comm_t handle, see dp.PeerComm) inside the optimizer kernel; `nscal` device floats ride along (summed)"""
+        _k.check(load().t4h_model_dp_attach(self.h, comm, scal_dev_ptr, nscal), "dp_attach")
+        return self
 
     def step_graph(self, x, tgt, loss_op, loss_dev_ptr, optimizer=2, lr=1e-3, b1=0.9, b2=0.999, wd=0.0):
         """forward + loss + backprop + optimizer as one replayed CUDA graph (optimizer: 0 sgd, 2 adam, 3 adamw)"""

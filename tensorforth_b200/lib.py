@@ -18,6 +18,7 @@ LOSS_MSE, LOSS_BCE, LOSS_CE, LOSS_NLL = range(4)
 UNIFORM, NORMAL = 0, 1
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = 0, 1, 2
 EINVAL, ENOSUP, ENOMEM = -1, -2, -3
+COMM_HANDLE_BYTES = 64
 
 _p, _i, _f, _l, _u64 = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint64
 
@@ -69,6 +70,14 @@ PROTOTYPES = {
     "t4k_adam": (_i, [_p, _p, _p, _p, _f, _f, _f, _l, _p]),
     "t4k_adamw": (_i, [_p, _p, _p, _p, _f, _f, _f, _f, _l, _p]),
     "t4k_optim_multi": (_i, [_i, _p, _p, _p, _p, _p, _i, _l, _f, _f, _f, _f, _p]),
+    "t4k_comm_create": (_i, [_i, _i, _l, C.POINTER(_p), _p]),
+    "t4k_comm_connect": (_i, [_p, _p]),
+    "t4k_comm_connect_local": (_i, [_p, C.POINTER(_p)]),
+    "t4k_comm_destroy": (_i, [_p]),
+    "t4k_comm_status": (_i, [_p]),
+    "t4k_comm_capacity": (_l, [_p]),
+    "t4k_allreduce_sum": (_i, [_p, _p, _l, _p]),
+    "t4k_optim_multi_dp": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _l, _f, _f, _f, _f, _p, _i, _p]),
     "t4k_rand_seed": (_i, [_u64]),
     "t4k_rand": (_i, [_p, _l, _i, _f, _f, _p]),
     "t4k_rand_at": (_i, [_p, _l, _i, _f, _f, _u64, _u64, _p]),

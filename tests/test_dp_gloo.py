@@ -87,6 +87,32 @@ def _worker(rank, world, port, N, q):
         dist.destroy_process_group()
 
 
+def _rendezvous_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        got = dp.gather_bytes(bytes([17 * (rank + 1)] * 64))        # what PeerComm does with the cudaIpc handles
+        if rank == 1:
+            q.put(got)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_handle_rendezvous_gathers_in_rank_order():
+    assert dp.gather_bytes(b"abc") == [b"abc"]                      # not distributed: own handle only
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rendezvous_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert got == [bytes([17] * 64), bytes([34] * 64)]
+
+
 def test_two_rank_step_equals_full_batch_step():
     from oracle import oracle as orc
     N, world = 12, 2

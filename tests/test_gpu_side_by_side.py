@@ -18,7 +18,7 @@ NEW = os.path.join(ROOT, "integration", "_build", "ten4_b200")
 def test_reference_vm_on_libt4k_prints_what_the_reference_prints(tmp_path):
     if not (os.path.exists(REF) and os.path.exists(NEW)):
         pytest.skip("oracle/_ref/ten4 or integration/_build/ten4_b200 not built")
-    out = str(tmp_path / "sbs")
+    out = os.path.join(ROOT, "gpurun_out", "side_by_side") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else str(tmp_path / "sbs")
     p = subprocess.run(["bash", os.path.join(ROOT, "integration", "run_side_by_side.sh"), out], capture_output=True, text=True, timeout=900)
     summary = open(os.path.join(out, "summary.txt")).read() if os.path.exists(os.path.join(out, "summary.txt")) else p.stdout
     sys.stdout.write(summary)
