@@ -68,6 +68,7 @@ int         t4k_device_count(void);                    /* 0 when no CUDA device/
 int         t4k_sm_count(void);                        /* SMs of the current device    */
 int         t4k_sync(t4k_stream_t stream);             /* cudaStreamSynchronize        */
 long        t4k_launch_count(void);                    /* kernels launched by this library so far */
+int         t4k_set_pdl(int on);                       /* programmatic dependent launch for the short kernels (default off, or T4K_PDL=1); returns the previous setting */
 
 /* ---- elementwise: src/t4math.cu:134-234 ------------------------------------------- */
 /* k_math via Tensor::map (src/mu/tensor.cu:566-571): in-place A[j] = op(A[j], v) */
@@ -225,9 +226,17 @@ int64_t t4k_comm_capacity(t4k_comm_t c);
 /* buf[i] = sum over ranks of buf[i], in place, n <= capacity */
 int t4k_allreduce_sum(t4k_comm_t c, float *buf, int64_t n, t4k_stream_t s);
 /* t4k_optim_multi on the rank-summed gradient: DG is exchanged, summed and consumed (zeroed) by the same kernel;
- * `scal[0..nscal)` (device, nscal <= 64: loss sums, hit counts) are sum-all-reduced in place in the same exchange */
+ * `scal[0..nscal)` (device, nscal <= 64: loss sums, hit counts) are sum-all-reduced in place in the same exchange.
+ * `pushed_from`: value returned by a t4k_dp_push of THIS step (0 or total: nothing was pushed early). */
 int t4k_optim_multi_dp(t4k_comm_t c, int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
-                       int64_t total, float lr, float b1, float b2, float wd, float *scal, int nscal, t4k_stream_t s);
+                       int64_t total, float lr, float b1, float b2, float wd, float *scal, int nscal, int64_t pushed_from,
+                       t4k_stream_t s);
+/* early half of a split exchange: push (and signal) the chunks of DG[0..total) that START at or beyond float `from` —
+ * the gradient segments that are already final while backprop still runs (gradients are produced last layer first, and
+ * the arena is laid out first layer first).  Returns the float offset of the first pushed chunk (pass it to
+ * t4k_optim_multi_dp as `pushed_from`; == total when nothing qualified), negative on error.  Exactly one
+ * t4k_optim_multi_dp must follow before the next push; no other exchange on this communicator in between. */
+int64_t t4k_dp_push(t4k_comm_t c, const float *DG, int64_t from, int64_t total, t4k_stream_t s);
 
 /* ---- RNG: src/util.cu:35-70 via System::rand (src/sys.cpp:77-95) ---------------------- */
 /* d[i] = scale * (bias + x), x ~ U(0,1] or N(0,1).  Counter-based Philox4x32-10 keyed by

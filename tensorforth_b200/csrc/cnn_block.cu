@@ -42,6 +42,7 @@ struct Cpr2P {
 template<int KS, int CP, int C0T, int C1T>
 __global__ void __launch_bounds__(256, 3) k_cpr2_fwd(Cpr2P p) {
     extern __shared__ __align__(16) float sm[];
+    pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     constexpr int P = (KS - 1) / 2;
     const int H = p.H, W = p.W, C1 = C1T ? C1T : p.C1, C0 = C0T ? C0T : p.C0;
     const int WP = W + 2 * P, HP = H + 2 * P;
@@ -194,6 +195,7 @@ __device__ __forceinline__ float warp_treduce32(float (&v)[32], int lane) {
 template<int CM, bool EXACT>
 __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
     extern __shared__ __align__(16) float sm[];
+    pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     constexpr int KS = 3, P = 1;
     constexpr int NG = (3 * CM + 31) / 32;              // 32-value groups per ky pass
     const int H = p.H, W = p.W, C0 = EXACT ? CM : p.C0;
@@ -449,7 +451,7 @@ extern "C" int t4k_conv_pool_relu_fwd(const float *I, const float *F, const floa
     const int threads = win_threads((H0 / 2) * (W0 / 2));
     const bool al = aligned16(convO) && aligned16(poolO) && aligned16(actO) && aligned16(actF) && (!flatO || aligned16(flatO));
     #define CPR2F(K_, CP_, CT_, C1_) { static bool attr = false; if (!attr && smem > 48 * 1024) { cudaFuncSetAttribute(k_cpr2_fwd<K_, CP_, CT_, C1_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; } \
-                                  k_cpr2_fwd<K_, CP_, CT_, C1_><<<N, threads, smem, STRM(s)>>>(p); }
+                                  launch_std(k_cpr2_fwd<K_, CP_, CT_, C1_>, dim3(N), dim3(threads), smem, STRM(s), p); }
     if (KS == 3) {
         if (al && C1 == 1 && C0 == 10) CPR2F(3, 12, 10, 1) else if (al && C1 == 1 && C0 == 16) CPR2F(3, 16, 16, 1) else if (al && C1 == 1 && C0 == 8) CPR2F(3, 8, 8, 1)
         else switch (CP) { case 4: CPR2F(3, 4, 0, 0) break; case 8: CPR2F(3, 8, 0, 0) break; case 12: CPR2F(3, 12, 0, 0) break; default: CPR2F(3, 16, 0, 0) break; }
@@ -473,7 +475,7 @@ extern "C" int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float 
     if (train) { p.part = (float*)workspace((size_t)N * (nF + C0) * sizeof(float), 4); if (!p.part) return T4K_ENOMEM; }
     const bool ex = (C0 == CM) && aligned16(convO);
     #define CPR2B(CM_, EX_) { static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_cpr2_bwd<CM_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cudaFuncSetAttribute(k_cpr2_bwd<CM_, EX_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); attr = true; } \
-                              k_cpr2_bwd<CM_, EX_><<<N, threads, smem, STRM(s)>>>(p); }
+                              launch_std(k_cpr2_bwd<CM_, EX_>, dim3(N), dim3(threads), smem, STRM(s), p); }
     if (CM == 10) { if (ex) CPR2B(10, true) else CPR2B(10, false) } else { if (ex) CPR2B(16, true) else CPR2B(16, false) }
     int rc = check_launch(); if (rc || !train) return rc;
     return wgrad_fin_launch(p.part, dF, dB, nF, C0, N, KS, S, STRM(s));

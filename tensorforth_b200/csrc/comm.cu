@@ -52,7 +52,9 @@ struct CommDev {
     int64_t cap;
     int rank, world, ch4;
 };
-struct DpOpt { float *G, *M, *V; const t4k_seg_t *seg; int nseg; bool mom; OptP p; };
+struct DpOpt { float *G, *M, *V; const t4k_seg_t *seg; int nseg; bool mom; OptP p;
+               int b0;                  // first chunk of this launch (push-only launches start past the late chunks)
+               int64_t pushed_from; };  // chunks starting at or beyond this float were pushed by an earlier MODE -1 launch of this epoch
 
 __device__ __forceinline__ float *slot_of(const CommDev &c, int where, int par, int r) {
     return reinterpret_cast<float*>(c.peer[where] + COMM_FLAGB) + (int64_t)(par * c.world + r) * (c.cap + COMM_NSCAL);
@@ -63,10 +65,14 @@ __device__ __forceinline__ uint32_t *flag_of(const CommDev &c, int where, int r,
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 // MODE 0: buf = Σ_r buf_r (in place).  MODE 1/2/3: sgd / adam / adamw on (G, Σ_r DG_r, M, V), DG = 0.
+// MODE -1: push + signal only (no wait, no finish, epoch not advanced): the early half of a split exchange — the gradient
+// segments that are final before backprop ends travel while the remaining backward kernels run (Model::step_graph forks
+// this launch onto a side stream); the MODE 1/2/3 launch that follows pushes only the chunks below `pushed_from`.
 template<int MODE, bool VEC>
 __global__ void __launch_bounds__(T4K_THREADS) k_dp_exchange(const __grid_constant__ CommDev c, float *buf, int64_t n, float *scal, int nscal, DpOpt o) {
     __shared__ uint32_t s_ep;
-    const int b = blockIdx.x, tid = threadIdx.x;
+    pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
+    const int b = blockIdx.x + o.b0, tid = threadIdx.x;
     if (tid == 0) s_ep = c.epoch[b] + 1;
     __syncthreads();
     const uint32_t ep = s_ep;
@@ -74,7 +80,9 @@ __global__ void __launch_bounds__(T4K_THREADS) k_dp_exchange(const __grid_consta
     const int64_t lo = (int64_t)b * c.ch4 * 4;
     const int64_t hi = (lo + (int64_t)c.ch4 * 4 < n) ? lo + (int64_t)c.ch4 * 4 : n;
     // ---- push this rank's chunk to every rank's slot[par][rank] (own slot last: it is the only local store)
-    if (VEC) {
+    const bool do_push = MODE < 0 || lo < o.pushed_from;
+    if (!do_push) { /* pushed and signalled by the early launch */ }
+    else if (VEC) {
         for (int64_t i = lo + 4 * tid; i < hi; i += 4 * T4K_THREADS) {
             const float4 v = *reinterpret_cast<const float4*>(buf + i);
             #pragma unroll 1
@@ -89,7 +97,7 @@ __global__ void __launch_bounds__(T4K_THREADS) k_dp_exchange(const __grid_consta
             for (int k = 1; k <= c.world; k++) slot_of(c, (c.rank + k) % c.world, par, c.rank)[i] = v;
         }
     }
-    if (b == 0 && tid < nscal) {
+    if (MODE >= 0 && b == 0 && tid < nscal) {
         const float v = scal[tid];
         for (int k = 1; k <= c.world; k++) slot_of(c, (c.rank + k) % c.world, par, c.rank)[c.cap + tid] = v;
     }
@@ -97,10 +105,11 @@ __global__ void __launch_bounds__(T4K_THREADS) k_dp_exchange(const __grid_consta
     // ---- signal every rank, then wait for every rank's signal for this chunk.  ONE fence.sys per block: the barrier orders the
     // block's peer stores before thread 0's fence, and fences are cumulative, so the flag stores that follow publish all of
     // them (measured on 2 B200s, 0.79 MB: a fence in every thread 17.7 us, this 9.9 us; NCCL 14.5 us).
-    if (tid == 0) {
+    if (tid == 0 && do_push) {
         __threadfence_system();
         for (int k = 1; k <= c.world; k++) *reinterpret_cast<volatile uint32_t*>(flag_of(c, (c.rank + k) % c.world, c.rank, b)) = ep;
     }
+    if (MODE < 0) return;
     if (tid < c.world) {
         const uint32_t *f = flag_of(c, c.rank, tid, b);
         const long long t0 = clock64();
@@ -257,27 +266,38 @@ int t4k_allreduce_sum(t4k_comm_t c, float *buf, int64_t n, t4k_stream_t s) {
     if (!ready(c) || !buf || n < 0 || n > c->cap) return T4K_EINVAL;
     if (n == 0) return 0;
     const int grid = (int)((((n + 3) / 4) + c->ch4 - 1) / c->ch4);
-    DpOpt o{};
-    if ((n & 3) == 0 && aligned16(buf)) k_dp_exchange<0, true ><<<grid, T4K_THREADS, 0, STRM(s)>>>(devview(c), buf, n, nullptr, 0, o);
-    else                                k_dp_exchange<0, false><<<grid, T4K_THREADS, 0, STRM(s)>>>(devview(c), buf, n, nullptr, 0, o);
+    DpOpt o{}; o.pushed_from = c->cap + 1;
+    if ((n & 3) == 0 && aligned16(buf)) launch_pdl(k_dp_exchange<0, true>, dim3(grid), dim3(T4K_THREADS), 0, STRM(s), devview(c), buf, n, nullptr, 0, o);
+    else                                launch_pdl(k_dp_exchange<0, false>, dim3(grid), dim3(T4K_THREADS), 0, STRM(s), devview(c), buf, n, nullptr, 0, o);
     return check_launch();
 }
 
+int64_t t4k_dp_push(t4k_comm_t c, const float *DG, int64_t from, int64_t total, t4k_stream_t s) {
+    if (!ready(c) || !DG || from < 0 || total < 0 || total > c->cap || (total & 3) || !aligned16(DG)) return T4K_EINVAL;
+    const int64_t chf = (int64_t)c->ch4 * 4;
+    const int64_t b0 = (from + chf - 1) / chf, nb = (total + chf - 1) / chf;
+    if (b0 >= nb) return total;                                   // nothing starts at or beyond `from`
+    DpOpt o{}; o.b0 = (int)b0; o.pushed_from = 0;
+    launch_pdl(k_dp_exchange<-1, true>, dim3((unsigned)(nb - b0)), dim3(T4K_THREADS), 0, STRM(s), devview(c), const_cast<float*>(DG), total, nullptr, 0, o);
+    const int rc = check_launch();
+    return rc ? (rc > 0 ? -(int64_t)rc - 1000 : rc) : b0 * chf;
+}
+
 int t4k_optim_multi_dp(t4k_comm_t c, int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
-                       int64_t total, float lr, float b1, float b2, float wd, float *scal, int nscal, t4k_stream_t s) {
+                       int64_t total, float lr, float b1, float b2, float wd, float *scal, int nscal, int64_t pushed_from, t4k_stream_t s) {
     if (!ready(c) || !G || !DG || !seg || nseg < 1 || total < 0 || total > c->cap || (total & 3) || !aligned16(DG) || !aligned16(G) ||
         nscal < 0 || nscal > COMM_NSCAL || (nscal && !scal)) return T4K_EINVAL;
     if (total == 0) return 0;
     const int grid = (int)(((total / 4) + c->ch4 - 1) / c->ch4);
-    DpOpt o{G, M, V, seg, nseg, true, OptP{lr, b1, b2, wd}};
+    DpOpt o{G, M, V, seg, nseg, true, OptP{lr, b1, b2, wd}, 0, (pushed_from > 0 && pushed_from <= total) ? pushed_from : total + 1};
     CommDev d = devview(c);
     switch (kind) {
     case 0: o.mom = !(fabsf(b1) < DU_EPS); if (o.mom && !M) return T4K_EINVAL;
-            k_dp_exchange<1, true><<<grid, T4K_THREADS, 0, STRM(s)>>>(d, DG, total, scal, nscal, o); break;
+            launch_pdl(k_dp_exchange<1, true>, dim3(grid), dim3(T4K_THREADS), 0, STRM(s), d, DG, total, scal, nscal, o); break;
     case 1: if (!M || !V || !aligned16(M) || !aligned16(V)) return T4K_EINVAL;
-            k_dp_exchange<2, true><<<grid, T4K_THREADS, 0, STRM(s)>>>(d, DG, total, scal, nscal, o); break;
+            launch_pdl(k_dp_exchange<2, true>, dim3(grid), dim3(T4K_THREADS), 0, STRM(s), d, DG, total, scal, nscal, o); break;
     case 2: if (!M || !V || !aligned16(M) || !aligned16(V)) return T4K_EINVAL;
-            k_dp_exchange<3, true><<<grid, T4K_THREADS, 0, STRM(s)>>>(d, DG, total, scal, nscal, o); break;
+            launch_pdl(k_dp_exchange<3, true>, dim3(grid), dim3(T4K_THREADS), 0, STRM(s), d, DG, total, scal, nscal, o); break;
     default: return T4K_EINVAL;
     }
     return check_launch();

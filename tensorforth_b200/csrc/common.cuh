@@ -24,6 +24,35 @@ int gemm_simt(const float *A, const float *B, float *O, float alpha, float beta,
 
 static inline cudaStream_t STRM(t4k_stream_t s) { return (cudaStream_t)s; }
 
+// ---- programmatic dependent launch (PDL).  A train step is a chain of ~12 short dependent kernels; with a plain
+// launch each one pays the previous grid's drain + its own launch/ramp latency (2-3 us per boundary).  Kernels launched
+// with launch_pdl() may be scheduled as soon as every CTA of the previous grid has passed pdl_trigger(); they run their
+// prologue (index math, shared-memory halos) and block in pdl_wait() until the previous grid has completed and its
+// memory is visible.  Rule kept everywhere: NO global access before pdl_wait().  Works in eager streams and under
+// CUDA-graph capture (programmatic edges).  Off by default (see below); T4K_PDL=1 / t4k_set_pdl(1) turns it on.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_wait()    { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Measured on the MNIST step (B200, 200 steps): the attribute on EVERY kernel made the step slower (100.3 -> 108.5 us):
+// early-resident CTAs of a machine-filling kernel (GEMM, conv block) pile onto the first SMs the previous grid frees and
+// the grid starts unbalanced (linear_bwd 24.6 -> 33.9 us), while the short kernels gain 0.3-0.5 us each.  So only the
+// short, latency-bound kernels are launched with it (launch_pdl); machine-filling ones use launch_std (they still execute
+// pdl_trigger, so the short kernel behind them is scheduled early).
+template<bool PDL, typename... KA, typename... A>
+static inline void launch_k(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (PDL && g_pdl) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KA(args)...);
+}
+template<typename... KA, typename... A>
+static inline void launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) { launch_k<true>(kern, grid, block, smem, st, args...); }
+template<typename... KA, typename... A>
+static inline void launch_std(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) { launch_k<false>(kern, grid, block, smem, st, args...); }
+
 // persistent-ish grid for HBM streaming kernels: enough CTAs to cover n items at `per_thread`
 // each, capped at 8 resident CTAs of 256 threads per SM (148 x 8 = 1184).
 static inline int stream_grid(int64_t n_items, int per_thread = 1) {

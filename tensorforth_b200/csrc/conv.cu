@@ -163,6 +163,7 @@ __host__ __device__ __forceinline__ int dconv_flush_mult(int KS, int S, int tap)
 __global__ void __launch_bounds__(T4K_THREADS) k_wgrad_fin(const float *__restrict__ part, float *dF, float *dB,
                                                            int nF, int C0, int nparts, int KS, int S) {
     __shared__ float red[T4K_THREADS / 32];
+    pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     const int t = blockIdx.x;                                      // one output element per CTA
     float v = 0.0f;
     for (int c = threadIdx.x; c < nparts; c += blockDim.x) v += part[(int64_t)c * (nF + C0) + t];
@@ -583,7 +584,7 @@ extern "C" int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, f
                                     k_conv_wgrad_small<K_><<<ctas, T4K_THREADS, smem_small, st>>>(p, part, strips); }
             switch (KS) { case 1: WG_LAUNCH(1) break; case 3: WG_LAUNCH(3) break; case 4: WG_LAUNCH(4) break; default: WG_LAUNCH(5) break; }
             rc = check_launch(); if (rc) return rc;
-            k_wgrad_fin<<<nF + C0, T4K_THREADS, 0, st>>>(part, dF, dB, nF, C0, ctas, KS, S);
+            launch_pdl(k_wgrad_fin, dim3(nF + C0), dim3(T4K_THREADS), 0, st, part, dF, dB, nF, C0, ctas, KS, S);
             rc = check_launch(); if (rc) return rc;
         } else {
             const int64_t Kg = (int64_t)N * H0 * W0;
@@ -672,11 +673,11 @@ int cpr_v1_bwd(const float *dY, float *actO, const float *actF, float *poolO, fl
                        k_cpr_bwd<K_><<<N, T4K_THREADS, smem, s>>>(p); }
     switch (KS) { case 1: CPRB(1) break; case 3: CPRB(3) break; case 4: CPRB(4) break; default: CPRB(5) break; }
     int rc = check_launch(); if (rc || !train) return rc;
-    k_wgrad_fin<<<nF + C0, T4K_THREADS, 0, s>>>(p.part, dF, dB, nF, C0, N, KS, S);
+    launch_pdl(k_wgrad_fin, dim3(nF + C0), dim3(T4K_THREADS), 0, s, p.part, dF, dB, nF, C0, N, KS, S);
     return check_launch();
 }
 int wgrad_fin_launch(const float *part, float *dF, float *dB, int nF, int C0, int nparts, int KS, int S, cudaStream_t st) {
-    k_wgrad_fin<<<nF + C0, T4K_THREADS, 0, st>>>(part, dF, dB, nF, C0, nparts, KS, S);
+    launch_pdl(k_wgrad_fin, dim3(nF + C0), dim3(T4K_THREADS), 0, st, part, dF, dB, nF, C0, nparts, KS, S);
     return check_launch();
 }
 } // namespace t4k

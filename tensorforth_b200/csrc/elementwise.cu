@@ -203,6 +203,7 @@ template<int KIND>
 __global__ void __launch_bounds__(T4K_THREADS) k_optim_multi(float *G, float *DG, float *M, float *V,
                                                              const t4k_seg_t *__restrict__ seg, int nseg,
                                                              int64_t total, bool mom, OptP p) {
+    pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = tid; j < total; j += nth) {
@@ -362,9 +363,9 @@ extern "C" int t4k_optim_multi(int kind, float *G, float *DG, float *M, float *V
     const int g = stream_grid(total);
     switch (kind) {
     case 0: { const bool mom = !(fabsf(b1) < DU_EPS); if (mom && !M) return T4K_EINVAL;
-              k_optim_multi<0><<<g, T4K_THREADS, 0, STRM(s)>>>(G, DG, M, V, seg, nseg, total, mom, p); } break;
-    case 1: if (!M || !V) return T4K_EINVAL; k_optim_multi<1><<<g, T4K_THREADS, 0, STRM(s)>>>(G, DG, M, V, seg, nseg, total, true, p); break;
-    case 2: if (!M || !V) return T4K_EINVAL; k_optim_multi<2><<<g, T4K_THREADS, 0, STRM(s)>>>(G, DG, M, V, seg, nseg, total, true, p); break;
+              launch_pdl(k_optim_multi<0>, dim3(g), dim3(T4K_THREADS), 0, STRM(s), G, DG, M, V, seg, nseg, total, mom, p); } break;
+    case 1: if (!M || !V) return T4K_EINVAL; launch_pdl(k_optim_multi<1>, dim3(g), dim3(T4K_THREADS), 0, STRM(s), G, DG, M, V, seg, nseg, total, true, p); break;
+    case 2: if (!M || !V) return T4K_EINVAL; launch_pdl(k_optim_multi<2>, dim3(g), dim3(T4K_THREADS), 0, STRM(s), G, DG, M, V, seg, nseg, total, true, p); break;
     default: return T4K_EINVAL;
     }
     return check_launch();

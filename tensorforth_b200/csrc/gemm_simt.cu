@@ -25,6 +25,7 @@ template<bool TA, bool TB>
 __global__ void __launch_bounds__(256) k_gemm_simt(GemmP p) {
     __shared__ float sA[2][SBK][SBM + 4];
     __shared__ float sB[2][SBK][SBN + 4];
+    pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int zc = blockIdx.z % p.C;                          // channel
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(256) k_gemm_simt(GemmP p) {
 
 // split-K epilogue: O = alpha * Σ_s part[s] + beta * O   (fixed order → deterministic)
 __global__ void __launch_bounds__(T4K_THREADS) k_splitk_fin(GemmP p, int batch) {
+    pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     const int64_t MN = (int64_t)p.M * p.N, total = MN * p.C * batch;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = t % MN; const int bc = (int)(t / MN); const int b = bc / p.C, c = bc % p.C;
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(128) k_gemm_v2(GemmP p) {
     constexpr int NA = BM * VBK / 4 / 128, NB = BN * VBK / 4 / 128;      // float4 loads per thread per k-tile
     __shared__ __align__(16) float sA[2][VBK][BM + 4];
     __shared__ __align__(16) float sB[2][VBK][BN + 4];
+    pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
     const int zs = blockIdx.z % p.splits, zb = blockIdx.z / p.splits;
     const int M = p.M, N = p.N, K = p.K;
@@ -236,8 +239,8 @@ __global__ void __launch_bounds__(128) k_gemm_v2(GemmP p) {
     }
 }
 template<int BM, int BN, int TM, int TN> static void launch_v2(const GemmP &p, dim3 g, int tA, int tB, cudaStream_t st) {
-    if (tA) { if (tB) k_gemm_v2<true, true, BM, BN, TM, TN><<<g, 128, 0, st>>>(p); else k_gemm_v2<true, false, BM, BN, TM, TN><<<g, 128, 0, st>>>(p); }
-    else    { if (tB) k_gemm_v2<false, true, BM, BN, TM, TN><<<g, 128, 0, st>>>(p); else k_gemm_v2<false, false, BM, BN, TM, TN><<<g, 128, 0, st>>>(p); }
+    if (tA) { if (tB) launch_std(k_gemm_v2<true, true, BM, BN, TM, TN>, g, dim3(128), 0, st, p); else launch_std(k_gemm_v2<true, false, BM, BN, TM, TN>, g, dim3(128), 0, st, p); }
+    else    { if (tB) launch_std(k_gemm_v2<false, true, BM, BN, TM, TN>, g, dim3(128), 0, st, p); else launch_std(k_gemm_v2<false, false, BM, BN, TM, TN>, g, dim3(128), 0, st, p); }
 }
 static bool v2_ok(const float *A, const float *B, const float *O, int tA, int tB, int M, int N, int K, int C, int64_t sA, int64_t sB, int64_t sO) {
     if (C != 1 || (N & 3) || !aligned16(A) || !aligned16(B) || !aligned16(O) || (sA & 3) || (sB & 3) || (sO & 3)) return false;
@@ -284,13 +287,13 @@ int gemm_simt(const float *A, const float *B, float *O, float alpha, float beta,
     dim3 g(gx, gy, C * splits * batch);
     if (K == 0) { p.splits = 1; }
     if (v2) { if (!wide) launch_v2<128, 64, 8, 8>(p, g, tA, tB, st); else if (big) launch_v2<64, 128, 8, 8>(p, g, tA, tB, st); else launch_v2<64, 64, 8, 4>(p, g, tA, tB, st); }
-    else if (tA) { if (tB) k_gemm_simt<true, true ><<<g, 256, 0, st>>>(p); else k_gemm_simt<true, false><<<g, 256, 0, st>>>(p); }
-    else    { if (tB) k_gemm_simt<false, true><<<g, 256, 0, st>>>(p); else k_gemm_simt<false, false><<<g, 256, 0, st>>>(p); }
+    else if (tA) { if (tB) launch_std(k_gemm_simt<true, true >, g, dim3(256), 0, st, p); else launch_std(k_gemm_simt<true, false>, g, dim3(256), 0, st, p); }
+    else    { if (tB) launch_std(k_gemm_simt<false, true>, g, dim3(256), 0, st, p); else launch_std(k_gemm_simt<false, false>, g, dim3(256), 0, st, p); }
     int rc = check_launch();
     if (defer) { defer->part = p.splits > 1 ? p.part : O; defer->splits = p.splits; return rc; }
     if (rc || p.splits == 1) return rc;
     const int64_t total = (int64_t)M * N * C * batch;
-    k_splitk_fin<<<stream_grid(total), T4K_THREADS, 0, st>>>(p, batch);
+    launch_pdl(k_splitk_fin, dim3(stream_grid(total)), dim3(T4K_THREADS), 0, st, p, batch);
     return check_launch();
 }
 

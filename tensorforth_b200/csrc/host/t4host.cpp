@@ -12,7 +12,8 @@
 namespace t4 {
 
 // =============================================================================== Runtime
-static cudaStream_t g_stream = nullptr;
+static cudaStream_t g_stream = nullptr, g_stream2 = nullptr;      // library stream + side stream (forked work inside a step)
+static cudaEvent_t  g_fork = nullptr, g_join = nullptr;
 static bool  g_init = false;
 static char  g_err[512] = "";
 
@@ -20,6 +21,8 @@ int Runtime::init(int device) {
     if (g_init) return 0;
     if (cudaSetDevice(device) != cudaSuccess) { error("cudaSetDevice(%d) failed: no CUDA device (there is no CPU fallback)", device); cudaGetLastError(); return T4K_EINVAL; }
     if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) { error("cudaStreamCreate failed"); return T4K_EINVAL; }
+    if (cudaStreamCreateWithFlags(&g_stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming) != cudaSuccess) { error("cudaStreamCreate failed"); return T4K_EINVAL; }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t keep = UINT64_MAX;                     // keep freed blocks cached: alloc/free in `for @ drop next` loops stay cheap
@@ -419,6 +422,7 @@ Model &Model::backprop(Tensor &tgt) {
     else { i = nxt; j = 1; }
     for (; i >= 0; j++) {
         const t4_layer fn = _layers[i]->grad_fn;
+        if (_dp_early && _dp_pushed_from < 0 && i < _second_layer) _dp_push();     // every gradient but the first parameter layer's is final
         const int adv = (j > 0 && (fn == T4K_L_FLATTEN || fn == T4K_L_RELU)) ? _bfused(i) : 0;
         if (adv) { i -= adv; continue; }
         if (skip_db && fn == T4K_L_LINEAR) { _blinear(*_layers[i], *_layers[i + 1], true); skip_db = false; }
@@ -426,6 +430,17 @@ Model &Model::backprop(Tensor &tgt) {
         i--;
     }
     return *this;
+}
+void Model::_dp_push() {
+    // Split exchange (comm.cu MODE -1): fork a side stream off the library stream, push the finished part of the gradient
+    // arena to the peers while the remaining backward kernels run; Model::_gradient joins it in front of the optimizer.
+    cudaStream_t st = (cudaStream_t)ST;
+    cudaEventRecord(g_fork, st); cudaStreamWaitEvent(g_stream2, g_fork, 0);
+    const int64_t r = t4k_dp_push((t4k_comm_t)_comm, _DG, _first_end, (int64_t)_total, (t4k_stream_t)g_stream2);
+    cudaEventRecord(g_join, g_stream2);
+    _dp_join = true;
+    if (r < 0) { Runtime::error("t4k_dp_push -> %ld", (long)r); _dp_pushed_from = (int64_t)_total; }
+    else _dp_pushed_from = r;
 }
 int Model::_bprep(Tensor &tgt) {                                          // backprop.cu:76-109
     Tensor &out = (*this)[-1];
@@ -536,18 +551,23 @@ Model &Model::grad_alloc(t4_optimizer op) {
     // Reference: per-tensor m / v tensors (gradient.cu:20-59).  Here: every (w,dw),(b,db) pair moves into flat
     // arenas G / DG (+ M, V, zero filled) at identical offsets, the Tensor objects become views; one
     // t4k_optim_multi launch then updates the whole model and DG is one contiguous all-reduce payload.
-    struct Seg { Tensor *g, *dg; int Nw; };
+    struct Seg { Tensor *g, *dg; int Nw; int layer; };
     std::vector<Seg> segs;
     for (size_t i = 0; i + 1 < _layers.size(); i++) {
         Tensor &in = *_layers[i];
-        if (in.grad[0] && in.grad[2]) segs.push_back({in.grad[0], in.grad[2], (int)in.grad[0]->N()});   // Nw = parameter tensor's N() (gradient.cu:137)
-        if (in.grad[1] && in.grad[3]) segs.push_back({in.grad[1], in.grad[3], (int)in.grad[1]->N()});
+        if (in.grad[0] && in.grad[2]) segs.push_back({in.grad[0], in.grad[2], (int)in.grad[0]->N(), (int)i});   // Nw = parameter tensor's N() (gradient.cu:137)
+        if (in.grad[1] && in.grad[3]) segs.push_back({in.grad[1], in.grad[3], (int)in.grad[1]->N(), (int)i});
     }
     _arena_opt = op;
     if (segs.empty()) return *this;
     std::vector<t4k_seg_t> table;
     U64 off = 0;
-    for (auto &s : segs) { U64 len = (s.g->numel + 3) & ~3ull; table.push_back({(int64_t)off, (int64_t)len, s.Nw, 0}); off += len; }
+    _second_layer = (int)_layers.size(); _first_end = 0;
+    for (auto &s : segs) {
+        U64 len = (s.g->numel + 3) & ~3ull; table.push_back({(int64_t)off, (int64_t)len, s.Nw, 0}); off += len;
+        if (s.layer == segs[0].layer) _first_end = (int64_t)off;
+        else if (s.layer < _second_layer) _second_layer = s.layer;
+    }
     _total = off; _nseg = (int)segs.size();
     _G = (DU*)Runtime::alloc(_total * 4); _DG = (DU*)Runtime::alloc(_total * 4);
     _M = (DU*)Runtime::alloc(_total * 4); _V  = (DU*)Runtime::alloc(_total * 4);
@@ -571,8 +591,12 @@ Model &Model::_gradient(t4_optimizer op, DU lr, DU b1, DU b2, DU wd) {     // gr
     if (_iter++ == 0 && epoch == 0 && !_G) grad_alloc(op);
     if (!train || !_G) return *this;
     const int kind = (op == OPTI_SGD || op == OPTI_SGDM) ? 0 : (op == OPTI_ADAM ? 1 : 2);
-    if (_comm) KCHK(t4k_optim_multi_dp((t4k_comm_t)_comm, kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, (int64_t)_total, lr, b1, b2, wd,
-                                       _dp_scal, _dp_nscal, ST));
+    if (_comm) {
+        if (_dp_join) { cudaStreamWaitEvent((cudaStream_t)ST, g_join, 0); _dp_join = false; }     // the early push of this step (side stream)
+        KCHK(t4k_optim_multi_dp((t4k_comm_t)_comm, kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, (int64_t)_total, lr, b1, b2, wd,
+                                _dp_scal, _dp_nscal, _dp_pushed_from > 0 ? _dp_pushed_from : (int64_t)_total, ST));
+        _dp_pushed_from = -1;
+    }
     else       KCHK(t4k_optim_multi(kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, (int64_t)_total, lr, b1, b2, wd, ST));
     return *this;
 }
@@ -601,7 +625,9 @@ int Model::step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_
     auto run = [&]() {
         forward(input);
         if (loss_dev) loss_async(lop, tgt, loss_dev);
+        _dp_early = _comm && (int)op >= 0 && train && _G;  // forward -> backprop -> optimizer is one unit here: the exchange may start early
         backprop(tgt);
+        _dp_early = false;
         if ((int)op < 0) return;                          // data parallel: the caller all-reduces DG, then calls the optimizer
         switch (op) { case OPTI_SGD: case OPTI_SGDM: sgd(lr, b1); break; case OPTI_ADAM: adam(lr, b1, b2); break; default: adamw(lr, wd, b1, b2); }
     };

@@ -132,6 +132,9 @@ class Model {
     // captured train step
     void   *_graph_exec = nullptr; U64 _graph_key[8] = {0};
     void   *_comm = nullptr; DU *_dp_scal = nullptr; int _dp_nscal = 0;   // data parallel: t4k_comm_t + scalars riding in the exchange
+    int     _second_layer = 0; int64_t _first_end = 0;                    // arena layout: end of the first parameter layer's segments, index of the next parameter layer
+    bool    _dp_early = false, _dp_join = false; int64_t _dp_pushed_from = -1;   // split exchange inside step_graph (early push on the side stream)
+    void    _dp_push();
     std::vector<Tensor*> _layers;      ///< layer i holds that layer's INPUT; last = output
 public:
     int  epoch    = 0;

@@ -18,6 +18,7 @@ namespace t4k {
 template<int L>
 __global__ void __launch_bounds__(T4K_THREADS) k_linear_fin(const float *__restrict__ part, int splits, int64_t MN, int E0,
                                                             const float *__restrict__ bias, float *Y, float *A, float *F, float alpha, int vec) {
+    pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
     if (vec) {
         for (int64_t q = tid; q < (MN >> 2); q += nth) {
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(T4K_THREADS) k_linear_fin(const float *__restr
 }
 template<int L> static int launch_fin(const GemmDeferred &d, int64_t MN, int E0, const float *B, float *Y, float *A, float *F, float alpha, cudaStream_t st) {
     const int vec = ((E0 & 3) == 0) && aligned16(d.part) && aligned16(B) && aligned16(Y) && (L == T4K_L_NONE || (aligned16(A) && aligned16(F)));
-    k_linear_fin<L><<<stream_grid(MN, vec ? 4 : 1), T4K_THREADS, 0, st>>>(d.part, d.splits, MN, E0, B, Y, A, F, alpha, vec);
+    launch_pdl(k_linear_fin<L>, dim3(stream_grid(MN, vec ? 4 : 1)), dim3(T4K_THREADS), 0, st, d.part, d.splits, MN, E0, B, Y, A, F, alpha, (int)vec);
     return check_launch();
 }
 static int linear_act_fwd(int layer, const float *X, const float *W, const float *B, float *Y, float *A, float *F, float alpha,
@@ -88,6 +89,7 @@ __device__ __forceinline__ float warp_treduce32(float (&v)[32], int lane) {
 __global__ void __launch_bounds__(T4K_THREADS) k_head_fwd(const float *__restrict__ X, const float *__restrict__ W, const float *__restrict__ B,
                                                           float *Y, float *P, int N, int E0, int E1) {
     extern __shared__ float sW[];                      // [E0][E1]
+    pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     for (int t = threadIdx.x; t < E0 * E1; t += blockDim.x) sW[t] = __ldg(W + t);
     __syncthreads();
     const int lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
@@ -139,6 +141,7 @@ __device__ __forceinline__ float ld_dsmem(const float *local, uint32_t rank) {  
 template<int KM>                                       // KM = compile-time bound on E0 (8, 16 or 32); E1 <= 128
 __global__ void __cluster_dims__(HB_CTAS, 1, 1) __launch_bounds__(T4K_THREADS) k_head_bwd(HeadB p) {
     extern __shared__ float sm[];
+    pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     const int E0 = p.E0, E1 = p.E1, nE = E0 * E1 + E0 + E1;
     float *sW = sm;                                    // [E0][128]       rows zero-padded: no column guards in the hot loop
     float *sPart = sm + E0 * 128;                      // [nE]            this CTA's partial (read by the whole cluster)
@@ -286,7 +289,7 @@ extern "C" int t4k_mlp_head_fwd(const float *X, const float *W, const float *B, 
     const int rows_per_cta = T4K_THREADS / 32;
     int g = (N + rows_per_cta - 1) / rows_per_cta;
     if (g > 2 * sm_count()) g = 2 * sm_count();
-    k_head_fwd<<<g, T4K_THREADS, (size_t)E0 * E1 * sizeof(float), STRM(s)>>>(X, W, B, Y, P, N, E0, E1);
+    launch_pdl(k_head_fwd, dim3(g), dim3(T4K_THREADS), (size_t)E0 * E1 * sizeof(float), STRM(s), X, W, B, Y, P, N, E0, E1);
     return check_launch();
 }
 extern "C" int t4k_mlp_head_bwd(float *P, const float *T, float *Ylin, float *X2, const float *F1, float *Y1, const float *W,
@@ -299,7 +302,7 @@ extern "C" int t4k_mlp_head_bwd(float *P, const float *T, float *Ylin, float *X2
     HeadB p{P, T, Ylin, X2, F1, Y1, W, dW, dB, dB1, N, E0, E1, train};
     #define HEADB(KM_) { static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_head_bwd<KM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
                                                                  cudaFuncSetAttribute(k_head_bwd<KM_>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); attr = true; } \
-                         k_head_bwd<KM_><<<HB_CTAS, T4K_THREADS, smem, STRM(s)>>>(p); }
+                         launch_pdl(k_head_bwd<KM_>, dim3(HB_CTAS), dim3(T4K_THREADS), smem, STRM(s), p); }
     if (E0 <= 8) HEADB(8) else if (E0 <= 16) HEADB(16) else HEADB(32)
     return check_launch();
 }

@@ -57,6 +57,7 @@ k_reduce(const float *__restrict__ A, const float *__restrict__ B, float p0, con
          int64_t n, float *slot, float *out, int fin, float fa, float fb) {
     __shared__ float sm32[32];
     __shared__ bool  last;
+    pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
     if (p0_dev) p0 = *p0_dev;
@@ -107,8 +108,8 @@ static int launch_reduce(const float *A, const float *B, float p0, const float *
     const bool vec = aligned16(A) && (!TWO || aligned16(B));
     int g = stream_grid(n, vec ? 8 : 2);
     if (g > RMAX_BLOCKS) g = RMAX_BLOCKS;
-    if (vec) k_reduce<KIND, TWO, true ><<<g, T4K_THREADS, 0, st>>>(A, B, p0, p0_dev, n, slot, out, fin, fa, fb);
-    else     k_reduce<KIND, TWO, false><<<g, T4K_THREADS, 0, st>>>(A, B, p0, p0_dev, n, slot, out, fin, fa, fb);
+    if (vec) launch_pdl(k_reduce<KIND, TWO, true >, dim3(g), dim3(T4K_THREADS), 0, st, A, B, p0, p0_dev, n, slot, out, fin, fa, fb);
+    else     launch_pdl(k_reduce<KIND, TWO, false>, dim3(g), dim3(T4K_THREADS), 0, st, A, B, p0, p0_dev, n, slot, out, fin, fa, fb);
     return check_launch();
 }
 

@@ -2,10 +2,12 @@
 #include "common.cuh"
 #include <mutex>
 #include <cstdio>
+#include <cstdlib>
 
 namespace t4k {
 
 long g_launches = 0;
+int  g_pdl = []{ const char *e = getenv("T4K_PDL"); return (e && e[0] == '1') ? 1 : 0; }();   // opt-in: no net gain measured on the MNIST step (common.cuh)
 
 int sm_count() {
     static int n = 0;
@@ -101,5 +103,7 @@ int t4k_sm_count(void) { return t4k::sm_count(); }
 int t4k_sync(t4k_stream_t s) { return (int)cudaStreamSynchronize((cudaStream_t)s); }
 
 long t4k_launch_count(void) { return t4k::g_launches; }
+
+int t4k_set_pdl(int on) { int was = t4k::g_pdl; t4k::g_pdl = on ? 1 : 0; return was; }
 
 } // extern "C"

@@ -30,6 +30,7 @@ PROTOTYPES = {
     "t4k_sm_count": (_i, []),
     "t4k_sync": (_i, [_p]),
     "t4k_launch_count": (C.c_long, []),
+    "t4k_set_pdl": (_i, [_i]),
     "t4k_map": (_i, [_i, _p, _f, _l, _p]),
     "t4k_ts_op": (_i, [_i, _p, _f, _p, _l, _p]),
     "t4k_tt_op": (_i, [_i, _p, _p, _p, _l, _i, _i, _p]),
@@ -77,7 +78,8 @@ PROTOTYPES = {
     "t4k_comm_status": (_i, [_p]),
     "t4k_comm_capacity": (_l, [_p]),
     "t4k_allreduce_sum": (_i, [_p, _p, _l, _p]),
-    "t4k_optim_multi_dp": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _l, _f, _f, _f, _f, _p, _i, _p]),
+    "t4k_optim_multi_dp": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _l, _f, _f, _f, _f, _p, _i, _l, _p]),
+    "t4k_dp_push": (_l, [_p, _p, _l, _l, _p]),
     "t4k_rand_seed": (_i, [_u64]),
     "t4k_rand": (_i, [_p, _l, _i, _f, _f, _p]),
     "t4k_rand_at": (_i, [_p, _l, _i, _f, _f, _u64, _u64, _p]),

@@ -68,7 +68,10 @@ def warm(L):
     seg = seg_table([(0, 4096, 1)])
     for kind in (0, 1, 2):
         g, dg, m, v = (torch.ones(4096, device="cuda") for _ in range(4))
-        ok(L.t4k_optim_multi_dp(r1.h[0], kind, ptr(g), ptr(dg), ptr(m), ptr(v), ptr(seg), 1, 4096, 1e-3, 0.9, 0.999, 0.0, None, 0, r1.st(0)))
+        ok(L.t4k_optim_multi_dp(r1.h[0], kind, ptr(g), ptr(dg), ptr(m), ptr(v), ptr(seg), 1, 4096, 1e-3, 0.9, 0.999, 0.0, None, 0, 0, r1.st(0)))
+    dg = torch.ones(4096, device="cuda")
+    assert L.t4k_dp_push(r1.h[0], ptr(dg), 8, 4096, r1.st(0)) >= 0
+    ok(L.t4k_optim_multi_dp(r1.h[0], 1, ptr(g), ptr(dg), ptr(m), ptr(v), ptr(seg), 1, 4096, 1e-3, 0.9, 0.999, 0.0, None, 0, 0, r1.st(0)))
     r1.sync()
     assert torch.equal(b, torch.ones_like(b))           # world=1: the sum over ranks is the identity
     r1.close()
@@ -102,9 +105,12 @@ def test_allreduce_sum_mixed_lengths(world):
     ring.close()
 
 
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("world,big", [(4, 48000), (2, 196000)])
 @pytest.mark.parametrize("kind", [0, 1, 2])
-def test_fused_exchange_optimizer_equals_optimizer_on_summed_gradient(kind, world, big):
+def test_fused_exchange_optimizer_equals_optimizer_on_summed_gradient(kind, world, big, split):
+    """split: the exchange in two launches — t4k_dp_push of everything past the first parameter layer's segments (what
+    Model::step_graph forks onto a side stream while the first layer's backward still runs), then the fused kernel"""
     L = lib()
     warm(L)
     segs = [(0, 92, 1), (92, 12, 1), (104, big, 1), (big + 104, 100, 1), (big + 204, 1000, 3), (big + 1204, 12, 1)]
@@ -125,9 +131,14 @@ def test_fused_exchange_optimizer_equals_optimizer_on_summed_gradient(kind, worl
         DGr = ranked_sum(DG)
         ok(L.t4k_optim_multi(kind, ptr(Gr), ptr(DGr), ptr(Mr), ptr(Vr), ptr(seg), len(segs), total, lr, b1, b2, wd, st0), "optim_multi")
         torch.cuda.synchronize()
+        pushed = [0] * world
+        if split:
+            for r in range(world):
+                pushed[r] = L.t4k_dp_push(ring.h[r], ptr(DG[r]), 104, total, ring.st(r))
+                assert 104 <= pushed[r] < total, pushed[r]
         for r in range(world):
             ok(L.t4k_optim_multi_dp(ring.h[r], kind, ptr(G[r]), ptr(DG[r]), ptr(M[r]), ptr(V[r]), ptr(seg), len(segs), total,
-                                    lr, b1, b2, wd, ptr(scal[r]), 3, ring.st(r)), "optim_multi_dp")
+                                    lr, b1, b2, wd, ptr(scal[r]), 3, pushed[r], ring.st(r)), "optim_multi_dp")
         ring.sync()
         for r in range(world):
             assert torch.equal(G[r], Gr), "G step %d rank %d" % (step, r)
