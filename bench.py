@@ -213,9 +213,11 @@ def main():
     L.t4k_rand_seed(1234)
     m = th.mnist_cnn(BATCH)
     rng = np.random.default_rng(100 + rank)
-    xh = torch.from_numpy((rng.random((BATCH, 28, 28, 1), dtype=np.float32) * 2 - 1).astype(np.float32)).pin_memory()
+    x8 = torch.from_numpy(rng.integers(0, 256, (BATCH, 28, 28, 1), dtype=np.uint8)).pin_memory()          # what an MNIST loader holds: U8 pixels
+    xh = torch.from_numpy(((x8.numpy().astype(np.float32) - 128.0) * np.float32(1.0 / 128.0)).astype(np.float32)).pin_memory()   # `128 128 normalize` (t4_40b.4th:52)
     proj = np.random.default_rng(7).standard_normal((784, 10)).astype(np.float32)    # learnable synthetic labels: argmax of a fixed
     lab = (xh.numpy().reshape(BATCH, 784) @ proj).argmax(1)                           # random projection of the image (same rule on every rank)
+    y8 = torch.from_numpy(lab.astype(np.uint8)).pin_memory()
     yh = torch.from_numpy(np.eye(10, dtype=np.float32)[lab]).pin_memory()
     X, Y = th.Tensor.tensor(BATCH, 28, 28, 1), th.Tensor.tensor(BATCH, 1, 10, 1)
     H.t4h_tensor_h2d(X.h, C.c_void_p(xh.data_ptr()), xh.numel()); H.t4h_tensor_h2d(Y.h, C.c_void_p(yh.data_ptr()), yh.numel())
@@ -292,39 +294,35 @@ def main():
             barrier()
     value = BATCH * world * args.steps / (ms / 1e3)
 
-    # ---- e2e through the public host API: EVERY step's batch comes from pinned host memory and every step's loss is
-    # read back on the host.  Pipelined like any input feeder: the H2D of step i+1 (copy stream, double-buffered
-    # staging) overlaps the compute of step i; the loss of step i is read on the host while step i+1 runs.
-    dev = torch.device("cuda", local)
-    copy_stream = torch.cuda.Stream(device=dev)
-    xs = [torch.empty(BATCH, 28, 28, 1, device=dev) for _ in range(2)]
-    ys = [torch.empty(BATCH, 10, device=dev) for _ in range(2)]
-    Xv = t4dp.device_view(X.data_ptr, xh.numel(), dev).view(BATCH, 28, 28, 1)
-    Yv = t4dp.device_view(Y.data_ptr, yh.numel(), dev).view(BATCH, 10)
+    # ---- e2e through the public host API, the way a training loop over a dataset runs (`ds for forward loss.ce backprop nn.adam next`):
+    # EVERY step's mini-batch starts in pinned host memory as the U8 pixels + U8 labels a loader holds, and every step's loss is
+    # read back on the host.  Dataset.stage() copies the bytes asynchronously (copy stream, double buffered: batch i+1 travels
+    # while batch i trains); step_graph_ds() normalises them on the device (t4k_dataset_load), one-hots the labels and replays the
+    # captured step; the loss of step i is read on the host while step i+1 runs.
+    ds = th.Dataset(BATCH, 28, 28, 1).normalize(128.0, 128.0)
     lh = [torch.zeros(1).pin_memory() for _ in range(2)]
-    staged = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
     lready = [torch.cuda.Event() for _ in range(2)]
     losses_seen = []
 
-    def stage(i):                                              # H2D of step i's batch into staging buffer i%2
-        b = i & 1
-        with torch.cuda.stream(copy_stream):
-            if i >= 2:
-                copy_stream.wait_event(consumed[b])
-            xs[b].copy_(xh, non_blocking=True); ys[b].copy_(yh, non_blocking=True)
-            staged[b].record(copy_stream)
-
     def e2e_run(nsteps):
-        stage(0)
-        for i in range(nsteps):
+        ds.stage(x8, y8)
+        if world == 1 or fused:
+            # one host call per iteration: Model::train_step = commit (normalise + one-hot, 1 launch) + the captured step + async loss
+            # D2H into pinned memory; it hands back the previous iteration's loss (read-back pipelined by one step)
+            for i in range(nsteps):
+                if i + 1 < nsteps:
+                    ds.stage(x8, y8)
+                prev = m.train_step_ds(ds, t4.LOSS_CE, lossp, optimizer=2, lr=LR)
+                if i >= 1:
+                    losses_seen.append(prev)
+            losses_seen.append(m.train_flush())
+            return
+        for i in range(nsteps):                                   # NCCL arm
             b = i & 1
             if i + 1 < nsteps:
-                stage(i + 1)
-            lib_stream.wait_event(staged[b])
-            Xv.copy_(xs[b], non_blocking=True); Yv.copy_(ys[b], non_blocking=True)     # D2D on the library stream
-            consumed[b].record(lib_stream)
-            step()
+                ds.stage(x8, y8)
+            t4.check(m.step_graph_ds(ds, t4.LOSS_CE, lossp, optimizer=-1, lr=LR), "step_graph_ds")
+            dpm.allreduce_grads(); m.adam(LR)
             lh[b].copy_(loss_dev[:1], non_blocking=True); lready[b].record(lib_stream)
             if i >= 1:
                 lready[b ^ 1].synchronize(); losses_seen.append(float(lh[b ^ 1][0]))  # step i-1's loss, on the host
@@ -342,8 +340,9 @@ def main():
     if world > 1:
         t = torch.tensor([ms_e2e], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_e2e = float(t.cpu()[0])
     e2e = {"value": BATCH * world * args.steps / (ms_e2e / 1e3), "unit": "samples/s",
-           "h2d_bytes_per_step": int(xh.numel() * 4 + yh.numel() * 4), "d2h_bytes_per_step": 4,
-           "note": "pinned host batch -> H2D (copy stream, double buffered) -> D2D into the model input -> step -> loss D2H read on the host, every step"}
+           "h2d_bytes_per_step": int(x8.numel() + y8.numel()), "d2h_bytes_per_step": 4,
+           "note": "per step: U8 pixels + U8 labels from pinned host memory -> async H2D (copy stream, double buffered) -> on-device normalise "
+                   "(u8-128)/128 + one-hot (1 launch) -> train step -> loss D2H read on the host (pipelined by one step); one host call per iteration"}
 
     if fused:
         stt = dpm.comm.status()

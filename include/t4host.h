@@ -73,6 +73,26 @@ int   t4h_model_forward(t4h_model m, t4h_tensor input);              /* `forward
 int   t4h_model_backprop(t4h_model m, t4h_tensor tgt);               /* `backprop` (tgt NULL → cached one-hot) */
 float t4h_model_loss(t4h_model m, int loss_op, t4h_tensor tgt);      /* `loss.mse|bce|ce|nll` (syncs) */
 int   t4h_model_loss_async(t4h_model m, int loss_op, t4h_tensor tgt, float *loss_dev);
+/* ---- Dataset (src/mu/dataset.h, dataset.cu): mini-batch feeding.  The loader side (file parsing, src/ld) stays with the
+ * caller; what it would hand to Dataset::_load — the raw U8 image block and U8 labels of a mini-batch — goes to
+ * t4h_dataset_stage (async H2D of the BYTES on a copy stream, double buffered: stage batch i+1 while batch i trains);
+ * t4h_dataset_commit normalises on the device into the dataset's tensor ((u8 - mean) * (1/scale), dataset.cu:142). */
+typedef void *t4h_dataset;
+t4h_dataset t4h_dataset_create(int n, int h, int w, int c);
+void  t4h_dataset_destroy(t4h_dataset d);
+void  t4h_dataset_normalize(t4h_dataset d, float mean, float scale);          /* word `normalize` ( DS mean scale -- DS' ) */
+int   t4h_dataset_stage(t4h_dataset d, const uint8_t *img_host, const uint8_t *lab_host, int n);
+int   t4h_dataset_commit(t4h_dataset d);
+t4h_tensor t4h_dataset_tensor(t4h_dataset d);                                 /* the dataset as the Tensor it is */
+const int32_t *t4h_dataset_labels(t4h_dataset d);                             /* device int32 labels of the committed batch */
+int   t4h_model_forward_ds(t4h_model m, t4h_dataset d);                       /* Model::forward(Dataset&): + onehot + hit (forward.cu:72-75) */
+/* one iteration of `ds for forward loss backprop nn.adam next`: commit + one-hot + the captured train step */
+int   t4h_model_step_graph_ds(t4h_model m, t4h_dataset d, int loss_op, float *loss_dev, int optimizer, float lr, float b1, float b2, float wd);
+/* the same with the loss read-back pipelined by one step: this step's loss goes to pinned host memory asynchronously,
+ * *prev_loss receives the PREVIOUS call's loss (NaN on the first call); t4h_model_train_flush waits for the last one.
+ * One host call per training iteration: nothing else touches the GPU queue. */
+int   t4h_model_train_step_ds(t4h_model m, t4h_dataset d, int loss_op, float *loss_dev, int optimizer, float lr, float b1, float b2, float wd, float *prev_loss);
+int   t4h_model_train_flush(t4h_model m, float *last_loss);
 int   t4h_model_onehot_labels(t4h_model m, const int32_t *labels_dev);   /* Model::onehot(Dataset&) on device */
 int   t4h_model_onehot_set(t4h_model m, t4h_tensor hot);             /* `nn.onehot=` */
 int   t4h_model_hit(t4h_model m, int recalc);                        /* `nn.hit` */

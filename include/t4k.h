@@ -246,6 +246,15 @@ int t4k_rand_seed(uint64_t seed);
 int t4k_rand(float *d, int64_t n, int opt, float bias, float scale, t4k_stream_t s);
 int t4k_rand_at(float *d, int64_t n, int opt, float bias, float scale, uint64_t seed, uint64_t offset, t4k_stream_t s);
 
+/* ---- dataset feeding: Dataset::_load (src/mu/dataset.cu:124-152), SURVEY.md §8f row 2 -------------------
+ * The reference converts each mini-batch on the host (one float per U8 pixel, then an H2D of 4 bytes per pixel).
+ * Here the U8 block is what crosses PCIe; the device does dst[i] = ((float)src[i] - mean) * scale (two roundings,
+ * bit-equal to the host loop), widens the U8 labels to int32 and — when `hot` is given — writes their one-hot rows
+ * [nlab, E] (Model::onehot(Dataset&), src/nn/loss.cpp:47-72: label >= E -> class 0), all in one launch.
+ * mean/scale as Dataset::normalize stores them (scale = 1/given, default mean 0, scale 1/256: dataset.h:35-36). */
+int t4k_dataset_load(const uint8_t *src_u8, float *dst, int64_t n, float mean, float scale,
+                     const uint8_t *label_u8, int32_t *label_i32, int nlab, float *hot, int E, t4k_stream_t s);
+
 /* ---- loss-side host loops moved on device: src/nn/loss.cpp:47-107 ---------------------- */
 /* Model::onehot(Dataset&): hot[n, label<E ? label : 0] = 1, everything else 0; labels are device int32 */
 int t4k_onehot(const int32_t *label, float *hot, int N, int E, t4k_stream_t s);

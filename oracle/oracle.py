@@ -273,6 +273,18 @@ def onehot(labels, E):
     return hot
 
 
+def dataset_normalize(mean, scale):
+    """Dataset::normalize (src/mu/dataset.cu:33-41): stores (mean, 1/scale); scale == 0 -> error, 1.0"""
+    return np.float32(mean), (np.float32(1.0) if abs(scale) < 1e-6 else np.float32(1.0) / np.float32(scale))
+
+
+def dataset_load(u8, mean=0.0, scale=1.0 / 256.0):
+    """Dataset::_load (src/mu/dataset.cu:139-143): d[i] = (I2D((int)u8[i]) - _mean) * _scale, two FP32 roundings.
+    `mean`/`scale` are the STORED values (dataset.h:35-36 defaults: 0, 1/256; see dataset_normalize)."""
+    x = np.ascontiguousarray(u8, dtype=np.uint8).astype(np.int32).astype(np.float32)
+    return ((x - np.float32(mean)).astype(np.float32) * np.float32(scale)).astype(np.float32)
+
+
 def hit(out, hot):
     out, hot = f32(out), f32(hot)
     N = out.shape[0]

@@ -170,6 +170,74 @@ U32 Tensor::has_nan() {
 int Tensor::h2d(const DU *h, U64 n) { return (int)cudaMemcpyAsync(data, h, sizeof(DU) * (n ? n : numel), cudaMemcpyHostToDevice, (cudaStream_t)ST); }
 int Tensor::d2h(DU *h, U64 n) { cudaMemcpyAsync(h, data, sizeof(DU) * (n ? n : numel), cudaMemcpyDeviceToHost, (cudaStream_t)ST); return Runtime::sync(); }
 
+// =============================================================================== Dataset
+static cudaStream_t g_copy = nullptr;                                     // H2D feeder stream
+Dataset &Dataset::create(U32 n, U32 h, U32 w, U32 c) {
+    Dataset *d = new Dataset();
+    const U64 sz = (U64)n * h * w * c;
+    d->reset(Runtime::alloc((sz + 4) * sizeof(DU)), sz);
+    d->reshape(n, h, w, c);
+    d->label = (int32_t*)Runtime::alloc(((size_t)n + 4) * sizeof(int32_t));
+    if (!g_copy) cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking);
+    for (int b = 0; b < 2; b++) {
+        d->_simg[b] = (uint8_t*)Runtime::alloc(sz + 16); d->_slab[b] = (uint8_t*)Runtime::alloc((size_t)n + 16);
+        cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); d->_staged[b] = e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming); d->_consumed[b] = e;
+    }
+    cudaMemsetAsync(d->data, 0, sz * sizeof(DU), (cudaStream_t)ST);
+    cudaMemsetAsync(d->label, 0, (size_t)n * sizeof(int32_t), (cudaStream_t)ST);
+    Runtime::sync();                                                       // staging buffers come from the library stream's pool
+    return *d;
+}
+void Dataset::destroy(Dataset &d) {
+    Runtime::sync(); if (g_copy) cudaStreamSynchronize(g_copy);
+    for (int b = 0; b < 2; b++) { Runtime::free(d._simg[b]); Runtime::free(d._slab[b]); cudaEventDestroy((cudaEvent_t)d._staged[b]); cudaEventDestroy((cudaEvent_t)d._consumed[b]); }
+    Runtime::free(d.label); Runtime::free(d.data);
+    delete &d;
+}
+void Dataset::normalize(DU mean, DU scale) {                               // dataset.cu:33-41
+    _mean = mean;
+    if (fabsf(scale) < DU_EPS_H) { Runtime::error("scale == 0?\n"); _scale = 1.0f; }
+    else _scale = 1.0f / scale;
+}
+int Dataset::stage(const uint8_t *img_host, const uint8_t *lab_host, int n) {
+    if (!img_host || !lab_host || n < 1 || n > (int)N()) { Runtime::error("dataset#stage n=%d of %d\n", n, (int)N()); return T4K_EINVAL; }
+    if (_head - _tail >= 2) { Runtime::error("dataset#stage: two batches already staged, commit one first\n"); return T4K_EINVAL; }
+    const int b = _head & 1;
+    if (_head >= 2) cudaStreamWaitEvent(g_copy, (cudaEvent_t)_consumed[b], 0);          // the batch that used this buffer has been normalised
+    cudaMemcpyAsync(_simg[b], img_host, (size_t)n * HWC(), cudaMemcpyHostToDevice, g_copy);
+    cudaMemcpyAsync(_slab[b], lab_host, (size_t)n, cudaMemcpyHostToDevice, g_copy);
+    cudaEventRecord((cudaEvent_t)_staged[b], g_copy);
+    _sn[b] = n; _head++;
+    return 0;
+}
+int Dataset::commit_begin(const uint8_t **simg, const uint8_t **slab, int *n) {
+    if (_head == _tail) { Runtime::error("dataset#commit: nothing staged\n"); return T4K_EINVAL; }
+    const int b = _tail & 1;
+    cudaStreamWaitEvent((cudaStream_t)ST, (cudaEvent_t)_staged[b], 0);
+    *simg = _simg[b]; *slab = _slab[b]; *n = _sn[b];
+    return 0;
+}
+int Dataset::commit_launch(const uint8_t *simg, const uint8_t *slab, int n, DU *hot, int E) {
+    // partial batch: the tail keeps the previous values, as _load does
+    const int rc = t4k_dataset_load(simg, data, (int64_t)n * HWC(), _mean, _scale, slab, label, n, hot, E, ST);
+    KCHK(rc);
+    return rc;
+}
+void Dataset::commit_end() {
+    const int b = _tail & 1;
+    cudaEventRecord((cudaEvent_t)_consumed[b], (cudaStream_t)ST);
+    batch_sz = _sn[b]; _tail++; batch_id++;
+}
+int Dataset::commit(DU *hot, int E) {
+    const uint8_t *si, *sl; int n;
+    int rc = commit_begin(&si, &sl, &n);
+    if (rc) return rc;
+    rc = commit_launch(si, sl, n, hot, E);
+    commit_end();
+    return rc;
+}
+
 // =============================================================================== Model
 Model::Model(U32 n, U32 h, U32 w, U32 c) { _layers.push_back(&Tensor::create(n, h, w, c)); }
 Model::~Model() {
@@ -180,7 +248,8 @@ Model::~Model() {
     }
     if (_own_hot && _hot) Tensor::destroy(*_hot);
     Runtime::free(_G); Runtime::free(_DG); Runtime::free(_M); Runtime::free(_V); Runtime::free(_seg_dev); Runtime::free(_cnt_dev);
-    if (_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)_graph_exec);
+    _drop_graphs();
+    if (_loss_pin) { cudaFreeHost(_loss_pin); for (int b = 0; b < 2; b++) cudaEventDestroy((cudaEvent_t)_loss_ev[b]); }
 }
 Tensor &Model::operator[](S32 i) { return *_layers[(i < 0) ? (S32)_layers.size() + i : i]; }     // model.cpp:47-49
 int Model::batch_size() { return _layers.empty() ? 1 : (int)_layers[0]->N(); }
@@ -516,6 +585,57 @@ Tensor &Model::onehot(Tensor &t) {                                        // los
     _hit = hit(true);
     return *_hot;
 }
+Model &Model::forward(Dataset &ds) {                                      // forward.cu:29-78: a Dataset input also refreshes onehot and hit (:72-75)
+    forward((Tensor&)ds);
+    onehot_labels(ds.label);
+    Tensor &out = (*this)[-1];
+    if (!_cnt_dev) _cnt_dev = (int*)Runtime::alloc(256);
+    KCHK(t4k_hit(out.data, _hot->data, out.N(), (int)out.HWC(), _cnt_dev, ST));       // stays on the device until `nn.hit` asks
+    _hit_dev = true;
+    return *this;
+}
+int Model::step_graph(Dataset &ds, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd) {
+    // one iteration of `ds for forward loss.ce backprop nn.adam next` (the loop fetches the next mini-batch, src/vm/eforth.cpp:614-634):
+    // normalise the staged U8 batch into the dataset tensor + one-hot its labels (one launch, inside the captured step), then the step
+    Tensor &out = (*this)[-1];
+    if (!_hot) { _hot = &Tensor::create(out.N(), 1, (U32)out.HWC(), 1); _own_hot = true; _hot->zeros(); }
+    StepExtra x; x.ds = &ds;
+    int rc = ds.commit_begin(&x.simg, &x.slab, &x.n);
+    if (rc) return rc;
+    rc = _step_graph((Tensor&)ds, *_hot, lop, loss_dev, op, lr, b1, b2, wd, x);
+    ds.commit_end();
+    return rc;
+}
+int Model::train_step(Dataset &ds, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd, DU *prev_loss) {
+    if (!loss_dev) return T4K_EINVAL;
+    if (!_loss_pin) {
+        if (cudaHostAlloc((void**)&_loss_pin, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return T4K_ENOMEM; }
+        for (int b = 0; b < 2; b++) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); _loss_ev[b] = e; }
+    }
+    Tensor &out = (*this)[-1];
+    if (!_hot) { _hot = &Tensor::create(out.N(), 1, (U32)out.HWC(), 1); _own_hot = true; _hot->zeros(); }
+    const unsigned b = _tstep & 1;
+    StepExtra x; x.ds = &ds; x.loss_pin = &_loss_pin[b];                  // the loss D2H rides in the captured step too
+    int rc = ds.commit_begin(&x.simg, &x.slab, &x.n);
+    if (rc) return rc;
+    rc = _step_graph((Tensor&)ds, *_hot, lop, loss_dev, op, lr, b1, b2, wd, x);
+    ds.commit_end();
+    if (rc) return rc;
+    cudaEventRecord((cudaEvent_t)_loss_ev[b], (cudaStream_t)ST);
+    if (prev_loss) {
+        if (_tstep >= 1) { cudaEventSynchronize((cudaEvent_t)_loss_ev[b ^ 1]); *prev_loss = _loss_pin[b ^ 1]; }
+        else *prev_loss = NAN;
+    }
+    _tstep++;
+    return 0;
+}
+int Model::train_flush(DU *last_loss) {
+    if (!_tstep || !_loss_pin) return T4K_EINVAL;
+    const unsigned b = (_tstep - 1) & 1;
+    cudaError_t e = cudaEventSynchronize((cudaEvent_t)_loss_ev[b]);
+    if (last_loss) *last_loss = _loss_pin[b];
+    return (int)e;
+}
 Tensor &Model::onehot_labels(const int32_t *labels_dev) {                 // loss.cpp:47-72, on device
     Tensor &out = (*this)[-1];
     if (!_hot) { _hot = &Tensor::create(out.N(), 1, (U32)out.HWC(), 1); _own_hot = true; }
@@ -523,6 +643,10 @@ Tensor &Model::onehot_labels(const int32_t *labels_dev) {                 // los
     return *_hot;
 }
 int Model::hit(bool recalc) {                                             // loss.cpp:75-107
+    if (!recalc && _hit_dev) {                                            // counted on the device by forward(Dataset&)
+        int cnt = 0; cudaMemcpyAsync(&cnt, _cnt_dev, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)ST); Runtime::sync();
+        _hit_dev = false; return _hit = cnt;
+    }
     if (!recalc) return _hit;
     if (!_hot) return 0;
     Tensor &out = (*this)[-1];
@@ -617,30 +741,55 @@ int Model::dp_attach(void *comm, DU *scal, int nscal) {
     if (!_G) grad_alloc(OPTI_ADAM);
     if (comm && (!_G || t4k_comm_capacity((t4k_comm_t)comm) < (int64_t)_total || nscal < 0 || nscal > 64)) return T4K_EINVAL;
     _comm = comm; _dp_scal = scal; _dp_nscal = comm ? nscal : 0;
-    if (_graph_exec) { Runtime::sync(); cudaGraphExecDestroy((cudaGraphExec_t)_graph_exec); _graph_exec = nullptr; }   // the captured optimizer node changes
+    Runtime::sync(); _drop_graphs();                          // the captured optimizer node changes
     return 0;
 }
 // ---- one train step as a CUDA graph: forward + loss + backprop + optimizer
 int Model::step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd) {
+    return _step_graph(input, tgt, lop, loss_dev, op, lr, b1, b2, wd, StepExtra());
+}
+void Model::_drop_graphs() {
+    for (auto &g : _graphs) if (g.exec) { cudaGraphExecDestroy((cudaGraphExec_t)g.exec); g.exec = nullptr; }
+}
+int Model::_step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd, const StepExtra &x) {
     auto run = [&]() {
+        if (x.ds) x.ds->commit_launch(x.simg, x.slab, x.n, tgt.data, (int)(*this)[-1].HWC());   // dataset feeding: normalise + one-hot
         forward(input);
         if (loss_dev) loss_async(lop, tgt, loss_dev);
+        // loss read-back: the 4-byte D2H takes the copy engine ~6 us — on a branch of its own (side stream) it overlaps backprop
+        // instead of delaying the next step.  With a communicator attached the loss is only final after the exchange (the ranks'
+        // loss sums ride in it), so there it stays at the end of the step.
+        const bool early_loss = x.loss_pin && loss_dev && !_comm;
+        if (early_loss) {
+            cudaEventRecord(g_fork, (cudaStream_t)ST); cudaStreamWaitEvent(g_stream2, g_fork, 0);
+            cudaMemcpyAsync(x.loss_pin, loss_dev, sizeof(DU), cudaMemcpyDeviceToHost, g_stream2);
+            cudaEventRecord(g_join, g_stream2);
+        }
         _dp_early = _comm && (int)op >= 0 && train && _G;  // forward -> backprop -> optimizer is one unit here: the exchange may start early
         backprop(tgt);
         _dp_early = false;
-        if ((int)op < 0) return;                          // data parallel: the caller all-reduces DG, then calls the optimizer
-        switch (op) { case OPTI_SGD: case OPTI_SGDM: sgd(lr, b1); break; case OPTI_ADAM: adam(lr, b1, b2); break; default: adamw(lr, wd, b1, b2); }
+        if ((int)op >= 0) {                                // op < 0 — data parallel over NCCL: the caller all-reduces DG, then calls the optimizer
+            switch (op) { case OPTI_SGD: case OPTI_SGDM: sgd(lr, b1); break; case OPTI_ADAM: adam(lr, b1, b2); break; default: adamw(lr, wd, b1, b2); }
+        }
+        if (early_loss) cudaStreamWaitEvent((cudaStream_t)ST, g_join, 0);
+        else if (x.loss_pin && loss_dev) cudaMemcpyAsync(x.loss_pin, loss_dev, sizeof(DU), cudaMemcpyDeviceToHost, (cudaStream_t)ST);
     };
     bool has_dropout = false;
     for (Tensor *t : _layers) if (t->grad_fn == T4K_L_DROPOUT) has_dropout = true;
-    U64 key[8]; float f4[4] = {lr, b1, b2, wd};
+    U64 key[12] = {0}; float f4[4] = {lr, b1, b2, wd};
     key[0] = (U64)input.data; key[1] = (U64)tgt.data; key[2] = (U64)lop; key[3] = (U64)loss_dev; key[4] = (U64)op;
-    memcpy(&key[5], f4, 16); key[7] = (U64)train;
+    memcpy(&key[5], f4, 16); key[7] = (U64)train; key[8] = (U64)x.simg; key[9] = (U64)x.slab; key[10] = (U64)x.n; key[11] = (U64)x.loss_pin;
     // SGD's first call forces momentum 0 (host state) and the first optimizer call builds the arenas: run those eagerly
     if (has_dropout || !_G || (_iter == 0 && (int)op >= 0)) { run(); return 0; }
     cudaStream_t st = (cudaStream_t)ST;
-    if (!_graph_exec || memcmp(key, _graph_key, sizeof(key)) != 0) {
-        if (_graph_exec) { cudaGraphExecDestroy((cudaGraphExec_t)_graph_exec); _graph_exec = nullptr; }
+    StepGraph *slot = nullptr, *lru = nullptr;        // cached graph for this key, else an empty slot, else the least recently used
+    for (auto &g : _graphs) {
+        if (g.exec && memcmp(key, g.key, sizeof(key)) == 0) { slot = &g; break; }
+        if (!lru || (!g.exec && lru->exec) || (!!g.exec == !!lru->exec && g.used < lru->used)) lru = &g;
+    }
+    if (!slot) {
+        slot = lru;
+        if (slot->exec) { cudaGraphExecDestroy((cudaGraphExec_t)slot->exec); slot->exec = nullptr; }
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); run(); return 0; }
         const int it = _iter;
@@ -651,11 +800,12 @@ int Model::step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_
         e = cudaGraphInstantiate(&ex, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) { cudaGetLastError(); _iter = it; run(); return 0; }
-        _graph_exec = ex; memcpy(_graph_key, key, sizeof(key));
+        slot->exec = ex; memcpy(slot->key, key, sizeof(key));
         _iter = it;                                   // the captured run did not execute; the launch below is the step
     }
+    slot->used = ++_graph_clock;
     if ((int)op >= 0) _iter++;
-    return (int)cudaGraphLaunch((cudaGraphExec_t)_graph_exec, st);
+    return (int)cudaGraphLaunch((cudaGraphExec_t)slot->exec, st);
 }
 
 } // namespace t4
@@ -771,6 +921,21 @@ int   t4h_model_backprop(t4h_model m, t4h_tensor tgt) {
 }
 float t4h_model_loss(t4h_model m, int op, t4h_tensor tgt) { return tgt ? MM(m).loss((t4_loss)op, TT(tgt)) : MM(m).loss((t4_loss)op); }
 int   t4h_model_loss_async(t4h_model m, int op, t4h_tensor tgt, float *loss_dev) { return MM(m).loss_async((t4_loss)op, TT(tgt), loss_dev); }
+t4h_dataset t4h_dataset_create(int n, int h, int w, int c) { return (t4h_dataset)&Dataset::create(n, h, w, c); }
+void  t4h_dataset_destroy(t4h_dataset d) { if (d) Dataset::destroy(*(Dataset*)d); }
+void  t4h_dataset_normalize(t4h_dataset d, float mean, float scale) { ((Dataset*)d)->normalize(mean, scale); }
+int   t4h_dataset_stage(t4h_dataset d, const uint8_t *img_host, const uint8_t *lab_host, int n) { return ((Dataset*)d)->stage(img_host, lab_host, n); }
+int   t4h_dataset_commit(t4h_dataset d) { return ((Dataset*)d)->commit(); }
+t4h_tensor t4h_dataset_tensor(t4h_dataset d) { return (t4h_tensor)(Tensor*)(Dataset*)d; }
+const int32_t *t4h_dataset_labels(t4h_dataset d) { return ((Dataset*)d)->label; }
+int   t4h_model_forward_ds(t4h_model m, t4h_dataset d) { MM(m).forward(*(Dataset*)d); return 0; }
+int   t4h_model_step_graph_ds(t4h_model m, t4h_dataset d, int lop, float *loss_dev, int optimizer, float lr, float b1, float b2, float wd) {
+    return MM(m).step_graph(*(Dataset*)d, (t4_loss)lop, loss_dev, (t4_optimizer)optimizer, lr, b1, b2, wd);
+}
+int   t4h_model_train_step_ds(t4h_model m, t4h_dataset d, int lop, float *loss_dev, int optimizer, float lr, float b1, float b2, float wd, float *prev_loss) {
+    return MM(m).train_step(*(Dataset*)d, (t4_loss)lop, loss_dev, (t4_optimizer)optimizer, lr, b1, b2, wd, prev_loss);
+}
+int   t4h_model_train_flush(t4h_model m, float *last_loss) { return MM(m).train_flush(last_loss); }
 int   t4h_model_onehot_labels(t4h_model m, const int32_t *labels_dev) { MM(m).onehot_labels(labels_dev); return 0; }
 int   t4h_model_onehot_set(t4h_model m, t4h_tensor hot) { MM(m).onehot(TT(hot)); return 0; }
 int   t4h_model_hit(t4h_model m, int recalc) { return MM(m).hit(recalc != 0); }

@@ -118,8 +118,33 @@ private:
     Tensor &_gemm(int engine, Tensor &A, Tensor &B, Tensor &O, DU alpha, DU beta, bool tA, bool tB, const char *nm);
 };
 
+// Dataset (src/mu/dataset.h:14-45): a Tensor whose data is refilled mini-batch by mini-batch, plus the batch's labels.
+// The reference converts U8 -> float on the host and copies floats (dataset.cu:124-152); here the U8 block crosses PCIe
+// (async, double-buffered staging, own copy stream) and t4k_dataset_load normalises on the device.  The Corpus/loader side
+// (file parsing, src/ld) stays with the caller: stage() takes the raw U8 image and label blocks it would hand to _load.
+struct Dataset : public Tensor {
+    int       batch_sz = 0, batch_id = 0;      ///< dataset.h:17-21
+    int32_t  *label = nullptr;                 ///< device int32 labels of the committed batch
+    DU        _mean = 0.0f, _scale = 1.0f / 256.0f;   ///< dataset.h:35-36
+    static Dataset &create(U32 n, U32 h, U32 w, U32 c);
+    static void     destroy(Dataset &d);
+    void normalize(DU mean, DU scale);         ///< dataset.cu:33-41
+    int  stage(const uint8_t *img_host, const uint8_t *lab_host, int n);   ///< async H2D of the next batch's U8 blocks
+    int  commit(DU *hot = nullptr, int E = 0); ///< library stream: wait for the oldest staged batch, normalise into data / label (+ one-hot rows [n,E])
+    // commit in three parts, for a caller that folds the normalise launch into its own CUDA graph (Model::step_graph):
+    int  commit_begin(const uint8_t **simg, const uint8_t **slab, int *n);     ///< stream-wait for the staged bytes; which staging buffers
+    int  commit_launch(const uint8_t *simg, const uint8_t *slab, int n, DU *hot, int E);   ///< the launch itself (capturable)
+    void commit_end();                                                          ///< mark the staging buffer consumed
+    friend class Model;
+private:
+    uint8_t *_simg[2] = {nullptr, nullptr}, *_slab[2] = {nullptr, nullptr};
+    void    *_staged[2] = {nullptr, nullptr}, *_consumed[2] = {nullptr, nullptr};
+    int      _sn[2] = {0, 0};
+    unsigned _head = 0, _tail = 0;             ///< staged batches: [_tail, _head)
+};
+
 class Model {
-    int     _hit  = 0;
+    int     _hit  = 0; bool _hit_dev = false;     ///< _hit_dev: the count of the last forward(Dataset&) is still on the device
     int     _iter = 0;
     Tensor *_hot  = nullptr;           ///< cached one-hot vector
     bool    _own_hot = false;
@@ -130,11 +155,16 @@ class Model {
     void   *_seg_dev = nullptr; int _nseg = 0;
     t4_optimizer _arena_opt = OPTI_SGD;
     // captured train step
-    void   *_graph_exec = nullptr; U64 _graph_key[8] = {0};
+    struct StepGraph { void *exec = nullptr; U64 key[12] = {0}; U64 used = 0; } _graphs[3];   // small LRU cache (dataset feeding alternates two staging buffers)
+    U64     _graph_clock = 0;
+    struct StepExtra { const uint8_t *simg = nullptr, *slab = nullptr; int n = 0; Dataset *ds = nullptr; DU *loss_pin = nullptr; };   // work folded into the captured step
+    int     _step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd, const StepExtra &x);
+    void    _drop_graphs();
     void   *_comm = nullptr; DU *_dp_scal = nullptr; int _dp_nscal = 0;   // data parallel: t4k_comm_t + scalars riding in the exchange
     int     _second_layer = 0; int64_t _first_end = 0;                    // arena layout: end of the first parameter layer's segments, index of the next parameter layer
     bool    _dp_early = false, _dp_join = false; int64_t _dp_pushed_from = -1;   // split exchange inside step_graph (early push on the side stream)
     void    _dp_push();
+    DU     *_loss_pin = nullptr; void *_loss_ev[2] = {nullptr, nullptr}; unsigned _tstep = 0;   // train_step read-back ring
     std::vector<Tensor*> _layers;      ///< layer i holds that layer's INPUT; last = output
 public:
     int  epoch    = 0;
@@ -158,6 +188,12 @@ public:
     Tensor &onehot();
     Tensor &onehot(Tensor &t);
     Tensor &onehot_labels(const int32_t *labels_dev);        ///< Model::onehot(Dataset&) with device labels
+    Model  &forward(Dataset &ds);                            ///< forward.cu:29-78 with a Dataset input: + onehot(ds) + hit (forward.cu:72-75), all on device
+    int     step_graph(Dataset &ds, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd);   ///< commit + onehot + train step
+    // the same, plus the loss read-back pipelined by one step: the loss of THIS step is copied to pinned host memory
+    // asynchronously, *prev_loss receives the loss of the PREVIOUS call (NaN on the first); train_flush waits for the last one
+    int     train_step(Dataset &ds, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd, DU *prev_loss);
+    int     train_flush(DU *last_loss);
     int     hit(bool recalc = true);
     DU      loss(t4_loss op);
     DU      loss(t4_loss op, Tensor &tgt);

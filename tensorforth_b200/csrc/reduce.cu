@@ -200,6 +200,40 @@ __global__ void __launch_bounds__(T4K_THREADS) k_hit(const float *__restrict__ o
     if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < T4K_THREADS / 32; w++) s += sm[w]; *cnt = s; }
 }
 
+// ------------------------------------------------------------------ Dataset::_load (src/mu/dataset.cu:124-152) on device
+// d[i] = ((float)(int)u8[i] - mean) * scale  — two roundings, as the host loop has them (no FMA contraction);
+// 16 pixels per thread: one 128-bit load of bytes, four 128-bit stores.  Labels widen U8 -> int32 in the same launch.
+__global__ void __launch_bounds__(T4K_THREADS) k_dataset_load(const uint8_t *__restrict__ src, float *dst, int64_t n, float mean, float scale,
+                                                              const uint8_t *__restrict__ lab8, int32_t *lab32, int nlab, float *hot, int E, int vec) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = tid; i < nlab; i += nth) lab32[i] = (int32_t)lab8[i];
+    if (hot) {                                              // Model::onehot(Dataset&) (loss.cpp:59-68): zeros, then hot[n, m < E ? m : 0] = 1
+        for (int64_t i = tid; i < (int64_t)nlab * E; i += nth) {
+            const int m = (int)lab8[i / E], e = (int)(i % E);
+            hot[i] = (e == (m < E ? m : 0)) ? 1.0f : 0.0f;
+        }
+    }
+    if (vec) {
+        const int64_t n16 = n >> 4;
+        for (int64_t q = tid; q < n16; q += nth) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(src) + q);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float4 o;
+                o.x = __fmul_rn(__fsub_rn((float)(int)(ww[k] & 0xffu), mean), scale);
+                o.y = __fmul_rn(__fsub_rn((float)(int)((ww[k] >> 8) & 0xffu), mean), scale);
+                o.z = __fmul_rn(__fsub_rn((float)(int)((ww[k] >> 16) & 0xffu), mean), scale);
+                o.w = __fmul_rn(__fsub_rn((float)(int)(ww[k] >> 24), mean), scale);
+                stg4(dst + 16 * q + 4 * k, o);
+            }
+        }
+        for (int64_t i = (n16 << 4) + tid; i < n; i += nth) dst[i] = __fmul_rn(__fsub_rn((float)(int)src[i], mean), scale);
+    } else {
+        for (int64_t i = tid; i < n; i += nth) dst[i] = __fmul_rn(__fsub_rn((float)(int)src[i], mean), scale);
+    }
+}
+
 } // namespace t4k
 using namespace t4k;
 
@@ -268,6 +302,15 @@ extern "C" int t4k_softmax_fwd(const float *I, float *O, int N, int C, t4k_strea
 extern "C" int t4k_logsoftmax_fwd(const float *I, float *O, int N, int C, t4k_stream_t s) {
     if (!I || !O || N < 1 || C < 1) return T4K_EINVAL;
     k_softmax<true><<<((int64_t)N * 32 + T4K_THREADS - 1) / T4K_THREADS, T4K_THREADS, 0, STRM(s)>>>(I, O, N, C);
+    return check_launch();
+}
+extern "C" int t4k_dataset_load(const uint8_t *src, float *dst, int64_t n, float mean, float scale,
+                                const uint8_t *lab8, int32_t *lab32, int nlab, float *hot, int E, t4k_stream_t s) {
+    if (!src || !dst || n < 0 || nlab < 0 || (nlab && (!lab8 || !lab32)) || (hot && E < 1)) return T4K_EINVAL;
+    if (n == 0 && nlab == 0) return 0;
+    const int vec = aligned16(src) && aligned16(dst);
+    const int64_t work = n / (vec ? 16 : 1) > (int64_t)nlab * (hot ? E : 1) ? n / (vec ? 16 : 1) : (int64_t)nlab * (hot ? E : 1);
+    k_dataset_load<<<stream_grid(work > 0 ? work : 1), T4K_THREADS, 0, STRM(s)>>>(src, dst, n, mean, scale, lab8, lab32, nlab, hot, E, vec);
     return check_launch();
 }
 extern "C" int t4k_onehot(const int32_t *label, float *hot, int N, int E, t4k_stream_t s) {

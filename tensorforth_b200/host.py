@@ -40,6 +40,11 @@ PROTOTYPES = {
     "t4h_model_arena": (_i, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_l)]),
     "t4h_model_step_graph": (_i, [_p, _p, _p, _i, _p, _i, _f, _f, _f, _f]),
     "t4h_model_dp_attach": (_i, [_p, _p, _p, _i]),
+    "t4h_dataset_create": (_p, [_i, _i, _i, _i]), "t4h_dataset_destroy": (None, [_p]), "t4h_dataset_normalize": (None, [_p, _f, _f]),
+    "t4h_dataset_stage": (_i, [_p, _p, _p, _i]), "t4h_dataset_commit": (_i, [_p]), "t4h_dataset_tensor": (_p, [_p]),
+    "t4h_dataset_labels": (_p, [_p]), "t4h_model_forward_ds": (_i, [_p, _p]),
+    "t4h_model_step_graph_ds": (_i, [_p, _p, _i, _p, _i, _f, _f, _f, _f]),
+    "t4h_model_train_step_ds": (_i, [_p, _p, _i, _p, _i, _f, _f, _f, _f, C.POINTER(_f)]), "t4h_model_train_flush": (_i, [_p, C.POINTER(_f)]),
 }
 _lib = None
 
@@ -281,9 +286,73 @@ class Model:
         _k.check(load().t4h_model_dp_attach(self.h, comm, scal_dev_ptr, nscal), "dp_attach")
         return self
 
+    def forward_ds(self, ds):
+        """Model::forward(Dataset&): forward + one-hot of the batch labels + hit count, all on the device"""
+        if load().t4h_model_forward_ds(self.h, ds.h): raise T4KError(_err())
+        return self
+
+    def step_graph_ds(self, ds, loss_op, loss_dev_ptr, optimizer=2, lr=1e-3, b1=0.9, b2=0.999, wd=0.0):
+        """one iteration of `ds for forward loss backprop nn.adam next`: commit the staged batch + one-hot + captured train step"""
+        return load().t4h_model_step_graph_ds(self.h, ds.h, loss_op, loss_dev_ptr, optimizer, lr, b1, b2, wd)
+
+    def train_step_ds(self, ds, loss_op, loss_dev_ptr, optimizer=2, lr=1e-3, b1=0.9, b2=0.999, wd=0.0):
+        """step_graph_ds + pipelined loss read-back: returns the loss of the PREVIOUS call (nan on the first)"""
+        prev = _f()
+        _k.check(load().t4h_model_train_step_ds(self.h, ds.h, loss_op, loss_dev_ptr, optimizer, lr, b1, b2, wd, C.byref(prev)), "train_step_ds")
+        return prev.value
+
+    def train_flush(self):
+        last = _f()
+        _k.check(load().t4h_model_train_flush(self.h, C.byref(last)), "train_flush")
+        return last.value
+
     def step_graph(self, x, tgt, loss_op, loss_dev_ptr, optimizer=2, lr=1e-3, b1=0.9, b2=0.999, wd=0.0):
         """forward + loss + backprop + optimizer as one replayed CUDA graph (optimizer: 0 sgd, 2 adam, 3 adamw)"""
         return load().t4h_model_step_graph(self.h, x.h, tgt.h, loss_op, loss_dev_ptr, optimizer, lr, b1, b2, wd)
+
+
+class Dataset:
+    """Mini-batch feeder mirroring the reference's Dataset (src/mu/dataset.h): `N dataset <name>` + `normalize`.  The loader
+    (file parsing) is the caller's; stage() takes the raw uint8 image block [n,H,W,C] and uint8 labels [n] of a mini-batch
+    (numpy arrays or pinned torch uint8 tensors) and copies the BYTES asynchronously; commit() normalises on the device."""
+
+    def __init__(self, N, H, W, C_):
+        self.h = load().t4h_dataset_create(N, H, W, C_)
+        self.N, self.shape = N, (N, H, W, C_)
+        self._keep = []
+
+    def normalize(self, mean, scale):
+        load().t4h_dataset_normalize(self.h, mean, scale); return self
+
+    @staticmethod
+    def _ptr(a):
+        if hasattr(a, "data_ptr"):
+            return C.c_void_p(a.data_ptr()), a.numel()
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        return C.c_void_p(a.ctypes.data), a.size, a
+
+    def stage(self, images_u8, labels_u8):
+        pi, pl = self._ptr(images_u8), self._ptr(labels_u8)
+        self._keep = (self._keep + [pi, pl])[-8:]                  # host blocks stay alive while the async copies run
+        if load().t4h_dataset_stage(self.h, pi[0], pl[0], pl[1]): raise T4KError(_err())
+        return self
+
+    def commit(self):
+        if load().t4h_dataset_commit(self.h): raise T4KError(_err())
+        return self
+
+    @property
+    def tensor(self):
+        return Tensor(load().t4h_dataset_tensor(self.h), owned=False)
+
+    @property
+    def labels_ptr(self): return C.c_void_p(load().t4h_dataset_labels(self.h))
+
+    def __del__(self):
+        try:
+            if self.h: load().t4h_dataset_destroy(self.h); self.h = None
+        except Exception:
+            pass
 
 
 def mnist_cnn(N):

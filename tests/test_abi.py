@@ -61,3 +61,19 @@ def test_no_gpu_means_error_not_fallback():
     buf = (C.c_float * 16)()
     rc = L.t4k_map(lib.FILL, C.cast(buf, C.c_void_p), 1.0, 16, None)
     assert rc != 0 and buf[0] == 0.0           # launch fails loudly; host memory is never touched by a CPU path
+
+
+def test_host_library_exports_every_symbol_of_t4host_h():
+    """libt4host.so (the Tensor/Model/Dataset class mirror) must export what include/t4host.h declares, and the ctypes face
+    must bind exactly those it uses"""
+    import ctypes as C
+    hdr = open(os.path.join(ROOT, "include", "t4host.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(t4h_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(syms) >= 50, len(syms)
+    L = C.CDLL(os.path.join(ROOT, "tensorforth_b200", "libt4host.so"))
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    from tensorforth_b200 import host
+    unknown = [s for s in host.PROTOTYPES if s not in syms]
+    assert not unknown, unknown

@@ -545,3 +545,24 @@ def test_launches_are_counted():
     d = zeros(1024)
     ok(lib().t4k_map(t4.FILL, ptr(d), 1.0, 1024, None))
     assert lib().t4k_launch_count() == before + 1
+
+
+# ------------------------------------------------------------------ dataset feeding
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 784 * 5 + 3, 512 * 784])
+@pytest.mark.parametrize("norm", [None, (128.0, 128.0), (0.0, 255.0)])
+def test_dataset_load_bit_exact(n, norm):
+    """Dataset::_load on device: U8 pixels -> (x - mean) * scale, labels U8 -> int32 -> one-hot; bit-exact vs the oracle"""
+    rng = np.random.default_rng(n + 1)
+    u8 = rng.integers(0, 256, max(n, 1), dtype=np.uint8)[:n]
+    lab = rng.integers(0, 12, 37, dtype=np.uint8)
+    mean, scale = orc.dataset_normalize(*norm) if norm else (np.float32(0.0), np.float32(1.0 / 256.0))
+    src = torch.from_numpy(np.concatenate([u8, np.zeros(16, np.uint8)])).cuda()
+    dst = zeros(max(n, 1)); l8 = torch.from_numpy(lab).cuda(); l32 = torch.zeros(37, dtype=torch.int32, device="cuda")
+    hot2 = zeros(37, 10) + 7.0
+    ok(lib().t4k_dataset_load(ptr(src), ptr(dst), n, float(mean), float(scale), C.c_void_p(l8.data_ptr()), C.c_void_p(l32.data_ptr()), 37, ptr(hot2), 10, None))
+    assert_exact(host(hot2), orc.onehot(lab.astype(np.int32), 10), "one-hot written by the load launch")
+    assert_exact(host(dst)[:n], orc.dataset_load(u8, mean, scale), "dataset_load")
+    assert np.array_equal(l32.cpu().numpy(), lab.astype(np.int32))
+    hot = zeros(37, 10)
+    ok(lib().t4k_onehot(C.c_void_p(l32.data_ptr()), ptr(hot), 37, 10, None))
+    assert_exact(host(hot), orc.onehot(lab.astype(np.int32), 10), "onehot of u8 labels (label >= E -> class 0, loss.cpp:66)")

@@ -296,3 +296,58 @@ def test_fused_block_equals_per_layer(kind, N):
         if ga.dw(i) is not None and ga.w(i) is not None and ga.db(i) is not None:
             assert_close(ga.dw(i).numpy(), gb.dw(i).numpy(), rtol=1e-5, what="dw%d" % i)
             assert_close(ga.db(i).numpy(), gb.db(i).numpy(), rtol=1e-5, what="db%d" % i)
+
+
+# ------------------------------------------------------------------ Dataset feeding (src/mu/dataset.cu, forward.cu:72-75)
+def test_dataset_feed_forward_onehot_hit_and_train_step():
+    """U8 mini-batches staged asynchronously (double buffered), normalised on the device, fed to Model::forward(Dataset&):
+    same tensor, one-hot, hit count and training trajectory as float batches prepared on the host the way Dataset::_load does."""
+    N, E = 32, 10
+    rng = np.random.default_rng(3)
+    batches = [(rng.integers(0, 256, (N, 28, 28, 1), dtype=np.uint8), rng.integers(0, 10, N, dtype=np.uint8)) for _ in range(4)]
+    ds = th.Dataset(N, 28, 28, 1).normalize(128.0, 128.0)                 # t4_40b.4th:52 `128 128 normalize`
+    mean, scale = orc.dataset_normalize(128.0, 128.0)
+
+    def build():
+        t4.load().t4k_rand_seed(77)
+        return th.mnist_cnn(N)
+    m, ref = build(), build()
+    loss_dev = torch.zeros(8, device="cuda"); lp = C.c_void_p(loss_dev.data_ptr())
+    loss_ref = torch.zeros(8, device="cuda"); lr_ = C.c_void_p(loss_ref.data_ptr())
+    # forward(Dataset): tensor contents, one-hot and hit
+    ds.stage(*batches[0]).commit()
+    x0 = orc.dataset_load(batches[0][0], mean, scale).reshape(N, 28, 28, 1)
+    assert np.array_equal(ds.tensor.numpy().view(np.uint32).ravel(), x0.view(np.uint32).ravel())
+    m.forward_ds(ds)
+    hot0 = orc.onehot(batches[0][1].astype(np.int32), E)
+    assert m.hit(False) == orc.hit(m.layer(-1).numpy().reshape(N, E), hot0)
+    ref.forward(th.Tensor.from_numpy(x0))
+    assert np.array_equal(m.layer(-1).numpy(), ref.layer(-1).numpy())
+    # training: stage batch i+1 while batch i trains
+    ds.stage(*batches[0])
+    got, want = [], []
+    for i in range(4):
+        if i + 1 < 4:
+            ds.stage(*batches[i + 1])
+        t4.check(m.step_graph_ds(ds, t4.LOSS_CE, lp, optimizer=2, lr=1e-3), "step_graph_ds")
+        th.sync(); got.append(float(loss_dev[0].cpu()))
+        xi = th.Tensor.from_numpy(orc.dataset_load(batches[i][0], mean, scale).reshape(N, 28, 28, 1))
+        yi = th.Tensor.tensor(N, 1, E, 1, orc.onehot(batches[i][1].astype(np.int32), E))
+        ref.forward(xi); ref.loss_async(t4.LOSS_CE, yi, lr_); ref.backprop(yi); ref.adam(1e-3)
+        th.sync(); want.append(float(loss_ref[0].cpu()))
+    np.testing.assert_allclose(got, want, rtol=1e-6)
+    assert np.array_equal(m.w(4).numpy(), ref.w(4).numpy())
+    # train_step_ds: same step, loss read-back pipelined by one call
+    ds.stage(*batches[0])
+    seen = []
+    for i in range(3):
+        if i + 1 < 3:
+            ds.stage(*batches[i + 1])
+        seen.append(m.train_step_ds(ds, t4.LOSS_CE, lp, optimizer=2, lr=1e-3))
+        xi = th.Tensor.from_numpy(orc.dataset_load(batches[i][0], mean, scale).reshape(N, 28, 28, 1))
+        yi = th.Tensor.tensor(N, 1, E, 1, orc.onehot(batches[i][1].astype(np.int32), E))
+        ref.forward(xi); ref.loss_async(t4.LOSS_CE, yi, lr_); ref.backprop(yi); ref.adam(1e-3)
+        th.sync(); want.append(float(loss_ref[0].cpu()))
+    seen.append(m.train_flush())
+    assert np.isnan(seen[0])
+    np.testing.assert_allclose(seen[1:], want[4:], rtol=1e-6)

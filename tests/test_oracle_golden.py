@@ -128,3 +128,14 @@ def test_t4_30c_mazur_n3():
     m.sgd(0.5, 0.0)
     close(L[0].w, [[0.1359, 0.1718], [0.2339, 0.2679]])         # :67 verify
     close(L[0].b, [0.0680, 0.0287])                             # :70 verify
+
+
+def test_dataset_load_known_values():
+    """Dataset::_load (src/mu/dataset.cu:139-143) with the default scale 1/256 (dataset.h:36) and with `128 128 normalize`
+    (examples/t4_40b.4th:52: [0,255] -> [-1, 1))"""
+    u8 = np.array([0, 1, 127, 128, 255], np.uint8)
+    np.testing.assert_array_equal(orc.dataset_load(u8), np.array([0, 1, 127, 128, 255], np.float32) / 256)
+    mean, scale = orc.dataset_normalize(128.0, 128.0)
+    assert (mean, scale) == (128.0, 1.0 / 128.0)
+    np.testing.assert_array_equal(orc.dataset_load(u8, mean, scale), np.array([-1.0, -0.9921875, -0.0078125, 0.0, 0.9921875], np.float32))
+    assert orc.dataset_normalize(0.0, 0.0)[1] == 1.0                    # "scale == 0?" -> 1.0
