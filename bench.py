@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 emit = None
 BATCH = 512                       # per GPU (BASELINE config 3)
+GAN_BATCH = 1024                  # per GPU (BASELINE config 4)
 REF_TEN4 = os.path.join(ROOT, "oracle", "_ref", "ten4")
 
 
@@ -96,6 +97,19 @@ def ref_script(kind, warm, steps, batch):
             "0 trace", "4096 4096 matrix rand", "4096 4096 matrix rand",
             ": mx ( A B n -- A B ) clock >r for @ drop next clock r> - . ;",
             "%d mx cr" % max(warm - 1, 0), "%d mx cr" % (steps - 1), "bye", ""])
+    if kind == "gan":                     # examples/t4_40b.4th:37-67 on a fixed synthetic "real" batch (no dataset files), no loss reads
+        return "\n".join([
+            "0 trace", "%d constant N" % batch,
+            "N 1 1 1 tensor ones constant REAL", "N 1 1 1 tensor zeros constant FAKE",
+            "N 28 28 1 nn.model 512 linear 0.2 leakyrelu 0.3 dropout 256 linear 0.2 leakyrelu 0.3 dropout 1 linear sigmoid constant D",
+            "N 128 1 1 nn.model 256 linear 0.2 leakyrelu 512 linear 0.2 leakyrelu 784 linear tanh constant G",
+            "N 28 28 1 tensor rand 2 *= 1 -= constant RX",
+            ": X N 128 1 1 tensor randn ;",
+            ": F G X forward -1 n@ N 28 28 1 reshape4 swap drop ;",
+            ": train_d 1 trainable RX forward REAL backprop F forward FAKE backprop 0.0001 0.5 nn.adam ;",
+            ": train_g 0 trainable F forward REAL backprop 0 n@ G swap backprop 0.0004 0.5 nn.adam drop ;",
+            ": bench ( D n -- D ) clock >r for train_d train_g next clock r> - . ;",
+            "D %d bench cr" % max(warm - 1, 0), "%d bench cr" % (steps - 1), "bye", ""])
     raise ValueError(kind)
 
 
@@ -140,6 +154,9 @@ def reference_arm(args):
         if not args.no_extras:
             gms, gwhy = run_ref("gemm", 3, 10)
             line["extras"] = {"gemm4096": ({"ms": gms / 10, "tflops": 2 * 4096 ** 3 / (gms / 10) / 1e9} if gms else {"unavailable": gwhy})}
+            ams, awhy = run_ref("gan", 3, 10, batch=GAN_BATCH)
+            line["extras"]["gan"] = ({"ms_per_iteration": ams / 10, "samples_per_s": GAN_BATCH * 10 / (ams / 1e3), "batch": GAN_BATCH,
+                                      "note": "train_d + train_g of t4_40b.4th:60-67, fixed synthetic real batch"} if ams else {"unavailable": awhy})
     line["wall_s"] = round(time.time() - t0, 2)
     emit(line)
 
@@ -166,6 +183,62 @@ def cpu_port_baseline(steps=4, batch=BATCH):
     dt = time.time() - t0
     cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return batch * n / dt, cores, "%d train steps of N=%d (%.1f s) with the C oracle, OpenMP" % (n, batch, dt)
+
+
+# --------------------------------------------------------------------------------------- GAN (BASELINE config 4)
+def gan_extra(th, t4, L, torch, dist, rank, world, local, lib_stream, iters=50, warm=5):
+    """train_d + train_g of examples/t4_40b.4th:60-67 at N=1024 per GPU on synthetic 28x28 data; data parallel: each model's
+    gradient arena is exchanged inside its Adam kernel (csrc/comm.cu).  Eager launches (dropout draws a fresh mask every
+    forward, so the iteration is not graph-captured).  Returns the extras entry (rank 0) or None."""
+    import numpy as np
+    from tensorforth_b200 import dp as t4dp
+    N = GAN_BATCH
+    L.t4k_rand_seed(4321)
+    D, G = th.gan_discriminator(N, 0.3), th.gan_generator(N)
+    rng = np.random.default_rng(200 + rank)
+    real = th.Tensor.from_numpy((rng.random((N, 28, 28, 1), dtype=np.float32) * 2 - 1).astype(np.float32))
+    REAL, FAKE = th.Tensor.tensor(N, 1, 1, 1, np.ones((N, 1), np.float32)), th.Tensor.tensor(N, 1, 1, 1, np.zeros((N, 1), np.float32))
+    z1, z2 = th.Tensor.tensor(N, 128, 1, 1), th.Tensor.tensor(N, 128, 1, 1)
+    exchange = "none"
+    keep = []
+    if world > 1:
+        dev = torch.device("cuda", local)
+        try:
+            keep = [t4dp.DataParallel(D, dev, fused=True), t4dp.DataParallel(G, dev, fused=True)]
+            exchange = "fused"
+        except Exception as e:
+            sys.stderr.write("rank %d: GAN fused exchange unavailable (%r)\n" % (rank, e))
+            return {"unavailable": "peer exchange unavailable"} if rank == 0 else None
+
+    def it():
+        z1.randn(); z2.randn()                                   # the two `X` draws of an iteration
+        th.gan_iteration(D, G, real, z1, z2, REAL, FAKE, losses=False)
+    n0 = L.t4k_launch_count(); it(); launches = L.t4k_launch_count() - n0
+    for _ in range(warm):
+        it()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(lib_stream)
+    for _ in range(iters):
+        it()
+    b.record(lib_stream)
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.cpu()[0])
+        for d in keep:
+            assert d.comm.status() == 0
+    l_dr, l_df, l_gr = th.gan_iteration(D, G, real, z1, z2, REAL, FAKE)
+    if rank != 0:
+        return None
+    flops = 3 * 2 * N * (784 * 512 + 512 * 256 + 256) * 2 + 2 * N * (784 * 512 + 512 * 256 + 256) + 2 * 2 * N * (128 * 256 + 256 * 512 + 512 * 784) + 2 * 2 * N * (128 * 256 + 256 * 512 + 512 * 784)
+    return {"batch_per_gpu": N, "ms_per_iteration": round(ms / iters, 4), "samples_per_s": round(N * world * iters / (ms / 1e3), 1),
+            "launches_per_iteration": int(launches), "exchange": exchange, "tflops": round(flops * world / (ms / iters) / 1e9, 2),
+            "losses_after": {"d_real": round(l_dr, 4), "d_fake": round(l_df, 4), "g": round(l_gr, 4)},
+            "note": "one iteration = train_d (D fwd/bwd on real + on G's fakes, Adam b1=0.5) + train_g (D frozen, dX of D's input through G, Adam); "
+                    "3 D-forwards, 3 D-backwards, 2 G-forwards, 1 G-backward, 2 Adam; eager launches, no loss reads in the timed loop"}
 
 
 # --------------------------------------------------------------------------------------- our arm
@@ -344,6 +417,13 @@ def main():
            "note": "per step: U8 pixels + U8 labels from pinned host memory -> async H2D (copy stream, double buffered) -> on-device normalise "
                    "(u8-128)/128 + one-hot (1 launch) -> train step -> loss D2H read on the host (pipelined by one step); one host call per iteration"}
 
+    gan = None
+    if not args.no_extras:
+        try:
+            gan = gan_extra(th, t4, L, torch, dist, rank, world, local, lib_stream)
+        except Exception as e:                                  # extras never take the headline line down
+            gan = {"unavailable": repr(e)[:200]}
+            sys.stderr.write("GAN extra failed: %r\n" % (e,))
     if fused:
         stt = dpm.comm.status()
         assert stt == 0, "rank %d: the gradient exchange timed out waiting for rank %d" % (rank, stt - 1)
@@ -473,6 +553,8 @@ def main():
                                "roofline_tensor": {"bound": "tensor", "achieved": round(fl / usf / 1e6, 1), "peak": round(tf32_peak / 3, 1), "unit": "TFLOP/s", "frac": round(fl / usf / 1e6 / (tf32_peak / 3), 4)},
                                "note": "NHWC, N=%d of the 8192-sample config per launch (per-sample cost is size independent); 3xTF32 implicit GEMM: tensor-bound, HBM fraction shown for the metric" % cn}
         out["extras"] = ex
+    if gan is not None:
+        out.setdefault("extras", {})["gan_t4_40b"] = gan
     if not args.no_cpu_baseline:
         v, cores, sample = cpu_port_baseline()
         out["cpu_baseline"] = {"value": round(v, 1), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}

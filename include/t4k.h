@@ -59,7 +59,9 @@ enum t4k_loss { T4K_LOSS_MSE = 0, T4K_LOSS_BCE, T4K_LOSS_CE, T4K_LOSS_NLL };
 /* rand_opt — src/util.h (UNIFORM, NORMAL) */
 enum t4k_rand_opt { T4K_UNIFORM = 0, T4K_NORMAL = 1 };
 /* GEMM engine selection for t4k_gemm_ex (0 = automatic) */
-enum t4k_gemm_engine { T4K_GEMM_AUTO = 0, T4K_GEMM_SIMT = 1, T4K_GEMM_TC = 2 };
+enum t4k_gemm_engine { T4K_GEMM_AUTO = 0, T4K_GEMM_SIMT = 1,   /* FP32 FMA (gemm_simt.cu) */
+                       T4K_GEMM_TC = 2,                        /* tcgen05 3xTF32, packed operand planes (gemm_tc.cu): large problems */
+                       T4K_GEMM_TCF = 3 };                     /* tcgen05 3xTF32, split fused into the kernel, one launch (gemm_tcf.cu): layer-sized problems */
 
 /* ---- library / device ------------------------------------------------------------- */
 int         t4k_version(void);

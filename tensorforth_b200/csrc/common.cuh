@@ -22,6 +22,11 @@ struct GemmDeferred { const float *part; int splits; };   // gemm_simt(..., defe
 int gemm_simt(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
               int M, int N, int K, int C, int batch, int64_t sA, int64_t sB, int64_t sO, cudaStream_t st, GemmDeferred *defer = nullptr);
 
+// mid-size single-launch tensor-core GEMM (gemm_tcf.cu): in-kernel 3xTF32 split, split-K; same deferred-finish contract
+bool gemm_tcf_ok(int tA, int tB, int M, int N, int K, int C, int batch);
+int  gemm_tcf(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
+              int M, int N, int K, cudaStream_t st, GemmDeferred *defer = nullptr);
+
 static inline cudaStream_t STRM(t4k_stream_t s) { return (cudaStream_t)s; }
 
 // ---- programmatic dependent launch (PDL).  A train step is a chain of ~12 short dependent kernels; with a plain

@@ -334,8 +334,15 @@ extern "C" int t4k_gemm_ex(int engine, const float *A, const float *B, float *O,
     if (!A || !B || !O || M < 1 || N < 1 || K < 0 || C < 1 || batch < 1) return T4K_EINVAL;
     bool tc = false;
     if (engine == T4K_GEMM_TC) { if (C != 1 || K < 1) return T4K_EINVAL; tc = true; }
+    else if (engine == T4K_GEMM_TCF) {
+        if (C != 1 || K < 1) return T4K_EINVAL;
+        for (int b = 0; b < batch; b++) { int rc = gemm_tcf(A + b * sA, B + b * sB, O + b * sO, alpha, beta, tA, tB, M, N, K, STRM(s)); if (rc) return rc; }
+        return 0;
+    }
     else if (engine == T4K_GEMM_AUTO) {
-        // tensor path pays two pack passes + a 128-wide tile: take it when there is real math
+        // mid-size problems (the NN layers): one launch with the operand split fused in (gemm_tcf.cu).  Big ones: packed planes +
+        // bulk-copy fed MMA (two pack passes amortised over many tiles).  Small / channel-interleaved / batched: FP32 FMA.
+        if ((double)M * N * K < 2.0e10 && gemm_tcf_ok(tA, tB, M, N, K, C, batch)) return gemm_tcf(A, B, O, alpha, beta, tA, tB, M, N, K, STRM(s));
         tc = (C == 1) && K >= 64 && (double)M * N * K >= 2.0e8 && M >= 64 && N >= 32;
     }
     for (int b = 0; tc && b < batch; b++) {

@@ -52,7 +52,8 @@ template<int L> static int launch_fin(const GemmDeferred &d, int64_t MN, int E0,
 static int linear_act_fwd(int layer, const float *X, const float *W, const float *B, float *Y, float *A, float *F, float alpha,
                           int N, int E0, int E1, cudaStream_t st) {
     GemmDeferred d{nullptr, 1};
-    int rc = gemm_simt(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, 1, 1, 0, 0, 0, st, &d);
+    int rc = gemm_tcf_ok(0, 1, N, E0, E1, 1, 1) ? gemm_tcf(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, st, &d)       // tensor cores for layer-sized products
+                                                : gemm_simt(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, 1, 1, 0, 0, 0, st, &d);
     if (rc) return rc;
     const int64_t MN = (int64_t)N * E0;
     switch (layer) {
@@ -238,7 +239,7 @@ using namespace t4k;
 
 extern "C" int t4k_linear_fwd(const float *X, const float *W, const float *B, float *Y, int N, int E0, int E1, t4k_stream_t s) {
     if (!X || !W || !B || !Y || N < 1 || E0 < 1 || E1 < 1) return T4K_EINVAL;
-    if ((double)N * E0 * E1 >= 2.0e8 && N >= 64 && E0 >= 32 && E1 >= 64) {         // tensor-core sized: GEMM engine + bias pass
+    if ((double)N * E0 * E1 >= 2.0e10 && N >= 64 && E0 >= 32 && E1 >= 64) {        // very large: packed-plane tensor-core engine + bias pass
         int rc = t4k_gemm(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, 1, 1, 0, 0, 0, s);
         if (rc) return rc;
         return t4k_bias(B, Y, N, E0, s);

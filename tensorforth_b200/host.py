@@ -368,3 +368,31 @@ def gan_discriminator(N):
 def gan_generator(N):
     """examples/t4_40b.4th:44-48"""
     return (Model(N, 128, 1, 1).linear(256).leakyrelu(0.2).linear(512).leakyrelu(0.2).linear(784).tanh())
+
+
+def gan_discriminator(N, p=0.3):
+    """examples/t4_40b.4th:37-41"""
+    return (Model(N, 28, 28, 1).linear(512).leakyrelu(0.2).dropout(p).linear(256).leakyrelu(0.2).dropout(p).linear(1).sigmoid())
+
+
+def gan_iteration(D, G, real, z_d, z_g, REAL, FAKE, d_lr=1e-4, g_lr=4e-4, b1=0.5, losses=True):
+    """one `train_d train_g` of examples/t4_40b.4th:60-67.  real: [N,28,28,1]; z_d / z_g: the latent batches the two `F` calls
+    draw ([N,128,1,1]); REAL / FAKE: the [N,1,1,1] ones / zeros targets.  Returns (loss_dr, loss_df, loss_gr) like the script's
+    `_dr _df _gr` (host reads: each synchronises) or None with losses=False."""
+    BCE = _k.LOSS_BCE
+    out = []
+    D.trainable(1)                                                      # train_d
+    D.forward(real)
+    if losses: out.append(D.loss(BCE, REAL))
+    D.backprop(REAL)
+    G.forward(z_d); D.forward(G.layer(-1))                              # F: G's output (same numel as [N,28,28,1]) feeds D
+    if losses: out.append(D.loss(BCE, FAKE))
+    D.backprop(FAKE)
+    D.adam(d_lr, b1)
+    D.trainable(0)                                                      # train_g: D passes the gradient through, no dW/dB
+    G.forward(z_g); D.forward(G.layer(-1))
+    if losses: out.append(D.loss(BCE, REAL))
+    D.backprop(REAL)
+    G.backprop(D.layer(0))                                              # `0 n@ G swap backprop`: dX of D's input is G's output gradient
+    G.adam(g_lr, b1)
+    return tuple(out) if losses else None

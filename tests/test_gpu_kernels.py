@@ -160,7 +160,7 @@ def gemm_ref64(A, B, O, alpha, beta, tA, tB):
     return alpha * (a @ b) + beta * O.astype(np.float64)
 
 
-@pytest.mark.parametrize("engine", [t4.GEMM_SIMT, t4.GEMM_TC])
+@pytest.mark.parametrize("engine", [t4.GEMM_SIMT, t4.GEMM_TC, t4.GEMM_TCF])
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(2, 2, 3), (64, 64, 64), (128, 128, 32), (200, 100, 70), (130, 260, 513), (512, 100, 1960)])
 def test_gemm_engines(engine, tA, tB, M, N, K):
@@ -178,7 +178,7 @@ def test_gemm_engines(engine, tA, tB, M, N, K):
 def test_gemm_beta0_ignores_garbage():
     M = N = K = 96
     A, B = rnd(M, K), rnd(K, N)
-    for eng in (t4.GEMM_SIMT, t4.GEMM_TC):
+    for eng in (t4.GEMM_SIMT, t4.GEMM_TC, t4.GEMM_TCF):
         o = dev(np.full((M, N), np.nan, np.float32))
         ok(lib().t4k_gemm_ex(eng, ptr(dev(A)), ptr(dev(B)), ptr(o), 1.0, 0.0, 0, 0, M, N, K, 1, 1, 0, 0, 0, None))
         assert_close(host(o), gemm_ref64(A, B, np.zeros((M, N)), 1, 0, 0, 0), rtol=2e-5)
@@ -205,6 +205,23 @@ def test_gemm_tc_large_vs_f64():
     assert_close(got, ref, rtol=1e-5, what="3xTF32 1024^3")
     rel = np.abs(got - ref).max() / np.abs(ref).max()
     assert rel < 2e-6, rel                                # FP32-grade: plain TF32 would be ~5e-4
+
+
+@pytest.mark.parametrize("tA,tB,M,N,K", [(0, 1, 1024, 512, 784), (1, 0, 512, 784, 1024), (0, 0, 1024, 784, 512),     # GAN D layer 1: fwd / dW / dX
+                                         (0, 1, 512, 100, 1960), (1, 0, 100, 1960, 512), (0, 0, 512, 1960, 100),     # MNIST linear 1960->100
+                                         (0, 0, 300, 132, 2052), (1, 1, 129, 257, 36)])                              # ragged tiles, K tails
+def test_gemm_tcf_layer_shapes_vs_f64(tA, tB, M, N, K):
+    """the single-launch tensor-core engine (in-kernel 3xTF32 split, split-K) on the linear-layer shapes: FP32-grade vs exact"""
+    A = rnd(K, M) if tA else rnd(M, K)
+    B = rnd(N, K) if tB else rnd(K, N)
+    O0 = rnd(M, N)
+    for alpha, beta in ((1.0, 0.0), (1.0, 1.0)):           # beta = 1: the dW accumulation of Model::_blinear
+        o = dev(O0)
+        ok(lib().t4k_gemm_ex(t4.GEMM_TCF, ptr(dev(A)), ptr(dev(B)), ptr(o), alpha, beta, tA, tB, M, N, K, 1, 1, 0, 0, 0, None), "gemm_tcf")
+        ref = gemm_ref64(A, B, O0, alpha, beta, tA, tB)
+        got = host(o)
+        assert_close(got, ref, rtol=1e-5, what="tcf vs f64")
+        assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-6
 
 
 def test_gemm_4096_property():

@@ -351,3 +351,43 @@ def test_dataset_feed_forward_onehot_hit_and_train_step():
     seen.append(m.train_flush())
     assert np.isnan(seen[0])
     np.testing.assert_allclose(seen[1:], want[4:], rtol=1e-6)
+
+
+# ------------------------------------------------------------------ GAN iteration (BASELINE config 4; examples/t4_40b.4th:37-67)
+def test_gan_iteration_vs_oracle():
+    """train_d + train_g exactly as the script sequences them (two accumulated D backprops -> Adam(b1=0.5); D frozen, dX of D's
+    input back-propagated through G -> Adam) against the oracle's Model restatement.  Dropout p = 0 here: the mask RNG is not
+    parity-comparable; the layer itself stays in the path (mask = all ones)."""
+    N = 16
+    rng = np.random.default_rng(21)
+    D, G = th.gan_discriminator(N, p=0.0), th.gan_generator(N)
+    oD = orc.OracleModel(N, 28, 28, 1, seed=31)
+    oD.add(orc.L_LINEAR, 512, 1.0).add(orc.L_LEAKYRL, 0, 0.2).add(orc.L_DROPOUT, 0, 0.0).add(orc.L_LINEAR, 256, 1.0).add(orc.L_LEAKYRL, 0, 0.2)
+    oD.add(orc.L_DROPOUT, 0, 0.0).add(orc.L_LINEAR, 1, 1.0).add(orc.L_SIGMOID)
+    oG = orc.OracleModel(N, 128, 1, 1, seed=32)
+    oG.add(orc.L_LINEAR, 256, 1.0).add(orc.L_LEAKYRL, 0, 0.2).add(orc.L_LINEAR, 512, 1.0).add(orc.L_LEAKYRL, 0, 0.2).add(orc.L_LINEAR, 784, 1.0).add(orc.L_TANH)
+    inject(D, oD); inject(G, oG)
+    ones, zeros_ = np.ones((N, 1), np.float32), np.zeros((N, 1), np.float32)
+    REAL, FAKE = th.Tensor.tensor(N, 1, 1, 1, ones), th.Tensor.tensor(N, 1, 1, 1, zeros_)
+    for it in range(2):
+        real = (rng.random((N, 28, 28, 1), dtype=np.float32) * 2 - 1).astype(np.float32)
+        z1, z2 = rng.standard_normal((N, 128, 1, 1)).astype(np.float32), rng.standard_normal((N, 128, 1, 1)).astype(np.float32)
+        got = th.gan_iteration(D, G, th.Tensor.from_numpy(real), th.Tensor.from_numpy(z1), th.Tensor.from_numpy(z2), REAL, FAKE)
+        # the same sequence on the oracle (t4_40b.4th:60-67)
+        oD.train = True
+        oD.forward(real); l_dr = oD.loss(orc.LOSS_BCE, ones); oD.backprop(ones)
+        fake = oG.forward(z1).output().reshape(N, 28, 28, 1).copy()
+        oD.forward(fake); l_df = oD.loss(orc.LOSS_BCE, zeros_); oD.backprop(zeros_)
+        oD.adam(1e-4, 0.5)
+        oD.train = False
+        fake = oG.forward(z2).output().reshape(N, 28, 28, 1).copy()
+        oD.forward(fake); l_gr = oD.loss(orc.LOSS_BCE, ones); oD.backprop(ones)
+        oG.backprop(oD.layers[0].data.reshape(N, -1).copy())
+        oG.adam(4e-4, 0.5)
+        assert_close(got, (l_dr, l_df, l_gr), rtol=1e-4, atol=1e-6, what="GAN losses it %d" % it)
+        compare_params(D, oD, "D it %d" % it, grads=False, w_atol=0.05 * 1e-4)
+        compare_params(G, oG, "G it %d" % it, grads=False, w_atol=0.05 * 4e-4)
+        for m_, o_ in ((D, oD), (G, oG)):                       # next iteration from identical parameters (Adam amplifies rounding noise)
+            for i, L in enumerate(o_.layers[:-1]):
+                if L.w is not None and L.dw is not None:
+                    L.w[...] = m_.w(i).numpy().reshape(L.w.shape); L.b[...] = m_.b(i).numpy().reshape(L.b.shape)
