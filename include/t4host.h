@@ -101,6 +101,10 @@ int   t4h_model_adam(t4h_model m, float lr, float b1, float b2);     /* `nn.adam
 int   t4h_model_adamw(t4h_model m, float lr, float wd, float b1, float b2);
 /* flat parameter arenas (built at the first optimizer call): pointers + float count; DG is what a
  * data-parallel caller sum-allreduces between backprop and the optimizer */
+/* words `save` / `load` on a model (src/vm/netvm.cpp:479-480 -> src/io/aio_model.cpp): the reference's model file — text header and
+ * layer lines, then `--- w.<layer>` / `--- b.<layer>` sections of raw FP32.  load fills an already built model (parameter path). */
+int   t4h_model_save(t4h_model m, const char *fname);
+int   t4h_model_load(t4h_model m, const char *fname);
 int   t4h_model_arena(t4h_model m, float **G, float **DG, int64_t *total);
 /* capture forward+loss+backprop+optimizer into one CUDA graph and replay it (launch-bound regime);
  * optimizer: 0 sgd, 1 sgd+momentum, 2 adam, 3 adamw, -1 none (data parallel: all-reduce DG, then call the optimizer) */

@@ -5,6 +5,9 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
+#include <fstream>
+#include <sstream>
+#include <string>
 #include <cstdarg>
 #include <cstring>
 #include <cfloat>
@@ -730,6 +733,76 @@ Model &Model::sgd(DU lr, DU b) {                                           // gr
 }
 Model &Model::adam(DU lr, DU b1, DU b2)         { return _gradient(OPTI_ADAM, lr, b1, b2, 0.0f); }     // gradient.cu:145-157 (no bias correction)
 Model &Model::adamw(DU lr, DU wd, DU b1, DU b2) { return _gradient(OPTI_ADAMW, lr, b1, b2, wd); }      // gradient.cu:159-169
+// ---- persistence: the reference's model file (src/io/aio_model.cpp)
+const char *Model::nname(int fn) {
+    static const char *name[] = { "output ", "conv2d ", "linear ", "flatten", "relu   ", "tanh   ", "sigmoid", "selu   ", "leakyrl", "elu    ",
+                                  "dropout", "softmax", "logsmax", "avgpool", "maxpool", "minpool", "batchnm", "upsampl", "dconv2d" };
+    return (fn >= 0 && fn < 19) ? name[fn] : "unknown";
+}
+static std::string layer_parm(Tensor &in, Tensor &out) {                  // AIO::_parm, aio_model.cpp:102-141 (ostream << float formatting)
+    std::ostringstream o;
+    const int S = in.stride[0]; const DU p = in.xparm;
+    switch (in.grad_fn) {
+    case T4K_L_CONV: case T4K_L_DCONV: o << "bias=" << p << ", C=" << out.C() << ", K=" << in.grad[0]->H() << ", S=" << S << ", P=" << in.stride[2]; break;
+    case T4K_L_LINEAR:  o << "bias=" << p << ", H=" << in.grad[0]->H(); break;
+    case T4K_L_SELU: case T4K_L_LEAKYRL: case T4K_L_ELU: o << "bias=" << p; break;
+    case T4K_L_DROPOUT: o << "rate=" << p * 100.0 << '%'; break;
+    case T4K_L_AVGPOOL: case T4K_L_MAXPOOL: case T4K_L_MINPOOL: o << S << "x" << S; break;
+    case T4K_L_BATCHNM: o << "mtum=" << p; break;
+    case T4K_L_USAMPLE: { const char *nm[] = { "nearest", "linear", "bilinear", "cubic" }; o << S << "x" << S << " " << nm[in.iparm & 3]; } break;
+    default: break;
+    }
+    return o.str();
+}
+int Model::save(const char *fname) {                                       // AIO::nsave + _nsave_model + _nsave_param
+    std::ofstream fs(fname, std::ios_base::binary);
+    if (!fs.is_open()) { Runtime::error("} => failed to open for output\n"); return 1; }
+    fs << "\\ tensorForth v4.0 model\n";
+    const int n = (int)_layers.size();
+    for (int i = 0; i < n - 1; i++) fs << layer_parm(*_layers[i], *_layers[i + 1]) << nname(_layers[i]->grad_fn) << std::endl;
+    std::vector<DU> h;
+    auto dump = [&](char pn, const char *nm, Tensor &t) {
+        fs << "\n--- " << pn << "." << nm << std::endl;
+        h.resize(t.numel); t.d2h(h.data());
+        fs.write((const char*)h.data(), t.numel * sizeof(DU));
+    };
+    for (int i = 0; i < n - 1; i++) {
+        Tensor &in = *_layers[i];
+        switch (in.grad_fn) {
+        case T4K_L_CONV: case T4K_L_LINEAR: dump('w', nname(in.grad_fn), *in.grad[0]); dump('b', nname(in.grad_fn), *in.grad[1]); break;
+        case T4K_L_BATCHNM: dump('w', nname(in.grad_fn), *in.grad[0]); break;
+        default: break;
+        }
+    }
+    fs << "\n---" << std::endl;
+    return fs.good() ? 0 : 1;
+}
+int Model::load(const char *fname) {                                       // AIO::nload (parameter path) + _nload_param
+    std::ifstream fs(fname, std::ios_base::binary);
+    if (!fs.is_open()) { Runtime::error("} => failed to open for input\n"); return 1; }
+    std::string line;
+    while (std::getline(fs, line) && line.length()) {}                     // skip the model section (up to the blank line)
+    std::vector<DU> h;
+    int err = 0;
+    auto read = [&](Tensor &t) {
+        while (std::getline(fs, line) && !line.length()) {}                // skip blank lines
+        if (line.size() < 3 || line[0] != '-' || line[1] != '-' || line[2] != '-') { Runtime::error(" model format error"); err = 1; return; }
+        h.resize(t.numel);
+        fs.read((char*)h.data(), t.numel * sizeof(DU));
+        if ((U64)fs.gcount() != t.numel * sizeof(DU)) { Runtime::error(" model format error"); err = 1; return; }
+        t.h2d(h.data()); Runtime::sync();                                  // `h` is reused by the next section
+    };
+    const int n = (int)_layers.size();
+    for (int i = 0; i < n - 1 && !err; i++) {
+        Tensor &in = *_layers[i];
+        switch (in.grad_fn) {
+        case T4K_L_CONV: case T4K_L_LINEAR: read(*in.grad[0]); if (!err) read(*in.grad[1]); break;
+        case T4K_L_BATCHNM: read(*in.grad[0]); break;
+        default: break;
+        }
+    }
+    return err;
+}
 int Model::arena(DU **G, DU **DG, int64_t *total) {
     if (!_G) grad_alloc(OPTI_ADAM);
     if (G) *G = _G;
@@ -942,6 +1015,8 @@ int   t4h_model_hit(t4h_model m, int recalc) { return MM(m).hit(recalc != 0); }
 int   t4h_model_sgd(t4h_model m, float lr, float b) { MM(m).sgd(lr, b); return 0; }
 int   t4h_model_adam(t4h_model m, float lr, float b1, float b2) { MM(m).adam(lr, b1, b2); return 0; }
 int   t4h_model_adamw(t4h_model m, float lr, float wd, float b1, float b2) { MM(m).adamw(lr, wd, b1, b2); return 0; }
+int   t4h_model_save(t4h_model m, const char *fname) { return MM(m).save(fname); }
+int   t4h_model_load(t4h_model m, const char *fname) { return MM(m).load(fname); }
 int   t4h_model_arena(t4h_model m, float **G, float **DG, int64_t *total) { return MM(m).arena(G, DG, total); }
 int   t4h_model_dp_attach(t4h_model m, void *comm, float *scal, int nscal) { return MM(m).dp_attach(comm, scal, nscal); }
 int   t4h_model_step_graph(t4h_model m, t4h_tensor input, t4h_tensor tgt, int lop, float *loss_dev, int optimizer, float lr, float b1, float b2, float wd) {

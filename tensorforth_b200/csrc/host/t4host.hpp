@@ -204,6 +204,13 @@ public:
     Model &sgd(DU lr, DU b = 0.9f);
     Model &adam(DU lr, DU b1 = 0.9f, DU b2 = 0.999f);
     Model &adamw(DU lr, DU wd = 0.001f, DU b1 = 0.9f, DU b2 = 0.999f);
+    // persistence (src/io/aio_model.cpp:16-235): `\\ tensorForth v4.0 model` header, one text line per layer (parameters glued to the
+    // 7-character layer name exactly as AIO::_nsave_model writes them), a blank line, then per parametrised layer
+    // `\n--- w.<name>\n` + raw FP32 of the weight (and `b.` bias; batchnorm: w only), closed by `\n---\n`.
+    // load() reads the parameter sections into an already built model of the same architecture (AIO::nload, numel > 2 path).
+    int    save(const char *fname);
+    int    load(const char *fname);
+    static const char *nname(int fn);                        ///< model.cpp:17-21 (LAYER_OP, ntypes.h:47-51)
     int    arena(DU **G, DU **DG, int64_t *total);
     // data parallel: with a communicator attached, the optimizer calls (sgd/adam/adamw, also inside step_graph)
     // first SUM the gradient arena over the ranks — one fused exchange+optimizer kernel over NVLink peer memory (comm.cu);

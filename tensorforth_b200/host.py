@@ -40,6 +40,7 @@ PROTOTYPES = {
     "t4h_model_arena": (_i, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_l)]),
     "t4h_model_step_graph": (_i, [_p, _p, _p, _i, _p, _i, _f, _f, _f, _f]),
     "t4h_model_dp_attach": (_i, [_p, _p, _p, _i]),
+    "t4h_model_save": (_i, [_p, C.c_char_p]), "t4h_model_load": (_i, [_p, C.c_char_p]),
     "t4h_dataset_create": (_p, [_i, _i, _i, _i]), "t4h_dataset_destroy": (None, [_p]), "t4h_dataset_normalize": (None, [_p, _f, _f]),
     "t4h_dataset_stage": (_i, [_p, _p, _p, _i]), "t4h_dataset_commit": (_i, [_p]), "t4h_dataset_tensor": (_p, [_p]),
     "t4h_dataset_labels": (_p, [_p]), "t4h_model_forward_ds": (_i, [_p, _p]),
@@ -279,6 +280,14 @@ class Model:
         g, dg, n = _p(), _p(), _l()
         _k.check(load().t4h_model_arena(self.h, C.byref(g), C.byref(dg), C.byref(n)), "arena")
         return g.value, dg.value, n.value
+
+    def save(self, fname):              # word `save` ( N adr len -- N ): the reference's model file (src/io/aio_model.cpp)
+        if load().t4h_model_save(self.h, str(fname).encode()): raise T4KError(_err())
+        return self
+
+    def load(self, fname):              # word `load`: parameters into an already built model
+        if load().t4h_model_load(self.h, str(fname).encode()): raise T4KError(_err())
+        return self
 
     def dp_attach(self, comm, scal_dev_ptr=None, nscal=0):
         """data parallel: from now on the optimizer calls sum the gradient arena over the ranks of `comm` (a connected

@@ -391,3 +391,60 @@ def test_gan_iteration_vs_oracle():
             for i, L in enumerate(o_.layers[:-1]):
                 if L.w is not None and L.dw is not None:
                     L.w[...] = m_.w(i).numpy().reshape(L.w.shape); L.b[...] = m_.b(i).numpy().reshape(L.b.shape)
+
+
+# ------------------------------------------------------------------ model file (src/io/aio_model.cpp)
+def _lit(v):
+    """a number as the reference VM holds it: FP32 with bit 0 cleared (bit 0 tags objects, src/t4base.h:16-30 SCALAR)"""
+    return (np.array([v], np.float32).view(np.uint32) & np.uint32(0xFFFFFFFE)).view(np.float32)[0]
+
+
+def _chaos(n, scale):
+    """integration/scripts/*.4th `chaos` in numpy: x0 = 0.1 + 0.8 j/n, 20 x (x <- 4 x (1 - x)), - 0.5, * scale — every step one IEEE
+    FP32 operation (and every literal the VM's bit-0-cleared float), so the reference's tensor words produce the same bits"""
+    f = np.float32
+    j = np.arange(n, dtype=np.int64)
+    x = (f(1.0) * j.astype(np.float32) / f(n)).astype(np.float32)          # gradfill: v * j / n (t4math.cu:192)
+    x = (x * _lit(0.8)).astype(np.float32); x = (x + _lit(0.1)).astype(np.float32)
+    for _ in range(20):
+        y = ((x * f(-1.0)).astype(np.float32) + f(1.0)).astype(np.float32)
+        x = ((x * y).astype(np.float32) * f(4.0)).astype(np.float32)
+    return ((x - f(0.5)).astype(np.float32) * _lit(scale)).astype(np.float32)
+
+
+def test_model_file_matches_the_reference_byte_for_byte(tmp_path):
+    """Model::save writes the reference's model file: compared byte for byte with what the reference binary itself saves for the same
+    model and weights (when oracle/_ref/ten4 is present), and reloaded into a fresh model (parameter path of AIO::nload)."""
+    import os, subprocess
+    N = 4
+    def build():
+        return th.Model(N, 8, 8, 1).conv2d(0.5, 2).maxpool(2).relu().flatten().linear(6, 0.0).batchnorm().leakyrelu(0.1).linear(3, 0.0).softmax()
+    m = build()
+    # layers: 0 conv2d, 1 maxpool, 2 relu, 3 flatten, 4 linear, 5 batchnm, 6 leakyrl, 7 linear, 8 softmax
+    w = {(0, "w"): _chaos(18, 1.6), (0, "b"): _chaos(2, 0.2), (4, "w"): _chaos(6 * 32, 0.4), (4, "b"): _chaos(6, 0.2),
+         (7, "w"): _chaos(18, 0.5), (7, "b"): _chaos(3, 0.2)}
+    for (i, k), v in w.items():
+        (m.set_w if k == "w" else m.set_b)(i, v)
+    mine = str(tmp_path / "mine.t4")
+    m.save(mine)
+    data = open(mine, "rb").read()
+    assert data.startswith(b"\\ tensorForth v4.0 model\nbias=0.5, C=2, K=3, S=1, P=1conv2d \n2x2maxpool\nrelu   \nflatten\nbias=0, H=6linear \n")
+    assert data.endswith(b"\n---\n") and b"\n--- w.conv2d \n" + w[(0, "w")].tobytes() + b"\n--- b.conv2d \n" in data
+    # round trip into a fresh model
+    m2 = build().load(mine)
+    for (i, k) in w:
+        assert np.array_equal((m2.w(i) if k == "w" else m2.b(i)).numpy().ravel(), w[(i, k)])
+    assert np.array_equal(m2.w(5).numpy(), m.w(5).numpy())                  # batchnorm gamma
+    ref_bin = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ten4")
+    if not os.path.exists(ref_bin):
+        return
+    theirs = str(tmp_path / "ref.t4")
+    script = "\n".join([
+        "0 trace", ": lg copy -1 *= 1 += *= 4 *= ;", ": chaos gradfill 0.8 *= 0.1 += 19 for lg next 0.5 -= ;",
+        "%d 8 8 1 nn.model 0.5 2 conv2d 2 maxpool relu flatten 0.0 6 linear 0.1 batchnorm 0.1 leakyrelu 0.0 3 linear softmax constant md" % N,
+        "md", "1 3 3 2 tensor chaos 1.6 *= 0 nn.w=", "2 vector chaos 0.2 *= 0 nn.b=", "6 32 matrix chaos 0.4 *= 4 nn.w=", "6 vector chaos 0.2 *= 4 nn.b=",
+        "3 6 matrix chaos 0.5 *= 7 nn.w=", "3 vector chaos 0.2 *= 7 nn.b=", 's" %s" save' % theirs, "drop", "bye", ""])
+    p = subprocess.run([ref_bin], input=script, capture_output=True, text=True, timeout=120)
+    assert os.path.exists(theirs), p.stdout[-1500:] + p.stderr[-500:]
+    ref = open(theirs, "rb").read()
+    assert ref == data, "model file differs from the reference's: %r ... vs %r ..." % (ref[:200], data[:200])
