@@ -70,6 +70,8 @@ int         t4k_device_count(void);                    /* 0 when no CUDA device/
 int         t4k_sm_count(void);                        /* SMs of the current device    */
 int         t4k_sync(t4k_stream_t stream);             /* cudaStreamSynchronize        */
 long        t4k_launch_count(void);                    /* kernels launched by this library so far */
+int         t4k_set_workspace_bank(int bank);          /* 0 / 1: which set of library workspaces the following calls use — a caller that forks
+                                                          * work onto a second stream gives that stream its own bank; returns the previous one */
 int         t4k_set_pdl(int on);                       /* programmatic dependent launch for the short kernels (default off, or T4K_PDL=1); returns the previous setting */
 
 /* ---- elementwise: src/t4math.cu:134-234 ------------------------------------------- */

@@ -422,10 +422,14 @@ int Model::_bfused(int i) {                                // i = index of the b
     if (po.grad_fn != T4K_L_RELU || co.grad_fn != T4K_L_MAXPOOL || co.stride[0] != 2 || in.grad_fn != T4K_L_CONV) return 0;
     Tensor &dy = *_layers[i + 1];                          // gradient arriving at the block output
     Tensor &f = *in.grad[0], &df = *in.grad[2], &db = *in.grad[3], &dx = *in.grad[4];
-    int rc = t4k_conv_pool_relu_bwd(dy.data, ao.data, po.grad[4]->data, po.data, co.data, in.data, dx.data, f.data, df.data, db.data,
+    // _skip_flat_copy: the flatten backward (ao = dy) was issued on the side stream behind the dW GEMM that still reads ao
+    // (see backprop): passing dy as the copy's destination makes the kernel skip it
+    DU *flat_dst = (flat && _skip_flat_copy) ? dy.data : ao.data;
+    int rc = t4k_conv_pool_relu_bwd(dy.data, flat_dst, po.grad[4]->data, po.data, co.data, in.data, dx.data, f.data, df.data, db.data,
                                     in.N(), in.H(), in.W(), in.C(), co.H(), co.W(), co.C(), f.H(), in.stride[0], in.stride[2], train, ST);
     if (rc == T4K_ENOSUP) return 0;
     KCHK(rc);
+    _skip_flat_copy = false;
     return flat ? 4 : 3;
 }
 void Model::_fstep(Tensor &in, Tensor &out) {                             // forward.cu:83-113
@@ -497,10 +501,24 @@ Model &Model::backprop(Tensor &tgt) {
         if (_dp_early && _dp_pushed_from < 0 && i < _second_layer) _dp_push();     // every gradient but the first parameter layer's is final
         const int adv = (j > 0 && (fn == T4K_L_FLATTEN || fn == T4K_L_RELU)) ? _bfused(i) : 0;
         if (adv) { i -= adv; continue; }
-        if (skip_db && fn == T4K_L_LINEAR) { _blinear(*_layers[i], *_layers[i + 1], true); skip_db = false; }
+        if (_skip_flat_copy) {                              // the fused block did not take the flatten: rejoin before the per-layer path touches it
+            cudaStreamWaitEvent((cudaStream_t)ST, g_join, 0); _skip_flat_copy = false; _side_join = false;
+        }
+        if (fn == T4K_L_LINEAR && j > 0) {
+            // a flatten in front of the linear layer leaves a second copy of X in its own input tensor (flatten is a copy and its
+            // backward has not run yet): dW can read that copy while dX overwrites X in place — two independent GEMMs, forked
+            Tensor *xdup = (fuse && i > 0 && _layers[i - 1]->grad_fn == T4K_L_FLATTEN && _layers[i - 1]->data != _layers[i]->data &&
+                            _layers[i - 1]->numel == _layers[i]->numel) ? _layers[i - 1] : nullptr;
+            // when the conv->pool->relu->flatten block kernel comes next (it is the only other writer of the duplicate), the side
+            // branch also takes the flatten backward (duplicate = dX) and is joined at the end of backprop: dW runs under dX + conv block
+            const bool defer = xdup && i >= 4 && _layers[i - 2]->grad_fn == T4K_L_RELU && _layers[i - 3]->grad_fn == T4K_L_MAXPOOL &&
+                               _layers[i - 4]->grad_fn == T4K_L_CONV;
+            _blinear(*_layers[i], *_layers[i + 1], skip_db, xdup, defer); skip_db = false;
+        }
         else _bstep(*_layers[i], *_layers[i + 1], j == 0);
         i--;
     }
+    if (_side_join) { cudaStreamWaitEvent((cudaStream_t)ST, g_join, 0); _side_join = false; }      // side-stream branch of this backprop
     return *this;
 }
 void Model::_dp_push() {
@@ -552,8 +570,27 @@ int Model::_bconv(Tensor &in, Tensor &out) {                              // bac
     in = dx;                                                               // x = dX (overwrite)
     return 0;
 }
-int Model::_blinear(Tensor &in, Tensor &out, bool skip_db) {              // backprop.cu:194-254
+int Model::_blinear(Tensor &in, Tensor &out, bool skip_db, Tensor *xdup, bool defer) { // backprop.cu:194-254
     Tensor &w = *in.grad[0], &dw = *in.grad[2], &db = *in.grad[3];
+    if (xdup && train) {
+        // dW[E0,E1] += dY^T @ X (X read from its duplicate) on the side stream  ||  dX = dY @ W in place on the library stream
+        const int N = (int)in.N(), E0 = (int)out.HWC(), E1 = (int)in.HWC();
+        cudaStream_t st = (cudaStream_t)ST;
+        if (!skip_db) KCHK(t4k_dbias(out.data, db.data, N, E0, ST));
+        cudaEventRecord(g_fork, st); cudaStreamWaitEvent(g_stream2, g_fork, 0);
+        t4k_set_workspace_bank(1);
+        KCHK(t4k_gemm(out.data, xdup->data, dw.data, 1.0f, 1.0f, 1, 0, E0, E1, N, 1, 1, 0, 0, 0, (t4k_stream_t)g_stream2));
+        t4k_set_workspace_bank(0);
+        cudaEventRecord(g_join, g_stream2);
+        KCHK(t4k_gemm(out.data, w.data, in.data, 1.0f, 0.0f, 0, 0, N, E1, E0, 1, 1, 0, 0, 0, ST));
+        if (!defer) { cudaStreamWaitEvent(st, g_join, 0); return 0; }
+        // deferred join: the flatten backward (duplicate <- dX) follows dW on the side stream, once dX is there
+        cudaEventRecord(g_fork, st); cudaStreamWaitEvent(g_stream2, g_fork, 0);
+        KCHK(t4k_copy(in.data, xdup->data, in.numel, (t4k_stream_t)g_stream2));
+        cudaEventRecord(g_join, g_stream2);
+        _side_join = true; _skip_flat_copy = true;
+        return 0;
+    }
     // dX overwrites the layer input in place; dW needs X first → t4k_linear_bwd orders dW before dX,
     // and dX = dY@W does not read X, so in.data may be both X and dX.
     KCHK(t4k_linear_bwd_ex(in.data, w.data, out.data, in.data, dw.data, db.data, in.N(), (int)out.HWC(), (int)in.HWC(), train, skip_db, ST));

@@ -34,13 +34,15 @@ int check_launch() {
 // Regrowth frees the old block with cudaFree (implicit device sync) — only happens when a
 // larger problem than ever before arrives.
 #define MAX_DEV  16
-#define MAX_SLOT 8
+#define MAX_SLOT 16          // 8 slots x 2 banks (bank 1: work forked onto a side stream, see t4k_set_workspace_bank)
+static int g_ws_bank = 0;
 static void  *g_ws[MAX_DEV][MAX_SLOT];
 static size_t g_ws_sz[MAX_DEV][MAX_SLOT];
 static std::mutex g_mu;
 
 void *workspace(size_t bytes, int slot) {
     int dev = 0;
+    slot += 8 * g_ws_bank;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= MAX_DEV || slot >= MAX_SLOT) return nullptr;
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_ws_sz[dev][slot] < bytes) {
@@ -103,6 +105,8 @@ int t4k_sm_count(void) { return t4k::sm_count(); }
 int t4k_sync(t4k_stream_t s) { return (int)cudaStreamSynchronize((cudaStream_t)s); }
 
 long t4k_launch_count(void) { return t4k::g_launches; }
+
+int t4k_set_workspace_bank(int bank) { int was = t4k::g_ws_bank; t4k::g_ws_bank = bank ? 1 : 0; return was; }
 
 int t4k_set_pdl(int on) { int was = t4k::g_pdl; t4k::g_pdl = on ? 1 : 0; return was; }
 

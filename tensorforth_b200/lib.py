@@ -31,6 +31,7 @@ PROTOTYPES = {
     "t4k_sync": (_i, [_p]),
     "t4k_launch_count": (C.c_long, []),
     "t4k_set_pdl": (_i, [_i]),
+    "t4k_set_workspace_bank": (_i, [_i]),
     "t4k_map": (_i, [_i, _p, _f, _l, _p]),
     "t4k_ts_op": (_i, [_i, _p, _f, _p, _l, _p]),
     "t4k_tt_op": (_i, [_i, _p, _p, _p, _l, _i, _i, _p]),
