@@ -129,6 +129,9 @@ int t4k_linear_act_fwd(int layer, const float *X, const float *W, const float *B
 /* classifier head, forward: small linear (E0 <= 32, W <= 40 KB) + bias + row softmax in one launch (forward.cu:158-198,231-243):
  * Y = X @ W^T + B, P = softmax(Y).  T4K_ENOSUP when the head is not small (caller: t4k_linear_fwd + t4k_softmax_fwd) */
 int t4k_mlp_head_fwd(const float *X, const float *W, const float *B, float *Y, float *P, int N, int E0, int E1, t4k_stream_t s);
+/* the same, with the probabilities also written to Pdup [N,E0] (may be NULL): Model::backprop turns P into p - y in place, so a
+ * caller that wants the loss kernel to overlap the backward pass (second stream) lets it read the duplicate */
+int t4k_mlp_head_fwd_dup(const float *X, const float *W, const float *B, float *Y, float *P, float *Pdup, int N, int E0, int E1, t4k_stream_t s);
 /* k_activate (nmath.cu:37-70, forward.cu:201-209): writes O and the saved derivative/mask F.
  * layer in RELU,TANH,SIGMOID,SELU,LEAKYRL,ELU,DROPOUT; for DROPOUT F holds U(0,1] on entry. */
 int t4k_activate_fwd(int layer, const float *I, float *O, float *F, float alpha, int64_t n, t4k_stream_t s);

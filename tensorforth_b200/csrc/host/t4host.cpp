@@ -250,7 +250,7 @@ Model::~Model() {
         Tensor::destroy(*t);
     }
     if (_own_hot && _hot) Tensor::destroy(*_hot);
-    Runtime::free(_G); Runtime::free(_DG); Runtime::free(_M); Runtime::free(_V); Runtime::free(_seg_dev); Runtime::free(_cnt_dev);
+    Runtime::free(_G); Runtime::free(_DG); Runtime::free(_M); Runtime::free(_V); Runtime::free(_seg_dev); Runtime::free(_cnt_dev); Runtime::free(_pdup);
     _drop_graphs();
     if (_loss_pin) { cudaFreeHost(_loss_pin); for (int b = 0; b < 2; b++) cudaEventDestroy((cudaEvent_t)_loss_ev[b]); }
 }
@@ -383,7 +383,14 @@ int Model::_ffused_linear(size_t i) {
     const int N = (int)lo.N(), E0 = (int)lo.HWC(), E1 = (int)in.HWC();
     const t4_layer fn = lo.grad_fn;
     int rc;
-    if (fn == T4K_L_SOFTMAX) rc = t4k_mlp_head_fwd(in.data, in.grad[0]->data, in.grad[1]->data, lo.data, ao.data, N, E0, E1, ST);
+    if (fn == T4K_L_SOFTMAX) {
+        DU *dup = nullptr;
+        if (_want_pdup && _pdup && i + 3 == n) {           // the model's output layer, inside step_graph: keep a copy of p for the loss
+            dup = _pdup;                                   // allocated by _step_graph, outside any stream capture
+        }
+        rc = t4k_mlp_head_fwd_dup(in.data, in.grad[0]->data, in.grad[1]->data, lo.data, ao.data, dup, N, E0, E1, ST);
+        _pdup_valid = (rc == 0 && dup != nullptr);
+    }
     else if (mask_act(fn) || fn == T4K_L_SIGMOID)
         rc = t4k_linear_act_fwd(fn, in.data, in.grad[0]->data, in.grad[1]->data, lo.data, ao.data, lo.grad[4]->data, lo.xparm, N, E0, E1, ST);
     else return 0;
@@ -864,12 +871,24 @@ void Model::_drop_graphs() {
 int Model::_step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd, const StepExtra &x) {
     auto run = [&]() {
         if (x.ds) x.ds->commit_launch(x.simg, x.slab, x.n, tgt.data, (int)(*this)[-1].HWC());   // dataset feeding: normalise + one-hot
+        _want_pdup = loss_dev != nullptr; _pdup_valid = false;
         forward(input);
-        if (loss_dev) loss_async(lop, tgt, loss_dev);
+        _want_pdup = false;
+        // the loss does not feed the backward pass: when the head kernel left a duplicate of the softmax output (backprop overwrites
+        // the original with p - y), the loss kernel — and its read-back — run on the side stream under the backward kernels
+        const bool side_loss = loss_dev && _pdup_valid && tgt.numel == (*this)[-1].numel;
+        if (side_loss) {
+            cudaEventRecord(g_fork, (cudaStream_t)ST); cudaStreamWaitEvent(g_stream2, g_fork, 0);
+            KCHK(t4k_loss(lop, _pdup, tgt.data, (int64_t)tgt.numel, (int)(*this)[-1].N(), loss_dev, (t4k_stream_t)g_stream2));
+            if (x.loss_pin && !_comm) cudaMemcpyAsync(x.loss_pin, loss_dev, sizeof(DU), cudaMemcpyDeviceToHost, g_stream2);
+            cudaEventRecord(g_join, g_stream2);
+            _side_join = true;
+        }
+        else if (loss_dev) loss_async(lop, tgt, loss_dev);
         // loss read-back: the 4-byte D2H takes the copy engine ~6 us — on a branch of its own (side stream) it overlaps backprop
         // instead of delaying the next step.  With a communicator attached the loss is only final after the exchange (the ranks'
         // loss sums ride in it), so there it stays at the end of the step.
-        const bool early_loss = x.loss_pin && loss_dev && !_comm;
+        const bool early_loss = x.loss_pin && loss_dev && !_comm && !side_loss;
         if (early_loss) {
             cudaEventRecord(g_fork, (cudaStream_t)ST); cudaStreamWaitEvent(g_stream2, g_fork, 0);
             cudaMemcpyAsync(x.loss_pin, loss_dev, sizeof(DU), cudaMemcpyDeviceToHost, g_stream2);
@@ -881,9 +900,11 @@ int Model::_step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4
         if ((int)op >= 0) {                                // op < 0 — data parallel over NCCL: the caller all-reduces DG, then calls the optimizer
             switch (op) { case OPTI_SGD: case OPTI_SGDM: sgd(lr, b1); break; case OPTI_ADAM: adam(lr, b1, b2); break; default: adamw(lr, wd, b1, b2); }
         }
+        if (_side_join) { cudaStreamWaitEvent((cudaStream_t)ST, g_join, 0); _side_join = false; }   // side-stream work of this step (backprop joins its own)
         if (early_loss) cudaStreamWaitEvent((cudaStream_t)ST, g_join, 0);
-        else if (x.loss_pin && loss_dev) cudaMemcpyAsync(x.loss_pin, loss_dev, sizeof(DU), cudaMemcpyDeviceToHost, (cudaStream_t)ST);
+        else if (x.loss_pin && loss_dev && !(side_loss && !_comm)) cudaMemcpyAsync(x.loss_pin, loss_dev, sizeof(DU), cudaMemcpyDeviceToHost, (cudaStream_t)ST);
     };
+    if (loss_dev && !_pdup) _pdup = (DU*)Runtime::alloc((size_t)(*this)[-1].numel * sizeof(DU) + 64);   // not inside the capture below
     bool has_dropout = false;
     for (Tensor *t : _layers) if (t->grad_fn == T4K_L_DROPOUT) has_dropout = true;
     U64 key[12] = {0}; float f4[4] = {lr, b1, b2, wd};

@@ -164,6 +164,7 @@ class Model {
     int     _second_layer = 0; int64_t _first_end = 0;                    // arena layout: end of the first parameter layer's segments, index of the next parameter layer
     bool    _dp_early = false, _dp_join = false; int64_t _dp_pushed_from = -1;   // split exchange inside step_graph (early push on the side stream)
     void    _dp_push();
+    DU     *_pdup = nullptr; bool _want_pdup = false, _pdup_valid = false;   // step_graph: duplicate of the softmax output for the side-stream loss
     bool    _side_join = false, _skip_flat_copy = false;   // backprop: work pending on the side stream / flatten copy already issued there
     DU     *_loss_pin = nullptr; void *_loss_ev[2] = {nullptr, nullptr}; unsigned _tstep = 0;   // train_step read-back ring
     std::vector<Tensor*> _layers;      ///< layer i holds that layer's INPUT; last = output

@@ -88,7 +88,7 @@ __device__ __forceinline__ float warp_treduce32(float (&v)[32], int lane) {
 // warp per row, W (E0 x E1, E0 <= 32) in shared memory; lane k ends up owning class k.
 #define HEAD_JMAX 8                      // E1 <= 32 * HEAD_JMAX
 __global__ void __launch_bounds__(T4K_THREADS) k_head_fwd(const float *__restrict__ X, const float *__restrict__ W, const float *__restrict__ B,
-                                                          float *Y, float *P, int N, int E0, int E1) {
+                                                          float *Y, float *P, float *P2, int N, int E0, int E1) {
     extern __shared__ float sW[];                      // [E0][E1]
     pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     for (int t = threadIdx.x; t < E0 * E1; t += blockDim.x) sW[t] = __ldg(W + t);
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(T4K_THREADS) k_head_fwd(const float *__restric
         const float mx = warp_max(on ? y : -FLT_MAX);  // k_softmax_small (nmath.cu:74-118): exp(x - max) / Σ
         const float ex = on ? __expf(y - mx) : 0.0f;
         const float sm = warp_sum(ex);
-        if (on) { Y[(int64_t)row * E0 + lane] = y; P[(int64_t)row * E0 + lane] = ex / sm; }
+        if (on) { const float pv = ex / sm; Y[(int64_t)row * E0 + lane] = y; P[(int64_t)row * E0 + lane] = pv; if (P2) P2[(int64_t)row * E0 + lane] = pv; }
     }
 }
 
@@ -285,12 +285,15 @@ extern "C" int t4k_linear_bwd(const float *X, const float *W, const float *dY, f
 }
 
 extern "C" int t4k_mlp_head_fwd(const float *X, const float *W, const float *B, float *Y, float *P, int N, int E0, int E1, t4k_stream_t s) {
+    return t4k_mlp_head_fwd_dup(X, W, B, Y, P, nullptr, N, E0, E1, s);
+}
+extern "C" int t4k_mlp_head_fwd_dup(const float *X, const float *W, const float *B, float *Y, float *P, float *Pdup, int N, int E0, int E1, t4k_stream_t s) {
     if (!X || !W || !B || !Y || !P || N < 1 || E0 < 1 || E1 < 1) return T4K_EINVAL;
     if (E0 > 32 || (size_t)E0 * E1 * sizeof(float) > 40 * 1024) return T4K_ENOSUP;
     const int rows_per_cta = T4K_THREADS / 32;
     int g = (N + rows_per_cta - 1) / rows_per_cta;
     if (g > 2 * sm_count()) g = 2 * sm_count();
-    launch_pdl(k_head_fwd, dim3(g), dim3(T4K_THREADS), (size_t)E0 * E1 * sizeof(float), STRM(s), X, W, B, Y, P, N, E0, E1);
+    launch_pdl(k_head_fwd, dim3(g), dim3(T4K_THREADS), (size_t)E0 * E1 * sizeof(float), STRM(s), X, W, B, Y, P, Pdup, N, E0, E1);
     return check_launch();
 }
 extern "C" int t4k_mlp_head_bwd(float *P, const float *T, float *Ylin, float *X2, const float *F1, float *Y1, const float *W,

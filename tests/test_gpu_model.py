@@ -448,3 +448,25 @@ def test_model_file_matches_the_reference_byte_for_byte(tmp_path):
     assert os.path.exists(theirs), p.stdout[-1500:] + p.stderr[-500:]
     ref = open(theirs, "rb").read()
     assert ref == data, "model file differs from the reference's: %r ... vs %r ..." % (ref[:200], data[:200])
+
+
+def test_step_graph_captured_on_its_first_call():
+    """bench.py's order: eager steps first (arenas built, _iter > 0), so the FIRST step_graph call captures — nothing the step needs
+    (workspaces, the softmax duplicate for the side-stream loss) may be allocated inside the capture"""
+    N = 16
+    rng = np.random.default_rng(9)
+    x = (rng.random((N, 28, 28, 1), dtype=np.float32) * 2 - 1).astype(np.float32); y = orc.onehot(rng.integers(0, 10, N), 10)
+    ga, _, *_ = build_pair("mnist", N)
+    gb, _, *_ = build_pair("mnist", N)
+    X, Y = th.Tensor.from_numpy(x), th.Tensor.tensor(N, 1, 10, 1, y)
+    la, lb = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    pa, pb = C.c_void_p(la.data_ptr()), C.c_void_p(lb.data_ptr())
+    for m_, p_ in ((ga, pa), (gb, pb)):
+        for _ in range(2):
+            m_.forward(X); m_.loss_async(t4.LOSS_CE, Y, p_); m_.backprop(Y); m_.adam(0.001)
+    for step in range(4):
+        ga.forward(X); ga.loss_async(t4.LOSS_CE, Y, pa); ga.backprop(Y); ga.adam(0.001)
+        assert gb.step_graph(X, Y, t4.LOSS_CE, pb, optimizer=2, lr=0.001) == 0
+        th.sync()
+        assert float(la.cpu()[0]) == float(lb.cpu()[0])
+    assert np.array_equal(ga.w(4).numpy(), gb.w(4).numpy())
