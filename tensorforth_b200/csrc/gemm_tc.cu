@@ -85,6 +85,10 @@ struct TcP {
     int kt_per_split;            // k blocks per gridDim.z slice
     int splits;
     float *part;                 // partials [splits][M*N] when splits > 1
+    // tail split (splits == 1, 1-D grid): tiles [0, tail_first) run whole; each tile from tail_first on is cut into tail_split
+    // K slices that write raw accumulators to tail_part[slice][tile - tail_first][128 x BN] (k_tail_fin adds them into O)
+    int gx, tail_first, tail_split, tail_kt_per, ntail;
+    float *tail_part;
 };
 
 // Accumulation accuracy: the tensor core's FP32 accumulator add TRUNCATES (round toward zero), so a chain of n MMAs
@@ -110,9 +114,20 @@ __global__ void __launch_bounds__(320, 1) k_gemm_tc(TcP p) {
     uint32_t *tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt = blockIdx.y, nt = blockIdx.x, zs = blockIdx.z;
-    const int kt0 = zs * p.kt_per_split;
-    const int kt1 = min(p.KT, kt0 + p.kt_per_split);
+    int mt = blockIdx.y, nt = blockIdx.x, zs = blockIdx.z;
+    int kt0 = zs * p.kt_per_split;
+    int kt1 = min(p.KT, kt0 + p.kt_per_split);
+    int tail_slot = -1;                                  // >= 0: this CTA computes a K slice of a tail tile
+    if (p.tail_split > 0) {
+        int tile = blockIdx.x; zs = 0; kt0 = 0; kt1 = p.KT;
+        if (tile >= p.tail_first) {
+            const int r = tile - p.tail_first, z = r % p.tail_split;
+            tile = p.tail_first + r / p.tail_split;
+            kt0 = z * p.tail_kt_per; kt1 = min(p.KT, kt0 + p.tail_kt_per);
+            tail_slot = z * p.ntail + (tile - p.tail_first);
+        }
+        mt = tile / p.gx; nt = tile % p.gx;
+    }
     const int nkb = kt1 - kt0;
     const int nchunk = (nkb + DRAIN_KB - 1) / DRAIN_KB;
 
@@ -215,15 +230,17 @@ __global__ void __launch_bounds__(320, 1) k_gemm_tc(TcP p) {
             if (lane == 0) mbar_arrive(aempty0 + 8 * b);                     // this warp's slice of accumulator b is free again
         }
         float *dst; float alpha = p.alpha, beta = p.beta;
-        if (p.splits > 1) { dst = p.part + (int64_t)zs * p.M * p.N; alpha = 1.0f; beta = 0.0f; }
+        int64_t ld = p.N; int orow = row, cbase = nt * BN, Mlim = p.M, Nlim = p.N;
+        if (tail_slot >= 0) { dst = p.tail_part + (int64_t)tail_slot * TBM * BN; alpha = 1.0f; beta = 0.0f; ld = BN; orow = q * 32 + lane; cbase = 0; Mlim = TBM; Nlim = BN; }
+        else if (p.splits > 1) { dst = p.part + (int64_t)zs * p.M * p.N; alpha = 1.0f; beta = 0.0f; }
         else dst = p.O;
-        const bool n_vec = ((p.N & 3) == 0) && ((((uintptr_t)dst) & 15) == 0);
+        const bool n_vec = ((ld & 3) == 0) && ((((uintptr_t)dst) & 15) == 0);
         #pragma unroll
         for (int g = 0; g < CW / 32; g++) {
-            const int col0 = nt * BN + h * CW + g * 32;
-            if (row < p.M && col0 < p.N) {
-                float *o = dst + (int64_t)row * p.N + col0;
-                if (n_vec && col0 + 32 <= p.N) {
+            const int col0 = cbase + h * CW + g * 32;
+            if (orow < Mlim && col0 < Nlim) {
+                float *o = dst + (int64_t)orow * ld + col0;
+                if (n_vec && col0 + 32 <= Nlim) {
                     #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 r = make_float4(acc[g * 32 + j] * alpha, acc[g * 32 + j + 1] * alpha,
@@ -237,7 +254,7 @@ __global__ void __launch_bounds__(320, 1) k_gemm_tc(TcP p) {
                 } else {
                     #pragma unroll
                     for (int j = 0; j < 32; j++) {
-                        if (col0 + j < p.N) {
+                        if (col0 + j < Nlim) {
                             float r = acc[g * 32 + j] * alpha;
                             if (beta != 0.0f) r += o[j] * beta;
                             o[j] = r;
@@ -263,6 +280,24 @@ __global__ void __launch_bounds__(T4K_THREADS) k_splitk_fin_tc(const float *__re
         float s = 0.0f;
         for (int k = 0; k < splits; k++) s += part[(int64_t)k * MN + e];
         O[e] = (beta == 0.0f) ? s * alpha : s * alpha + O[e] * beta;
+    }
+}
+
+// tail fix-up: O[tile] = alpha * Σ_slice tail_part[slice][tile] + beta * O[tile] for the tiles that were cut along K
+__global__ void __launch_bounds__(T4K_THREADS) k_tail_fin(const float *__restrict__ part, float *O, float alpha, float beta,
+                                                          int M, int N, int BN, int gx, int tail_first, int ntail, int nslice) {
+    const int t = blockIdx.y, tile = tail_first + t, mt = tile / gx, nt = tile % gx;
+    const int64_t tile_flts = (int64_t)TBM * BN;
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) * 4; e < tile_flts; e += gridDim.x * blockDim.x * 4) {
+        const int r = e / BN, c = e % BN;
+        const int gm = mt * TBM + r, gn = nt * BN + c;
+        if (gm >= M || gn >= N) continue;
+        float4 sum = ldg4(part + (int64_t)t * tile_flts + e);
+        for (int z = 1; z < nslice; z++) { const float4 v = ldg4(part + ((int64_t)z * ntail + t) * tile_flts + e); sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w; }
+        float *o = O + (int64_t)gm * N + gn;
+        const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
+        #pragma unroll
+        for (int j = 0; j < 4; j++) if (gn + j < N) o[j] = (beta == 0.0f) ? sv[j] * alpha : sv[j] * alpha + o[j] * beta;
     }
 }
 
@@ -312,14 +347,31 @@ int gemm_tc(const float *A, const float *B, float *O, float alpha, float beta, i
     }
     int kt_per = (KT + splits - 1) / splits;
     splits = (KT + kt_per - 1) / kt_per;
-    TcP p{PA, PB, O, alpha, beta, M, N, KT, kt_per, splits, nullptr};
+    TcP p{PA, PB, O, alpha, beta, M, N, KT, kt_per, splits, nullptr, gx, 0, 0, 0, 0, nullptr};
     if (splits > 1) {
         p.part = (float*)workspace((size_t)splits * M * N * 4, 3);
         if (!p.part) return T4K_ENOMEM;
     }
     dim3 grid(gx, gy, splits);
+    // Wave quantisation: T tiles on S SMs (1 CTA / SM) take ceil(T/S) waves; 4096^3 is 512 tiles on 148 SMs = 3.46 -> 4 waves.  When the
+    // last wave is less than half full, its tiles are cut into K slices so that it fills the machine and takes 1/slices of the time
+    // (the slices' accumulators go through a small workspace and k_tail_fin; the full waves are untouched).
+    const int T = gx * gy, rem = T % sms;
+    if (splits == 1 && T > sms && rem > 0 && 2 * rem <= sms && KT >= 16) {
+        int sl = sms / rem; if (sl > 4) sl = 4;
+        p.tail_first = T - rem; p.tail_split = sl; p.tail_kt_per = (KT + sl - 1) / sl; p.ntail = rem;
+        p.tail_split = (KT + p.tail_kt_per - 1) / p.tail_kt_per;
+        p.tail_part = (float*)workspace((size_t)p.tail_split * rem * TBM * BN * 4, 3);
+        if (!p.tail_part) return T4K_ENOMEM;
+        grid = dim3(p.tail_first + rem * p.tail_split, 1, 1);
+    }
     int rc = (BN == 256) ? launch_tc<256, 2>(p, grid, st) : launch_tc<128, 3>(p, grid, st);
-    if (rc || splits == 1) return rc;
+    if (rc) return rc;
+    if (p.tail_split > 0) {
+        k_tail_fin<<<dim3(8, p.ntail), T4K_THREADS, 0, st>>>(p.tail_part, O, alpha, beta, M, N, BN, gx, p.tail_first, p.ntail, p.tail_split);
+        return check_launch();
+    }
+    if (splits == 1) return rc;
     const int64_t MN = (int64_t)M * N;
     k_splitk_fin_tc<<<stream_grid(MN), T4K_THREADS, 0, st>>>(p.part, O, alpha, beta, MN, splits);
     return check_launch();

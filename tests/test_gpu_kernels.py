@@ -224,6 +224,21 @@ def test_gemm_tcf_layer_shapes_vs_f64(tA, tB, M, N, K):
         assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-6
 
 
+@pytest.mark.parametrize("tA,tB", [(0, 0), (1, 1)])
+def test_gemm_tc_tail_split_ragged(tA, tB):
+    """170 tiles on 148 SMs: the 22 tiles of the last wave are cut into K slices (gemm_tc.cu tail split); ragged M and N, alpha/beta"""
+    M, N, K = 2100, 2400, 1024
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.rand((K, M) if tA else (M, K), device="cuda", generator=g) * 2 - 1
+    B = torch.rand((N, K) if tB else (K, N), device="cuda", generator=g) * 2 - 1
+    O0 = torch.rand(M, N, device="cuda", generator=g) * 2 - 1
+    o = O0.clone()
+    ok(lib().t4k_gemm_ex(t4.GEMM_TC, ptr(A), ptr(B), ptr(o), 0.5, 2.0, tA, tB, M, N, K, 1, 1, 0, 0, 0, None), "gemm_tc tail")
+    a = (A.double().T if tA else A.double()); b = (B.double().T if tB else B.double())
+    ref = (0.5 * (a @ b) + 2.0 * O0.double()).cpu().numpy()
+    assert_close(o.cpu().numpy(), ref, rtol=1e-5, what="tail split vs f64")
+
+
 def test_gemm_4096_property():
     # BASELINE size (config 2): size-independent checks — linearity in alpha and the row-sum identity
     # (A@B)·1 = A·(B·1), evaluated in float64 on the host in O(n^2).
