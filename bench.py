@@ -185,6 +185,65 @@ def cpu_port_baseline(steps=4, batch=BATCH):
     return batch * n / dt, cores, "%d train steps of N=%d (%.1f s) with the C oracle, OpenMP" % (n, batch, dt)
 
 
+# --------------------------------------------------------------------------------------- conv sweep (BASELINE config 5)
+def conv_extra(t4, L, torch, dist, rank, world, local, lib_stream, st, pk):
+    """conv2d 3x3 s1 p1, NHWC 8192 x 56 x 56 x 64 -> 64, forward + backward, the 8192 samples sharded over the ranks (strong
+    scaling: 8192 / world per GPU, no exchange in forward; backward sum-all-reduces dF, dB = 36 928 floats over the peer-store
+    exchange).  3xTF32 implicit GEMM on tcgen05: tensor-bound; the HBM figure is the metric BASELINE.json names."""
+    import ctypes as C
+    from tensorforth_b200 import dp as t4dp
+    NT = 8192
+    cn = NT // world
+    p = lambda t: C.c_void_p(t.data_ptr())
+    f32 = lambda *s: torch.empty(*s, device="cuda").uniform_(-1, 1)
+    Ic, Fc, Bc, Oc = f32(cn, 56, 56, 64), f32(64, 3, 3, 64) * 0.1, f32(64), f32(cn, 56, 56, 64)
+    dXc = f32(cn, 56, 56, 64)
+    dFB = torch.zeros(64 * 9 * 64 + 64, device="cuda")           # dF | dB contiguous: one exchange
+    dFc, dBc = dFB[:64 * 9 * 64], dFB[64 * 9 * 64:]
+    comm = t4dp.PeerComm(dFB.numel()) if world > 1 else None
+
+    def kt(fn, iters):
+        for _ in range(2):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(lib_stream)
+        for _ in range(iters):
+            fn()
+        b.record(lib_stream); torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / iters
+        if world > 1:
+            t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.cpu()[0])
+        return ms * 1e3
+
+    def bwd():
+        t4.check(L.t4k_conv2d_bwd(p(Ic), p(Oc), p(Fc), p(dXc), p(dFc), p(dBc), cn, 56, 56, 64, 56, 56, 64, 3, 1, 1, 1, st), "conv bwd")
+        if comm is not None:
+            t4.check(L.t4k_allreduce_sum(comm.handle, p(dFB), dFB.numel(), st), "dF exchange")
+    usf = kt(lambda: t4.check(L.t4k_conv2d_fwd(p(Ic), p(Fc), p(Bc), p(Oc), cn, 56, 56, 64, 56, 56, 64, 3, 1, 1, st), "conv fwd"), 4)
+    usb = kt(bwd, 3)
+    if comm is not None:
+        assert comm.status() == 0
+    if rank != 0:
+        return None
+    n_el = NT * 56 * 56 * 64
+    fb = (2 * n_el + Fc.numel()) * 4                           # whole job: read I once, write O once
+    bb = (3 * n_el + 2 * Fc.numel()) * 4                       # read I, dO; write dX; dF
+    fl = 2.0 * NT * 56 * 56 * 64 * 64 * 9
+    tf32_peak = pk["bf16_tflops"] / 2
+    return {"samples_total": NT, "samples_per_gpu": cn, "fwd_ms": round(usf / 1e3, 3), "bwd_ms": round(usb / 1e3, 3),
+            "fwd_GBps": round(fb / usf / 1e3, 1), "bwd_GBps": round(bb / usb / 1e3, 1),
+            "fwd_tflops": round(fl / usf / 1e6, 2), "bwd_tflops": round(2 * fl / usb / 1e6, 2),
+            "roofline": {"bound": "hbm", "achieved": round(fb / usf / 1e3 / world, 1), "peak": pk["hbm_gbs"], "unit": "GB/s per GPU",
+                         "frac": round(fb / usf / 1e3 / world / pk["hbm_gbs"], 4)},
+            "roofline_tensor": {"bound": "tensor", "achieved": round(fl / usf / 1e6 / world, 1), "peak": round(tf32_peak / 3, 1), "unit": "TFLOP/s per GPU",
+                                "frac": round(fl / usf / 1e6 / world / (tf32_peak / 3), 4)},
+            "note": "whole-job numbers over %d GPU(s), max over ranks; 3xTF32 implicit GEMM (FP32-grade): tensor-bound, the HBM fraction is shown because "
+                    "BASELINE.json names it; backward includes the dF/dB exchange" % world}
+
+
 # --------------------------------------------------------------------------------------- GAN (BASELINE config 4)
 def gan_extra(th, t4, L, torch, dist, rank, world, local, lib_stream, iters=50, warm=5):
     """train_d + train_g of examples/t4_40b.4th:60-67 at N=1024 per GPU on synthetic 28x28 data; data parallel: each model's
@@ -417,8 +476,14 @@ def main():
            "note": "per step: U8 pixels + U8 labels from pinned host memory -> async H2D (copy stream, double buffered) -> on-device normalise "
                    "(u8-128)/128 + one-hot (1 launch) -> train step -> loss D2H read on the host (pipelined by one step); one host call per iteration"}
 
-    gan = None
+    gan = conv = None
     if not args.no_extras:
+        try:
+            conv = conv_extra(t4, L, torch, dist, rank, world, local, lib_stream, C.c_void_p(th.stream()), pk)
+        except Exception as e:
+            conv = {"unavailable": repr(e)[:200]}
+            sys.stderr.write("conv extra failed: %r\n" % (e,))
+        torch.cuda.empty_cache()
         try:
             gan = gan_extra(th, t4, L, torch, dist, rank, world, local, lib_stream)
         except Exception as e:                                  # extras never take the headline line down
@@ -537,22 +602,9 @@ def main():
                                        "note": "peak = measured BF16 %.0f /2 (TF32) /3 (3 MMAs per product for FP32-grade accuracy); "
                                                "vs plain TF32 peak: %.3f" % (pk["bf16_tflops"], tf / tf32_peak)}}
         del A, B_, Oo
-        cn = 512                                               # samples of config 5 per launch (411 MB per activation tensor: > L2)
-        Ic, Fc, Bc, Oc = f32(cn, 56, 56, 64), f32(64, 3, 3, 64), f32(64), f32(cn, 56, 56, 64)
-        dXc, dFc, dBc = f32(cn, 56, 56, 64), f32(64, 3, 3, 64), f32(64)
-        usf = kt(lambda: L.t4k_conv2d_fwd(p(Ic), p(Fc), p(Bc), p(Oc), cn, 56, 56, 64, 56, 56, 64, 3, 1, 1, st), iters=5)
-        usb = kt(lambda: L.t4k_conv2d_bwd(p(Ic), p(Oc), p(Fc), p(dXc), p(dFc), p(dBc), cn, 56, 56, 64, 56, 56, 64, 3, 1, 1, 1, st), iters=5)
-        fb = (2 * Ic.numel() + Fc.numel()) * 4
-        bb = (3 * Ic.numel() + 2 * Fc.numel()) * 4
-        fl = 2.0 * cn * 56 * 56 * 64 * 64 * 9
-        ex["conv2d_3x3_64"] = {"samples": cn, "fwd_ms": round(usf / 1e3, 3), "bwd_ms": round(usb / 1e3, 3),
-                               "fwd_GBps": round(fb / usf / 1e3, 1), "bwd_GBps": round(bb / usb / 1e3, 1),
-                               "fwd_tflops": round(fl / usf / 1e6, 2), "bwd_tflops": round(2 * fl / usb / 1e6, 2),
-                               "roofline": {"bound": "hbm", "achieved": round(fb / usf / 1e3, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                            "frac": round(fb / usf / 1e3 / pk["hbm_gbs"], 4)},
-                               "roofline_tensor": {"bound": "tensor", "achieved": round(fl / usf / 1e6, 1), "peak": round(tf32_peak / 3, 1), "unit": "TFLOP/s", "frac": round(fl / usf / 1e6 / (tf32_peak / 3), 4)},
-                               "note": "NHWC, N=%d of the 8192-sample config per launch (per-sample cost is size independent); 3xTF32 implicit GEMM: tensor-bound, HBM fraction shown for the metric" % cn}
         out["extras"] = ex
+    if conv is not None:
+        out.setdefault("extras", {})["conv2d_3x3_64"] = conv
     if gan is not None:
         out.setdefault("extras", {})["gan_t4_40b"] = gan
     if not args.no_cpu_baseline:
