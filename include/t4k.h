@@ -61,7 +61,10 @@ enum t4k_rand_opt { T4K_UNIFORM = 0, T4K_NORMAL = 1 };
 /* GEMM engine selection for t4k_gemm_ex (0 = automatic) */
 enum t4k_gemm_engine { T4K_GEMM_AUTO = 0, T4K_GEMM_SIMT = 1,   /* FP32 FMA (gemm_simt.cu) */
                        T4K_GEMM_TC = 2,                        /* tcgen05 3xTF32, packed operand planes (gemm_tc.cu): large problems */
-                       T4K_GEMM_TCF = 3 };                     /* tcgen05 3xTF32, split fused into the kernel, one launch (gemm_tcf.cu): layer-sized problems */
+                       T4K_GEMM_TCF = 3,                       /* tcgen05 3xTF32, split fused into the kernel, one launch (gemm_tcf.cu): layer-sized problems */
+                       T4K_GEMM_TC_BF16X3 = 4 };               /* tcgen05 BF16x3 (a = hi + lo in bf16; hi*hi + hi*lo + lo*hi): twice the MMA rate of 3xTF32;
+                                                                * measured 4.1e-6 of the result's rms at K=4096 (3xTF32: 1.8e-6; the reference's FP32-FMA
+                                                                * accumulation itself: ~3.8e-6).  AUTO takes it for M*N*K >= 2e10 only (T4K_GEMM_BIG=tf32: never) */
 
 /* ---- library / device ------------------------------------------------------------- */
 int         t4k_version(void);

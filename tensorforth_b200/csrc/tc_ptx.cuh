@@ -2,6 +2,7 @@
 // tcgen05 (alloc / mma / commit / ld / st / fences), UMMA shared-memory + instruction descriptors.
 #pragma once
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace t4k {
 
@@ -53,6 +54,17 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 // A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// kind::f16 with BF16 operands: a_format [7,10) = 1 (BF16), b_format [10,13) = 1, D = F32
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
