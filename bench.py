@@ -275,18 +275,34 @@ def gan_extra(th, t4, L, torch, dist, rank, world, local, lib_stream, iters=50, 
     n0 = L.t4k_launch_count(); it(); launches = L.t4k_launch_count() - n0
     for _ in range(warm):
         it()
+
+    def timed(fn):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(lib_stream)
+        for _ in range(iters):
+            fn()
+        b.record(lib_stream)
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.cpu()[0])
+        return ms
+    ms_eager = timed(it)
+    # the same iteration captured once (draws included: the graph starts with the RNG replay-epoch tick) and replayed
+    ms = ms_eager
+    graph_ok = True
+    try:
+        g = th.Graph(it)
+        for _ in range(3):
+            g()
+        ms = timed(g)
+    except Exception as e:
+        graph_ok = False
+        sys.stderr.write("rank %d: GAN graph capture unavailable (%r)\n" % (rank, e))
     if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(lib_stream)
-    for _ in range(iters):
-        it()
-    b.record(lib_stream)
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.cpu()[0])
         for d in keep:
             assert d.comm.status() == 0
     l_dr, l_df, l_gr = th.gan_iteration(D, G, real, z1, z2, REAL, FAKE)
@@ -294,10 +310,12 @@ def gan_extra(th, t4, L, torch, dist, rank, world, local, lib_stream, iters=50, 
         return None
     flops = 3 * 2 * N * (784 * 512 + 512 * 256 + 256) * 2 + 2 * N * (784 * 512 + 512 * 256 + 256) + 2 * 2 * N * (128 * 256 + 256 * 512 + 512 * 784) + 2 * 2 * N * (128 * 256 + 256 * 512 + 512 * 784)
     return {"batch_per_gpu": N, "ms_per_iteration": round(ms / iters, 4), "samples_per_s": round(N * world * iters / (ms / 1e3), 1),
-            "launches_per_iteration": int(launches), "exchange": exchange, "tflops": round(flops * world / (ms / iters) / 1e9, 2),
+            "launches_per_iteration": int(launches), "cuda_graph": graph_ok, "ms_per_iteration_eager": round(ms_eager / iters, 4),
+            "exchange": exchange, "tflops": round(flops * world / (ms / iters) / 1e9, 2),
             "losses_after": {"d_real": round(l_dr, 4), "d_fake": round(l_df, 4), "g": round(l_gr, 4)},
             "note": "one iteration = train_d (D fwd/bwd on real + on G's fakes, Adam b1=0.5) + train_g (D frozen, dX of D's input through G, Adam); "
-                    "3 D-forwards, 3 D-backwards, 2 G-forwards, 1 G-backward, 2 Adam; eager launches, no loss reads in the timed loop"}
+                    "3 D-forwards, 3 D-backwards, 2 G-forwards, 1 G-backward, 2 Adam; the whole iteration (latent draws and dropout masks included) "
+                    "is one replayed CUDA graph; no loss reads in the timed loop"}
 
 
 # --------------------------------------------------------------------------------------- our arm

@@ -101,6 +101,12 @@ int   t4h_model_adam(t4h_model m, float lr, float b1, float b2);     /* `nn.adam
 int   t4h_model_adamw(t4h_model m, float lr, float wd, float b1, float b2);
 /* flat parameter arenas (built at the first optimizer call): pointers + float count; DG is what a
  * data-parallel caller sum-allreduces between backprop and the optimizer */
+/* generic CUDA-graph capture of a sequence of library calls (e.g. one GAN iteration over two models): begin, make the calls (no host
+ * reads: they synchronise), end -> handle; replay with t4h_graph_launch.  Warm the sequence up once before capturing. */
+int   t4h_capture_begin(void);
+void *t4h_capture_end(void);
+int   t4h_graph_launch(void *graph);
+void  t4h_graph_free(void *graph);
 /* words `save` / `load` on a model (src/vm/netvm.cpp:479-480 -> src/io/aio_model.cpp): the reference's model file — text header and
  * layer lines, then `--- w.<layer>` / `--- b.<layer>` sections of raw FP32.  load fills an already built model (parameter path). */
 int   t4h_model_save(t4h_model m, const char *fname);

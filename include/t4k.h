@@ -255,6 +255,10 @@ int64_t t4k_dp_push(t4k_comm_t c, const float *DG, int64_t from, int64_t total, 
 int t4k_rand_seed(uint64_t seed);
 int t4k_rand(float *d, int64_t n, int opt, float bias, float scale, t4k_stream_t s);
 int t4k_rand_at(float *d, int64_t n, int opt, float bias, float scale, uint64_t seed, uint64_t offset, t4k_stream_t s);
+/* CUDA-graph replays: a captured t4k_rand has its seed and offset baked in; t4k_rand adds a device-side replay epoch (x 2^40) to its
+ * counter, and t4k_rand_tick — put once at the head of a captured sequence that draws — advances it, so that every replay draws
+ * fresh numbers (dropout masks, latent batches).  Never ticked outside graphs. */
+int t4k_rand_tick(t4k_stream_t s);
 
 /* ---- dataset feeding: Dataset::_load (src/mu/dataset.cu:124-152), SURVEY.md §8f row 2 -------------------
  * The reference converts each mini-batch on the host (one float per U8 pixel, then an H2D of 4 bytes per pixel).

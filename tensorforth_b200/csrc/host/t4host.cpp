@@ -1073,6 +1073,26 @@ int   t4h_model_hit(t4h_model m, int recalc) { return MM(m).hit(recalc != 0); }
 int   t4h_model_sgd(t4h_model m, float lr, float b) { MM(m).sgd(lr, b); return 0; }
 int   t4h_model_adam(t4h_model m, float lr, float b1, float b2) { MM(m).adam(lr, b1, b2); return 0; }
 int   t4h_model_adamw(t4h_model m, float lr, float wd, float b1, float b2) { MM(m).adamw(lr, wd, b1, b2); return 0; }
+/* ---- generic capture: whatever the library enqueues on its stream between begin and end becomes a replayable CUDA graph (several
+ * models, tensor words, draws ...).  No host reads in between (they synchronise); warm the sequence up once first so that every
+ * workspace and arena exists.  The graph starts with t4k_rand_tick: replays draw fresh random numbers. */
+int   t4h_capture_begin(void) {
+    cudaStream_t st = (cudaStream_t)Runtime::stream();
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    return t4k_rand_tick((t4k_stream_t)st);
+}
+void *t4h_capture_end(void) {
+    cudaGraph_t g = nullptr;
+    if (cudaStreamEndCapture((cudaStream_t)Runtime::stream(), &g) != cudaSuccess || !g) { cudaGetLastError(); Runtime::error("graph capture failed"); return nullptr; }
+    cudaGraphExec_t ex = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { cudaGetLastError(); Runtime::error("graph instantiation failed: %s", cudaGetErrorString(e)); return nullptr; }
+    return (void*)ex;
+}
+int   t4h_graph_launch(void *g) { return g ? (int)cudaGraphLaunch((cudaGraphExec_t)g, (cudaStream_t)Runtime::stream()) : T4K_EINVAL; }
+void  t4h_graph_free(void *g) { if (g) { Runtime::sync(); cudaGraphExecDestroy((cudaGraphExec_t)g); } }
 int   t4h_model_save(t4h_model m, const char *fname) { return MM(m).save(fname); }
 int   t4h_model_load(t4h_model m, const char *fname) { return MM(m).load(fname); }
 int   t4h_model_arena(t4h_model m, float **G, float **DG, int64_t *total) { return MM(m).arena(G, DG, total); }

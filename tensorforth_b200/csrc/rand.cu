@@ -9,6 +9,20 @@
 namespace t4k {
 
 static uint64_t g_seed = 0x243F6A8885A308D3ull, g_offset = 0;
+// Replay epoch (device memory): a captured CUDA graph bakes seed and offset into its kernel nodes, so every replay would draw the same
+// numbers (same dropout masks, same latent batches).  Each draw therefore adds epoch * 2^40 to its counter, and a graph that contains
+// draws starts with t4k_rand_tick (epoch += 1).  Eager streams never tick: the host offset alone advances, as before.
+static uint64_t *g_epoch_dev[16];
+static uint64_t *epoch_ptr() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= 16) return nullptr;
+    if (!g_epoch_dev[dev]) {
+        if (cudaMalloc((void**)&g_epoch_dev[dev], 64) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        cudaMemset(g_epoch_dev[dev], 0, 64);
+    }
+    return g_epoch_dev[dev];
+}
+__global__ void k_rand_tick(uint64_t *epoch) { if (threadIdx.x == 0 && blockIdx.x == 0) epoch[0] += 1; }
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     #pragma unroll
@@ -23,8 +37,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 __device__ __forceinline__ float u01(uint32_t x) { return (float)x * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }  // (0,1]
 
 __global__ void __launch_bounds__(T4K_THREADS)
-k_rand(float *d, int64_t n, int opt, float bias, float scale, uint64_t seed, uint64_t offset) {
+k_rand(float *d, int64_t n, int opt, float bias, float scale, uint64_t seed, uint64_t offset, const uint64_t *__restrict__ epoch) {
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    if (epoch) offset += epoch[0] << 40;
     const int64_t nq = (n + 3) >> 2;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
         // counter = absolute quad index; unaligned offsets are handled by drawing per element below
@@ -51,15 +66,29 @@ k_rand(float *d, int64_t n, int opt, float bias, float scale, uint64_t seed, uin
 } // namespace t4k
 using namespace t4k;
 
-extern "C" int t4k_rand_seed(uint64_t seed) { g_seed = seed; g_offset = 0; return 0; }
+extern "C" int t4k_rand_seed(uint64_t seed) {
+    g_seed = seed; g_offset = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev < 16 && g_epoch_dev[dev]) cudaMemset(g_epoch_dev[dev], 0, 64);   // synchronising; seeding is rare
+    else cudaGetLastError();
+    return 0;
+}
 extern "C" int t4k_rand_at(float *d, int64_t n, int opt, float bias, float scale, uint64_t seed, uint64_t offset, t4k_stream_t s) {
     if (!d || n < 0 || (opt != T4K_UNIFORM && opt != T4K_NORMAL)) return T4K_EINVAL;
     if (n == 0) return 0;
-    k_rand<<<stream_grid((n + 3) / 4), T4K_THREADS, 0, STRM(s)>>>(d, n, opt, bias, scale, seed, offset);
+    k_rand<<<stream_grid((n + 3) / 4), T4K_THREADS, 0, STRM(s)>>>(d, n, opt, bias, scale, seed, offset, nullptr);
+    return check_launch();
+}
+extern "C" int t4k_rand_tick(t4k_stream_t s) {
+    uint64_t *e = epoch_ptr();
+    if (!e) return T4K_ENOMEM;
+    k_rand_tick<<<1, 32, 0, STRM(s)>>>(e);
     return check_launch();
 }
 extern "C" int t4k_rand(float *d, int64_t n, int opt, float bias, float scale, t4k_stream_t s) {
-    int rc = t4k_rand_at(d, n, opt, bias, scale, g_seed, g_offset, s);
+    if (!d || n < 0 || (opt != T4K_UNIFORM && opt != T4K_NORMAL)) return T4K_EINVAL;
+    if (n == 0) return 0;
+    k_rand<<<stream_grid((n + 3) / 4), T4K_THREADS, 0, STRM(s)>>>(d, n, opt, bias, scale, g_seed, g_offset, epoch_ptr());
     g_offset += (uint64_t)((n + 3) & ~3ll);        // successive calls draw disjoint counters
-    return rc;
+    return check_launch();
 }

@@ -40,6 +40,7 @@ PROTOTYPES = {
     "t4h_model_arena": (_i, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_l)]),
     "t4h_model_step_graph": (_i, [_p, _p, _p, _i, _p, _i, _f, _f, _f, _f]),
     "t4h_model_dp_attach": (_i, [_p, _p, _p, _i]),
+    "t4h_capture_begin": (_i, []), "t4h_capture_end": (_p, []), "t4h_graph_launch": (_i, [_p]), "t4h_graph_free": (None, [_p]),
     "t4h_model_save": (_i, [_p, C.c_char_p]), "t4h_model_load": (_i, [_p, C.c_char_p]),
     "t4h_dataset_create": (_p, [_i, _i, _i, _i]), "t4h_dataset_destroy": (None, [_p]), "t4h_dataset_normalize": (None, [_p, _f, _f]),
     "t4h_dataset_stage": (_i, [_p, _p, _p, _i]), "t4h_dataset_commit": (_i, [_p]), "t4h_dataset_tensor": (_p, [_p]),
@@ -377,6 +378,29 @@ def gan_discriminator(N):
 def gan_generator(N):
     """examples/t4_40b.4th:44-48"""
     return (Model(N, 128, 1, 1).linear(256).leakyrelu(0.2).linear(512).leakyrelu(0.2).linear(784).tanh())
+
+
+class Graph:
+    """A sequence of library calls captured once into a CUDA graph and replayed: `g = Graph(lambda: gan_iteration(..., losses=False))`,
+    then `g()` per iteration.  The callable must not read anything back on the host; run it eagerly once before capturing."""
+
+    def __init__(self, fn):
+        _k.check(load().t4h_capture_begin(), "capture_begin")
+        try:
+            fn()
+        finally:
+            self.h = load().t4h_capture_end()
+        if not self.h:
+            raise T4KError("graph capture: " + _err())
+
+    def __call__(self):
+        _k.check(load().t4h_graph_launch(self.h), "graph_launch")
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None): load().t4h_graph_free(self.h); self.h = None
+        except Exception:
+            pass
 
 
 def gan_discriminator(N, p=0.3):

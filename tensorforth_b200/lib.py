@@ -85,6 +85,7 @@ PROTOTYPES = {
     "t4k_rand_seed": (_i, [_u64]),
     "t4k_rand": (_i, [_p, _l, _i, _f, _f, _p]),
     "t4k_rand_at": (_i, [_p, _l, _i, _f, _f, _u64, _u64, _p]),
+    "t4k_rand_tick": (_i, [_p]),
     "t4k_dataset_load": (_i, [_p, _p, _l, _f, _f, _p, _p, _i, _p, _i, _p]),
     "t4k_onehot": (_i, [_p, _p, _i, _i, _p]),
     "t4k_hit": (_i, [_p, _p, _i, _i, _p, _p]),

@@ -470,3 +470,31 @@ def test_step_graph_captured_on_its_first_call():
         th.sync()
         assert float(la.cpu()[0]) == float(lb.cpu()[0])
     assert np.array_equal(ga.w(4).numpy(), gb.w(4).numpy())
+
+
+def test_graph_replays_draw_fresh_random_numbers():
+    """th.Graph: a captured sequence that draws (randn, dropout masks) starts with the RNG replay-epoch tick, so every replay gets new
+    numbers, and the captured computation equals the eager one on the same inputs"""
+    t4.load().t4k_rand_seed(99)
+    z = th.Tensor.tensor(8, 16, 1, 1)
+    m = th.Model(8, 16, 1, 1).linear(12).leakyrelu(0.2).dropout(0.5).linear(4).sigmoid()
+    x = th.Tensor.from_numpy(np.random.default_rng(2).standard_normal((8, 16, 1, 1)).astype(np.float32))
+    m.forward(x)                                     # warm-up: workspaces exist before the capture
+
+    def seq():
+        z.randn(); m.forward(z)
+    seq()
+    g = th.Graph(seq)
+    draws, masks = [], []
+    for _ in range(3):
+        g(); th.sync()
+        draws.append(z.numpy().copy()); masks.append(m.ex(2).numpy().copy())     # layer 2 = dropout: its saved mask
+    assert not np.array_equal(draws[0], draws[1]) and not np.array_equal(draws[1], draws[2])
+    assert not np.array_equal(masks[0], masks[1])
+    assert abs(float(np.mean(draws[2]))) < 0.5 and 0.5 < float(np.std(draws[2])) < 1.5
+    # the graph computes what the eager path computes for the input it drew (dropout mask taken from the replay)
+    out_g = m.layer(-1).numpy().copy()
+    h = np.maximum(draws[2].reshape(8, 16) @ m.w(0).numpy().reshape(12, 16).T + m.b(0).numpy(), 0.2 * (draws[2].reshape(8, 16) @ m.w(0).numpy().reshape(12, 16).T + m.b(0).numpy()))
+    h = h * masks[2].reshape(8, 12)
+    o = 1.0 / (1.0 + np.exp(-(h @ m.w(3).numpy().reshape(4, 12).T + m.b(3).numpy())))
+    np.testing.assert_allclose(out_g.reshape(8, 4), o, rtol=1e-4, atol=1e-6)
