@@ -869,7 +869,10 @@ void Model::_drop_graphs() {
     for (auto &g : _graphs) if (g.exec) { cudaGraphExecDestroy((cudaGraphExec_t)g.exec); g.exec = nullptr; }
 }
 int Model::_step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd, const StepExtra &x) {
+    bool has_dropout = false;
+    for (Tensor *t : _layers) if (t->grad_fn == T4K_L_DROPOUT) has_dropout = true;
     auto run = [&]() {
+        if (has_dropout) t4k_rand_tick(ST);                    // replayed graphs draw a fresh dropout mask every step (rand.cu)
         if (x.ds) x.ds->commit_launch(x.simg, x.slab, x.n, tgt.data, (int)(*this)[-1].HWC());   // dataset feeding: normalise + one-hot
         _want_pdup = loss_dev != nullptr; _pdup_valid = false;
         forward(input);
@@ -905,13 +908,11 @@ int Model::_step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4
         else if (x.loss_pin && loss_dev && !(side_loss && !_comm)) cudaMemcpyAsync(x.loss_pin, loss_dev, sizeof(DU), cudaMemcpyDeviceToHost, (cudaStream_t)ST);
     };
     if (loss_dev && !_pdup) _pdup = (DU*)Runtime::alloc((size_t)(*this)[-1].numel * sizeof(DU) + 64);   // not inside the capture below
-    bool has_dropout = false;
-    for (Tensor *t : _layers) if (t->grad_fn == T4K_L_DROPOUT) has_dropout = true;
     U64 key[12] = {0}; float f4[4] = {lr, b1, b2, wd};
     key[0] = (U64)input.data; key[1] = (U64)tgt.data; key[2] = (U64)lop; key[3] = (U64)loss_dev; key[4] = (U64)op;
     memcpy(&key[5], f4, 16); key[7] = (U64)train; key[8] = (U64)x.simg; key[9] = (U64)x.slab; key[10] = (U64)x.n; key[11] = (U64)x.loss_pin;
     // SGD's first call forces momentum 0 (host state) and the first optimizer call builds the arenas: run those eagerly
-    if (has_dropout || !_G || (_iter == 0 && (int)op >= 0)) { run(); return 0; }
+    if (!_G || (_iter == 0 && (int)op >= 0)) { run(); return 0; }
     cudaStream_t st = (cudaStream_t)ST;
     StepGraph *slot = nullptr, *lru = nullptr;        // cached graph for this key, else an empty slot, else the least recently used
     for (auto &g : _graphs) {

@@ -498,3 +498,20 @@ def test_graph_replays_draw_fresh_random_numbers():
     h = h * masks[2].reshape(8, 12)
     o = 1.0 / (1.0 + np.exp(-(h @ m.w(3).numpy().reshape(4, 12).T + m.b(3).numpy())))
     np.testing.assert_allclose(out_g.reshape(8, 4), o, rtol=1e-4, atol=1e-6)
+
+
+def test_step_graph_with_dropout_draws_a_new_mask_every_step():
+    N = 16
+    t4.load().t4k_rand_seed(5)
+    m = th.Model(N, 8, 8, 1).flatten().linear(32).relu().dropout(0.5).linear(4).softmax()
+    rng = np.random.default_rng(1)
+    X = th.Tensor.from_numpy((rng.random((N, 8, 8, 1), dtype=np.float32) * 2 - 1).astype(np.float32))
+    Y = th.Tensor.tensor(N, 1, 4, 1, orc.onehot(rng.integers(0, 4, N), 4))
+    ld = torch.zeros(1, device="cuda"); lp = C.c_void_p(ld.data_ptr())
+    masks, losses = [], []
+    for step in range(5):
+        assert m.step_graph(X, Y, t4.LOSS_CE, lp, optimizer=2, lr=1e-3) == 0
+        th.sync(); masks.append(m.ex(3).numpy().copy()); losses.append(float(ld.cpu()[0]))
+    assert all(np.isfinite(losses))
+    assert set(np.unique(masks[-1])) <= {0.0, 1.0} and 0.2 < masks[-1].mean() < 0.8
+    assert not np.array_equal(masks[2], masks[3]) and not np.array_equal(masks[3], masks[4])      # steps 3.. are graph replays
