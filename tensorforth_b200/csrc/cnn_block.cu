@@ -28,6 +28,9 @@ int cpr_v1_bwd(const float *dY, float *actO, const float *actF, float *poolO, fl
                int KS, int S, int P, int train, cudaStream_t st);
 int wgrad_fin_launch(const float *part, float *dF, float *dB, int nF, int C0, int nparts, int KS, int S, cudaStream_t st);
 
+#ifndef CPR2_FWD_MINB
+#define CPR2_FWD_MINB 4        // 64 registers, no spills: 4 x 224-thread CTAs per SM = 592 slots, so the 512 samples of the MNIST batch are ONE wave (3 per SM: 1.15 waves)
+#endif
 struct Cpr2P {
     const float *I, *F, *B, *dY, *actFc;
     float *Icopy, *convO, *poolO, *actO, *actF, *flatO, *Iio, *dXbuf, *part;
@@ -40,7 +43,7 @@ struct Cpr2P {
 // leave the registers as 128-bit stores of contiguous 2*C0 runs, the pooled values are staged in smem and the four
 // pooled tensors (pool, relu, mask, flatten) leave as contiguous 128-bit streams.
 template<int KS, int CP, int C0T, int C1T>
-__global__ void __launch_bounds__(256, 3) k_cpr2_fwd(Cpr2P p) {
+__global__ void __launch_bounds__(256, CPR2_FWD_MINB) k_cpr2_fwd(Cpr2P p) {
     extern __shared__ __align__(16) float sm[];
     pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     constexpr int P = (KS - 1) / 2;
