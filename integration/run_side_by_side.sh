@@ -16,7 +16,9 @@ for f in $HERE/scripts/*.4th $ROOT/oracle/_ref/examples/t4_10a.4th $ROOT/oracle/
   [ -f $f ] || continue
   b=$(basename $f .4th)
   timeout 120 $REF < $f > $OUT/ref/$b.out 2> $OUT/ref/$b.err;  echo "ref  $b rc=$?"
+  sleep 1.1    # the reference seeds its RNG with time() (1 s resolution): the second run must not share the first one's seed
   timeout 120 $REF < $f > $OUT/ref2/$b.out 2> $OUT/ref2/$b.err   # second run of the reference: its own run-to-run spread
+  sleep 1.1
   timeout 120 $NEW < $f > $OUT/b200/$b.out 2> $OUT/b200/$b.err; echo "b200 $b rc=$?"
 done
 python $HERE/diff_outputs.py $OUT/ref $OUT/b200 $OUT/ref2 | tee $OUT/summary.txt
