@@ -5,17 +5,22 @@ bench.py — the measurement contract (task §④).
   python bench.py --gpus N --steps K --warmup W            our arm (N>1: launched by torch.distributed.run)
   python bench.py --impl reference --gpus N --steps K ...   the reference's own legacy CUDA build (oracle/_ref/ten4)
 
-Metric (BASELINE.json): MNIST-CNN training samples/s — the CNN of examples/t4_40a.4th:10-13 at N=512 per GPU
-(weak scaling), one step = forward + loss.ce + backprop + nn.adam on synthetic 28x28x1 data — plus, at N=1, the two
-other headline numbers as `extras`: GEMM 4096^3 FP32 TFLOP/s and conv2d 3x3 64->64 @56x56 HBM GB/s, each against its
-roofline (MEASURED_PEAKS.json).  One JSON line on stdout (rank 0).
+Metric (BASELINE.json): MNIST-CNN training samples/s — the CNN of examples/t4_40a.4th:10-13 at N=512 per GPU (weak scaling),
+one step = forward + loss.ce + backprop + nn.adam on synthetic 28x28x1 data.  One JSON line on stdout (rank 0).
 
-`value`   : device-timed (CUDA events on the launching stream, max over ranks), inputs resident in HBM.
-`e2e`     : same step through the public host API with the batch copied from pinned host memory and the loss read
-            back every step.
-`roofline`: the dominant kernel of the step, timed live (K launches between two events on its stream).
+`value`   : device-timed (CUDA events on the launching stream, max over ranks), inputs resident in HBM, one CUDA-graph launch per step.
+`e2e`     : the same step through the public host API the way a training loop over a dataset runs: every step's mini-batch starts in
+            pinned host memory as U8 pixels + U8 labels (what an MNIST loader holds), Dataset.stage() copies the bytes, the device
+            normalises and one-hots them, and every step's loss is read back on the host (Model.train_step).
+`roofline`: the dominant call of the step, timed live (graph of 20 launches replayed between two events on its stream), against the
+            measured HBM bandwidth; `calls` lists every call of the step the same way.
+`extras`  : the other headline numbers — GEMM 4096^3 (both tensor-core engines, with their measured error), conv2d 3x3 64->64 @56x56 at
+            the full N=8192 sharded over the ranks, one GAN iteration of examples/t4_40b.4th at N=1024 per GPU.
 `cpu_baseline`: the C oracle (oracle/, "port") timed on the host cores on a bounded sample — reported, not a target.
-tensorForth has no CPU tensor path; the reference arm therefore times the reference's GPU build.
+N > 1     : one rank per GPU (torchrun); the gradient exchange is fused into the optimizer kernel over NVLink peer memory
+            (`--exchange nccl` selects the NCCL all-reduce arm).
+tensorForth has no CPU tensor path; the reference arm (`--impl reference`) therefore times the reference's own CUDA build on GPU 0
+(SURVEY.md §8d).
 """
 import argparse
 import ctypes as C
