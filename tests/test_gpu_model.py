@@ -515,3 +515,66 @@ def test_step_graph_with_dropout_draws_a_new_mask_every_step():
     assert all(np.isfinite(losses))
     assert set(np.unique(masks[-1])) <= {0.0, 1.0} and 0.2 < masks[-1].mean() < 0.8
     assert not np.array_equal(masks[2], masks[3]) and not np.array_equal(masks[3], masks[4])      # steps 3.. are graph replays
+
+
+# ------------------------------------------------------------------ golden: what the reference PROGRAM printed (tests/golden/ref_program)
+def _golden_numbers(name, key):
+    import os, re
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_program", name + ".out")
+    return [float(m) for m in re.findall(r"^%s=([-+0-9.eE]+)" % re.escape(key), open(path).read(), flags=re.M)]
+
+
+def _close_printed(got, want, what):
+    """the VM prints 6 significant digits; the north star's bar is 1e-4 relative"""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    assert np.all(np.abs(got - want) <= 1e-4 * np.abs(want) + 1e-5), (what, got.tolist(), want.tolist())
+
+
+def test_reference_program_golden_cnn_parity():
+    """integration/scripts/cnn_parity.4th through the host mirror: same model (t4_40a.4th:10-13 at N=64), same bits in weights, input and
+    labels; loss before training, after one Adam step at lr=1e-3 and nine at 2e-5 — against what the reference program printed"""
+    N = 64
+    m = (th.Model(N, 28, 28, 1).conv2d(0.5, 10).maxpool(2).relu().flatten().linear(100, 0.0).relu().linear(10, 0.0).softmax())
+    m.set_w(0, _chaos(90, 1.6)); m.set_b(0, _chaos(10, 0.2))
+    m.set_w(4, _chaos(100 * 1960, 0.05)); m.set_b(4, _chaos(100, 0.1))
+    m.set_w(6, _chaos(1000, 0.2)); m.set_b(6, _chaos(10, 0.1))
+    x = (_chaos(N * 784, 1.0) * np.float32(2.0)).astype(np.float32).reshape(N, 28, 28, 1)
+    y = np.zeros((N, 10), np.float32)
+    y[np.arange(N), (7 * np.arange(N) + 3) % 10] = 1.0
+    X, Y = th.Tensor.from_numpy(x), th.Tensor.tensor(N, 1, 10, 1, y)
+    assert abs(float(x.astype(np.float64).sum()) - _golden_numbers("cnn_parity", "X sum")[0]) < 0.06        # printed with 4 digits: the input bits are the reference's
+    m.forward(X)
+    _close_printed([m.loss(t4.LOSS_CE, Y)], _golden_numbers("cnn_parity", "loss0"), "loss0")
+    m.backprop(Y)
+    _close_printed([np.sqrt(float((m.dw(6).numpy().astype(np.float64) ** 2).sum()))], _golden_numbers("cnn_parity", "dw6 norm"), "dw6 norm")
+    m.adam(float(_lit(0.001)))
+    losses = []
+    for _ in range(10):
+        m.forward(X); m.backprop(Y); m.adam(float(_lit(0.00002)))
+        m.forward(X); losses.append(m.loss(t4.LOSS_CE, Y))
+    _close_printed(losses, _golden_numbers("cnn_parity", "loss"), "loss trajectory")
+    _close_printed([np.sqrt(float((m.w(6).numpy().astype(np.float64) ** 2).sum()))], _golden_numbers("cnn_parity", "w6 norm"), "w6 norm")
+
+
+def test_reference_program_golden_mlp_bn():
+    """integration/scripts/mlp_bn_parity.4th: flatten, linear, batchnorm, tanh, leakyrelu, sigmoid, MSE, SGD with momentum"""
+    N = 32
+    m = (th.Model(N, 8, 8, 2).flatten().linear(48, 0.0).batchnorm(0.1).tanh().linear(24, 0.0).leakyrelu(float(_lit(0.1))).linear(4, 0.0).sigmoid())
+    m.set_w(1, _chaos(48 * 128, 0.3)); m.set_b(1, _chaos(48, 0.2))
+    m.set_w(4, _chaos(24 * 48, 0.4)); m.set_b(4, _chaos(24, 0.2))
+    m.set_w(6, _chaos(4 * 24, 0.5)); m.set_b(6, _chaos(4, 0.2))
+    x = (_chaos(N * 128, 1.0) * np.float32(2.0)).astype(np.float32).reshape(N, 8, 8, 2)
+    t = (_chaos(N * 4, 1.0) + _lit(0.5)).astype(np.float32).reshape(N, 4)
+    X, T = th.Tensor.from_numpy(x), th.Tensor.tensor(N, 1, 4, 1, t)
+    m.forward(X)
+    _close_printed([m.loss(t4.LOSS_MSE, T)], _golden_numbers("mlp_bn_parity", "loss0"), "loss0")
+    m.backprop(T)
+    _close_printed([np.sqrt(float((m.dw(1).numpy().astype(np.float64) ** 2).sum()))], _golden_numbers("mlp_bn_parity", "dw1 norm"), "dw1 norm")
+    m.sgd(float(_lit(0.01)), float(_lit(0.9)))
+    losses = []
+    for _ in range(10):
+        m.forward(X); m.backprop(T); m.sgd(float(_lit(0.01)), float(_lit(0.9)))
+        m.forward(X); losses.append(m.loss(t4.LOSS_MSE, T))
+    _close_printed(losses, _golden_numbers("mlp_bn_parity", "loss"), "loss trajectory")
+    _close_printed([np.sqrt(float((m.w(1).numpy().astype(np.float64) ** 2).sum()))], _golden_numbers("mlp_bn_parity", "w1 norm"), "w1 norm")
