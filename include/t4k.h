@@ -233,6 +233,7 @@ int t4k_comm_connect_local(t4k_comm_t c, t4k_comm_t *all /* world communicators 
 int t4k_comm_destroy(t4k_comm_t c);
 int t4k_comm_status(t4k_comm_t c);      /* 0 healthy; k>0: a wait for rank k-1 timed out (~2 s without progress) */
 int64_t t4k_comm_capacity(t4k_comm_t c);
+int t4k_shard_info(int64_t n, int world, int rank, int64_t *lo, int64_t *hi);   /* batch shard of a rank: samples [lo, hi) (no device needed) */
 /* buf[i] = sum over ranks of buf[i], in place, n <= capacity */
 int t4k_allreduce_sum(t4k_comm_t c, float *buf, int64_t n, t4k_stream_t s);
 /* t4k_optim_multi on the rank-summed gradient: DG is exchanged, summed and consumed (zeroed) by the same kernel;

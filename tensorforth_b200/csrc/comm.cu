@@ -262,6 +262,15 @@ int t4k_comm_status(t4k_comm_t c) {
 
 int64_t t4k_comm_capacity(t4k_comm_t c) { return c ? c->cap : 0; }
 
+/* samples [lo, hi) of a batch of n owned by `rank` of `world`: contiguous, sizes differ by at most one, first ranks larger (host-only) */
+int t4k_shard_info(int64_t n, int world, int rank, int64_t *lo, int64_t *hi) {
+    if (n < 0 || world < 1 || rank < 0 || rank >= world || !lo || !hi) return T4K_EINVAL;
+    const int64_t q = n / world, r = n % world;
+    *lo = rank * q + (rank < r ? rank : r);
+    *hi = *lo + q + (rank < r ? 1 : 0);
+    return 0;
+}
+
 int t4k_allreduce_sum(t4k_comm_t c, float *buf, int64_t n, t4k_stream_t s) {
     if (!ready(c) || !buf || n < 0 || n > c->cap) return T4K_EINVAL;
     if (n == 0) return 0;

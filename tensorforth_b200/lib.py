@@ -79,6 +79,7 @@ PROTOTYPES = {
     "t4k_comm_destroy": (_i, [_p]),
     "t4k_comm_status": (_i, [_p]),
     "t4k_comm_capacity": (_l, [_p]),
+    "t4k_shard_info": (_i, [_l, _i, _i, C.POINTER(_l), C.POINTER(_l)]),
     "t4k_allreduce_sum": (_i, [_p, _p, _l, _p]),
     "t4k_optim_multi_dp": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _l, _f, _f, _f, _f, _p, _i, _l, _p]),
     "t4k_dp_push": (_l, [_p, _p, _l, _l, _p]),

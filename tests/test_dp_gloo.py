@@ -138,3 +138,16 @@ def test_two_rank_step_equals_full_batch_step():
     np.testing.assert_allclose(got_losses, ref_losses, rtol=1e-5)
     np.testing.assert_allclose(got_params, _flat(m, ""), rtol=1e-4, atol=1e-6)
     assert int(got_hits) == int(ref_hits)
+
+
+def test_c_abi_shard_info_matches_the_host_helper():
+    import ctypes as C
+    from tensorforth_b200 import lib
+    L = lib.load()
+    for n in (0, 1, 7, 512, 8192):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                lo, hi = C.c_int64(), C.c_int64()
+                assert L.t4k_shard_info(n, world, r, C.byref(lo), C.byref(hi)) == 0
+                assert (lo.value, hi.value) == dp.shard_bounds(n, world, r)
+    assert L.t4k_shard_info(8, 2, 2, C.byref(lo), C.byref(hi)) == lib.EINVAL
