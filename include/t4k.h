@@ -132,6 +132,12 @@ int t4k_linear_act_fwd(int layer, const float *X, const float *W, const float *B
 /* classifier head, forward: small linear (E0 <= 32, W <= 40 KB) + bias + row softmax in one launch (forward.cu:158-198,231-243):
  * Y = X @ W^T + B, P = softmax(Y).  T4K_ENOSUP when the head is not small (caller: t4k_linear_fwd + t4k_softmax_fwd) */
 int t4k_mlp_head_fwd(const float *X, const float *W, const float *B, float *Y, float *P, int N, int E0, int E1, t4k_stream_t s);
+/* hidden linear + activation + classifier head in two launches (GEMM, then split-K finish + bias + activation + small linear + softmax):
+ * X [N,E1] -> Y1 = X @ W1^T + B1 [N,EH], A1 = act(Y1), F1 = saved derivative -> Y2 = A1 @ W2^T + B2 [N,E0], P = softmax(Y2) (+ Pdup).
+ * Same tensors, same bits as t4k_linear_act_fwd followed by t4k_mlp_head_fwd.  T4K_ENOSUP when EH > 128, E0 > 32 or the layer is
+ * not relu / tanh / sigmoid / selu / leakyrelu / elu: use the two calls. */
+int t4k_linear_act_head_fwd(int layer, const float *X, const float *W1, const float *B1, float *Y1, float *A1, float *F1, float alpha,
+                            const float *W2, const float *B2, float *Y2, float *P, float *Pdup, int N, int EH, int E1, int E0, t4k_stream_t s);
 /* the same, with the probabilities also written to Pdup [N,E0] (may be NULL): Model::backprop turns P into p - y in place, so a
  * caller that wants the loss kernel to overlap the backward pass (second stream) lets it read the duplicate */
 int t4k_mlp_head_fwd_dup(const float *X, const float *W, const float *B, float *Y, float *P, float *Pdup, int N, int E0, int E1, t4k_stream_t s);

@@ -383,6 +383,15 @@ int Model::_ffused_linear(size_t i) {
     const int N = (int)lo.N(), E0 = (int)lo.HWC(), E1 = (int)in.HWC();
     const t4_layer fn = lo.grad_fn;
     int rc;
+    // linear -> activation -> small linear -> softmax at the end of the model: the split-K finish of the first linear and the whole head
+    // are one launch (the activations of a row never leave the warp that owns it)
+    if ((mask_act(fn) || fn == T4K_L_SIGMOID) && i + 5 == n && ao.grad_fn == T4K_L_LINEAR && _layers[i + 3]->grad_fn == T4K_L_SOFTMAX) {
+        Tensor &l2o = *_layers[i + 3], &po = *_layers[i + 4];
+        DU *dup = (_want_pdup && _pdup) ? _pdup : nullptr;
+        rc = t4k_linear_act_head_fwd(fn, in.data, in.grad[0]->data, in.grad[1]->data, lo.data, ao.data, lo.grad[4]->data, lo.xparm,
+                                     ao.grad[0]->data, ao.grad[1]->data, l2o.data, po.data, dup, N, E0, E1, (int)l2o.HWC(), ST);
+        if (rc != T4K_ENOSUP) { KCHK(rc); _pdup_valid = (rc == 0 && dup != nullptr); return 4; }
+    }
     if (fn == T4K_L_SOFTMAX) {
         DU *dup = nullptr;
         if (_want_pdup && _pdup && i + 3 == n) {           // the model's output layer, inside step_graph: keep a copy of p for the loss

@@ -114,6 +114,59 @@ __global__ void __launch_bounds__(T4K_THREADS) k_head_fwd(const float *__restric
     }
 }
 
+// ------------------------------------------------------------------ split-K finish of the hidden linear layer + activation, fused with the head
+// forward: row n of  Y1 = Σ_k part_k + b1,  A1 = act(Y1) (+ mask F1)  stays in the registers of the warp that owns the row and feeds
+// Y2 = A1 @ W2^T + b2, P = softmax(Y2) directly.  Same arithmetic, same order as k_linear_fin followed by k_head_fwd (bit-equal); one
+// launch and one round trip of A1 less on the critical path of the step.  E1 (hidden width) <= 128, E0 (classes) <= 32.
+template<int L>
+__global__ void __launch_bounds__(T4K_THREADS) k_fin_head_fwd(const float *__restrict__ part, int splits, int64_t MN, const float *__restrict__ B1,
+                                                              float *Y1, float *A1, float *F1, float alpha,
+                                                              const float *__restrict__ W2, const float *__restrict__ B2, float *Y2, float *P, float *P2,
+                                                              int N, int E0, int E1) {
+    extern __shared__ float sW[];                      // [E0][E1]
+    pdl_wait(); pdl_trigger();
+    for (int t = threadIdx.x; t < E0 * E1; t += blockDim.x) sW[t] = __ldg(W2 + t);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < N; row += nw) {
+        float acc[32];
+        #pragma unroll
+        for (int k = 0; k < 32; k++) acc[k] = 0.0f;
+        const int64_t r0 = (int64_t)row * E1;
+        // the lane's (up to) four hidden units, all partial loads of a split in flight together; sums in split order as k_linear_fin
+        float sv[4];
+        #pragma unroll
+        for (int j = 0; j < 4; j++) { const int e = lane + 32 * j; sv[j] = (e < E1) ? part[r0 + e] : 0.0f; }
+        #pragma unroll 4
+        for (int k = 1; k < splits; k++) {
+            float tv[4];
+            #pragma unroll
+            for (int j = 0; j < 4; j++) { const int e = lane + 32 * j; tv[j] = (e < E1) ? part[(int64_t)k * MN + r0 + e] : 0.0f; }
+            #pragma unroll
+            for (int j = 0; j < 4; j++) sv[j] += tv[j];
+        }
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int e = lane + 32 * j;
+            if (e < E1) {
+                const float s = sv[j] + __ldg(B1 + e);
+                Y1[r0 + e] = s;
+                float xv = s;
+                if (L != T4K_L_NONE) { float o, f = (L == T4K_L_DROPOUT) ? F1[r0 + e] : 0.0f; act<L>(s, alpha, o, f); A1[r0 + e] = o; F1[r0 + e] = f; xv = o; }
+                #pragma unroll
+                for (int k = 0; k < 32; k++) if (k < E0) acc[k] = fmaf(xv, sW[k * E1 + e], acc[k]);
+            }
+        }
+        float y = warp_treduce32(acc, lane);
+        const bool on = lane < E0;
+        if (on) y += __ldg(B2 + lane);
+        const float mx = warp_max(on ? y : -FLT_MAX);
+        const float ex = on ? __expf(y - mx) : 0.0f;
+        const float sm = warp_sum(ex);
+        if (on) { const float pv = ex / sm; Y2[(int64_t)row * E0 + lane] = y; P[(int64_t)row * E0 + lane] = pv; if (P2) P2[(int64_t)row * E0 + lane] = pv; }
+    }
+}
+
 // ------------------------------------------------------------------ head backward
 // per row n:  d = P - T  → P (in place, Model::_bprep) and → Ylin (softmax backward: in = out)
 //             dX2[e] = Σ_k d[k] W[k][e]                → X2 row (the small linear's input tensor, in place)
@@ -295,6 +348,36 @@ extern "C" int t4k_mlp_head_fwd_dup(const float *X, const float *W, const float 
     if (g > 2 * sm_count()) g = 2 * sm_count();
     launch_pdl(k_head_fwd, dim3(g), dim3(T4K_THREADS), (size_t)E0 * E1 * sizeof(float), STRM(s), X, W, B, Y, P, Pdup, N, E0, E1);
     return check_launch();
+}
+template<int L> static int launch_fin_head(const GemmDeferred &d, int64_t MN, const float *B1, float *Y1, float *A1, float *F1, float alpha,
+                                           const float *W2, const float *B2, float *Y2, float *P, float *Pdup, int N, int E0, int E1, cudaStream_t st) {
+    const int rows_per_cta = T4K_THREADS / 32;
+    int g = (N + rows_per_cta - 1) / rows_per_cta;
+    if (g > 2 * sm_count()) g = 2 * sm_count();
+    launch_pdl(k_fin_head_fwd<L>, dim3(g), dim3(T4K_THREADS), (size_t)E0 * E1 * sizeof(float), st,
+               d.part, d.splits, MN, B1, Y1, A1, F1, alpha, W2, B2, Y2, P, Pdup, N, E0, E1);
+    return check_launch();
+}
+extern "C" int t4k_linear_act_head_fwd(int layer, const float *X, const float *W1, const float *B1, float *Y1, float *A1, float *F1, float alpha,
+                                       const float *W2, const float *B2, float *Y2, float *P, float *Pdup,
+                                       int N, int EH, int E1, int E0, t4k_stream_t s) {
+    if (!X || !W1 || !B1 || !Y1 || !A1 || !F1 || !W2 || !B2 || !Y2 || !P || N < 1 || EH < 1 || E1 < 1 || E0 < 1) return T4K_EINVAL;
+    if (E0 > 32 || EH > 128 || (size_t)E0 * EH * sizeof(float) > 40 * 1024) return T4K_ENOSUP;
+    cudaStream_t st = STRM(s);
+    GemmDeferred d{nullptr, 1};
+    int rc = gemm_tcf_ok(0, 1, N, EH, E1, 1, 1) ? gemm_tcf(X, W1, Y1, 1.0f, 0.0f, 0, 1, N, EH, E1, st, &d)
+                                                : gemm_simt(X, W1, Y1, 1.0f, 0.0f, 0, 1, N, EH, E1, 1, 1, 0, 0, 0, st, &d);
+    if (rc) return rc;
+    const int64_t MN = (int64_t)N * EH;
+    switch (layer) {
+    case T4K_L_RELU:    return launch_fin_head<T4K_L_RELU>(d, MN, B1, Y1, A1, F1, alpha, W2, B2, Y2, P, Pdup, N, E0, EH, st);
+    case T4K_L_TANH:    return launch_fin_head<T4K_L_TANH>(d, MN, B1, Y1, A1, F1, alpha, W2, B2, Y2, P, Pdup, N, E0, EH, st);
+    case T4K_L_SIGMOID: return launch_fin_head<T4K_L_SIGMOID>(d, MN, B1, Y1, A1, F1, alpha, W2, B2, Y2, P, Pdup, N, E0, EH, st);
+    case T4K_L_SELU:    return launch_fin_head<T4K_L_SELU>(d, MN, B1, Y1, A1, F1, alpha, W2, B2, Y2, P, Pdup, N, E0, EH, st);
+    case T4K_L_LEAKYRL: return launch_fin_head<T4K_L_LEAKYRL>(d, MN, B1, Y1, A1, F1, alpha, W2, B2, Y2, P, Pdup, N, E0, EH, st);
+    case T4K_L_ELU:     return launch_fin_head<T4K_L_ELU>(d, MN, B1, Y1, A1, F1, alpha, W2, B2, Y2, P, Pdup, N, E0, EH, st);
+    default:            return T4K_ENOSUP;
+    }
 }
 extern "C" int t4k_mlp_head_bwd(float *P, const float *T, float *Ylin, float *X2, const float *F1, float *Y1, const float *W,
                                 float *dW, float *dB, float *dB1, int N, int E0, int E1, int train, t4k_stream_t s) {

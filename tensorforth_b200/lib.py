@@ -62,6 +62,7 @@ PROTOTYPES = {
     "t4k_linear_act_fwd": (_i, [_i] + [_p] * 6 + [_f] + [_i] * 3 + [_p]),
     "t4k_mlp_head_fwd": (_i, [_p] * 5 + [_i] * 3 + [_p]),
     "t4k_mlp_head_fwd_dup": (_i, [_p] * 6 + [_i] * 3 + [_p]),
+    "t4k_linear_act_head_fwd": (_i, [_i] + [_p] * 6 + [_f] + [_p] * 5 + [_i] * 4 + [_p]),
     "t4k_mlp_head_bwd": (_i, [_p] * 10 + [_i] * 4 + [_p]),
     "t4k_activate_bwd": (_i, [_p, _p, _p, _l, _p]),
     "t4k_conv2d_bwd": (_i, [_p] * 6 + [_i] * 11 + [_p]),

@@ -622,3 +622,23 @@ def test_dataset_load_bit_exact(n, norm):
     hot = zeros(37, 10)
     ok(lib().t4k_onehot(C.c_void_p(l32.data_ptr()), ptr(hot), 37, 10, None))
     assert_exact(host(hot), orc.onehot(lab.astype(np.int32), 10), "onehot of u8 labels (label >= E -> class 0, loss.cpp:66)")
+
+
+@pytest.mark.parametrize("layer", [t4.L_RELU, t4.L_TANH, t4.L_LEAKYRL])
+@pytest.mark.parametrize("N,E1,EH,E0", [(512, 1960, 100, 10), (37, 300, 128, 32), (8, 64, 20, 3)])
+def test_linear_act_head_fwd_equals_the_two_calls(layer, N, E1, EH, E0):
+    """hidden linear + activation + classifier head with the split-K finish fused into the head kernel: bit-equal to
+    t4k_linear_act_fwd followed by t4k_mlp_head_fwd (same sums, same order)"""
+    X, W1, B1 = rnd(N, E1), rnd(EH, E1) * 0.05, rnd(EH)
+    W2, B2 = rnd(E0, EH) * 0.3, rnd(E0)
+    Xd, W1d, B1d, W2d, B2d = dev(X), dev(W1), dev(B1), dev(W2), dev(B2)
+    y1a, a1a, f1a, y2a, pa = zeros(N, EH), zeros(N, EH), zeros(N, EH), zeros(N, E0), zeros(N, E0)
+    y1b, a1b, f1b, y2b, pb, pd = zeros(N, EH), zeros(N, EH), zeros(N, EH), zeros(N, E0), zeros(N, E0), zeros(N, E0)
+    ok(lib().t4k_linear_act_fwd(layer, ptr(Xd), ptr(W1d), ptr(B1d), ptr(y1a), ptr(a1a), ptr(f1a), 0.1, N, EH, E1, None))
+    ok(lib().t4k_mlp_head_fwd(ptr(a1a), ptr(W2d), ptr(B2d), ptr(y2a), ptr(pa), N, E0, EH, None))
+    ok(lib().t4k_linear_act_head_fwd(layer, ptr(Xd), ptr(W1d), ptr(B1d), ptr(y1b), ptr(a1b), ptr(f1b), 0.1,
+                                     ptr(W2d), ptr(B2d), ptr(y2b), ptr(pb), ptr(pd), N, EH, E1, E0, None))
+    for a, b, nm in ((y1a, y1b, "Y1"), (a1a, a1b, "A1"), (f1a, f1b, "F1"), (y2a, y2b, "Y2"), (pa, pb, "P"), (pa, pd, "Pdup")):
+        assert_exact(host(b), host(a), nm)
+    assert lib().t4k_linear_act_head_fwd(layer, ptr(Xd), ptr(W1d), ptr(B1d), ptr(y1b), ptr(a1b), ptr(f1b), 0.1,
+                                         ptr(W2d), ptr(B2d), ptr(y2b), ptr(pb), None, N, 129, E1, E0, None) == t4.ENOSUP
