@@ -558,8 +558,9 @@ def main():
     kernels = [  # (name, call, algorithmic bytes = every operand read once / every result written once)
         ("conv_pool_relu_fwd (+input copy, +flatten)", lambda h: L.t4k_conv_pool_relu_fwd(p(I), p(F), p(Bv), p(I0), p(cO), p(pO), p(aO), p(aF), p(fO), N, 28, 28, 1, 28, 28, 10, 3, 1, 1, h),
          fl(I, I0, cO, pO, aO, aF, fO)),
-        ("linear_act_fwd 1960->100 (+bias+relu)", lambda h: L.t4k_linear_act_fwd(t4.L_RELU, p(fO), p(W1), p(B1), p(Y1), p(A1), p(F1), 0.0, N, 100, 1960, h), fl(fO, W1, Y1, A1, F1)),
-        ("mlp_head_fwd 100->10 (+bias+softmax)", lambda h: L.t4k_mlp_head_fwd(p(A1), p(W2), p(B2), p(Y2), p(Pp), N, 10, 100, h), fl(A1, W2, Y2, Pp)),
+        ("linear_act_head_fwd 1960->100 relu ->10 softmax (GEMM + fused finish/bias/relu/head)",
+         lambda h: L.t4k_linear_act_head_fwd(t4.L_RELU, p(fO), p(W1), p(B1), p(Y1), p(A1), p(F1), 0.0, p(W2), p(B2), p(Y2), p(Pp), None, N, 100, 1960, 10, h),
+         fl(fO, W1, Y1, A1, F1, W2, Y2, Pp)),
         ("loss.ce", lambda h: L.t4k_loss(t4.LOSS_CE, p(Pp), p(Tt), N * 10, N, p(lossd), h), fl(Pp, Tt)),
         ("mlp_head_bwd (p-y, dB2,dW2,dX2, relu', dB1)", lambda h: L.t4k_mlp_head_bwd(p(Pp), p(Tt), p(Y2), p(A1), p(F1), p(Y1), p(W2), p(dW2), p(dB2), p(dB1), N, 10, 100, 1, h),
          fl(Pp, Tt, Pp, Y2, A1, A1, F1, Y1, W2)),
