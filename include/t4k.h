@@ -62,9 +62,13 @@ enum t4k_rand_opt { T4K_UNIFORM = 0, T4K_NORMAL = 1 };
 enum t4k_gemm_engine { T4K_GEMM_AUTO = 0, T4K_GEMM_SIMT = 1,   /* FP32 FMA (gemm_simt.cu) */
                        T4K_GEMM_TC = 2,                        /* tcgen05 3xTF32, packed operand planes (gemm_tc.cu): large problems */
                        T4K_GEMM_TCF = 3,                       /* tcgen05 3xTF32, split fused into the kernel, one launch (gemm_tcf.cu): layer-sized problems */
-                       T4K_GEMM_TC_BF16X3 = 4 };               /* tcgen05 BF16x3 (a = hi + lo in bf16; hi*hi + hi*lo + lo*hi): twice the MMA rate of 3xTF32;
+                       T4K_GEMM_TC_BF16X3 = 4,                 /* tcgen05 BF16x3 (a = hi + lo in bf16; hi*hi + hi*lo + lo*hi): twice the MMA rate of 3xTF32;
                                                                 * measured 4.1e-6 of the result's rms at K=4096 (3xTF32: 1.8e-6; the reference's FP32-FMA
                                                                 * accumulation itself: ~3.8e-6).  AUTO takes it for M*N*K >= 2e10 only (T4K_GEMM_BIG=tf32: never) */
+                       T4K_GEMM_MMA = 5 };                     /* warp-level MMA (mma.sync m16n8k8 TF32) 3xTF32, 64x64 tiles, in-kernel split-K finish, one launch
+                                                                * (gemm_mma.cu): the layer-sized products (0.004 - 1.5 G multiply-adds), latency-bound class;
+                                                                * measured no faster than the FP32-FMA engine on B200 (legacy MMA rate), so AUTO takes it only with
+                                                                * T4K_GEMM_MMA=1 in the environment */
 
 /* ---- library / device ------------------------------------------------------------- */
 int         t4k_version(void);

@@ -18,6 +18,7 @@
 //             summed in sample order by k_wgrad_fin (deterministic; the reference uses atomics, nmath.tcu:307-336).
 // Shapes outside this envelope fall back to the first-generation kernels in conv.cu (same results).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace t4k {
 
@@ -213,6 +214,41 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
     float *sD = sRed + (size_t)(blockDim.x >> 5) * (3 * NG * 32 + 32);      // [nwin][C0] dY, overwritten with g = dY*mask
     const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int nI = H * W;
+    float *gO = p.convO + (int64_t)n * H * W * C0;
+    constexpr bool VEC = EXACT && ((2 * CM) & 3) == 0;
+    // the forward conv outputs of a window (4 pixels x C0), 128-bit loads: t_[dy*2+dx][c]
+    auto load_window = [&](int w, float (&t_)[4][CM]) {
+        const int j0 = w % Wp, i0 = w / Wp;
+        #pragma unroll
+        for (int dy = 0; dy < 2; dy++) {
+            const float *o = gO + ((2 * i0 + dy) * W + 2 * j0) * C0;
+            if constexpr (VEC) {
+                #pragma unroll
+                for (int e = 0; e < 2 * CM; e += 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(o + e);
+                    const float qq[4] = {q.x, q.y, q.z, q.w};
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (e + k < CM) t_[dy * 2][(e + k) % CM] = qq[k];
+                        else            t_[dy * 2 + 1][(e + k) % CM] = qq[k];
+                    }
+                }
+            } else {
+                #pragma unroll
+                for (int c = 0; c < CM; c++) if (c < C0) { t_[dy * 2][c] = o[c]; t_[dy * 2 + 1][c] = o[C0 + c]; }
+            }
+        }
+    };
+    // Global-latency plan: the conv outputs of this thread's first NPF windows are requested FIRST, so that their round trip
+    // overlaps the set-up below (pooled-tensor streams, taps, input tile, zeroing) instead of following its barrier; with
+    // 128-thread CTAs (two windows per thread, cpr2_bwd_threads) every HBM read of the CTA is in flight before the barrier.
+    constexpr int NPF = (CM <= 10) ? 2 : 1;             // 2 x 4 x CM registers held across the set-up
+    float tpre[NPF][4][CM];
+    #pragma unroll
+    for (int wi = 0; wi < NPF; wi++) {
+        const int w = threadIdx.x + wi * blockDim.x;
+        if (w < nwin) load_window(w, tpre[wi]);
+    }
     const int64_t gp = (int64_t)n * nP;
     const bool alp = (nP & 3) == 0 && aligned16(p.dY) && aligned16(p.actFc) && aligned16(p.actO) && aligned16(p.poolO);
     if (alp) {                                          // coalesced 128-bit streams of the pooled-size tensors
@@ -252,110 +288,96 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
         for (int t = threadIdx.x; t < nq; t += blockDim.x) *reinterpret_cast<float4*>(sR + 4 * t) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    float *gO = p.convO + (int64_t)n * H * W * C0;
-    constexpr bool VEC = EXACT && ((2 * CM) & 3) == 0;
     const int RSTRIDE = 3 * NG * 32 + 32;
     const int cs = HP * RW;                               // channel stride of the routed tile
     float accB[CM];
     #pragma unroll
     for (int c = 0; c < CM; c++) accB[c] = 0.0f;
+    // ---- phase A (once per window): relu backward is in sD, arg-max routing (first strict max in y,x order, nmath.tcu:535-549),
+    //      routed gradient back to HBM (in place of the conv output) and into the haloed channel-major tile
+    auto route_window = [&](int w, float (&t_)[4][CM]) {
+        const int j0 = w % Wp, i0 = w / Wp;
+        const int rb0 = 2 * i0 * RW + 2 * j0;              // window origin in the haloed routed tile (row 2*i0, col 2*j0)
+        const float *sg = sD + w * C0;
+        #pragma unroll
+        for (int c = 0; c < CM; c++) {
+            if (c < C0) {
+                const float g = sg[c];
+                float best = t_[0][c]; int arg = 0;
+                if (t_[1][c] > best) { best = t_[1][c]; arg = 1; }
+                if (t_[2][c] > best) { best = t_[2][c]; arg = 2; }
+                if (t_[3][c] > best) { best = t_[3][c]; arg = 3; }
+                t_[0][c] = (arg == 0) ? g : 0.0f; t_[1][c] = (arg == 1) ? g : 0.0f;
+                t_[2][c] = (arg == 2) ? g : 0.0f; t_[3][c] = (arg == 3) ? g : 0.0f;
+                accB[c] += g;
+                float *rr = sR + c * cs + rb0 + RW + 1;
+                rr[0] = t_[0][c]; rr[1] = t_[1][c]; rr[RW] = t_[2][c]; rr[RW + 1] = t_[3][c];
+            } else { t_[0][c] = t_[1][c] = t_[2][c] = t_[3][c] = 0.0f; }
+        }
+        #pragma unroll
+        for (int dy = 0; dy < 2; dy++) {
+            float *o = gO + ((2 * i0 + dy) * W + 2 * j0) * C0;
+            if constexpr (VEC) {
+                #pragma unroll
+                for (int e = 0; e < 2 * CM; e += 4) {
+                    float q[4];
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) q[k] = (e + k < CM) ? t_[dy * 2][(e + k) % CM] : t_[dy * 2 + 1][(e + k) % CM];
+                    stg4(o + e, make_float4(q[0], q[1], q[2], q[3]));
+                }
+            } else {
+                #pragma unroll
+                for (int c = 0; c < CM; c++) if (c < C0) { o[c] = t_[dy * 2][c]; o[C0 + c] = t_[dy * 2 + 1][c]; }
+            }
+        }
+    };
+    #pragma unroll
+    for (int wi = 0; wi < NPF; wi++) {
+        const int w = threadIdx.x + wi * blockDim.x;
+        if (w < nwin) route_window(w, tpre[wi]);
+    }
+    for (int w = threadIdx.x + NPF * blockDim.x; w < nwin; w += blockDim.x) {       // more than NPF windows per thread: load in place
+        float t_[4][CM];
+        load_window(w, t_);
+        route_window(w, t_);
+    }
+    // ---- dF: three ky passes over this thread's windows (its own routed values, read back from the tile it just wrote)
     float accF[NG * 32];                                  // current ky pass: [kx*CM + c]
-    // a thread may own several windows (nwin > blockDim): the routed values are recomputed per pass from smem
-    for (int ky = 0; ky < 3; ky++) {
+    for (int ky = 0; ky < 3 && p.train; ky++) {
         #pragma unroll
         for (int g = 0; g < NG * 32; g++) accF[g] = 0.0f;
         for (int w = threadIdx.x; w < nwin; w += blockDim.x) {
             const int j0 = w % Wp, i0 = w / Wp;
-            const int rb0 = 2 * i0 * RW + 2 * j0;          // window origin in the haloed routed tile (row 2*i0, col 2*j0)
+            const int rb0 = 2 * i0 * RW + 2 * j0;
             float r[4][CM];
-            if (ky == 0) {
-                // ---- phase A (once): flatten copy, relu backward, arg-max routing, write-back
-                float t_[4][CM];
-                #pragma unroll
-                for (int dy = 0; dy < 2; dy++) {
-                    const float *o = gO + ((2 * i0 + dy) * W + 2 * j0) * C0;
-                    if constexpr (VEC) {
-                        #pragma unroll
-                        for (int e = 0; e < 2 * CM; e += 4) {
-                            const float4 q = *reinterpret_cast<const float4*>(o + e);
-                            const float qq[4] = {q.x, q.y, q.z, q.w};
-                            #pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                if (e + k < CM) t_[dy * 2][(e + k) % CM] = qq[k];
-                                else            t_[dy * 2 + 1][(e + k) % CM] = qq[k];
-                            }
-                        }
-                    } else {
-                        #pragma unroll
-                        for (int c = 0; c < CM; c++) if (c < C0) { t_[dy * 2][c] = o[c]; t_[dy * 2 + 1][c] = o[C0 + c]; }
-                    }
-                }
-                const float *sg = sD + w * C0;
-                #pragma unroll
-                for (int c = 0; c < CM; c++) {
-                    if (c < C0) {
-                        const float g = sg[c];
-                        float best = t_[0][c]; int arg = 0;
-                        if (t_[1][c] > best) { best = t_[1][c]; arg = 1; }
-                        if (t_[2][c] > best) { best = t_[2][c]; arg = 2; }
-                        if (t_[3][c] > best) { best = t_[3][c]; arg = 3; }
-                        r[0][c] = (arg == 0) ? g : 0.0f; r[1][c] = (arg == 1) ? g : 0.0f;
-                        r[2][c] = (arg == 2) ? g : 0.0f; r[3][c] = (arg == 3) ? g : 0.0f;
-                        accB[c] += g;
-                        float *rr = sR + c * cs + rb0 + RW + 1;
-                        rr[0] = r[0][c]; rr[1] = r[1][c]; rr[RW] = r[2][c]; rr[RW + 1] = r[3][c];
-                    } else { r[0][c] = r[1][c] = r[2][c] = r[3][c] = 0.0f; }
-                }
-                #pragma unroll
-                for (int dy = 0; dy < 2; dy++) {
-                    float *o = gO + ((2 * i0 + dy) * W + 2 * j0) * C0;
-                    if constexpr (VEC) {
-                        #pragma unroll
-                        for (int e = 0; e < 2 * CM; e += 4) {
-                            float q[4];
-                            #pragma unroll
-                            for (int k = 0; k < 4; k++) q[k] = (e + k < CM) ? r[dy * 2][(e + k) % CM] : r[dy * 2 + 1][(e + k) % CM];
-                            stg4(o + e, make_float4(q[0], q[1], q[2], q[3]));
-                        }
-                    } else {
-                        #pragma unroll
-                        for (int c = 0; c < CM; c++) if (c < C0) { o[c] = r[dy * 2][c]; o[C0 + c] = r[dy * 2 + 1][c]; }
-                    }
-                }
-            } else {
-                #pragma unroll
-                for (int c = 0; c < CM; c++) {
-                    if (c < C0) {
-                        const float *rr = sR + c * cs + rb0 + RW + 1;
-                        r[0][c] = rr[0]; r[1][c] = rr[1]; r[2][c] = rr[RW]; r[3][c] = rr[RW + 1];
-                    } else { r[0][c] = r[1][c] = r[2][c] = r[3][c] = 0.0f; }
-                }
+            #pragma unroll
+            for (int c = 0; c < CM; c++) {
+                if (c < C0) {
+                    const float *rr = sR + c * cs + rb0 + RW + 1;
+                    r[0][c] = rr[0]; r[1][c] = rr[1]; r[2][c] = rr[RW]; r[3][c] = rr[RW + 1];
+                } else { r[0][c] = r[1][c] = r[2][c] = r[3][c] = 0.0f; }
             }
-            if (p.train) {
-                // dF[ky][kx][c] += Σ_{pixel (dy,dx) of the window} I[2*i0+dy+ky-1][2*j0+dx+kx-1] * r[dy*2+dx][c]
+            // dF[ky][kx][c] += Σ_{pixel (dy,dx) of the window} I[2*i0+dy+ky-1][2*j0+dx+kx-1] * r[dy*2+dx][c]
+            #pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+                const float *ip = sI + (2 * i0 + ky) * WP + 2 * j0 + kx;
+                const float i00 = ip[0], i01 = ip[1], i10 = ip[WP], i11 = ip[WP + 1];
                 #pragma unroll
-                for (int kx = 0; kx < 3; kx++) {
-                    const float *ip = sI + (2 * i0 + ky) * WP + 2 * j0 + kx;
-                    const float i00 = ip[0], i01 = ip[1], i10 = ip[WP], i11 = ip[WP + 1];
-                    #pragma unroll
-                    for (int c = 0; c < CM; c++) {
-                        float a = accF[kx * CM + c];
-                        a = fmaf(i00, r[0][c], a); a = fmaf(i01, r[1][c], a);
-                        a = fmaf(i10, r[2][c], a); a = fmaf(i11, r[3][c], a);
-                        accF[kx * CM + c] = a;
-                    }
+                for (int c = 0; c < CM; c++) {
+                    float a = accF[kx * CM + c];
+                    a = fmaf(i00, r[0][c], a); a = fmaf(i01, r[1][c], a);
+                    a = fmaf(i10, r[2][c], a); a = fmaf(i11, r[3][c], a);
+                    accF[kx * CM + c] = a;
                 }
             }
         }
-        if (p.train) {
+        #pragma unroll
+        for (int g = 0; g < NG; g++) {
+            float v[32];
             #pragma unroll
-            for (int g = 0; g < NG; g++) {
-                float v[32];
-                #pragma unroll
-                for (int k = 0; k < 32; k++) v[k] = accF[g * 32 + k];
-                const float s = warp_treduce32(v, lane);
-                sRed[warp * RSTRIDE + (ky * NG + g) * 32 + lane] = s;
-            }
+            for (int k = 0; k < 32; k++) v[k] = accF[g * 32 + k];
+            const float s = warp_treduce32(v, lane);
+            sRed[warp * RSTRIDE + (ky * NG + g) * 32 + lane] = s;
         }
     }
     if (p.train) {
@@ -435,6 +457,11 @@ static bool cpr2_bwd_ok(int H1, int W1, int C1, int H0, int W0, int C0, int KS, 
              ((nP + 3) & ~(size_t)3)) * sizeof(float);
     return *smem <= 100 * 1024 && (W1 & 1) == 0;
 }
+static int cpr2_bwd_threads(int nwin) {
+    const int full = (nwin + 31) & ~31;
+    if (full <= 128 || full > 256) return full > 256 ? 256 : (full < 32 ? 32 : full);
+    return (((nwin + 1) / 2) + 31) & ~31;                  // two windows per thread
+}
 static int win_threads(int nwin) { int t = (nwin + 31) & ~31; return t > 256 ? 256 : (t < 32 ? 32 : t); }
 
 } // namespace t4k
@@ -469,7 +496,12 @@ extern "C" int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float 
                                       int KS, int S, int P, int train, t4k_stream_t s) {
     if (!dY || !actO || !actF || !poolO || !convO || !Iio || !dXbuf || !F || N < 1 || (train && (!dF || !dB))) return T4K_EINVAL;
     int CM = 0; size_t smem = 0;
-    const int threads = win_threads((H0 / 2) * (W0 / 2));
+    // CTA width of the backward block: one thread per pool window (224 threads at 14x14 windows, 2 CTAs/SM at 126 registers:
+    // 512 samples = 1.73 waves), or HALF the windows per pass (128 threads x 4 CTAs/SM = 592 slots: the batch is one wave and each
+    // thread walks two windows).  T4K_CPR2_BWD_THREADS overrides (multiple of 32).
+    static int thr_env = -1;
+    if (thr_env < 0) { const char *e = getenv("T4K_CPR2_BWD_THREADS"); thr_env = e ? atoi(e) : 0; if (thr_env < 32 || thr_env > 256 || (thr_env & 31)) thr_env = 0; }
+    const int threads = thr_env ? thr_env : cpr2_bwd_threads((H0 / 2) * (W0 / 2));
     if (!cpr2_bwd_ok(H1, W1, C1, H0, W0, C0, KS, S, P, &CM, &smem, threads))
         return cpr_v1_bwd(dY, actO, actF, poolO, convO, Iio, dXbuf, F, dF, dB, N, H1, W1, C1, H0, W0, C0, KS, S, P, train, STRM(s));
     const int nF = 9 * C0;

@@ -27,6 +27,12 @@ bool gemm_tcf_ok(int tA, int tB, int M, int N, int K, int C, int batch);
 int  gemm_tcf(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
               int M, int N, int K, cudaStream_t st, GemmDeferred *defer = nullptr);
 
+// layer-sized single-launch GEMM on warp-level MMA (gemm_mma.cu): 3xTF32, split-K with in-kernel last-CTA finish; deferred-finish contract as above
+bool gemm_mma_ok(int M, int N, int K, int C, int batch);
+int  gemm_mma(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
+              int M, int N, int K, cudaStream_t st, GemmDeferred *defer = nullptr);
+bool layer_mma(int M, int N, int K, int C, int batch);      // policy: does AUTO take gemm_mma for this problem (T4K_GEMM_MMA=0: never)
+
 static inline cudaStream_t STRM(t4k_stream_t s) { return (cudaStream_t)s; }
 
 // ---- programmatic dependent launch (PDL).  A train step is a chain of ~12 short dependent kernels; with a plain

@@ -5,6 +5,7 @@
 // Tile 64x64x16, 256 threads, 4x4 register micro-tile, register-staged double buffering.
 // Bound: FP32 FMA pipe (128 FMA/clk/SM); used where launch latency, not math, dominates.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace t4k {
 
@@ -265,8 +266,10 @@ int gemm_simt(const float *A, const float *B, float *O, float alpha, float beta,
     // split K when the output grid cannot fill the machine and K is deep
     int splits = 1;
     const int sms = sm_count();
+    static int mult = 0;                                  // CTAs per SM the split aims at (T4K_SIMT_SPLIT_MULT, measured default below)
+    if (!mult) { const char *e = getenv("T4K_SIMT_SPLIT_MULT"); mult = e ? atoi(e) : 2; if (mult < 1 || mult > 8) mult = 2; }
     if (ctas < sms && K >= 8 * SBK) {
-        splits = (int)((2 * sms + ctas - 1) / ctas);
+        splits = (int)((mult * sms + ctas - 1) / ctas);
         const int maxs = K / (4 * SBK);
         if (splits > maxs) splits = maxs;
         if (splits > 64) splits = 64;

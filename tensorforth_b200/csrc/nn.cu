@@ -52,7 +52,8 @@ template<int L> static int launch_fin(const GemmDeferred &d, int64_t MN, int E0,
 static int linear_act_fwd(int layer, const float *X, const float *W, const float *B, float *Y, float *A, float *F, float alpha,
                           int N, int E0, int E1, cudaStream_t st) {
     GemmDeferred d{nullptr, 1};
-    int rc = gemm_tcf_ok(0, 1, N, E0, E1, 1, 1) ? gemm_tcf(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, st, &d)       // tensor cores for layer-sized products
+    int rc = layer_mma(N, E0, E1, 1, 1)         ? gemm_mma(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, st, &d)       // tensor cores for layer-sized products
+           : gemm_tcf_ok(0, 1, N, E0, E1, 1, 1) ? gemm_tcf(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, st, &d)
                                                 : gemm_simt(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, 1, 1, 0, 0, 0, st, &d);
     if (rc) return rc;
     const int64_t MN = (int64_t)N * E0;
@@ -365,7 +366,8 @@ extern "C" int t4k_linear_act_head_fwd(int layer, const float *X, const float *W
     if (E0 > 32 || EH > 128 || (size_t)E0 * EH * sizeof(float) > 40 * 1024) return T4K_ENOSUP;
     cudaStream_t st = STRM(s);
     GemmDeferred d{nullptr, 1};
-    int rc = gemm_tcf_ok(0, 1, N, EH, E1, 1, 1) ? gemm_tcf(X, W1, Y1, 1.0f, 0.0f, 0, 1, N, EH, E1, st, &d)
+    int rc = layer_mma(N, EH, E1, 1, 1)         ? gemm_mma(X, W1, Y1, 1.0f, 0.0f, 0, 1, N, EH, E1, st, &d)
+           : gemm_tcf_ok(0, 1, N, EH, E1, 1, 1) ? gemm_tcf(X, W1, Y1, 1.0f, 0.0f, 0, 1, N, EH, E1, st, &d)
                                                 : gemm_simt(X, W1, Y1, 1.0f, 0.0f, 0, 1, N, EH, E1, 1, 1, 0, 0, 0, st, &d);
     if (rc) return rc;
     const int64_t MN = (int64_t)N * EH;

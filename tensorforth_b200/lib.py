@@ -16,7 +16,7 @@ SO_PATH = os.path.join(_HERE, "libt4k.so")
  L_DCONV) = range(19)
 LOSS_MSE, LOSS_BCE, LOSS_CE, LOSS_NLL = range(4)
 UNIFORM, NORMAL = 0, 1
-GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_TCF, GEMM_TC_BF16X3 = 0, 1, 2, 3, 4
+GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_TCF, GEMM_TC_BF16X3, GEMM_MMA = 0, 1, 2, 3, 4, 5
 EINVAL, ENOSUP, ENOMEM = -1, -2, -3
 COMM_HANDLE_BYTES = 64
 

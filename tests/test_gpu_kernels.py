@@ -160,9 +160,9 @@ def gemm_ref64(A, B, O, alpha, beta, tA, tB):
     return alpha * (a @ b) + beta * O.astype(np.float64)
 
 
-@pytest.mark.parametrize("engine", [t4.GEMM_SIMT, t4.GEMM_TC, t4.GEMM_TCF])
+@pytest.mark.parametrize("engine", [t4.GEMM_SIMT, t4.GEMM_TC, t4.GEMM_TCF, t4.GEMM_MMA])
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
-@pytest.mark.parametrize("M,N,K", [(2, 2, 3), (64, 64, 64), (128, 128, 32), (200, 100, 70), (130, 260, 513), (512, 100, 1960)])
+@pytest.mark.parametrize("M,N,K", [(2, 2, 3), (64, 64, 64), (128, 128, 32), (200, 100, 70), (67, 63, 45), (130, 260, 513), (512, 100, 1960)])
 def test_gemm_engines(engine, tA, tB, M, N, K):
     A = rnd(K, M) if tA else rnd(M, K)
     B = rnd(N, K) if tB else rnd(K, N)
@@ -178,7 +178,7 @@ def test_gemm_engines(engine, tA, tB, M, N, K):
 def test_gemm_beta0_ignores_garbage():
     M = N = K = 96
     A, B = rnd(M, K), rnd(K, N)
-    for eng in (t4.GEMM_SIMT, t4.GEMM_TC, t4.GEMM_TCF):
+    for eng in (t4.GEMM_SIMT, t4.GEMM_TC, t4.GEMM_TCF, t4.GEMM_MMA):
         o = dev(np.full((M, N), np.nan, np.float32))
         ok(lib().t4k_gemm_ex(eng, ptr(dev(A)), ptr(dev(B)), ptr(o), 1.0, 0.0, 0, 0, M, N, K, 1, 1, 0, 0, 0, None))
         assert_close(host(o), gemm_ref64(A, B, np.zeros((M, N)), 1, 0, 0, 0), rtol=2e-5)
@@ -210,18 +210,35 @@ def test_gemm_tc_large_vs_f64():
 @pytest.mark.parametrize("tA,tB,M,N,K", [(0, 1, 1024, 512, 784), (1, 0, 512, 784, 1024), (0, 0, 1024, 784, 512),     # GAN D layer 1: fwd / dW / dX
                                          (0, 1, 512, 100, 1960), (1, 0, 100, 1960, 512), (0, 0, 512, 1960, 100),     # MNIST linear 1960->100
                                          (0, 0, 300, 132, 2052), (1, 1, 129, 257, 36)])                              # ragged tiles, K tails
-def test_gemm_tcf_layer_shapes_vs_f64(tA, tB, M, N, K):
-    """the single-launch tensor-core engine (in-kernel 3xTF32 split, split-K) on the linear-layer shapes: FP32-grade vs exact"""
+@pytest.mark.parametrize("engine", [t4.GEMM_TCF, t4.GEMM_MMA, t4.GEMM_AUTO])
+def test_gemm_tcf_layer_shapes_vs_f64(engine, tA, tB, M, N, K):
+    """the single-launch tensor-core engines (in-kernel 3xTF32 split, split-K: tcgen05 `tcf`, warp-level `mma` with its last-CTA
+    finish, and whatever AUTO picks) on the linear-layer shapes: FP32-grade vs exact"""
     A = rnd(K, M) if tA else rnd(M, K)
     B = rnd(N, K) if tB else rnd(K, N)
     O0 = rnd(M, N)
     for alpha, beta in ((1.0, 0.0), (1.0, 1.0)):           # beta = 1: the dW accumulation of Model::_blinear
         o = dev(O0)
-        ok(lib().t4k_gemm_ex(t4.GEMM_TCF, ptr(dev(A)), ptr(dev(B)), ptr(o), alpha, beta, tA, tB, M, N, K, 1, 1, 0, 0, 0, None), "gemm_tcf")
+        ok(lib().t4k_gemm_ex(engine, ptr(dev(A)), ptr(dev(B)), ptr(o), alpha, beta, tA, tB, M, N, K, 1, 1, 0, 0, 0, None), "gemm layer engine")
         ref = gemm_ref64(A, B, O0, alpha, beta, tA, tB)
         got = host(o)
         assert_close(got, ref, rtol=1e-5, what="tcf vs f64")
         assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-6
+
+
+def test_gemm_mma_counters_survive_ring_wrap():
+    """the warp-MMA engine finishes split-K in the last CTA of each tile, counted on a ring of self-resetting arrival counters
+    (gemm_mma.cu: tile_counters): more calls than the ring holds must keep giving the same answer"""
+    M, N, K = 128, 128, 1024                               # 4 tiles x 8 splits; the ring holds 65536 counters
+    A, B = rnd(M, K), rnd(N, K)
+    dA, dB_, o = dev(A), dev(B), zeros(M, N)
+    ref = gemm_ref64(A, B, np.zeros((M, N)), 1.0, 0.0, 0, 1)
+    L = lib()
+    for i in range(17000):
+        rc = L.t4k_gemm_ex(t4.GEMM_MMA, ptr(dA), ptr(dB_), ptr(o), 1.0, 0.0, 0, 1, M, N, K, 1, 1, 0, 0, 0, None)
+        assert rc == 0
+        if i in (0, 16383, 16384, 16999):
+            assert_close(host(o), ref, rtol=1e-5, what="mma split-K call %d" % i)
 
 
 @pytest.mark.parametrize("tA,tB", [(0, 0), (1, 1)])
