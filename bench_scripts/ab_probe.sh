@@ -1,11 +1,8 @@
 #!/bin/bash
-# A/B of tuning knobs on the MNIST step (development aid): T4K_CPR2_BWD_THREADS, T4K_SIMT_SPLIT_MULT, T4K_GEMM_MMA
+# development aid: GPU tests + the MNIST step bench (+ optional ncu capture: AB_NCU=<kernel regex> AB_NCU_WHAT=<perf_probe section>)
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -x -q -k "cpr or conv_pool or block or fused or train_steps or step_graph or golden or gemm_engines" > gpurun_out/ab_pytest.log 2>&1; echo "pytest rc=$?"
+timeout 600 python -m pytest tests -x -q -m gpu ${AB_K:+-k "$AB_K"} > gpurun_out/ab_pytest.log 2>&1; echo "pytest rc=$?"
 tail -3 gpurun_out/ab_pytest.log
-for thr in 224 128; do
-  echo "== cpr bwd threads=$thr"; T4K_CPR2_BWD_THREADS=$thr timeout 120 python tests/perf_probe.py cpr 2>&1 | tail -1
-done
 run() { echo "== bench $1"; env $2 timeout 200 python bench.py --no-extras --no-cpu-baseline > gpurun_out/ab_bench_$1.json 2> gpurun_out/ab_bench_$1.err; python - <<PY
 import json
 try:
@@ -17,6 +14,6 @@ except Exception as e:
 PY
 }
 run default "T4K_X=1"
-run cpr224 "T4K_CPR2_BWD_THREADS=224"
-run mult3 "T4K_SIMT_SPLIT_MULT=3"
-run mult4 "T4K_SIMT_SPLIT_MULT=4"
+if [ -n "$AB_NCU" ]; then
+  timeout 240 ncu --set full --clock-control none --import-source on -k regex:$AB_NCU -s ${AB_NCU_SKIP:-3} -c 1 -o gpurun_out/ab_ncu -f python tests/perf_probe.py ${AB_NCU_WHAT:-cpr} > gpurun_out/ab_ncu.log 2>&1; tail -1 gpurun_out/ab_ncu.log
+fi

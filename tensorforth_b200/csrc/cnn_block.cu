@@ -59,28 +59,36 @@ __global__ void __launch_bounds__(256, CPR2_FWD_MINB) k_cpr2_fwd(Cpr2P p) {
     const int n = blockIdx.x;
     const int nI = H * W * C1;
     const float *gI = p.I + (int64_t)n * nI;
+    // Order of issue (one global round trip instead of three): the sample's input first (HBM, into a register), then taps and bias
+    // as asynchronous copies straight into shared memory, then the halo zeros; the input is consumed last.
+    const int rowp = WP * C1;
+    const int rowf = W * C1;
+    const bool vecI = (rowf & 3) == 0 && aligned16(p.I) && (!p.Icopy || aligned16(p.Icopy));
+    const int rq = rowf >> 2;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool has0 = vecI && (int)threadIdx.x < H * rq;
+    if (has0) { const int y = threadIdx.x / rq, q = threadIdx.x - y * rq; v0 = ldg4(gI + y * rowf + 4 * q); }
     for (int t = threadIdx.x; t < nFp; t += blockDim.x) {
         const int c = t % CP; int r = t / CP; const int c1 = r % C1; r /= C1;        // r = ky*KS+kx
-        sF[t] = (c < C0) ? __ldg(p.F + ((int64_t)c1 * KS * KS + r) * C0 + c) : 0.0f;
+        cp_async4(sF + t, p.F + ((c < C0) ? ((int64_t)c1 * KS * KS + r) * C0 + c : 0), c < C0);
     }
-    for (int t = threadIdx.x; t < CP; t += blockDim.x) sB[t] = (t < C0) ? __ldg(p.B + t) : 0.0f;
+    for (int t = threadIdx.x; t < CP; t += blockDim.x) cp_async4(sB + t, p.B + ((t < C0) ? t : 0), t < C0);
+    cp_async_commit();
     // halo zeros (top/bottom rows, left/right columns), then the interior from 128-bit loads (else scalar)
-    const int rowp = WP * C1;
     for (int t = threadIdx.x; t < P * rowp; t += blockDim.x) { sI[t] = 0.0f; sI[(HP - P) * rowp + t] = 0.0f; }
     for (int t = threadIdx.x; t < H * P * C1; t += blockDim.x) {
         const int y = t / (P * C1), q = t - y * (P * C1);
         sI[(y + P) * rowp + q] = 0.0f; sI[(y + P) * rowp + (W + P) * C1 + q] = 0.0f;
     }
-    const int rowf = W * C1;
-    if ((rowf & 3) == 0 && aligned16(p.I) && (!p.Icopy || aligned16(p.Icopy))) {
-        const int rq = rowf >> 2;
-        for (int t = threadIdx.x; t < H * rq; t += blockDim.x) {
+    if (vecI) {
+        auto put = [&](int t, const float4 v) {
             const int y = t / rq, q = t - y * rq;
-            const float4 v = ldg4(gI + y * rowf + 4 * q);
             if (p.Icopy) stg4(p.Icopy + (int64_t)n * nI + y * rowf + 4 * q, v);       // Model::forward: n0 = input
             float *d = sI + ((y + P) * WP + P) * C1 + 4 * q;
             d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
+        };
+        if (has0) put(threadIdx.x, v0);
+        for (int t = threadIdx.x + blockDim.x; t < H * rq; t += blockDim.x) { const int y = t / rq, q = t - y * rq; put(t, ldg4(gI + y * rowf + 4 * q)); }
     } else {
         for (int t = threadIdx.x; t < nI; t += blockDim.x) {
             const int y = t / rowf, q = t - y * rowf;
@@ -89,6 +97,7 @@ __global__ void __launch_bounds__(256, CPR2_FWD_MINB) k_cpr2_fwd(Cpr2P p) {
             sI[((y + P) * WP + P) * C1 + q] = v;
         }
     }
+    cp_async_wait_all();
     __syncthreads();
     float *gO = p.convO + (int64_t)n * H * W * C0;
     constexpr bool VEC = C0T > 0 && (C0T & 1) == 0;        // host checks 16-byte alignment of the tensors
@@ -242,23 +251,49 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
     // Global-latency plan: the conv outputs of this thread's first NPF windows are requested FIRST, so that their round trip
     // overlaps the set-up below (pooled-tensor streams, taps, input tile, zeroing) instead of following its barrier; with
     // 128-thread CTAs (two windows per thread, cpr2_bwd_threads) every HBM read of the CTA is in flight before the barrier.
+    // Order of issue: (1) asynchronous copies global -> shared (no registers, no stall): dY -> sD, the forward input -> sI, the
+    // taps -> sF / sFx; (2) the relu mask, first chunk, into registers; (3) the window prefetch; (4) shared-memory zeroing while
+    // all of that is in flight; then the copies are awaited and consumed.
     constexpr int NPF = (CM <= 10) ? 2 : 1;             // 2 x 4 x CM registers held across the set-up
+    constexpr int MU = 4;                               // mask quads per thread held in registers per chunk
+    const int64_t gp = (int64_t)n * nP;
+    const bool alp = (nP & 3) == 0 && aligned16(p.dY) && aligned16(p.actFc) && aligned16(p.actO) && aligned16(p.poolO);
+    const int nq4 = nP >> 2;
+    float *gI = p.Iio + (int64_t)n * nI;
+    if (alp) for (int t = threadIdx.x; t < nq4; t += blockDim.x) cp_async16(sD + 4 * t, p.dY + gp + 4 * t);
+    for (int t = threadIdx.x; t < nI; t += blockDim.x) { const int y = t / W; cp_async4(sI + (y + 1) * WP + 1 + (t - y * W), gI + t, true); }
+    for (int t = threadIdx.x; t < 9 * CM; t += blockDim.x) { const int c = t % CM, tap = t / CM; cp_async4(sF + t, p.F + (c < C0 ? tap * C0 + c : 0), c < C0); }
+    for (int t = threadIdx.x; t < 12 * CM; t += blockDim.x) { const int k = t % 12, c = t / 12; const bool on = (c < C0 && k < 9); cp_async4(sFx + t, p.F + (on ? (8 - k) * C0 + c : 0), on); }
+    cp_async_commit();
+    float4 mv[MU];
+    if (alp) {
+        #pragma unroll
+        for (int u = 0; u < MU; u++) { const int t = threadIdx.x + u * blockDim.x; if (t < nq4) mv[u] = ldg4(p.actFc + gp + 4 * t); }
+    }
     float tpre[NPF][4][CM];
     #pragma unroll
     for (int wi = 0; wi < NPF; wi++) {
         const int w = threadIdx.x + wi * blockDim.x;
         if (w < nwin) load_window(w, tpre[wi]);
     }
-    const int64_t gp = (int64_t)n * nP;
-    const bool alp = (nP & 3) == 0 && aligned16(p.dY) && aligned16(p.actFc) && aligned16(p.actO) && aligned16(p.poolO);
+    for (int t = threadIdx.x; t < WP; t += blockDim.x) { sI[t] = 0.0f; sI[(HP - 1) * WP + t] = 0.0f; }
+    for (int t = threadIdx.x; t < H; t += blockDim.x) { sI[(t + 1) * WP] = 0.0f; sI[(t + 1) * WP + W + 1] = 0.0f; }
+    {   // zero the whole routed tile (halo + padding stay zero; the interior is overwritten in phase A after the barrier)
+        const int nq = (int)((((size_t)C0 * HP * RW + 3) & ~(size_t)3) >> 2);
+        for (int t = threadIdx.x; t < nq; t += blockDim.x) *reinterpret_cast<float4*>(sR + 4 * t) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_wait_all();                                // this thread's own copies have landed (it consumes only those before the barrier)
     if (alp) {                                          // coalesced 128-bit streams of the pooled-size tensors
-        for (int t = threadIdx.x; t < (nP >> 2); t += blockDim.x) {
-            const float4 d = ldg4(p.dY + gp + 4 * t), m = ldg4(p.actFc + gp + 4 * t);
+        auto consume = [&](int t, const float4 m) {
+            const float4 d = *reinterpret_cast<const float4*>(sD + 4 * t);
             if (p.actO != p.dY) stg4(p.actO + gp + 4 * t, d);                         // flatten backward: in = out
             const float4 g = make_float4(__fmul_rn(d.x, m.x), __fmul_rn(d.y, m.y), __fmul_rn(d.z, m.z), __fmul_rn(d.w, m.w));
             stg4(p.poolO + gp + 4 * t, g);                                            // _bactivate: in = out * mask
             *reinterpret_cast<float4*>(sD + 4 * t) = g;
-        }
+        };
+        #pragma unroll
+        for (int u = 0; u < MU; u++) { const int t = threadIdx.x + u * blockDim.x; if (t < nq4) consume(t, mv[u]); }
+        for (int t = threadIdx.x + MU * blockDim.x; t < nq4; t += blockDim.x) consume(t, ldg4(p.actFc + gp + 4 * t));
     } else {
         for (int t = threadIdx.x; t < nP; t += blockDim.x) {
             const float d = p.dY[gp + t];
@@ -266,26 +301,6 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
             const float g = __fmul_rn(d, p.actFc[gp + t]);
             p.poolO[gp + t] = g; sD[t] = g;
         }
-    }
-    float *gI = p.Iio + (int64_t)n * nI;
-    for (int t = threadIdx.x; t < 9 * CM; t += blockDim.x) { const int c = t % CM, tap = t / CM; sF[t] = (c < C0) ? __ldg(p.F + tap * C0 + c) : 0.0f; }
-    for (int t = threadIdx.x; t < 12 * CM; t += blockDim.x) { const int k = t % 12, c = t / 12; sFx[t] = (c < C0 && k < 9) ? __ldg(p.F + (8 - k) * C0 + c) : 0.0f; }
-    for (int t = threadIdx.x; t < WP; t += blockDim.x) { sI[t] = 0.0f; sI[(HP - 1) * WP + t] = 0.0f; }
-    for (int t = threadIdx.x; t < H; t += blockDim.x) { sI[(t + 1) * WP] = 0.0f; sI[(t + 1) * WP + W + 1] = 0.0f; }
-    if ((W & 3) == 0 && aligned16(p.Iio)) {
-        const int rq = W >> 2;
-        for (int t = threadIdx.x; t < H * rq; t += blockDim.x) {
-            const int y = t / rq, q = t - y * rq;
-            const float4 v = *reinterpret_cast<const float4*>(gI + y * W + 4 * q);
-            float *d = sI + (y + 1) * WP + 1 + 4 * q;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
-    } else {
-        for (int t = threadIdx.x; t < nI; t += blockDim.x) { const int y = t / W; sI[(y + 1) * WP + 1 + (t - y * W)] = gI[t]; }
-    }
-    {   // zero the whole routed tile (halo + padding stay zero; the interior is overwritten in phase A after the barrier)
-        const int nq = (int)((((size_t)C0 * HP * RW + 3) & ~(size_t)3) >> 2);
-        for (int t = threadIdx.x; t < nq; t += blockDim.x) *reinterpret_cast<float4*>(sR + 4 * t) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
     const int RSTRIDE = 3 * NG * 32 + 32;

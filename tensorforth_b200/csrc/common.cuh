@@ -102,6 +102,16 @@ __device__ __forceinline__ float block_sum(float v, float *sm32) {
     __syncthreads();
     return v;
 }
+// ------------------------------------------------------------------ asynchronous global -> shared copies (LDGSTS)
+__device__ __forceinline__ void cp_async16(float *dst, const float *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+// 4-byte copy; on == false writes a zero (src-size 0) and reads nothing
+__device__ __forceinline__ void cp_async4(float *dst, const float *src, bool on) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(on ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()   { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // 128-bit streaming global access
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void   stg4(float *p, float4 v) { *reinterpret_cast<float4*>(p) = v; }

@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(T4K_THREADS) k_head_fwd(const float *__restric
                                                           float *Y, float *P, float *P2, int N, int E0, int E1) {
     extern __shared__ float sW[];                      // [E0][E1]
     pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
-    for (int t = threadIdx.x; t < E0 * E1; t += blockDim.x) sW[t] = __ldg(W + t);
+    for (int t = threadIdx.x; t < E0 * E1; t += blockDim.x) cp_async4(sW + t, W + t, true);     // all copies in flight at once (a load -> store loop pays one L2 round trip per trip)
+    cp_async_commit(); cp_async_wait_all();
     __syncthreads();
     const int lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
     for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < N; row += nw) {
@@ -126,19 +127,16 @@ __global__ void __launch_bounds__(T4K_THREADS) k_fin_head_fwd(const float *__res
                                                               int N, int E0, int E1) {
     extern __shared__ float sW[];                      // [E0][E1]
     pdl_wait(); pdl_trigger();
-    for (int t = threadIdx.x; t < E0 * E1; t += blockDim.x) sW[t] = __ldg(W2 + t);
-    __syncthreads();
+    // W2 arrives by asynchronous copies while the split-K partials of the warp's first row are being summed: the barrier that
+    // publishes sW sits behind those loads, so the kernel pays one L2 round trip for both instead of one per fill-loop trip
+    for (int t = threadIdx.x; t < E0 * E1; t += blockDim.x) cp_async4(sW + t, W2 + t, true);
+    cp_async_commit();
     const int lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
-    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < N; row += nw) {
-        float acc[32];
-        #pragma unroll
-        for (int k = 0; k < 32; k++) acc[k] = 0.0f;
-        const int64_t r0 = (int64_t)row * E1;
-        // the lane's (up to) four hidden units, all partial loads of a split in flight together; sums in split order as k_linear_fin
-        float sv[4];
+    // the lane's (up to) four hidden units; eight splits' loads in flight together; sums in split order as k_linear_fin
+    auto sum_parts = [&](int64_t r0, float (&sv)[4]) {
         #pragma unroll
         for (int j = 0; j < 4; j++) { const int e = lane + 32 * j; sv[j] = (e < E1) ? part[r0 + e] : 0.0f; }
-        #pragma unroll 4
+        #pragma unroll 8
         for (int k = 1; k < splits; k++) {
             float tv[4];
             #pragma unroll
@@ -146,11 +144,29 @@ __global__ void __launch_bounds__(T4K_THREADS) k_fin_head_fwd(const float *__res
             #pragma unroll
             for (int j = 0; j < 4; j++) sv[j] += tv[j];
         }
+    };
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float sv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    bool have = row < N;
+    if (have) sum_parts((int64_t)row * E1, sv);
+    float b1v[4];                                          // biases: requested with everything else, not after the barrier
+    #pragma unroll
+    for (int j = 0; j < 4; j++) { const int e = lane + 32 * j; b1v[j] = (e < E1) ? __ldg(B1 + e) : 0.0f; }
+    const float b2v = (lane < E0) ? __ldg(B2 + lane) : 0.0f;
+    cp_async_wait_all();
+    __syncthreads();
+    for (; row < N; row += nw) {
+        float acc[32];
+        #pragma unroll
+        for (int k = 0; k < 32; k++) acc[k] = 0.0f;
+        const int64_t r0 = (int64_t)row * E1;
+        if (!have) sum_parts(r0, sv);
+        have = false;
         #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int e = lane + 32 * j;
             if (e < E1) {
-                const float s = sv[j] + __ldg(B1 + e);
+                const float s = sv[j] + b1v[j];
                 Y1[r0 + e] = s;
                 float xv = s;
                 if (L != T4K_L_NONE) { float o, f = (L == T4K_L_DROPOUT) ? F1[r0 + e] : 0.0f; act<L>(s, alpha, o, f); A1[r0 + e] = o; F1[r0 + e] = f; xv = o; }
@@ -160,7 +176,7 @@ __global__ void __launch_bounds__(T4K_THREADS) k_fin_head_fwd(const float *__res
         }
         float y = warp_treduce32(acc, lane);
         const bool on = lane < E0;
-        if (on) y += __ldg(B2 + lane);
+        if (on) y += b2v;
         const float mx = warp_max(on ? y : -FLT_MAX);
         const float ex = on ? __expf(y - mx) : 0.0f;
         const float sm = warp_sum(ex);
@@ -201,16 +217,18 @@ __global__ void __cluster_dims__(HB_CTAS, 1, 1) __launch_bounds__(T4K_THREADS) k
     float *sW = sm;                                    // [E0][128]       rows zero-padded: no column guards in the hot loop
     float *sPart = sm + E0 * 128;                      // [nE]            this CTA's partial (read by the whole cluster)
     float *sAcc = sPart + ((nE + 3) & ~3);             // [nwarps][nE]    per-warp partials
-    for (int t = threadIdx.x; t < E0 * 128; t += blockDim.x) { const int e = t & 127, k = t >> 7; sW[t] = (e < E1) ? __ldg(p.W + k * E1 + e) : 0.0f; }
-    __syncthreads();
+    // W by asynchronous copies (zero-filled padding), the warp's first rows requested before the barrier that publishes it:
+    // one global round trip for both (a load -> store fill loop pays one L2 round trip per trip, five of them here)
+    for (int t = threadIdx.x; t < E0 * 128; t += blockDim.x) { const int e = t & 127, k = t >> 7; cp_async4(sW + t, p.W + ((e < E1) ? k * E1 + e : 0), e < E1); }
+    cp_async_commit();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int nw = gridDim.x * nwarps;
     float accW[KM][4], accB1[4], accB = 0.0f;
     #pragma unroll
     for (int k = 0; k < KM; k++) { accW[k][0] = accW[k][1] = accW[k][2] = accW[k][3] = 0.0f; }
     accB1[0] = accB1[1] = accB1[2] = accB1[3] = 0.0f;
-    for (int row0 = (blockIdx.x * nwarps + warp) * HB_ROWS; row0 < p.N; row0 += nw * HB_ROWS) {
-        float d[HB_ROWS], x[HB_ROWS][4], f[HB_ROWS][4];
+    float d[HB_ROWS], x[HB_ROWS][4], f[HB_ROWS][4];
+    auto load_rows = [&](int row0) {                                               // rows past N read nothing (zeros)
         #pragma unroll
         for (int r = 0; r < HB_ROWS; r++) {
             const int row = row0 + r;
@@ -225,6 +243,15 @@ __global__ void __cluster_dims__(HB_CTAS, 1, 1) __launch_bounds__(T4K_THREADS) k
                 f[r][j] = (ev && p.F1) ? p.F1[(int64_t)row * E1 + e] : 1.0f;
             }
         }
+    };
+    int row0 = (blockIdx.x * nwarps + warp) * HB_ROWS;
+    bool have = true;
+    load_rows(row0);
+    cp_async_wait_all();
+    __syncthreads();
+    for (; row0 < p.N; row0 += nw * HB_ROWS) {
+        if (!have) load_rows(row0);
+        have = false;
         #pragma unroll
         for (int r = 0; r < HB_ROWS; r++) {
             const int row = row0 + r;
