@@ -212,6 +212,14 @@ int t4k_batchnorm_bwd(const float *dO, const float *XH, float *dX, const float *
 int t4k_conv_pool_relu_fwd(const float *I, const float *F, const float *B, float *Icopy, float *convO, float *poolO, float *actO,
                            float *actF, float *flatO, int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P,
                            t4k_stream_t s);
+/* the forward block fed from a staged U8 mini-batch: Dataset::_load (src/mu/dataset.cu:124-152: d = ((float)u8 - mean) * scale) +
+ * Model::onehot (src/nn/loss.cpp:47-72) + the block in ONE launch.  data = the dataset tensor [N,H1,W1,C1] (first feedN samples
+ * rewritten, the rest kept: partial batch as _load), Icopy = the model's input layer, lab32/hot as t4k_dataset_load.  Shapes
+ * outside the fused envelope run t4k_dataset_load then t4k_conv_pool_relu_fwd (same results). */
+int t4k_conv_pool_relu_fwd_feed(const uint8_t *u8I, const uint8_t *u8L, int feedN, float mean, float scale, int32_t *lab32,
+                                float *hot, int E, float *data, const float *F, const float *B, float *Icopy, float *convO,
+                                float *poolO, float *actO, float *actF, float *flatO, int N, int H1, int W1, int C1,
+                                int H0, int W0, int C0, int KS, int S, int P, t4k_stream_t s);
 int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,
                            const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
                            int KS, int S, int P, int train, t4k_stream_t s);

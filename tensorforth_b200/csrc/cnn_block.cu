@@ -36,6 +36,9 @@ struct Cpr2P {
     const float *I, *F, *B, *dY, *actFc;
     float *Icopy, *convO, *poolO, *actO, *actF, *flatO, *Iio, *dXbuf, *part;
     int H, W, C1, C0, train;
+    // dataset feed folded into the forward block (t4k_conv_pool_relu_fwd_feed): samples n < feedN take their pixels from the staged
+    // U8 block — d = ((float)u8 - mean) * scale as t4k_dataset_load — and write them to the dataset tensor (I) as well
+    const uint8_t *u8I, *u8L; float mean, scale; int32_t *lab32; float *hot; int E, feedN;
 };
 
 // ------------------------------------------------------------------ forward
@@ -43,7 +46,7 @@ struct Cpr2P {
 // Global traffic is kept at full-sector granularity: the sample's input arrives as 128-bit loads, the conv pixels
 // leave the registers as 128-bit stores of contiguous 2*C0 runs, the pooled values are staged in smem and the four
 // pooled tensors (pool, relu, mask, flatten) leave as contiguous 128-bit streams.
-template<int KS, int CP, int C0T, int C1T>
+template<int KS, int CP, int C0T, int C1T, bool FEED = false>
 __global__ void __launch_bounds__(256, CPR2_FWD_MINB) k_cpr2_fwd(Cpr2P p) {
     extern __shared__ __align__(16) float sm[];
     pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
@@ -66,8 +69,16 @@ __global__ void __launch_bounds__(256, CPR2_FWD_MINB) k_cpr2_fwd(Cpr2P p) {
     const bool vecI = (rowf & 3) == 0 && aligned16(p.I) && (!p.Icopy || aligned16(p.Icopy));
     const int rq = rowf >> 2;
     float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool has0 = vecI && (int)threadIdx.x < H * rq;
+    const bool feed = FEED && n < p.feedN;                // host-checked for FEED: vecI, nI % 16 == 0, 16-byte aligned blocks, E <= blockDim
+    const bool has0 = vecI && !feed && (int)threadIdx.x < H * rq;
     if (has0) { const int y = threadIdx.x / rq, q = threadIdx.x - y * rq; v0 = ldg4(gI + y * rowf + 4 * q); }
+    uint4 u0 = make_uint4(0u, 0u, 0u, 0u);
+    int lab = 0;
+    const uint8_t *gU = FEED ? p.u8I + (int64_t)n * nI : nullptr;
+    if (FEED && feed) {
+        if ((int)threadIdx.x < (nI >> 4)) u0 = __ldg(reinterpret_cast<const uint4*>(gU) + threadIdx.x);
+        if ((int)threadIdx.x < p.E) lab = (int)__ldg(p.u8L + n);
+    }
     for (int t = threadIdx.x; t < nFp; t += blockDim.x) {
         const int c = t % CP; int r = t / CP; const int c1 = r % C1; r /= C1;        // r = ky*KS+kx
         cp_async4(sF + t, p.F + ((c < C0) ? ((int64_t)c1 * KS * KS + r) * C0 + c : 0), c < C0);
@@ -80,7 +91,31 @@ __global__ void __launch_bounds__(256, CPR2_FWD_MINB) k_cpr2_fwd(Cpr2P p) {
         const int y = t / (P * C1), q = t - y * (P * C1);
         sI[(y + P) * rowp + q] = 0.0f; sI[(y + P) * rowp + (W + P) * C1 + q] = 0.0f;
     }
-    if (vecI) {
+    if (FEED && feed) {
+        // Dataset::_load on the fly (src/mu/dataset.cu:139-152): 16 pixels per 128-bit load; the normalised pixels go to the dataset
+        // tensor, to the model's input layer (n0 = input) and into the conv tile; labels widen to int32 and to their one-hot row
+        float *gD = const_cast<float*>(p.I) + (int64_t)n * nI;
+        auto putu = [&](int t, const uint4 w) {
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float4 o;
+                o.x = __fmul_rn(__fsub_rn((float)(int)(ww[k] & 0xffu), p.mean), p.scale);
+                o.y = __fmul_rn(__fsub_rn((float)(int)((ww[k] >> 8) & 0xffu), p.mean), p.scale);
+                o.z = __fmul_rn(__fsub_rn((float)(int)((ww[k] >> 16) & 0xffu), p.mean), p.scale);
+                o.w = __fmul_rn(__fsub_rn((float)(int)(ww[k] >> 24), p.mean), p.scale);
+                const int idx = 16 * t + 4 * k, y = idx / rowf, q = idx - y * rowf;       // rowf % 4 == 0: the quad stays in one row
+                stg4(gD + idx, o);
+                stg4(p.Icopy + (int64_t)n * nI + idx, o);
+                float *d = sI + ((y + P) * WP + P) * C1 + q;
+                d[0] = o.x; d[1] = o.y; d[2] = o.z; d[3] = o.w;
+            }
+        };
+        if ((int)threadIdx.x < (nI >> 4)) putu(threadIdx.x, u0);
+        for (int t = threadIdx.x + blockDim.x; t < (nI >> 4); t += blockDim.x) putu(t, __ldg(reinterpret_cast<const uint4*>(gU) + t));
+        if ((int)threadIdx.x < p.E) p.hot[(int64_t)n * p.E + threadIdx.x] = ((int)threadIdx.x == (lab < p.E ? lab : 0)) ? 1.0f : 0.0f;   // loss.cpp:59-68
+        if (threadIdx.x == 0) p.lab32[n] = lab;
+    } else if (vecI) {
         auto put = [&](int t, const float4 v) {
             const int y = t / rq, q = t - y * rq;
             if (p.Icopy) stg4(p.Icopy + (int64_t)n * nI + y * rowf + 4 * q, v);       // Model::forward: n0 = input
@@ -479,6 +514,34 @@ static int cpr2_bwd_threads(int nwin) {
 }
 static int win_threads(int nwin) { int t = (nwin + 31) & ~31; return t > 256 ? 256 : (t < 32 ? 32 : t); }
 
+// feed != nullptr: dataset feed folded in (fields u8I .. feedN of *feed are copied into the launch parameters; caller checked eligibility)
+static int cpr2_fwd_launch(const float *I, const float *F, const float *B, float *Icopy, float *convO, float *poolO,
+                           float *actO, float *actF, float *flatO, int N, int H1, int W1, int C1, int H0, int W0,
+                           int C0, int KS, int S, int P, const Cpr2P *feed, cudaStream_t st) {
+    int CP = 0; size_t smem = 0;
+    if (!cpr2_fwd_ok(H1, W1, C1, H0, W0, C0, KS, S, P, &CP, &smem)) return T4K_ENOSUP;
+    Cpr2P p{}; p.I = I; p.F = F; p.B = B; p.Icopy = (Icopy == I) ? nullptr : Icopy; p.convO = convO; p.poolO = poolO; p.actO = actO;
+    p.actF = actF; p.flatO = flatO; p.H = H1; p.W = W1; p.C1 = C1; p.C0 = C0;
+    const int threads = win_threads((H0 / 2) * (W0 / 2));
+    const bool al = aligned16(convO) && aligned16(poolO) && aligned16(actO) && aligned16(actF) && (!flatO || aligned16(flatO));
+    #define CPR2F(K_, CP_, CT_, C1_, FD_) { static bool attr = false; if (!attr && smem > 48 * 1024) { cudaFuncSetAttribute(k_cpr2_fwd<K_, CP_, CT_, C1_, FD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; } \
+                                  launch_std(k_cpr2_fwd<K_, CP_, CT_, C1_, FD_>, dim3(N), dim3(threads), smem, st, p); }
+    if (feed) {
+        // the feed variants exist for the exact single-input-channel 3x3 shapes (the MNIST-style first block)
+        if (!(KS == 3 && al && C1 == 1 && (C0 == 10 || C0 == 16 || C0 == 8)) || feed->E > threads) return T4K_ENOSUP;
+        p.u8I = feed->u8I; p.u8L = feed->u8L; p.mean = feed->mean; p.scale = feed->scale; p.lab32 = feed->lab32; p.hot = feed->hot; p.E = feed->E; p.feedN = feed->feedN;
+        if (C0 == 10) CPR2F(3, 12, 10, 1, true) else if (C0 == 16) CPR2F(3, 16, 16, 1, true) else CPR2F(3, 8, 8, 1, true)
+        return check_launch();
+    }
+    if (KS == 3) {
+        if (al && C1 == 1 && C0 == 10) CPR2F(3, 12, 10, 1, false) else if (al && C1 == 1 && C0 == 16) CPR2F(3, 16, 16, 1, false) else if (al && C1 == 1 && C0 == 8) CPR2F(3, 8, 8, 1, false)
+        else switch (CP) { case 4: CPR2F(3, 4, 0, 0, false) break; case 8: CPR2F(3, 8, 0, 0, false) break; case 12: CPR2F(3, 12, 0, 0, false) break; default: CPR2F(3, 16, 0, 0, false) break; }
+    } else {
+        switch (CP) { case 4: CPR2F(5, 4, 0, 0, false) break; case 8: CPR2F(5, 8, 0, 0, false) break; case 12: CPR2F(5, 12, 0, 0, false) break; default: CPR2F(5, 16, 0, 0, false) break; }
+    }
+    return check_launch();
+}
+
 } // namespace t4k
 using namespace t4k;
 
@@ -486,24 +549,31 @@ extern "C" int t4k_conv_pool_relu_fwd(const float *I, const float *F, const floa
                                       float *actO, float *actF, float *flatO, int N, int H1, int W1, int C1, int H0, int W0,
                                       int C0, int KS, int S, int P, t4k_stream_t s) {
     if (!I || !F || !B || !convO || !poolO || !actO || !actF || N < 1) return T4K_EINVAL;
-    int CP = 0; size_t smem = 0;
-    if (!cpr2_fwd_ok(H1, W1, C1, H0, W0, C0, KS, S, P, &CP, &smem)) {
-        if (Icopy && Icopy != I) { int rc = t4k_copy(I, Icopy, (int64_t)N * H1 * W1 * C1, s); if (rc) return rc; }
-        return cpr_v1_fwd(I, F, B, convO, poolO, actO, actF, flatO, N, H1, W1, C1, H0, W0, C0, KS, S, P, STRM(s));
+    int rc = cpr2_fwd_launch(I, F, B, Icopy, convO, poolO, actO, actF, flatO, N, H1, W1, C1, H0, W0, C0, KS, S, P, nullptr, STRM(s));
+    if (rc != T4K_ENOSUP) return rc;
+    if (Icopy && Icopy != I) { rc = t4k_copy(I, Icopy, (int64_t)N * H1 * W1 * C1, s); if (rc) return rc; }
+    return cpr_v1_fwd(I, F, B, convO, poolO, actO, actF, flatO, N, H1, W1, C1, H0, W0, C0, KS, S, P, STRM(s));
+}
+
+// The forward block fed straight from a staged U8 mini-batch: Dataset::_load (src/mu/dataset.cu:124-152) + Model::onehot
+// (src/nn/loss.cpp:47-72) + the block, one launch.  `data` is the dataset tensor [N,H1,W1,C1]: its first feedN samples are
+// rewritten with ((float)u8 - mean) * scale, the rest keep their values (partial batch, as _load); Icopy = the model's input layer.
+// Shapes outside the fused envelope run t4k_dataset_load followed by t4k_conv_pool_relu_fwd (same results).
+extern "C" int t4k_conv_pool_relu_fwd_feed(const uint8_t *u8I, const uint8_t *u8L, int feedN, float mean, float scale, int32_t *lab32,
+                                           float *hot, int E, float *data, const float *F, const float *B, float *Icopy, float *convO,
+                                           float *poolO, float *actO, float *actF, float *flatO, int N, int H1, int W1, int C1,
+                                           int H0, int W0, int C0, int KS, int S, int P, t4k_stream_t s) {
+    if (!u8I || !u8L || !lab32 || !data || !F || !B || !convO || !poolO || !actO || !actF || N < 1 || feedN < 0 || feedN > N || (hot && E < 1)) return T4K_EINVAL;
+    const int nI = H1 * W1 * C1;
+    const bool fusable = hot && Icopy && Icopy != data && (nI & 15) == 0 && ((W1 * C1) & 3) == 0 && aligned16(u8I) && aligned16(data) && aligned16(Icopy);
+    if (fusable) {
+        Cpr2P fd{}; fd.u8I = u8I; fd.u8L = u8L; fd.mean = mean; fd.scale = scale; fd.lab32 = lab32; fd.hot = hot; fd.E = E; fd.feedN = feedN;
+        int rc = cpr2_fwd_launch(data, F, B, Icopy, convO, poolO, actO, actF, flatO, N, H1, W1, C1, H0, W0, C0, KS, S, P, &fd, STRM(s));
+        if (rc != T4K_ENOSUP) return rc;
     }
-    Cpr2P p{}; p.I = I; p.F = F; p.B = B; p.Icopy = (Icopy == I) ? nullptr : Icopy; p.convO = convO; p.poolO = poolO; p.actO = actO;
-    p.actF = actF; p.flatO = flatO; p.H = H1; p.W = W1; p.C1 = C1; p.C0 = C0;
-    const int threads = win_threads((H0 / 2) * (W0 / 2));
-    const bool al = aligned16(convO) && aligned16(poolO) && aligned16(actO) && aligned16(actF) && (!flatO || aligned16(flatO));
-    #define CPR2F(K_, CP_, CT_, C1_) { static bool attr = false; if (!attr && smem > 48 * 1024) { cudaFuncSetAttribute(k_cpr2_fwd<K_, CP_, CT_, C1_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; } \
-                                  launch_std(k_cpr2_fwd<K_, CP_, CT_, C1_>, dim3(N), dim3(threads), smem, STRM(s), p); }
-    if (KS == 3) {
-        if (al && C1 == 1 && C0 == 10) CPR2F(3, 12, 10, 1) else if (al && C1 == 1 && C0 == 16) CPR2F(3, 16, 16, 1) else if (al && C1 == 1 && C0 == 8) CPR2F(3, 8, 8, 1)
-        else switch (CP) { case 4: CPR2F(3, 4, 0, 0) break; case 8: CPR2F(3, 8, 0, 0) break; case 12: CPR2F(3, 12, 0, 0) break; default: CPR2F(3, 16, 0, 0) break; }
-    } else {
-        switch (CP) { case 4: CPR2F(5, 4, 0, 0) break; case 8: CPR2F(5, 8, 0, 0) break; case 12: CPR2F(5, 12, 0, 0) break; default: CPR2F(5, 16, 0, 0) break; }
-    }
-    return check_launch();
+    int rc = t4k_dataset_load(u8I, data, (int64_t)feedN * nI, mean, scale, u8L, lab32, feedN, hot, E, s);
+    if (rc) return rc;
+    return t4k_conv_pool_relu_fwd(data, F, B, Icopy, convO, poolO, actO, actF, flatO, N, H1, W1, C1, H0, W0, C0, KS, S, P, s);
 }
 
 extern "C" int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,

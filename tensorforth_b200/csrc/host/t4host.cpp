@@ -342,13 +342,16 @@ Model &Model::forward(Tensor &input) {
     if (input.numel != n0.numel) {
         Runtime::error("nn#forward dataset wrong shape[%d,%d,%d,%d] != model input[%d,%d,%d,%d]\n",
                        input.N(), input.H(), input.W(), input.C(), n0.N(), n0.H(), n0.W(), n0.C());
+        _feed = nullptr;
         return *this;
     }
     size_t i0 = 0;
     if (input.data != n0.data) {
-        i0 = (size_t)_ffused(0, input.data);               // first block fused: the `n0 = input` copy rides in the same launch
+        i0 = (size_t)_ffused(0, input.data);               // first block fused: the `n0 = input` copy (and a pending dataset feed) ride in the same launch
+        if (_feed) _feed_fallback();                       // not taken by a fused block: the plain load, before the copy below reads the tensor
         if (!i0) n0 = input;
     }
+    else if (_feed) _feed_fallback();
     for (size_t i = i0; i + 1 < _layers.size(); ) {
         int adv = _ffused(i);                              // conv → maxpool(2) → relu (→ flatten) in one launch
         if (!adv) adv = _ffused_linear(i);                 // linear → activation | linear → softmax
@@ -356,6 +359,10 @@ Model &Model::forward(Tensor &input) {
         _fstep(*_layers[i], *_layers[i + 1]); i++;
     }
     return *this;
+}
+void Model::_feed_fallback() {
+    const StepExtra &x = *_feed; _feed = nullptr;
+    x.ds->commit_launch(x.simg, x.slab, x.n, _feed_hot, (int)(*this)[-1].HWC());
 }
 // The canonical CNN block of the reference's examples ("conv2d 2 maxpool relu [flatten]", t4_40a.4th:11-12):
 // same layer tensors written as the per-layer path (forward.cu:83-113), one kernel.  Returns layers consumed.
@@ -366,6 +373,15 @@ int Model::_ffused(size_t i, const DU *src) {
     if (in.grad_fn != T4K_L_CONV || co.grad_fn != T4K_L_MAXPOOL || co.stride[0] != 2 || po.grad_fn != T4K_L_RELU) return 0;
     Tensor *fl = (ao.grad_fn == T4K_L_FLATTEN && i + 4 < n) ? _layers[i + 4] : nullptr;
     Tensor &f = *in.grad[0], &b = *in.grad[1];
+    if (src && _feed) {                                    // step_graph with a Dataset: U8 -> normalise -> one-hot inside this launch
+        const StepExtra &x = *_feed; _feed = nullptr;      // the entry point always performs the load (fused, or as its own launch in front)
+        int rc = t4k_conv_pool_relu_fwd_feed(x.simg, x.slab, x.n, x.ds->_mean, x.ds->_scale, x.ds->label, _feed_hot, (int)(*this)[-1].HWC(),
+                                             (DU*)src, f.data, b.data, in.data, co.data, po.data, ao.data, po.grad[4]->data, fl ? fl->data : nullptr,
+                                             co.N(), in.H(), in.W(), in.C(), co.H(), co.W(), co.C(), f.H(), in.stride[0], in.stride[2], ST);
+        if (rc == T4K_ENOSUP) return 0;
+        KCHK(rc);
+        return fl ? 4 : 3;
+    }
     int rc = t4k_conv_pool_relu_fwd(src ? src : in.data, f.data, b.data, src ? in.data : nullptr, co.data, po.data, ao.data, po.grad[4]->data, fl ? fl->data : nullptr,
                                     co.N(), in.H(), in.W(), in.C(), co.H(), co.W(), co.C(), f.H(), in.stride[0], in.stride[2], ST);
     if (rc == T4K_ENOSUP) return 0;
@@ -882,7 +898,7 @@ int Model::_step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4
     for (Tensor *t : _layers) if (t->grad_fn == T4K_L_DROPOUT) has_dropout = true;
     auto run = [&]() {
         if (has_dropout) t4k_rand_tick(ST);                    // replayed graphs draw a fresh dropout mask every step (rand.cu)
-        if (x.ds) x.ds->commit_launch(x.simg, x.slab, x.n, tgt.data, (int)(*this)[-1].HWC());   // dataset feeding: normalise + one-hot
+        if (x.ds) { _feed = &x; _feed_hot = tgt.data; }        // dataset feeding (normalise + one-hot): rides in the first fused block, else its own launch (forward)
         _want_pdup = loss_dev != nullptr; _pdup_valid = false;
         forward(input);
         _want_pdup = false;

@@ -165,6 +165,8 @@ class Model {
     bool    _dp_early = false, _dp_join = false; int64_t _dp_pushed_from = -1;   // split exchange inside step_graph (early push on the side stream)
     void    _dp_push();
     DU     *_pdup = nullptr; bool _want_pdup = false, _pdup_valid = false;   // step_graph: duplicate of the softmax output for the side-stream loss
+    const StepExtra *_feed = nullptr; DU *_feed_hot = nullptr;   // step_graph: staged U8 batch still to be loaded (folded into the first fused block when there is one)
+    void    _feed_fallback();
     bool    _side_join = false, _skip_flat_copy = false;   // backprop: work pending on the side stream / flatten copy already issued there
     DU     *_loss_pin = nullptr; void *_loss_ev[2] = {nullptr, nullptr}; unsigned _tstep = 0;   // train_step read-back ring
     std::vector<Tensor*> _layers;      ///< layer i holds that layer's INPUT; last = output

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "t4k_pool_bwd": (_i, [_i, _p, _p] + [_i] * 7 + [_p]),
     "t4k_batchnorm_bwd": (_i, [_p] * 7 + [_i] * 4 + [_p]),
     "t4k_conv_pool_relu_fwd": (_i, [_p] * 9 + [_i] * 10 + [_p]),
+    "t4k_conv_pool_relu_fwd_feed": (_i, [_p, _p, _i, _f, _f, _p, _p, _i] + [_p] * 9 + [_i] * 10 + [_p]),
     "t4k_conv_pool_relu_bwd": (_i, [_p] * 10 + [_i] * 11 + [_p]),
     "t4k_sgd": (_i, [_p, _p, _p, _i, _f, _f, _l, _p]),
     "t4k_adam": (_i, [_p, _p, _p, _p, _f, _f, _f, _l, _p]),

@@ -641,6 +641,42 @@ def test_dataset_load_bit_exact(n, norm):
     assert_exact(host(hot), orc.onehot(lab.astype(np.int32), 10), "onehot of u8 labels (label >= E -> class 0, loss.cpp:66)")
 
 
+@pytest.mark.parametrize("N,feedN,C0,hw", [(8, 8, 10, 28), (8, 5, 10, 28), (4, 4, 16, 28), (4, 3, 6, 28), (4, 4, 10, 18)])
+def test_conv_pool_relu_fwd_feed_equals_load_then_block(N, feedN, C0, hw):
+    """the forward block fed from a staged U8 mini-batch (t4k_conv_pool_relu_fwd_feed: Dataset::_load + Model::onehot + conv -> maxpool
+    -> relu -> flatten in one launch) writes bit for bit what t4k_dataset_load followed by t4k_conv_pool_relu_fwd writes — dataset
+    tensor (partial batch: the tail keeps its values), labels, one-hot rows, input copy and every layer tensor; C0 = 6 and 18 x 18
+    (324 pixels: not a multiple of 16) take the entry point's unfused path"""
+    rng = np.random.default_rng(N * 100 + feedN + C0)
+    u8 = rng.integers(0, 256, (N, hw, hw, 1), dtype=np.uint8)
+    lab = rng.integers(0, 12, N, dtype=np.uint8)                       # labels >= E fold to class 0 (loss.cpp:66)
+    mean, scale = orc.dataset_normalize(128.0, 128.0)
+    F, B = rnd(1, 3, 3, C0), rnd(C0)
+    old = rnd(N, hw, hw, 1)                                            # what the dataset tensor held before (kept past feedN)
+    E, hp = 10, hw // 2
+    dF, dB = dev(F), dev(B)
+    s8 = torch.from_numpy(np.concatenate([u8.ravel(), np.zeros(16, np.uint8)])).cuda(); l8 = torch.from_numpy(lab).cuda()
+
+    def run(fused):
+        data = dev(old); icopy = zeros(N, hw, hw, 1); l32 = torch.full((N,), -1, dtype=torch.int32, device="cuda"); hot = zeros(N, E) + 7.0
+        cO, pO, aO, aF, fO = zeros(N, hw, hw, C0), zeros(N, hp, hp, C0), zeros(N, hp, hp, C0), zeros(N, hp, hp, C0), zeros(N, hp * hp * C0)
+        u8p, l8p, l32p = C.c_void_p(s8.data_ptr()), C.c_void_p(l8.data_ptr()), C.c_void_p(l32.data_ptr())
+        if fused:
+            ok(lib().t4k_conv_pool_relu_fwd_feed(u8p, l8p, feedN, float(mean), float(scale), l32p, ptr(hot), E, ptr(data), ptr(dF), ptr(dB), ptr(icopy),
+                                                 ptr(cO), ptr(pO), ptr(aO), ptr(aF), ptr(fO), N, hw, hw, 1, hw, hw, C0, 3, 1, 1, None), "fwd_feed")
+        else:
+            ok(lib().t4k_dataset_load(u8p, ptr(data), feedN * hw * hw, float(mean), float(scale), l8p, l32p, feedN, ptr(hot), E, None))
+            ok(lib().t4k_conv_pool_relu_fwd(ptr(data), ptr(dF), ptr(dB), ptr(icopy), ptr(cO), ptr(pO), ptr(aO), ptr(aF), ptr(fO), N, hw, hw, 1, hw, hw, C0, 3, 1, 1, None))
+        return [host(t).copy() for t in (data, icopy, hot, cO, pO, aO, aF, fO)] + [l32.cpu().numpy().copy()]
+    a, b = run(True), run(False)
+    for x, y, nm in zip(a, b, ("dataset tensor", "input copy", "one-hot", "conv", "pool", "relu", "mask", "flatten", "labels")):
+        assert np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x, y.view(np.uint32) if y.dtype == np.float32 else y), nm
+    want = np.concatenate([orc.dataset_load(u8[:feedN].ravel(), mean, scale), old.ravel()[feedN * hw * hw:]])
+    assert_exact(a[0], want, "dataset tensor vs oracle (fed part) and previous values (tail)")
+    assert_exact(a[2][:feedN], orc.onehot(lab[:feedN].astype(np.int32), E), "one-hot vs oracle")
+    assert np.array_equal(a[8][:feedN], lab[:feedN].astype(np.int32)) and np.all(a[8][feedN:] == -1)
+
+
 @pytest.mark.parametrize("layer", [t4.L_RELU, t4.L_TANH, t4.L_LEAKYRL])
 @pytest.mark.parametrize("N,E1,EH,E0", [(512, 1960, 100, 10), (37, 300, 128, 32), (8, 64, 20, 3)])
 def test_linear_act_head_fwd_equals_the_two_calls(layer, N, E1, EH, E0):

@@ -331,6 +331,8 @@ def test_dataset_feed_forward_onehot_hit_and_train_step():
             ds.stage(*batches[i + 1])
         t4.check(m.step_graph_ds(ds, t4.LOSS_CE, lp, optimizer=2, lr=1e-3), "step_graph_ds")
         th.sync(); got.append(float(loss_dev[0].cpu()))
+        # the load rides in the step's first fused block: the dataset tensor still holds exactly what Dataset::_load would have put there
+        assert np.array_equal(ds.tensor.numpy().view(np.uint32).ravel(), orc.dataset_load(batches[i][0], mean, scale).view(np.uint32).ravel())
         xi = th.Tensor.from_numpy(orc.dataset_load(batches[i][0], mean, scale).reshape(N, 28, 28, 1))
         yi = th.Tensor.tensor(N, 1, E, 1, orc.onehot(batches[i][1].astype(np.int32), E))
         ref.forward(xi); ref.loss_async(t4.LOSS_CE, yi, lr_); ref.backprop(yi); ref.adam(1e-3)
