@@ -17,3 +17,4 @@ run default "T4K_X=1"
 if [ -n "$AB_NCU" ]; then
   timeout 240 ncu --set full --clock-control none --import-source on -k regex:$AB_NCU -s ${AB_NCU_SKIP:-3} -c 1 -o gpurun_out/ab_ncu -f python tests/perf_probe.py ${AB_NCU_WHAT:-cpr} > gpurun_out/ab_ncu.log 2>&1; tail -1 gpurun_out/ab_ncu.log
 fi
+if [ -n "$AB_ENV2" ]; then run alt "$AB_ENV2"; fi

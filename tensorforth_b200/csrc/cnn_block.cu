@@ -245,7 +245,10 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
     extern __shared__ __align__(16) float sm[];
     pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     constexpr int KS = 3, P = 1;
-    constexpr int NG = (3 * CM + 31) / 32;              // 32-value groups per ky pass
+    // dF/dB partials: NPASS passes over CH channels each; a pass accumulates the 9 taps x CH channels (+ the CH dB sums) in registers
+    constexpr int CH = (CM == 10) ? 5 : 4, NPASS = CM / CH, NACC = 9 * CH;
+    constexpr int NGP = (NACC + CH + 31) / 32;          // 32-value groups per pass (45 + 5 -> 2, 36 + 4 -> 2)
+    static_assert(CM % CH == 0, "channel passes");
     const int H = p.H, W = p.W, C0 = EXACT ? CM : p.C0;
     const int WP = W + 2, HP = H + 2;
     const int RW = (WP + 1) & ~1;                       // even row stride → 8-byte aligned pairs
@@ -253,9 +256,9 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
     float *sFx = sF + ((9 * CM + 3) & ~3);              // [CM][12] flipped taps, channel-major (dX gather: 3 x 128-bit per channel)
     float *sI = sFx + 12 * CM;                          // [HP][WP] zero halo (forward input, C1 == 1)
     float *sR = sI + ((HP * WP + 3) & ~3);              // [C0][HP][RW] routed gradient, zero halo
-    float *sRed = sR + (((size_t)C0 * HP * RW + 3) & ~(size_t)3);   // [nwarps][3*NG*32 + 32]
+    float *sRed = sR + (((size_t)C0 * HP * RW + 3) & ~(size_t)3);   // [nwarps][NPASS*NGP*32]
     const int Hp = H / 2, Wp = W / 2, nwin = Hp * Wp, nP = nwin * C0;
-    float *sD = sRed + (size_t)(blockDim.x >> 5) * (3 * NG * 32 + 32);      // [nwin][C0] dY, overwritten with g = dY*mask
+    float *sD = sRed + (size_t)(blockDim.x >> 5) * (NPASS * NGP * 32);      // [nwin][C0] dY, overwritten with g = dY*mask
     const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int nI = H * W;
     float *gO = p.convO + (int64_t)n * H * W * C0;
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
         }
     }
     __syncthreads();
-    const int RSTRIDE = 3 * NG * 32 + 32;
+    constexpr int RSTRIDE = NPASS * NGP * 32;
     const int cs = HP * RW;                               // channel stride of the routed tile
     float accB[CM];
     #pragma unroll
@@ -391,62 +394,71 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
         load_window(w, t_);
         route_window(w, t_);
     }
-    // ---- dF: three ky passes over this thread's windows (its own routed values, read back from the tile it just wrote)
-    float accF[NG * 32];                                  // current ky pass: [kx*CM + c]
-    for (int ky = 0; ky < 3 && p.train; ky++) {
-        #pragma unroll
-        for (int g = 0; g < NG * 32; g++) accF[g] = 0.0f;
-        for (int w = threadIdx.x; w < nwin; w += blockDim.x) {
-            const int j0 = w % Wp, i0 = w / Wp;
-            const int rb0 = 2 * i0 * RW + 2 * j0;
-            float r[4][CM];
-            #pragma unroll
-            for (int c = 0; c < CM; c++) {
-                if (c < C0) {
-                    const float *rr = sR + c * cs + rb0 + RW + 1;
-                    r[0][c] = rr[0]; r[1][c] = rr[1]; r[2][c] = rr[RW]; r[3][c] = rr[RW + 1];
-                } else { r[0][c] = r[1][c] = r[2][c] = r[3][c] = 0.0f; }
-            }
-            // dF[ky][kx][c] += Σ_{pixel (dy,dx) of the window} I[2*i0+dy+ky-1][2*j0+dx+kx-1] * r[dy*2+dx][c]
-            #pragma unroll
-            for (int kx = 0; kx < 3; kx++) {
-                const float *ip = sI + (2 * i0 + ky) * WP + 2 * j0 + kx;
-                const float i00 = ip[0], i01 = ip[1], i10 = ip[WP], i11 = ip[WP + 1];
-                #pragma unroll
-                for (int c = 0; c < CM; c++) {
-                    float a = accF[kx * CM + c];
-                    a = fmaf(i00, r[0][c], a); a = fmaf(i01, r[1][c], a);
-                    a = fmaf(i10, r[2][c], a); a = fmaf(i11, r[3][c], a);
-                    accF[kx * CM + c] = a;
-                }
-            }
-        }
-        #pragma unroll
-        for (int g = 0; g < NG; g++) {
-            float v[32];
-            #pragma unroll
-            for (int k = 0; k < 32; k++) v[k] = accF[g * 32 + k];
-            const float s = warp_treduce32(v, lane);
-            sRed[warp * RSTRIDE + (ky * NG + g) * 32 + lane] = s;
-        }
-    }
+    // ---- dF / dB: NPASS passes of CH channels.  Per window and pass: the 4 x 4 input neighbourhood (8 x 64-bit loads) and the window's
+    //      own routed values for CH channels (read back from the tile it just wrote) feed 9 taps x CH channels x 4 pixels of FMAs; every
+    //      routed value is read ONCE for all nine taps (a ky-major loop would read it three times).  Same FMA order per (tap, channel)
+    //      as before: window after window, pixels (0,0) (0,1) (1,0) (1,1).
     if (p.train) {
-        float v[32];
         #pragma unroll
-        for (int k = 0; k < 32; k++) v[k] = (k < CM) ? accB[k < CM ? k : 0] : 0.0f;
-        const float s = warp_treduce32(v, lane);
-        sRed[warp * RSTRIDE + 3 * NG * 32 + lane] = s;
+        for (int pass = 0; pass < NPASS; pass++) {
+            float acc[NGP * 32];                          // [(ky*3+kx)*CH + cc], then the CH dB sums
+            #pragma unroll
+            for (int g = 0; g < NGP * 32; g++) acc[g] = 0.0f;
+            for (int w = threadIdx.x; w < nwin; w += blockDim.x) {
+                const int j0 = w % Wp, i0 = w / Wp;
+                const int rb0 = 2 * i0 * RW + 2 * j0;
+                float nb[4][4];
+                #pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    const float *ip = sI + (2 * i0 + a) * WP + 2 * j0;       // WP even (host-checked): 8-byte aligned pairs
+                    const float2 u = *reinterpret_cast<const float2*>(ip), v = *reinterpret_cast<const float2*>(ip + 2);
+                    nb[a][0] = u.x; nb[a][1] = u.y; nb[a][2] = v.x; nb[a][3] = v.y;
+                }
+                float r[4][CH];
+                #pragma unroll
+                for (int cc = 0; cc < CH; cc++) {
+                    const int c = pass * CH + cc;
+                    if (c < C0) {
+                        const float *rr = sR + c * cs + rb0 + RW + 1;
+                        r[0][cc] = rr[0]; r[1][cc] = rr[1]; r[2][cc] = rr[RW]; r[3][cc] = rr[RW + 1];
+                    } else { r[0][cc] = r[1][cc] = r[2][cc] = r[3][cc] = 0.0f; }
+                }
+                // dF[ky][kx][c] += Σ_{pixel (dy,dx) of the window} I[2*i0+dy+ky-1][2*j0+dx+kx-1] * r[dy*2+dx][c]
+                #pragma unroll
+                for (int ky = 0; ky < 3; ky++)
+                    #pragma unroll
+                    for (int kx = 0; kx < 3; kx++)
+                        #pragma unroll
+                        for (int cc = 0; cc < CH; cc++) {
+                            float a = acc[(ky * 3 + kx) * CH + cc];
+                            a = fmaf(nb[ky][kx], r[0][cc], a);     a = fmaf(nb[ky][kx + 1], r[1][cc], a);
+                            a = fmaf(nb[ky + 1][kx], r[2][cc], a); a = fmaf(nb[ky + 1][kx + 1], r[3][cc], a);
+                            acc[(ky * 3 + kx) * CH + cc] = a;
+                        }
+            }
+            #pragma unroll
+            for (int cc = 0; cc < CH; cc++) acc[NACC + cc] = accB[pass * CH + cc];
+            #pragma unroll
+            for (int g = 0; g < NGP; g++) {
+                float v[32];
+                #pragma unroll
+                for (int k = 0; k < 32; k++) v[k] = acc[g * 32 + k];
+                const float sv_ = warp_treduce32(v, lane);
+                sRed[warp * RSTRIDE + (pass * NGP + g) * 32 + lane] = sv_;
+            }
+        }
     }
     __syncthreads();
     if (p.train) {
         const int nF = 9 * C0, nE = nF + C0;
         for (int t = threadIdx.x; t < nE; t += blockDim.x) {
-            int slot;
-            if (t < nF) { const int c = t % C0, kx = (t / C0) % 3, ky = t / (3 * C0); slot = ky * NG * 32 + kx * CM + c; }
-            else slot = 3 * NG * 32 + (t - nF);
-            float s = 0.0f;
-            for (int wv = 0; wv < nwarps; wv++) s += sRed[wv * RSTRIDE + slot];
-            p.part[(int64_t)n * nE + t] = s;
+            int c, idx;
+            if (t < nF) { c = t % C0; idx = (t / C0) * CH + c % CH; }      // t / C0 = ky*3 + kx
+            else        { c = t - nF; idx = NACC + c % CH; }
+            const int slot = (c / CH) * NGP * 32 + idx;
+            float s_ = 0.0f;
+            for (int wv = 0; wv < nwarps; wv++) s_ += sRed[wv * RSTRIDE + slot];
+            p.part[(int64_t)n * nE + t] = s_;
         }
     }
     // ---- dX (flipped taps, nmath.tcu:304): dX[y][x] = Σ_c Σ_{ky,kx} F[2-ky][2-kx][c] * R[y+1-ky][x+1-kx][c]
@@ -500,10 +512,10 @@ static bool cpr2_fwd_ok(int H1, int W1, int C1, int H0, int W0, int C0, int KS, 
 static bool cpr2_bwd_ok(int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, int *CM, size_t *smem, int threads) {
     if (KS != 3 || S != 1 || P != 1 || H0 != H1 || W0 != W1 || C1 != 1 || C0 > 16 || (H0 & 1) || (W0 & 1)) return false;
     *CM = (C0 <= 10) ? 10 : 16;
-    const int NG = (3 * *CM + 31) / 32;
+    const int CH = (*CM == 10) ? 5 : 4, NPASS = *CM / CH, NGP = (9 * CH + CH + 31) / 32;      // as in k_cpr2_bwd
     const int HP = H1 + 2, WP = W1 + 2, RW = (WP + 1) & ~1;
     const size_t nP = (size_t)(H0 / 2) * (W0 / 2) * C0;
-    *smem = ((size_t)((9 * *CM + 3) & ~3) + 12 * *CM + ((HP * WP + 3) & ~3) + (((size_t)C0 * HP * RW + 3) & ~(size_t)3) + (size_t)(threads / 32) * (3 * NG * 32 + 32) +
+    *smem = ((size_t)((9 * *CM + 3) & ~3) + 12 * *CM + ((HP * WP + 3) & ~3) + (((size_t)C0 * HP * RW + 3) & ~(size_t)3) + (size_t)(threads / 32) * (NPASS * NGP * 32) +
              ((nP + 3) & ~(size_t)3)) * sizeof(float);
     return *smem <= 100 * 1024 && (W1 & 1) == 0;
 }

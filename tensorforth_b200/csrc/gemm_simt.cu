@@ -139,10 +139,12 @@ __global__ void __launch_bounds__(T4K_THREADS) k_splitk_fin(GemmP p, int batch) 
 #define VBK 16
 // register tile TM x TN (4 or 8 each): an 8-wide side is two 4-wide groups half a tile apart (conflict-free LDS.128)
 template<bool TA, bool TB, int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(128) k_gemm_v2(GemmP p) {
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) k_gemm_v2(GemmP p) {
     constexpr int TX = BN / TN;
-    static_assert((BM / TM) * (BN / TN) == 128, "128 threads");
-    constexpr int NA = BM * VBK / 4 / 128, NB = BN * VBK / 4 / 128;      // float4 loads per thread per k-tile
+    constexpr int NT = (BM / TM) * (BN / TN);                            // threads per CTA: 128, or 256 for the 4 x 4 register tile
+    static_assert(NT == 128 || NT == 256, "128 or 256 threads");
+    constexpr int NA = BM * VBK / 4 / NT, NB = BN * VBK / 4 / NT;        // float4 loads per thread per k-tile
+    static_assert(NA >= 1 && NB >= 1, "tile too small for the CTA");
     __shared__ __align__(16) float sA[2][VBK][BM + 4];
     __shared__ __align__(16) float sB[2][VBK][BN + 4];
     pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(128) k_gemm_v2(GemmP p) {
     auto load = [&](int k0) {
         #pragma unroll
         for (int i = 0; i < NA; i++) {
-            const int f = tid + 128 * i;
+            const int f = tid + NT * i;
             if (TA) { const int k = f / (BM / 4), mq = f % (BM / 4); const int gk = k0 + k, gm = m0 + mq * 4;       // A^T [K,M]: float4 along m
                       ra[i] = (gk < kend && gm < M) ? ldg4(A + (int64_t)gk * M + gm) : z4; }
             else    { const int m = f / (VBK / 4), kq = f % (VBK / 4); const int gm = m0 + m, gk = k0 + kq * 4;      // A [M,K]: float4 along k
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(128) k_gemm_v2(GemmP p) {
         }
         #pragma unroll
         for (int i = 0; i < NB; i++) {
-            const int f = tid + 128 * i;
+            const int f = tid + NT * i;
             if (TB) { const int n = f / (VBK / 4), kq = f % (VBK / 4); const int gn = n0 + n, gk = k0 + kq * 4;      // B^T [N,K]: float4 along k
                       rb[i] = (gn < N && gk < kend) ? ldg4(B + (int64_t)gn * K + gk) : z4; }
             else    { const int k = f / (BN / 4), nq = f % (BN / 4); const int gk = k0 + k, gn = n0 + nq * 4;        // B [K,N]: float4 along n
@@ -175,14 +177,14 @@ __global__ void __launch_bounds__(128) k_gemm_v2(GemmP p) {
     auto store = [&](int buf) {
         #pragma unroll
         for (int i = 0; i < NA; i++) {
-            const int f = tid + 128 * i;
+            const int f = tid + NT * i;
             if (TA) { const int k = f / (BM / 4), mq = f % (BM / 4); *reinterpret_cast<float4*>(&sA[buf][k][mq * 4]) = ra[i]; }
             else    { const int m = f / (VBK / 4), kq = f % (VBK / 4);
                       sA[buf][kq * 4][m] = ra[i].x; sA[buf][kq * 4 + 1][m] = ra[i].y; sA[buf][kq * 4 + 2][m] = ra[i].z; sA[buf][kq * 4 + 3][m] = ra[i].w; }
         }
         #pragma unroll
         for (int i = 0; i < NB; i++) {
-            const int f = tid + 128 * i;
+            const int f = tid + NT * i;
             if (TB) { const int n = f / (VBK / 4), kq = f % (VBK / 4);
                       sB[buf][kq * 4][n] = rb[i].x; sB[buf][kq * 4 + 1][n] = rb[i].y; sB[buf][kq * 4 + 2][n] = rb[i].z; sB[buf][kq * 4 + 3][n] = rb[i].w; }
             else    { const int k = f / (BN / 4), nq = f % (BN / 4); *reinterpret_cast<float4*>(&sB[buf][k][nq * 4]) = rb[i]; }
@@ -240,8 +242,9 @@ __global__ void __launch_bounds__(128) k_gemm_v2(GemmP p) {
     }
 }
 template<int BM, int BN, int TM, int TN> static void launch_v2(const GemmP &p, dim3 g, int tA, int tB, cudaStream_t st) {
-    if (tA) { if (tB) launch_std(k_gemm_v2<true, true, BM, BN, TM, TN>, g, dim3(128), 0, st, p); else launch_std(k_gemm_v2<true, false, BM, BN, TM, TN>, g, dim3(128), 0, st, p); }
-    else    { if (tB) launch_std(k_gemm_v2<false, true, BM, BN, TM, TN>, g, dim3(128), 0, st, p); else launch_std(k_gemm_v2<false, false, BM, BN, TM, TN>, g, dim3(128), 0, st, p); }
+    constexpr int NT = (BM / TM) * (BN / TN);
+    if (tA) { if (tB) launch_std(k_gemm_v2<true, true, BM, BN, TM, TN>, g, dim3(NT), 0, st, p); else launch_std(k_gemm_v2<true, false, BM, BN, TM, TN>, g, dim3(NT), 0, st, p); }
+    else    { if (tB) launch_std(k_gemm_v2<false, true, BM, BN, TM, TN>, g, dim3(NT), 0, st, p); else launch_std(k_gemm_v2<false, false, BM, BN, TM, TN>, g, dim3(NT), 0, st, p); }
 }
 static bool v2_ok(const float *A, const float *B, const float *O, int tA, int tB, int M, int N, int K, int C, int64_t sA, int64_t sB, int64_t sO) {
     if (C != 1 || (N & 3) || !aligned16(A) || !aligned16(B) || !aligned16(O) || (sA & 3) || (sB & 3) || (sO & 3)) return false;
@@ -289,7 +292,13 @@ int gemm_simt(const float *A, const float *B, float *O, float alpha, float beta,
     if ((int64_t)C * splits * batch > 65535) return T4K_EINVAL;
     dim3 g(gx, gy, C * splits * batch);
     if (K == 0) { p.splits = 1; }
-    if (v2) { if (!wide) launch_v2<128, 64, 8, 8>(p, g, tA, tB, st); else if (big) launch_v2<64, 128, 8, 8>(p, g, tA, tB, st); else launch_v2<64, 64, 8, 4>(p, g, tA, tB, st); }
+    // 64 x 64 tile when the grid is small (the layer products): 128 threads with an 8 x 4 register tile.  A 256-thread 4 x 4 variant
+    // (twice the warps per SM) was measured SLOWER on the MNIST step (linear_bwd 26.1 vs 24.5 us, step 84.3 vs 80.1 us): opt-in
+    // with T4K_SIMT_T256=1
+    static int t256 = -1;
+    if (t256 < 0) { const char *e = getenv("T4K_SIMT_T256"); t256 = (e && e[0] == '1') ? 1 : 0; }
+    if (v2) { if (!wide) launch_v2<128, 64, 8, 8>(p, g, tA, tB, st); else if (big) launch_v2<64, 128, 8, 8>(p, g, tA, tB, st);
+              else if (t256) launch_v2<64, 64, 4, 4>(p, g, tA, tB, st); else launch_v2<64, 64, 8, 4>(p, g, tA, tB, st); }
     else if (tA) { if (tB) launch_std(k_gemm_simt<true, true >, g, dim3(256), 0, st, p); else launch_std(k_gemm_simt<true, false>, g, dim3(256), 0, st, p); }
     else    { if (tB) launch_std(k_gemm_simt<false, true>, g, dim3(256), 0, st, p); else launch_std(k_gemm_simt<false, false>, g, dim3(256), 0, st, p); }
     int rc = check_launch();
