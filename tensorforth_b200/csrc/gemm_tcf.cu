@@ -16,6 +16,7 @@
 // issues 12 MMAs of 128x128x8: producers and tensor pipe are balanced at ~0.5 us per k-block.
 // Bound: tensor pipe for large K, launch/ramp latency for the layer shapes (a few k-blocks per CTA).
 #include "tc_ptx.cuh"
+#include <cstdlib>
 
 namespace t4k {
 
@@ -102,6 +103,26 @@ __device__ __forceinline__ void produce_tile(const float *__restrict__ X, int64_
     }
 }
 
+// ---- thread-block cluster helpers (CLUSTER variant: split-K reduced through distributed shared memory)
+__device__ __forceinline__ void tcf_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 tcf_ld_dsmem4(const float *local, uint32_t rank) {      // the same shared-memory offset in CTA `rank` of the cluster
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(local), r; float4 v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(r) : "memory");
+    return v;
+}
+// staging tile [128 rows][128 cols] fp32 over the (idle) operand ring: 16-byte chunk c4 of row r lives at chunk (c4 ^ (r & 31)):
+// the epilogue's per-row float4 stores (lanes = rows) and the reduction's per-row reads (lanes = chunks) are both conflict-free
+__device__ __forceinline__ int tcf_stage_off(int row, int c4) { return row * F_BN + ((c4 ^ (row & 31)) << 2); }
+
+// CLUSTER = false: split-K partials go to global memory, a second launch (or the caller's fused finish) adds them.
+// CLUSTER = true (EXPERIMENTAL, opt-in with T4K_TCF_CLUSTER=1, not yet measured on the device): the `splits` CTAs of one output tile
+// form a thread-block cluster (1 x 1 x splits, splits a power of two <= 8); every CTA parks its accumulator tile in its own shared
+// memory, and after a cluster barrier CTA r adds rows [r*128/splits, (r+1)*128/splits) of all the parked tiles in RANK ORDER through
+// distributed shared memory and writes alpha*sum + beta*O: no partials in HBM, no finish launch, deterministic.
+template<bool CLUSTER>
 __global__ void __launch_bounds__(F_THREADS, 1) k_gemm_tcf(TcfP p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // SWIZZLE_128B tiles: 1024-byte aligned
@@ -200,12 +221,20 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_gemm_tcf(TcfP p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(aempty0 + 8 * b);
         }
+        if (CLUSTER) {
+            // park the tile: the operand ring is idle (the last accumulator commit covers every MMA that read it)
+            float *stage = reinterpret_cast<float*>(smem);
+            const int r = q * 32 + lane;
+            #pragma unroll
+            for (int j = 0; j < CW; j += 4)
+                *reinterpret_cast<float4*>(stage + tcf_stage_off(r, (h * CW + j) >> 2)) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        }
         float *dst; float alpha = p.alpha, beta = p.beta;
         if (p.splits > 1) { dst = p.part + (int64_t)zs * p.M * p.N; alpha = 1.0f; beta = 0.0f; }
         else dst = p.O;
         const bool n_vec = ((p.N & 3) == 0) && ((((uintptr_t)dst) & 15) == 0);
         const int col0 = nt * F_BN + h * CW;
-        if (row < p.M && col0 < p.N) {
+        if (!CLUSTER && row < p.M && col0 < p.N) {
             float *o = dst + (int64_t)row * p.N + col0;
             #pragma unroll
             for (int j = 0; j < CW; j += 4) {
@@ -231,6 +260,34 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_gemm_tcf(TcfP p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER) {
+        const int S = (int)gridDim.z;                                  // cluster = (1, 1, S): rank in the cluster = blockIdx.z
+        tcf_cluster_sync();                                            // every CTA's tile is parked and visible cluster-wide
+        const float *stage = reinterpret_cast<const float*>(smem);
+        const int rpr = F_BM / S;                                      // rows of the tile this CTA finishes (S divides 128)
+        const bool o_vec = ((p.N & 3) == 0) && ((((uintptr_t)p.O) & 15) == 0);
+        for (int idx = threadIdx.x; idx < rpr * (F_BN / 4); idx += F_THREADS) {
+            const int r = zs * rpr + (idx >> 5), c4 = idx & 31;
+            float4 sum = tcf_ld_dsmem4(stage + tcf_stage_off(r, c4), 0u);
+            for (int qk = 1; qk < S; qk++) {
+                const float4 v = tcf_ld_dsmem4(stage + tcf_stage_off(r, c4), (uint32_t)qk);
+                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            }
+            const int gr = mt * F_BM + r, gc = nt * F_BN + c4 * 4;
+            if (gr >= p.M || gc >= p.N) continue;
+            float *o = p.O + (int64_t)gr * p.N + gc;
+            const float out[4] = {sum.x * p.alpha, sum.y * p.alpha, sum.z * p.alpha, sum.w * p.alpha};
+            if (o_vec && gc + 3 < p.N) {
+                float4 w = make_float4(out[0], out[1], out[2], out[3]);
+                if (p.beta != 0.0f) { const float4 old = *reinterpret_cast<const float4*>(o); w.x += old.x * p.beta; w.y += old.y * p.beta; w.z += old.z * p.beta; w.w += old.w * p.beta; }
+                stg4(o, w);
+            } else {
+                #pragma unroll
+                for (int e = 0; e < 4; e++) if (gc + e < p.N) o[e] = (p.beta != 0.0f) ? out[e] + o[e] * p.beta : out[e];
+            }
+        }
+        tcf_cluster_sync();                                            // nobody leaves while its tile is still being read
+    }
     if (warp == F_NPROD) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * F_BN); }
 }
 
@@ -276,24 +333,52 @@ int gemm_tcf(const float *A, const float *B, float *O, float alpha, float beta, 
         if (splits > 32) splits = 32;
         if (splits < 1) splits = 1;
     }
+    // EXPERIMENTAL cluster variant (T4K_TCF_CLUSTER=1): split count = cluster size, a power of two <= 8 (portable), every split non-empty
+    static int use_cluster = -1;
+    if (use_cluster < 0) { const char *e = getenv("T4K_TCF_CLUSTER"); use_cluster = (e && e[0] == '1') ? 1 : 0; }
+    bool cluster = false;
+    if (use_cluster && splits >= 2) {
+        int S = 1; while (S * 2 <= splits && S * 2 <= 8) S *= 2;
+        const int per = (KT + S - 1) / S;
+        if (S >= 2 && (KT + per - 1) / per == S) { splits = S; cluster = true; }
+    }
     int kt_per = (KT + splits - 1) / splits;
     splits = (KT + kt_per - 1) / kt_per;
     TcfP p{A, B, O, alpha, beta, M, N, K,
            tA ? 1 : (int64_t)K, tA ? (int64_t)M : 1,          // A [M,K] row-major, or stored [K,M] when tA
            tB ? (int64_t)K : 1, tB ? 1 : (int64_t)N,          // B [K,N] row-major → (n,k) at k*N + n; stored [N,K] when tB
            KT, kt_per, splits, nullptr};
+    constexpr size_t smem = (size_t)F_STAGES * F_STAGE_B + 1024 + 256;
+    if (cluster) {
+        static bool cattr = false;
+        if (!cattr) {
+            cudaError_t e = cudaFuncSetAttribute(k_gemm_tcf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            cattr = true;
+        }
+        p.splits = 1;                                                  // the kernel writes O itself (its split count is gridDim.z)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ntiles, mtiles, splits); cfg.blockDim = dim3(F_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = (unsigned)splits;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_gemm_tcf<true>, p);
+        int rc = check_launch();
+        if (defer) { defer->part = O; defer->splits = 1; }
+        return rc;
+    }
     if (splits > 1) {
         p.part = (float*)workspace((size_t)splits * M * N * sizeof(float), 7);
         if (!p.part) return T4K_ENOMEM;
     }
-    constexpr size_t smem = (size_t)F_STAGES * F_STAGE_B + 1024 + 256;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tcf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tcf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    launch_std(k_gemm_tcf, dim3(ntiles, mtiles, splits), dim3(F_THREADS), smem, st, p);
+    launch_std(k_gemm_tcf<false>, dim3(ntiles, mtiles, splits), dim3(F_THREADS), smem, st, p);
     int rc = check_launch();
     if (defer) { defer->part = splits > 1 ? p.part : O; defer->splits = splits; return rc; }
     if (rc || splits == 1) return rc;
