@@ -11,8 +11,9 @@ one step = forward + loss.ce + backprop + nn.adam on synthetic 28x28x1 data.  On
 `value`   : device-timed (CUDA events on the launching stream, max over ranks), inputs resident in HBM, one CUDA-graph launch per step.
 `e2e`     : the same step through the public host API the way a training loop over a dataset runs: every step's mini-batch starts in
             pinned host memory as U8 pixels + U8 labels (what an MNIST loader holds), Dataset.stage() copies the bytes, the device
-            normalises and one-hots them, and every step's loss is read back on the host (Model.train_step).
-`roofline`: the dominant call of the step, timed live (graph of 20 launches replayed between two events on its stream), against the
+            normalises and one-hots them (inside the step's first kernel), and every step's loss is read back on the host (Model.train_step).
+`roofline`: the call around the dominant kernel of the step (largest single launch of the committed ncu launch list, named in
+            profiles/ncu_traffic.json), timed live (graph of 20 launches replayed between two events on its stream), against the
             measured HBM bandwidth; `calls` lists every call of the step the same way.
 `extras`  : the other headline numbers — GEMM 4096^3 (both tensor-core engines, with their measured error), conv2d 3x3 64->64 @56x56 at
             the full N=8192 sharded over the ranks, one GAN iteration of examples/t4_40b.4th at N=1024 per GPU.
