@@ -118,7 +118,8 @@ __device__ __forceinline__ float4 tcf_ld_dsmem4(const float *local, uint32_t ran
 __device__ __forceinline__ int tcf_stage_off(int row, int c4) { return row * F_BN + ((c4 ^ (row & 31)) << 2); }
 
 // CLUSTER = false: split-K partials go to global memory, a second launch (or the caller's fused finish) adds them.
-// CLUSTER = true (EXPERIMENTAL, opt-in with T4K_TCF_CLUSTER=1, not yet measured on the device): the `splits` CTAs of one output tile
+// CLUSTER = true (EXPERIMENTAL, opt-in with T4K_TCF_CLUSTER=1; correct on the device — tests/test_gpu_kernels.py -k tcf_layer_shapes with the
+// variable set: 24/24 vs float64 — but not yet TIMED, so the automatic path does not use it): the `splits` CTAs of one output tile
 // form a thread-block cluster (1 x 1 x splits, splits a power of two <= 8); every CTA parks its accumulator tile in its own shared
 // memory, and after a cluster barrier CTA r adds rows [r*128/splits, (r+1)*128/splits) of all the parked tiles in RANK ORDER through
 // distributed shared memory and writes alpha*sum + beta*O: no partials in HBM, no finish launch, deterministic.
