@@ -10,12 +10,17 @@
 //   forward : conv (FMA order of k_conv_fwd_small: bias, then ky,kx,c1 — bit-equal), max-pool and relu never leave
 //             registers; the conv output is written as 2 x (2*C0) contiguous floats per thread (128-bit stores,
 //             neighbouring threads neighbouring addresses), pooled tensors as 64-bit stores;
-//   backward: (C1 == 1) the window's forward conv outputs are re-read into registers (128-bit loads) to redo the
+//   backward: (C1 == 1) 128-thread CTAs, TWO windows per thread (4 CTAs/SM: a 512-sample batch is one wave).  Every global read of
+//             the CTA is requested before its first barrier: dY / input / taps as asynchronous copies into shared memory, the relu
+//             mask and the windows' forward conv outputs (128-bit loads) into registers.  The conv outputs redo the
 //             arg-max routing (first strict max in y,x order, nmath.tcu:535-549), the routed gradient goes back
 //             to HBM from registers and into a zero-haloed channel-major smem tile for the dX gather;
-//             dF/dB: per-thread partial over its window (3 taps x C0 per pass), reduced across the warp with a
+//             dF/dB: per-thread partials in channel passes (9 taps x 5 channels + their dB sums per pass: every routed value is
+//             read once for all taps), reduced across the warp with a
 //             transposing butterfly (31 shuffles per 32 values), across warps in smem, per-sample partials are
 //             summed in sample order by k_wgrad_fin (deterministic; the reference uses atomics, nmath.tcu:307-336).
+//   forward with dataset feed (FEED): the sample's pixels come from the staged U8 block, are normalised in registers and written to
+//             the dataset tensor, the model's input layer and the conv tile; the CTA also writes the sample's label and one-hot row.
 // Shapes outside this envelope fall back to the first-generation kernels in conv.cu (same results).
 #include "common.cuh"
 #include <cstdlib>
