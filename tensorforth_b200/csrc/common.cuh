@@ -18,14 +18,17 @@ int  check_launch();                          // cudaGetLastError() → rc, ++g_
 void *workspace(size_t bytes, int slot);      // library-owned per-device scratch (grown on demand)
 float *reduce_slot(cudaStream_t st);          // 4 KiB partials + counter, ring of slots, zeroed counter
 
-struct GemmDeferred { const float *part; int splits; };   // gemm_simt(..., defer): caller-side split-K finish
+struct GemmDeferred { const float *part; int splits; };   // gemm_simt(..., defer): caller-side split-K finish (splits == 0: nothing left to do, see GemmEpilogue)
+// bias + activation epilogue a GEMM engine MAY apply itself (only the cluster variant of gemm_tcf does): Y = product + bias (written to O),
+// A = act(Y), F = saved derivative / mask.  An engine that applied it reports defer->splits = 0.
+struct GemmEpilogue { const float *bias; float *A, *F; int layer; float alpha; };
 int gemm_simt(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
               int M, int N, int K, int C, int batch, int64_t sA, int64_t sB, int64_t sO, cudaStream_t st, GemmDeferred *defer = nullptr);
 
 // mid-size single-launch tensor-core GEMM (gemm_tcf.cu): in-kernel 3xTF32 split, split-K; same deferred-finish contract
 bool gemm_tcf_ok(int tA, int tB, int M, int N, int K, int C, int batch);
 int  gemm_tcf(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
-              int M, int N, int K, cudaStream_t st, GemmDeferred *defer = nullptr);
+              int M, int N, int K, cudaStream_t st, GemmDeferred *defer = nullptr, const GemmEpilogue *epi = nullptr);
 
 // layer-sized single-launch GEMM on warp-level MMA (gemm_mma.cu): 3xTF32, split-K with in-kernel last-CTA finish; deferred-finish contract as above
 bool gemm_mma_ok(int M, int N, int K, int C, int batch);

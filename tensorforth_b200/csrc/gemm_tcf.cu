@@ -16,6 +16,7 @@
 // issues 12 MMAs of 128x128x8: producers and tensor pipe are balanced at ~0.5 us per k-block.
 // Bound: tensor pipe for large K, launch/ramp latency for the layer shapes (a few k-blocks per CTA).
 #include "tc_ptx.cuh"
+#include "act.cuh"
 #include <cstdlib>
 
 namespace t4k {
@@ -41,6 +42,11 @@ struct TcfP {
     int KT, kt_per_split, splits;
     float *part;                 // [splits][M*N] when splits > 1
 };
+// CLUSTER variant only: fused bias (+ activation) epilogue of a linear layer, bias == nullptr: none.  Kept out of TcfP so that the
+// parameter block — and with it the generated code — of the default kernel stays exactly what was validated on the device.
+struct TcfEpi { const float *bias; float *actA, *actF; int layer; float act_alpha; };
+template<bool CLUSTER> struct TcfArgs { TcfP p; };
+template<> struct TcfArgs<true> { TcfP p; TcfEpi e; };
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -119,12 +125,14 @@ __device__ __forceinline__ int tcf_stage_off(int row, int c4) { return row * F_B
 
 // CLUSTER = false: split-K partials go to global memory, a second launch (or the caller's fused finish) adds them.
 // CLUSTER = true (EXPERIMENTAL, opt-in with T4K_TCF_CLUSTER=1; correct on the device — tests/test_gpu_kernels.py -k tcf_layer_shapes with the
-// variable set: 24/24 vs float64 — but not yet TIMED, so the automatic path does not use it): the `splits` CTAs of one output tile
+// variable set: 24/24 vs float64 — but not yet TIMED, so the automatic path does not use it; the fused bias/activation epilogue below
+// (t4k_linear_act_fwd passes it) was added after that run and has not been on a device yet): the `splits` CTAs of one output tile
 // form a thread-block cluster (1 x 1 x splits, splits a power of two <= 8); every CTA parks its accumulator tile in its own shared
 // memory, and after a cluster barrier CTA r adds rows [r*128/splits, (r+1)*128/splits) of all the parked tiles in RANK ORDER through
 // distributed shared memory and writes alpha*sum + beta*O: no partials in HBM, no finish launch, deterministic.
 template<bool CLUSTER>
-__global__ void __launch_bounds__(F_THREADS, 1) k_gemm_tcf(TcfP p) {
+__global__ void __launch_bounds__(F_THREADS, 1) k_gemm_tcf(const TcfArgs<CLUSTER> args) {
+    const TcfP &p = args.p;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // SWIZZLE_128B tiles: 1024-byte aligned
     uint64_t *bars = (uint64_t*)(smem + F_STAGES * F_STAGE_B);                        // full[S], empty[S], acc_full[2], acc_empty[2]
@@ -267,6 +275,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_gemm_tcf(TcfP p) {
         const float *stage = reinterpret_cast<const float*>(smem);
         const int rpr = F_BM / S;                                      // rows of the tile this CTA finishes (S divides 128)
         const bool o_vec = ((p.N & 3) == 0) && ((((uintptr_t)p.O) & 15) == 0);
+        const TcfEpi epi = [&] { if constexpr (CLUSTER) return args.e; else return TcfEpi{}; }();
         for (int idx = threadIdx.x; idx < rpr * (F_BN / 4); idx += F_THREADS) {
             const int r = zs * rpr + (idx >> 5), c4 = idx & 31;
             float4 sum = tcf_ld_dsmem4(stage + tcf_stage_off(r, c4), 0u);
@@ -277,7 +286,31 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_gemm_tcf(TcfP p) {
             const int gr = mt * F_BM + r, gc = nt * F_BN + c4 * 4;
             if (gr >= p.M || gc >= p.N) continue;
             float *o = p.O + (int64_t)gr * p.N + gc;
-            const float out[4] = {sum.x * p.alpha, sum.y * p.alpha, sum.z * p.alpha, sum.w * p.alpha};
+            float out[4] = {sum.x * p.alpha, sum.y * p.alpha, sum.z * p.alpha, sum.w * p.alpha};
+            if (epi.bias) {
+                // linear layer epilogue (k_linear_fin's arithmetic: Σ splits, + bias, activation): beta == 0 here
+                #pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (gc + e >= p.N) break;
+                    const float y = out[e] + __ldg(epi.bias + gc + e);
+                    o[e] = y;
+                    if (epi.layer != T4K_L_NONE) {
+                        const int64_t at = (int64_t)gr * p.N + gc + e;
+                        float a = 0.0f, f = (epi.layer == T4K_L_DROPOUT) ? epi.actF[at] : 0.0f;
+                        switch (epi.layer) {
+                        case T4K_L_RELU:    act<T4K_L_RELU>(y, epi.act_alpha, a, f); break;
+                        case T4K_L_TANH:    act<T4K_L_TANH>(y, epi.act_alpha, a, f); break;
+                        case T4K_L_SIGMOID: act<T4K_L_SIGMOID>(y, epi.act_alpha, a, f); break;
+                        case T4K_L_SELU:    act<T4K_L_SELU>(y, epi.act_alpha, a, f); break;
+                        case T4K_L_LEAKYRL: act<T4K_L_LEAKYRL>(y, epi.act_alpha, a, f); break;
+                        case T4K_L_ELU:     act<T4K_L_ELU>(y, epi.act_alpha, a, f); break;
+                        default:            act<T4K_L_DROPOUT>(y, epi.act_alpha, a, f); break;
+                        }
+                        epi.actA[at] = a; epi.actF[at] = f;
+                    }
+                }
+                continue;
+            }
             if (o_vec && gc + 3 < p.N) {
                 float4 w = make_float4(out[0], out[1], out[2], out[3]);
                 if (p.beta != 0.0f) { const float4 old = *reinterpret_cast<const float4*>(o); w.x += old.x * p.beta; w.y += old.y * p.beta; w.z += old.z * p.beta; w.w += old.w * p.beta; }
@@ -324,7 +357,7 @@ bool gemm_tcf_ok(int tA, int tB, int M, int N, int K, int C, int batch) {
 
 // defer: as gemm_simt — the caller runs its own split-K finish over defer->part [splits][M*N] (splits == 1: O holds the product)
 int gemm_tcf(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
-             int M, int N, int K, cudaStream_t st, GemmDeferred *defer) {
+             int M, int N, int K, cudaStream_t st, GemmDeferred *defer, const GemmEpilogue *epi) {
     const int mtiles = (M + F_BM - 1) / F_BM, ntiles = (N + F_BN - 1) / F_BN, KT = (K + F_BK - 1) / F_BK;
     const int sms = sm_count();
     int splits = 1;
@@ -358,15 +391,18 @@ int gemm_tcf(const float *A, const float *B, float *O, float alpha, float beta, 
             cattr = true;
         }
         p.splits = 1;                                                  // the kernel writes O itself (its split count is gridDim.z)
+        const bool fused_epi = epi && epi->bias && beta == 0.0f && (epi->layer == T4K_L_NONE || (epi->A && epi->F));
+        TcfArgs<true> ca{p, TcfEpi{nullptr, nullptr, nullptr, T4K_L_NONE, 0.0f}};
+        if (fused_epi) ca.e = TcfEpi{epi->bias, epi->A, epi->F, epi->layer, epi->alpha};
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(ntiles, mtiles, splits); cfg.blockDim = dim3(F_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = (unsigned)splits;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, k_gemm_tcf<true>, p);
+        cudaLaunchKernelEx(&cfg, k_gemm_tcf<true>, ca);
         int rc = check_launch();
-        if (defer) { defer->part = O; defer->splits = 1; }
+        if (defer) { defer->part = O; defer->splits = fused_epi ? 0 : 1; }
         return rc;
     }
     if (splits > 1) {
@@ -379,7 +415,7 @@ int gemm_tcf(const float *A, const float *B, float *O, float alpha, float beta, 
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    launch_std(k_gemm_tcf<false>, dim3(ntiles, mtiles, splits), dim3(F_THREADS), smem, st, p);
+    launch_std(k_gemm_tcf<false>, dim3(ntiles, mtiles, splits), dim3(F_THREADS), smem, st, TcfArgs<false>{p});
     int rc = check_launch();
     if (defer) { defer->part = splits > 1 ? p.part : O; defer->splits = splits; return rc; }
     if (rc || splits == 1) return rc;

@@ -52,10 +52,11 @@ template<int L> static int launch_fin(const GemmDeferred &d, int64_t MN, int E0,
 static int linear_act_fwd(int layer, const float *X, const float *W, const float *B, float *Y, float *A, float *F, float alpha,
                           int N, int E0, int E1, cudaStream_t st) {
     GemmDeferred d{nullptr, 1};
+    const GemmEpilogue epi{B, A, F, layer, alpha};         // taken by the (opt-in) cluster variant of gemm_tcf only: reports d.splits == 0
     int rc = layer_mma(N, E0, E1, 1, 1)         ? gemm_mma(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, st, &d)       // tensor cores for layer-sized products
-           : gemm_tcf_ok(0, 1, N, E0, E1, 1, 1) ? gemm_tcf(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, st, &d)
+           : gemm_tcf_ok(0, 1, N, E0, E1, 1, 1) ? gemm_tcf(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, st, &d, &epi)
                                                 : gemm_simt(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, 1, 1, 0, 0, 0, st, &d);
-    if (rc) return rc;
+    if (rc || d.splits == 0) return rc;
     const int64_t MN = (int64_t)N * E0;
     switch (layer) {
     case T4K_L_NONE:    return launch_fin<T4K_L_NONE>(d, MN, E0, B, Y, A, F, alpha, st);
