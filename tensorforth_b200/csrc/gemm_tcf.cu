@@ -346,13 +346,19 @@ __global__ void __launch_bounds__(T4K_THREADS) k_splitk_fin_f(const float *__res
     }
 }
 
+static bool tcf_cluster_on() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("T4K_TCF_CLUSTER"); on = (e && e[0] == '1') ? 1 : 0; }
+    return on == 1;
+}
 bool gemm_tcf_ok(int tA, int tB, int M, int N, int K, int C, int batch) {
     // Measured on B200 (bench_scripts/gemm_probe.py, profiles/r01_gemm_probe.txt): launch + TMEM/barrier set-up + epilogue + split-K
     // finish cost ~10 us, so the FP32-FMA kernel wins below ~0.25 GFLOP (MNIST 1960->100 = 0.2 GFLOP stays there).  Above it this
     // kernel wins when BOTH operands are K-contiguous (X @ W^T, the linear forward: 0.27 GFLOP 13 vs 16 us, 0.82 GFLOP 20 vs 33 us);
     // an operand that is contiguous along M/N goes through 4-byte scattered shared-memory stores and loses to the packed-plane
     // engine (dW, dX at 0.82 GFLOP: 24-28 vs 21 us), so those shapes are left to the other two engines.
-    return C == 1 && batch == 1 && tA == 0 && tB == 1 && M >= 32 && N >= 32 && K >= 32 && (double)M * N * K >= 1.2e8;
+    // with the (opt-in, untimed) cluster variant the finish launch and the partial round trip are gone: let the 0.2-GFLOP class in too
+    return C == 1 && batch == 1 && tA == 0 && tB == 1 && M >= 32 && N >= 32 && K >= 32 && (double)M * N * K >= (tcf_cluster_on() ? 5.0e7 : 1.2e8);
 }
 
 // defer: as gemm_simt — the caller runs its own split-K finish over defer->part [splits][M*N] (splits == 1: O holds the product)
@@ -368,10 +374,8 @@ int gemm_tcf(const float *A, const float *B, float *O, float alpha, float beta, 
         if (splits < 1) splits = 1;
     }
     // EXPERIMENTAL cluster variant (T4K_TCF_CLUSTER=1): split count = cluster size, a power of two <= 8 (portable), every split non-empty
-    static int use_cluster = -1;
-    if (use_cluster < 0) { const char *e = getenv("T4K_TCF_CLUSTER"); use_cluster = (e && e[0] == '1') ? 1 : 0; }
     bool cluster = false;
-    if (use_cluster && splits >= 2) {
+    if (tcf_cluster_on() && splits >= 2) {
         int S = 1; while (S * 2 <= splits && S * 2 <= 8) S *= 2;
         const int per = (KT + S - 1) / S;
         if (S >= 2 && (KT + per - 1) / per == S) { splits = S; cluster = true; }
