@@ -28,7 +28,7 @@ for N, layers in ((512, [(1960, 100)]), (1024, [(784, 512), (512, 256), (128, 25
     for E1, E0 in layers:
         shapes += [("N%d fwd  %d->%d" % (N, E1, E0), N, E0, E1, 0, 1), ("N%d dW   %d->%d" % (N, E1, E0), E0, E1, N, 1, 0), ("N%d dX   %d->%d" % (N, E1, E0), N, E1, E0, 0, 0)]
 shapes += [("square 512", 512, 512, 512, 0, 0), ("square 1024", 1024, 1024, 1024, 0, 0), ("square 2048", 2048, 2048, 2048, 0, 0)]
-engines = (("simt", t4.GEMM_SIMT), ("tc(pack)", t4.GEMM_TC), ("tcf", t4.GEMM_TCF), ("mma", t4.GEMM_MMA), ("auto", t4.GEMM_AUTO))
+engines = (("simt", t4.GEMM_SIMT), ("tc(pack)", t4.GEMM_TC), ("tcf", t4.GEMM_TCF), ("tl", t4.GEMM_TL), ("auto", t4.GEMM_AUTO))
 for name, M, Nn, K, tA, tB in shapes:
     A = torch.randn((K, M) if tA else (M, K), device="cuda"); B = torch.randn((Nn, K) if tB else (K, Nn), device="cuda"); O = torch.zeros(M, Nn, device="cuda")
     ref = (A.double().T if tA else A.double()) @ (B.double().T if tB else B.double())

@@ -65,10 +65,11 @@ enum t4k_gemm_engine { T4K_GEMM_AUTO = 0, T4K_GEMM_SIMT = 1,   /* FP32 FMA (gemm
                        T4K_GEMM_TC_BF16X3 = 4,                 /* tcgen05 BF16x3 (a = hi + lo in bf16; hi*hi + hi*lo + lo*hi): twice the MMA rate of 3xTF32;
                                                                 * measured 4.1e-6 of the result's rms at K=4096 (3xTF32: 1.8e-6; the reference's FP32-FMA
                                                                 * accumulation itself: ~3.8e-6).  AUTO takes it for M*N*K >= 2e10 only (T4K_GEMM_BIG=tf32: never) */
-                       T4K_GEMM_MMA = 5 };                     /* warp-level MMA (mma.sync m16n8k8 TF32) 3xTF32, 64x64 tiles, in-kernel split-K finish, one launch
-                                                                * (gemm_mma.cu): the layer-sized products (0.004 - 1.5 G multiply-adds), latency-bound class;
-                                                                * measured no faster than the FP32-FMA engine on B200 (legacy MMA rate), so AUTO takes it only with
-                                                                * T4K_GEMM_MMA=1 in the environment */
+                       T4K_GEMM_MMA = 5,                       /* (retired: warp-level mma.sync engine of round 1, measured no faster than FP32 FMA; T4K_ENOSUP) */
+                       T4K_GEMM_TL = 6 };                      /* tcgen05 3xTF32 LAYER GEMM (gemm_tl.cu): TMA-fed raw FP32 tiles (any transposition native: MN-major
+                                                                * UMMA operands), lo plane derived in shared memory, split-K inside a thread-block cluster reduced over
+                                                                * distributed shared memory, fused linear-layer epilogues; one launch.  AUTO takes it for
+                                                                * 4e6 <= M*N*K < 2e10 when the operands are 16-byte aligned with row pitches that are multiples of 4 */
 
 /* ---- library / device ------------------------------------------------------------- */
 int         t4k_version(void);
@@ -123,6 +124,11 @@ int t4k_gemm(const float *A, const float *B, float *O, float alpha, float beta, 
 int t4k_gemm_ex(int engine, const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
              int M, int N, int K, int C, int batch, int64_t strideA, int64_t strideB, int64_t strideO,
              t4k_stream_t s);
+
+/* tuning / test hook of the layer GEMM (T4K_GEMM_TL): what 0 = AUTO may take it (default 1; T4K_GEMM_TL=0), 1 = store the masked hi plane
+ * explicitly instead of relying on kind::tf32 ignoring the 13 low mantissa bits (default 0), 2 = largest cluster size / split-K factor
+ * (default 16).  Returns the previous value. */
+int t4k_set_gemm_tl(int what, int value);
 
 /* ---- NN forward: src/nn/forward.cu + src/nn/nmath.cu/.tcu ---------------------------- */
 /* k_bias (nmath.cu:27-35, forward.cu:195): Y[n,e] += B[e] */
@@ -179,6 +185,11 @@ int t4k_linear_bwd(const float *X, const float *W, const float *dY, float *dX, f
 /* as t4k_linear_bwd; skip_db != 0 leaves dB alone (it was accumulated by t4k_mlp_head_bwd) */
 int t4k_linear_bwd_ex(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
                       int N, int E0, int E1, int train, int skip_db, t4k_stream_t s);
+/* _blinear followed by the _bactivate of the activation layer in front of it (backprop.cu:194-263) with the mask multiply in the dX
+ * GEMM's epilogue: dX = dY @ W (the linear layer's input tensor = the activation's output tensor), dXprev = dX * Fprev (the activation's
+ * input tensor); dW/dB as t4k_linear_bwd_ex.  Same tensors written as the two calls. */
+int t4k_linear_bwd_act(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
+                       const float *Fprev, float *dXprev, int N, int E0, int E1, int train, int skip_db, t4k_stream_t s);
 /* classifier head, backward, one launch (backprop.cu:76-140,194-263), E0 <= 32, E1 <= 128 else T4K_ENOSUP:
  *   P <- P - T (Model::_bprep), Ylin <- P - T (softmax backward is a copy), dB += Σ_n (P-T), dW += (P-T)^T @ X2,
  *   X2 <- (P-T) @ W (in place: the small linear's input tensor receives its dX),

@@ -30,11 +30,17 @@ bool gemm_tcf_ok(int tA, int tB, int M, int N, int K, int C, int batch);
 int  gemm_tcf(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
               int M, int N, int K, cudaStream_t st, GemmDeferred *defer = nullptr, const GemmEpilogue *epi = nullptr);
 
-// layer-sized single-launch GEMM on warp-level MMA (gemm_mma.cu): 3xTF32, split-K with in-kernel last-CTA finish; deferred-finish contract as above
-bool gemm_mma_ok(int M, int N, int K, int C, int batch);
-int  gemm_mma(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
-              int M, int N, int K, cudaStream_t st, GemmDeferred *defer = nullptr);
-bool layer_mma(int M, int N, int K, int C, int batch);      // policy: does AUTO take gemm_mma for this problem (T4K_GEMM_MMA=0: never)
+// the layer GEMM (gemm_tl.cu): TMA-fed 3xTF32 on tcgen05, any transposition native, split-K in a thread-block cluster reduced over
+// distributed shared memory, epilogue fused (TlEpi.mode: 0 alpha/beta, 1 bias + activation, 2 bias + activation + classifier head,
+// 3 dX and dX * F).  One launch, nothing deferred.
+struct TlEpi {
+    int mode; const float *bias; float *actA, *actF; int layer; float act_alpha;       // mode 1, 2: Y = acc + bias (to O), A = act(Y), F = derivative / mask
+    const float *W2, *B2; float *Y2, *P, *P2; int E2;                                 // mode 2: Y2 = A @ W2^T + B2 [M,E2], P = softmax(Y2), P2 = copy of P (may be null)
+    const float *F; float *O2;                                                        // mode 3: O = acc, O2 = acc * F
+};
+bool gemm_tl_ok(const float *A, const float *B, const float *O, int tA, int tB, int M, int N, int K, int C, int batch);
+int  gemm_tl(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
+             int M, int N, int K, cudaStream_t st, const TlEpi *epi = nullptr);
 
 static inline cudaStream_t STRM(t4k_stream_t s) { return (cudaStream_t)s; }
 

@@ -459,14 +459,16 @@ extern "C" int t4k_gemm_ex(int engine, const float *A, const float *B, float *O,
         for (int b = 0; b < batch; b++) { int rc = gemm_tcf(A + b * sA, B + b * sB, O + b * sO, alpha, beta, tA, tB, M, N, K, STRM(s)); if (rc) return rc; }
         return 0;
     }
-    else if (engine == T4K_GEMM_MMA) {
-        if (!gemm_mma_ok(M, N, K, C, 1)) return T4K_EINVAL;
-        for (int b = 0; b < batch; b++) { int rc = gemm_mma(A + b * sA, B + b * sB, O + b * sO, alpha, beta, tA, tB, M, N, K, STRM(s)); if (rc) return rc; }
+    else if (engine == T4K_GEMM_MMA) return T4K_ENOSUP;                       // retired (include/t4k.h)
+    else if (engine == T4K_GEMM_TL) {
+        if (C != 1 || K < 1) return T4K_EINVAL;
+        if (((tA ? M : K) & 3) || ((tB ? K : N) & 3) || !aligned16(A) || !aligned16(B)) return T4K_EINVAL;   // TMA: 16-byte pitches
+        for (int b = 0; b < batch; b++) { int rc = gemm_tl(A + b * sA, B + b * sB, O + b * sO, alpha, beta, tA, tB, M, N, K, STRM(s)); if (rc) return rc; }
         return 0;
     }
     else if (engine == T4K_GEMM_AUTO) {
-        // layer-sized products (linear fwd / dW / dX at batch 512-1024): latency-bound, one launch on the warp-level MMA (gemm_mma.cu)
-        if (layer_mma(M, N, K, C, batch)) return gemm_mma(A, B, O, alpha, beta, tA, tB, M, N, K, STRM(s));
+        // layer-sized products (linear fwd / dW / dX at batch 64-4096): latency-bound, one launch of the layer GEMM (gemm_tl.cu)
+        if (gemm_tl_ok(A, B, O, tA, tB, M, N, K, C, batch)) return gemm_tl(A, B, O, alpha, beta, tA, tB, M, N, K, STRM(s));
         // mid-size problems (the NN layers): one launch with the operand split fused in (gemm_tcf.cu).  Big ones: packed planes +
         // bulk-copy fed MMA (two pack passes amortised over many tiles).  Small / channel-interleaved / batched: FP32 FMA.
         if ((double)M * N * K < 2.0e10 && gemm_tcf_ok(tA, tB, M, N, K, C, batch)) return gemm_tcf(A, B, O, alpha, beta, tA, tB, M, N, K, STRM(s));

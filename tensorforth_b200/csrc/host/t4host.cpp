@@ -545,6 +545,10 @@ Model &Model::backprop(Tensor &tgt) {
             // branch also takes the flatten backward (duplicate = dX) and is joined at the end of backprop: dW runs under dX + conv block
             const bool defer = xdup && i >= 4 && _layers[i - 2]->grad_fn == T4K_L_RELU && _layers[i - 3]->grad_fn == T4K_L_MAXPOOL &&
                                _layers[i - 4]->grad_fn == T4K_L_CONV;
+            // an activation / dropout in front of the linear layer: its backward (dX * saved mask) rides in the dX GEMM's epilogue
+            Tensor *pa = (fuse && !xdup && i > 0 && (mask_act(_layers[i - 1]->grad_fn) || _layers[i - 1]->grad_fn == T4K_L_DROPOUT) &&
+                          _layers[i - 1]->numel == _layers[i]->numel && _layers[i - 1]->grad[4]) ? _layers[i - 1] : nullptr;
+            if (pa) { _blinear_act(*_layers[i], *_layers[i + 1], *pa, skip_db); skip_db = false; i -= 2; j++; continue; }
             _blinear(*_layers[i], *_layers[i + 1], skip_db, xdup, defer); skip_db = false;
         }
         else _bstep(*_layers[i], *_layers[i + 1], j == 0);
@@ -626,6 +630,12 @@ int Model::_blinear(Tensor &in, Tensor &out, bool skip_db, Tensor *xdup, bool de
     // dX overwrites the layer input in place; dW needs X first → t4k_linear_bwd orders dW before dX,
     // and dX = dY@W does not read X, so in.data may be both X and dX.
     KCHK(t4k_linear_bwd_ex(in.data, w.data, out.data, in.data, dw.data, db.data, in.N(), (int)out.HWC(), (int)in.HWC(), train, skip_db, ST));
+    return 0;
+}
+int Model::_blinear_act(Tensor &in, Tensor &out, Tensor &act_in, bool skip_db) {     // backprop.cu:194-263
+    Tensor &w = *in.grad[0], &dw = *in.grad[2], &db = *in.grad[3];
+    KCHK(t4k_linear_bwd_act(in.data, w.data, out.data, in.data, dw.data, db.data, act_in.grad[4]->data, act_in.data,
+                            in.N(), (int)out.HWC(), (int)in.HWC(), train, skip_db, ST));
     return 0;
 }
 int Model::_bactivate(Tensor &in, Tensor &out) { KCHK(t4k_activate_bwd(out.data, in.grad[4]->data, in.data, in.numel, ST)); return 0; } // backprop.cu:257-263

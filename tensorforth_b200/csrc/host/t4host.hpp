@@ -248,6 +248,7 @@ private:
     int  _bconv(Tensor &in, Tensor &out);
     int  _blinear(Tensor &in, Tensor &out, bool skip_db = false, Tensor *xdup = nullptr, bool defer = false);
     int  _bactivate(Tensor &in, Tensor &out);
+    int  _blinear_act(Tensor &in, Tensor &out, Tensor &act_in, bool skip_db);   ///< _blinear + the _bactivate of the activation in front (one GEMM epilogue)
     int  _bpool(Tensor &in, Tensor &out, t4_layer fn);
     int  _bupsample(Tensor &in, Tensor &out, t4_layer fn);
     int  _bbatchnorm(Tensor &in, Tensor &out);

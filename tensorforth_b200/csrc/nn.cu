@@ -51,10 +51,13 @@ template<int L> static int launch_fin(const GemmDeferred &d, int64_t MN, int E0,
 }
 static int linear_act_fwd(int layer, const float *X, const float *W, const float *B, float *Y, float *A, float *F, float alpha,
                           int N, int E0, int E1, cudaStream_t st) {
+    if (gemm_tl_ok(X, W, Y, 0, 1, N, E0, E1, 1, 1)) {       // the layer GEMM: bias + activation in its cluster epilogue, one launch
+        TlEpi e{}; e.mode = 1; e.bias = B; e.actA = A; e.actF = F; e.layer = layer; e.act_alpha = alpha;
+        return gemm_tl(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, st, &e);
+    }
     GemmDeferred d{nullptr, 1};
     const GemmEpilogue epi{B, A, F, layer, alpha};         // taken by the (opt-in) cluster variant of gemm_tcf only: reports d.splits == 0
-    int rc = layer_mma(N, E0, E1, 1, 1)         ? gemm_mma(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, st, &d)       // tensor cores for layer-sized products
-           : gemm_tcf_ok(0, 1, N, E0, E1, 1, 1) ? gemm_tcf(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, st, &d, &epi)
+    int rc = gemm_tcf_ok(0, 1, N, E0, E1, 1, 1) ? gemm_tcf(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, st, &d, &epi)
                                                 : gemm_simt(X, W, Y, 1.0f, 0.0f, 0, 1, N, E0, E1, 1, 1, 0, 0, 0, st, &d);
     if (rc || d.splits == 0) return rc;
     const int64_t MN = (int64_t)N * E0;
@@ -361,6 +364,24 @@ extern "C" int t4k_linear_bwd_ex(const float *X, const float *W, const float *dY
     }
     return t4k_gemm(dY, W, dX, 1.0f, 0.0f, 0, 0, N, E1, E0, 1, 1, 0, 0, 0, s);       // dX[N,E1] = dY[N,E0] @ W[E0,E1]
 }
+extern "C" int t4k_linear_bwd_act(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
+                                  const float *Fprev, float *dXprev, int N, int E0, int E1, int train, int skip_db, t4k_stream_t s) {
+    if (!X || !W || !dY || !dX || !Fprev || !dXprev || N < 1 || E0 < 1 || E1 < 1) return T4K_EINVAL;
+    if (!gemm_tl_ok(dY, W, dX, 0, 0, N, E1, E0, 1, 1)) {                            // per-layer path: _blinear, then _bactivate
+        int rc = t4k_linear_bwd_ex(X, W, dY, dX, dW, dB, N, E0, E1, train, skip_db, s);
+        if (rc) return rc;
+        return t4k_activate_bwd(dX, Fprev, dXprev, (int64_t)N * E1, s);
+    }
+    if (train) {
+        if (!dW || (!dB && !skip_db)) return T4K_EINVAL;
+        int rc = 0;
+        if (!skip_db) { rc = t4k_dbias(dY, dB, N, E0, s); if (rc) return rc; }
+        rc = t4k_gemm(dY, X, dW, 1.0f, 1.0f, 1, 0, E0, E1, N, 1, 1, 0, 0, 0, s);
+        if (rc) return rc;
+    }
+    TlEpi e{}; e.mode = 3; e.F = Fprev; e.O2 = dXprev;
+    return gemm_tl(dY, W, dX, 1.0f, 0.0f, 0, 0, N, E1, E0, STRM(s), &e);            // dX = dY @ W ; dXprev = dX * Fprev
+}
 extern "C" int t4k_linear_bwd(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
                               int N, int E0, int E1, int train, t4k_stream_t s) {
     return t4k_linear_bwd_ex(X, W, dY, dX, dW, dB, N, E0, E1, train, 0, s);
@@ -393,9 +414,15 @@ extern "C" int t4k_linear_act_head_fwd(int layer, const float *X, const float *W
     if (!X || !W1 || !B1 || !Y1 || !A1 || !F1 || !W2 || !B2 || !Y2 || !P || N < 1 || EH < 1 || E1 < 1 || E0 < 1) return T4K_EINVAL;
     if (E0 > 32 || EH > 128 || (size_t)E0 * EH * sizeof(float) > 40 * 1024) return T4K_ENOSUP;
     cudaStream_t st = STRM(s);
+    if (layer != T4K_L_DROPOUT && (EH & 3) == 0 && gemm_tl_ok(X, W1, Y1, 0, 1, N, EH, E1, 1, 1)) {
+        // ONE launch: layer GEMM, and in its cluster epilogue bias + activation + the small linear + softmax on the finished rows
+        TlEpi e{}; e.mode = 2; e.bias = B1; e.actA = A1; e.actF = F1; e.layer = layer; e.act_alpha = alpha;
+        e.W2 = W2; e.B2 = B2; e.Y2 = Y2; e.P = P; e.P2 = Pdup; e.E2 = E0;
+        int rc = gemm_tl(X, W1, Y1, 1.0f, 0.0f, 0, 1, N, EH, E1, st, &e);
+        if (rc != T4K_ENOSUP) return rc;
+    }
     GemmDeferred d{nullptr, 1};
-    int rc = layer_mma(N, EH, E1, 1, 1)         ? gemm_mma(X, W1, Y1, 1.0f, 0.0f, 0, 1, N, EH, E1, st, &d)
-           : gemm_tcf_ok(0, 1, N, EH, E1, 1, 1) ? gemm_tcf(X, W1, Y1, 1.0f, 0.0f, 0, 1, N, EH, E1, st, &d)
+    int rc = gemm_tcf_ok(0, 1, N, EH, E1, 1, 1) ? gemm_tcf(X, W1, Y1, 1.0f, 0.0f, 0, 1, N, EH, E1, st, &d)
                                                 : gemm_simt(X, W1, Y1, 1.0f, 0.0f, 0, 1, N, EH, E1, 1, 1, 0, 0, 0, st, &d);
     if (rc) return rc;
     const int64_t MN = (int64_t)N * EH;

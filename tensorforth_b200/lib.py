@@ -16,7 +16,7 @@ SO_PATH = os.path.join(_HERE, "libt4k.so")
  L_DCONV) = range(19)
 LOSS_MSE, LOSS_BCE, LOSS_CE, LOSS_NLL = range(4)
 UNIFORM, NORMAL = 0, 1
-GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_TCF, GEMM_TC_BF16X3, GEMM_MMA = 0, 1, 2, 3, 4, 5
+GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_TCF, GEMM_TC_BF16X3, GEMM_MMA, GEMM_TL = 0, 1, 2, 3, 4, 5, 6
 EINVAL, ENOSUP, ENOMEM = -1, -2, -3
 COMM_HANDLE_BYTES = 64
 
@@ -47,6 +47,7 @@ PROTOTYPES = {
     "t4k_nan_inf": (_i, [_p, _l, _p, _p]),
     "t4k_gemm": (_i, [_p, _p, _p, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _l, _p]),
     "t4k_gemm_ex": (_i, [_i, _p, _p, _p, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _l, _p]),
+    "t4k_set_gemm_tl": (_i, [_i, _i]),
     "t4k_bias": (_i, [_p, _p, _i, _i, _p]),
     "t4k_linear_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "t4k_activate_fwd": (_i, [_i, _p, _p, _p, _f, _l, _p]),
@@ -59,6 +60,7 @@ PROTOTYPES = {
     "t4k_dbias": (_i, [_p, _p, _i, _i, _p]),
     "t4k_linear_bwd": (_i, [_p] * 6 + [_i] * 4 + [_p]),
     "t4k_linear_bwd_ex": (_i, [_p] * 6 + [_i] * 5 + [_p]),
+    "t4k_linear_bwd_act": (_i, [_p] * 8 + [_i] * 5 + [_p]),
     "t4k_linear_act_fwd": (_i, [_i] + [_p] * 6 + [_f] + [_i] * 3 + [_p]),
     "t4k_mlp_head_fwd": (_i, [_p] * 5 + [_i] * 3 + [_p]),
     "t4k_mlp_head_fwd_dup": (_i, [_p] * 6 + [_i] * 3 + [_p]),

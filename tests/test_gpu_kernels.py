@@ -160,10 +160,12 @@ def gemm_ref64(A, B, O, alpha, beta, tA, tB):
     return alpha * (a @ b) + beta * O.astype(np.float64)
 
 
-@pytest.mark.parametrize("engine", [t4.GEMM_SIMT, t4.GEMM_TC, t4.GEMM_TCF, t4.GEMM_MMA])
+@pytest.mark.parametrize("engine", [t4.GEMM_SIMT, t4.GEMM_TC, t4.GEMM_TCF, t4.GEMM_TL])
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(2, 2, 3), (64, 64, 64), (128, 128, 32), (200, 100, 70), (67, 63, 45), (130, 260, 513), (512, 100, 1960)])
 def test_gemm_engines(engine, tA, tB, M, N, K):
+    if engine == t4.GEMM_TL and (((M if tA else K) % 4) or ((K if tB else N) % 4)):
+        pytest.skip("layer GEMM: TMA needs 16-byte row pitches (AUTO routes these shapes to the other engines)")
     A = rnd(K, M) if tA else rnd(M, K)
     B = rnd(N, K) if tB else rnd(K, N)
     O0 = rnd(M, N)
@@ -178,7 +180,7 @@ def test_gemm_engines(engine, tA, tB, M, N, K):
 def test_gemm_beta0_ignores_garbage():
     M = N = K = 96
     A, B = rnd(M, K), rnd(K, N)
-    for eng in (t4.GEMM_SIMT, t4.GEMM_TC, t4.GEMM_TCF, t4.GEMM_MMA):
+    for eng in (t4.GEMM_SIMT, t4.GEMM_TC, t4.GEMM_TCF, t4.GEMM_TL):
         o = dev(np.full((M, N), np.nan, np.float32))
         ok(lib().t4k_gemm_ex(eng, ptr(dev(A)), ptr(dev(B)), ptr(o), 1.0, 0.0, 0, 0, M, N, K, 1, 1, 0, 0, 0, None))
         assert_close(host(o), gemm_ref64(A, B, np.zeros((M, N)), 1, 0, 0, 0), rtol=2e-5)
@@ -210,7 +212,7 @@ def test_gemm_tc_large_vs_f64():
 @pytest.mark.parametrize("tA,tB,M,N,K", [(0, 1, 1024, 512, 784), (1, 0, 512, 784, 1024), (0, 0, 1024, 784, 512),     # GAN D layer 1: fwd / dW / dX
                                          (0, 1, 512, 100, 1960), (1, 0, 100, 1960, 512), (0, 0, 512, 1960, 100),     # MNIST linear 1960->100
                                          (0, 0, 300, 132, 2052), (1, 1, 129, 257, 36)])                              # ragged tiles, K tails
-@pytest.mark.parametrize("engine", [t4.GEMM_TCF, t4.GEMM_MMA, t4.GEMM_AUTO])
+@pytest.mark.parametrize("engine", [t4.GEMM_TCF, t4.GEMM_AUTO])
 def test_gemm_tcf_layer_shapes_vs_f64(engine, tA, tB, M, N, K):
     """the single-launch tensor-core engines (in-kernel 3xTF32 split, split-K: tcgen05 `tcf`, warp-level `mma` with its last-CTA
     finish, and whatever AUTO picks) on the linear-layer shapes: FP32-grade vs exact"""
@@ -226,19 +228,77 @@ def test_gemm_tcf_layer_shapes_vs_f64(engine, tA, tB, M, N, K):
         assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-6
 
 
-def test_gemm_mma_counters_survive_ring_wrap():
-    """the warp-MMA engine finishes split-K in the last CTA of each tile, counted on a ring of self-resetting arrival counters
-    (gemm_mma.cu: tile_counters): more calls than the ring holds must keep giving the same answer"""
-    M, N, K = 128, 128, 1024                               # 4 tiles x 8 splits; the ring holds 65536 counters
-    A, B = rnd(M, K), rnd(N, K)
-    dA, dB_, o = dev(A), dev(B), zeros(M, N)
-    ref = gemm_ref64(A, B, np.zeros((M, N)), 1.0, 0.0, 0, 1)
+TL_SHAPES = [(0, 1, 1024, 512, 784), (1, 0, 512, 784, 1024), (0, 0, 1024, 784, 512),       # GAN D layer 1: fwd / dW / dX
+             (0, 1, 512, 100, 1960), (1, 0, 100, 1960, 512), (0, 0, 512, 1960, 100),       # MNIST linear 1960->100
+             (0, 1, 1024, 256, 128), (1, 0, 256, 512, 1024), (0, 0, 1024, 256, 512),       # GAN G layers
+             (0, 0, 300, 132, 2052), (1, 1, 132, 260, 36), (1, 0, 36, 48, 4100), (0, 1, 64, 16, 4096),   # ragged tiles, K tails, thin outputs
+             (1, 1, 256, 128, 3000), (0, 0, 128, 128, 8192)]                                # long K per rank: several accumulator chains
+
+
+@pytest.mark.parametrize("tA,tB,M,N,K", TL_SHAPES)
+def test_gemm_tl_layer_shapes_vs_f64(tA, tB, M, N, K):
+    """the layer GEMM (gemm_tl.cu: TMA-fed raw tiles, MN-major operands native, lo plane derived in shared memory, cluster split-K over
+    distributed shared memory): FP32-grade vs exact for every transposition, alpha/beta, ragged tiles and K tails"""
+    A = rnd(K, M) if tA else rnd(M, K)
+    B = rnd(N, K) if tB else rnd(K, N)
+    O0 = rnd(M, N)
+    for alpha, beta in ((1.0, 0.0), (1.0, 1.0), (0.5, 2.0)):
+        o = dev(O0)
+        ok(lib().t4k_gemm_ex(t4.GEMM_TL, ptr(dev(A)), ptr(dev(B)), ptr(o), alpha, beta, tA, tB, M, N, K, 1, 1, 0, 0, 0, None), "gemm tl")
+        ref = gemm_ref64(A, B, O0, alpha, beta, tA, tB)
+        got = host(o)
+        assert_close(got, ref, rtol=1e-5, what="tl vs f64")
+        assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-6
+    assert_close(got, orc.gemm(A, B, O0, 0.5, 2.0, bool(tA), bool(tB), M, N, K, 1), rtol=1e-4, what="tl vs oracle")
+
+
+@pytest.mark.parametrize("tA,tB,M,N,K", [(0, 1, 512, 100, 1960), (1, 0, 100, 1960, 512), (0, 0, 512, 1960, 100), (1, 1, 132, 260, 36)])
+def test_gemm_tl_hi_plane_and_cluster_sizes(tA, tB, M, N, K):
+    """(i) the raw FP32 plane as the hi operand (the tensor core ignores the 13 low mantissa bits) must give the same BITS as storing the
+    masked hi explicitly; (ii) every cluster size (split-K factor) gives an FP32-grade result, deterministic from call to call"""
+    A = rnd(K, M) if tA else rnd(M, K)
+    B = rnd(N, K) if tB else rnd(K, N)
+    dA, dB_ = dev(A), dev(B)
+    ref = gemm_ref64(A, B, np.zeros((M, N)), 1.0, 0.0, tA, tB)
     L = lib()
-    for i in range(17000):
-        rc = L.t4k_gemm_ex(t4.GEMM_MMA, ptr(dA), ptr(dB_), ptr(o), 1.0, 0.0, 0, 1, M, N, K, 1, 1, 0, 0, 0, None)
-        assert rc == 0
-        if i in (0, 16383, 16384, 16999):
-            assert_close(host(o), ref, rtol=1e-5, what="mma split-K call %d" % i)
+
+    def run():
+        o = zeros(M, N)
+        ok(L.t4k_gemm_ex(t4.GEMM_TL, ptr(dA), ptr(dB_), ptr(o), 1.0, 0.0, tA, tB, M, N, K, 1, 1, 0, 0, 0, None), "gemm tl")
+        return host(o).copy()
+    base = run()
+    assert_exact(run(), base, "deterministic")
+    was = L.t4k_set_gemm_tl(1, 1)
+    try:
+        assert_exact(run(), base, "masked hi == raw plane as hi")
+    finally:
+        L.t4k_set_gemm_tl(1, was)
+    for smax in (1, 2, 4, 8):
+        was = L.t4k_set_gemm_tl(2, smax)
+        try:
+            got = run()
+        finally:
+            L.t4k_set_gemm_tl(2, was)
+        assert_close(got, ref, rtol=1e-5, what="cluster size <= %d" % smax)
+
+
+@pytest.mark.parametrize("N,E0,E1", [(1024, 512, 784), (512, 100, 1960), (1024, 256, 512), (96, 36, 48)])
+def test_linear_bwd_act(N, E0, E1):
+    """_blinear + the _bactivate in front of it, mask multiply in the dX GEMM's epilogue: same tensors as the two calls"""
+    X, W, dY = rnd(N, E1), rnd(E0, E1), rnd(N, E0)
+    F = (rnd(N, E1) > 0).astype(np.float32) * 0.8 + 0.2
+    dW0, dB0 = rnd(E0, E1), rnd(E0)
+    dx, dxp, dw, db = zeros(N, E1), zeros(N, E1), dev(dW0), dev(dB0)
+    ok(lib().t4k_linear_bwd_act(ptr(dev(X)), ptr(dev(W)), ptr(dev(dY)), ptr(dx), ptr(dw), ptr(db), ptr(dev(F)), ptr(dxp), N, E0, E1, 1, 0, None))
+    rdb = dB0.copy(); orc.lib().orc_dlinear_db(orc._p(dY), orc._p(rdb), N, E0)
+    assert_close(host(db), rdb, rtol=1e-4, what="dB")
+    assert_close(host(dw), orc.gemm(dY, X, O=dW0, alpha=1.0, beta=1.0, tA=True), rtol=1e-4, what="dW")
+    assert_close(host(dx), orc.gemm(dY, W), rtol=1e-4, what="dX")
+    assert_exact(host(dxp), orc.tt_op(orc.MUL, host(dx), F), "dX * F")
+    # in place (X and dX share a buffer, as Model::_blinear calls it)
+    xio, dw2, db2 = dev(X), dev(dW0), dev(dB0)
+    ok(lib().t4k_linear_bwd_act(ptr(xio), ptr(dev(W)), ptr(dev(dY)), ptr(xio), ptr(dw2), ptr(db2), ptr(dev(F)), ptr(dxp), N, E0, E1, 1, 0, None))
+    assert_exact(host(xio), host(dx)); assert_exact(host(dw2), host(dw))
 
 
 @pytest.mark.parametrize("tA,tB", [(0, 0), (1, 1)])
