@@ -260,7 +260,10 @@ int t4k_comm_create(int rank, int world, int64_t cap_floats, t4k_comm_t *out, vo
 int t4k_comm_connect(t4k_comm_t c, const void *handles /* world x T4K_COMM_HANDLE_BYTES, rank order */);
 int t4k_comm_connect_local(t4k_comm_t c, t4k_comm_t *all /* world communicators of THIS process, rank order */);
 int t4k_comm_destroy(t4k_comm_t c);
-int t4k_comm_status(t4k_comm_t c);      /* 0 healthy; k>0: a wait for rank k-1 timed out (~2 s without progress) */
+int t4k_comm_status(t4k_comm_t c);      /* 0 healthy; k>0: a wait for rank k-1 timed out (T4K_COMM_TIMEOUT_S seconds, default 60, without progress);
+                                         * synchronises the device.  The error is STICKY: the chunk that timed out is not finished (no optimizer
+                                         * step on a half-summed gradient) and every later exchange on this communicator is a no-op */
+int t4k_comm_poll(t4k_comm_t c);        /* the same word read from mapped host memory, no synchronisation (cheap enough for every step) */
 int64_t t4k_comm_capacity(t4k_comm_t c);
 int t4k_shard_info(int64_t n, int world, int rank, int64_t *lo, int64_t *hi);   /* batch shard of a rank: samples [lo, hi) (no device needed) */
 /* buf[i] = sum over ranks of buf[i], in place, n <= capacity */

@@ -541,7 +541,7 @@ static int cpr2_fwd_launch(const float *I, const float *F, const float *B, float
     p.actF = actF; p.flatO = flatO; p.H = H1; p.W = W1; p.C1 = C1; p.C0 = C0;
     const int threads = win_threads((H0 / 2) * (W0 / 2));
     const bool al = aligned16(convO) && aligned16(poolO) && aligned16(actO) && aligned16(actF) && (!flatO || aligned16(flatO));
-    #define CPR2F(K_, CP_, CT_, C1_, FD_) { static bool attr = false; if (!attr && smem > 48 * 1024) { cudaFuncSetAttribute(k_cpr2_fwd<K_, CP_, CT_, C1_, FD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; } \
+    #define CPR2F(K_, CP_, CT_, C1_, FD_) { static DevFlag attr; if (smem > 48 * 1024 && dev_first(attr)) { cudaFuncSetAttribute(k_cpr2_fwd<K_, CP_, CT_, C1_, FD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); } \
                                   launch_std(k_cpr2_fwd<K_, CP_, CT_, C1_, FD_>, dim3(N), dim3(threads), smem, st, p); }
     if (feed) {
         // the feed variants exist for the exact single-input-channel 3x3 shapes (the MNIST-style first block)
@@ -611,7 +611,7 @@ extern "C" int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float 
     p.H = H1; p.W = W1; p.C1 = 1; p.C0 = C0; p.train = train;
     if (train) { p.part = (float*)workspace((size_t)N * (nF + C0) * sizeof(float), 4); if (!p.part) return T4K_ENOMEM; }
     const bool ex = (C0 == CM) && aligned16(convO);
-    #define CPR2B(CM_, EX_) { static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_cpr2_bwd<CM_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cudaFuncSetAttribute(k_cpr2_bwd<CM_, EX_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); attr = true; } \
+    #define CPR2B(CM_, EX_) { static DevFlag attr; if (dev_first(attr)) { cudaFuncSetAttribute(k_cpr2_bwd<CM_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cudaFuncSetAttribute(k_cpr2_bwd<CM_, EX_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); } \
                               launch_std(k_cpr2_bwd<CM_, EX_>, dim3(N), dim3(threads), smem, STRM(s), p); }
     if (CM == 10) { if (ex) CPR2B(10, true) else CPR2B(10, false) } else { if (ex) CPR2B(16, true) else CPR2B(16, false) }
     int rc = check_launch(); if (rc || !train) return rc;

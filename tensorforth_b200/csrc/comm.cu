@@ -19,8 +19,11 @@
 // Epoch counters live in device memory, so the kernel is CUDA-graph capturable (Model::step_graph captures the whole
 // data-parallel train step: forward + loss + backprop + exchange/optimizer, one graph launch per step).
 // One process per GPU: the exchange blocks are cudaMalloc'ed and exported with cudaIpc handles, which the host side
-// (tensorforth_b200/dp.py, torch.distributed) gathers.  A wait that sees no progress for ~2 s raises the communicator's
-// error word instead of hanging the GPU.
+// (tensorforth_b200/dp.py, torch.distributed) gathers.  A wait that sees no progress for T4K_COMM_TIMEOUT_S seconds (default 60: a
+// checkpoint save, an evaluation pass or a stalled loader on one rank are legitimate skews) does NOT hang the GPU and does NOT
+// apply a half-summed gradient: the chunk's finish is skipped (G / M / V / DG untouched, epoch not advanced) and a STICKY error word
+// is raised, in device memory — every later exchange kernel of this communicator returns at once without touching the model —
+// and in mapped host memory, which t4k_comm_poll reads without synchronising (Model::_gradient checks it on every optimizer call).
 #include "common.cuh"
 #include "optim.cuh"
 #include <cstring>
@@ -31,7 +34,7 @@
 #define COMM_MAXB   512          // chunks (= blocks) per call
 #define COMM_NSCAL  64           // extra scalars riding in the same exchange (loss sum, hit count …)
 #define COMM_FLAGB  (COMM_MAXW * COMM_MAXB * 4)
-#define COMM_SPIN_LIMIT (4000000000ll)       // clock64 ticks (~2 s)
+#define COMM_TIMEOUT_S_DEFAULT 60
 
 struct t4k_comm {
     int rank, world, dev;
@@ -40,7 +43,9 @@ struct t4k_comm {
     char *base;                  // this rank's exchange block
     char *peer[COMM_MAXW];       // every rank's block as mapped here (peer[rank] == base)
     bool ipc[COMM_MAXW];
-    uint32_t *epoch;             // [COMM_MAXB] per-chunk epoch counters + [COMM_MAXB] error word (local)
+    uint32_t *epoch;             // [COMM_MAXB] per-chunk epoch counters + [COMM_MAXB] sticky error word (local device memory)
+    uint32_t *err_host, *err_dev;    // the same error word in mapped pinned host memory (host pointer / device alias): polled without a sync
+    long long spin_limit;        // clock64 ticks a wait may go without progress
     size_t bytes;
 };
 
@@ -49,6 +54,8 @@ namespace t4k {
 struct CommDev {
     char *peer[COMM_MAXW];
     uint32_t *epoch;
+    uint32_t *err_host;          // device alias of the mapped host error word
+    long long spin_limit;
     int64_t cap;
     int rank, world, ch4;
 };
@@ -70,11 +77,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) { uint32_t
 // this launch onto a side stream); the MODE 1/2/3 launch that follows pushes only the chunks below `pushed_from`.
 template<int MODE, bool VEC>
 __global__ void __launch_bounds__(T4K_THREADS) k_dp_exchange(const __grid_constant__ CommDev c, float *buf, int64_t n, float *scal, int nscal, DpOpt o) {
-    __shared__ uint32_t s_ep;
+    __shared__ uint32_t s_ep, s_err;
     pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     const int b = blockIdx.x + o.b0, tid = threadIdx.x;
-    if (tid == 0) s_ep = c.epoch[b] + 1;
+    if (tid == 0) { s_ep = c.epoch[b] + 1; s_err = c.epoch[COMM_MAXB]; }
     __syncthreads();
+    if (s_err) return;                          // sticky: an earlier exchange timed out, the replicas are no longer in step — touch nothing
     const uint32_t ep = s_ep;
     const int par = (int)(ep & 1u);
     const int64_t lo = (int64_t)b * c.ch4 * 4;
@@ -114,9 +122,15 @@ __global__ void __launch_bounds__(T4K_THREADS) k_dp_exchange(const __grid_consta
         const uint32_t *f = flag_of(c, c.rank, tid, b);
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(f) - ep) < 0)
-            if (clock64() - t0 > COMM_SPIN_LIMIT) { c.epoch[COMM_MAXB] = 1u + (uint32_t)tid; break; }
+            if (clock64() - t0 > c.spin_limit) {
+                atomicCAS(c.epoch + COMM_MAXB, 0u, 1u + (uint32_t)tid);           // first failure wins, never cleared
+                if (c.err_host) { *reinterpret_cast<volatile uint32_t*>(c.err_host) = 1u + (uint32_t)tid; __threadfence_system(); }
+                s_err = 1u + (uint32_t)tid;
+                break;
+            }
     }
     __syncthreads();
+    if (s_err) return;                          // no finish on incomplete data: G / M / V / DG stay as they are, the epoch is not advanced
     // ---- finish: rank-ordered sum of the local slots (+ optimizer)
     const float *mine = slot_of(c, c.rank, par, 0);
     const int64_t sstride = c.cap + COMM_NSCAL;
@@ -164,7 +178,7 @@ __global__ void __launch_bounds__(T4K_THREADS) k_dp_exchange(const __grid_consta
 static CommDev devview(const t4k_comm *c) {
     CommDev d;
     for (int i = 0; i < COMM_MAXW; i++) d.peer[i] = c->peer[i];
-    d.epoch = c->epoch; d.cap = c->cap; d.rank = c->rank; d.world = c->world; d.ch4 = c->ch4;
+    d.epoch = c->epoch; d.err_host = c->err_dev; d.spin_limit = c->spin_limit; d.cap = c->cap; d.rank = c->rank; d.world = c->world; d.ch4 = c->ch4;
     return d;
 }
 static bool ready(const t4k_comm *c) {
@@ -202,6 +216,16 @@ int t4k_comm_create(int rank, int world, int64_t cap_floats, t4k_comm_t *out, vo
     if (e != cudaSuccess) { cudaGetLastError(); cudaFree(c->base); delete c; return T4K_ENOMEM; }
     cudaMemset(c->base, 0, c->bytes);
     cudaMemset(c->epoch, 0, (COMM_MAXB + 8) * 4);
+    if (cudaHostAlloc((void**)&c->err_host, 64, cudaHostAllocMapped) == cudaSuccess && c->err_host) {
+        *c->err_host = 0;
+        if (cudaHostGetDevicePointer((void**)&c->err_dev, c->err_host, 0) != cudaSuccess) { cudaGetLastError(); c->err_dev = nullptr; }
+    } else { cudaGetLastError(); c->err_host = c->err_dev = nullptr; }
+    {
+        int khz = 0; double secs = COMM_TIMEOUT_S_DEFAULT;
+        if (const char *e = getenv("T4K_COMM_TIMEOUT_S")) { const double v = atof(e); if (v > 0) secs = v; }
+        if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->dev) != cudaSuccess || khz <= 0) { cudaGetLastError(); khz = 2000000; }
+        c->spin_limit = (long long)(secs * 1e3 * (double)khz);
+    }
     cudaDeviceSynchronize();
     c->peer[rank] = c->base;
     if (handle64) {
@@ -246,6 +270,7 @@ int t4k_comm_destroy(t4k_comm_t c) {
     for (int r = 0; r < c->world; r++) if (c->ipc[r] && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
     if (c->base) cudaFree(c->base);
     if (c->epoch) cudaFree(c->epoch);
+    if (c->err_host) cudaFreeHost(c->err_host);
     cudaGetLastError();
     delete c;
     return 0;
@@ -258,6 +283,12 @@ int t4k_comm_status(t4k_comm_t c) {
     cudaError_t e = cudaMemcpy(&w, c->epoch + COMM_MAXB, 4, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return (int)e;
     return (int)w;
+}
+
+/* the sticky error word without synchronising anything (mapped host memory written by the kernel that timed out) */
+int t4k_comm_poll(t4k_comm_t c) {
+    if (!c) return T4K_EINVAL;
+    return c->err_host ? (int)*reinterpret_cast<volatile uint32_t*>(c->err_host) : 0;
 }
 
 int64_t t4k_comm_capacity(t4k_comm_t c) { return c ? c->cap : 0; }

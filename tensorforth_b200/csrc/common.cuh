@@ -13,7 +13,13 @@
 namespace t4k {
 
 extern long g_launches;                       // counted kernel launches (t4k_launch_count)
-int  sm_count();                              // cached cudaDevAttrMultiProcessorCount
+int  sm_count();                              // cudaDevAttrMultiProcessorCount of the CURRENT device (cached per device)
+int  cur_device();                            // cudaGetDevice, -1 on error
+// function attributes (max dynamic shared memory, non-portable cluster sizes) are PER DEVICE: "set once" flags are kept per device
+struct DevFlag { bool f[16]; };
+static inline bool dev_first(DevFlag &x) { const int d = cur_device(); if (d < 0 || d >= 16) return true; if (x.f[d]) return false; x.f[d] = true; return true; }
+struct DevSize { size_t v[16]; };
+static inline bool dev_grow(DevSize &x, size_t s) { const int d = cur_device(); if (d < 0 || d >= 16) return true; if (s <= x.v[d]) return false; x.v[d] = s; return true; }
 int  check_launch();                          // cudaGetLastError() → rc, ++g_launches
 void *workspace(size_t bytes, int slot);      // library-owned per-device scratch (grown on demand)
 float *reduce_slot(cudaStream_t st);          // 4 KiB partials + counter, ring of slots, zeroed counter

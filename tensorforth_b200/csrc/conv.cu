@@ -579,8 +579,8 @@ extern "C" int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, f
             const int ctas = N * strips;
             float *part = (float*)workspace((size_t)ctas * (nF + C0) * sizeof(float), 4);
             if (!part) return T4K_ENOMEM;
-            static bool attr[6] = {false, false, false, false, false, false};
-            #define WG_LAUNCH(K_) { if (!attr[K_] && smem_small > 48 * 1024) { cudaFuncSetAttribute(k_conv_wgrad_small<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr[K_] = true; } \
+            static DevFlag attr[6];
+            #define WG_LAUNCH(K_) { if (smem_small > 48 * 1024 && dev_first(attr[K_])) { cudaFuncSetAttribute(k_conv_wgrad_small<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); } \
                                     k_conv_wgrad_small<K_><<<ctas, T4K_THREADS, smem_small, st>>>(p, part, strips); }
             switch (KS) { case 1: WG_LAUNCH(1) break; case 3: WG_LAUNCH(3) break; case 4: WG_LAUNCH(4) break; default: WG_LAUNCH(5) break; }
             rc = check_launch(); if (rc) return rc;
@@ -652,8 +652,8 @@ int cpr_v1_fwd(const float *I, const float *F, const float *B, float *convO, flo
     if (!cpr_ok(H1, W1, C1, H0, W0, C0, KS, S, P, &smem)) return T4K_ENOSUP;
     CprP p{}; p.I = I; p.F = F; p.B = B; p.convO = convO; p.poolO = poolO; p.actO = actO; p.actF = actF; p.flatO = flatO;
     p.H1 = H1; p.W1 = W1; p.C1 = C1; p.H0 = H0; p.W0 = W0; p.C0 = C0; p.S = S; p.P = P;
-    static bool attr[6] = {false};
-    #define CPRF(K_) { if (!attr[K_] && smem > 48 * 1024) { cudaFuncSetAttribute(k_cpr_fwd<K_, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr[K_] = true; } \
+    static DevFlag attr[6];
+    #define CPRF(K_) { if (smem > 48 * 1024 && dev_first(attr[K_])) { cudaFuncSetAttribute(k_cpr_fwd<K_, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); } \
                        k_cpr_fwd<K_, 16><<<N, T4K_THREADS, smem, s>>>(p); }
     switch (KS) { case 1: CPRF(1) break; case 3: CPRF(3) break; case 4: CPRF(4) break; default: CPRF(5) break; }
     return check_launch();
@@ -668,8 +668,8 @@ int cpr_v1_bwd(const float *dY, float *actO, const float *actF, float *poolO, fl
     CprP p{}; p.F = F; p.convO = convO; p.poolO = poolO; p.actO = actO; p.actF = (float*)actF; p.dY = dY; p.Iio = Iio; p.dXbuf = dXbuf;
     p.H1 = H1; p.W1 = W1; p.C1 = C1; p.H0 = H0; p.W0 = W0; p.C0 = C0; p.S = S; p.P = P; p.train = train;
     if (train) { p.part = (float*)workspace((size_t)N * (nF + C0) * sizeof(float), 4); if (!p.part) return T4K_ENOMEM; }
-    static bool attr[6] = {false};
-    #define CPRB(K_) { if (!attr[K_] && smem > 40 * 1024) { cudaFuncSetAttribute(k_cpr_bwd<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr[K_] = true; } \
+    static DevFlag attr[6];
+    #define CPRB(K_) { if (smem > 40 * 1024 && dev_first(attr[K_])) { cudaFuncSetAttribute(k_cpr_bwd<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); } \
                        k_cpr_bwd<K_><<<N, T4K_THREADS, smem, s>>>(p); }
     switch (KS) { case 1: CPRB(1) break; case 3: CPRB(3) break; case 4: CPRB(4) break; default: CPRB(5) break; }
     int rc = check_launch(); if (rc || !train) return rc;

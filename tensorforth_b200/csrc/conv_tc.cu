@@ -598,8 +598,8 @@ int conv_wgrad_tc(const float *I, const float *dO, float *dF, float *dB, int N, 
     int rc = tmap_rows(&imap, I, p.Mg, C1, p.SR); if (rc) return rc;
     rc = tmap_rows(&omap, dO, p.Mg, C0, WG_KB); if (rc) return rc;
     const size_t smem = 2 * (size_t)p.stage_bytes + 1024 + 256;
-    static size_t attr = 0;
-    if (smem > attr) { cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return (int)e; attr = smem; }
+    static DevSize attr;
+    if (dev_grow(attr, smem)) { cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return (int)e; }
     k_conv_wgrad_tc<<<grid, CT_THREADS, smem, st>>>(p, imap, omap);
     rc = check_launch(); if (rc) return rc;
     const int tot = (int)nF + C0;
@@ -644,12 +644,12 @@ int conv_tc(const float *X, const float *F, const float *bias, float *Y, int N, 
     { int rc = tmap_rows(&xmap, X, p.Mg, CI, 128); if (rc) return rc; }
     const size_t smem = (size_t)nstage * stage + 1024 + 256;
     int grid = sm_count(); if (grid > p.ntiles) grid = p.ntiles;
-    static size_t attr32 = 0, attr64 = 0;
+    static DevSize attr32, attr64;
     if (CK == 64) {
-        if (smem > attr64) { cudaError_t e = cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return (int)e; attr64 = smem; }
+        if (dev_grow(attr64, smem)) { cudaError_t e = cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return (int)e; }
         k_conv_tc<64><<<grid, CT_THREADS, smem, st>>>(p, xmap);
     } else {
-        if (smem > attr32) { cudaError_t e = cudaFuncSetAttribute(k_conv_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return (int)e; attr32 = smem; }
+        if (dev_grow(attr32, smem)) { cudaError_t e = cudaFuncSetAttribute(k_conv_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return (int)e; }
         k_conv_tc<32><<<grid, CT_THREADS, smem, st>>>(p, xmap);
     }
     return check_launch();

@@ -366,11 +366,10 @@ __global__ void __launch_bounds__(T4K_THREADS) k_tail_fin(const float *__restric
 
 template<int BN, int STAGES, bool BF> static int launch_tc(const TcP &p, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * ((size_t)TILE_FLTS * 4 + (size_t)(BN / TBM) * TILE_FLTS * 4) + 1024 + 256;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DevFlag attr_done;
+    if (dev_first(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, STAGES, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr_done = true;
     }
     k_gemm_tc<BN, STAGES, BF><<<grid, 320, smem, st>>>(p);
     return check_launch();

@@ -388,11 +388,10 @@ int gemm_tcf(const float *A, const float *B, float *O, float alpha, float beta, 
            KT, kt_per, splits, nullptr};
     constexpr size_t smem = (size_t)F_STAGES * F_STAGE_B + 1024 + 256;
     if (cluster) {
-        static bool cattr = false;
-        if (!cattr) {
+        static DevFlag cattr;
+        if (dev_first(cattr)) {
             cudaError_t e = cudaFuncSetAttribute(k_gemm_tcf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            cattr = true;
         }
         p.splits = 1;                                                  // the kernel writes O itself (its split count is gridDim.z)
         const bool fused_epi = epi && epi->bias && beta == 0.0f && (epi->layer == T4K_L_NONE || (epi->A && epi->F));
@@ -413,11 +412,10 @@ int gemm_tcf(const float *A, const float *B, float *O, float alpha, float beta, 
         p.part = (float*)workspace((size_t)splits * M * N * sizeof(float), 7);
         if (!p.part) return T4K_ENOMEM;
     }
-    static bool attr = false;
-    if (!attr) {
+    static DevFlag attr;
+    if (dev_first(attr)) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm_tcf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr = true;
     }
     launch_std(k_gemm_tcf<false>, dim3(ntiles, mtiles, splits), dim3(F_THREADS), smem, st, TcfArgs<false>{p});
     int rc = check_launch();

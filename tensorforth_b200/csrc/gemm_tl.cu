@@ -9,8 +9,9 @@
 //   * operands arrive by TMA (cp.async.bulk.tensor.2d of the RAW FP32 tiles, SWIZZLE_128B, out-of-range rows/cols/k zero filled by
 //     the TMA unit): one elected thread keeps a whole ring (3 x 32 KiB) in flight, nothing is staged through registers;
 //   * ANY transposition is native: an operand that is contiguous along M/N is loaded as [k][32 x m] boxes and handed to the tensor
-//     core as an MN-major UMMA operand (instruction-descriptor bits 15/16, LBO = 4 KiB between 32-wide m blocks, SBO = 1 KiB
-//     between 8-row k groups) — dW (both operands MN-major) and dX (B MN-major) no longer pay scattered 4-byte shared stores;
+//     core as an MN-major UMMA operand (instruction-descriptor bits 15/16; 32-bit MN-major operands use the SWIZZLE_128B_BASE32B
+//     layout = TMA's 128B_ATOM_32B swizzle: LBO = 4 KiB between 32-wide m blocks, SBO = 512 B between 4-row k groups) — dW (both
+//     operands MN-major) and dX (B MN-major) no longer pay scattered 4-byte shared stores;
 //   * the raw FP32 plane IS the hi operand: kind::tf32 reads the upper 19 bits of each word (the 13 low mantissa bits are ignored:
 //     hi = truncate(a)); eight converter warps only derive the lo plane, lo = tf32(a - hi), elementwise on the swizzled image
 //     (same offset in a second plane, whatever the layout); product = lo*hi + hi*lo + hi*hi with FP32 accumulation in TMEM;
@@ -48,6 +49,7 @@ struct TlP {
     int KT, kt_per;              // k-blocks of 32: total, per cluster rank
     int a_mn, b_mn;              // operand is contiguous along M / N in memory (tA / !tB)
     int mask_hi;                 // debug: store the masked hi back over the raw plane (does not rely on the MMA ignoring the low bits)
+    uint32_t mn_type, mn_lbo, mn_sbo, mn_kstep;      // MN-major operand descriptor: layout type, LBO / SBO / start-address step per 8 k (bytes)
     int mode;
     const float *bias; float *actA, *actF; int layer; float act_alpha;          // mode 1, 2
     const float *W2, *B2; float *Y2, *P, *P2; int E2;                          // mode 2
@@ -72,13 +74,15 @@ __device__ __forceinline__ float4 tl_ld_dsmem4(uint32_t local_saddr, uint32_t ra
 // the epilogue warps' per-row float4 stores (lanes = rows) and the reduction's per-row reads (lanes = chunks) are both conflict-free
 __device__ __forceinline__ int tl_park_off(int row, int c4) { return row * L_BN + ((c4 ^ (row & 31)) << 2); }
 
-// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor): version 1, SWIZZLE_128B
-//   K-major : rows of 128 B (32 tf32 along k), 8-row groups 1024 B apart (SBO); a k-step of 8 advances the start address by 32 B
-//   MN-major: rows of 128 B (32 tf32 along m/n) at one k, 8 k-rows = one 1024 B atom (SBO = 1 KiB between k groups),
-//             32-wide m/n blocks LBO = 4 KiB apart (one TMA box of 32 k-rows); a k-step of 8 advances the start address by 1024 B
-__device__ __forceinline__ uint64_t tl_desc(uint32_t saddr, bool mn) {
-    const uint64_t lbo = mn ? (4096u >> 4) : 1u, sbo = 1024u >> 4;
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), version 1
+//   K-major : SWIZZLE_128B (type 2: 16-byte chunks XOR row & 7); rows of 128 B (32 tf32 along k), 8-row groups 1024 B apart (SBO); a k-step
+//             of 8 advances the start address by 32 B
+//   MN-major: 32-bit operands have ONE legal layout, SWIZZLE_128B_BASE32B (type 1: 32-byte chunks XOR row & 3 — the TMA mode
+//             CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B (32 tf32 along m/n) at one k, 4 k-rows = one 512 B atom (SBO = 512 B
+//             between k groups), 32-wide m/n blocks LBO = 4 KiB apart (one TMA box of 32 k-rows); a k-step of 8 = two atoms = 1024 B
+__device__ __forceinline__ uint64_t tl_desc(uint32_t saddr, bool mn, const TlP &p) {
+    const uint64_t lbo = mn ? (p.mn_lbo >> 4) : 1u, sbo = mn ? (p.mn_sbo >> 4) : (1024u >> 4), type = mn ? p.mn_type : 2u;
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (type << 61);
 }
 
 template<int L> __device__ __forceinline__ void tl_act4(const float (&y)[4], float alpha, float (&a)[4], float (&f)[4]) {
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
         int nv = p.N - nt * L_BN; if (nv > L_BN) nv = L_BN;
         const int un = (nv + 15) & ~15;                                               // UMMA N: the valid columns of this tile, rounded to 16
         const uint32_t idesc = idesc_tf32(L_BM, un) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) | ((uint32_t)(p.b_mn ? 1 : 0) << 16);
-        const uint64_t ka = p.a_mn ? (1024u >> 4) : (32u >> 4), kb = p.b_mn ? (1024u >> 4) : (32u >> 4);      // start-address step per 8 k
+        const uint64_t ka = p.a_mn ? (p.mn_kstep >> 4) : (32u >> 4), kb = p.b_mn ? (p.mn_kstep >> 4) : (32u >> 4);      // start-address step per 8 k
         for (int i = 0; i < nkb; i++) {
             const int s = i % L_STAGES, it = i / L_STAGES;
             const int c = i / L_DRAIN_KB, ib = i % L_DRAIN_KB, b = c & 1;
@@ -184,8 +188,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
             if (elect_one()) {
                 const uint32_t acc = tmem_base + (uint32_t)(b * L_BN);
                 const uint32_t sa = smem_u32(smem + (size_t)s * L_STAGE_B), sb = sa + L_OP_B;
-                const uint64_t a_hi = tl_desc(sa, p.a_mn), a_lo = tl_desc(sa + L_PLANE_B, p.a_mn);
-                const uint64_t b_hi = tl_desc(sb, p.b_mn), b_lo = tl_desc(sb + L_PLANE_B, p.b_mn);
+                const uint64_t a_hi = tl_desc(sa, p.a_mn, p), a_lo = tl_desc(sa + L_PLANE_B, p.a_mn, p);
+                const uint64_t b_hi = tl_desc(sb, p.b_mn, p), b_lo = tl_desc(sb + L_PLANE_B, p.b_mn, p);
                 #pragma unroll
                 for (int k = 0; k < L_BK / L_UK; k++) {
                     tc_mma_tf32(acc, a_lo + k * ka, b_hi + k * kb, idesc, (ib | k) ? 1u : 0u);
@@ -380,22 +384,23 @@ static PFN_tl_encode tl_encoder() {
     }
     return enc;
 }
-// 2-D FP32 matrix [outer][inner] (row pitch = inner floats), box = box_outer x 32 floats, 128-byte swizzle, zero fill out of bounds
-static int tl_map(CUtensorMap *m, const float *X, int64_t inner, int64_t outer, int box_outer) {
+// 2-D FP32 matrix [outer][inner] (row pitch = inner floats), box = box_outer x 32 floats, 128-byte swizzle (16-byte chunks, or 32-byte
+// chunks for the MN-major operands), zero fill out of bounds
+static int tl_map(CUtensorMap *m, const float *X, int64_t inner, int64_t outer, int box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     PFN_tl_encode enc = tl_encoder();
     if (!enc) return T4K_ENOSUP;
     const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
     const cuuint64_t gstr[1] = {(cuuint64_t)inner * 4};
     const cuuint32_t box[2] = {32, (cuuint32_t)box_outer}, estr[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)X, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : T4K_EINVAL;
+               swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : T4K_EINVAL;
 }
 
 constexpr size_t L_SMEM = (size_t)L_STAGES * L_STAGE_B + 256 + (size_t)L_W2_FLTS * 4 + 1024;
 #define TL_MAX_DEV 16
 static int g_tl_maxcl[TL_MAX_DEV][5];                   // [device][log2 S]: co-resident clusters of size S (0: not queried yet, -1: unavailable)
 
-static int tl_device() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= TL_MAX_DEV) { cudaGetLastError(); return -1; } return d; }
+static int tl_device() { const int d = cur_device(); return (d < 0 || d >= TL_MAX_DEV) ? -1 : d; }
 static int tl_prepare(int dev) {
     static bool attr[TL_MAX_DEV];
     if (attr[dev]) return 0;
@@ -418,10 +423,14 @@ static int tl_prepare(int dev) {
     return 0;
 }
 static int tl_env(const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; }
-// knobs (t4k_set_gemm_tl): 0 engine on/off for AUTO, 1 mask_hi (debug), 2 largest cluster size
-static int g_tl_knob[3] = {-1, -1, -1};
+// knobs (t4k_set_gemm_tl): 0 engine on/off for AUTO, 1 mask_hi (debug), 2 largest cluster size; 3-7 (bring-up probes only): MN-major
+// descriptor layout type, TMA swizzle mode, LBO, SBO, start-address step per 8 k
+#define TL_NKNOB 8
+static int g_tl_knob[TL_NKNOB] = {-1, -1, -1, -1, -1, -1, -1, -1};
 static int tl_knob(int k) {
-    if (g_tl_knob[k] < 0) g_tl_knob[k] = k == 0 ? tl_env("T4K_GEMM_TL", 1) : k == 1 ? tl_env("T4K_TL_MASKHI", 0) : tl_env("T4K_TL_SMAX", 16);
+    static const char *name[TL_NKNOB] = {"T4K_GEMM_TL", "T4K_TL_MASKHI", "T4K_TL_SMAX", "T4K_TL_MN_TYPE", "T4K_TL_MN_SWZ", "T4K_TL_MN_LBO", "T4K_TL_MN_SBO", "T4K_TL_MN_KSTEP"};
+    static const int dflt[TL_NKNOB] = {1, 0, 16, 1, (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 4096, 512, 1024};
+    if (g_tl_knob[k] < 0) g_tl_knob[k] = tl_env(name[k], dflt[k]);
     return g_tl_knob[k];
 }
 
@@ -456,15 +465,17 @@ int gemm_tl(const float *A, const float *B, float *O, float alpha, float beta, i
     TlP p{};
     p.O = O; p.alpha = alpha; p.beta = beta; p.M = M; p.N = N; p.K = K; p.KT = KT; p.kt_per = kt_per;
     p.a_mn = tA ? 1 : 0; p.b_mn = tB ? 0 : 1; p.mask_hi = mask_hi; p.mode = 0;
+    p.mn_type = (uint32_t)tl_knob(3); p.mn_lbo = (uint32_t)tl_knob(5); p.mn_sbo = (uint32_t)tl_knob(6); p.mn_kstep = (uint32_t)tl_knob(7);
+    const CUtensorMapSwizzle mn_swz = (CUtensorMapSwizzle)tl_knob(4);
     if (epi) {
         p.mode = epi->mode; p.bias = epi->bias; p.actA = epi->actA; p.actF = epi->actF; p.layer = epi->layer; p.act_alpha = epi->act_alpha;
         p.W2 = epi->W2; p.B2 = epi->B2; p.Y2 = epi->Y2; p.P = epi->P; p.P2 = epi->P2; p.E2 = epi->E2; p.F = epi->F; p.O2 = epi->O2;
     }
     CUtensorMap amap, bmap;
     // op(A)(m,k): A stored [M][K] (K-major: box 128 rows x 32 k) or [K][M] when tA (M-major: box 32 k-rows x 32 m)
-    rc = tA ? tl_map(&amap, A, M, K, 32) : tl_map(&amap, A, K, M, 128); if (rc) return rc;
+    rc = tA ? tl_map(&amap, A, M, K, 32, mn_swz) : tl_map(&amap, A, K, M, 128); if (rc) return rc;
     // op(B)(k,n): B stored [N][K] when tB (K-major) or [K][N] (N-major)
-    rc = tB ? tl_map(&bmap, B, K, N, 128) : tl_map(&bmap, B, N, K, 32); if (rc) return rc;
+    rc = tB ? tl_map(&bmap, B, K, N, 128) : tl_map(&bmap, B, N, K, 32, mn_swz); if (rc) return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ntiles, mtiles, S); cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = L_SMEM; cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -479,7 +490,7 @@ int gemm_tl(const float *A, const float *B, float *O, float alpha, float beta, i
 } // namespace t4k
 
 extern "C" int t4k_set_gemm_tl(int what, int value) {
-    if (what < 0 || what > 2) return T4K_EINVAL;
+    if (what < 0 || what >= TL_NKNOB) return T4K_EINVAL;
     const int was = t4k::tl_knob(what);
     t4k::g_tl_knob[what] = value;
     return was;

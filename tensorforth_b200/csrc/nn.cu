@@ -444,8 +444,8 @@ extern "C" int t4k_mlp_head_bwd(float *P, const float *T, float *Ylin, float *X2
     const size_t smem = ((size_t)E0 * 128 + ((nE + 3) & ~3) + (size_t)nwarps * nE) * sizeof(float);
     if (smem > 96 * 1024) return T4K_ENOSUP;
     HeadB p{P, T, Ylin, X2, F1, Y1, W, dW, dB, dB1, N, E0, E1, train};
-    #define HEADB(KM_) { static bool attr = false; if (!attr) { cudaFuncSetAttribute(k_head_bwd<KM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
-                                                                 cudaFuncSetAttribute(k_head_bwd<KM_>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); attr = true; } \
+    #define HEADB(KM_) { static DevFlag attr; if (dev_first(attr)) { cudaFuncSetAttribute(k_head_bwd<KM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
+                                                                 cudaFuncSetAttribute(k_head_bwd<KM_>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); } \
                          launch_pdl(k_head_bwd<KM_>, dim3(HB_CTAS), dim3(T4K_THREADS), smem, STRM(s), p); }
     if (E0 <= 8) HEADB(8) else if (E0 <= 16) HEADB(16) else HEADB(32)
     return check_launch();

@@ -1,6 +1,7 @@
 // runtime.cu — library state: device attributes, workspace, launch accounting, error strings
 #include "common.cuh"
 #include <mutex>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 
@@ -9,18 +10,21 @@ namespace t4k {
 long g_launches = 0;
 int  g_pdl = []{ const char *e = getenv("T4K_PDL"); return (e && e[0] == '1') ? 1 : 0; }();   // opt-in: no net gain measured on the MNIST step (common.cuh)
 
+int cur_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return dev;
+}
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
-            cudaGetLastError();
-            n = 0;
-            return T4K_SMS;
-        }
+    static int n[16];
+    const int dev = cur_device();
+    if (dev < 0 || dev >= 16) return T4K_SMS;
+    if (n[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); return T4K_SMS; }
+        n[dev] = v;
     }
-    return n;
+    return n[dev];
 }
 
 int check_launch() {
@@ -31,14 +35,18 @@ int check_launch() {
 
 // Library-owned scratch, one growing buffer per (device, slot).  Ownership rule of the boundary
 // (SURVEY.md §8b): user-visible tensors belong to the caller's arena, workspace lives here.
-// Regrowth frees the old block with cudaFree (implicit device sync) — only happens when a
-// larger problem than ever before arrives.
+// Regrowth RETIRES the old block instead of freeing it: its address may be baked into cached CUDA graphs (Model::step_graph,
+// th.Graph) that a later, larger call must not invalidate — those graphs keep replaying on the block they were captured with (it is
+// large enough for them).  Growth is geometric, so the retired blocks of a slot add up to less than 4x its final size; they are
+// released at process exit.  A regrowth attempted INSIDE a stream capture fails (cudaMalloc is not capturable): the call returns
+// T4K_ENOMEM, the capture is abandoned by the caller (Model::_step_graph falls back to the eager step, which sizes the workspace).
 #define MAX_DEV  16
 #define MAX_SLOT 16          // 8 slots x 2 banks (bank 1: work forked onto a side stream, see t4k_set_workspace_bank)
 static int g_ws_bank = 0;
 static void  *g_ws[MAX_DEV][MAX_SLOT];
 static size_t g_ws_sz[MAX_DEV][MAX_SLOT];
 static std::mutex g_mu;
+static std::vector<void*> g_retired;                  // outgrown blocks: possibly referenced by cached graphs, never freed while the process runs
 
 void *workspace(size_t bytes, int slot) {
     int dev = 0;
@@ -46,11 +54,11 @@ void *workspace(size_t bytes, int slot) {
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= MAX_DEV || slot >= MAX_SLOT) return nullptr;
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_ws_sz[dev][slot] < bytes) {
-        if (g_ws[dev][slot]) cudaFree(g_ws[dev][slot]);
         size_t want = bytes + (bytes >> 2);
         want = (want + 255) & ~(size_t)255;
         void *p = nullptr;
-        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); g_ws[dev][slot] = nullptr; g_ws_sz[dev][slot] = 0; return nullptr; }
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }      // the old block (if any) stays valid for its users
+        if (g_ws[dev][slot]) g_retired.push_back(g_ws[dev][slot]);
         g_ws[dev][slot] = p; g_ws_sz[dev][slot] = want;
     }
     return g_ws[dev][slot];
