@@ -129,6 +129,11 @@ int t4k_gemm_ex(int engine, const float *A, const float *B, float *O, float alph
  * explicitly instead of relying on kind::tf32 ignoring the 13 low mantissa bits (default 0), 2 = largest cluster size / split-K factor
  * (default 16).  Returns the previous value. */
 int t4k_set_gemm_tl(int what, int value);
+/* bring-up aid: when given a device buffer of 16 int64, CTA (0,0,0) of every following layer-GEMM launch stamps clock64() at its phases
+ * (0 start, 1 set-up done, 2 first TMA issued, 3 first tile landed, 4 first lo plane done, 5 first MMA issued, 6 last TMA issued, 7 last tile
+ * landed, 8 last MMA issued, 9 last accumulator ready, 10 tile parked, 11 cluster barrier passed, 12 first row reduced, 13 epilogue done,
+ * 14 exit); NULL switches it off (the default) */
+int t4k_gemm_tl_trace(long long *dev16);
 
 /* ---- NN forward: src/nn/forward.cu + src/nn/nmath.cu/.tcu ---------------------------- */
 /* k_bias (nmath.cu:27-35, forward.cu:195): Y[n,e] += B[e] */
@@ -190,6 +195,14 @@ int t4k_linear_bwd_ex(const float *X, const float *W, const float *dY, float *dX
  * input tensor); dW/dB as t4k_linear_bwd_ex.  Same tensors written as the two calls. */
 int t4k_linear_bwd_act(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
                        const float *Fprev, float *dXprev, int N, int E0, int E1, int train, int skip_db, t4k_stream_t s);
+/* dX of the hidden linear layer straight from the classifier head's FORWARD tensors — off the critical path goes t4k_mlp_head_bwd:
+ *   dX[N,E1] = A @ W1,  A[n][e] = (Σ_k (P[n][k] - T[n][k]) * W2[k][e]) * F1[n][e]      (W2 [E2,EH], W1 [EH,E1], F1 [N,EH] or NULL)
+ * i.e. Model::_bprep, the small linear's dX and the activation backward (backprop.cu:76-140,194-263) are evaluated inside the GEMM's
+ * operand producer (same arithmetic, same order as t4k_mlp_head_bwd: the same bits as the dX GEMM run on its stored output).  Reads only
+ * tensors the backward pass never overwrites when P is the duplicate of the softmax output (t4k_mlp_head_fwd_dup), so it can run
+ * concurrently with t4k_mlp_head_bwd.  T4K_ENOSUP: E2 > 32, EH > 128, EH % 4, or a shape the layer GEMM does not take. */
+int t4k_linear_dx_from_head(const float *P, const float *T, const float *W2, const float *F1, const float *W1, float *dX,
+                            int N, int E2, int EH, int E1, t4k_stream_t s);
 /* classifier head, backward, one launch (backprop.cu:76-140,194-263), E0 <= 32, E1 <= 128 else T4K_ENOSUP:
  *   P <- P - T (Model::_bprep), Ylin <- P - T (softmax backward is a copy), dB += Σ_n (P-T), dW += (P-T)^T @ X2,
  *   X2 <- (P-T) @ W (in place: the small linear's input tensor receives its dX),

@@ -43,6 +43,9 @@ struct TlEpi {
     int mode; const float *bias; float *actA, *actF; int layer; float act_alpha;       // mode 1, 2: Y = acc + bias (to O), A = act(Y), F = derivative / mask
     const float *W2, *B2; float *Y2, *P, *P2; int E2;                                 // mode 2: Y2 = A @ W2^T + B2 [M,E2], P = softmax(Y2), P2 = copy of P (may be null)
     const float *F; float *O2;                                                        // mode 3: O = acc, O2 = acc * F
+    // generated A operand (gP != nullptr; the A argument of gemm_tl is ignored): A[m][k] = (Σ_j (gP[m][j] - gT[m][j]) * gW2[j][k]) * gF[m][k]
+    // (gF may be null), j < gE2 <= 32, K <= 128, K % 4 == 0
+    const float *gP, *gT, *gW2, *gF; int gE2;
 };
 bool gemm_tl_ok(const float *A, const float *B, const float *O, int tA, int tB, int M, int N, int K, int C, int batch);
 int  gemm_tl(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,

@@ -41,7 +41,8 @@ constexpr int L_NCONV = 6, L_NEPI = 8;                   // 16 warps: register f
 constexpr int L_WARPS = 2 + L_NCONV + L_NEPI;            // 16
 constexpr int L_THREADS = L_WARPS * 32;                  // 512
 constexpr int L_CONV_T = L_NCONV * 32;                   // 192 converter threads
-constexpr int L_W2_FLTS = 32 * 128;                      // head weights [E2 <= 32][EH <= 128] in shared memory (mode 2)
+constexpr int L_W2_FLTS = 32 * 128;                      // head weights [E2 <= 32][EH <= 128] in shared memory (mode 2, generated A)
+constexpr int L_D_FLTS = 128 * 32;                       // generated A: p - y rows of the tile [128][E2 <= 32]
 
 struct TlP {
     float *O; float alpha, beta;
@@ -54,7 +55,14 @@ struct TlP {
     const float *bias; float *actA, *actF; int layer; float act_alpha;          // mode 1, 2
     const float *W2, *B2; float *Y2, *P, *P2; int E2;                          // mode 2
     const float *F; float *O2;                                                  // mode 3
+    // generated A operand (gen != 0; A is K-major [M][K], K <= 128): A[m][k] = (Σ_j (gP[m][j] - gT[m][j]) * gW2[j][k]) * gF[m][k] — the classifier
+    // head's backward (Model::_bprep + the small linear's dX + the activation backward, backprop.cu:76-140,194-263) evaluated in the
+    // converter warps instead of being loaded: the dX GEMM of the hidden linear layer no longer waits for a head-backward kernel
+    int gen, gE2; const float *gP, *gT, *gW2, *gF;
+    float *part;                 // split-K partials [cluster][rank][128][128] in the library workspace (L2-resident); nullptr: reduce over distributed shared memory
+    long long *trace;            // bring-up: clock64 stamps of CTA (0,0,0)'s phases (t4k_gemm_tl_trace), nullptr in production
 };
+#define TL_TRACE(ev) do { if (p.trace && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) p.trace[ev] = clock64(); } while (0)
 
 __device__ __forceinline__ void tl_tma_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -120,8 +128,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
     uint8_t *smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // SWIZZLE_128B tiles: 1024-byte aligned
     uint64_t *bars = (uint64_t*)(smem + L_STAGES * L_STAGE_B);                        // raw_full[S], lo_full[S], empty[S], acc_full[2], acc_empty[2]
     uint32_t *tmem_slot = (uint32_t*)(bars + 3 * L_STAGES + 4);
-    float *sW2 = reinterpret_cast<float*>(smem + L_STAGES * L_STAGE_B + 256);         // mode 2: head weights
+    float *sW2 = reinterpret_cast<float*>(smem + L_STAGES * L_STAGE_B + 256);         // mode 2 / generated A: head weights
+    float *sD = sW2 + L_W2_FLTS;                                                      // generated A: p - y
     pdl_wait(); pdl_trigger();
+    if (threadIdx.x == 0) TL_TRACE(0);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = blockIdx.y, nt = blockIdx.x, zs = blockIdx.z, S = (int)gridDim.z;
@@ -132,12 +142,34 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
     const uint32_t raw0 = smem_u32(bars), lo0 = smem_u32(bars + L_STAGES), empty0 = smem_u32(bars + 2 * L_STAGES);
     const uint32_t afull0 = smem_u32(bars + 3 * L_STAGES), aempty0 = smem_u32(bars + 3 * L_STAGES + 2);
 
+    // one k-block's TMA loads (raw FP32 tiles) into stage s; complete on raw_full[s]
+    auto tma_issue = [&](int i) {
+        const int s = i % L_STAGES;
+        const uint32_t sa = smem_u32(smem + (size_t)s * L_STAGE_B), sb = sa + L_OP_B, bar = raw0 + 8 * s;
+        const int m0 = mt * L_BM, n0 = nt * L_BN, k0 = (kt0 + i) * L_BK;
+        mbar_expect_tx(bar, p.gen ? L_PLANE_B : 2 * L_PLANE_B);
+        if (i == 0) TL_TRACE(2);
+        if (i == nkb - 1) TL_TRACE(6);
+        if (p.gen) { /* A is written by the converter warps */ }
+        else if (!p.a_mn) tl_tma_2d(sa, &amap, k0, m0, bar);                          // box {32 k, 128 rows}
+        else {
+            #pragma unroll
+            for (int j = 0; j < 4; j++) tl_tma_2d(sa + j * 4096u, &amap, m0 + 32 * j, k0, bar);              // box {32 m, 32 k}
+        }
+        if (!p.b_mn) tl_tma_2d(sb, &bmap, k0, n0, bar);
+        else {
+            #pragma unroll
+            for (int j = 0; j < 4; j++) tl_tma_2d(sb + j * 4096u, &bmap, n0 + 32 * j, k0, bar);
+        }
+    };
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&amap) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&bmap) : "memory");
         for (int s = 0; s < L_STAGES; s++) { mbar_init(raw0 + 8 * s, 1); mbar_init(lo0 + 8 * s, L_NCONV); mbar_init(empty0 + 8 * s, 1); }
         for (int b = 0; b < 2; b++) { mbar_init(afull0 + 8 * b, 1); mbar_init(aempty0 + 8 * b, L_NEPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the first ring of loads leaves before the set-up barrier (TMEM allocation, head weights): their latency overlaps it
+        for (int i = 0; i < nkb && i < L_STAGES; i++) tma_issue(i);
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * L_BN);                         // two accumulators of 128 fp32 columns
     if (p.mode == 2 && warp >= 2) {                                                   // head weights: asynchronous copies, published by the barrier in front of the reduction
@@ -145,31 +177,30 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
         for (int t = threadIdx.x - 64; t < tot; t += L_THREADS - 64) cp_async4(sW2 + t, p.W2 + t, true);
         cp_async_commit();
     }
+    if (p.gen && warp >= 2) {                                                         // generated A: W2 [E2][K] and d = p - y of the tile's rows
+        const int tot = p.gE2 * p.K;
+        for (int t = threadIdx.x - 64; t < tot; t += L_THREADS - 64) cp_async4(sW2 + t, p.gW2 + t, true);
+        cp_async_commit();
+        const int nd = L_BM * p.gE2, m0 = blockIdx.y * L_BM;
+        for (int t = threadIdx.x - 64; t < nd; t += L_THREADS - 64) {
+            const int r = t / p.gE2, j = t - r * p.gE2, gr = m0 + r;
+            sD[t] = (gr < p.M) ? __fsub_rn(__ldg(p.gP + (int64_t)gr * p.gE2 + j), __ldg(p.gT + (int64_t)gr * p.gE2 + j)) : 0.0f;
+        }
+        cp_async_wait_all();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TL_TRACE(1);
 
     if (warp == 0) {
         // ===== TMA producer: raw FP32 tiles, the whole ring in flight =====
         if (lane == 0) {
-            const int m0 = mt * L_BM, n0 = nt * L_BN;
-            for (int i = 0; i < nkb; i++) {
+            for (int i = L_STAGES; i < nkb; i++) {
                 const int s = i % L_STAGES, it = i / L_STAGES;
                 mbar_wait(empty0 + 8 * s, (it & 1) ^ 1);
-                const uint32_t sa = smem_u32(smem + (size_t)s * L_STAGE_B), sb = sa + L_OP_B, bar = raw0 + 8 * s;
-                mbar_expect_tx(bar, 2 * L_PLANE_B);
-                const int k0 = (kt0 + i) * L_BK;
-                if (!p.a_mn) tl_tma_2d(sa, &amap, k0, m0, bar);                       // box {32 k, 128 rows}
-                else {
-                    #pragma unroll
-                    for (int j = 0; j < 4; j++) tl_tma_2d(sa + j * 4096u, &amap, m0 + 32 * j, k0, bar);      // box {32 m, 32 k}
-                }
-                if (!p.b_mn) tl_tma_2d(sb, &bmap, k0, n0, bar);
-                else {
-                    #pragma unroll
-                    for (int j = 0; j < 4; j++) tl_tma_2d(sb + j * 4096u, &bmap, n0 + 32 * j, k0, bar);
-                }
+                tma_issue(i);
             }
         }
     } else if (warp == 1) {
@@ -185,6 +216,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
             mbar_wait(raw0 + 8 * s, it & 1);
             mbar_wait(lo0 + 8 * s, it & 1);
             tc_fence_after();
+            if (lane == 0 && i == 0) TL_TRACE(5);
+            if (lane == 0 && i == nkb - 1) TL_TRACE(8);
             if (elect_one()) {
                 const uint32_t acc = tmem_base + (uint32_t)(b * L_BN);
                 const uint32_t sa = smem_u32(smem + (size_t)s * L_STAGE_B), sb = sa + L_OP_B;
@@ -210,17 +243,47 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
         constexpr int NV = (2048 + L_CONV_T - 1) / L_CONV_T;                           // 16-byte words of a stage's two raw planes per thread (11)
         for (int i = 0; i < nkb; i++) {
             const int s = i % L_STAGES, it = i / L_STAGES;
+            if (p.gen) {
+                // the A tile of this k-block, computed: thread -> (row, 16-byte chunk); 8 threads write one 128-byte row (swizzled: conflict-free)
+                mbar_wait(empty0 + 8 * s, (it & 1) ^ 1);                              // the stage's previous MMAs are done
+                uint8_t *abase = smem + (size_t)s * L_STAGE_B;
+                const int k0 = (kt0 + i) * L_BK, c = t & 7, k = k0 + 4 * c, E2 = p.gE2, EH = p.K;
+                #pragma unroll 1
+                for (int r = t >> 3; r < L_BM; r += L_CONV_T / 8) {
+                    const int gr = mt * L_BM + r;
+                    float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    if (gr < p.M && k < EH) {                                         // EH % 4 == 0 (host check): whole chunks
+                        for (int j = 0; j < E2; j++) {                                // class order as k_head_bwd: the same bits as the stored dY1
+                            const float dj = sD[r * E2 + j];
+                            const float4 w = *reinterpret_cast<const float4*>(sW2 + j * EH + k);
+                            x[0] = fmaf(dj, w.x, x[0]); x[1] = fmaf(dj, w.y, x[1]); x[2] = fmaf(dj, w.z, x[2]); x[3] = fmaf(dj, w.w, x[3]);
+                        }
+                        if (p.gF) {
+                            const float4 f = ldg4(p.gF + (int64_t)gr * EH + k);
+                            x[0] = __fmul_rn(x[0], f.x); x[1] = __fmul_rn(x[1], f.y); x[2] = __fmul_rn(x[2], f.z); x[3] = __fmul_rn(x[3], f.w);
+                        }
+                    }
+                    float hi[4], lo[4];
+                    #pragma unroll
+                    for (int e = 0; e < 4; e++) { hi[e] = __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u); lo[e] = to_tf32(x[e] - hi[e]); }
+                    uint8_t *q = abase + (size_t)r * 128 + (size_t)((c ^ (r & 7)) << 4);
+                    *reinterpret_cast<float4*>(q) = make_float4(x[0], x[1], x[2], x[3]);
+                    *reinterpret_cast<float4*>(q + L_PLANE_B) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
             mbar_wait(raw0 + 8 * s, it & 1);
+            if (t == 0 && i == 0) TL_TRACE(3);
+            if (t == 0 && i == nkb - 1) TL_TRACE(7);
             uint8_t *base = smem + (size_t)s * L_STAGE_B;
             float4 v[NV];
             #pragma unroll
             for (int j = 0; j < NV; j++) {
-                const int idx = t + L_CONV_T * j;
+                const int idx = t + L_CONV_T * j + (p.gen ? 1024 : 0);                 // generated A: only the B planes are converted
                 if (idx < 2048) v[j] = *reinterpret_cast<const float4*>(base + (size_t)(idx >> 10) * L_OP_B + (size_t)(idx & 1023) * 16);
             }
             #pragma unroll
             for (int j = 0; j < NV; j++) {
-                const int idx = t + L_CONV_T * j;
+                const int idx = t + L_CONV_T * j + (p.gen ? 1024 : 0);
                 if (idx >= 2048) break;
                 uint8_t *q = base + (size_t)(idx >> 10) * L_OP_B + (size_t)(idx & 1023) * 16;
                 const float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
@@ -236,6 +299,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
             tl_fence_proxy_async();                      // generic-proxy stores → visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(lo0 + 8 * s);
+            if (t == 0 && i == 0) TL_TRACE(4);
         }
     } else {
         // ===== epilogue warps: drain the accumulator chains into registers (round-to-nearest adds), park the tile =====
@@ -248,6 +312,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
             const int b = c & 1;
             mbar_wait(afull0 + 8 * b, (c >> 1) & 1);
             tc_fence_after();
+            if (c == nchunk - 1 && warp == 2 + L_NCONV && lane == 0) TL_TRACE(9);
             #pragma unroll
             for (int gq = 0; gq < CW / 16; gq++) {
                 uint32_t v[16];
@@ -266,11 +331,26 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
         #pragma unroll
         for (int j = 0; j < CW; j += 4)
             *reinterpret_cast<float4*>(park + tl_park_off(r, (h * CW + j) >> 2)) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        if (warp == 2 + L_NCONV && lane == 0) TL_TRACE(10);
     }
     if (p.mode == 2) cp_async_wait_all();
     tc_fence_before();
     __syncthreads();
-    if (S > 1) tl_cluster_sync();                                                     // every CTA's tile is parked and visible cluster-wide
+    // split-K partials through L2 (default): distributed shared memory serves ~20 B/clk per SM — 60 KiB of peer tiles cost 1.6 us and every CTA
+    // has to stay resident until its last reader is done (measured, profiles/r02_tl_trace.txt); the L2 takes the same bytes at 3x the rate
+    // and nobody waits at the exit.  The tile goes out coalesced (a warp per row), the cluster barrier (release/acquire) publishes it.
+    float *mypart = nullptr;
+    if (S > 1 && p.part) {
+        mypart = p.part + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * S) * (size_t)(L_BM * L_BN);
+        const float *park = reinterpret_cast<const float*>(smem);
+        float *dst = mypart + (size_t)zs * (L_BM * L_BN);
+        const int rows = min(L_BM, p.M - mt * L_BM);
+        if (nt * L_BN + lane * 4 < p.N)
+            for (int r = warp; r < rows; r += L_WARPS)
+                __stcg(reinterpret_cast<float4*>(dst + r * L_BN + lane * 4), *reinterpret_cast<const float4*>(park + tl_park_off(r, lane)));
+    }
+    if (S > 1) tl_cluster_sync();                                                     // every CTA's tile is parked / stored and visible cluster-wide
+    if (threadIdx.x == 0) TL_TRACE(11);
 
     // ===== reduction over the cluster + epilogue: CTA `zs` finishes rows [zs*rpr, (zs+1)*rpr) of the tile, a warp per row, lane = 16-byte chunk =====
     {
@@ -286,13 +366,21 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
             if (S == 1) sum = *reinterpret_cast<const float4*>(park + tl_park_off(r, lane));
             else {
                 float4 v[16];
-                const uint32_t a = park_s + (uint32_t)tl_park_off(r, lane) * 4u;
-                #pragma unroll
-                for (int qk = 0; qk < 16; qk++) if (qk < S) v[qk] = tl_ld_dsmem4(a, (uint32_t)qk);
+                if (mypart) {
+                    const float *src = mypart + r * L_BN + lane * 4;
+                    const bool ld = gc < p.N;
+                    #pragma unroll
+                    for (int qk = 0; qk < 16; qk++) if (qk < S) v[qk] = ld ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)qk * (L_BM * L_BN))) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    const uint32_t a = park_s + (uint32_t)tl_park_off(r, lane) * 4u;
+                    #pragma unroll
+                    for (int qk = 0; qk < 16; qk++) if (qk < S) v[qk] = tl_ld_dsmem4(a, (uint32_t)qk);
+                }
                 sum = v[0];
                 #pragma unroll
                 for (int qk = 1; qk < 16; qk++) if (qk < S) { sum.x += v[qk].x; sum.y += v[qk].y; sum.z += v[qk].z; sum.w += v[qk].w; }
             }
+            if (threadIdx.x == 0 && rr == 0) TL_TRACE(12);
             const bool in = gc < p.N;
             const bool full = o_vec && gc + 3 < p.N;
             const int64_t at = (int64_t)gr * p.N + gc;
@@ -367,7 +455,9 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
             }
         }
     }
-    if (S > 1) tl_cluster_sync();                                                     // nobody leaves while its tile is still being read
+    if (threadIdx.x == 0) TL_TRACE(13);
+    if (S > 1 && !mypart) tl_cluster_sync();                                          // distributed shared memory: nobody leaves while its tile is still being read
+    if (threadIdx.x == 0) TL_TRACE(14);
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * L_BN); }
 }
 
@@ -396,7 +486,8 @@ static int tl_map(CUtensorMap *m, const float *X, int64_t inner, int64_t outer, 
                swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : T4K_EINVAL;
 }
 
-constexpr size_t L_SMEM = (size_t)L_STAGES * L_STAGE_B + 256 + (size_t)L_W2_FLTS * 4 + 1024;
+constexpr size_t L_SMEM = (size_t)L_STAGES * L_STAGE_B + 256 + (size_t)(L_W2_FLTS + L_D_FLTS) * 4 + 1024;
+static_assert(L_SMEM <= 227 * 1024, "shared memory budget");
 #define TL_MAX_DEV 16
 static int g_tl_maxcl[TL_MAX_DEV][5];                   // [device][log2 S]: co-resident clusters of size S (0: not queried yet, -1: unavailable)
 
@@ -424,12 +515,14 @@ static int tl_prepare(int dev) {
 }
 static int tl_env(const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; }
 // knobs (t4k_set_gemm_tl): 0 engine on/off for AUTO, 1 mask_hi (debug), 2 largest cluster size; 3-7 (bring-up probes only): MN-major
-// descriptor layout type, TMA swizzle mode, LBO, SBO, start-address step per 8 k
-#define TL_NKNOB 8
-static int g_tl_knob[TL_NKNOB] = {-1, -1, -1, -1, -1, -1, -1, -1};
+// descriptor layout type, TMA swizzle mode, LBO, SBO, start-address step per 8 k; 8: split-K partials through L2 (1, default) or reduced
+// over distributed shared memory (0)
+#define TL_NKNOB 9
+static long long *g_tl_trace = nullptr;
+static int g_tl_knob[TL_NKNOB] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
 static int tl_knob(int k) {
-    static const char *name[TL_NKNOB] = {"T4K_GEMM_TL", "T4K_TL_MASKHI", "T4K_TL_SMAX", "T4K_TL_MN_TYPE", "T4K_TL_MN_SWZ", "T4K_TL_MN_LBO", "T4K_TL_MN_SBO", "T4K_TL_MN_KSTEP"};
-    static const int dflt[TL_NKNOB] = {1, 0, 16, 1, (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 4096, 512, 1024};
+    static const char *name[TL_NKNOB] = {"T4K_GEMM_TL", "T4K_TL_MASKHI", "T4K_TL_SMAX", "T4K_TL_MN_TYPE", "T4K_TL_MN_SWZ", "T4K_TL_MN_LBO", "T4K_TL_MN_SBO", "T4K_TL_MN_KSTEP", "T4K_TL_L2RED"};
+    static const int dflt[TL_NKNOB] = {1, 0, 16, 1, (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 4096, 512, 1024, 1};
     if (g_tl_knob[k] < 0) g_tl_knob[k] = tl_env(name[k], dflt[k]);
     return g_tl_knob[k];
 }
@@ -467,13 +560,24 @@ int gemm_tl(const float *A, const float *B, float *O, float alpha, float beta, i
     p.a_mn = tA ? 1 : 0; p.b_mn = tB ? 0 : 1; p.mask_hi = mask_hi; p.mode = 0;
     p.mn_type = (uint32_t)tl_knob(3); p.mn_lbo = (uint32_t)tl_knob(5); p.mn_sbo = (uint32_t)tl_knob(6); p.mn_kstep = (uint32_t)tl_knob(7);
     const CUtensorMapSwizzle mn_swz = (CUtensorMapSwizzle)tl_knob(4);
+    p.trace = g_tl_trace;
+    if (S > 1 && tl_knob(8)) {
+        p.part = (float*)workspace((size_t)T * S * L_BM * L_BN * sizeof(float), 7);
+        if (!p.part) return T4K_ENOMEM;
+    }
     if (epi) {
         p.mode = epi->mode; p.bias = epi->bias; p.actA = epi->actA; p.actF = epi->actF; p.layer = epi->layer; p.act_alpha = epi->act_alpha;
         p.W2 = epi->W2; p.B2 = epi->B2; p.Y2 = epi->Y2; p.P = epi->P; p.P2 = epi->P2; p.E2 = epi->E2; p.F = epi->F; p.O2 = epi->O2;
+        if (epi->gP) {
+            if (tA || K > 128 || (K & 3) || epi->gE2 < 1 || epi->gE2 > 32 || !epi->gT || !epi->gW2) return T4K_ENOSUP;
+            p.gen = 1; p.gE2 = epi->gE2; p.gP = epi->gP; p.gT = epi->gT; p.gW2 = epi->gW2; p.gF = epi->gF;
+        }
     }
     CUtensorMap amap, bmap;
     // op(A)(m,k): A stored [M][K] (K-major: box 128 rows x 32 k) or [K][M] when tA (M-major: box 32 k-rows x 32 m)
-    rc = tA ? tl_map(&amap, A, M, K, 32, mn_swz) : tl_map(&amap, A, K, M, 128); if (rc) return rc;
+    if (p.gen) rc = tl_map(&amap, B, tB ? K : N, tB ? N : K, tB ? 128 : 32, tB ? CU_TENSOR_MAP_SWIZZLE_128B : mn_swz);       // unused: a valid map
+    else rc = tA ? tl_map(&amap, A, M, K, 32, mn_swz) : tl_map(&amap, A, K, M, 128);
+    if (rc) return rc;
     // op(B)(k,n): B stored [N][K] when tB (K-major) or [K][N] (N-major)
     rc = tB ? tl_map(&bmap, B, K, N, 128) : tl_map(&bmap, B, N, K, 32, mn_swz); if (rc) return rc;
     cudaLaunchConfig_t cfg = {};
@@ -489,6 +593,7 @@ int gemm_tl(const float *A, const float *B, float *O, float alpha, float beta, i
 
 } // namespace t4k
 
+extern "C" int t4k_gemm_tl_trace(long long *dev16) { t4k::g_tl_trace = dev16; return 0; }   // bring-up: 16 clock64 stamps of CTA (0,0,0), nullptr = off
 extern "C" int t4k_set_gemm_tl(int what, int value) {
     if (what < 0 || what >= TL_NKNOB) return T4K_EINVAL;
     const int was = t4k::tl_knob(what);

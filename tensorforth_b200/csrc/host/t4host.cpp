@@ -16,7 +16,7 @@ namespace t4 {
 
 // =============================================================================== Runtime
 static cudaStream_t g_stream = nullptr, g_stream2 = nullptr;      // library stream + side stream (forked work inside a step)
-static cudaEvent_t  g_fork = nullptr, g_join = nullptr;
+static cudaEvent_t  g_fork = nullptr, g_join = nullptr, g_head = nullptr;
 static bool  g_init = false;
 static char  g_err[512] = "";
 
@@ -25,7 +25,7 @@ int Runtime::init(int device) {
     if (cudaSetDevice(device) != cudaSuccess) { error("cudaSetDevice(%d) failed: no CUDA device (there is no CPU fallback)", device); cudaGetLastError(); return T4K_EINVAL; }
     if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) { error("cudaStreamCreate failed"); return T4K_EINVAL; }
     if (cudaStreamCreateWithFlags(&g_stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming) != cudaSuccess) { error("cudaStreamCreate failed"); return T4K_EINVAL; }
+        cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&g_head, cudaEventDisableTiming) != cudaSuccess) { error("cudaStreamCreate failed"); return T4K_EINVAL; }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t keep = UINT64_MAX;                     // keep freed blocks cached: alloc/free in `for @ drop next` loops stay cheap
@@ -437,6 +437,18 @@ int Model::_bfused_head(Tensor &tgt, bool *skip_db) {
     Tensor *act = (n >= 5 && (mask_act(_layers[n - 4]->grad_fn) || _layers[n - 4]->grad_fn == T4K_L_DROPOUT)) ? _layers[n - 4] : nullptr;
     const int prev = act ? n - 5 : n - 4;
     Tensor *lin1 = (prev >= 0 && _layers[prev]->grad_fn == T4K_L_LINEAR && train) ? _layers[prev] : nullptr;
+    // Inside step_graph (a duplicate of the softmax output exists) with the hidden linear's dW on the side stream (a flatten in front of it
+    // holds a second copy of X): the head kernel is NOT launched here.  Model::_blinear puts it on the side stream in front of the dW GEMM,
+    // and the dX GEMM of the hidden layer — the critical path — evaluates p - y, the small linear's dX and the activation backward in its
+    // operand producer from tensors nobody overwrites (t4k_linear_dx_from_head).
+    if (lin1 && _pdup_valid && _pdup && prev > 0 && _layers[prev - 1]->grad_fn == T4K_L_FLATTEN && _layers[prev - 1]->data != lin1->data &&
+        _layers[prev - 1]->numel == lin1->numel && (E1 & 3) == 0 && (lin1->HWC() & 3) == 0) {
+        _hp.on = true; _hp.P = P.data; _hp.T = tgt.data; _hp.Ylin = yl.data; _hp.X2 = x2.data;
+        _hp.F1 = act ? act->grad[4]->data : nullptr; _hp.Y1 = act ? act->data : nullptr; _hp.W2 = x2.grad[0]->data;
+        _hp.dW2 = x2.grad[2]->data; _hp.dB2 = x2.grad[3]->data; _hp.dB1 = lin1->grad[3]->data; _hp.N = N; _hp.E0 = E0; _hp.E1 = E1;
+        *skip_db = true;
+        return prev;
+    }
     int rc = t4k_mlp_head_bwd(P.data, tgt.data, yl.data, x2.data, act ? act->grad[4]->data : nullptr, act ? act->data : nullptr,
                               x2.grad[0]->data, x2.grad[2]->data, x2.grad[3]->data, lin1 ? lin1->grad[3]->data : nullptr,
                               N, E0, E1, train, ST);
@@ -614,11 +626,21 @@ int Model::_blinear(Tensor &in, Tensor &out, bool skip_db, Tensor *xdup, bool de
         cudaStream_t st = (cudaStream_t)ST;
         if (!skip_db) KCHK(t4k_dbias(out.data, db.data, N, E0, ST));
         cudaEventRecord(g_fork, st); cudaStreamWaitEvent(g_stream2, g_fork, 0);
+        const bool hp = _hp.on; _hp.on = false;
+        if (hp) {                                            // the deferred head backward (see _bfused_head): produces dY (= out) for the dW GEMM behind it
+            KCHK(t4k_mlp_head_bwd(_hp.P, _hp.T, _hp.Ylin, _hp.X2, _hp.F1, _hp.Y1, _hp.W2, _hp.dW2, _hp.dB2, _hp.dB1, _hp.N, _hp.E0, _hp.E1, train, (t4k_stream_t)g_stream2));
+            cudaEventRecord(g_head, g_stream2);
+        }
         t4k_set_workspace_bank(1);
         KCHK(t4k_gemm(out.data, xdup->data, dw.data, 1.0f, 1.0f, 1, 0, E0, E1, N, 1, 1, 0, 0, 0, (t4k_stream_t)g_stream2));
         t4k_set_workspace_bank(0);
         cudaEventRecord(g_join, g_stream2);
-        KCHK(t4k_gemm(out.data, w.data, in.data, 1.0f, 0.0f, 0, 0, N, E1, E0, 1, 1, 0, 0, 0, ST));
+        int rcx = T4K_ENOSUP;
+        if (hp) rcx = t4k_linear_dx_from_head(_pdup, _hp.T, _hp.W2, _hp.F1, w.data, in.data, N, _hp.E0, E0, E1, ST);
+        if (rcx == T4K_ENOSUP) {
+            if (hp) cudaStreamWaitEvent(st, g_head, 0);      // not taken: dY comes from the head kernel after all
+            KCHK(t4k_gemm(out.data, w.data, in.data, 1.0f, 0.0f, 0, 0, N, E1, E0, 1, 1, 0, 0, 0, ST));
+        } else KCHK(rcx);
         if (!defer) { cudaStreamWaitEvent(st, g_join, 0); return 0; }
         // deferred join: the flatten backward (duplicate <- dX) follows dW on the side stream, once dX is there
         cudaEventRecord(g_fork, st); cudaStreamWaitEvent(g_stream2, g_fork, 0);

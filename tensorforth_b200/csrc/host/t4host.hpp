@@ -167,6 +167,9 @@ class Model {
     DU     *_pdup = nullptr; bool _want_pdup = false, _pdup_valid = false;   // step_graph: duplicate of the softmax output for the side-stream loss
     const StepExtra *_feed = nullptr; DU *_feed_hot = nullptr;   // step_graph: staged U8 batch still to be loaded (folded into the first fused block when there is one)
     void    _feed_fallback();
+    // classifier-head backward deferred onto the side stream (in front of the hidden linear's dW GEMM) while that layer's dX GEMM generates
+    // its operand from the forward tensors (t4k_linear_dx_from_head): the arguments of the pending t4k_mlp_head_bwd
+    struct HeadPending { bool on = false; DU *P, *T, *Ylin, *X2, *F1, *Y1, *W2, *dW2, *dB2, *dB1; int N, E0, E1; } _hp;
     bool    _side_join = false, _skip_flat_copy = false;   // backprop: work pending on the side stream / flatten copy already issued there
     DU     *_loss_pin = nullptr; void *_loss_ev[2] = {nullptr, nullptr}; unsigned _tstep = 0;   // train_step read-back ring
     std::vector<Tensor*> _layers;      ///< layer i holds that layer's INPUT; last = output

@@ -105,10 +105,17 @@ __global__ void __launch_bounds__(T4K_THREADS) k_head_fwd(const float *__restric
         #pragma unroll
         for (int k = 0; k < 32; k++) acc[k] = 0.0f;
         const float *x = X + (int64_t)row * E1;
-        for (int e = lane; e < E1; e += 32) {
-            const float xv = x[e];
+        // a lane owns the inputs 4*lane .. 4*lane+3 (+128 j): the partition (and with it the bits) of the layer GEMM's fused head epilogue
+        for (int e0 = 4 * lane; e0 < E1; e0 += 128) {
             #pragma unroll
-            for (int k = 0; k < 32; k++) if (k < E0) acc[k] = fmaf(xv, sW[k * E1 + e], acc[k]);
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u;
+                if (e < E1) {
+                    const float xv = x[e];
+                    #pragma unroll
+                    for (int k = 0; k < 32; k++) if (k < E0) acc[k] = fmaf(xv, sW[k * E1 + e], acc[k]);
+                }
+            }
         }
         float y = warp_treduce32(acc, lane);           // lane k: Σ_e x[e] W[k][e]
         const bool on = lane < E0;
@@ -136,15 +143,16 @@ __global__ void __launch_bounds__(T4K_THREADS) k_fin_head_fwd(const float *__res
     for (int t = threadIdx.x; t < E0 * E1; t += blockDim.x) cp_async4(sW + t, W2 + t, true);
     cp_async_commit();
     const int lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
-    // the lane's (up to) four hidden units; eight splits' loads in flight together; sums in split order as k_linear_fin
+    // the lane's (up to) four hidden units 4*lane .. 4*lane+3 (the partition of the layer GEMM's fused head epilogue: same bits); eight
+    // splits' loads in flight together; sums in split order as k_linear_fin
     auto sum_parts = [&](int64_t r0, float (&sv)[4]) {
         #pragma unroll
-        for (int j = 0; j < 4; j++) { const int e = lane + 32 * j; sv[j] = (e < E1) ? part[r0 + e] : 0.0f; }
+        for (int j = 0; j < 4; j++) { const int e = 4 * lane + j; sv[j] = (e < E1) ? part[r0 + e] : 0.0f; }
         #pragma unroll 8
         for (int k = 1; k < splits; k++) {
             float tv[4];
             #pragma unroll
-            for (int j = 0; j < 4; j++) { const int e = lane + 32 * j; tv[j] = (e < E1) ? part[(int64_t)k * MN + r0 + e] : 0.0f; }
+            for (int j = 0; j < 4; j++) { const int e = 4 * lane + j; tv[j] = (e < E1) ? part[(int64_t)k * MN + r0 + e] : 0.0f; }
             #pragma unroll
             for (int j = 0; j < 4; j++) sv[j] += tv[j];
         }
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(T4K_THREADS) k_fin_head_fwd(const float *__res
     if (have) sum_parts((int64_t)row * E1, sv);
     float b1v[4];                                          // biases: requested with everything else, not after the barrier
     #pragma unroll
-    for (int j = 0; j < 4; j++) { const int e = lane + 32 * j; b1v[j] = (e < E1) ? __ldg(B1 + e) : 0.0f; }
+    for (int j = 0; j < 4; j++) { const int e = 4 * lane + j; b1v[j] = (e < E1) ? __ldg(B1 + e) : 0.0f; }
     const float b2v = (lane < E0) ? __ldg(B2 + lane) : 0.0f;
     cp_async_wait_all();
     __syncthreads();
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(T4K_THREADS) k_fin_head_fwd(const float *__res
         have = false;
         #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const int e = lane + 32 * j;
+            const int e = 4 * lane + j;
             if (e < E1) {
                 const float s = sv[j] + b1v[j];
                 Y1[r0 + e] = s;
@@ -381,6 +389,13 @@ extern "C" int t4k_linear_bwd_act(const float *X, const float *W, const float *d
     }
     TlEpi e{}; e.mode = 3; e.F = Fprev; e.O2 = dXprev;
     return gemm_tl(dY, W, dX, 1.0f, 0.0f, 0, 0, N, E1, E0, STRM(s), &e);            // dX = dY @ W ; dXprev = dX * Fprev
+}
+extern "C" int t4k_linear_dx_from_head(const float *P, const float *T, const float *W2, const float *F1, const float *W1, float *dX,
+                                       int N, int E2, int EH, int E1, t4k_stream_t s) {
+    if (!P || !T || !W2 || !W1 || !dX || N < 1 || E2 < 1 || EH < 1 || E1 < 1) return T4K_EINVAL;
+    if (E2 > 32 || EH > 128 || (EH & 3) || !gemm_tl_ok(W1, W1, dX, 0, 0, N, E1, EH, 1, 1) || !aligned16(W2) || (F1 && !aligned16(F1))) return T4K_ENOSUP;
+    TlEpi e{}; e.mode = 0; e.gP = P; e.gT = T; e.gW2 = W2; e.gF = F1; e.gE2 = E2;
+    return gemm_tl(nullptr, W1, dX, 1.0f, 0.0f, 0, 0, N, E1, EH, STRM(s), &e);      // dX[N,E1] = A[N,EH] @ W1[EH,E1], A generated
 }
 extern "C" int t4k_linear_bwd(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
                               int N, int E0, int E1, int train, t4k_stream_t s) {

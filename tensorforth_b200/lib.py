@@ -48,6 +48,7 @@ PROTOTYPES = {
     "t4k_gemm": (_i, [_p, _p, _p, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _l, _p]),
     "t4k_gemm_ex": (_i, [_i, _p, _p, _p, _f, _f, _i, _i, _i, _i, _i, _i, _i, _l, _l, _l, _p]),
     "t4k_set_gemm_tl": (_i, [_i, _i]),
+    "t4k_gemm_tl_trace": (_i, [_p]),
     "t4k_bias": (_i, [_p, _p, _i, _i, _p]),
     "t4k_linear_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "t4k_activate_fwd": (_i, [_i, _p, _p, _p, _f, _l, _p]),
@@ -60,6 +61,7 @@ PROTOTYPES = {
     "t4k_dbias": (_i, [_p, _p, _i, _i, _p]),
     "t4k_linear_bwd": (_i, [_p] * 6 + [_i] * 4 + [_p]),
     "t4k_linear_bwd_ex": (_i, [_p] * 6 + [_i] * 5 + [_p]),
+    "t4k_linear_dx_from_head": (_i, [_p] * 6 + [_i] * 4 + [_p]),
     "t4k_linear_bwd_act": (_i, [_p] * 8 + [_i] * 5 + [_p]),
     "t4k_linear_act_fwd": (_i, [_i] + [_p] * 6 + [_f] + [_i] * 3 + [_p]),
     "t4k_mlp_head_fwd": (_i, [_p] * 5 + [_i] * 3 + [_p]),
@@ -82,6 +84,7 @@ PROTOTYPES = {
     "t4k_comm_connect_local": (_i, [_p, C.POINTER(_p)]),
     "t4k_comm_destroy": (_i, [_p]),
     "t4k_comm_status": (_i, [_p]),
+    "t4k_comm_poll": (_i, [_p]),
     "t4k_comm_capacity": (_l, [_p]),
     "t4k_shard_info": (_i, [_l, _i, _i, C.POINTER(_l), C.POINTER(_l)]),
     "t4k_allreduce_sum": (_i, [_p, _p, _l, _p]),

@@ -282,6 +282,36 @@ def test_gemm_tl_hi_plane_and_cluster_sizes(tA, tB, M, N, K):
         assert_close(got, ref, rtol=1e-5, what="cluster size <= %d" % smax)
 
 
+@pytest.mark.parametrize("N,E2,EH,E1,act", [(512, 10, 100, 1960, True), (512, 10, 100, 1960, False), (200, 32, 128, 516, True), (64, 3, 20, 64, True)])
+def test_linear_dx_from_head(N, E2, EH, E1, act):
+    """dX of the hidden linear layer computed straight from the head's forward tensors (p - y, the small linear's dX and the activation
+    backward evaluated in the GEMM's operand producer) == t4k_mlp_head_bwd followed by the dX GEMM on its stored output: the same bits"""
+    P, T, X2, W2 = np.abs(rnd(N, E2)), orc.onehot(np.arange(N) % E2, E2), rnd(N, EH), rnd(E2, EH)
+    F1 = (rnd(N, EH) > 0).astype(np.float32)
+    W1 = rnd(EH, E1) * 0.05
+    dP, dT, dW2_, dF1, dW1 = dev(P), dev(T), dev(W2), dev(F1), dev(W1)
+    # reference path: head backward (writes dY1 into y1 / dX2 into x2), then the dX GEMM
+    p, yl, x2, y1 = dev(P), zeros(N, E2), dev(X2), zeros(N, EH)
+    dw, db, db1 = zeros(E2, EH), zeros(E2), zeros(EH)
+    ok(lib().t4k_mlp_head_bwd(ptr(p), ptr(dT), ptr(yl), ptr(x2), ptr(dF1) if act else None, ptr(y1) if act else None, ptr(dW2_),
+                              ptr(dw), ptr(db), ptr(db1), N, E2, EH, 1, None))
+    dy1 = y1 if act else x2
+    ref = zeros(N, E1)
+    ok(lib().t4k_gemm(ptr(dy1), ptr(dW1), ptr(ref), 1.0, 0.0, 0, 0, N, E1, EH, 1, 1, 0, 0, 0, None))
+    got = zeros(N, E1)
+    rc = lib().t4k_linear_dx_from_head(ptr(dP), ptr(dT), ptr(dW2_), ptr(dF1) if act else None, ptr(dW1), ptr(got), N, E2, EH, E1, None)
+    if (N, E2, EH, E1) == (64, 3, 20, 64):
+        assert rc in (0, t4.ENOSUP)                        # below the layer GEMM's size class: the caller keeps the two-kernel path
+        if rc:
+            return
+    else:
+        ok(rc, "dx_from_head")
+    assert_exact(host(got), host(ref), "dX from the head's forward tensors")
+    d = orc.tt_op(orc.SUB, P, T)
+    g = orc.gemm(d, W2) * (F1 if act else 1.0)
+    assert_close(host(got), orc.gemm(np.ascontiguousarray(g, np.float32), W1), rtol=1e-4, what="dX vs oracle")
+
+
 @pytest.mark.parametrize("N,E0,E1", [(1024, 512, 784), (512, 100, 1960), (1024, 256, 512), (96, 36, 48)])
 def test_linear_bwd_act(N, E0, E1):
     """_blinear + the _bactivate in front of it, mask multiply in the dX GEMM's epilogue: same tensors as the two calls"""
