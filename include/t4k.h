@@ -203,6 +203,11 @@ int t4k_linear_bwd_act(const float *X, const float *W, const float *dY, float *d
  * concurrently with t4k_mlp_head_bwd.  T4K_ENOSUP: E2 > 32, EH > 128, EH % 4, or a shape the layer GEMM does not take. */
 int t4k_linear_dx_from_head(const float *P, const float *T, const float *W2, const float *F1, const float *W1, float *dX,
                             int N, int E2, int EH, int E1, t4k_stream_t s);
+/* the same for BOTH products of the hidden layer, ONE launch: dX = A @ W1 and dW1 += A^T @ X with A generated K-major for the one and
+ * M-major for the other (two problems share the grid of the layer GEMM).  X must not alias dX (Model::backprop passes the flatten layer's
+ * duplicate of X).  T4K_ENOSUP: as above, or the two problems do not fit one co-resident wave. */
+int t4k_linear_bwd_from_head(const float *P, const float *T, const float *W2, const float *F1, const float *X, const float *W1,
+                             float *dX, float *dW1, int N, int E2, int EH, int E1, t4k_stream_t s);
 /* classifier head, backward, one launch (backprop.cu:76-140,194-263), E0 <= 32, E1 <= 128 else T4K_ENOSUP:
  *   P <- P - T (Model::_bprep), Ylin <- P - T (softmax backward is a copy), dB += Σ_n (P-T), dW += (P-T)^T @ X2,
  *   X2 <- (P-T) @ W (in place: the small linear's input tensor receives its dX),
@@ -258,6 +263,19 @@ int t4k_adamw(float *G, float *DG, float *M, float *V, float lr, float b1, float
 typedef struct { int64_t off; int64_t len; int32_t Nw; int32_t pad; } t4k_seg_t;
 int t4k_optim_multi(int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
                     int64_t total, float lr, float b1, float b2, float wd, t4k_stream_t s);
+
+/* the same over the arena elements [from, to) only (absolute indices: `seg` stays the whole table).  Lets a caller run the optimizer of the
+ * layers whose gradients are final early, on a second stream, while backprop still works on the first layers */
+int t4k_optim_multi_range(int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
+                          int64_t from, int64_t to, float lr, float b1, float b2, float wd, t4k_stream_t s);
+/* optimizer step applied by the kernel that FINISHES a gradient (the conv block's dF/dB reduction): G/M/V are the arena bases, offF/offB
+ * the offsets of the filter / bias segments (dF = DG + offF, dB = DG + offB), Nw their t4k_seg_t.Nw; same arithmetic as t4k_optim_multi */
+typedef struct { int kind; float lr, b1, b2, wd; float *G, *M, *V; int64_t offF, offB; int32_t NwF, NwB; } t4k_fused_opt_t;
+/* t4k_conv_pool_relu_bwd with `opt` (may be NULL = plain): the last launch of the block (per-sample partials -> dF, dB) also applies the
+ * optimizer step to the filter and bias and zeroes dF, dB — one launch less at the end of a train step */
+int t4k_conv_pool_relu_bwd_opt(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,
+                               const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
+                               int KS, int S, int P, int train, const t4k_fused_opt_t *opt, t4k_stream_t s);
 
 /* ---- data-parallel extras (SURVEY.md §8b "DP extras", §8e) --------------------------------
  * The reference is single-GPU; Model::forward/backprop shard over the batch and the parameter gradients are batch

@@ -33,6 +33,7 @@ int cpr_v1_bwd(const float *dY, float *actO, const float *actF, float *poolO, fl
                const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
                int KS, int S, int P, int train, cudaStream_t st);
 int wgrad_fin_launch(const float *part, float *dF, float *dB, int nF, int C0, int nparts, int KS, int S, cudaStream_t st);
+int wgrad_fin_opt_launch(const float *part, float *dF, float *dB, int nF, int C0, int nparts, int KS, int S, const t4k_fused_opt_t *opt, cudaStream_t st);
 
 #ifndef CPR2_FWD_MINB
 #define CPR2_FWD_MINB 4        // 64 registers, no spills: 4 x 224-thread CTAs per SM = 592 slots, so the 512 samples of the MNIST batch are ONE wave (3 per SM: 1.15 waves)
@@ -596,6 +597,11 @@ extern "C" int t4k_conv_pool_relu_fwd_feed(const uint8_t *u8I, const uint8_t *u8
 extern "C" int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,
                                       const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
                                       int KS, int S, int P, int train, t4k_stream_t s) {
+    return t4k_conv_pool_relu_bwd_opt(dY, actO, actF, poolO, convO, Iio, dXbuf, F, dF, dB, N, H1, W1, C1, H0, W0, C0, KS, S, P, train, nullptr, s);
+}
+extern "C" int t4k_conv_pool_relu_bwd_opt(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,
+                                          const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
+                                          int KS, int S, int P, int train, const t4k_fused_opt_t *opt, t4k_stream_t s) {
     if (!dY || !actO || !actF || !poolO || !convO || !Iio || !dXbuf || !F || N < 1 || (train && (!dF || !dB))) return T4K_EINVAL;
     int CM = 0; size_t smem = 0;
     // CTA width of the backward block: one thread per pool window (224 threads at 14x14 windows, 2 CTAs/SM at 126 registers:
@@ -604,8 +610,10 @@ extern "C" int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float 
     static int thr_env = -1;
     if (thr_env < 0) { const char *e = getenv("T4K_CPR2_BWD_THREADS"); thr_env = e ? atoi(e) : 0; if (thr_env < 32 || thr_env > 256 || (thr_env & 31)) thr_env = 0; }
     const int threads = thr_env ? thr_env : cpr2_bwd_threads((H0 / 2) * (W0 / 2));
-    if (!cpr2_bwd_ok(H1, W1, C1, H0, W0, C0, KS, S, P, &CM, &smem, threads))
+    if (!cpr2_bwd_ok(H1, W1, C1, H0, W0, C0, KS, S, P, &CM, &smem, threads)) {
+        if (opt) return T4K_ENOSUP;                       // the fused optimizer rides in this generation's finish launch only
         return cpr_v1_bwd(dY, actO, actF, poolO, convO, Iio, dXbuf, F, dF, dB, N, H1, W1, C1, H0, W0, C0, KS, S, P, train, STRM(s));
+    }
     const int nF = 9 * C0;
     Cpr2P p{}; p.F = F; p.dY = dY; p.actFc = actF; p.actO = actO; p.poolO = poolO; p.convO = convO; p.Iio = Iio; p.dXbuf = dXbuf;
     p.H = H1; p.W = W1; p.C1 = 1; p.C0 = C0; p.train = train;
@@ -615,5 +623,6 @@ extern "C" int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float 
                               launch_std(k_cpr2_bwd<CM_, EX_>, dim3(N), dim3(threads), smem, STRM(s), p); }
     if (CM == 10) { if (ex) CPR2B(10, true) else CPR2B(10, false) } else { if (ex) CPR2B(16, true) else CPR2B(16, false) }
     int rc = check_launch(); if (rc || !train) return rc;
+    if (opt) return wgrad_fin_opt_launch(p.part, dF, dB, nF, C0, N, KS, S, opt, STRM(s));
     return wgrad_fin_launch(p.part, dF, dB, nF, C0, N, KS, S, STRM(s));
 }

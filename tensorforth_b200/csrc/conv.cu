@@ -12,6 +12,7 @@
 //     the reference uses shared + global atomics, nmath.tcu:307-336).
 // dX uses the reference's 180-degree flipped filter taps (nmath.tcu:304) — replicated, not "fixed".
 #include "common.cuh"
+#include "optim.cuh"
 
 namespace t4k {
 
@@ -158,6 +159,28 @@ __host__ __device__ __forceinline__ int dconv_flush_mult(int KS, int S, int tap)
     int m = 0;
     for (int ty = 0; ty < 16; ty++) { const int tx = tap - ty * TS; if (tx >= 0 && tx < 16) m++; }
     return m;
+}
+// the same + the optimizer step on the finished element (t4k_fused_opt_t): the arithmetic of k_optim_multi on DG = dF / dB, then DG = 0
+struct WgOpt { bool mom; OptP p; float *G, *M, *V; int64_t offF, offB; float nwF, nwB; };
+template<int KIND>
+__global__ void __launch_bounds__(T4K_THREADS) k_wgrad_fin_opt(const float *__restrict__ part, float *dF, float *dB,
+                                                               int nF, int C0, int nparts, int KS, int S, WgOpt o) {
+    __shared__ float red[T4K_THREADS / 32];
+    pdl_wait(); pdl_trigger();
+    const int t = blockIdx.x;
+    float v = 0.0f;
+    for (int c = threadIdx.x; c < nparts; c += blockDim.x) v += part[(int64_t)c * (nF + C0) + t];
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) {
+        float dg, nw; int64_t j; float *d;
+        if (t < nF) { d = dF + t; dg = *d; dg += v * (float)dconv_flush_mult(KS, S, (t / C0) % (KS * KS)); j = o.offF + t; nw = o.nwF; }
+        else        { d = dB + (t - nF); dg = *d; dg += v; j = o.offB + (t - nF); nw = o.nwB; }
+        float g = o.G[j], m = 0.0f, vv = 0.0f;
+        if (KIND == 0) { dg = dg / nw; if (o.mom) m = o.M[j]; } else { m = o.M[j]; vv = o.V[j]; }
+        opt_step<KIND>(g, dg, m, vv, 1.0f, o.mom, o.p);
+        o.G[j] = g; *d = 0.0f;
+        if (KIND == 0) { if (o.mom) o.M[j] = m; } else { o.M[j] = m; o.V[j] = vv; }
+    }
 }
 // dF[t] += Σ_cta part[cta][t] (t < nF) ; dB[t-nF] += ... ; ordered → deterministic
 __global__ void __launch_bounds__(T4K_THREADS) k_wgrad_fin(const float *__restrict__ part, float *dF, float *dB,
@@ -674,6 +697,15 @@ int cpr_v1_bwd(const float *dY, float *actO, const float *actF, float *poolO, fl
     switch (KS) { case 1: CPRB(1) break; case 3: CPRB(3) break; case 4: CPRB(4) break; default: CPRB(5) break; }
     int rc = check_launch(); if (rc || !train) return rc;
     launch_pdl(k_wgrad_fin, dim3(nF + C0), dim3(T4K_THREADS), 0, s, p.part, dF, dB, nF, C0, N, KS, S);
+    return check_launch();
+}
+int wgrad_fin_opt_launch(const float *part, float *dF, float *dB, int nF, int C0, int nparts, int KS, int S, const t4k_fused_opt_t *opt, cudaStream_t st) {
+    if (!opt->G || opt->kind < 0 || opt->kind > 2 || (opt->kind && (!opt->M || !opt->V))) return T4K_EINVAL;
+    WgOpt o{!(fabsf(opt->b1) < DU_EPS), OptP{opt->lr, opt->b1, opt->b2, opt->wd}, opt->G, opt->M, opt->V, opt->offF, opt->offB, (float)opt->NwF, (float)opt->NwB};
+    if (opt->kind == 0 && o.mom && !opt->M) return T4K_EINVAL;
+    if (opt->kind == 0)      launch_pdl(k_wgrad_fin_opt<0>, dim3(nF + C0), dim3(T4K_THREADS), 0, st, part, dF, dB, nF, C0, nparts, KS, S, o);
+    else if (opt->kind == 1) launch_pdl(k_wgrad_fin_opt<1>, dim3(nF + C0), dim3(T4K_THREADS), 0, st, part, dF, dB, nF, C0, nparts, KS, S, o);
+    else                     launch_pdl(k_wgrad_fin_opt<2>, dim3(nF + C0), dim3(T4K_THREADS), 0, st, part, dF, dB, nF, C0, nparts, KS, S, o);
     return check_launch();
 }
 int wgrad_fin_launch(const float *part, float *dF, float *dB, int nF, int C0, int nparts, int KS, int S, cudaStream_t st) {

@@ -202,11 +202,11 @@ __global__ void __launch_bounds__(T4K_THREADS) k_optim(float *G, float *DG, floa
 template<int KIND>
 __global__ void __launch_bounds__(T4K_THREADS) k_optim_multi(float *G, float *DG, float *M, float *V,
                                                              const t4k_seg_t *__restrict__ seg, int nseg,
-                                                             int64_t total, bool mom, OptP p) {
+                                                             int64_t from, int64_t total, bool mom, OptP p) {
     pdl_wait(); pdl_trigger();                  // PDL: nothing global before this line
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t j = tid; j < total; j += nth) {
+    for (int64_t j = from + tid; j < total; j += nth) {
         float g = G[j], dg = DG[j], m = 0.0f, v = 0.0f;
         if (KIND == 0) {
             int lo = 0, hi = nseg - 1;                     // binary search the owning segment (nseg is tiny)
@@ -357,15 +357,19 @@ extern "C" int t4k_adamw(float *G, float *DG, float *M, float *V, float lr, floa
 }
 extern "C" int t4k_optim_multi(int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
                                int64_t total, float lr, float b1, float b2, float wd, t4k_stream_t s) {
-    if (!G || !DG || !seg || nseg < 1 || total < 0) return T4K_EINVAL;
-    if (total == 0) return 0;
+    return t4k_optim_multi_range(kind, G, DG, M, V, seg, nseg, 0, total, lr, b1, b2, wd, s);
+}
+extern "C" int t4k_optim_multi_range(int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
+                                     int64_t from, int64_t total, float lr, float b1, float b2, float wd, t4k_stream_t s) {
+    if (!G || !DG || !seg || nseg < 1 || from < 0 || total < from) return T4K_EINVAL;
+    if (total == from) return 0;
     OptP p{lr, b1, b2, wd};
-    const int g = stream_grid(total);
+    const int g = stream_grid(total - from);
     switch (kind) {
     case 0: { const bool mom = !(fabsf(b1) < DU_EPS); if (mom && !M) return T4K_EINVAL;
-              launch_pdl(k_optim_multi<0>, dim3(g), dim3(T4K_THREADS), 0, STRM(s), G, DG, M, V, seg, nseg, total, mom, p); } break;
-    case 1: if (!M || !V) return T4K_EINVAL; launch_pdl(k_optim_multi<1>, dim3(g), dim3(T4K_THREADS), 0, STRM(s), G, DG, M, V, seg, nseg, total, true, p); break;
-    case 2: if (!M || !V) return T4K_EINVAL; launch_pdl(k_optim_multi<2>, dim3(g), dim3(T4K_THREADS), 0, STRM(s), G, DG, M, V, seg, nseg, total, true, p); break;
+              launch_pdl(k_optim_multi<0>, dim3(g), dim3(T4K_THREADS), 0, STRM(s), G, DG, M, V, seg, nseg, from, total, mom, p); } break;
+    case 1: if (!M || !V) return T4K_EINVAL; launch_pdl(k_optim_multi<1>, dim3(g), dim3(T4K_THREADS), 0, STRM(s), G, DG, M, V, seg, nseg, from, total, true, p); break;
+    case 2: if (!M || !V) return T4K_EINVAL; launch_pdl(k_optim_multi<2>, dim3(g), dim3(T4K_THREADS), 0, STRM(s), G, DG, M, V, seg, nseg, from, total, true, p); break;
     default: return T4K_EINVAL;
     }
     return check_launch();

@@ -6,24 +6,30 @@
 //   and the activation backward (backprop.cu:257-263) fused in.
 //
 // What is different from gemm_tcf.cu (whose ~10 us of fixed cost made it tie with the FP32-FMA kernel at these sizes):
-//   * operands arrive by TMA (cp.async.bulk.tensor.2d of the RAW FP32 tiles, SWIZZLE_128B, out-of-range rows/cols/k zero filled by
-//     the TMA unit): one elected thread keeps a whole ring (3 x 32 KiB) in flight, nothing is staged through registers;
+//   * operands arrive by TMA (cp.async.bulk.tensor.2d of the RAW FP32 tiles, out-of-range rows/cols/k zero filled by the TMA unit): one
+//     elected thread keeps a ring of FOUR k-blocks (4 x 32 KiB) in flight, nothing is staged through registers;
 //   * ANY transposition is native: an operand that is contiguous along M/N is loaded as [k][32 x m] boxes and handed to the tensor
 //     core as an MN-major UMMA operand (instruction-descriptor bits 15/16; 32-bit MN-major operands use the SWIZZLE_128B_BASE32B
 //     layout = TMA's 128B_ATOM_32B swizzle: LBO = 4 KiB between 32-wide m blocks, SBO = 512 B between 4-row k groups) — dW (both
 //     operands MN-major) and dX (B MN-major) no longer pay scattered 4-byte shared stores;
 //   * the raw FP32 plane IS the hi operand: kind::tf32 reads the upper 19 bits of each word (the 13 low mantissa bits are ignored:
-//     hi = truncate(a)); eight converter warps only derive the lo plane, lo = tf32(a - hi), elementwise on the swizzled image
-//     (same offset in a second plane, whatever the layout); product = lo*hi + hi*lo + hi*hi with FP32 accumulation in TMEM;
-//   * split-K lives in a THREAD-BLOCK CLUSTER (1 x 1 x S, S <= 16): every CTA parks its accumulator tile in its own shared memory and
-//     CTA r reduces rows [r*128/S, (r+1)*128/S) of all S tiles in rank order over distributed shared memory — no partials in HBM, no
-//     finish launch, deterministic — and applies the epilogue there, a warp per output row:
+//     hi = truncate(a), verified bit-for-bit on the device); six converter warps only derive the lo plane, lo = tf32(a - hi), elementwise on
+//     the swizzled image (same offset in a second ring of TWO slots, whatever the layout); product = lo*hi + hi*lo + hi*hi, FP32 in TMEM;
+//   * an operand can be GENERATED instead of loaded: A = ((P - T) @ W2) * F — the classifier head's backward (Model::_bprep, the small
+//     linear's dX and the activation backward, backprop.cu:76-140,194-263) evaluated by the converter warps, K-major (the dX GEMM of the
+//     hidden layer) or MN-major (its dW GEMM): neither waits for a head-backward kernel any more;
+//   * split-K lives in a THREAD-BLOCK CLUSTER (S <= 16 CTAs): every CTA parks its accumulator tile in shared memory, writes it to an
+//     L2-resident workspace, and after the cluster barrier CTA r adds rows [r*128/S, (r+1)*128/S) of the S tiles in rank order —
+//     deterministic, no finish launch — and applies the epilogue there, a warp per output row:
 //       mode 0  O = alpha * acc + beta * O                                  (Tensor::mm / gemm words, dW with beta = 1)
 //       mode 1  Y = acc + bias ; A = act(Y) ; F = saved derivative / mask   (Model::_flinear + _factivate)
 //       mode 2  mode 1, then Y2 = A @ W2^T + B2 ; P = softmax(Y2) (+ dup)   (... + the classifier head: the row never leaves the warp)
 //       mode 3  O = acc ; O2 = acc * F                                      (Model::_blinear's dX + the _bactivate in front of it)
-// Bound: launch + one HBM/L2 round trip + a handful of MMAs; at the largest layer shapes (0.8 GFLOP) shared-memory bandwidth
-// (operand reads of the SS MMAs + the lo pass).
+//   * TWO problems can share one launch (dW and dX of a layer when X has a duplicate): a cluster is either the K-split of one tile or S
+//     independent tiles, so both fill the machine together instead of queueing behind each other (this kernel owns its SM: 512 threads x
+//     128 registers, 225 KiB of shared memory — nothing else is co-resident).
+// Measured timeline of a CTA (profiles/r02_tl_trace.txt): set-up 0.4 us, first tile landed at 1.2 us, 0.65 us per k-block (shared-memory
+// bound: the lo pass and the operand reads of the SS MMAs), reduction 3.5 us.
 #include "tc_ptx.cuh"
 #include "act.cuh"
 #include <cuda.h>
@@ -33,36 +39,41 @@ namespace t4k {
 
 constexpr int L_BM = 128, L_BN = 128, L_BK = 32, L_UK = 8;
 constexpr uint32_t L_PLANE_B = 128u * L_BK * 4u;         // 16 KiB: one raw (= hi) or lo plane of a 128 x 32 operand tile
-constexpr uint32_t L_OP_B = 2u * L_PLANE_B;              // raw + lo
-constexpr uint32_t L_STAGE_B = 2u * L_OP_B;              // A + B = 64 KiB
-constexpr int L_STAGES = 3;
+constexpr uint32_t L_SLOT_B = 2u * L_PLANE_B;            // A plane + B plane = 32 KiB: one slot of the raw ring or of the lo ring
+constexpr int L_RAW = 4, L_LO = 2;                       // ring depths: raw tiles in flight / lo planes
+constexpr uint32_t L_RING_B = (L_RAW + L_LO) * L_SLOT_B; // 192 KiB
 constexpr int L_DRAIN_KB = 8;                            // k-blocks per accumulator chain (gemm_tc.cu: DRAIN_KB)
 constexpr int L_NCONV = 6, L_NEPI = 8;                   // 16 warps: register files are granted per 4 warps, 512 threads leave 128 registers each
 constexpr int L_WARPS = 2 + L_NCONV + L_NEPI;            // 16
 constexpr int L_THREADS = L_WARPS * 32;                  // 512
 constexpr int L_CONV_T = L_NCONV * 32;                   // 192 converter threads
 constexpr int L_W2_FLTS = 32 * 128;                      // head weights [E2 <= 32][EH <= 128] in shared memory (mode 2, generated A)
-constexpr int L_D_FLTS = 128 * 32;                       // generated A: p - y rows of the tile [128][E2 <= 32]
+constexpr int L_D_FLTS = 128 * 32;                       // generated A: p - y rows [128][E2 <= 32]
+constexpr int L_NBAR = 2 * L_RAW + 2 * L_LO + 4;         // raw_full, raw_empty, lo_full, lo_empty, acc_full[2], acc_empty[2]
 
 struct TlP {
     float *O; float alpha, beta;
     int M, N, K;
-    int KT, kt_per;              // k-blocks of 32: total, per cluster rank
+    int KT, kt_per, split;       // k-blocks of 32: total, per rank; ranks per tile (1 or the cluster size)
+    int mtiles, ntiles;
     int a_mn, b_mn;              // operand is contiguous along M / N in memory (tA / !tB)
-    int mask_hi;                 // debug: store the masked hi back over the raw plane (does not rely on the MMA ignoring the low bits)
-    uint32_t mn_type, mn_lbo, mn_sbo, mn_kstep;      // MN-major operand descriptor: layout type, LBO / SBO / start-address step per 8 k (bytes)
     int mode;
     const float *bias; float *actA, *actF; int layer; float act_alpha;          // mode 1, 2
     const float *W2, *B2; float *Y2, *P, *P2; int E2;                          // mode 2
     const float *F; float *O2;                                                  // mode 3
-    // generated A operand (gen != 0; A is K-major [M][K], K <= 128): A[m][k] = (Σ_j (gP[m][j] - gT[m][j]) * gW2[j][k]) * gF[m][k] — the classifier
-    // head's backward (Model::_bprep + the small linear's dX + the activation backward, backprop.cu:76-140,194-263) evaluated in the
-    // converter warps instead of being loaded: the dX GEMM of the hidden linear layer no longer waits for a head-backward kernel
+    // generated A operand (gen 1: K-major [M][K], K <= 128; gen 2: M-major, A(m,k) = the same matrix transposed, M <= 128):
+    //   dY1[n][e] = (Σ_j (gP[n][j] - gT[n][j]) * gW2[j][e]) * gF[n][e];  gen 1: A[m=n][k=e];  gen 2: A[m=e][k=n]
     int gen, gE2; const float *gP, *gT, *gW2, *gF;
-    float *part;                 // split-K partials [cluster][rank][128][128] in the library workspace (L2-resident); nullptr: reduce over distributed shared memory
-    long long *trace;            // bring-up: clock64 stamps of CTA (0,0,0)'s phases (t4k_gemm_tl_trace), nullptr in production
+    float *part;                 // split-K partials [tile][rank][128][128] in the library workspace (L2-resident); nullptr: reduce over distributed shared memory
 };
-#define TL_TRACE(ev) do { if (p.trace && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) p.trace[ev] = clock64(); } while (0)
+struct TlG {
+    TlP p[2];
+    int ncl0;                    // clusters of problem 0 (the rest run problem 1)
+    int mask_hi;                 // debug: store the masked hi back over the raw plane (does not rely on the MMA ignoring the low bits)
+    uint32_t mn_type, mn_lbo, mn_sbo, mn_kstep;      // MN-major operand descriptor: layout type, LBO / SBO / start-address step per 8 k (bytes)
+    long long *trace;            // bring-up: clock64 stamps of CTA 0's phases (t4k_gemm_tl_trace), nullptr in production
+};
+#define TL_TRACE(ev) do { if (g.trace && blockIdx.x == 0) g.trace[ev] = clock64(); } while (0)
 
 __device__ __forceinline__ void tl_tma_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -78,7 +89,7 @@ __device__ __forceinline__ float4 tl_ld_dsmem4(uint32_t local_saddr, uint32_t ra
     asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(r) : "memory");
     return v;
 }
-// parked accumulator tile [128 rows][128 cols] fp32 over the (idle) operand ring: 16-byte chunk c4 of row r lives at chunk (c4 ^ (r & 31)):
+// parked accumulator tile [128 rows][128 cols] fp32 over the (idle) raw ring: 16-byte chunk c4 of row r lives at chunk (c4 ^ (r & 31)):
 // the epilogue warps' per-row float4 stores (lanes = rows) and the reduction's per-row reads (lanes = chunks) are both conflict-free
 __device__ __forceinline__ int tl_park_off(int row, int c4) { return row * L_BN + ((c4 ^ (row & 31)) << 2); }
 
@@ -88,8 +99,8 @@ __device__ __forceinline__ int tl_park_off(int row, int c4) { return row * L_BN 
 //   MN-major: 32-bit operands have ONE legal layout, SWIZZLE_128B_BASE32B (type 1: 32-byte chunks XOR row & 3 — the TMA mode
 //             CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B (32 tf32 along m/n) at one k, 4 k-rows = one 512 B atom (SBO = 512 B
 //             between k groups), 32-wide m/n blocks LBO = 4 KiB apart (one TMA box of 32 k-rows); a k-step of 8 = two atoms = 1024 B
-__device__ __forceinline__ uint64_t tl_desc(uint32_t saddr, bool mn, const TlP &p) {
-    const uint64_t lbo = mn ? (p.mn_lbo >> 4) : 1u, sbo = mn ? (p.mn_sbo >> 4) : (1024u >> 4), type = mn ? p.mn_type : 2u;
+__device__ __forceinline__ uint64_t tl_desc(uint32_t saddr, bool mn, const TlG &g) {
+    const uint64_t lbo = mn ? (g.mn_lbo >> 4) : 1u, sbo = mn ? (g.mn_sbo >> 4) : (1024u >> 4), type = mn ? g.mn_type : 2u;
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (type << 61);
 }
 
@@ -123,68 +134,88 @@ __device__ __forceinline__ float tl_treduce32(float (&v)[32], int lane) {
     return v[0];
 }
 
-__global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap) {
+__global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const __grid_constant__ TlG g,
+                                                          const __grid_constant__ CUtensorMap amap0, const __grid_constant__ CUtensorMap bmap0,
+                                                          const __grid_constant__ CUtensorMap amap1, const __grid_constant__ CUtensorMap bmap1) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // SWIZZLE_128B tiles: 1024-byte aligned
-    uint64_t *bars = (uint64_t*)(smem + L_STAGES * L_STAGE_B);                        // raw_full[S], lo_full[S], empty[S], acc_full[2], acc_empty[2]
-    uint32_t *tmem_slot = (uint32_t*)(bars + 3 * L_STAGES + 4);
-    float *sW2 = reinterpret_cast<float*>(smem + L_STAGES * L_STAGE_B + 256);         // mode 2 / generated A: head weights
+    uint8_t *smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // swizzled tiles: 1024-byte aligned
+    uint8_t *lo_ring = smem + L_RAW * L_SLOT_B;
+    uint64_t *bars = (uint64_t*)(smem + L_RING_B);
+    uint32_t *tmem_slot = (uint32_t*)(bars + L_NBAR);
+    float *sW2 = reinterpret_cast<float*>(smem + L_RING_B + 256);                     // mode 2 / generated A: head weights
     float *sD = sW2 + L_W2_FLTS;                                                      // generated A: p - y
     pdl_wait(); pdl_trigger();
     if (threadIdx.x == 0) TL_TRACE(0);
 
+    // ---- which problem, which tile, which k range: cluster `cl` is the K-split of ONE tile (split == S) or S tiles side by side (split == 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt = blockIdx.y, nt = blockIdx.x, zs = blockIdx.z, S = (int)gridDim.z;
+    uint32_t S, rk;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(S));
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rk));
+    const int cl = (int)(blockIdx.x / S);
+    const bool second = cl >= g.ncl0;
+    const TlP &p = g.p[second ? 1 : 0];
+    const CUtensorMap *amap = second ? &amap1 : &amap0, *bmap = second ? &bmap1 : &bmap0;
+    const int split = p.split, tpc = (int)S / split;                                  // tiles per cluster
+    const int tile = (second ? cl - g.ncl0 : cl) * tpc + (int)rk / split;
+    const int zs = (int)rk % split, rk0 = (int)rk - zs;                               // rank inside the tile's group, first cluster rank of the group
+    const bool active = tile < p.mtiles * p.ntiles;
+    const int mt = active ? tile / p.ntiles : 0, nt = active ? tile % p.ntiles : 0;
     const int kt0 = zs * p.kt_per;
     const int kt1 = min(p.KT, kt0 + p.kt_per);
-    const int nkb = max(0, kt1 - kt0);
+    const int nkb = active ? max(0, kt1 - kt0) : 0;
     const int nchunk = (nkb + L_DRAIN_KB - 1) / L_DRAIN_KB;
-    const uint32_t raw0 = smem_u32(bars), lo0 = smem_u32(bars + L_STAGES), empty0 = smem_u32(bars + 2 * L_STAGES);
-    const uint32_t afull0 = smem_u32(bars + 3 * L_STAGES), aempty0 = smem_u32(bars + 3 * L_STAGES + 2);
+    const uint32_t rawf0 = smem_u32(bars), rawe0 = rawf0 + 8 * L_RAW, lof0 = rawe0 + 8 * L_RAW, loe0 = lof0 + 8 * L_LO;
+    const uint32_t afull0 = loe0 + 8 * L_LO, aempty0 = afull0 + 16;
+    const int gen = active ? p.gen : 0;
 
-    // one k-block's TMA loads (raw FP32 tiles) into stage s; complete on raw_full[s]
+    // one k-block's TMA loads (raw FP32 tiles) into raw slot i % L_RAW; complete on raw_full
     auto tma_issue = [&](int i) {
-        const int s = i % L_STAGES;
-        const uint32_t sa = smem_u32(smem + (size_t)s * L_STAGE_B), sb = sa + L_OP_B, bar = raw0 + 8 * s;
+        const int s = i % L_RAW;
+        const uint32_t sa = smem_u32(smem + (size_t)s * L_SLOT_B), sb = sa + L_PLANE_B, bar = rawf0 + 8 * s;
         const int m0 = mt * L_BM, n0 = nt * L_BN, k0 = (kt0 + i) * L_BK;
-        mbar_expect_tx(bar, p.gen ? L_PLANE_B : 2 * L_PLANE_B);
+        mbar_expect_tx(bar, gen ? L_PLANE_B : 2 * L_PLANE_B);
         if (i == 0) TL_TRACE(2);
         if (i == nkb - 1) TL_TRACE(6);
-        if (p.gen) { /* A is written by the converter warps */ }
-        else if (!p.a_mn) tl_tma_2d(sa, &amap, k0, m0, bar);                          // box {32 k, 128 rows}
+        if (gen) { /* A is written by the converter warps */ }
+        else if (!p.a_mn) tl_tma_2d(sa, amap, k0, m0, bar);                           // box {32 k, 128 rows}
         else {
             #pragma unroll
-            for (int j = 0; j < 4; j++) tl_tma_2d(sa + j * 4096u, &amap, m0 + 32 * j, k0, bar);              // box {32 m, 32 k}
+            for (int j = 0; j < 4; j++) tl_tma_2d(sa + j * 4096u, amap, m0 + 32 * j, k0, bar);               // box {32 m, 32 k}
         }
-        if (!p.b_mn) tl_tma_2d(sb, &bmap, k0, n0, bar);
+        if (!p.b_mn) tl_tma_2d(sb, bmap, k0, n0, bar);
         else {
             #pragma unroll
-            for (int j = 0; j < 4; j++) tl_tma_2d(sb + j * 4096u, &bmap, n0 + 32 * j, k0, bar);
+            for (int j = 0; j < 4; j++) tl_tma_2d(sb + j * 4096u, bmap, n0 + 32 * j, k0, bar);
         }
     };
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" :: "l"(&amap) : "memory");
-        asm volatile("prefetch.tensormap [%0];" :: "l"(&bmap) : "memory");
-        for (int s = 0; s < L_STAGES; s++) { mbar_init(raw0 + 8 * s, 1); mbar_init(lo0 + 8 * s, L_NCONV); mbar_init(empty0 + 8 * s, 1); }
+        asm volatile("prefetch.tensormap [%0];" :: "l"(amap) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(bmap) : "memory");
+        for (int s = 0; s < L_RAW; s++) { mbar_init(rawf0 + 8 * s, 1); mbar_init(rawe0 + 8 * s, 1); }
+        for (int s = 0; s < L_LO; s++) { mbar_init(lof0 + 8 * s, L_NCONV); mbar_init(loe0 + 8 * s, 1); }
         for (int b = 0; b < 2; b++) { mbar_init(afull0 + 8 * b, 1); mbar_init(aempty0 + 8 * b, L_NEPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // the first ring of loads leaves before the set-up barrier (TMEM allocation, head weights): their latency overlaps it
-        for (int i = 0; i < nkb && i < L_STAGES; i++) tma_issue(i);
+        for (int i = 0; i < nkb && i < L_RAW; i++) tma_issue(i);
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * L_BN);                         // two accumulators of 128 fp32 columns
-    if (p.mode == 2 && warp >= 2) {                                                   // head weights: asynchronous copies, published by the barrier in front of the reduction
+    if (active && p.mode == 2 && warp >= 2) {                                         // head weights: asynchronous copies, published by the barrier in front of the reduction
         const int EH = p.N, tot = p.E2 * EH;
         for (int t = threadIdx.x - 64; t < tot; t += L_THREADS - 64) cp_async4(sW2 + t, p.W2 + t, true);
         cp_async_commit();
     }
-    if (p.gen && warp >= 2) {                                                         // generated A: W2 [E2][K] and d = p - y of the tile's rows
-        const int tot = p.gE2 * p.K;
+    // generated A: dY1 = ((P - T) @ W2) * F with dY1 [Ng][EHg]; gen 1: A rows = dY1 rows of this M tile; gen 2: A(m,k) = dY1[k][m], rows of this k range
+    const int EHg = (gen == 2) ? p.M : p.K, Ng = (gen == 2) ? p.K : p.M;
+    const int drow0 = (gen == 2) ? kt0 * L_BK : mt * L_BM;                            // first dY1 row held in sD
+    if (gen && warp >= 2) {
+        const int tot = p.gE2 * EHg;
         for (int t = threadIdx.x - 64; t < tot; t += L_THREADS - 64) cp_async4(sW2 + t, p.gW2 + t, true);
         cp_async_commit();
-        const int nd = L_BM * p.gE2, m0 = blockIdx.y * L_BM;
+        const int nd = L_BM * p.gE2;
         for (int t = threadIdx.x - 64; t < nd; t += L_THREADS - 64) {
-            const int r = t / p.gE2, j = t - r * p.gE2, gr = m0 + r;
-            sD[t] = (gr < p.M) ? __fsub_rn(__ldg(p.gP + (int64_t)gr * p.gE2 + j), __ldg(p.gT + (int64_t)gr * p.gE2 + j)) : 0.0f;
+            const int r = t / p.gE2, j = t - r * p.gE2, gr = drow0 + r;
+            sD[t] = (gr < Ng) ? __fsub_rn(__ldg(p.gP + (int64_t)gr * p.gE2 + j), __ldg(p.gT + (int64_t)gr * p.gE2 + j)) : 0.0f;
         }
         cp_async_wait_all();
     }
@@ -195,11 +226,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
     if (threadIdx.x == 0) TL_TRACE(1);
 
     if (warp == 0) {
-        // ===== TMA producer: raw FP32 tiles, the whole ring in flight =====
+        // ===== TMA producer: raw FP32 tiles, four k-blocks in flight =====
         if (lane == 0) {
-            for (int i = L_STAGES; i < nkb; i++) {
-                const int s = i % L_STAGES, it = i / L_STAGES;
-                mbar_wait(empty0 + 8 * s, (it & 1) ^ 1);
+            for (int i = L_RAW; i < nkb; i++) {
+                mbar_wait(rawe0 + 8 * (i % L_RAW), ((i / L_RAW) & 1) ^ 1);
                 tma_issue(i);
             }
         }
@@ -208,21 +238,22 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
         int nv = p.N - nt * L_BN; if (nv > L_BN) nv = L_BN;
         const int un = (nv + 15) & ~15;                                               // UMMA N: the valid columns of this tile, rounded to 16
         const uint32_t idesc = idesc_tf32(L_BM, un) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) | ((uint32_t)(p.b_mn ? 1 : 0) << 16);
-        const uint64_t ka = p.a_mn ? (p.mn_kstep >> 4) : (32u >> 4), kb = p.b_mn ? (p.mn_kstep >> 4) : (32u >> 4);      // start-address step per 8 k
+        const uint64_t ka = p.a_mn ? (g.mn_kstep >> 4) : (32u >> 4), kb = p.b_mn ? (g.mn_kstep >> 4) : (32u >> 4);       // start-address step per 8 k
         for (int i = 0; i < nkb; i++) {
-            const int s = i % L_STAGES, it = i / L_STAGES;
+            const int s = i % L_RAW, sl = i % L_LO;
             const int c = i / L_DRAIN_KB, ib = i % L_DRAIN_KB, b = c & 1;
             if (ib == 0 && c >= 2) { mbar_wait(aempty0 + 8 * b, ((c >> 1) - 1) & 1); tc_fence_after(); }      // chunk c-2 drained
-            mbar_wait(raw0 + 8 * s, it & 1);
-            mbar_wait(lo0 + 8 * s, it & 1);
+            mbar_wait(rawf0 + 8 * s, (i / L_RAW) & 1);
+            mbar_wait(lof0 + 8 * sl, (i / L_LO) & 1);
             tc_fence_after();
             if (lane == 0 && i == 0) TL_TRACE(5);
             if (lane == 0 && i == nkb - 1) TL_TRACE(8);
             if (elect_one()) {
                 const uint32_t acc = tmem_base + (uint32_t)(b * L_BN);
-                const uint32_t sa = smem_u32(smem + (size_t)s * L_STAGE_B), sb = sa + L_OP_B;
-                const uint64_t a_hi = tl_desc(sa, p.a_mn, p), a_lo = tl_desc(sa + L_PLANE_B, p.a_mn, p);
-                const uint64_t b_hi = tl_desc(sb, p.b_mn, p), b_lo = tl_desc(sb + L_PLANE_B, p.b_mn, p);
+                const uint32_t sa = smem_u32(smem + (size_t)s * L_SLOT_B), sb = sa + L_PLANE_B;
+                const uint32_t la = smem_u32(lo_ring + (size_t)sl * L_SLOT_B), lb = la + L_PLANE_B;
+                const uint64_t a_hi = tl_desc(sa, p.a_mn, g), a_lo = tl_desc(la, p.a_mn, g);
+                const uint64_t b_hi = tl_desc(sb, p.b_mn, g), b_lo = tl_desc(lb, p.b_mn, g);
                 #pragma unroll
                 for (int k = 0; k < L_BK / L_UK; k++) {
                     tc_mma_tf32(acc, a_lo + k * ka, b_hi + k * kb, idesc, (ib | k) ? 1u : 0u);
@@ -232,60 +263,75 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
             }
             __syncwarp();
             if (elect_one()) {
-                tc_commit(empty0 + 8 * s);
+                tc_commit(rawe0 + 8 * s);
+                tc_commit(loe0 + 8 * sl);
                 if (ib == L_DRAIN_KB - 1 || i == nkb - 1) tc_commit(afull0 + 8 * b);
             }
             __syncwarp();
         }
     } else if (warp < 2 + L_NCONV) {
-        // ===== converters: lo = tf32(a - truncate(a)) on the swizzled image, same offset in the second plane =====
+        // ===== converters: lo = tf32(a - truncate(a)) on the swizzled image, same offset in the lo ring; generated A tiles =====
         const int t = threadIdx.x - 64;                                               // 0..191
-        constexpr int NV = (2048 + L_CONV_T - 1) / L_CONV_T;                           // 16-byte words of a stage's two raw planes per thread (11)
+        constexpr int NV = (2048 + L_CONV_T - 1) / L_CONV_T;                           // 16-byte words of a k-block's two raw planes per thread (11)
         for (int i = 0; i < nkb; i++) {
-            const int s = i % L_STAGES, it = i / L_STAGES;
-            if (p.gen) {
-                // the A tile of this k-block, computed: thread -> (row, 16-byte chunk); 8 threads write one 128-byte row (swizzled: conflict-free)
-                mbar_wait(empty0 + 8 * s, (it & 1) ^ 1);                              // the stage's previous MMAs are done
-                uint8_t *abase = smem + (size_t)s * L_STAGE_B;
-                const int k0 = (kt0 + i) * L_BK, c = t & 7, k = k0 + 4 * c, E2 = p.gE2, EH = p.K;
-                #pragma unroll 1
-                for (int r = t >> 3; r < L_BM; r += L_CONV_T / 8) {
-                    const int gr = mt * L_BM + r;
-                    float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                    if (gr < p.M && k < EH) {                                         // EH % 4 == 0 (host check): whole chunks
-                        for (int j = 0; j < E2; j++) {                                // class order as k_head_bwd: the same bits as the stored dY1
-                            const float dj = sD[r * E2 + j];
-                            const float4 w = *reinterpret_cast<const float4*>(sW2 + j * EH + k);
+            const int s = i % L_RAW, sl = i % L_LO;
+            uint8_t *rbase = smem + (size_t)s * L_SLOT_B, *lbase = lo_ring + (size_t)sl * L_SLOT_B;
+            mbar_wait(loe0 + 8 * sl, ((i / L_LO) & 1) ^ 1);                           // the lo slot's previous MMAs are done
+            if (gen) {
+                mbar_wait(rawe0 + 8 * s, ((i / L_RAW) & 1) ^ 1);                      // ... and the raw slot's
+                const int E2 = p.gE2;
+                auto dy1 = [&](int dr, int gr, int e0, float (&x)[4]) {               // dY1[gr][e0 .. e0+3]; dr = row in sD.  Class order as k_head_bwd: the same bits
+                    x[0] = x[1] = x[2] = x[3] = 0.0f;
+                    if (gr < Ng && e0 < EHg) {                                        // EHg % 4 == 0 (host check): whole chunks
+                        for (int j = 0; j < E2; j++) {
+                            const float dj = sD[dr * E2 + j];
+                            const float4 w = *reinterpret_cast<const float4*>(sW2 + j * EHg + e0);
                             x[0] = fmaf(dj, w.x, x[0]); x[1] = fmaf(dj, w.y, x[1]); x[2] = fmaf(dj, w.z, x[2]); x[3] = fmaf(dj, w.w, x[3]);
                         }
                         if (p.gF) {
-                            const float4 f = ldg4(p.gF + (int64_t)gr * EH + k);
+                            const float4 f = ldg4(p.gF + (int64_t)gr * EHg + e0);
                             x[0] = __fmul_rn(x[0], f.x); x[1] = __fmul_rn(x[1], f.y); x[2] = __fmul_rn(x[2], f.z); x[3] = __fmul_rn(x[3], f.w);
                         }
                     }
-                    float hi[4], lo[4];
+                };
+                auto put = [&](uint32_t off, const float (&x)[4]) {
+                    float lo[4];
                     #pragma unroll
-                    for (int e = 0; e < 4; e++) { hi[e] = __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u); lo[e] = to_tf32(x[e] - hi[e]); }
-                    uint8_t *q = abase + (size_t)r * 128 + (size_t)((c ^ (r & 7)) << 4);
-                    *reinterpret_cast<float4*>(q) = make_float4(x[0], x[1], x[2], x[3]);
-                    *reinterpret_cast<float4*>(q + L_PLANE_B) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    for (int e = 0; e < 4; e++) lo[e] = to_tf32(x[e] - __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u));
+                    *reinterpret_cast<float4*>(rbase + off) = make_float4(x[0], x[1], x[2], x[3]);
+                    *reinterpret_cast<float4*>(lbase + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                };
+                if (gen == 1) {
+                    // K-major tile [128 rows = samples][32 k = hidden units]: thread -> (row, 16-byte chunk); 8 threads write one swizzled 128-byte row
+                    const int c = t & 7, e0 = (kt0 + i) * L_BK + 4 * c;
+                    #pragma unroll 1
+                    for (int r = t >> 3; r < L_BM; r += L_CONV_T / 8) {
+                        float x[4]; dy1(r, mt * L_BM + r, e0, x);
+                        put((uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4), x);
+                    }
+                } else {
+                    // M-major tile: 32 k-rows (samples) x 4 blocks of 32 m (hidden units); 16-byte chunk cc of a row sits in 32-byte chunk (cc >> 1) ^ (row & 3)
+                    #pragma unroll 1
+                    for (int idx = t; idx < 1024; idx += L_CONV_T) {
+                        const int row = idx >> 5, c = idx & 31, j = c >> 3, cc = c & 7;
+                        float x[4]; dy1(i * L_BK + row, (kt0 + i) * L_BK + row, 4 * c, x);
+                        put((uint32_t)j * 4096u + (uint32_t)row * 128u + (uint32_t)((((cc >> 1) ^ (row & 3)) << 5) | ((cc & 1) << 4)), x);
+                    }
                 }
             }
-            mbar_wait(raw0 + 8 * s, it & 1);
+            mbar_wait(rawf0 + 8 * s, (i / L_RAW) & 1);
             if (t == 0 && i == 0) TL_TRACE(3);
             if (t == 0 && i == nkb - 1) TL_TRACE(7);
-            uint8_t *base = smem + (size_t)s * L_STAGE_B;
             float4 v[NV];
             #pragma unroll
             for (int j = 0; j < NV; j++) {
-                const int idx = t + L_CONV_T * j + (p.gen ? 1024 : 0);                 // generated A: only the B planes are converted
-                if (idx < 2048) v[j] = *reinterpret_cast<const float4*>(base + (size_t)(idx >> 10) * L_OP_B + (size_t)(idx & 1023) * 16);
+                const int idx = t + L_CONV_T * j + (gen ? 1024 : 0);                  // generated A: only the B plane is converted
+                if (idx < 2048) v[j] = *reinterpret_cast<const float4*>(rbase + (size_t)idx * 16);
             }
             #pragma unroll
             for (int j = 0; j < NV; j++) {
-                const int idx = t + L_CONV_T * j + (p.gen ? 1024 : 0);
+                const int idx = t + L_CONV_T * j + (gen ? 1024 : 0);
                 if (idx >= 2048) break;
-                uint8_t *q = base + (size_t)(idx >> 10) * L_OP_B + (size_t)(idx & 1023) * 16;
                 const float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
                 float hi[4], lo[4];
                 #pragma unroll
@@ -293,12 +339,12 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
                     hi[e] = __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u);
                     lo[e] = to_tf32(x[e] - hi[e]);
                 }
-                *reinterpret_cast<float4*>(q + L_PLANE_B) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                if (p.mask_hi) *reinterpret_cast<float4*>(q) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(lbase + (size_t)idx * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                if (g.mask_hi) *reinterpret_cast<float4*>(rbase + (size_t)idx * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
             }
             tl_fence_proxy_async();                      // generic-proxy stores → visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(lo0 + 8 * s);
+            if (lane == 0) mbar_arrive(lof0 + 8 * sl);
             if (t == 0 && i == 0) TL_TRACE(4);
         }
     } else {
@@ -325,7 +371,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
             __syncwarp();
             if (lane == 0) mbar_arrive(aempty0 + 8 * b);
         }
-        // the operand ring is idle: the last accumulator commit covers every MMA that read it, every TMA write was consumed
+        // the raw ring is idle: the last accumulator commit covers every MMA that read it, every TMA write was consumed
         float *park = reinterpret_cast<float*>(smem);
         const int r = q * 32 + lane;
         #pragma unroll
@@ -333,15 +379,15 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
             *reinterpret_cast<float4*>(park + tl_park_off(r, (h * CW + j) >> 2)) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         if (warp == 2 + L_NCONV && lane == 0) TL_TRACE(10);
     }
-    if (p.mode == 2) cp_async_wait_all();
+    if (active && p.mode == 2) cp_async_wait_all();
     tc_fence_before();
     __syncthreads();
-    // split-K partials through L2 (default): distributed shared memory serves ~20 B/clk per SM — 60 KiB of peer tiles cost 1.6 us and every CTA
-    // has to stay resident until its last reader is done (measured, profiles/r02_tl_trace.txt); the L2 takes the same bytes at 3x the rate
-    // and nobody waits at the exit.  The tile goes out coalesced (a warp per row), the cluster barrier (release/acquire) publishes it.
+    // split-K partials through L2: distributed shared memory serves ~20 B/clk per SM (60 KiB of peer tiles: 2 us) and keeps every CTA resident
+    // until its last reader is done; the L2 path costs about the same for the reader and lets everybody leave early.  The tile goes out
+    // coalesced (a warp per row), the cluster barrier (release/acquire) publishes it.
     float *mypart = nullptr;
-    if (S > 1 && p.part) {
-        mypart = p.part + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * S) * (size_t)(L_BM * L_BN);
+    if (active && split > 1 && p.part) {
+        mypart = p.part + (size_t)tile * split * (size_t)(L_BM * L_BN);
         const float *park = reinterpret_cast<const float*>(smem);
         float *dst = mypart + (size_t)zs * (L_BM * L_BN);
         const int rows = min(L_BM, p.M - mt * L_BM);
@@ -352,9 +398,9 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
     if (S > 1) tl_cluster_sync();                                                     // every CTA's tile is parked / stored and visible cluster-wide
     if (threadIdx.x == 0) TL_TRACE(11);
 
-    // ===== reduction over the cluster + epilogue: CTA `zs` finishes rows [zs*rpr, (zs+1)*rpr) of the tile, a warp per row, lane = 16-byte chunk =====
-    {
-        const int rpr = L_BM / S;
+    // ===== reduction over the tile's ranks + epilogue: rank `zs` finishes rows [zs*rpr, (zs+1)*rpr) of the tile, a warp per row, lane = 16-byte chunk =====
+    if (active) {
+        const int rpr = L_BM / split;
         const uint32_t park_s = smem_u32(smem);
         const float *park = reinterpret_cast<const float*>(smem);
         const int gc = nt * L_BN + lane * 4;
@@ -363,22 +409,22 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
             const int r = zs * rpr + rr, gr = mt * L_BM + r;
             if (gr >= p.M) break;                                                     // rows ascend with rr
             float4 sum;
-            if (S == 1) sum = *reinterpret_cast<const float4*>(park + tl_park_off(r, lane));
+            if (split == 1) sum = *reinterpret_cast<const float4*>(park + tl_park_off(r, lane));
             else {
                 float4 v[16];
                 if (mypart) {
                     const float *src = mypart + r * L_BN + lane * 4;
                     const bool ld = gc < p.N;
                     #pragma unroll
-                    for (int qk = 0; qk < 16; qk++) if (qk < S) v[qk] = ld ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)qk * (L_BM * L_BN))) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int qk = 0; qk < 16; qk++) if (qk < split) v[qk] = ld ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)qk * (L_BM * L_BN))) : make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
                     const uint32_t a = park_s + (uint32_t)tl_park_off(r, lane) * 4u;
                     #pragma unroll
-                    for (int qk = 0; qk < 16; qk++) if (qk < S) v[qk] = tl_ld_dsmem4(a, (uint32_t)qk);
+                    for (int qk = 0; qk < 16; qk++) if (qk < split) v[qk] = tl_ld_dsmem4(a, (uint32_t)(rk0 + qk));
                 }
                 sum = v[0];
                 #pragma unroll
-                for (int qk = 1; qk < 16; qk++) if (qk < S) { sum.x += v[qk].x; sum.y += v[qk].y; sum.z += v[qk].z; sum.w += v[qk].w; }
+                for (int qk = 1; qk < 16; qk++) if (qk < split) { sum.x += v[qk].x; sum.y += v[qk].y; sum.z += v[qk].z; sum.w += v[qk].w; }
             }
             if (threadIdx.x == 0 && rr == 0) TL_TRACE(12);
             const bool in = gc < p.N;
@@ -456,7 +502,9 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const TlP p, const __g
         }
     }
     if (threadIdx.x == 0) TL_TRACE(13);
-    if (S > 1 && !mypart) tl_cluster_sync();                                          // distributed shared memory: nobody leaves while its tile is still being read
+    // distributed shared memory: nobody leaves while its tile is still being read (uniform over the grid: it depends on the problems only)
+    const bool dsm_exit = (g.p[0].split > 1 && !g.p[0].part) || (g.p[1].split > 1 && !g.p[1].part);
+    if (S > 1 && dsm_exit) tl_cluster_sync();
     if (threadIdx.x == 0) TL_TRACE(14);
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * L_BN); }
 }
@@ -486,10 +534,11 @@ static int tl_map(CUtensorMap *m, const float *X, int64_t inner, int64_t outer, 
                swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : T4K_EINVAL;
 }
 
-constexpr size_t L_SMEM = (size_t)L_STAGES * L_STAGE_B + 256 + (size_t)(L_W2_FLTS + L_D_FLTS) * 4 + 1024;
+constexpr size_t L_SMEM = (size_t)L_RING_B + 256 + (size_t)(L_W2_FLTS + L_D_FLTS) * 4 + 1024;
 static_assert(L_SMEM <= 227 * 1024, "shared memory budget");
+static_assert(L_NBAR * 8 + 8 <= 256, "barrier block");
 #define TL_MAX_DEV 16
-static int g_tl_maxcl[TL_MAX_DEV][5];                   // [device][log2 S]: co-resident clusters of size S (0: not queried yet, -1: unavailable)
+static int g_tl_maxcl[TL_MAX_DEV][5];                   // [device][log2 S]: co-resident clusters of size S (-1: unavailable)
 
 static int tl_device() { const int d = cur_device(); return (d < 0 || d >= TL_MAX_DEV) ? -1 : d; }
 static int tl_prepare(int dev) {
@@ -501,9 +550,9 @@ static int tl_prepare(int dev) {
     for (int l = 0; l < 5; l++) {
         const int S = 1 << l;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(1, 1, S); cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = L_SMEM;
+        cfg.gridDim = dim3(S, 1, 1); cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = L_SMEM;
         cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = (unsigned)S;
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int n = 0;
         if (S == 1) n = sm_count();
@@ -535,65 +584,108 @@ bool gemm_tl_ok(const float *A, const float *B, const float *O, int tA, int tB, 
     return w >= 4.0e6 && w < 2.0e10;
 }
 
-int gemm_tl(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB, int M, int N, int K, cudaStream_t st, const TlEpi *epi) {
+// one problem of a launch → TlP (everything but the split) + its two tensor maps
+static int tl_fill(const TlJob &j, TlP &p, CUtensorMap *amap, CUtensorMap *bmap, CUtensorMapSwizzle mn_swz) {
+    p = TlP{};
+    p.O = j.O; p.alpha = j.alpha; p.beta = j.beta; p.M = j.M; p.N = j.N; p.K = j.K;
+    p.mtiles = (j.M + L_BM - 1) / L_BM; p.ntiles = (j.N + L_BN - 1) / L_BN; p.KT = (j.K + L_BK - 1) / L_BK;
+    p.a_mn = j.tA ? 1 : 0; p.b_mn = j.tB ? 0 : 1; p.mode = 0;
+    if (const TlEpi *epi = j.epi) {
+        p.mode = epi->mode; p.bias = epi->bias; p.actA = epi->actA; p.actF = epi->actF; p.layer = epi->layer; p.act_alpha = epi->act_alpha;
+        p.W2 = epi->W2; p.B2 = epi->B2; p.Y2 = epi->Y2; p.P = epi->P; p.P2 = epi->P2; p.E2 = epi->E2; p.F = epi->F; p.O2 = epi->O2;
+        if (epi->mode == 2 && (p.ntiles != 1 || (j.N & 3) || epi->E2 > 32 || epi->E2 < 1)) return T4K_ENOSUP;
+        if (epi->gP) {
+            const int EH = j.tA ? j.M : j.K;                                   // hidden width: K of the K-major operand, M of the M-major one
+            if (EH > 128 || (EH & 3) || epi->gE2 < 1 || epi->gE2 > 32 || !epi->gT || !epi->gW2) return T4K_ENOSUP;
+            p.gen = j.tA ? 2 : 1; p.gE2 = epi->gE2; p.gP = epi->gP; p.gT = epi->gT; p.gW2 = epi->gW2; p.gF = epi->gF;
+        }
+    }
+    int rc;
+    // op(A)(m,k): A stored [M][K] (K-major: box 128 rows x 32 k) or [K][M] when tA (M-major: box 32 k-rows x 32 m)
+    if (p.gen) rc = tl_map(amap, j.B, j.tB ? j.K : j.N, j.tB ? j.N : j.K, j.tB ? 128 : 32, j.tB ? CU_TENSOR_MAP_SWIZZLE_128B : mn_swz);   // unused: any valid map
+    else rc = j.tA ? tl_map(amap, j.A, j.M, j.K, 32, mn_swz) : tl_map(amap, j.A, j.K, j.M, 128);
+    if (rc) return rc;
+    // op(B)(k,n): B stored [N][K] when tB (K-major) or [K][N] (N-major)
+    return j.tB ? tl_map(bmap, j.B, j.K, j.N, 128) : tl_map(bmap, j.B, j.N, j.K, 32, mn_swz);
+}
+
+// One launch for one or two problems.  Cluster size S and, per problem, K-split (split == S: a cluster is one tile) or none (split == 1: a
+// cluster is S tiles): the combination with the fewest k-blocks per CTA that keeps the whole grid co-resident (one wave).
+int gemm_tl_multi(const TlJob *jobs, int njobs, cudaStream_t st) {
+    if (njobs < 1 || njobs > 2) return T4K_EINVAL;
     const int dev = tl_device();
     if (dev < 0) return T4K_EINVAL;
     int rc = tl_prepare(dev); if (rc) return rc;
-    const int mtiles = (M + L_BM - 1) / L_BM, ntiles = (N + L_BN - 1) / L_BN, KT = (K + L_BK - 1) / L_BK, T = mtiles * ntiles;
-    if (epi && epi->mode == 2 && (ntiles != 1 || (N & 3) || epi->E2 > 32 || epi->E2 < 1)) return T4K_ENOSUP;
-    // cluster size = split-K factor: the largest power of two that keeps the whole grid in one wave of co-resident clusters and
-    // leaves every rank at least one k-block (two when there is a choice)
-    int S = 1;
-    const int smax = tl_knob(2);
-    for (int l = 4; l >= 1; l--) {
-        const int s = 1 << l, cap = g_tl_maxcl[dev][l];
-        if (s > smax || cap <= 0 || T > cap) continue;
-        const int per = (KT + s - 1) / s;
-        if ((KT + per - 1) / per != s) continue;                               // an empty rank
-        if (per < 2 && l > 1 && KT >= 4) continue;
-        S = s; break;
-    }
-    const int kt_per = (KT + S - 1) / S;
-    const int mask_hi = tl_knob(1);
-    TlP p{};
-    p.O = O; p.alpha = alpha; p.beta = beta; p.M = M; p.N = N; p.K = K; p.KT = KT; p.kt_per = kt_per;
-    p.a_mn = tA ? 1 : 0; p.b_mn = tB ? 0 : 1; p.mask_hi = mask_hi; p.mode = 0;
-    p.mn_type = (uint32_t)tl_knob(3); p.mn_lbo = (uint32_t)tl_knob(5); p.mn_sbo = (uint32_t)tl_knob(6); p.mn_kstep = (uint32_t)tl_knob(7);
+    TlG g{};
+    CUtensorMap maps[4];
     const CUtensorMapSwizzle mn_swz = (CUtensorMapSwizzle)tl_knob(4);
-    p.trace = g_tl_trace;
-    if (S > 1 && tl_knob(8)) {
-        p.part = (float*)workspace((size_t)T * S * L_BM * L_BN * sizeof(float), 7);
-        if (!p.part) return T4K_ENOMEM;
-    }
-    if (epi) {
-        p.mode = epi->mode; p.bias = epi->bias; p.actA = epi->actA; p.actF = epi->actF; p.layer = epi->layer; p.act_alpha = epi->act_alpha;
-        p.W2 = epi->W2; p.B2 = epi->B2; p.Y2 = epi->Y2; p.P = epi->P; p.P2 = epi->P2; p.E2 = epi->E2; p.F = epi->F; p.O2 = epi->O2;
-        if (epi->gP) {
-            if (tA || K > 128 || (K & 3) || epi->gE2 < 1 || epi->gE2 > 32 || !epi->gT || !epi->gW2) return T4K_ENOSUP;
-            p.gen = 1; p.gE2 = epi->gE2; p.gP = epi->gP; p.gT = epi->gT; p.gW2 = epi->gW2; p.gF = epi->gF;
+    for (int q = 0; q < njobs; q++) { rc = tl_fill(jobs[q], g.p[q], &maps[2 * q], &maps[2 * q + 1], mn_swz); if (rc) return rc; }
+    if (njobs == 1) { maps[2] = maps[0]; maps[3] = maps[1]; }
+    const int smax = tl_knob(2);
+    int bestS = 1, bestSplit[2] = {1, 1}, bestCost = 1 << 30, bestCtas = 0;
+    for (int l = 0; l <= 4; l++) {
+        const int S = 1 << l, cap = g_tl_maxcl[dev][l];
+        if (S > smax || cap <= 0) continue;
+        for (int c0 = 0; c0 < 2; c0++) for (int c1 = 0; c1 < (njobs == 2 ? 2 : 1); c1++) {
+            const int sp[2] = {c0 ? S : 1, c1 ? S : 1};
+            if (S == 1 && (c0 || c1)) continue;
+            int ncl = 0, cost = 0; bool okc = true;
+            for (int q = 0; q < njobs; q++) {
+                const TlP &p = g.p[q];
+                const int T = p.mtiles * p.ntiles, per = (p.KT + sp[q] - 1) / sp[q];
+                if ((p.KT + per - 1) / per != sp[q]) okc = false;             // an empty rank
+                if (p.gen == 2 && per > 4) okc = false;                        // generated M-major A: the k range's p - y rows must fit sD (128 rows)
+                ncl += (T * sp[q] + S - 1) / S;
+                // k-blocks per CTA, plus what a split costs (store + barrier + reload of the partials: about three k-blocks' worth)
+                cost = max(cost, per + (sp[q] > 1 ? 3 : 0));
+            }
+            if (!okc || ncl > cap) continue;
+            if (cost < bestCost || (cost == bestCost && ncl * S < bestCtas)) { bestCost = cost; bestS = S; bestSplit[0] = sp[0]; bestSplit[1] = sp[1]; bestCtas = ncl * S; }
         }
     }
-    CUtensorMap amap, bmap;
-    // op(A)(m,k): A stored [M][K] (K-major: box 128 rows x 32 k) or [K][M] when tA (M-major: box 32 k-rows x 32 m)
-    if (p.gen) rc = tl_map(&amap, B, tB ? K : N, tB ? N : K, tB ? 128 : 32, tB ? CU_TENSOR_MAP_SWIZZLE_128B : mn_swz);       // unused: a valid map
-    else rc = tA ? tl_map(&amap, A, M, K, 32, mn_swz) : tl_map(&amap, A, K, M, 128);
-    if (rc) return rc;
-    // op(B)(k,n): B stored [N][K] when tB (K-major) or [K][N] (N-major)
-    rc = tB ? tl_map(&bmap, B, K, N, 128) : tl_map(&bmap, B, N, K, 32, mn_swz); if (rc) return rc;
+    if (bestCost == (1 << 30)) return T4K_ENOSUP;                              // does not fit one wave in any shape
+    const int S = bestS;
+    int ncl[2] = {0, 0};
+    size_t part_flts = 0;
+    for (int q = 0; q < njobs; q++) {
+        TlP &p = g.p[q];
+        p.split = bestSplit[q]; p.kt_per = (p.KT + p.split - 1) / p.split;
+        const int T = p.mtiles * p.ntiles;
+        ncl[q] = (T * p.split + S - 1) / S;
+        if (p.split > 1 && tl_knob(8)) part_flts += (size_t)T * p.split * L_BM * L_BN;
+    }
+    if (part_flts) {
+        float *part = (float*)workspace(part_flts * sizeof(float), 7);
+        if (!part) return T4K_ENOMEM;
+        for (int q = 0; q < njobs; q++) {
+            TlP &p = g.p[q];
+            if (p.split > 1) { p.part = part; part += (size_t)p.mtiles * p.ntiles * p.split * L_BM * L_BN; }
+        }
+    }
+    if (njobs == 1) g.p[1] = g.p[0];
+    g.ncl0 = ncl[0];
+    g.mask_hi = tl_knob(1);
+    g.mn_type = (uint32_t)tl_knob(3); g.mn_lbo = (uint32_t)tl_knob(5); g.mn_sbo = (uint32_t)tl_knob(6); g.mn_kstep = (uint32_t)tl_knob(7);
+    g.trace = g_tl_trace;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ntiles, mtiles, S); cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = L_SMEM; cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)((ncl[0] + ncl[1]) * S)); cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = L_SMEM; cfg.stream = st;
     cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = (unsigned)S;
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = S > 1 ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_gemm_tl, p, amap, bmap);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_gemm_tl, g, maps[0], maps[1], maps[2], maps[3]);
     ++g_launches;
     if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
     return (int)cudaGetLastError();
 }
 
+int gemm_tl(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB, int M, int N, int K, cudaStream_t st, const TlEpi *epi) {
+    TlJob j{A, B, O, alpha, beta, tA, tB, M, N, K, epi};
+    return gemm_tl_multi(&j, 1, st);
+}
+
 } // namespace t4k
 
-extern "C" int t4k_gemm_tl_trace(long long *dev16) { t4k::g_tl_trace = dev16; return 0; }   // bring-up: 16 clock64 stamps of CTA (0,0,0), nullptr = off
+extern "C" int t4k_gemm_tl_trace(long long *dev16) { t4k::g_tl_trace = dev16; return 0; }   // bring-up: 16 clock64 stamps of CTA 0, nullptr = off
 extern "C" int t4k_set_gemm_tl(int what, int value) {
     if (what < 0 || what >= TL_NKNOB) return T4K_EINVAL;
     const int was = t4k::tl_knob(what);

@@ -469,7 +469,16 @@ int Model::_bfused(int i) {                                // i = index of the b
     // _skip_flat_copy: the flatten backward (ao = dy) was issued on the side stream behind the dW GEMM that still reads ao
     // (see backprop): passing dy as the copy's destination makes the kernel skip it
     DU *flat_dst = (flat && _skip_flat_copy) ? dy.data : ao.data;
-    int rc = t4k_conv_pool_relu_bwd(dy.data, flat_dst, po.grad[4]->data, po.data, co.data, in.data, dx.data, f.data, df.data, db.data,
+    int rc = T4K_ENOSUP;
+    if (_oe.on && _oe.rest && !_oe.first && train && df.data == _DG && db.data > _DG && db.data < _DG + _first_end) {
+        // the block of the FIRST parameter layer, the rest of the arena already stepped on the side stream: its finish launch steps its own segments
+        t4k_fused_opt_t fo{_oe.kind, _oe.lr, _oe.b1, _oe.b2, _oe.wd, _G, _M, _V, 0, (int64_t)(db.data - _DG), (int32_t)f.N(), (int32_t)in.grad[1]->N()};
+        rc = t4k_conv_pool_relu_bwd_opt(dy.data, flat_dst, po.grad[4]->data, po.data, co.data, in.data, dx.data, f.data, df.data, db.data,
+                                        in.N(), in.H(), in.W(), in.C(), co.H(), co.W(), co.C(), f.H(), in.stride[0], in.stride[2], train, &fo, ST);
+        if (rc == 0) _oe.first = true;
+    }
+    if (rc == T4K_ENOSUP)
+        rc = t4k_conv_pool_relu_bwd(dy.data, flat_dst, po.grad[4]->data, po.data, co.data, in.data, dx.data, f.data, df.data, db.data,
                                     in.N(), in.H(), in.W(), in.C(), co.H(), co.W(), co.C(), f.H(), in.stride[0], in.stride[2], train, ST);
     if (rc == T4K_ENOSUP) return 0;
     KCHK(rc);
@@ -543,6 +552,7 @@ Model &Model::backprop(Tensor &tgt) {
     for (; i >= 0; j++) {
         const t4_layer fn = _layers[i]->grad_fn;
         if (_dp_early && _dp_pushed_from < 0 && i < _second_layer) _dp_push();     // every gradient but the first parameter layer's is final
+        if (_oe.on && !_oe.rest && i < _second_layer && (int64_t)_total > _first_end) _opt_push();
         const int adv = (j > 0 && (fn == T4K_L_FLATTEN || fn == T4K_L_RELU)) ? _bfused(i) : 0;
         if (adv) { i -= adv; continue; }
         if (_skip_flat_copy) {                              // the fused block did not take the flatten: rejoin before the per-layer path touches it
@@ -568,6 +578,16 @@ Model &Model::backprop(Tensor &tgt) {
     }
     if (_side_join) { cudaStreamWaitEvent((cudaStream_t)ST, g_join, 0); _side_join = false; }      // side-stream branch of this backprop
     return *this;
+}
+void Model::_opt_push() {
+    // the optimizer of every parameter layer but the first, on the side stream (behind the dW GEMMs that live there, and behind everything the
+    // library stream has issued so far); joined at the end of backprop / the step
+    cudaStream_t st = (cudaStream_t)ST;
+    cudaEventRecord(g_fork, st); cudaStreamWaitEvent(g_stream2, g_fork, 0);
+    KCHK(t4k_optim_multi_range(_oe.kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, _first_end, (int64_t)_total, _oe.lr, _oe.b1, _oe.b2, _oe.wd,
+                               (t4k_stream_t)g_stream2));
+    cudaEventRecord(g_join, g_stream2);
+    _side_join = true; _oe.rest = true;
 }
 void Model::_dp_push() {
     // Split exchange (comm.cu MODE -1): fork a side stream off the library stream, push the finished part of the gradient
@@ -627,9 +647,16 @@ int Model::_blinear(Tensor &in, Tensor &out, bool skip_db, Tensor *xdup, bool de
         if (!skip_db) KCHK(t4k_dbias(out.data, db.data, N, E0, ST));
         cudaEventRecord(g_fork, st); cudaStreamWaitEvent(g_stream2, g_fork, 0);
         const bool hp = _hp.on; _hp.on = false;
-        if (hp) {                                            // the deferred head backward (see _bfused_head): produces dY (= out) for the dW GEMM behind it
+        if (hp) {
+            // the deferred head backward (see _bfused_head) goes to the side stream: parameter gradients of the head, dB of this layer and the
+            // layer tensors' gradient values — nothing the library stream waits for before the end of the step
             KCHK(t4k_mlp_head_bwd(_hp.P, _hp.T, _hp.Ylin, _hp.X2, _hp.F1, _hp.Y1, _hp.W2, _hp.dW2, _hp.dB2, _hp.dB1, _hp.N, _hp.E0, _hp.E1, train, (t4k_stream_t)g_stream2));
             cudaEventRecord(g_head, g_stream2);
+            cudaEventRecord(g_join, g_stream2);
+            // dX and dW of this layer in ONE launch on the library stream, their dY operand generated from the head's forward tensors
+            const int rcg = t4k_linear_bwd_from_head(_pdup, _hp.T, _hp.W2, _hp.F1, xdup->data, w.data, in.data, dw.data, N, _hp.E0, E0, E1, ST);
+            if (rcg == 0) { _side_join = true; return 0; }                 // the conv block that follows writes the flatten backward itself
+            if (rcg != T4K_ENOSUP) KCHK(rcg);
         }
         t4k_set_workspace_bank(1);
         KCHK(t4k_gemm(out.data, xdup->data, dw.data, 1.0f, 1.0f, 1, 0, E0, E1, N, 1, 1, 0, 0, 0, (t4k_stream_t)g_stream2));
@@ -825,7 +852,11 @@ Model &Model::_gradient(t4_optimizer op, DU lr, DU b1, DU b2, DU wd) {     // gr
                                 _dp_scal, _dp_nscal, _dp_pushed_from > 0 ? _dp_pushed_from : (int64_t)_total, ST));
         _dp_pushed_from = -1;
     }
+    else if (_oe.on && _oe.rest) {                                          // the side stream stepped [first_end, total) during backprop (_opt_push)
+        if (!_oe.first) KCHK(t4k_optim_multi_range(kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, 0, _first_end, lr, b1, b2, wd, ST));
+    }
     else       KCHK(t4k_optim_multi(kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, (int64_t)_total, lr, b1, b2, wd, ST));
+    _oe = OptEarly();
     return *this;
 }
 Model &Model::sgd(DU lr, DU b) {                                           // gradient.cu:133-143: momentum forced to 0 on the first call
@@ -955,6 +986,13 @@ int Model::_step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4
             cudaEventRecord(g_join, g_stream2);
         }
         _dp_early = _comm && (int)op >= 0 && train && _G;  // forward -> backprop -> optimizer is one unit here: the exchange may start early
+        _oe = OptEarly();
+        if (!_comm && (int)op >= 0 && train && _G && _iter > 0 && fuse) {     // single GPU: the optimizer may start early too (see OptEarly)
+            _oe.on = true; _oe.lr = lr; _oe.b2 = b2; _oe.wd = 0.0f;
+            if (op == OPTI_SGD || op == OPTI_SGDM) { _oe.kind = 0; _oe.b1 = fabsf(b1) < DU_EPS_H ? 0.0f : b1; _oe.b2 = 0.0f; }
+            else if (op == OPTI_ADAM) { _oe.kind = 1; _oe.b1 = b1; }
+            else { _oe.kind = 2; _oe.b1 = b1; _oe.wd = wd; }
+        }
         backprop(tgt);
         _dp_early = false;
         if ((int)op >= 0) {                                // op < 0 — data parallel over NCCL: the caller all-reduces DG, then calls the optimizer

@@ -397,6 +397,16 @@ extern "C" int t4k_linear_dx_from_head(const float *P, const float *T, const flo
     TlEpi e{}; e.mode = 0; e.gP = P; e.gT = T; e.gW2 = W2; e.gF = F1; e.gE2 = E2;
     return gemm_tl(nullptr, W1, dX, 1.0f, 0.0f, 0, 0, N, E1, EH, STRM(s), &e);      // dX[N,E1] = A[N,EH] @ W1[EH,E1], A generated
 }
+extern "C" int t4k_linear_bwd_from_head(const float *P, const float *T, const float *W2, const float *F1, const float *X, const float *W1,
+                                        float *dX, float *dW1, int N, int E2, int EH, int E1, t4k_stream_t s) {
+    if (!P || !T || !W2 || !X || !W1 || !dX || !dW1 || N < 1 || E2 < 1 || EH < 1 || E1 < 1 || X == dX) return T4K_EINVAL;
+    if (E2 > 32 || EH > 128 || (EH & 3) || !aligned16(W2) || (F1 && !aligned16(F1)) ||
+        !gemm_tl_ok(W1, W1, dX, 0, 0, N, E1, EH, 1, 1) || !gemm_tl_ok(X, X, dW1, 1, 0, EH, E1, N, 1, 1)) return T4K_ENOSUP;
+    TlEpi e{}; e.mode = 0; e.gP = P; e.gT = T; e.gW2 = W2; e.gF = F1; e.gE2 = E2;
+    const TlJob jobs[2] = {{nullptr, W1, dX, 1.0f, 0.0f, 0, 0, N, E1, EH, &e},          // dX[N,E1]   = dY1[N,EH] @ W1[EH,E1]
+                           {nullptr, X, dW1, 1.0f, 1.0f, 1, 0, EH, E1, N, &e}};         // dW1[EH,E1] += dY1^T @ X[N,E1]
+    return gemm_tl_multi(jobs, 2, STRM(s));
+}
 extern "C" int t4k_linear_bwd(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
                               int N, int E0, int E1, int train, t4k_stream_t s) {
     return t4k_linear_bwd_ex(X, W, dY, dX, dW, dB, N, E0, E1, train, 0, s);

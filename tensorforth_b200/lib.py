@@ -61,6 +61,7 @@ PROTOTYPES = {
     "t4k_dbias": (_i, [_p, _p, _i, _i, _p]),
     "t4k_linear_bwd": (_i, [_p] * 6 + [_i] * 4 + [_p]),
     "t4k_linear_bwd_ex": (_i, [_p] * 6 + [_i] * 5 + [_p]),
+    "t4k_linear_bwd_from_head": (_i, [_p] * 8 + [_i] * 4 + [_p]),
     "t4k_linear_dx_from_head": (_i, [_p] * 6 + [_i] * 4 + [_p]),
     "t4k_linear_bwd_act": (_i, [_p] * 8 + [_i] * 5 + [_p]),
     "t4k_linear_act_fwd": (_i, [_i] + [_p] * 6 + [_f] + [_i] * 3 + [_p]),
@@ -78,6 +79,8 @@ PROTOTYPES = {
     "t4k_sgd": (_i, [_p, _p, _p, _i, _f, _f, _l, _p]),
     "t4k_adam": (_i, [_p, _p, _p, _p, _f, _f, _f, _l, _p]),
     "t4k_adamw": (_i, [_p, _p, _p, _p, _f, _f, _f, _f, _l, _p]),
+    "t4k_optim_multi_range": (_i, [_i, _p, _p, _p, _p, _p, _i, _l, _l, _f, _f, _f, _f, _p]),
+    "t4k_conv_pool_relu_bwd_opt": (_i, [_p] * 10 + [_i] * 11 + [_p, _p]),
     "t4k_optim_multi": (_i, [_i, _p, _p, _p, _p, _p, _i, _l, _f, _f, _f, _f, _p]),
     "t4k_comm_create": (_i, [_i, _i, _l, C.POINTER(_p), _p]),
     "t4k_comm_connect": (_i, [_p, _p]),

@@ -282,7 +282,7 @@ def test_gemm_tl_hi_plane_and_cluster_sizes(tA, tB, M, N, K):
         assert_close(got, ref, rtol=1e-5, what="cluster size <= %d" % smax)
 
 
-@pytest.mark.parametrize("N,E2,EH,E1,act", [(512, 10, 100, 1960, True), (512, 10, 100, 1960, False), (200, 32, 128, 516, True), (64, 3, 20, 64, True)])
+@pytest.mark.parametrize("N,E2,EH,E1,act", [(512, 10, 100, 1960, True), (512, 10, 100, 1960, False), (200, 16, 128, 516, True), (64, 3, 20, 64, True)])
 def test_linear_dx_from_head(N, E2, EH, E1, act):
     """dX of the hidden linear layer computed straight from the head's forward tensors (p - y, the small linear's dX and the activation
     backward evaluated in the GEMM's operand producer) == t4k_mlp_head_bwd followed by the dX GEMM on its stored output: the same bits"""
@@ -310,6 +310,38 @@ def test_linear_dx_from_head(N, E2, EH, E1, act):
     d = orc.tt_op(orc.SUB, P, T)
     g = orc.gemm(d, W2) * (F1 if act else 1.0)
     assert_close(host(got), orc.gemm(np.ascontiguousarray(g, np.float32), W1), rtol=1e-4, what="dX vs oracle")
+
+
+@pytest.mark.parametrize("N,E2,EH,E1,act", [(512, 10, 100, 1960, True), (512, 10, 100, 1960, False), (200, 16, 128, 516, True), (1024, 10, 64, 784, True)])
+def test_linear_bwd_from_head(N, E2, EH, E1, act):
+    """dX AND dW of the hidden linear layer in one launch, their dY operand generated from the head's forward tensors (K-major for dX, M-major
+    for dW) == t4k_mlp_head_bwd followed by the two GEMMs on its stored output: dX the same bits, dW FP32-grade (its split may differ)"""
+    P, T, W2 = np.abs(rnd(N, E2)), orc.onehot(np.arange(N) % E2, E2), rnd(E2, EH)
+    X2, X = rnd(N, EH), rnd(N, E1)
+    F1 = (rnd(N, EH) > 0).astype(np.float32)
+    W1, dW0 = rnd(EH, E1) * 0.05, rnd(EH, E1)
+    dP, dT, dW2_, dF1, dW1, dX_ = dev(P), dev(T), dev(W2), dev(F1), dev(W1), dev(X)
+    p, yl, x2, y1 = dev(P), zeros(N, E2), dev(X2), zeros(N, EH)
+    dw, db, db1 = zeros(E2, EH), zeros(E2), zeros(EH)
+    ok(lib().t4k_mlp_head_bwd(ptr(p), ptr(dT), ptr(yl), ptr(x2), ptr(dF1) if act else None, ptr(y1) if act else None, ptr(dW2_),
+                              ptr(dw), ptr(db), ptr(db1), N, E2, EH, 1, None))
+    dy1 = y1 if act else x2
+    ref_dx, ref_dw = zeros(N, E1), dev(dW0)
+    ok(lib().t4k_gemm(ptr(dy1), ptr(dW1), ptr(ref_dx), 1.0, 0.0, 0, 0, N, E1, EH, 1, 1, 0, 0, 0, None))
+    ok(lib().t4k_gemm(ptr(dy1), ptr(dX_), ptr(ref_dw), 1.0, 1.0, 1, 0, EH, E1, N, 1, 1, 0, 0, 0, None))
+    got_dx, got_dw = zeros(N, E1), dev(dW0)
+    ok(lib().t4k_linear_bwd_from_head(ptr(dP), ptr(dT), ptr(dW2_), ptr(dF1) if act else None, ptr(dX_), ptr(dW1), ptr(got_dx), ptr(got_dw),
+                                      N, E2, EH, E1, None), "bwd_from_head")
+    assert_close(host(got_dx), host(ref_dx), rtol=1e-5, what="dX (one launch)")
+    assert_close(host(got_dw), host(ref_dw), rtol=1e-5, what="dW (one launch)")
+    g = (orc.gemm(orc.tt_op(orc.SUB, P, T), W2) * (F1 if act else 1.0)).astype(np.float32)
+    assert_close(host(got_dx), orc.gemm(np.ascontiguousarray(g), W1), rtol=1e-4, what="dX vs oracle")
+    assert_close(host(got_dw), orc.gemm(np.ascontiguousarray(g), X, O=dW0, alpha=1.0, beta=1.0, tA=True), rtol=1e-4, what="dW vs oracle")
+    a2 = host(got_dw).copy()
+    got_dw2, got_dx2 = dev(dW0), zeros(N, E1)
+    ok(lib().t4k_linear_bwd_from_head(ptr(dP), ptr(dT), ptr(dW2_), ptr(dF1) if act else None, ptr(dX_), ptr(dW1), ptr(got_dx2), ptr(got_dw2),
+                                      N, E2, EH, E1, None), "bwd_from_head")
+    assert_exact(host(got_dw2), a2, "deterministic"); assert_exact(host(got_dx2), host(got_dx), "deterministic")
 
 
 @pytest.mark.parametrize("N,E0,E1", [(1024, 512, 784), (512, 100, 1960), (1024, 256, 512), (96, 36, 48)])
