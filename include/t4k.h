@@ -208,6 +208,20 @@ int t4k_linear_dx_from_head(const float *P, const float *T, const float *W2, con
  * duplicate of X).  T4K_ENOSUP: as above, or the two problems do not fit one co-resident wave. */
 int t4k_linear_bwd_from_head(const float *P, const float *T, const float *W2, const float *F1, const float *X, const float *W1,
                              float *dX, float *dW1, int N, int E2, int EH, int E1, t4k_stream_t s);
+/* THE TRAIN TAIL (inside a fused train step only: the target is known at forward time and the forward values of the tail's layer tensors
+ * are never observable): hidden linear + activation + classifier head + softmax AND, on the same rows, Model::_bprep, the head linear's dX
+ * and the activation backward (forward.cu:158-243, backprop.cu:76-140,194-263) in ONE launch of the layer GEMM.  On return the layer tensors
+ * hold what they hold after t4k_linear_act_head_fwd + t4k_mlp_head_bwd: Y1 = dY1, A1 = dX of the head linear, F1 = mask, Ylin = P = p - y,
+ * Pdup = p (for the loss); the head's parameter gradients are left as per-CTA partials in `scratch` (t4k_head_train_scratch_floats floats;
+ * 0 = shape not supported) for t4k_head_grad_finish(scratch, *ncta, ...) to add into dW2 / dB2 / dB1 — on any stream, off the critical path. */
+int64_t t4k_head_train_scratch_floats(int layer, int N, int EH, int E1, int E0);
+int t4k_linear_act_head_train(int layer, const float *X, const float *W1, const float *B1, float *Y1, float *A1, float *F1, float alpha,
+                              const float *W2, const float *B2, float *Ylin, float *P, float *Pdup, const float *T,
+                              float *scratch, int *ncta, int N, int EH, int E1, int E0, t4k_stream_t s);
+int t4k_head_grad_finish(const float *scratch, int ncta, int E0, int EH, float *dW2, float *dB2, float *dB1, t4k_stream_t s);
+/* dX = dY @ W and dW += dY^T @ X of Model::_blinear in ONE launch (two problems share the layer GEMM's grid); X must not alias dX.
+ * T4K_ENOSUP when a product is outside the layer GEMM's class or the pair does not fit one co-resident wave: use t4k_linear_bwd_ex */
+int t4k_linear_bwd_pair(const float *X, const float *W, const float *dY, float *dX, float *dW, int N, int E0, int E1, t4k_stream_t s);
 /* classifier head, backward, one launch (backprop.cu:76-140,194-263), E0 <= 32, E1 <= 128 else T4K_ENOSUP:
  *   P <- P - T (Model::_bprep), Ylin <- P - T (softmax backward is a copy), dB += Σ_n (P-T), dW += (P-T)^T @ X2,
  *   X2 <- (P-T) @ W (in place: the small linear's input tensor receives its dX),

@@ -43,13 +43,15 @@ struct TlEpi {
     int mode; const float *bias; float *actA, *actF; int layer; float act_alpha;       // mode 1, 2: Y = acc + bias (to O), A = act(Y), F = derivative / mask
     const float *W2, *B2; float *Y2, *P, *P2; int E2;                                 // mode 2: Y2 = A @ W2^T + B2 [M,E2], P = softmax(Y2), P2 = copy of P (may be null)
     const float *F; float *O2;                                                        // mode 3: O = acc, O2 = acc * F
+    const float *T; float *Ylin, *hpart;                                              // mode 4 (train tail, see gemm_tl.cu): target [M,E2], head linear's output tensor, partials [ctas][nEp]
     // generated A operand (gP != nullptr; the A argument of gemm_tl is ignored): with dY1[n][e] = (Σ_j (gP[n][j] - gT[n][j]) * gW2[j][e]) * gF[n][e]
     // (gF may be null, j < gE2 <= 32, e < EH <= 128, EH % 4 == 0):  tA == 0: A[m][k] = dY1[m][k] (EH = K);  tA == 1: A(m,k) = dY1[k][m] (EH = M)
     const float *gP, *gT, *gW2, *gF; int gE2;
 };
 struct TlJob { const float *A, *B; float *O; float alpha, beta; int tA, tB, M, N, K; const TlEpi *epi; };
 // one launch for one or two independent problems (e.g. dW and dX of a layer): T4K_ENOSUP when they do not fit one co-resident wave
-int  gemm_tl_multi(const TlJob *jobs, int njobs, cudaStream_t st);
+int  gemm_tl_multi(const TlJob *jobs, int njobs, cudaStream_t st, int *ctas_out = nullptr);
+int  gemm_tl_ctas(const TlJob *jobs, int njobs);          // CTAs gemm_tl_multi would launch for these problems (<= 0: not supported)
 bool gemm_tl_ok(const float *A, const float *B, const float *O, int tA, int tB, int M, int N, int K, int C, int batch);
 int  gemm_tl(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,
              int M, int N, int K, cudaStream_t st, const TlEpi *epi = nullptr);

@@ -25,6 +25,9 @@
 //       mode 1  Y = acc + bias ; A = act(Y) ; F = saved derivative / mask   (Model::_flinear + _factivate)
 //       mode 2  mode 1, then Y2 = A @ W2^T + B2 ; P = softmax(Y2) (+ dup)   (... + the classifier head: the row never leaves the warp)
 //       mode 3  O = acc ; O2 = acc * F                                      (Model::_blinear's dX + the _bactivate in front of it)
+//       mode 4  the TRAIN TAIL: mode 2, and on the same row, still in the warp, the head's backward (Model::_bprep p - y, the head linear's
+//               dX and the activation backward): the layer tensors receive their BACKWARD values directly (inside a fused train step the
+//               forward values are never observable), the head's parameter gradients leave as per-CTA partials (k_head_grad_fin adds them)
 //   * TWO problems can share one launch (dW and dX of a layer when X has a duplicate): a cluster is either the K-split of one tile or S
 //     independent tiles, so both fill the machine together instead of queueing behind each other (this kernel owns its SM: 512 threads x
 //     128 registers, 225 KiB of shared memory — nothing else is co-resident).
@@ -61,6 +64,7 @@ struct TlP {
     const float *bias; float *actA, *actF; int layer; float act_alpha;          // mode 1, 2
     const float *W2, *B2; float *Y2, *P, *P2; int E2;                          // mode 2
     const float *F; float *O2;                                                  // mode 3
+    const float *T; float *Ylin, *hpart;                                        // mode 4 (train tail): target rows, the head linear's output tensor, per-CTA gradient partials
     // generated A operand (gen 1: K-major [M][K], K <= 128; gen 2: M-major, A(m,k) = the same matrix transposed, M <= 128):
     //   dY1[n][e] = (Σ_j (gP[n][j] - gT[n][j]) * gW2[j][e]) * gF[n][e];  gen 1: A[m=n][k=e];  gen 2: A[m=e][k=n]
     int gen, gE2; const float *gP, *gT, *gW2, *gF;
@@ -405,6 +409,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const __grid_constant_
         const float *park = reinterpret_cast<const float*>(smem);
         const int gc = nt * L_BN + lane * 4;
         const bool o_vec = ((p.N & 3) == 0);
+        // mode 4: per-warp gradient partials of the head in the idle ring behind the parked tile, zeroed here
+        const int E2p = (p.E2 + 3) & ~3, nEp = p.E2 * p.N + E2p + ((p.N + 3) & ~3);
+        float *sAcc = reinterpret_cast<float*>(smem + (size_t)L_BM * L_BN * 4);
+        if (p.mode == 4) { for (int t = lane; t < nEp; t += 32) sAcc[(size_t)warp * nEp + t] = 0.0f; __syncwarp(); }
         for (int rr = warp; rr < rpr; rr += L_WARPS) {
             const int r = zs * rpr + rr, gr = mt * L_BM + r;
             if (gr >= p.M) break;                                                     // rows ascend with rr
@@ -462,7 +470,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const __grid_constant_
                     }
                     if (p.layer != T4K_L_NONE) tl_act(p.layer, y, p.act_alpha, a, f);
                     else { a[0] = y[0]; a[1] = y[1]; a[2] = y[2]; a[3] = y[3]; }
-                    if (full) {
+                    if (p.mode == 4) stg4(p.actF + at, make_float4(f[0], f[1], f[2], f[3]));      // N % 4 == 0 (host check); Y1 / A1 receive their backward values below
+                    else if (full) {
                         stg4(p.O + at, make_float4(y[0], y[1], y[2], y[3]));
                         if (p.layer != T4K_L_NONE) { stg4(p.actA + at, make_float4(a[0], a[1], a[2], a[3])); stg4(p.actF + at, make_float4(f[0], f[1], f[2], f[3])); }
                     } else {
@@ -473,7 +482,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const __grid_constant_
                         }
                     }
                 }
-                if (p.mode == 2) {
+                if (p.mode == 2 || p.mode == 4) {
                     // classifier head on the finished row (one n-tile: the lane's four hidden units are columns gc..gc+3)
                     const int EH = p.N, E2 = p.E2;
                     float hacc[32];
@@ -493,12 +502,51 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const __grid_constant_
                     const float mx = warp_max(on ? y2 : -FLT_MAX);                    // k_softmax_small (nmath.cu:74-118): exp(x - max) / Σ
                     const float ex = on ? __expf(y2 - mx) : 0.0f;
                     const float sm = warp_sum(ex);
-                    if (on) {
-                        const float pv = ex / sm; const int64_t o2 = (int64_t)gr * E2 + lane;
-                        p.Y2[o2] = y2; p.P[o2] = pv; if (p.P2) p.P2[o2] = pv;
+                    const float pv = on ? ex / sm : 0.0f;
+                    const int64_t o2 = (int64_t)gr * E2 + lane;
+                    if (p.mode == 2) { if (on) { p.Y2[o2] = y2; p.P[o2] = pv; if (p.P2) p.P2[o2] = pv; } }
+                    else {
+                        // ---- head backward on the same row (k_head_bwd's arithmetic, class order ascending: the same bits)
+                        const float d = on ? __fsub_rn(pv, __ldg(p.T + o2)) : 0.0f;
+                        if (on) { p.P[o2] = d; p.Ylin[o2] = d; if (p.P2) p.P2[o2] = pv; }
+                        float dx[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                        float *acc_w = sAcc + (size_t)warp * nEp;                      // this warp's gradient partials [E2][EH] | [E2] | [EH]
+                        #pragma unroll 1
+                        for (int k = 0; k < E2; k++) {
+                            const float dk = __shfl_sync(0xffffffffu, d, k);
+                            if (gc < EH) {
+                                const float4 w = *reinterpret_cast<const float4*>(sW2 + k * EH + gc);
+                                dx[0] = fmaf(dk, w.x, dx[0]); dx[1] = fmaf(dk, w.y, dx[1]); dx[2] = fmaf(dk, w.z, dx[2]); dx[3] = fmaf(dk, w.w, dx[3]);
+                                float4 *q = reinterpret_cast<float4*>(acc_w + k * EH + gc);      // dW2[k][e] += d_k * a1[e]
+                                float4 t4 = *q;
+                                t4.x = fmaf(dk, a[0], t4.x); t4.y = fmaf(dk, a[1], t4.y); t4.z = fmaf(dk, a[2], t4.z); t4.w = fmaf(dk, a[3], t4.w);
+                                *q = t4;
+                            }
+                        }
+                        if (on) acc_w[E2 * EH + lane] += d;                            // dB2
+                        if (gc < EH) {
+                            const float dy[4] = {__fmul_rn(dx[0], f[0]), __fmul_rn(dx[1], f[1]), __fmul_rn(dx[2], f[2]), __fmul_rn(dx[3], f[3])};
+                            stg4(p.actA + at, make_float4(dx[0], dx[1], dx[2], dx[3]));      // the activation's output tensor <- dX of the head linear
+                            stg4(p.O + at, make_float4(dy[0], dy[1], dy[2], dy[3]));         // the hidden linear's output tensor <- dY1
+                            float4 *q = reinterpret_cast<float4*>(acc_w + E2 * EH + E2p + gc);   // dB1
+                            float4 t4 = *q; t4.x += dy[0]; t4.y += dy[1]; t4.z += dy[2]; t4.w += dy[3]; *q = t4;
+                        }
                     }
                 }
             }
+        }
+    }
+    if (active && p.mode == 4) {
+        // the CTA's partial of (dW2 | dB2 | dB1): warps summed in order; k_head_grad_fin adds the CTAs' partials in CTA order (deterministic)
+        __syncthreads();
+        const int E2p = (p.E2 + 3) & ~3, nEp = p.E2 * p.N + E2p + ((p.N + 3) & ~3);
+        const float *sAcc = reinterpret_cast<const float*>(smem + (size_t)L_BM * L_BN * 4);
+        float *dst = p.hpart + (size_t)blockIdx.x * nEp;
+        for (int t = threadIdx.x; t < nEp; t += L_THREADS) {
+            float s_ = 0.0f;
+            #pragma unroll
+            for (int w = 0; w < L_WARPS; w++) s_ += sAcc[(size_t)w * nEp + t];
+            dst[t] = s_;
         }
     }
     if (threadIdx.x == 0) TL_TRACE(13);
@@ -593,7 +641,12 @@ static int tl_fill(const TlJob &j, TlP &p, CUtensorMap *amap, CUtensorMap *bmap,
     if (const TlEpi *epi = j.epi) {
         p.mode = epi->mode; p.bias = epi->bias; p.actA = epi->actA; p.actF = epi->actF; p.layer = epi->layer; p.act_alpha = epi->act_alpha;
         p.W2 = epi->W2; p.B2 = epi->B2; p.Y2 = epi->Y2; p.P = epi->P; p.P2 = epi->P2; p.E2 = epi->E2; p.F = epi->F; p.O2 = epi->O2;
-        if (epi->mode == 2 && (p.ntiles != 1 || (j.N & 3) || epi->E2 > 32 || epi->E2 < 1)) return T4K_ENOSUP;
+        if ((epi->mode == 2 || epi->mode == 4) && (p.ntiles != 1 || (j.N & 3) || epi->E2 > 32 || epi->E2 < 1)) return T4K_ENOSUP;
+        if (epi->mode == 4) {
+            const int E2p = (epi->E2 + 3) & ~3, nEp = epi->E2 * j.N + E2p + ((j.N + 3) & ~3);
+            if ((size_t)L_WARPS * nEp * 4 > (size_t)(L_RAW * L_SLOT_B) - (size_t)L_BM * L_BN * 4 || !epi->T || !epi->Ylin || !epi->hpart) return T4K_ENOSUP;
+            p.T = epi->T; p.Ylin = epi->Ylin; p.hpart = epi->hpart;
+        }
         if (epi->gP) {
             const int EH = j.tA ? j.M : j.K;                                   // hidden width: K of the K-major operand, M of the M-major one
             if (EH > 128 || (EH & 3) || epi->gE2 < 1 || epi->gE2 > 32 || !epi->gT || !epi->gW2) return T4K_ENOSUP;
@@ -611,7 +664,7 @@ static int tl_fill(const TlJob &j, TlP &p, CUtensorMap *amap, CUtensorMap *bmap,
 
 // One launch for one or two problems.  Cluster size S and, per problem, K-split (split == S: a cluster is one tile) or none (split == 1: a
 // cluster is S tiles): the combination with the fewest k-blocks per CTA that keeps the whole grid co-resident (one wave).
-int gemm_tl_multi(const TlJob *jobs, int njobs, cudaStream_t st) {
+static int tl_launch(const TlJob *jobs, int njobs, cudaStream_t st, int *ctas_out, bool dry) {
     if (njobs < 1 || njobs > 2) return T4K_EINVAL;
     const int dev = tl_device();
     if (dev < 0) return T4K_EINVAL;
@@ -654,6 +707,8 @@ int gemm_tl_multi(const TlJob *jobs, int njobs, cudaStream_t st) {
         ncl[q] = (T * p.split + S - 1) / S;
         if (p.split > 1 && tl_knob(8)) part_flts += (size_t)T * p.split * L_BM * L_BN;
     }
+    if (ctas_out) *ctas_out = (ncl[0] + ncl[1]) * S;
+    if (dry) return 0;
     if (part_flts) {
         float *part = (float*)workspace(part_flts * sizeof(float), 7);
         if (!part) return T4K_ENOMEM;
@@ -678,6 +733,8 @@ int gemm_tl_multi(const TlJob *jobs, int njobs, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
+int gemm_tl_multi(const TlJob *jobs, int njobs, cudaStream_t st, int *ctas_out) { return tl_launch(jobs, njobs, st, ctas_out, false); }
+int gemm_tl_ctas(const TlJob *jobs, int njobs) { int n = 0; const int rc = tl_launch(jobs, njobs, nullptr, &n, true); return rc ? rc : n; }
 int gemm_tl(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB, int M, int N, int K, cudaStream_t st, const TlEpi *epi) {
     TlJob j{A, B, O, alpha, beta, tA, tB, M, N, K, epi};
     return gemm_tl_multi(&j, 1, st);

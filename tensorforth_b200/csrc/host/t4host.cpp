@@ -250,7 +250,7 @@ Model::~Model() {
         Tensor::destroy(*t);
     }
     if (_own_hot && _hot) Tensor::destroy(*_hot);
-    Runtime::free(_G); Runtime::free(_DG); Runtime::free(_M); Runtime::free(_V); Runtime::free(_seg_dev); Runtime::free(_cnt_dev); Runtime::free(_pdup);
+    Runtime::free(_G); Runtime::free(_DG); Runtime::free(_M); Runtime::free(_V); Runtime::free(_seg_dev); Runtime::free(_cnt_dev); Runtime::free(_pdup); Runtime::free(_hscratch);
     _drop_graphs();
     if (_loss_pin) { cudaFreeHost(_loss_pin); for (int b = 0; b < 2; b++) cudaEventDestroy((cudaEvent_t)_loss_ev[b]); }
 }
@@ -404,6 +404,15 @@ int Model::_ffused_linear(size_t i) {
     if ((mask_act(fn) || fn == T4K_L_SIGMOID) && i + 5 == n && ao.grad_fn == T4K_L_LINEAR && _layers[i + 3]->grad_fn == T4K_L_SOFTMAX) {
         Tensor &l2o = *_layers[i + 3], &po = *_layers[i + 4];
         DU *dup = (_want_pdup && _pdup) ? _pdup : nullptr;
+        _tail_done = false;
+        if (_fwd_tgt && _hscratch && train && mask_act(fn) && _fwd_tgt->numel == po.numel) {
+            // fused train step: forward tail + the head's backward on the same rows, one launch (the layer tensors get their backward values)
+            rc = t4k_linear_act_head_train(fn, in.data, in.grad[0]->data, in.grad[1]->data, lo.data, ao.data, lo.grad[4]->data, lo.xparm,
+                                           ao.grad[0]->data, ao.grad[1]->data, l2o.data, po.data, dup, _fwd_tgt->data, _hscratch, &_hncta,
+                                           N, E0, E1, (int)l2o.HWC(), ST);
+            if (rc == 0) { _tail_done = true; _pdup_valid = dup != nullptr; return 4; }
+            if (rc != T4K_ENOSUP) KCHK(rc);
+        }
         rc = t4k_linear_act_head_fwd(fn, in.data, in.grad[0]->data, in.grad[1]->data, lo.data, ao.data, lo.grad[4]->data, lo.xparm,
                                      ao.grad[0]->data, ao.grad[1]->data, l2o.data, po.data, dup, N, E0, E1, (int)l2o.HWC(), ST);
         if (rc != T4K_ENOSUP) { KCHK(rc); _pdup_valid = (rc == 0 && dup != nullptr); return 4; }
@@ -437,6 +446,18 @@ int Model::_bfused_head(Tensor &tgt, bool *skip_db) {
     Tensor *act = (n >= 5 && (mask_act(_layers[n - 4]->grad_fn) || _layers[n - 4]->grad_fn == T4K_L_DROPOUT)) ? _layers[n - 4] : nullptr;
     const int prev = act ? n - 5 : n - 4;
     Tensor *lin1 = (prev >= 0 && _layers[prev]->grad_fn == T4K_L_LINEAR && train) ? _layers[prev] : nullptr;
+    if (_tail_done) {
+        // the forward tail kernel of this step already wrote p - y, the head linear's dX and the activation backward (Model::forward, train tail);
+        // what is left are the head's parameter gradients: per-CTA partials -> dW2, dB2, dB1 on the side stream, joined at the end of the step
+        _tail_done = false;
+        cudaStream_t st = (cudaStream_t)ST;
+        cudaEventRecord(g_fork, st); cudaStreamWaitEvent(g_stream2, g_fork, 0);
+        KCHK(t4k_head_grad_finish(_hscratch, _hncta, E0, E1, x2.grad[2]->data, x2.grad[3]->data, lin1 ? lin1->grad[3]->data : nullptr, (t4k_stream_t)g_stream2));
+        cudaEventRecord(g_join, g_stream2);
+        _side_join = true;
+        *skip_db = lin1 != nullptr;
+        return prev;
+    }
     // Inside step_graph (a duplicate of the softmax output exists) with the hidden linear's dW on the side stream (a flatten in front of it
     // holds a second copy of X): the head kernel is NOT launched here.  Model::_blinear puts it on the side stream in front of the dW GEMM,
     // and the dX GEMM of the hidden layer — the critical path — evaluates p - y, the small linear's dX and the activation backward in its
@@ -645,6 +666,12 @@ int Model::_blinear(Tensor &in, Tensor &out, bool skip_db, Tensor *xdup, bool de
         const int N = (int)in.N(), E0 = (int)out.HWC(), E1 = (int)in.HWC();
         cudaStream_t st = (cudaStream_t)ST;
         if (!skip_db) KCHK(t4k_dbias(out.data, db.data, N, E0, ST));
+        if (!_hp.on) {
+            // dX and dW in ONE launch of the layer GEMM (X read from its duplicate): the conv block that follows writes the flatten backward itself
+            const int rcp = t4k_linear_bwd_pair(xdup->data, w.data, out.data, in.data, dw.data, N, E0, E1, ST);
+            if (rcp == 0) return 0;
+            if (rcp != T4K_ENOSUP) KCHK(rcp);
+        }
         cudaEventRecord(g_fork, st); cudaStreamWaitEvent(g_stream2, g_fork, 0);
         const bool hp = _hp.on; _hp.on = false;
         if (hp) {
@@ -963,7 +990,9 @@ int Model::_step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4
         if (has_dropout) t4k_rand_tick(ST);                    // replayed graphs draw a fresh dropout mask every step (rand.cu)
         if (x.ds) { _feed = &x; _feed_hot = tgt.data; }        // dataset feeding (normalise + one-hot): rides in the first fused block, else its own launch (forward)
         _want_pdup = loss_dev != nullptr; _pdup_valid = false;
+        _fwd_tgt = (train && fuse && tgt.numel == (*this)[-1].numel) ? &tgt : nullptr;     // backprop(tgt) follows at once: the forward tail may do the head's backward
         forward(input);
+        _fwd_tgt = nullptr;
         _want_pdup = false;
         // the loss does not feed the backward pass: when the head kernel left a duplicate of the softmax output (backprop overwrites
         // the original with p - y), the loss kernel — and its read-back — run on the side stream under the backward kernels
@@ -1003,6 +1032,15 @@ int Model::_step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4
         else if (x.loss_pin && loss_dev && !(side_loss && !_comm)) cudaMemcpyAsync(x.loss_pin, loss_dev, sizeof(DU), cudaMemcpyDeviceToHost, (cudaStream_t)ST);
     };
     if (loss_dev && !_pdup) _pdup = (DU*)Runtime::alloc((size_t)(*this)[-1].numel * sizeof(DU) + 64);   // not inside the capture below
+    if (!_hscratch && fuse && train) {                    // train tail: linear -> mask activation -> small linear -> softmax at the end of the model
+        const int n = (int)_layers.size();
+        if (n >= 5 && _layers[n - 5]->grad_fn == T4K_L_LINEAR && mask_act(_layers[n - 4]->grad_fn) && _layers[n - 3]->grad_fn == T4K_L_LINEAR &&
+            _layers[n - 2]->grad_fn == T4K_L_SOFTMAX) {
+            const int64_t nf = t4k_head_train_scratch_floats(_layers[n - 4]->grad_fn, (int)_layers[n - 4]->N(), (int)_layers[n - 4]->HWC(),
+                                                             (int)_layers[n - 5]->HWC(), (int)_layers[n - 2]->HWC());
+            if (nf > 0) _hscratch = (DU*)Runtime::alloc((size_t)nf * sizeof(DU) + 64);
+        }
+    }
     U64 key[12] = {0}; float f4[4] = {lr, b1, b2, wd};
     key[0] = (U64)input.data; key[1] = (U64)tgt.data; key[2] = (U64)lop; key[3] = (U64)loss_dev; key[4] = (U64)op;
     memcpy(&key[5], f4, 16); key[7] = (U64)train; key[8] = (U64)x.simg; key[9] = (U64)x.slab; key[10] = (U64)x.n; key[11] = (U64)x.loss_pin;

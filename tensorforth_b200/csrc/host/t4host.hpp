@@ -169,6 +169,9 @@ class Model {
     void    _feed_fallback();
     // classifier-head backward deferred onto the side stream (in front of the hidden linear's dW GEMM) while that layer's dX GEMM generates
     // its operand from the forward tensors (t4k_linear_dx_from_head): the arguments of the pending t4k_mlp_head_bwd
+    // the TRAIN TAIL inside step_graph (t4k_linear_act_head_train): the forward tail kernel already did the head's backward on its rows; the
+    // head's parameter gradients wait as per-CTA partials in _hscratch for t4k_head_grad_finish (side stream)
+    Tensor *_fwd_tgt = nullptr; bool _tail_done = false; DU *_hscratch = nullptr; int _hncta = 0;
     struct HeadPending { bool on = false; DU *P, *T, *Ylin, *X2, *F1, *Y1, *W2, *dW2, *dB2, *dB1; int N, E0, E1; } _hp;
     // optimizer split inside step_graph (single GPU): once every gradient but the first parameter layer's is final, the optimizer of the rest of
     // the arena runs on the side stream under the first layers' backward (_opt_push); the fused conv block applies the step to its own filter /

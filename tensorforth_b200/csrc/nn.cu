@@ -327,8 +327,60 @@ __global__ void __cluster_dims__(HB_CTAS, 1, 1) __launch_bounds__(T4K_THREADS) k
     cluster_sync_all();                                                            // nobody leaves while its smem is still being read
 }
 
+// dW2 | dB2 | dB1 += Σ_cta partial[cta] (CTA order: deterministic); layout of a partial: [E0][EH] | [E0 padded to 4] | [EH padded to 4]
+__global__ void __launch_bounds__(T4K_THREADS) k_head_grad_fin(const float *__restrict__ part, int ncta, int E0, int EH, float *dW2, float *dB2, float *dB1) {
+    pdl_wait(); pdl_trigger();
+    const int E0p = (E0 + 3) & ~3, nEp = E0 * EH + E0p + ((EH + 3) & ~3);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nEp) return;
+    float s_ = 0.0f;
+    for (int c = 0; c < ncta; c++) s_ += part[(size_t)c * nEp + t];
+    if (t < E0 * EH) dW2[t] += s_;
+    else if (t < E0 * EH + E0p) { if (t - E0 * EH < E0) dB2[t - E0 * EH] += s_; }
+    else if (t - E0 * EH - E0p < EH && dB1) dB1[t - E0 * EH - E0p] += s_;
+}
+
 } // namespace t4k
 using namespace t4k;
+
+static bool head_train_ok(int layer, int N, int EH, int E1, int E0) {
+    return (layer == T4K_L_RELU || layer == T4K_L_TANH || layer == T4K_L_SELU || layer == T4K_L_LEAKYRL || layer == T4K_L_ELU) &&
+           E0 >= 1 && E0 <= 32 && EH <= 128 && (EH & 3) == 0 && (E1 & 3) == 0 && N >= 32;
+}
+extern "C" int64_t t4k_head_train_scratch_floats(int layer, int N, int EH, int E1, int E0) {
+    if (!head_train_ok(layer, N, EH, E1, E0)) return 0;
+    TlEpi e{}; e.mode = 4; e.E2 = E0; e.T = (const float*)16; e.Ylin = (float*)16; e.hpart = (float*)16; e.layer = layer;
+    const TlJob j{(const float*)16, (const float*)16, (float*)16, 1.0f, 0.0f, 0, 1, N, EH, E1, &e};
+    if ((double)N * EH * E1 < 4.0e6) return 0;
+    const int ctas = gemm_tl_ctas(&j, 1);
+    if (ctas <= 0) return 0;
+    const int E0p = (E0 + 3) & ~3;
+    return (int64_t)ctas * (E0 * EH + E0p + ((EH + 3) & ~3));
+}
+extern "C" int t4k_linear_act_head_train(int layer, const float *X, const float *W1, const float *B1, float *Y1, float *A1, float *F1, float alpha,
+                                         const float *W2, const float *B2, float *Ylin, float *P, float *Pdup, const float *T,
+                                         float *scratch, int *ncta, int N, int EH, int E1, int E0, t4k_stream_t s) {
+    if (!X || !W1 || !B1 || !Y1 || !A1 || !F1 || !W2 || !B2 || !Ylin || !P || !T || !scratch || !ncta) return T4K_EINVAL;
+    if (!head_train_ok(layer, N, EH, E1, E0) || !gemm_tl_ok(X, W1, Y1, 0, 1, N, EH, E1, 1, 1) || !aligned16(W2) || !aligned16(F1) || !aligned16(A1) || !aligned16(Y1) || !aligned16(scratch))
+        return T4K_ENOSUP;
+    TlEpi e{}; e.mode = 4; e.bias = B1; e.actA = A1; e.actF = F1; e.layer = layer; e.act_alpha = alpha;
+    e.W2 = W2; e.B2 = B2; e.Y2 = Ylin; e.P = P; e.P2 = Pdup; e.E2 = E0; e.T = T; e.Ylin = Ylin; e.hpart = scratch;
+    const TlJob j{X, W1, Y1, 1.0f, 0.0f, 0, 1, N, EH, E1, &e};
+    return gemm_tl_multi(&j, 1, STRM(s), ncta);
+}
+extern "C" int t4k_head_grad_finish(const float *scratch, int ncta, int E0, int EH, float *dW2, float *dB2, float *dB1, t4k_stream_t s) {
+    if (!scratch || ncta < 1 || E0 < 1 || EH < 1 || !dW2 || !dB2) return T4K_EINVAL;
+    const int E0p = (E0 + 3) & ~3, nEp = E0 * EH + E0p + ((EH + 3) & ~3);
+    launch_pdl(k_head_grad_fin, dim3((nEp + T4K_THREADS - 1) / T4K_THREADS), dim3(T4K_THREADS), 0, STRM(s), scratch, ncta, E0, EH, dW2, dB2, dB1);
+    return check_launch();
+}
+extern "C" int t4k_linear_bwd_pair(const float *X, const float *W, const float *dY, float *dX, float *dW, int N, int E0, int E1, t4k_stream_t s) {
+    if (!X || !W || !dY || !dX || !dW || N < 1 || E0 < 1 || E1 < 1 || X == dX) return T4K_EINVAL;
+    if (!gemm_tl_ok(dY, W, dX, 0, 0, N, E1, E0, 1, 1) || !gemm_tl_ok(dY, X, dW, 1, 0, E0, E1, N, 1, 1)) return T4K_ENOSUP;
+    const TlJob jobs[2] = {{dY, W, dX, 1.0f, 0.0f, 0, 0, N, E1, E0, nullptr},           // dX[N,E1]  = dY[N,E0] @ W[E0,E1]
+                           {dY, X, dW, 1.0f, 1.0f, 1, 0, E0, E1, N, nullptr}};          // dW[E0,E1] += dY^T @ X[N,E1]
+    return gemm_tl_multi(jobs, 2, STRM(s));
+}
 
 extern "C" int t4k_linear_fwd(const float *X, const float *W, const float *B, float *Y, int N, int E0, int E1, t4k_stream_t s) {
     if (!X || !W || !B || !Y || N < 1 || E0 < 1 || E1 < 1) return T4K_EINVAL;

@@ -61,6 +61,10 @@ PROTOTYPES = {
     "t4k_dbias": (_i, [_p, _p, _i, _i, _p]),
     "t4k_linear_bwd": (_i, [_p] * 6 + [_i] * 4 + [_p]),
     "t4k_linear_bwd_ex": (_i, [_p] * 6 + [_i] * 5 + [_p]),
+    "t4k_head_train_scratch_floats": (_l, [_i] * 5),
+    "t4k_linear_act_head_train": (_i, [_i] + [_p] * 6 + [_f] + [_p] * 8 + [_i] * 4 + [_p]),
+    "t4k_head_grad_finish": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
+    "t4k_linear_bwd_pair": (_i, [_p] * 5 + [_i] * 3 + [_p]),
     "t4k_linear_bwd_from_head": (_i, [_p] * 8 + [_i] * 4 + [_p]),
     "t4k_linear_dx_from_head": (_i, [_p] * 6 + [_i] * 4 + [_p]),
     "t4k_linear_bwd_act": (_i, [_p] * 8 + [_i] * 5 + [_p]),

@@ -344,6 +344,56 @@ def test_linear_bwd_from_head(N, E2, EH, E1, act):
     assert_exact(host(got_dw2), a2, "deterministic"); assert_exact(host(got_dx2), host(got_dx), "deterministic")
 
 
+@pytest.mark.parametrize("layer", [t4.L_RELU, t4.L_LEAKYRL, t4.L_TANH])
+@pytest.mark.parametrize("N,E1,EH,E0", [(512, 1960, 100, 10), (200, 516, 128, 16), (64, 784, 64, 3)])
+def test_linear_act_head_train_equals_fwd_then_head_bwd(layer, N, E1, EH, E0):
+    """the TRAIN TAIL (forward tail + the head's backward on the same rows, one launch) leaves the layer tensors exactly as
+    t4k_linear_act_head_fwd followed by t4k_mlp_head_bwd leaves them (same bits), and its per-CTA partials add up to that kernel's
+    parameter gradients (other summation order: FP32 rounding noise)"""
+    X, W1, B1 = rnd(N, E1), rnd(EH, E1) * 0.05, rnd(EH)
+    W2, B2 = rnd(E0, EH) * 0.3, rnd(E0)
+    T = orc.onehot(np.arange(N) % E0, E0)
+    dW20, dB20, dB10 = rnd(E0, EH), rnd(E0), rnd(EH)
+    Xd, W1d, B1d, W2d, B2d, Td = dev(X), dev(W1), dev(B1), dev(W2), dev(B2), dev(T)
+    L = lib()
+    # reference: two launches
+    y1a, a1a, f1a, y2a, pa, pda = zeros(N, EH), zeros(N, EH), zeros(N, EH), zeros(N, E0), zeros(N, E0), zeros(N, E0)
+    ok(L.t4k_linear_act_head_fwd(layer, ptr(Xd), ptr(W1d), ptr(B1d), ptr(y1a), ptr(a1a), ptr(f1a), 0.1, ptr(W2d), ptr(B2d), ptr(y2a), ptr(pa), ptr(pda),
+                                 N, EH, E1, E0, None))
+    dwa, dba, db1a = dev(dW20), dev(dB20), dev(dB10)
+    ok(L.t4k_mlp_head_bwd(ptr(pa), ptr(Td), ptr(y2a), ptr(a1a), ptr(f1a), ptr(y1a), ptr(W2d), ptr(dwa), ptr(dba), ptr(db1a), N, E0, EH, 1, None))
+    # train tail
+    nf = L.t4k_head_train_scratch_floats(layer, N, EH, E1, E0)
+    if nf == 0:
+        pytest.skip("shape outside the train tail's envelope (the caller keeps the two launches)")
+    y1b, a1b, f1b, y2b, pb, pdb = zeros(N, EH), zeros(N, EH), zeros(N, EH), zeros(N, E0), zeros(N, E0), zeros(N, E0)
+    scratch = zeros(int(nf))
+    ncta = C.c_int(0)
+    ok(L.t4k_linear_act_head_train(layer, ptr(Xd), ptr(W1d), ptr(B1d), ptr(y1b), ptr(a1b), ptr(f1b), 0.1, ptr(W2d), ptr(B2d), ptr(y2b), ptr(pb), ptr(pdb),
+                                   ptr(Td), ptr(scratch), C.byref(ncta), N, EH, E1, E0, None), "train tail")
+    dwb, dbb, db1b = dev(dW20), dev(dB20), dev(dB10)
+    ok(L.t4k_head_grad_finish(ptr(scratch), ncta.value, E0, EH, ptr(dwb), ptr(dbb), ptr(db1b), None))
+    for a, b, nm in ((y1a, y1b, "Y1 <- dY1"), (a1a, a1b, "A1 <- dX2"), (f1a, f1b, "F1"), (y2a, y2b, "Ylin <- p - y"), (pa, pb, "P <- p - y"), (pda, pdb, "Pdup = p")):
+        assert_exact(host(b), host(a), nm)
+    assert_close(host(dwb), host(dwa), rtol=1e-5, what="dW2"); assert_close(host(dbb), host(dba), rtol=1e-5, what="dB2")
+    assert_close(host(db1b), host(db1a), rtol=1e-5, what="dB1")
+
+
+@pytest.mark.parametrize("N,E0,E1", [(512, 100, 1960), (1024, 512, 784), (1024, 256, 512), (96, 36, 48)])
+def test_linear_bwd_pair(N, E0, E1):
+    """dX and dW of a linear layer in one launch of the layer GEMM == the two GEMM calls (FP32-grade; splits may differ)"""
+    X, W, dY, dW0 = rnd(N, E1), rnd(E0, E1), rnd(N, E0), rnd(E0, E1)
+    dx, dw = zeros(N, E1), dev(dW0)
+    rc = lib().t4k_linear_bwd_pair(ptr(dev(X)), ptr(dev(W)), ptr(dev(dY)), ptr(dx), ptr(dw), N, E0, E1, None)
+    if rc == t4.ENOSUP:
+        pytest.skip("pair does not fit one co-resident wave: the caller uses t4k_linear_bwd_ex")
+    ok(rc, "bwd pair")
+    assert_close(host(dx), orc.gemm(dY, W), rtol=1e-4, what="dX")
+    assert_close(host(dw), orc.gemm(dY, X, O=dW0, alpha=1.0, beta=1.0, tA=True), rtol=1e-4, what="dW")
+    assert_close(host(dx), gemm_ref64(dY, W, np.zeros((N, E1)), 1.0, 0.0, 0, 0), rtol=1e-5, what="dX vs f64")
+    assert_close(host(dw), gemm_ref64(dY, X, dW0, 1.0, 1.0, 1, 0), rtol=1e-5, what="dW vs f64")
+
+
 @pytest.mark.parametrize("N,E0,E1", [(1024, 512, 784), (512, 100, 1960), (1024, 256, 512), (96, 36, 48)])
 def test_linear_bwd_act(N, E0, E1):
     """_blinear + the _bactivate in front of it, mask multiply in the dX GEMM's epilogue: same tensors as the two calls"""

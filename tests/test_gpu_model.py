@@ -258,9 +258,11 @@ def test_step_graph_equals_eager():
         th.sync(); losses_a.append(float(la.cpu()[0]))
         assert gb.step_graph(X, Y, t4.LOSS_CE, C.c_void_p(lb.data_ptr()), optimizer=2, lr=0.001) == 0
         th.sync(); losses_b.append(float(lb.cpu()[0]))
-    assert losses_a == losses_b, (losses_a, losses_b)          # same kernels, same order → same bits
+    # the captured step takes the train tail (head backward inside the forward tail kernel, head parameter gradients summed from per-CTA
+    # partials) and the one-launch dX/dW pair: same arithmetic, other summation orders -> equal within FP32 rounding noise
+    assert np.allclose(losses_a, losses_b, rtol=2e-6, atol=0), (losses_a, losses_b)
     for i in (0, 4, 6):
-        assert np.array_equal(ga.w(i).numpy(), gb.w(i).numpy())
+        assert_close(gb.w(i).numpy(), ga.w(i).numpy(), rtol=2e-5, what="weights of layer %d" % i)
 
 
 @pytest.mark.parametrize("kind,N", [("mnist", 32), ("toycnn", 3)])
