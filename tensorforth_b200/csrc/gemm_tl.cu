@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const __grid_constant_
         for (int i = 0; i < nkb && i < L_RAW; i++) tma_issue(i);
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * L_BN);                         // two accumulators of 128 fp32 columns
-    if (active && p.mode == 2 && warp >= 2) {                                         // head weights: asynchronous copies, published by the barrier in front of the reduction
+    if (active && (p.mode == 2 || p.mode == 4) && warp >= 2) {                                         // head weights: asynchronous copies, published by the barrier in front of the reduction
         const int EH = p.N, tot = p.E2 * EH;
         for (int t = threadIdx.x - 64; t < tot; t += L_THREADS - 64) cp_async4(sW2 + t, p.W2 + t, true);
         cp_async_commit();
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const __grid_constant_
             *reinterpret_cast<float4*>(park + tl_park_off(r, (h * CW + j) >> 2)) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         if (warp == 2 + L_NCONV && lane == 0) TL_TRACE(10);
     }
-    if (active && p.mode == 2) cp_async_wait_all();
+    if (active && (p.mode == 2 || p.mode == 4)) cp_async_wait_all();
     tc_fence_before();
     __syncthreads();
     // split-K partials through L2: distributed shared memory serves ~20 B/clk per SM (60 KiB of peer tiles: 2 us) and keeps every CTA resident
@@ -644,7 +644,7 @@ static int tl_fill(const TlJob &j, TlP &p, CUtensorMap *amap, CUtensorMap *bmap,
         if ((epi->mode == 2 || epi->mode == 4) && (p.ntiles != 1 || (j.N & 3) || epi->E2 > 32 || epi->E2 < 1)) return T4K_ENOSUP;
         if (epi->mode == 4) {
             const int E2p = (epi->E2 + 3) & ~3, nEp = epi->E2 * j.N + E2p + ((j.N + 3) & ~3);
-            if ((size_t)L_WARPS * nEp * 4 > (size_t)(L_RAW * L_SLOT_B) - (size_t)L_BM * L_BN * 4 || !epi->T || !epi->Ylin || !epi->hpart) return T4K_ENOSUP;
+            if ((size_t)L_WARPS * nEp * 4 > (size_t)L_RING_B - (size_t)L_BM * L_BN * 4 || !epi->T || !epi->Ylin || !epi->hpart) return T4K_ENOSUP;
             p.T = epi->T; p.Ylin = epi->Ylin; p.hpart = epi->hpart;
         }
         if (epi->gP) {

@@ -366,6 +366,11 @@ def test_linear_act_head_train_equals_fwd_then_head_bwd(layer, N, E1, EH, E0):
     nf = L.t4k_head_train_scratch_floats(layer, N, EH, E1, E0)
     if nf == 0:
         pytest.skip("shape outside the train tail's envelope (the caller keeps the two launches)")
+    # a forward tail with OTHER head weights in between: the train tail must stage W2 itself (shared memory outlives a kernel: a launch
+    # that relied on what the reference launch above left there would still pass without this)
+    W2x, junk = dev(rnd(E0, EH) * 3.0), [zeros(N, EH) for _ in range(3)] + [zeros(N, E0) for _ in range(3)]
+    ok(L.t4k_linear_act_head_fwd(layer, ptr(Xd), ptr(W1d), ptr(B1d), ptr(junk[0]), ptr(junk[1]), ptr(junk[2]), 0.1, ptr(W2x), ptr(B2d), ptr(junk[3]), ptr(junk[4]),
+                                 ptr(junk[5]), N, EH, E1, E0, None))
     y1b, a1b, f1b, y2b, pb, pdb = zeros(N, EH), zeros(N, EH), zeros(N, EH), zeros(N, E0), zeros(N, E0), zeros(N, E0)
     scratch = zeros(int(nf))
     ncta = C.c_int(0)
@@ -472,6 +477,27 @@ def test_gemm_4096_property():
     o3 = zeros(n, n)
     ok(lib().t4k_gemm_ex(t4.GEMM_TC, ptr(A), ptr(B), ptr(o3), 1.0, 0.0, 0, 0, n, n, n, 1, 1, 0, 0, 0, None))
     assert_close(o3[idx].cpu().numpy(), ref_rows, rtol=1e-5, what="4096 rows, 3xTF32")
+
+
+@pytest.mark.parametrize("engine", [t4.GEMM_TC, t4.GEMM_AUTO])
+def test_gemm_4096_vs_reference_kernel(engine):
+    """BASELINE config 2 at full size against the REFERENCE'S OWN kernel (k_gemm_tile_claude, src/t4math.cu:478-583, run through
+    oracle/_ref/refkern on this GPU): both tensor-core engines (3xTF32, and BF16x3 which AUTO selects at this size) within the north
+    star's 1e-4 of the reference output"""
+    from oracle import refkern
+    if not refkern.available():
+        pytest.skip("oracle/_ref/refkern not built (needs the reference sources; built in the build container)")
+    n = 4096
+    rng = np.random.default_rng(5)
+    A = (rng.random((n, n), dtype=np.float32) * 2 - 1).astype(np.float32)
+    B = (rng.random((n, n), dtype=np.float32) * 2 - 1).astype(np.float32)
+    ref = refkern.one("gemm", ints=(3, 0, 0, n, n, n, 1), flts=(1.0, 0.0), arrs=(A, B, np.zeros((n, n), np.float32)))[0].reshape(n, n)
+    o = zeros(n, n)
+    ok(lib().t4k_gemm_ex(engine, ptr(dev(A)), ptr(dev(B)), ptr(o), 1.0, 0.0, 0, 0, n, n, n, 1, 1, 0, 0, 0, None), "gemm 4096")
+    got = host(o)
+    assert_close(got, ref, rtol=1e-4, what="4096^3 vs the reference kernel")
+    rms = np.sqrt(np.mean((got.astype(np.float64) - ref) ** 2)) / np.sqrt(np.mean(ref.astype(np.float64) ** 2))
+    assert rms < 1e-5, rms
 
 
 # ------------------------------------------------------------------ fused linear epilogues / classifier head
