@@ -87,6 +87,10 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
 
 
+WORKLOAD = ("MNIST CNN (examples/t4_40a.4th:10-13) conv3x3(1->10)+maxpool2+relu+flatten+linear100+relu+linear10+softmax, "
+            "N=%d per GPU, step = forward + loss.ce + backprop + nn.adam(lr=1e-3)" % 512)
+
+
 # --------------------------------------------------------------------------------------- reference arm
 def ref_script(kind, warm, steps, batch):
     """Forth text both builds could run (SURVEY.md §8d 'synthetic step script')"""
@@ -143,7 +147,7 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": "mnist_cnn_train_samples_per_sec", "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "MNIST CNN (t4_40a.4th:10-13) N=%d fwd+loss.ce+backprop+nn.adam" % BATCH,
+            "config": {"workload": WORKLOAD,
                        "note": "reference = chochain/tensorForth's own CUDA kernels, unmodified, built for sm_100 (oracle/ref/build_ref.sh), "
                                "1 GPU (it has no multi-GPU and no CPU tensor path); timed with its own `clock` word incl. its per-kernel syncs"}}
     if ms is None:
@@ -171,7 +175,14 @@ def reference_arm(args):
 def cpu_port_baseline(steps=4, batch=BATCH):
     """the oracle's Model restatement (C kernels, OpenMP) on the host cores: bounded sample of the same workload"""
     import numpy as np
+    import ctypes
     from oracle import oracle as orc
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the baseline is "the host cores of the box", so the OpenMP team is sized here
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(cores))
+    except OSError:
+        cores = int(os.environ.get("OMP_NUM_THREADS", cores))
     om = orc.OracleModel(batch, 28, 28, 1, seed=1)
     om.add(orc.L_CONV, 10, 0.5, [3, 1, 1, 1]).add(orc.L_MAXPOOL, 2).add(orc.L_RELU).add(orc.L_FLATTEN)
     om.add(orc.L_LINEAR, 100, 1.0).add(orc.L_RELU).add(orc.L_LINEAR, 10, 1.0).add(orc.L_SOFTMAX)
@@ -187,7 +198,6 @@ def cpu_port_baseline(steps=4, batch=BATCH):
     while n < steps or (time.time() - t0 < 10.0 and n < 200):
         step(); n += 1
     dt = time.time() - t0
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return batch * n / dt, cores, "%d train steps of N=%d (%.1f s) with the C oracle, OpenMP" % (n, batch, dt)
 
 
@@ -430,20 +440,39 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # kernels of ONE step as the timed loop runs it: the first graph step captures (every launch wrapper counts at capture time, a replay launches
+    # exactly those nodes); the eager count above is what --eager would launch
+    n0 = L.t4k_launch_count()
+    step()
+    if graph:
+        launches_per_step = L.t4k_launch_count() - n0
     for _ in range(args.warmup):
         step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as cs:
+    # The timed region is EXACTLY --steps steps between two events (barrier + synchronize on both sides, max over ranks).  A 20-step window
+    # of this workload is 1.4 ms — one scheduling hiccup of the host thread is 5 % of it — so the window is repeated and the MEDIAN window is
+    # the line's value; every window's time is in "timing".
+    nwin = max(1, min(15, 300 // max(args.steps, 1)))
+
+    def window(run):
+        barrier()
         e0.record(lib_stream)
-        for _ in range(args.steps):
-            step()
+        run()
         e1.record(lib_stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        final_loss = float(loss_dev[0].cpu()) / (world if fused else 1)   # last timed step: global mean (fused: the loss sums ride in the exchange) or this rank's shard
+        w = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.cpu()[0])
+            t = torch.tensor([w], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); w = float(t.cpu()[0])
+        return w
+
+    def steps_k():
+        for _ in range(args.steps):
+            step()
+    with ClockSampler(local) as cs:
+        wins = sorted(window(steps_k) for _ in range(nwin))
+        ms = wins[len(wins) // 2] if len(wins) & 1 else 0.5 * (wins[len(wins) // 2 - 1] + wins[len(wins) // 2])
+        final_loss = float(loss_dev[0].cpu()) / (world if fused else 1)   # last timed step: global mean (fused: the loss sums ride in the exchange) or this rank's shard
         if ms < 600:                                           # keep the GPU under the same load so nvidia-smi sees clocks under load
             for _ in range(min(20000, int(800.0 / max(ms / args.steps, 1e-3)))):   # same count on every rank (collective inside)
                 step()
@@ -485,20 +514,20 @@ def main():
         lready[(nsteps - 1) & 1].synchronize(); losses_seen.append(float(lh[(nsteps - 1) & 1][0]))
 
     e2e_run(max(args.warmup, 4))
-    losses_seen.clear()
-    barrier()
-    e0.record(lib_stream)
-    e2e_run(args.steps)
-    e1.record(lib_stream)
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    assert len(losses_seen) == args.steps
-    if world > 1:
-        t = torch.tensor([ms_e2e], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_e2e = float(t.cpu()[0])
+    wins_e2e = []
+    for _ in range(nwin):
+        losses_seen.clear()
+        wins_e2e.append(window(lambda: e2e_run(args.steps)))
+        assert len(losses_seen) == args.steps
+    wins_e2e.sort()
+    ms_e2e = wins_e2e[len(wins_e2e) // 2] if len(wins_e2e) & 1 else 0.5 * (wins_e2e[len(wins_e2e) // 2 - 1] + wins_e2e[len(wins_e2e) // 2])
     e2e = {"value": BATCH * world * args.steps / (ms_e2e / 1e3), "unit": "samples/s",
            "h2d_bytes_per_step": int(x8.numel() + y8.numel()), "d2h_bytes_per_step": 4,
            "note": "per step: U8 pixels + U8 labels from pinned host memory -> async H2D (copy stream, double buffered) -> on-device normalise "
-                   "(u8-128)/128 + one-hot, folded into the step's first kernel (t4k_conv_pool_relu_fwd_feed) -> train step -> loss D2H read on the host (pipelined by one step); one host call per iteration"}
+                   "(u8-128)/128 + one-hot, folded into the step's first kernel (t4k_conv_pool_relu_fwd_feed) -> train step -> loss D2H read on the host (pipelined by one step); one host call per iteration.  "
+                   "It can come out a hair ABOVE `value`: the feed kernel reads 0.4 MB of U8 where the resident-input step copies 1.6 MB of FP32 into the model's input layer, "
+                   "and the H2D copy + loss read-back overlap the step on their own streams",
+           "window_ms": [round(w, 4) for w in wins_e2e]}
 
     gan = conv = None
     if not args.no_extras:
@@ -555,17 +584,20 @@ def main():
     dW1, dB1, dW2, dB2, dX1 = f32(100, 1960), f32(100), f32(10, 100), f32(10), f32(N, 1960)
     G_, DG_, M_, V_ = (f32(197710) for _ in range(4))
     lossd = torch.zeros(4, device="cuda")
+    Pd = f32(N, 10)
+    hscr = torch.zeros(max(int(L.t4k_head_train_scratch_floats(t4.L_RELU, N, 100, 1960, 10)), 4), device="cuda")
+    hncta = C.c_int(0)
     fl = lambda *ts: sum(t.numel() for t in ts) * 4
     kernels = [  # (name, call, algorithmic bytes = every operand read once / every result written once)
         ("conv_pool_relu_fwd (+input copy, +flatten)", lambda h: L.t4k_conv_pool_relu_fwd(p(I), p(F), p(Bv), p(I0), p(cO), p(pO), p(aO), p(aF), p(fO), N, 28, 28, 1, 28, 28, 10, 3, 1, 1, h),
          fl(I, I0, cO, pO, aO, aF, fO)),
-        ("linear_act_head_fwd 1960->100 relu ->10 softmax (GEMM + fused finish/bias/relu/head)",
-         lambda h: L.t4k_linear_act_head_fwd(t4.L_RELU, p(fO), p(W1), p(B1), p(Y1), p(A1), p(F1), 0.0, p(W2), p(B2), p(Y2), p(Pp), None, N, 100, 1960, 10, h),
-         fl(fO, W1, Y1, A1, F1, W2, Y2, Pp)),
-        ("loss.ce", lambda h: L.t4k_loss(t4.LOSS_CE, p(Pp), p(Tt), N * 10, N, p(lossd), h), fl(Pp, Tt)),
-        ("mlp_head_bwd (p-y, dB2,dW2,dX2, relu', dB1)", lambda h: L.t4k_mlp_head_bwd(p(Pp), p(Tt), p(Y2), p(A1), p(F1), p(Y1), p(W2), p(dW2), p(dB2), p(dB1), N, 10, 100, 1, h),
-         fl(Pp, Tt, Pp, Y2, A1, A1, F1, Y1, W2)),
-        ("linear_bwd 1960->100 (dW1 += , dX1)", lambda h: L.t4k_linear_bwd_ex(p(fO), p(W1), p(Y1), p(dX1), p(dW1), p(dB1), N, 100, 1960, 1, 1, h), fl(fO, Y1, dW1, dW1, Y1, W1, dX1)),
+        ("linear_act_head_train 1960->100 relu ->10 softmax + the head's backward on the same rows (layer GEMM, tcgen05, mode 4)",
+         lambda h: L.t4k_linear_act_head_train(t4.L_RELU, p(fO), p(W1), p(B1), p(Y1), p(A1), p(F1), 0.0, p(W2), p(B2), p(Y2), p(Pp), p(Pd), p(Tt), p(hscr), C.byref(hncta), N, 100, 1960, 10, h),
+         fl(fO, W1, Y1, A1, F1, W2, Y2, Pp, Pd, Tt)),
+        ("loss.ce (side stream)", lambda h: L.t4k_loss(t4.LOSS_CE, p(Pd), p(Tt), N * 10, N, p(lossd), h), fl(Pd, Tt)),
+        ("head_grad_finish (dW2, dB2, dB1 from per-CTA partials; side stream)", lambda h: L.t4k_head_grad_finish(p(hscr), max(hncta.value, 1), 10, 100, p(dW2), p(dB2), p(dB1), h),
+         hscr.numel() * 4 + fl(dW2, dW2, dB2, dB1)),
+        ("linear_bwd_pair 1960->100 (dX1 and dW1 += in one launch of the layer GEMM)", lambda h: L.t4k_linear_bwd_pair(p(fO), p(W1), p(Y1), p(dX1), p(dW1), N, 100, 1960, h), fl(fO, Y1, dW1, dW1, Y1, W1, dX1)),
         ("conv_pool_relu_bwd (flatten', relu', pool', dF,dB,dX)", lambda h: L.t4k_conv_pool_relu_bwd(p(dY), p(aO), p(aF), p(pO), p(cO), p(I0), p(dXb), p(F), p(dF), p(dB), N, 28, 28, 1, 28, 28, 10, 3, 1, 1, 1, h),
          fl(dY, aF, cO, I0, aO, pO, cO, I0, dXb)),
         ("adam (197710 params)", lambda h: L.t4k_adam(p(G_), p(DG_), p(M_), p(V_), 1e-3, 0.9, 0.999, 197710, h), 7 * 197710 * 4),
@@ -599,13 +631,13 @@ def main():
     out = {"metric": "mnist_cnn_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "MNIST CNN (examples/t4_40a.4th:10-13) conv3x3(1->10)+maxpool2+relu+flatten+linear100+relu+linear10+softmax, "
-                                  "N=%d per GPU, step = forward + loss.ce + backprop + nn.adam(lr=1e-3)" % BATCH,
+           "config": {"workload": WORKLOAD,
                       "global_batch": BATCH * world, "parallelism": "dp%d" % world if world > 1 else "single",
                       "cuda_graph": bool(graph), "exchange": exchange,
                       "l2": "working set per step ~190 MB > 126 MB L2; no explicit flush (back-to-back steps is the workload)"},
            "clocks": cs.summary(), "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
            "launches_per_step": int(launches_per_step), "final_loss": final_loss,
+           "timing": {"windows": nwin, "steps_per_window": args.steps, "value_from": "median window", "window_ms": [round(w, 4) for w in wins]},
            "roofline": roofline, "calls": ktab}
 
     # ---- extras: the other two headline numbers of BASELINE.json (1 GPU only)

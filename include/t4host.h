@@ -117,6 +117,14 @@ int   t4h_model_arena(t4h_model m, float **G, float **DG, int64_t *total);
 /* data parallel: attach a connected t4k_comm_t (include/t4k.h); from then on sgd/adam/adamw — also inside step_graph —
  * sum the gradient arena over the ranks inside the optimizer kernel; scal[0..nscal) device floats ride along (summed) */
 int   t4h_model_dp_attach(t4h_model m, void *comm, float *scal, int nscal);
+/* this model holds shard `rank` of `world` equal shards of the global batch: dropout masks come from the shard's global element offsets, batch-norm
+ * statistics are summed over the ranks on `comm_stat` (a t4k_comm_t of its own, capacity >= 4 x t4h_model_bn_channels; may be NULL without batchnorm).
+ * A model with batchnorm layers refuses t4h_model_dp_attach until this was called with a communicator. */
+int   t4h_model_dp_shard(t4h_model m, int rank, int world, void *comm_stat);
+int   t4h_model_bn_channels(t4h_model m);        /* widest batchnorm layer (0: none) */
+int   t4h_tensor_rand_sharded(t4h_tensor t, int opt, int rank, int world);   /* t4k_rand_sharded on a batch-major tensor holding shard `rank` */
+void *t4h_side_stream(void);                     /* the side stream of the current lane (work forked inside a step) */
+int   t4h_use_lane(int lane);                    /* tests: switch the process to stream set `lane` (0..3); lane 0 is the default */
 int   t4h_model_step_graph(t4h_model m, t4h_tensor input, t4h_tensor tgt, int loss_op, float *loss_dev,
                            int optimizer, float lr, float b1, float b2, float wd);
 

@@ -40,6 +40,7 @@ extern "C" {
 #define T4K_ENOMEM  (-3)               /* workspace allocation failed */
 
 typedef void *t4k_stream_t;            /* cudaStream_t */
+typedef struct t4k_comm *t4k_comm_t;     /* data-parallel communicator (see "data-parallel extras" below) */
 
 /* math_op — identical numbering to src/t4math.h:25-56 */
 enum t4k_math_op {
@@ -78,7 +79,7 @@ int         t4k_device_count(void);                    /* 0 when no CUDA device/
 int         t4k_sm_count(void);                        /* SMs of the current device    */
 int         t4k_sync(t4k_stream_t stream);             /* cudaStreamSynchronize        */
 long        t4k_launch_count(void);                    /* kernels launched by this library so far */
-int         t4k_set_workspace_bank(int bank);          /* 0 / 1: which set of library workspaces the following calls use — a caller that forks
+int         t4k_set_workspace_bank(int bank);          /* 0..7: which set of library workspaces the following calls use — a caller that forks
                                                           * work onto a second stream gives that stream its own bank; returns the previous one */
 int         t4k_set_pdl(int on);                       /* programmatic dependent launch for the short kernels (default off, or T4K_PDL=1); returns the previous setting */
 
@@ -243,6 +244,14 @@ int t4k_pool_bwd(int layer, float *I, const float *dO, int N, int H1, int W1, in
  * ([C,2C) and [2C,3C) receive mean(dy), mean(dy*xhat)); if train: dgamma += mean(dy*xhat), dbeta += mean(dy) */
 int t4k_batchnorm_bwd(const float *dO, const float *XH, float *dX, const float *gamma,
                       float *dgamma, float *dbeta, float *scratch3C, int N, int HW, int C, int train, t4k_stream_t s);
+/* data parallel (SURVEY.md §8e collective 2): the same two layers over a batch SHARDED across the ranks of `comm` — the per-channel sums
+ * (Σx, Σx² forward; Σdy, Σdy·x̂ backward; 2C floats) are SUM-all-reduced between the statistics pass and the apply pass, N_global = samples of
+ * the whole batch.  dgamma / dbeta receive this rank's share (local sum / global rows): the gradient exchange adds the shares up to the
+ * reference's means (nmath.cu:378-381).  `comm`: a communicator of its own, capacity >= 4C (not the gradient arena's). */
+int t4k_batchnorm_fwd_dp(t4k_comm_t comm, const float *I, float *O, float *XH, const float *gamma, const float *beta,
+                         float *scratch3C, int N, int N_global, int HW, int C, t4k_stream_t s);
+int t4k_batchnorm_bwd_dp(t4k_comm_t comm, const float *dO, const float *XH, float *dX, const float *gamma,
+                         float *dgamma, float *dbeta, float *scratch3C, int N, int N_global, int HW, int C, int train, t4k_stream_t s);
 
 /* ---- fused CNN block: conv2d → maxpool(2) → relu (→ flatten), the layer group of examples/t4_40a.4th:11-12.
  * One launch each way; writes exactly the layer tensors the per-layer calls write (forward.cu:83-155,201-228;
@@ -299,7 +308,6 @@ int t4k_conv_pool_relu_bwd_opt(const float *dY, float *actO, const float *actF, 
  * handles (torch.distributed / MPI / anything) and connects.  The exchange itself is one kernel per call over NVLink
  * peer stores (tensorforth_b200/csrc/comm.cu), CUDA-graph capturable; sums are taken in rank order, so every rank
  * holds bit-identical results.  Every rank must issue the same sequence of calls with the same lengths. */
-typedef struct t4k_comm *t4k_comm_t;
 #define T4K_COMM_HANDLE_BYTES 64
 int t4k_comm_create(int rank, int world, int64_t cap_floats, t4k_comm_t *out, void *handle64);
 int t4k_comm_connect(t4k_comm_t c, const void *handles /* world x T4K_COMM_HANDLE_BYTES, rank order */);
@@ -332,6 +340,9 @@ int64_t t4k_dp_push(t4k_comm_t c, const float *DG, int64_t from, int64_t total, 
  * XORWOW stream is seeded with time(), so bit parity is not defined). */
 int t4k_rand_seed(uint64_t seed);
 int t4k_rand(float *d, int64_t n, int opt, float bias, float scale, t4k_stream_t s);
+/* this rank's shard [before, before + n) of a batch-major tensor of global_n elements, drawn with the counters a single device holding the
+ * whole tensor would use (per-rank Philox offset = global element index); every rank advances the stream by global_n */
+int t4k_rand_sharded(float *d, int64_t n, int64_t before, int64_t global_n, int opt, float bias, float scale, t4k_stream_t s);
 int t4k_rand_at(float *d, int64_t n, int opt, float bias, float scale, uint64_t seed, uint64_t offset, t4k_stream_t s);
 /* CUDA-graph replays: a captured t4k_rand has its seed and offset baked in; t4k_rand adds a device-side replay epoch (x 2^40) to its
  * counter, and t4k_rand_tick — put once at the head of a captured sequence that draws — advances it, so that every replay draws

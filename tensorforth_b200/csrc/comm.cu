@@ -181,6 +181,20 @@ static CommDev devview(const t4k_comm *c) {
     d.epoch = c->epoch; d.err_host = c->err_dev; d.spin_limit = c->spin_limit; d.cap = c->cap; d.rank = c->rank; d.world = c->world; d.ch4 = c->ch4;
     return d;
 }
+// An SM changes its L1 / shared-memory split only when it is empty.  Exchange kernels WAIT — resident on every SM — and would pin the split
+// they were launched with (they use no shared memory: the smallest) for as long as they wait: a kernel of another stream that needs a larger
+// carve-out (the fused conv blocks, the layer GEMM) could not start next to them.  One GPU per rank never runs anything next to its own
+// exchange; several ranks of one process on one device (the single-GPU data-parallel tests) do.  The exchange reads through L2 (__ldcg,
+// peer stores), so asking for the largest shared-memory split costs it nothing.
+static void exchange_carveout() {
+    static bool done[16];
+    const int dev = cur_device();
+    if (dev < 0 || dev >= 16 || done[dev]) return;
+    const void *k[] = {(const void*)k_dp_exchange<-1, true>, (const void*)k_dp_exchange<0, true>, (const void*)k_dp_exchange<0, false>,
+                       (const void*)k_dp_exchange<1, true>, (const void*)k_dp_exchange<2, true>, (const void*)k_dp_exchange<3, true>};
+    for (const void *f : k) if (cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) cudaGetLastError();
+    done[dev] = true;
+}
 static bool ready(const t4k_comm *c) {
     if (!c || !c->base) return false;
     for (int i = 0; i < c->world; i++) if (!c->peer[i]) return false;
@@ -209,6 +223,7 @@ int t4k_comm_create(int rank, int world, int64_t cap_floats, t4k_comm_t *out, vo
     while ((cap4 + ch4 - 1) / ch4 > COMM_MAXB) ch4 += 32;
     c->ch4 = (int)ch4;
     if (cudaGetDevice(&c->dev) != cudaSuccess) { cudaGetLastError(); delete c; return T4K_EINVAL; }
+    exchange_carveout();
     c->bytes = (size_t)COMM_FLAGB + (size_t)2 * world * (size_t)(c->cap + COMM_NSCAL) * 4;
     cudaError_t e = cudaMalloc((void**)&c->base, c->bytes);
     if (e != cudaSuccess) { cudaGetLastError(); delete c; return T4K_ENOMEM; }

@@ -15,9 +15,19 @@
 namespace t4 {
 
 // =============================================================================== Runtime
-static cudaStream_t g_stream = nullptr, g_stream2 = nullptr;      // library stream + side stream (forked work inside a step)
-static cudaEvent_t  g_fork = nullptr, g_join = nullptr, g_head = nullptr;
+// per host thread: the lane the thread works on (every thread starts on lane 0, see Runtime::use_lane)
+static thread_local cudaStream_t g_stream = nullptr, g_stream2 = nullptr;      // library stream + side stream (forked work inside a step)
+static thread_local cudaEvent_t  g_fork = nullptr, g_join = nullptr, g_head = nullptr;
 static bool  g_init = false;
+static int   g_device = 0;
+// Lanes: independent (stream, side stream, events, workspace banks) sets of ONE process.  Lane 0 is the default and the only one a
+// training process uses; the data-parallel tests run `world` ranks of one process on one device, each on its own lane, so that the ranks'
+// kernels can wait on one another exactly as they do across GPUs (Runtime::use_lane).
+#define T4_MAX_LANES 4
+static struct Lane { cudaStream_t s = nullptr, s2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, head = nullptr; } g_lanes[T4_MAX_LANES];
+static thread_local int g_lane = 0;
+#define WS_BANK_MAIN (2 * g_lane)
+#define WS_BANK_SIDE (2 * g_lane + 1)
 static char  g_err[512] = "";
 
 int Runtime::init(int device) {
@@ -31,11 +41,29 @@ int Runtime::init(int device) {
         uint64_t keep = UINT64_MAX;                     // keep freed blocks cached: alloc/free in `for @ drop next` loops stay cheap
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
+    g_lanes[0] = Lane{g_stream, g_stream2, g_fork, g_join, g_head};
+    g_device = device;
     g_init = true;
     return 0;
 }
-void *Runtime::stream() { return (void*)g_stream; }
-int   Runtime::sync()   { return (int)cudaStreamSynchronize(g_stream); }
+int Runtime::use_lane(int k) {
+    if (k < 0 || k >= T4_MAX_LANES || (!g_init && init(0))) return T4K_EINVAL;
+    Lane &l = g_lanes[k];
+    cudaSetDevice(g_device);                              // the current device is per host thread as well
+    if (!l.s) {
+        if (cudaStreamCreateWithFlags(&l.s, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&l.s2, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.head, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); error("lane %d: stream creation failed", k); return T4K_EINVAL; }
+    }
+    g_lane = k; g_stream = l.s; g_stream2 = l.s2; g_fork = l.fork; g_join = l.join; g_head = l.head;
+    t4k_set_workspace_bank(WS_BANK_MAIN);
+    return 0;
+}
+void *Runtime::stream() {
+    if (!g_stream && g_init) use_lane(0);                 // a thread other than the one that initialised the runtime: lane 0 until it picks another
+    return (void*)g_stream;
+}
+int   Runtime::sync()   { return (int)cudaStreamSynchronize((cudaStream_t)stream()); }
 void  Runtime::error(const char *fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
@@ -44,10 +72,10 @@ void *Runtime::alloc(size_t bytes) {
     if (!g_init && init(0)) return nullptr;
     void *p = nullptr;
     bytes = (bytes + 255) & ~(size_t)255;
-    if (cudaMallocAsync(&p, bytes, g_stream) != cudaSuccess) { cudaGetLastError(); error("device allocation of %zu bytes failed", bytes); return nullptr; }
+    if (cudaMallocAsync(&p, bytes, (cudaStream_t)stream()) != cudaSuccess) { cudaGetLastError(); error("device allocation of %zu bytes failed", bytes); return nullptr; }
     return p;
 }
-void Runtime::free(void *p) { if (p) cudaFreeAsync(p, g_stream); }
+void Runtime::free(void *p) { if (p) cudaFreeAsync(p, (cudaStream_t)stream()); }
 
 #define ST         (Runtime::stream())
 #define KCHK(call) do { int _rc = (call); if (_rc) Runtime::error("%s -> %d (%s)", #call, _rc, t4k_strerror(_rc)); } while (0)
@@ -516,7 +544,9 @@ void Model::_fstep(Tensor &in, Tensor &out) {                             // for
     case T4K_L_LEAKYRL: case T4K_L_ELU: _factivate(in, out, fn); break;
     case T4K_L_DROPOUT: {
         Tensor &t = *in.grad[4];
-        KCHK(t4k_rand(t.data, t.numel, T4K_UNIFORM, 0.0f, 1.0f, ST));     // fresh mask every forward (forward.cu:98-102)
+        // fresh mask every forward (forward.cu:98-102); data parallel: the mask of THIS shard of the global batch (rand.cu)
+        if (_dp_world > 1) KCHK(t4k_rand_sharded(t.data, (int64_t)t.numel, (int64_t)_dp_rank * (int64_t)t.numel, (int64_t)_dp_world * (int64_t)t.numel, T4K_UNIFORM, 0.0f, 1.0f, ST));
+        else KCHK(t4k_rand(t.data, t.numel, T4K_UNIFORM, 0.0f, 1.0f, ST));
         _factivate(in, out, fn);
     } break;
     case T4K_L_SOFTMAX: _fsoftmax(in, out);    break;
@@ -550,6 +580,11 @@ int Model::_fpool(Tensor &in, Tensor &out, t4_layer fn) {                 // for
 int Model::_fsoftmax(Tensor &in, Tensor &out)    { KCHK(t4k_softmax_fwd(in.data, out.data, in.N(), (int)in.HWC(), ST)); return 0; }     // forward.cu:231-243
 int Model::_flogsoftmax(Tensor &in, Tensor &out) { KCHK(t4k_logsoftmax_fwd(in.data, out.data, in.N(), (int)in.HWC(), ST)); return 0; }  // forward.cu:246-259
 int Model::_fbatchnorm(Tensor &in, Tensor &out) {                         // forward.cu:264-309
+    if (_comm_stat && _dp_world > 1) {                                     // statistics of the GLOBAL batch (SURVEY §8e collective 2)
+        KCHK(t4k_batchnorm_fwd_dp((t4k_comm_t)_comm_stat, in.data, out.data, in.grad[4]->data, in.grad[0]->data, in.grad[1]->data, in.mtum[4]->data,
+                                  out.N(), out.N() * _dp_world, out.H() * out.W(), out.C(), ST));
+        return 0;
+    }
     KCHK(t4k_batchnorm_fwd(in.data, out.data, in.grad[4]->data, in.grad[0]->data, in.grad[1]->data, in.mtum[4]->data,
                            out.N(), out.H() * out.W(), out.C(), ST));
     return 0;
@@ -685,9 +720,9 @@ int Model::_blinear(Tensor &in, Tensor &out, bool skip_db, Tensor *xdup, bool de
             if (rcg == 0) { _side_join = true; return 0; }                 // the conv block that follows writes the flatten backward itself
             if (rcg != T4K_ENOSUP) KCHK(rcg);
         }
-        t4k_set_workspace_bank(1);
+        t4k_set_workspace_bank(WS_BANK_SIDE);
         KCHK(t4k_gemm(out.data, xdup->data, dw.data, 1.0f, 1.0f, 1, 0, E0, E1, N, 1, 1, 0, 0, 0, (t4k_stream_t)g_stream2));
-        t4k_set_workspace_bank(0);
+        t4k_set_workspace_bank(WS_BANK_MAIN);
         cudaEventRecord(g_join, g_stream2);
         int rcx = T4K_ENOSUP;
         if (hp) rcx = t4k_linear_dx_from_head(_pdup, _hp.T, _hp.W2, _hp.F1, w.data, in.data, N, _hp.E0, E0, E1, ST);
@@ -725,6 +760,11 @@ int Model::_bupsample(Tensor &in, Tensor &out, t4_layer fn) {             // bac
     KCHK(t4k_pool_fwd(T4K_L_USAMPLE, out.data, in.data, in.N(), out.H(), out.W(), in.H(), in.W(), in.C(), in.stride[0], ST)); return 0;
 }
 int Model::_bbatchnorm(Tensor &in, Tensor &out) {                         // backprop.cu:312-370
+    if (_comm_stat && _dp_world > 1) {
+        KCHK(t4k_batchnorm_bwd_dp((t4k_comm_t)_comm_stat, out.data, in.grad[4]->data, in.data, in.grad[0]->data, in.grad[2]->data, in.grad[3]->data,
+                                  in.mtum[4]->data, in.N(), in.N() * _dp_world, in.H() * in.W(), in.C(), train, ST));
+        return 0;
+    }
     KCHK(t4k_batchnorm_bwd(out.data, in.grad[4]->data, in.data, in.grad[0]->data, in.grad[2]->data, in.grad[3]->data,
                            in.mtum[4]->data, in.N(), in.H() * in.W(), in.C(), train, ST));
     return 0;
@@ -969,9 +1009,27 @@ int Model::arena(DU **G, DU **DG, int64_t *total) {
     if (total) *total = (int64_t)_total;
     return _G ? 0 : T4K_EINVAL;
 }
+int Model::bn_channels() {
+    int c = 0;
+    for (Tensor *t : _layers) if (t->grad_fn == T4K_L_BATCHNM) c = std::max(c, (int)t->C());
+    return c;
+}
+int Model::dp_shard(int rank, int world, void *comm_stat) {
+    if (world < 1 || rank < 0 || rank >= world) return T4K_EINVAL;
+    const int C = bn_channels();
+    if (comm_stat && t4k_comm_capacity((t4k_comm_t)comm_stat) < 4 * (int64_t)C) return T4K_EINVAL;
+    _dp_rank = rank; _dp_world = world; _comm_stat = world > 1 ? comm_stat : nullptr;
+    Runtime::sync(); _drop_graphs();
+    return 0;
+}
 int Model::dp_attach(void *comm, DU *scal, int nscal) {
     if (!_G) grad_alloc(OPTI_ADAM);
     if (comm && (!_G || t4k_comm_capacity((t4k_comm_t)comm) < (int64_t)_total || nscal < 0 || nscal > 64)) return T4K_EINVAL;
+    if (comm && bn_channels() && !(_comm_stat && _dp_world > 1)) {
+        // per-shard batch statistics would silently train another model than the single-device step (nmath.cu:177-264,295-414 over the whole batch)
+        Runtime::error("nn#dp_attach: the model has batchnorm layers; give it a statistics communicator first (Model::dp_shard)\n");
+        return T4K_ENOSUP;
+    }
     _comm = comm; _dp_scal = scal; _dp_nscal = comm ? nscal : 0;
     Runtime::sync(); _drop_graphs();                          // the captured optimizer node changes
     return 0;
@@ -1083,6 +1141,7 @@ extern "C" {
 const char *t4h_last_error(void) { return Runtime::last_error(); }
 int   t4h_init(int device) { return Runtime::init(device); }
 void *t4h_stream(void) { return Runtime::stream(); }
+void *t4h_side_stream(void) { Runtime::stream(); return (void*)g_stream2; }
 int   t4h_sync(void) { return Runtime::sync(); }
 long  t4h_launch_count(void) { return t4k_launch_count(); }
 
@@ -1231,6 +1290,14 @@ int   t4h_model_save(t4h_model m, const char *fname) { return MM(m).save(fname);
 int   t4h_model_load(t4h_model m, const char *fname) { return MM(m).load(fname); }
 int   t4h_model_arena(t4h_model m, float **G, float **DG, int64_t *total) { return MM(m).arena(G, DG, total); }
 int   t4h_model_dp_attach(t4h_model m, void *comm, float *scal, int nscal) { return MM(m).dp_attach(comm, scal, nscal); }
+int   t4h_model_dp_shard(t4h_model m, int rank, int world, void *comm_stat) { return MM(m).dp_shard(rank, world, comm_stat); }
+int   t4h_model_bn_channels(t4h_model m) { return MM(m).bn_channels(); }
+int   t4h_use_lane(int lane) { return Runtime::use_lane(lane); }
+int   t4h_tensor_rand_sharded(t4h_tensor t, int opt, int rank, int world) {
+    if (world < 1 || rank < 0 || rank >= world) return T4K_EINVAL;
+    const int64_t n = (int64_t)TT(t).numel;
+    return t4k_rand_sharded(TT(t).data, n, rank * n, world * n, opt, 0.0f, 1.0f, Runtime::stream());
+}
 int   t4h_model_step_graph(t4h_model m, t4h_tensor input, t4h_tensor tgt, int lop, float *loss_dev, int optimizer, float lr, float b1, float b2, float wd) {
     return MM(m).step_graph(TT(input), TT(tgt), (t4_loss)lop, loss_dev, (t4_optimizer)optimizer, lr, b1, b2, wd);
 }

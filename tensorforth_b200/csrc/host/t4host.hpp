@@ -35,6 +35,7 @@ struct Runtime {
     static const char *last_error();
     static void *alloc(size_t bytes);                  // stream-ordered pool (replaces MMU::talloc)
     static void  free(void *p);
+    static int   use_lane(int k);                      // switch the process to stream set k (tests: several ranks of one process)
 };
 
 struct Tensor {
@@ -161,6 +162,7 @@ class Model {
     int     _step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd, const StepExtra &x);
     void    _drop_graphs();
     void   *_comm = nullptr; DU *_dp_scal = nullptr; int _dp_nscal = 0;   // data parallel: t4k_comm_t + scalars riding in the exchange
+    void   *_comm_stat = nullptr; int _dp_rank = 0, _dp_world = 1;        // data parallel: batch-norm statistics communicator, this rank's shard of the global batch
     int     _second_layer = 0; int64_t _first_end = 0;                    // arena layout: end of the first parameter layer's segments, index of the next parameter layer
     bool    _dp_early = false, _dp_join = false; int64_t _dp_pushed_from = -1;   // split exchange inside step_graph (early push on the side stream)
     void    _dp_push();
@@ -231,6 +233,11 @@ public:
     // first SUM the gradient arena over the ranks — one fused exchange+optimizer kernel over NVLink peer memory (comm.cu);
     // `scal[0..nscal)` device floats (this rank's loss sum …) are summed over the ranks in the same exchange
     int    dp_attach(void *comm, DU *scal, int nscal);
+    // this model holds shard `rank` of `world` equal shards of the global batch: dropout masks are drawn at the shard's global element offsets
+    // (the masks of a single-device run of the whole batch), batch-norm statistics are SUM-all-reduced on `comm_stat` (a communicator of its
+    // own, capacity >= 4 x bn_channels(); required before dp_attach when the model has batchnorm layers)
+    int    dp_shard(int rank, int world, void *comm_stat);
+    int    bn_channels();
     int    step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd);
 private:
     void _iconv(Tensor &in, U32 c, DU bias, U16 *opt);

@@ -176,6 +176,26 @@ k_bn_dx(const float *__restrict__ dO, const float *__restrict__ XH, float *dX, c
     }
 }
 
+// data parallel: the CTAs' partial column sums -> ONE [2C] vector (the payload of the cross-rank SUM), in CTA order
+__global__ void __launch_bounds__(T4K_THREADS)
+k_bn_sum_parts(const float *__restrict__ part, float *out2C, int C, int nparts) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * C) return;
+    const int which = t / C, c = t - which * C;
+    float s = 0.0f;
+    for (int k = 0; k < nparts; k++) s += part[((int64_t)k * 2 + which) * C + c];
+    out2C[t] = s;
+}
+// backward finalize, data parallel: s1 / s2 are means over the GLOBAL batch (sums already reduced over the ranks); the parameter gradients
+// receive this rank's SHARE, local sum / global rows — the gradient exchange adds the ranks' shares to the reference's means (nmath.cu:378-381)
+__global__ void __launch_bounds__(T4K_THREADS)
+k_bn_fin_bwd_dp(const float *__restrict__ glob2C, const float *__restrict__ loc2C, float *scratch, float *dW, float *dB, int64_t NHW_global, int C, int train) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    scratch[C + c] = glob2C[c] / (float)NHW_global; scratch[2 * C + c] = glob2C[C + c] / (float)NHW_global;
+    if (train) { dB[c] += loc2C[c] / (float)NHW_global; dW[c] += loc2C[C + c] / (float)NHW_global; }
+}
+
 static int bn_parts(int64_t rows, int64_t *rows_per) {
     int nparts = 4 * sm_count();
     int64_t rp = (rows + nparts - 1) / nparts; if (rp < 1) rp = 1;
@@ -235,6 +255,55 @@ extern "C" int t4k_batchnorm_bwd(const float *dO, const float *XH, float *dX, co
     k_bn_colsum2<1><<<nparts, T4K_THREADS, 0, STRM(s)>>>(dO, XH, part, rows, C, rows_per);
     int rc = check_launch(); if (rc) return rc;
     k_bn_fin_bwd<<<(C + T4K_THREADS - 1) / T4K_THREADS, T4K_THREADS, 0, STRM(s)>>>(part, scratch3C, dgamma, dbeta, rows, C, nparts, train);
+    rc = check_launch(); if (rc) return rc;
+    const bool vec = (C % 4 == 0) && aligned16(dO) && aligned16(XH) && aligned16(dX) && aligned16(gamma) && aligned16(scratch3C);
+    if (vec) k_bn_dx<true ><<<stream_grid(total, 4), T4K_THREADS, 0, STRM(s)>>>(dO, XH, dX, gamma, scratch3C, C, total);
+    else     k_bn_dx<false><<<stream_grid(total, 1), T4K_THREADS, 0, STRM(s)>>>(dO, XH, dX, gamma, scratch3C, C, total);
+    return check_launch();
+}
+
+/* Batch norm over a batch that is SHARDED across the ranks of `comm` (SURVEY §8e collective 2): the per-channel sums of the shard are
+ * SUM-all-reduced (2C floats over NVLink peer memory, t4k_allreduce_sum) between the statistics pass and the apply pass, so mean / variance
+ * (forward) and mean(dy), mean(dy*xhat) (backward) are those of the global batch of N_global samples — the single-device result of
+ * k_batchnorm_1/2/3 and k_dbatchnorm_1/2/3 (src/nn/nmath.cu:177-264,295-414) on the concatenated batch.  `comm` must be a communicator of
+ * its own (capacity >= 4C), not the one the gradient arena is exchanged on: its chunks' epochs advance with every call. */
+extern "C" int t4k_batchnorm_fwd_dp(t4k_comm_t comm, const float *I, float *O, float *XH, const float *gamma, const float *beta,
+                                    float *scratch3C, int N, int N_global, int HW, int C, t4k_stream_t s) {
+    if (!comm || !I || !O || !XH || !gamma || !beta || !scratch3C || N < 1 || N_global < N || HW < 1 || C < 1 || t4k_comm_capacity(comm) < 4 * (int64_t)C) return T4K_EINVAL;
+    const int64_t rows = (int64_t)N * HW, total = rows * C;
+    int64_t rows_per; const int nparts = bn_parts(rows, &rows_per);
+    float *part = (float*)workspace(((size_t)nparts * 2 * C + 4 * (size_t)C + 8) * sizeof(float), 6);
+    if (!part) return T4K_ENOMEM;
+    float *glob = part + (size_t)nparts * 2 * C; glob = (float*)(((uintptr_t)glob + 15) & ~(uintptr_t)15);
+    k_bn_colsum2<0><<<nparts, T4K_THREADS, 0, STRM(s)>>>(I, nullptr, part, rows, C, rows_per);
+    int rc = check_launch(); if (rc) return rc;
+    k_bn_sum_parts<<<(2 * C + T4K_THREADS - 1) / T4K_THREADS, T4K_THREADS, 0, STRM(s)>>>(part, glob, C, nparts);
+    rc = check_launch(); if (rc) return rc;
+    rc = t4k_allreduce_sum(comm, glob, 2 * (int64_t)C, s); if (rc) return rc;
+    k_bn_fin_fwd<<<(C + T4K_THREADS - 1) / T4K_THREADS, T4K_THREADS, 0, STRM(s)>>>(glob, scratch3C, (int64_t)N_global * HW, C, 1);
+    rc = check_launch(); if (rc) return rc;
+    const bool vec = (C % 4 == 0) && aligned16(I) && aligned16(O) && aligned16(XH) && aligned16(gamma) && aligned16(beta) && aligned16(scratch3C);
+    if (vec) k_bn_apply<true ><<<stream_grid(total, 4), T4K_THREADS, 0, STRM(s)>>>(I, O, XH, gamma, beta, scratch3C, C, total);
+    else     k_bn_apply<false><<<stream_grid(total, 1), T4K_THREADS, 0, STRM(s)>>>(I, O, XH, gamma, beta, scratch3C, C, total);
+    return check_launch();
+}
+extern "C" int t4k_batchnorm_bwd_dp(t4k_comm_t comm, const float *dO, const float *XH, float *dX, const float *gamma,
+                                    float *dgamma, float *dbeta, float *scratch3C, int N, int N_global, int HW, int C, int train, t4k_stream_t s) {
+    if (!comm || !dO || !XH || !dX || !gamma || !scratch3C || N < 1 || N_global < N || HW < 1 || C < 1 || t4k_comm_capacity(comm) < 4 * (int64_t)C) return T4K_EINVAL;
+    if (train && (!dgamma || !dbeta)) return T4K_EINVAL;
+    const int64_t rows = (int64_t)N * HW, total = rows * C;
+    int64_t rows_per; const int nparts = bn_parts(rows, &rows_per);
+    float *part = (float*)workspace(((size_t)nparts * 2 * C + 4 * (size_t)C + 8) * sizeof(float), 6);
+    if (!part) return T4K_ENOMEM;
+    float *glob = part + (size_t)nparts * 2 * C; glob = (float*)(((uintptr_t)glob + 15) & ~(uintptr_t)15);
+    float *loc = glob + 2 * (size_t)C;
+    k_bn_colsum2<1><<<nparts, T4K_THREADS, 0, STRM(s)>>>(dO, XH, part, rows, C, rows_per);
+    int rc = check_launch(); if (rc) return rc;
+    k_bn_sum_parts<<<(2 * C + T4K_THREADS - 1) / T4K_THREADS, T4K_THREADS, 0, STRM(s)>>>(part, loc, C, nparts);
+    rc = check_launch(); if (rc) return rc;
+    rc = t4k_copy(loc, glob, 2 * (int64_t)C, s); if (rc) return rc;
+    rc = t4k_allreduce_sum(comm, glob, 2 * (int64_t)C, s); if (rc) return rc;
+    k_bn_fin_bwd_dp<<<(C + T4K_THREADS - 1) / T4K_THREADS, T4K_THREADS, 0, STRM(s)>>>(glob, loc, scratch3C, dgamma, dbeta, (int64_t)N_global * HW, C, train);
     rc = check_launch(); if (rc) return rc;
     const bool vec = (C % 4 == 0) && aligned16(dO) && aligned16(XH) && aligned16(dX) && aligned16(gamma) && aligned16(scratch3C);
     if (vec) k_bn_dx<true ><<<stream_grid(total, 4), T4K_THREADS, 0, STRM(s)>>>(dO, XH, dX, gamma, scratch3C, C, total);

@@ -85,6 +85,19 @@ extern "C" int t4k_rand_tick(t4k_stream_t s) {
     k_rand_tick<<<1, 32, 0, STRM(s)>>>(e);
     return check_launch();
 }
+/* Draw this rank's shard of a batch-major tensor exactly as ONE device holding the whole batch would draw it (per-rank Philox
+ * offset = global element index): `n` = this shard's elements, `before` = elements of the shards of the ranks in front of it, `global_n` =
+ * elements of the whole tensor.  Element i of the shard gets the counter of global element before + i; the host offset advances by the global
+ * length on every rank alike, so successive draws stay aligned across ranks and with a single-device run of the same program. */
+extern "C" int t4k_rand_sharded(float *d, int64_t n, int64_t before, int64_t global_n, int opt, float bias, float scale, t4k_stream_t s) {
+    if (!d || n < 0 || before < 0 || global_n < before + n || (opt != T4K_UNIFORM && opt != T4K_NORMAL)) return T4K_EINVAL;
+    if (n > 0) {
+        k_rand<<<stream_grid((n + 3) / 4), T4K_THREADS, 0, STRM(s)>>>(d, n, opt, bias, scale, g_seed, g_offset + (uint64_t)before, epoch_ptr());
+        const int rc = check_launch(); if (rc) return rc;
+    }
+    g_offset += (uint64_t)((global_n + 3) & ~3ll);
+    return 0;
+}
 extern "C" int t4k_rand(float *d, int64_t n, int opt, float bias, float scale, t4k_stream_t s) {
     if (!d || n < 0 || (opt != T4K_UNIFORM && opt != T4K_NORMAL)) return T4K_EINVAL;
     if (n == 0) return 0;

@@ -41,8 +41,8 @@ int check_launch() {
 // released at process exit.  A regrowth attempted INSIDE a stream capture fails (cudaMalloc is not capturable): the call returns
 // T4K_ENOMEM, the capture is abandoned by the caller (Model::_step_graph falls back to the eager step, which sizes the workspace).
 #define MAX_DEV  16
-#define MAX_SLOT 16          // 8 slots x 2 banks (bank 1: work forked onto a side stream, see t4k_set_workspace_bank)
-static int g_ws_bank = 0;
+#define MAX_SLOT 64          // 8 slots x 8 banks (odd banks: work forked onto a side stream; banks 2k, 2k+1: lane k of the host runtime, see t4k_set_workspace_bank)
+static thread_local int g_ws_bank = 0;       // per host thread (the host runtime gives every lane, and each lane's side stream, its own bank)
 static void  *g_ws[MAX_DEV][MAX_SLOT];
 static size_t g_ws_sz[MAX_DEV][MAX_SLOT];
 static std::mutex g_mu;
@@ -114,7 +114,7 @@ int t4k_sync(t4k_stream_t s) { return (int)cudaStreamSynchronize((cudaStream_t)s
 
 long t4k_launch_count(void) { return t4k::g_launches; }
 
-int t4k_set_workspace_bank(int bank) { int was = t4k::g_ws_bank; t4k::g_ws_bank = bank ? 1 : 0; return was; }
+int t4k_set_workspace_bank(int bank) { int was = t4k::g_ws_bank; t4k::g_ws_bank = bank & 7; return was; }
 
 int t4k_set_pdl(int on) { int was = t4k::g_pdl; t4k::g_pdl = on ? 1 : 0; return was; }
 

@@ -136,9 +136,24 @@ class DataParallel:
         self.params = device_view(g, total, device) if device.type == "cuda" else None
         self.grads = device_view(dg, total, device) if device.type == "cuda" else None
         self.total = total
-        self.comm = None
+        self.comm = self.stat_comm = None
         if sync_params and self.params is not None:
-            broadcast_(self.params, 0)
+            if self.params.is_cuda:
+                from . import host as _h
+                with torch.cuda.stream(torch.cuda.ExternalStream(_h.stream(), device=device)):
+                    broadcast_(self.params, 0)
+            else:
+                broadcast_(self.params, 0)
+        if active():
+            # this rank's shard of the global batch: dropout masks drawn at the shard's global element offsets, batch-norm statistics summed
+            # over the ranks (over NVLink peer memory, inside Model::forward / backprop) — with either gradient exchange
+            bn = model.bn_channels() if hasattr(model, "bn_channels") else 0
+            if bn and device.type != "cuda":
+                raise NotImplementedError("batch-norm statistics are exchanged over CUDA peer memory: no CPU path")
+            if bn:
+                self.stat_comm = PeerComm(4 * bn)
+            if hasattr(model, "dp_shard"):
+                model.dp_shard(dist.get_rank(), dist.get_world_size(), self.stat_comm.handle if self.stat_comm else None)
         if fused and active():
             import ctypes as C
             self.comm = PeerComm(total)
@@ -147,8 +162,14 @@ class DataParallel:
                             scalars.numel() if scalars is not None else 0)
 
     def allreduce_grads(self):
+        """SUM of the gradient arena over the ranks (torch.distributed), ordered after the library stream's backprop and before its optimizer:
+        the collective is issued on the library's own stream whatever torch's current stream is"""
         if self.comm is not None:
             raise RuntimeError("fused data parallel: the optimizer call does the exchange")
+        if self.grads is not None and self.grads.is_cuda:
+            from . import host as _h
+            with torch.cuda.stream(torch.cuda.ExternalStream(_h.stream(), device=self.device)):
+                return allreduce_sum_(self.grads)
         return allreduce_sum_(self.grads)
 
     def hit(self):

@@ -40,6 +40,11 @@ PROTOTYPES = {
     "t4h_model_arena": (_i, [_p, C.POINTER(_p), C.POINTER(_p), C.POINTER(_l)]),
     "t4h_model_step_graph": (_i, [_p, _p, _p, _i, _p, _i, _f, _f, _f, _f]),
     "t4h_model_dp_attach": (_i, [_p, _p, _p, _i]),
+    "t4h_model_dp_shard": (_i, [_p, _i, _i, _p]),
+    "t4h_model_bn_channels": (_i, [_p]),
+    "t4h_tensor_rand_sharded": (_i, [_p, _i, _i, _i]),
+    "t4h_use_lane": (_i, [_i]),
+    "t4h_side_stream": (_p, []),
     "t4h_capture_begin": (_i, []), "t4h_capture_end": (_p, []), "t4h_graph_launch": (_i, [_p]), "t4h_graph_free": (None, [_p]),
     "t4h_model_save": (_i, [_p, C.c_char_p]), "t4h_model_load": (_i, [_p, C.c_char_p]),
     "t4h_dataset_create": (_p, [_i, _i, _i, _i]), "t4h_dataset_destroy": (None, [_p]), "t4h_dataset_normalize": (None, [_p, _f, _f]),
@@ -73,6 +78,11 @@ def init(device=0):
     rc = load().t4h_init(device)
     if rc:
         raise T4KError("t4h_init(%d): %s" % (device, _err()))
+
+
+def use_lane(k):
+    """tests: switch the process to stream set k (several data-parallel ranks of one process, each on its own lane)"""
+    _k.check(load().t4h_use_lane(int(k)), "use_lane")
 
 
 def sync():
@@ -154,6 +164,10 @@ class Tensor:
     def eye(self): load().t4h_tensor_identity(self.h); return self
     def rand(self): _k.check(load().t4h_tensor_rand(self.h, _k.UNIFORM)); return self
     def randn(self): _k.check(load().t4h_tensor_rand(self.h, _k.NORMAL)); return self
+
+    def rand_sharded(self, rank, world, normal=False):
+        """this tensor holds shard `rank` of `world` equal shards of a batch-major tensor: draw it as one device holding the whole would"""
+        _k.check(load().t4h_tensor_rand_sharded(self.h, _k.NORMAL if normal else _k.UNIFORM, rank, world)); return self
 
     def _bin(self, op, other, out=None):
         out = out or self
@@ -289,6 +303,15 @@ class Model:
     def load(self, fname):              # word `load`: parameters into an already built model
         if load().t4h_model_load(self.h, str(fname).encode()): raise T4KError(_err())
         return self
+
+    def dp_shard(self, rank, world, comm_stat=None):
+        """this model holds shard `rank` of `world` equal shards of the global batch (dropout masks at the shard's global offsets; batch-norm
+        statistics summed over the ranks on `comm_stat`, a t4k_comm_t of its own — required before dp_attach for a model with batchnorm)"""
+        _k.check(load().t4h_model_dp_shard(self.h, rank, world, comm_stat), "dp_shard")
+        return self
+
+    def bn_channels(self):
+        return int(load().t4h_model_bn_channels(self.h))
 
     def dp_attach(self, comm, scal_dev_ptr=None, nscal=0):
         """data parallel: from now on the optimizer calls sum the gradient arena over the ranks of `comm` (a connected

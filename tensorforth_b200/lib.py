@@ -61,6 +61,9 @@ PROTOTYPES = {
     "t4k_dbias": (_i, [_p, _p, _i, _i, _p]),
     "t4k_linear_bwd": (_i, [_p] * 6 + [_i] * 4 + [_p]),
     "t4k_linear_bwd_ex": (_i, [_p] * 6 + [_i] * 5 + [_p]),
+    "t4k_rand_sharded": (_i, [_p, _l, _l, _l, _i, _f, _f, _p]),
+    "t4k_batchnorm_fwd_dp": (_i, [_p] * 7 + [_i] * 4 + [_p]),
+    "t4k_batchnorm_bwd_dp": (_i, [_p] * 8 + [_i] * 5 + [_p]),
     "t4k_head_train_scratch_floats": (_l, [_i] * 5),
     "t4k_linear_act_head_train": (_i, [_i] + [_p] * 6 + [_f] + [_p] * 8 + [_i] * 4 + [_p]),
     "t4k_head_grad_finish": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),

@@ -77,6 +77,23 @@ def warm(L):
     r1.close()
 
 
+def warm_bn(L):
+    """the data-parallel batch-norm kernels, loaded with a world=1 communicator (same reason as warm(): the first launch of a kernel loads its
+    module, and a load issued while a peer's kernel spins waits for it — in ONE process that peer's partner is launched by the same thread)"""
+    r1 = Ring(1, 64)
+    x = torch.ones(2, 4, 8, device="cuda")
+    o, xh, dx, s3 = torch.zeros_like(x), torch.zeros_like(x), torch.zeros_like(x), torch.zeros(3 * 8 + 4, device="cuda")
+    g, b, dg, db = (torch.ones(8, device="cuda") for _ in range(4))
+    ok(L.t4k_batchnorm_fwd_dp(r1.h[0], ptr(x), ptr(o), ptr(xh), ptr(g), ptr(b), ptr(s3), 2, 2, 4, 8, r1.st(0)))
+    ok(L.t4k_batchnorm_bwd_dp(r1.h[0], ptr(x), ptr(xh), ptr(dx), ptr(g), ptr(dg), ptr(db), ptr(s3), 2, 2, 4, 8, 1, r1.st(0)))
+    x7 = torch.ones(2, 4, 7, device="cuda")                  # the unaligned variants
+    o7, xh7, dx7 = torch.zeros_like(x7), torch.zeros_like(x7), torch.zeros_like(x7)
+    ok(L.t4k_batchnorm_fwd_dp(r1.h[0], ptr(x7), ptr(o7), ptr(xh7), ptr(g), ptr(b), ptr(s3), 2, 2, 4, 7, r1.st(0)))
+    ok(L.t4k_batchnorm_bwd_dp(r1.h[0], ptr(x7), ptr(xh7), ptr(dx7), ptr(g), ptr(dg), ptr(db), ptr(s3), 2, 2, 4, 7, 1, r1.st(0)))
+    r1.sync()
+    r1.close()
+
+
 def seg_table(segs):
     a = np.zeros((len(segs), 3), dtype=np.int64)        # {int64 off; int64 len; int32 Nw; int32 pad}
     for k, (off, ln, nw) in enumerate(segs):
@@ -172,4 +189,77 @@ def test_exchange_replays_inside_cuda_graphs():
         ring.sync()
         for r in range(world):
             assert float(bufs[r].min()) == float(bufs[r].max()) == float(sum(k + 1 + it for k in range(world)))
+    ring.close()
+
+
+# ------------------------------------------------------------------ data-parallel semantics beyond the gradient sum
+def test_rand_sharded_is_a_slice_of_the_single_device_draw():
+    """per-rank Philox offsets = global element index: the shards drawn by `world` ranks are the slices of ONE draw of the whole tensor,
+    and every rank's stream advances by the global length (the next draws stay aligned)"""
+    L = lib()
+    n, world = 4096 * 3 + 8, 4                               # per-shard elements
+    for opt in (t4.UNIFORM, t4.NORMAL):
+        L.t4k_rand_seed(99)
+        full, nxt = torch.zeros(n * world, device="cuda"), torch.zeros(100, device="cuda")
+        ok(L.t4k_rand(ptr(full), n * world, opt, 0.0, 1.0, None)); ok(L.t4k_rand(ptr(nxt), 100, opt, 0.0, 1.0, None))
+        torch.cuda.synchronize()
+        for r in range(world):
+            L.t4k_rand_seed(99)
+            sh, nx = torch.zeros(n, device="cuda"), torch.zeros(100, device="cuda")
+            ok(L.t4k_rand_sharded(ptr(sh), n, r * n, world * n, opt, 0.0, 1.0, None)); ok(L.t4k_rand(ptr(nx), 100, opt, 0.0, 1.0, None))
+            torch.cuda.synchronize()
+            assert torch.equal(sh, full[r * n:(r + 1) * n]), (opt, r)
+            assert torch.equal(nx, nxt)
+    assert L.t4k_rand_sharded(ptr(full), n, 4, n, t4.UNIFORM, 0.0, 1.0, None) == t4.EINVAL        # shard past the end of the tensor
+
+
+@pytest.mark.parametrize("world,N,HW,Cc", [(2, 8, 16, 6), (4, 4, 49, 32), (2, 16, 1, 100)])
+def test_batchnorm_dp_equals_single_device_on_the_whole_batch(world, N, HW, Cc):
+    """batch norm over a batch sharded across `world` ranks (statistics SUM-all-reduced over peer memory between the two passes) against
+    t4k_batchnorm_fwd / _bwd on the concatenated batch: activations, x-hat, dX within FP32 summation noise; the ranks' dgamma / dbeta
+    shares add up to the single-device parameter gradients (the gradient exchange performs that sum)"""
+    from oracle import oracle as orc
+    L = lib()
+    warm(L); warm_bn(L)
+    ring = Ring(world, 4 * Cc)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    X = torch.randn(world * N, HW, Cc, device="cuda", generator=g) * 2 + 0.5
+    dY = torch.randn(world * N, HW, Cc, device="cuda", generator=g)
+    gamma, beta = torch.rand(Cc, device="cuda", generator=g) + 0.5, torch.randn(Cc, device="cuda", generator=g)
+    # single device, whole batch
+    O1, XH1, dX1, s1 = torch.zeros_like(X), torch.zeros_like(X), torch.zeros_like(X), torch.zeros(3 * Cc + 4, device="cuda")
+    dg1, db1 = torch.ones(Cc, device="cuda"), torch.ones(Cc, device="cuda")
+    ok(L.t4k_batchnorm_fwd(ptr(X), ptr(O1), ptr(XH1), ptr(gamma), ptr(beta), ptr(s1), world * N, HW, Cc, None))
+    ok(L.t4k_batchnorm_bwd(ptr(dY), ptr(XH1), ptr(dX1), ptr(gamma), ptr(dg1), ptr(db1), ptr(s1), world * N, HW, Cc, 1, None))
+    torch.cuda.synchronize()
+    # sharded
+    Xs, dYs = [X[r * N:(r + 1) * N].contiguous() for r in range(world)], [dY[r * N:(r + 1) * N].contiguous() for r in range(world)]
+    Os, XHs, dXs = ([torch.zeros_like(Xs[0]) for _ in range(world)] for _ in range(3))
+    ss = [torch.zeros(3 * Cc + 4, device="cuda") for _ in range(world)]
+    dgs, dbs = [torch.zeros(Cc, device="cuda") for _ in range(world)], [torch.zeros(Cc, device="cuda") for _ in range(world)]
+    # ranks of ONE process: each takes its own bank of the library workspaces (separate processes have their own)
+    for r in range(world):
+        L.t4k_set_workspace_bank(2 * (r % 4))
+        ok(L.t4k_batchnorm_fwd_dp(ring.h[r], ptr(Xs[r]), ptr(Os[r]), ptr(XHs[r]), ptr(gamma), ptr(beta), ptr(ss[r]), N, world * N, HW, Cc, ring.st(r)), "bn fwd dp")
+    ring.sync()
+    for r in range(world):
+        L.t4k_set_workspace_bank(2 * (r % 4))
+        ok(L.t4k_batchnorm_bwd_dp(ring.h[r], ptr(dYs[r]), ptr(XHs[r]), ptr(dXs[r]), ptr(gamma), ptr(dgs[r]), ptr(dbs[r]), ptr(ss[r]), N, world * N, HW, Cc, 1, ring.st(r)), "bn bwd dp")
+    ring.sync()
+    L.t4k_set_workspace_bank(0)
+    from gpu_util import assert_close
+    assert_close(torch.cat(Os).cpu().numpy(), O1.cpu().numpy(), rtol=1e-5, what="O")
+    assert_close(torch.cat(XHs).cpu().numpy(), XH1.cpu().numpy(), rtol=1e-5, what="x-hat")
+    assert_close(torch.cat(dXs).cpu().numpy(), dX1.cpu().numpy(), rtol=1e-5, what="dX")
+    assert_close(sum(dgs).cpu().numpy(), (dg1 - 1).cpu().numpy(), rtol=1e-5, atol=1e-6, what="dgamma shares")
+    assert_close(sum(dbs).cpu().numpy(), (db1 - 1).cpu().numpy(), rtol=1e-5, atol=1e-6, what="dbeta shares")
+    for r in range(1, world):                                  # every rank derived the same statistics (rank-ordered sums: same bits)
+        assert torch.equal(ss[r][:3 * Cc], ss[0][:3 * Cc])
+    # and against the oracle's restatement of k_batchnorm_1/2/3 on the whole batch
+    o_ref, xh_ref, _, rvar = orc.batchnorm(X.cpu().numpy().reshape(world * N, HW, 1, Cc), gamma.cpu().numpy(), beta.cpu().numpy())
+    assert_close(torch.cat(Os).cpu().numpy(), o_ref, rtol=1e-4, what="O vs oracle")
+    dx_ref, dw_ref, db_ref = orc.dbatchnorm(dY.cpu().numpy().reshape(world * N, HW, 1, Cc), xh_ref, gamma.cpu().numpy(), rvar, np.zeros(Cc, np.float32), np.zeros(Cc, np.float32))
+    assert_close(torch.cat(dXs).cpu().numpy(), dx_ref, rtol=1e-4, what="dX vs oracle")
+    assert_close(sum(dgs).cpu().numpy(), dw_ref, rtol=1e-4, atol=1e-6, what="dgamma vs oracle")
+    assert_close(sum(dbs).cpu().numpy(), db_ref, rtol=1e-4, atol=1e-6, what="dbeta vs oracle")
     ring.close()
