@@ -286,7 +286,12 @@ def gan_extra(th, t4, L, torch, dist, rank, world, local, lib_stream, iters=50, 
             return {"unavailable": "peer exchange unavailable"} if rank == 0 else None
 
     def it():
-        z1.randn(); z2.randn()                                   # the two `X` draws of an iteration
+        # the two `X` draws of an iteration; data parallel: every rank draws ITS shard of the global latent batch (per-rank Philox offset =
+        # global element index, csrc/rand.cu) — and, through Model::dp_shard, its shard of the global dropout masks
+        if world > 1:
+            z1.rand_sharded(rank, world, normal=True); z2.rand_sharded(rank, world, normal=True)
+        else:
+            z1.randn(); z2.randn()
         th.gan_iteration(D, G, real, z1, z2, REAL, FAKE, losses=False)
     n0 = L.t4k_launch_count(); it(); launches = L.t4k_launch_count() - n0
     for _ in range(warm):

@@ -237,6 +237,17 @@ int t4k_activate_bwd(const float *dY, const float *F, float *dX, int64_t n, t4k_
 int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, float *dX, float *dF, float *dB,
                    int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P,
                    int train, t4k_stream_t s);
+/* conv-transpose layer (L_DCONV; word `dconv2d`: 4x4, stride 2, padding 1).  The reference wires it as the convolution layer with the two
+ * kernels' roles swapped (src/nn/forward.cu:110 -> Model::_bconv, src/nn/backprop.cu:137 -> Model::_fconv; output shape src/nn/model.cpp:129-133):
+ *   forward   O [N,H0,W0,C0] = k_dconv2d's input-gradient half applied to I [N,H1,W1,C1] (flipped taps, nmath.tcu:304), + bias per output channel
+ *   backward  dX [N,H1,W1,C1] = k_conv2d(dO, F) without bias;  train: dF += k_dconv2d's filter-gradient half on (input, output gradient) = (dO, I),
+ *             dB[c0] += sum of dO over the pixels
+ * F [C0][K][K][C1]: the filter of the convolution (C0 -> C1, K, S, P) that maps the large image onto the small one, (H0 - K + 2P)/S + 1 == H1.
+ * I and dX must not alias (dF reads I). */
+int t4k_dconv2d_fwd(const float *I, const float *F, const float *B, float *O,
+                    int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, t4k_stream_t s);
+int t4k_dconv2d_bwd(const float *I, const float *dO, const float *F, float *dX, float *dF, float *dB,
+                    int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, int train, t4k_stream_t s);
 /* k_dpool<KS> (nmath.tcu:475-568, backprop.cu:266-280; also upsample-forward forward.cu:314-329):
  * IN PLACE on the forward input I: max/min → zero window, dO at first strict max/min. */
 int t4k_pool_bwd(int layer, float *I, const float *dO, int N, int H1, int W1, int H0, int W0, int C, int KS, t4k_stream_t s);

@@ -7,6 +7,8 @@
 #   * src/nn/forward.cu, src/nn/backprop.cu                  — replaced by integration/model_shim.cu
 #   * src/nn/nmath.cu (NN kernels)                           — dropped (nothing references it any more)
 #   * src/t4math.cu                                          — kept only for the out-of-scope LA kernels (inverse / LU / det)
+#   * src/mu/mmu.cu, src/ten4.cu                             — compiled with `-include integration/arena_shim.h` (object store sized for the
+#     device, device-preferred managed memory); src/mu/tlsf.cpp replaced by integration/arena_shim.cpp (64-bit host-side allocator, §8f row 3)
 # Same CMake bypass and `-include iostream` fix-up as oracle/ref/build_ref.sh.  No reference source is copied.
 set -e
 REF=${1:-/root/reference}; HERE=$(cd $(dirname $0) && pwd); OUT=${2:-$HERE/_build}
@@ -16,15 +18,19 @@ mkdir -p $O
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 NV="nvcc -std=c++17 -O2 -I$R --device-c --expt-extended-lambda $ARCH -w"
 SHIM="-include $HERE/ref_fork_shim.h"
-for f in util t4math ten4; do $NV -c $R/$f.cu -o $O/$f.o & done
-for f in mmu dataset; do $NV -c $R/mu/$f.cu -o $O/mu_$f.o & done
+ARENA="-include $HERE/arena_shim.h"
+for f in util t4math; do $NV -c $R/$f.cu -o $O/$f.o & done
+$NV $ARENA -c $R/ten4.cu -o $O/ten4.o &
+$NV $ARENA -c $R/mu/mmu.cu -o $O/mu_mmu.o &
+$NV -c $R/mu/dataset.cu -o $O/mu_dataset.o &
 $NV -include iostream $SHIM -c $R/mu/tensor.cu -o $O/mu_tensor.o &
 $NV $SHIM -c $R/nn/gradient.cu -o $O/nn_gradient.o &
 $NV $SHIM -c $R/nn/debug.cu -o $O/nn_debug.o &
 $NV -c $HERE/model_shim.cu -o $O/model_shim.o &
 CX="g++ -std=c++17 -O2 -I$R -I/usr/local/cuda/include -w"
 for f in sys debug; do $CX -c $R/$f.cpp -o $O/$f.cpp.o & done
-for f in tlsf mpool; do $CX -c $R/mu/$f.cpp -o $O/mu_$f.cpp.o & done
+$CX -c $R/mu/mpool.cpp -o $O/mu_mpool.cpp.o &
+$CX -c $HERE/arena_shim.cpp -o $O/arena_shim.cpp.o &
 for f in $R/io/aio*.cpp $R/vm/*.cpp $R/ld/*.cpp $R/nn/loss.cpp $R/nn/model.cpp $R/tb/summary.cpp; do
   b=$(echo $f | sed "s#$R/##; s#/#_#g"); $CX -c $f -o $O/$b.o & done
 wait

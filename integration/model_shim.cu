@@ -132,7 +132,14 @@ Model::_fstep(Tensor &in, Tensor &out) {                          // forward.cu:
     case L_MINPOOL: _fpool(in, out, fn);     break;
     case L_BATCHNM: _fbatchnorm(in, out);    break;
     case L_USAMPLE: _fupsample(in, out);     break;
-    default: ERROR("nn#fstep layer=%d not supported\n", fn);      // L_DCONV: SURVEY.md §8f row 4 (next)
+    case L_DCONV: {                                               // forward.cu:110: the convolution's kernels with swapped roles (t4k_dconv2d_fwd);
+        Tensor &f = *in.grad[0], &b = *in.grad[1];                // the reference's filter T4(C1,K,K,C0) is read as [C0][K][K][C1] (same numel)
+        int rc = t4k_dconv2d_fwd(in.data, f.data, b.data, out.data, out.N(), in.H(), in.W(), in.C(), out.H(), out.W(), out.C(),
+                                 f.H(), in.stride[0], in.stride[2], ST0);
+        if (rc == T4K_ENOSUP) ERROR("nn#fconv kernel_size=%d stride=%d padding=%d not supported\n", f.H(), in.stride[0], in.stride[2]);
+        else KCALL(rc);
+    } break;
+    default: ERROR("nn#fstep layer=%d not supported\n", fn);
     }
 }
 __HOST__ int
@@ -324,6 +331,13 @@ Model::_bstep(Tensor &in, Tensor &out, bool last_layer) {         // backprop.cu
     case L_MINPOOL: _bpool(in, out, fn);     break;
     case L_BATCHNM: _bbatchnorm(in, out);    break;
     case L_USAMPLE: _bupsample(in, out, fn); break;
+    case L_DCONV: {                                               // backprop.cu:137
+        Tensor &f = *in.grad[0], &df = *in.grad[2], &db = *in.grad[3], &dx = *in.grad[4];
+        int rc = t4k_dconv2d_bwd(in.data, out.data, f.data, dx.data, df.data, db.data, in.N(), in.H(), in.W(), in.C(),
+                                 out.H(), out.W(), out.C(), f.H(), in.stride[0], in.stride[2], train, ST0);
+        if (rc == T4K_ENOSUP) ERROR("nn#bconv kernel_size=%d stride=%d padding=%d not supported\n", f.H(), in.stride[0], in.stride[2]);
+        else { KCALL(rc); KCALL(t4k_copy(dx.data, in.data, dx.numel, ST0)); }     // x = dX (overwrite), as Model::_bconv
+    } break;
     default: ERROR("nn#bstep layer=%d not supported\n", fn);
     }
 }

@@ -228,6 +228,40 @@ def dconv2d(I, dO, F, K, S, P, dF=None, dB=None, train=True):
     return dX, dF, dB
 
 
+def convt_out_dims(H1, W1, K, S, P):
+    """Model::_iconv, transposed branch (src/nn/model.cpp:129-133)"""
+    P0 = (H1 + 2 * P - K) % S
+    return (H1 - 1) * S - 2 * P + K + P0, (W1 - 1) * S - 2 * P + K + P0
+
+
+def convt2d(I, F, B, K, S, P, out_hw=None):
+    """conv-transpose forward as the reference wires L_DCONV (src/nn/forward.cu:110 -> Model::_bconv): the input-gradient half of k_dconv2d
+    (orc_dconv2d, flipped taps) applied to the layer input, on the geometry of the convolution (C0 -> C1) that maps the large image onto the small
+    one; F [C0][K][K][C1]; then k_bias per output channel."""
+    I, F, B = f32(I), f32(F), f32(B)
+    N, H1, W1, C1 = I.shape
+    C0 = F.shape[0]
+    H0, W0 = out_hw if out_hw else convt_out_dims(H1, W1, K, S, P)   # out_hw: any large size the convolution maps onto (H1, W1)
+    assert conv_out_dims(H0, W0, K, S, P) == (H1, W1)
+    O, _, _ = dconv2d(np.zeros((N, H0, W0, C0), np.float32), I, F, K, S, P, train=False)
+    lib().orc_bias(_p(B), _p(O), N * H0 * W0, C0)
+    return O
+
+
+def dconvt2d(I, dO, F, K, S, P, dF=None, dB=None, train=True):
+    """conv-transpose backward (src/nn/backprop.cu:137 -> Model::_fconv): dX = k_conv2d(dO, F) without bias; train: dF += the filter-gradient half
+    of k_dconv2d on (input, output gradient) = (dO, I), dB[c0] += sum of dO over the pixels"""
+    I, dO, F = f32(I), f32(dO), f32(F)
+    C0, C1 = F.shape[0], F.shape[3]
+    dF = np.zeros_like(F) if dF is None else f32(dF).copy()
+    dB = np.zeros(C0, np.float32) if dB is None else f32(dB).copy()
+    if train:
+        _, dF, _ = dconv2d(dO, I, F, K, S, P, dF=dF, dB=np.zeros(C1, np.float32), train=True)
+        dB = (dB + dO.reshape(-1, C0).sum(axis=0, dtype=np.float64)).astype(np.float32)
+    dX = conv2d(dO, F, np.zeros(C1, np.float32), K, S, P)
+    return dX, dF, dB
+
+
 def pool(layer, I, K):
     I = f32(I)
     N, H1, W1, Cc = I.shape
@@ -340,6 +374,19 @@ class OracleModel:
             t.ex = np.zeros_like(t.data)
             H0, W0 = conv_out_dims(H, W, K, S, P)
             self.layers.append(Layer((N, H0, W0, n)))
+        elif fn == L_DCONV:
+            K = opt[0] if opt else 4
+            S = opt[1] if opt else 2
+            P = opt[2] if (opt and K > 1 and opt[2]) else (K - 1) // 2
+            t.K, t.S, t.P = K, S, P
+            t.xparm = bias
+            k = np.float32(np.sqrt(6.0 / (K * K * Cc)))
+            t.w = self._rand((n, K, K, Cc), k)              # [C0][K][K][C1]: see convt2d
+            t.b = self._rand((n,), bias)
+            t.dw = np.zeros_like(t.w); t.db = np.zeros_like(t.b)
+            t.ex = np.zeros_like(t.data)
+            H0, W0 = convt_out_dims(H, W, K, S, P)
+            self.layers.append(Layer((N, H0, W0, n)))
         elif fn == L_LINEAR:
             E1 = H * W * Cc
             k = np.float32(np.sqrt(1.0 / (n + E1)))
@@ -382,6 +429,8 @@ class OracleModel:
             N = t.data.shape[0]
             if fn == L_CONV:
                 o.data = conv2d(t.data, t.w, t.b, t.K, t.S, t.P)
+            elif fn == L_DCONV:
+                o.data = convt2d(t.data, t.w, t.b, t.K, t.S, t.P)
             elif fn == L_LINEAR:
                 y = gemm(t.data.reshape(N, -1), t.w, tB=True)
                 lib().orc_bias(_p(t.b), _p(y), N, y.shape[1])
@@ -435,6 +484,9 @@ class OracleModel:
             if fn == L_CONV:
                 dX, t.dw, t.db = dconv2d(t.data, o.data, t.w, t.K, t.S, t.P, t.dw, t.db, self.train)
                 t.ex = dX; t.data = dX.copy()
+            elif fn == L_DCONV:
+                dX, t.dw, t.db = dconvt2d(t.data, o.data, t.w, t.K, t.S, t.P, t.dw, t.db, self.train)
+                t.ex = dX; t.data = dX.copy()
             elif fn == L_LINEAR:
                 if j == 0:                               # last layer linear + MSE :119-121
                     t.data = o.data.reshape(t.data.shape).copy()
@@ -465,7 +517,7 @@ class OracleModel:
         for t in self.layers[:-1]:
             if t.w is not None and t.dw is not None:
                 # Nw = parameter tensor's N(): conv filter T4(C1,K,K,C0) → C1; linear T4(1,..) → 1; VEC → 1
-                yield t, "w", (t.w.shape[0] if t.fn == L_CONV else 1)
+                yield t, "w", (t.w.shape[0] if t.fn == L_CONV else t.w.shape[3] if t.fn == L_DCONV else 1)   # dconv2d: the reference's T4(C1,K,K,C0) -> C1
                 yield t, "b", 1
 
     def _step(self, kind, lr, b1, b2, wd=0.0):

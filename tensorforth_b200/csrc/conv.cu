@@ -581,14 +581,11 @@ extern "C" int t4k_conv2d_fwd(const float *I, const float *F, const float *B, fl
     return 0;
 }
 
-extern "C" int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, float *dX, float *dF, float *dB,
-                              int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P,
-                              int train, t4k_stream_t s) {
-    if (!I || !dO || !F || !dX || N < 1 || H1 < 1 || W1 < 1 || C1 < 1 || H0 < 1 || W0 < 1 || C0 < 1) return T4K_EINVAL;
-    if (train && (!dF || !dB)) return T4K_EINVAL;
-    if (!conv_cfg_ok(KS, S, P)) return T4K_ENOSUP;
+// the two halves of k_dconv2d: parameter gradients (train: dF += , dB += ; reads I and dO) and input gradient (dX: reads dO and F; skipped when
+// dX == nullptr).  t4k_conv2d_bwd runs both; the conv-transpose layer (t4k_dconv2d_*) takes one half at a time with the roles swapped.
+static int conv_bwd_impl(const float *I, const float *dO, const float *F, float *dX, float *dF, float *dB,
+                         int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, int train, cudaStream_t st) {
     ConvP p{I, F, nullptr, dO, nullptr, dX, dF, dB, N, H1, W1, C1, H0, W0, C0, KS, S, P};
-    cudaStream_t st = STRM(s);
     const int nF = C1 * KS * KS * C0;
     int rc;
     // ---- weight + bias gradient first (dX may alias nothing, but keep I intact until wgrad has read it)
@@ -638,6 +635,7 @@ extern "C" int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, f
             rc = check_launch(); if (rc) return rc;
         }
     }
+    if (!dX) return 0;
     // ---- input gradient (flipped taps)
     const int64_t npix = (int64_t)N * H1 * W1;
     const size_t fbytes = (size_t)nF * sizeof(float);
@@ -664,6 +662,61 @@ extern "C" int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, f
         rc = check_launch(); if (rc) return rc;
     }
     return 0;
+}
+
+extern "C" int t4k_conv2d_bwd(const float *I, const float *dO, const float *F, float *dX, float *dF, float *dB,
+                              int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P,
+                              int train, t4k_stream_t s) {
+    if (!I || !dO || !F || !dX || N < 1 || H1 < 1 || W1 < 1 || C1 < 1 || H0 < 1 || W0 < 1 || C0 < 1) return T4K_EINVAL;
+    if (train && (!dF || !dB)) return T4K_EINVAL;
+    if (!conv_cfg_ok(KS, S, P)) return T4K_ENOSUP;
+    return conv_bwd_impl(I, dO, F, dX, dF, dB, N, H1, W1, C1, H0, W0, C0, KS, S, P, train, STRM(s));
+}
+
+// ---- conv-transpose layer (L_DCONV, `dconv2d`: 4x4, stride 2): the reference wires it as the convolution layer with the two kernels' roles
+// swapped — forward = k_dconv2d's input-gradient half, backward = k_conv2d (src/nn/forward.cu:110, backprop.cu:137; shapes model.cpp:129-133).
+// Layer input I [N,H1,W1,C1] (small), output O [N,H0,W0,C0] (large); F is the filter [C0][K][K][C1] of the convolution (C0 -> C1, K, S, P) that maps
+// the large image onto the small one.
+extern "C" int t4k_dconv2d_fwd(const float *I, const float *F, const float *B, float *O,
+                               int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, t4k_stream_t s) {
+    if (!I || !F || !B || !O || N < 1 || H1 < 1 || W1 < 1 || C1 < 1 || H0 < 1 || W0 < 1 || C0 < 1) return T4K_EINVAL;
+    if (!conv_cfg_ok(KS, S, P)) return T4K_ENOSUP;
+    if ((H0 - KS + 2 * P) / S + 1 != H1 || (W0 - KS + 2 * P) / S + 1 != W1) return T4K_EINVAL;
+    // O = "dX" of the convolution whose output gradient is I (flipped taps, as k_dconv2d computes it), then + bias per output channel
+    int rc = conv_bwd_impl(nullptr, I, F, O, nullptr, nullptr, N, H0, W0, C0, H1, W1, C1, KS, S, P, 0, STRM(s));
+    if (rc) return rc;
+    return t4k_bias(B, O, (int)((int64_t)N * H0 * W0), C0, s);
+}
+extern "C" int t4k_dconv2d_bwd(const float *I, const float *dO, const float *F, float *dX, float *dF, float *dB,
+                               int N, int H1, int W1, int C1, int H0, int W0, int C0, int KS, int S, int P, int train, t4k_stream_t s) {
+    if (!I || !dO || !F || !dX || N < 1 || H1 < 1 || W1 < 1 || C1 < 1 || H0 < 1 || W0 < 1 || C0 < 1 || I == dX) return T4K_EINVAL;
+    if (train && (!dF || !dB)) return T4K_EINVAL;
+    if (!conv_cfg_ok(KS, S, P)) return T4K_ENOSUP;
+    if ((H0 - KS + 2 * P) / S + 1 != H1 || (W0 - KS + 2 * P) / S + 1 != W1) return T4K_EINVAL;
+    cudaStream_t st = STRM(s);
+    int rc;
+    float *zb = (float*)workspace((size_t)(2 * C1 + 8) * sizeof(float), 3);        // [C1] zero bias | [C1] the convolution's own dB (discarded)
+    if (!zb) return T4K_ENOMEM;
+    if (cudaMemsetAsync(zb, 0, (size_t)2 * C1 * sizeof(float), st) != cudaSuccess) return (int)cudaGetLastError();
+    if (train) {
+        // dF += the convolution's filter gradient with (input, output gradient) = (dO, I): k_dconv2d's parameter half
+        rc = conv_bwd_impl(dO, I, F, nullptr, dF, zb + C1, N, H0, W0, C0, H1, W1, C1, KS, S, P, 1, st);
+        if (rc) return rc;
+        // dB[c0] += sum over the output pixels of dO (the bias is added per output channel in the forward)
+        const int64_t rows = (int64_t)N * H0 * W0;
+        int nparts = 4 * sm_count();
+        int64_t rows_per = (rows + nparts - 1) / nparts; if (rows_per < 1) rows_per = 1;
+        nparts = (int)((rows + rows_per - 1) / rows_per);
+        float *bp = (float*)workspace((size_t)nparts * C0 * sizeof(float), 5);
+        if (!bp) return T4K_ENOMEM;
+        if (C0 <= T4K_THREADS) k_colsum_part_c<<<nparts, T4K_THREADS, 0, st>>>(dO, bp, rows, C0, rows_per);
+        else                   k_colsum_part<<<nparts, T4K_THREADS, 0, st>>>(dO, bp, rows, C0, rows_per);
+        rc = check_launch(); if (rc) return rc;
+        k_colsum_fin<<<(C0 + T4K_THREADS - 1) / T4K_THREADS, T4K_THREADS, 0, st>>>(bp, dB, C0, nparts);
+        rc = check_launch(); if (rc) return rc;
+    }
+    // dX = k_conv2d(dO) with the same filter, no bias
+    return t4k_conv2d_fwd(dO, F, zb, dX, N, H0, W0, C0, H1, W1, C1, KS, S, P, s);
 }
 
 // ---- fused conv → maxpool(2) → relu (→ flatten) block; T4K_ENOSUP when the shape is not eligible (caller: per-layer calls)

@@ -296,6 +296,7 @@ Model &Model::add(t4_layer fn, U32 n, DU bias, U16 *opt) {
     size_t before = _layers.size();
     switch (fn) {
     case T4K_L_CONV:    _iconv(in, n, bias, opt ? opt : dflt); break;
+    case T4K_L_DCONV: { U16 d4[4] = {4, 2, 0, 1}; _iconv(in, n, bias, opt ? opt : d4, true); } break;   // word `dconv2d` = _conv(4, true, 2), netvm.cpp:315
     case T4K_L_LINEAR:  _ilinear(in, n, bias);                 break;
     case T4K_L_FLATTEN: _iflatten(in);                         break;
     case T4K_L_RELU: case T4K_L_TANH: case T4K_L_SIGMOID: case T4K_L_SELU:
@@ -304,23 +305,33 @@ Model &Model::add(t4_layer fn, U32 n, DU bias, U16 *opt) {
     case T4K_L_AVGPOOL: case T4K_L_MAXPOOL: case T4K_L_MINPOOL: _ipool(in, (U16)n); break;
     case T4K_L_BATCHNM: _ibatchnorm(in, bias);                 break;
     case T4K_L_USAMPLE: _iup(in, (U16)n, bias);                break;
-    default: Runtime::error("Model#add layer %d not supported\n", fn); err = true; return *this;   // L_DCONV: SURVEY §8f row 4
+    default: Runtime::error("Model#add layer %d not supported\n", fn); err = true; return *this;
     }
     if (_layers.size() > before) in.grad_fn = fn;
     return *this;
 }
-void Model::_iconv(Tensor &in, U32 C0, DU bias, U16 *opt) {               // model.cpp:122-180
+void Model::_iconv(Tensor &in, U32 C0, DU bias, U16 *opt, bool txn) {     // model.cpp:122-180
     U32 N1 = in.N(), H1 = in.H(), W1 = in.W(), C1 = in.C();
     U16 Kx = opt[0], Ky = opt[0], S = opt[1];
     U16 P  = (Kx > 1 && opt[2]) ? opt[2] : (Kx - 1) / 2;
-    U16 H0 = (H1 - Kx + P * 2) / S + 1;
-    U16 W0 = (H1 - Ky + P * 2) / S + 1;                                   // sic: W0 from H1 (model.cpp:137)
-    (void)W1;
-    if (Kx != 1 && Kx != 3 && Kx != 5) { Runtime::error("nn#iconv conv2d f=[%d,%d]? 1x1, 3x3, 4x4, and 5x5 supported only.\n", Kx, Ky); err = true; return; }
+    U16 H0, W0;
+    if (txn) {                                                            // transposed: output padding + output size (model.cpp:129-133)
+        const U16 P0 = (H1 + P * 2 - Kx) % S;
+        H0 = (H1 - 1) * S - P * 2 + Kx + P0;
+        W0 = (W1 - 1) * S - P * 2 + Ky + P0;
+    } else {
+        H0 = (H1 - Kx + P * 2) / S + 1;
+        W0 = (H1 - Ky + P * 2) / S + 1;                                   // sic: W0 from H1 (model.cpp:137)
+    }
+    if ((!txn && Kx != 1 && Kx != 3 && Kx != 5) || (txn && Kx != 4)) {
+        Runtime::error("nn#iconv %s f=[%d,%d]? 1x1, 3x3, 4x4, and 5x5 supported only.\n", txn ? "dconv2d" : "conv2d", Kx, Ky); err = true; return;
+    }
     in.stride[0] = in.stride[1] = S; in.stride[2] = in.stride[3] = P; in.xparm = bias;
-    Tensor *f = in.grad[0] = &Tensor::create(C1, Kx, Ky, C0);
+    // conv: f [C1][K][K][C0].  conv-transpose: the same number of elements, held as the filter [C0][K][K][C1] of the convolution (C0 -> C1) whose
+    // kernels the layer runs with swapped roles (t4k_dconv2d_*); Kaiming range from the layer's input channels either way (model.cpp:160)
+    Tensor *f = in.grad[0] = txn ? &Tensor::create(C0, Kx, Ky, C1) : &Tensor::create(C1, Kx, Ky, C0);
     Tensor *b = in.grad[1] = &Tensor::create((U64)C0);
-    in.grad[2] = &Tensor::create(C1, Kx, Ky, C0).zeros();
+    in.grad[2] = txn ? &Tensor::create(C0, Kx, Ky, C1).zeros() : &Tensor::create(C1, Kx, Ky, C0).zeros();
     in.grad[3] = &Tensor::create((U64)C0).zeros();
     in.grad[4] = &Tensor::create(N1, H1, in.W(), C1).zeros();
     DU k = sqrtf(6.0f / (Kx * Ky * C1));
@@ -538,6 +549,7 @@ void Model::_fstep(Tensor &in, Tensor &out) {                             // for
     t4_layer fn = in.grad_fn;
     switch (fn) {
     case T4K_L_CONV:    _fconv(in, out);   break;
+    case T4K_L_DCONV:   _fdconv(in, out);  break;
     case T4K_L_LINEAR:  _flinear(in, out); break;
     case T4K_L_FLATTEN: out = in;          break;
     case T4K_L_RELU: case T4K_L_TANH: case T4K_L_SIGMOID: case T4K_L_SELU:
@@ -563,6 +575,23 @@ int Model::_fconv(Tensor &in, Tensor &out) {                              // for
                             f.H(), in.stride[0], in.stride[2], ST);
     if (rc == T4K_ENOSUP) { Runtime::error("nn#fconv kernel_size=%d stride=%d padding=%d not supported\n", f.H(), in.stride[0], in.stride[2]); return -1; }
     KCHK(rc);
+    return 0;
+}
+int Model::_fdconv(Tensor &in, Tensor &out) {                             // forward.cu:110 (the convolution's kernels, roles swapped)
+    Tensor &f = *in.grad[0], &b = *in.grad[1];
+    int rc = t4k_dconv2d_fwd(in.data, f.data, b.data, out.data, out.N(), in.H(), in.W(), in.C(), out.H(), out.W(), out.C(),
+                             f.H(), in.stride[0], in.stride[2], ST);
+    if (rc == T4K_ENOSUP) { Runtime::error("nn#fconv kernel_size=%d stride=%d padding=%d not supported\n", f.H(), in.stride[0], in.stride[2]); return -1; }
+    KCHK(rc);
+    return 0;
+}
+int Model::_bdconv(Tensor &in, Tensor &out) {                             // backprop.cu:137
+    Tensor &f = *in.grad[0], &df = *in.grad[2], &db = *in.grad[3], &dx = *in.grad[4];
+    int rc = t4k_dconv2d_bwd(in.data, out.data, f.data, dx.data, df.data, db.data, in.N(), in.H(), in.W(), in.C(),
+                             out.H(), out.W(), out.C(), f.H(), in.stride[0], in.stride[2], train, ST);
+    if (rc == T4K_ENOSUP) { Runtime::error("nn#bconv kernel_size=%d stride=%d padding=%d not supported\n", f.H(), in.stride[0], in.stride[2]); return -1; }
+    KCHK(rc);
+    in = dx;                                                               // x = dX (overwrite), as Model::_bconv
     return 0;
 }
 int Model::_flinear(Tensor &in, Tensor &out) {                            // forward.cu:158-198
@@ -674,6 +703,7 @@ void Model::_bstep(Tensor &in, Tensor &out, bool last_layer) {            // bac
     t4_layer fn = in.grad_fn;
     switch (fn) {
     case T4K_L_CONV:    _bconv(in, out); break;
+    case T4K_L_DCONV:   _bdconv(in, out); break;
     case T4K_L_LINEAR:  if (last_layer) in = out; else _blinear(in, out); break;
     case T4K_L_FLATTEN: in = out; break;
     case T4K_L_RELU: case T4K_L_TANH: case T4K_L_SELU: case T4K_L_LEAKYRL: case T4K_L_ELU:
@@ -877,7 +907,8 @@ Model &Model::grad_alloc(t4_optimizer op) {
     std::vector<Seg> segs;
     for (size_t i = 0; i + 1 < _layers.size(); i++) {
         Tensor &in = *_layers[i];
-        if (in.grad[0] && in.grad[2]) segs.push_back({in.grad[0], in.grad[2], (int)in.grad[0]->N(), (int)i});   // Nw = parameter tensor's N() (gradient.cu:137)
+        // Nw = parameter tensor's N() (gradient.cu:137); conv-transpose: the reference's filter is T4(C1,K,K,C0), N() = the layer's input channels
+        if (in.grad[0] && in.grad[2]) segs.push_back({in.grad[0], in.grad[2], (int)(in.grad_fn == T4K_L_DCONV ? in.C() : in.grad[0]->N()), (int)i});
         if (in.grad[1] && in.grad[3]) segs.push_back({in.grad[1], in.grad[3], (int)in.grad[1]->N(), (int)i});
     }
     _arena_opt = op;
@@ -968,7 +999,7 @@ int Model::save(const char *fname) {                                       // AI
     for (int i = 0; i < n - 1; i++) {
         Tensor &in = *_layers[i];
         switch (in.grad_fn) {
-        case T4K_L_CONV: case T4K_L_LINEAR: dump('w', nname(in.grad_fn), *in.grad[0]); dump('b', nname(in.grad_fn), *in.grad[1]); break;
+        case T4K_L_CONV: case T4K_L_DCONV: case T4K_L_LINEAR: dump('w', nname(in.grad_fn), *in.grad[0]); dump('b', nname(in.grad_fn), *in.grad[1]); break;
         case T4K_L_BATCHNM: dump('w', nname(in.grad_fn), *in.grad[0]); break;
         default: break;
         }
@@ -995,7 +1026,7 @@ int Model::load(const char *fname) {                                       // AI
     for (int i = 0; i < n - 1 && !err; i++) {
         Tensor &in = *_layers[i];
         switch (in.grad_fn) {
-        case T4K_L_CONV: case T4K_L_LINEAR: read(*in.grad[0]); if (!err) read(*in.grad[1]); break;
+        case T4K_L_CONV: case T4K_L_DCONV: case T4K_L_LINEAR: read(*in.grad[0]); if (!err) read(*in.grad[1]); break;
         case T4K_L_BATCHNM: read(*in.grad[0]); break;
         default: break;
         }

@@ -240,7 +240,7 @@ public:
     int    bn_channels();
     int    step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd);
 private:
-    void _iconv(Tensor &in, U32 c, DU bias, U16 *opt);
+    void _iconv(Tensor &in, U32 c, DU bias, U16 *opt, bool txn = false);
     void _ilinear(Tensor &in, U32 n, DU bias);
     void _iflatten(Tensor &in);
     void _isoftmax(Tensor &in);
@@ -254,6 +254,8 @@ private:
     int  _bfused_head(Tensor &tgt, bool *skip_db);
     int  _bfused(int i);
     int  _fconv(Tensor &in, Tensor &out);
+    int  _fdconv(Tensor &in, Tensor &out);
+    int  _bdconv(Tensor &in, Tensor &out);
     int  _flinear(Tensor &in, Tensor &out);
     int  _factivate(Tensor &in, Tensor &out, t4_layer fn);
     int  _fpool(Tensor &in, Tensor &out, t4_layer fn);

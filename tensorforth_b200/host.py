@@ -240,6 +240,7 @@ class Model:
     def maxpool(self, k): return self.add(_k.L_MAXPOOL, k)
     def avgpool(self, k): return self.add(_k.L_AVGPOOL, k)
     def minpool(self, k): return self.add(_k.L_MINPOOL, k)
+    def dconv2d(self, bias, c, k=4, s=2, p=0, d=1): return self.add(_k.L_DCONV, c, bias, [k, s, p, d])   # word `dconv2d` = _conv(4, true, 2): 4x4, stride 2 (netvm.cpp:315)
     def batchnorm(self, m=0.1): return self.add(_k.L_BATCHNM, 0, m)
     def upsample(self, k, m=0.0): return self.add(_k.L_USAMPLE, k, m)
 

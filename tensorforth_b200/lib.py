@@ -61,6 +61,8 @@ PROTOTYPES = {
     "t4k_dbias": (_i, [_p, _p, _i, _i, _p]),
     "t4k_linear_bwd": (_i, [_p] * 6 + [_i] * 4 + [_p]),
     "t4k_linear_bwd_ex": (_i, [_p] * 6 + [_i] * 5 + [_p]),
+    "t4k_dconv2d_fwd": (_i, [_p] * 4 + [_i] * 10 + [_p]),
+    "t4k_dconv2d_bwd": (_i, [_p] * 6 + [_i] * 11 + [_p]),
     "t4k_rand_sharded": (_i, [_p, _l, _l, _l, _i, _f, _f, _p]),
     "t4k_batchnorm_fwd_dp": (_i, [_p] * 7 + [_i] * 4 + [_p]),
     "t4k_batchnorm_bwd_dp": (_i, [_p] * 8 + [_i] * 5 + [_p]),

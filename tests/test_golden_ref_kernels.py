@@ -276,3 +276,27 @@ def test_oracle_reproduces_reference_kernels(key):
 @pytest.mark.parametrize("key", KEYS)
 def test_cuda_path_reproduces_reference_kernels(key):
     run_case(Gpu(), key)
+
+
+# ------------------------------------------------------------------ conv-transpose (L_DCONV): the reference's kernels with swapped roles
+def test_conv_transpose_oracle_is_the_reference_kernels_with_swapped_roles():
+    """oracle.convt2d / dconvt2d (what t4k_dconv2d_fwd / _bwd are held to) against the outputs of the reference's OWN k_dconv2d and k_conv2d at the
+    layer's configuration (4x4, stride 2, padding 1: fixtures dconv_k4 / conv_k4, produced by oracle/ref/refkern.cu from the unmodified nmath.tcu):
+      forward   = k_dconv2d's dX with (output gradient := layer input)                       (src/nn/forward.cu:110)
+      backward  = k_conv2d of the layer's output gradient (bias-free) and k_dconv2d's dF with (input, output gradient) := (dO, I)  (backprop.cu:137)"""
+    key = "dconv_k4"
+    N, H, W, C1, H0, W0, C0, K, S, P, tr = ints(key)
+    big, small, F = gin(key, 0).reshape(N, H, W, C1), gin(key, 1).reshape(N, H0, W0, C0), gin(key, 2).reshape(C1, K, K, C0)                   # conv input [N,14,14,2], its output gradient [N,7,7,6], filter [2][4][4][6]
+    assert orc.convt_out_dims(H0, W0, K, S, P) == (H + 1, W + 1)            # model.cpp:129-133 gives an odd input the larger of the two pre-images (15);
+    # forward: layer input = `small`; no bias; the fixture's own pre-image (14) exercises the same kernel
+    O = orc.convt2d(small, F, np.zeros(C1, np.float32), K, S, P, out_hw=(H, W))
+    close(O, G[key + "/dX"], what="conv-transpose forward == the reference's k_dconv2d dX")
+    # backward, parameters: layer input `small`, output gradient `big`
+    dX, dF, dB = orc.dconvt2d(small, big, F, K, S, P, dF=gin(key, 4).reshape(C1, K, K, C0), dB=np.zeros(C1, np.float32), train=True)
+    close(dF, G[key + "/dF"], what="conv-transpose dF == the reference's k_dconv2d dF")
+    close(dB, big.reshape(-1, C1).astype(np.float64).sum(0), rtol=1e-5, what="dB = pixel sums of dO")
+    # backward, input gradient: the reference's k_conv2d on the same input (fixture conv_k4 carries a bias: removed)
+    ck = "conv_k4"
+    want = G[ck + "/O"].astype(np.float64).reshape(-1, C0) - gin(ck, 2).astype(np.float64)
+    got, _, _ = orc.dconvt2d(np.zeros((N, H0, W0, C0), np.float32), gin(ck, 0).reshape(N, H, W, C1), gin(ck, 1).reshape(C1, K, K, C0), K, S, P, train=False)
+    close(got, want, rtol=1e-5, what="conv-transpose dX == the reference's k_conv2d (bias removed)")

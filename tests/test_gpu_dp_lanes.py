@@ -136,8 +136,7 @@ def shards(a, world):
     return [np.ascontiguousarray(a[r * n:(r + 1) * n]) for r in range(world)]
 
 
-@pytest.mark.parametrize("graph", [False, True])
-@pytest.mark.parametrize("world,N", [(2, 16), (4, 8)])
+@pytest.mark.parametrize("world,N,graph", [(2, 16, False), (4, 8, False), (2, 16, True)])
 def test_mnist_cnn_dp_follows_the_single_rank_trajectory(world, N, graph):
     """t4_40a.4th's CNN, global batch world*N sharded over `world` ranks: eager (forward / backprop / adam with the exchange fused into the optimizer
     kernel) and the CAPTURED step (early push of the finished gradient segments on the side stream) against one rank on the whole batch"""

@@ -622,6 +622,32 @@ CONV_CASES = [  # N,H,W,C1,C0,K,S,P
 ]
 
 
+@pytest.mark.parametrize("N,H1,W1,C1,C0", [(2, 7, 7, 6, 2), (3, 4, 4, 8, 6), (2, 8, 8, 6, 1), (2, 7, 7, 24, 24), (1, 14, 14, 64, 32)])
+def test_conv_transpose_fwd_bwd(N, H1, W1, C1, C0):
+    """L_DCONV (word `dconv2d`: 4x4, stride 2, padding 1): t4k_dconv2d_fwd / _bwd against the oracle's restatement — the reference's k_dconv2d /
+    k_conv2d with swapped roles (forward.cu:110, backprop.cu:137), itself pinned to the reference kernels' outputs (tests/test_golden_ref_kernels.py)"""
+    K, S, P = 4, 2, 1
+    H0, W0 = orc.convt_out_dims(H1, W1, K, S, P)
+    I, F, Bv = rnd(N, H1, W1, C1), rnd(C0, K, K, C1, lo=-.3, hi=.3), rnd(C0)
+    o = dev(np.full((N, H0, W0, C0), np.nan, np.float32))                    # must not need pre-zeroing
+    ok(lib().t4k_dconv2d_fwd(ptr(dev(I)), ptr(dev(F)), ptr(dev(Bv)), ptr(o), N, H1, W1, C1, H0, W0, C0, K, S, P, None), "dconv fwd")
+    assert_close(host(o), orc.convt2d(I, F, Bv, K, S, P), rtol=1e-4, what="conv-transpose fwd")
+    dO, dF0, dB0 = rnd(N, H0, W0, C0), rnd(C0, K, K, C1), rnd(C0)
+    dx, df, db = dev(np.full(I.shape, np.nan, np.float32)), dev(dF0), dev(dB0)
+    ok(lib().t4k_dconv2d_bwd(ptr(dev(I)), ptr(dev(dO)), ptr(dev(F)), ptr(dx), ptr(df), ptr(db), N, H1, W1, C1, H0, W0, C0, K, S, P, 1, None), "dconv bwd")
+    rdx, rdf, rdb = orc.dconvt2d(I, dO, F, K, S, P, dF0, dB0, True)
+    assert_close(host(dx), rdx, rtol=1e-4, what="conv-transpose dX")
+    assert_close(host(df), rdf, rtol=1e-4, what="conv-transpose dF")
+    assert_close(host(db), rdb, rtol=1e-4, what="conv-transpose dB")
+    # not trainable: parameters untouched
+    df2, db2 = dev(dF0), dev(dB0)
+    ok(lib().t4k_dconv2d_bwd(ptr(dev(I)), ptr(dev(dO)), ptr(dev(F)), ptr(dx), ptr(df2), ptr(db2), N, H1, W1, C1, H0, W0, C0, K, S, P, 0, None))
+    assert_exact(host(df2), dF0, "dF untouched"); assert_exact(host(db2), dB0, "dB untouched")
+    # geometry the layer cannot have / aliasing
+    assert lib().t4k_dconv2d_fwd(ptr(dev(I)), ptr(dev(F)), ptr(dev(Bv)), ptr(o), N, H1, W1, C1, H0 + 2, W0, C0, K, S, P, None) == t4.EINVAL
+    assert lib().t4k_dconv2d_fwd(ptr(dev(I)), ptr(dev(F)), ptr(dev(Bv)), ptr(o), N, H1, W1, C1, H0, W0, C0, 2, 2, 0, None) == t4.ENOSUP
+
+
 @pytest.mark.parametrize("N,H,W,C1,C0,K,S,P", CONV_CASES)
 def test_conv2d_fwd_bwd(N, H, W, C1, C0, K, S, P):
     I, F, Bv = rnd(N, H, W, C1), rnd(C1, K, K, C0, lo=-.3, hi=.3), rnd(C0)

@@ -242,6 +242,11 @@ def build_pair(kind, N):
         om.add(orc.L_LINEAR, 256, 1.0).add(orc.L_LEAKYRL, 0, 0.2).add(orc.L_LINEAR, 512, 1.0).add(orc.L_LEAKYRL, 0, 0.2)
         om.add(orc.L_LINEAR, 784, 1.0).add(orc.L_TANH)
         shape, E, lop = (N, 128, 1, 1), 784, t4.LOSS_MSE
+    elif kind == "dcgan":             # conv-transpose up-sampling stack (word `dconv2d`, netvm.cpp:315): 4x4 -> 8x8 -> 16x16
+        gm = th.Model(N, 4, 4, 8).dconv2d(0.5, 6).relu().dconv2d(0.5, 1).tanh()
+        om = orc.OracleModel(N, 4, 4, 8, seed=9)
+        om.add(orc.L_DCONV, 6, 0.5).add(orc.L_RELU).add(orc.L_DCONV, 1, 0.5).add(orc.L_TANH)
+        shape, E, lop = (N, 4, 4, 8), 256, t4.LOSS_MSE
     elif kind == "bn":                # conv + batchnorm block as in examples/t4_30e.4th:28-31
         gm = (th.Model(N, 8, 8, 3).conv2d(0.5, 6).batchnorm().relu().avgpool(2).flatten().linear(5).sigmoid())
         om = orc.OracleModel(N, 8, 8, 3, seed=8)
@@ -252,7 +257,7 @@ def build_pair(kind, N):
     return gm, om, shape, E, lop
 
 
-@pytest.mark.parametrize("kind,N", [("mnist", 8), ("mnist", 64), ("mnist", 512), ("toycnn", 2), ("gan_g", 16), ("gan_g", 1024), ("bn", 4)])   # 512 / 1024: the BASELINE batch sizes
+@pytest.mark.parametrize("kind,N", [("mnist", 8), ("mnist", 64), ("mnist", 512), ("toycnn", 2), ("gan_g", 16), ("gan_g", 1024), ("bn", 4), ("dcgan", 6)])   # 512 / 1024: the BASELINE batch sizes
 @pytest.mark.parametrize("opt", ["sgd", "adam", "adamw"])
 def test_model_train_steps_vs_oracle(kind, N, opt):
     rng = np.random.default_rng(11)

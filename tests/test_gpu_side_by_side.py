@@ -24,3 +24,26 @@ def test_reference_vm_on_libt4k_prints_what_the_reference_prints(tmp_path):
     sys.stdout.write(summary)
     assert " OK " in summary, p.stdout[-2000:] + p.stderr[-2000:]
     assert "DIFF" not in summary and "MISSING" not in summary, summary
+
+
+@pytest.mark.gpu
+def test_object_store_beyond_2gib_from_forth():
+    """`ten4_b200` carries integration/arena_shim (object store sized for the device, 64-bit host-side allocator,
+    device-preferred managed memory): a 4096^2 `@` and an N=1024 64-channel 56x56 conv2d layer (3.3 GB of tensors) run from Forth text on the
+    new kernels.  The reference's own 2 GiB TLSF store (src/ten4_config.h:67, src/mu/tlsf.h:19-31) cannot hold the model."""
+    if not os.path.exists(NEW):
+        pytest.skip("integration/_build/ten4_b200 not built")
+    src = open(os.path.join(ROOT, "integration", "scripts_b200", "big_arena.4th")).read()
+    p = subprocess.run([NEW], input=src, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = p.stdout
+    sys.stdout.write(out[-1500:])
+
+    def val(tag):
+        import re
+        m = re.search(re.escape(tag) + r"\s*(-?[0-9.]+(?:e[-+]?\d+)?)", out)
+        assert m, (tag, out[-1500:], p.stderr[-500:])
+        return float(m.group(1))
+    assert abs(val("gemm sum/4096^3=") - 1.0) < 1e-3
+    assert abs(val("conv out max=") - 9 * 64 * 0.5 * 0.001) < 1e-4          # interior pixel: all nine taps in the image
+    assert abs(val("conv out min=") - 4 * 64 * 0.5 * 0.001) < 1e-4          # corner pixel: four taps
+    assert val("dw sum/1e6=") > 0
