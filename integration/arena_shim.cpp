@@ -89,12 +89,14 @@ __HOST__ void *TLSF::realloc(void *p0, U64 sz) {
 
 __HOST__ int  TLSF::_mmu_ok() { return 1; }
 __HOST__ void TLSF::_show_stat() {
+#if T4_VERBOSE > 1                                       // as the reference: the allocator reports only in verbose builds (src/mu/tlsf.cpp:414-415)
     std::lock_guard<std::mutex> lk(_mutex);
     U64 fr = 0, big = 0;
     for (auto &b : g_a.free_by_off) { fr += b.second; if (b.second > big) big = b.second; }
     printf("\\ object store %p: %lu MiB, used %lu MiB in %zu blocks (peak %lu MiB), free %lu MiB in %zu blocks (largest %lu MiB)\n",
            (void*)_heap, (unsigned long)(_heap_sz >> 20), (unsigned long)(g_a.in_use >> 20), g_a.used.size(), (unsigned long)(g_a.peak >> 20),
            (unsigned long)(fr >> 20), g_a.free_by_off.size(), (unsigned long)(big >> 20));
+#endif
 }
 __HOST__ void TLSF::_dump_freelist() {
 #if MM_DEBUG
