@@ -110,7 +110,9 @@ void  t4h_graph_free(void *graph);
 /* words `save` / `load` on a model (src/vm/netvm.cpp:479-480 -> src/io/aio_model.cpp): the reference's model file — text header and
  * layer lines, then `--- w.<layer>` / `--- b.<layer>` sections of raw FP32.  load fills an already built model (parameter path). */
 int   t4h_model_save(t4h_model m, const char *fname);
-int   t4h_model_load(t4h_model m, const char *fname);
+int   t4h_model_load(t4h_model m, const char *fname);      /* parameters; + optimizer state when the file carries it */
+int   t4h_model_save_state(t4h_model m, const char *fname); /* t4h_model_save + the optimizer state (moment arenas, step count) for resume, appended behind
+                                                             * the reference's closing section: the reference's reader still loads the file */
 int   t4h_model_arena(t4h_model m, float **G, float **DG, int64_t *total);
 /* capture forward+loss+backprop+optimizer into one CUDA graph and replay it (launch-bound regime);
  * optimizer: 0 sgd, 1 sgd+momentum, 2 adam, 3 adamw, -1 none (data parallel: all-reduce DG, then call the optimizer) */

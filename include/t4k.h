@@ -81,6 +81,8 @@ int         t4k_sync(t4k_stream_t stream);             /* cudaStreamSynchronize 
 long        t4k_launch_count(void);                    /* kernels launched by this library so far */
 int         t4k_set_workspace_bank(int bank);          /* 0..7: which set of library workspaces the following calls use — a caller that forks
                                                           * work onto a second stream gives that stream its own bank; returns the previous one */
+int         t4k_set_carveout(int pct);                 /* shared-memory split (percent, -1 = leave it to the driver) the SHORT kernels ask for; default 100 so that they can share
+                                                          * an SM with the big-shared-memory kernels of another stream (or T4K_CARVEOUT); returns the previous setting */
 int         t4k_set_pdl(int on);                       /* programmatic dependent launch for the short kernels (default off, or T4K_PDL=1); returns the previous setting */
 
 /* ---- elementwise: src/t4math.cu:134-234 ------------------------------------------- */
@@ -286,6 +288,9 @@ int t4k_conv_pool_relu_fwd_feed(const uint8_t *u8I, const uint8_t *u8L, int feed
 int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,
                            const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
                            int KS, int S, int P, int train, t4k_stream_t s);
+/* one-shot: the next t4k_conv_pool_relu_bwd[_opt] of this thread records `event` (a cudaEvent_t) between its main kernel and its finish launch —
+ * a place to hang side-stream work that may overlap the short finish launch but must not take SMs from the main kernel */
+int t4k_conv_pool_relu_bwd_mid_event(void *event);
 
 /* ---- optimizers: src/nn/gradient.cu:133-169 + nmath.cu:419-472 ------------------------ */
 int t4k_sgd(float *G, float *DG, float *M, int Nw, float lr, float b, int64_t n, t4k_stream_t s);
@@ -338,12 +343,23 @@ int t4k_allreduce_sum(t4k_comm_t c, float *buf, int64_t n, t4k_stream_t s);
 int t4k_optim_multi_dp(t4k_comm_t c, int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
                        int64_t total, float lr, float b1, float b2, float wd, float *scal, int nscal, int64_t pushed_from,
                        t4k_stream_t s);
+/* the same on the chunks of the arena that START in [from, to) (chunk k starts at k * t4k_comm_chunk_floats(c)): a step may run the exchange +
+ * optimizer of the part whose gradients are final early on a side stream, under the rest of backprop, and only the first layers' chunks at the
+ * end (chunks carry their own epochs; the scalars ride with chunk 0; every rank splits at the same offsets) */
+int t4k_optim_multi_dp_range(t4k_comm_t c, int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
+                             int64_t from, int64_t to, int64_t total, float lr, float b1, float b2, float wd, float *scal, int nscal,
+                             int64_t pushed_from, t4k_stream_t s);
+int64_t t4k_comm_chunk_floats(t4k_comm_t c);
 /* early half of a split exchange: push (and signal) the chunks of DG[0..total) that START at or beyond float `from` —
  * the gradient segments that are already final while backprop still runs (gradients are produced last layer first, and
  * the arena is laid out first layer first).  Returns the float offset of the first pushed chunk (pass it to
  * t4k_optim_multi_dp as `pushed_from`; == total when nothing qualified), negative on error.  Exactly one
  * t4k_optim_multi_dp must follow before the next push; no other exchange on this communicator in between. */
 int64_t t4k_dp_push(t4k_comm_t c, const float *DG, int64_t from, int64_t total, t4k_stream_t s);
+/* the same push with the data moved by the copy engines (peer-to-peer cudaMemcpyAsync) and a one-block kernel raising the flags: no SM is taken
+ * from the backward kernels it overlaps.  `step` = exchanges this communicator has completed so far (selects the slot parity the copies are
+ * addressed with; a captured step is captured once per parity). */
+int64_t t4k_dp_push_dma(t4k_comm_t c, const float *DG, int64_t from, int64_t total, uint32_t step, t4k_stream_t s);
 
 /* ---- RNG: src/util.cu:35-70 via System::rand (src/sys.cpp:77-95) ---------------------- */
 /* d[i] = scale * (bias + x), x ~ U(0,1] or N(0,1).  Counter-based Philox4x32-10 keyed by

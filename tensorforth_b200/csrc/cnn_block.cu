@@ -594,6 +594,11 @@ extern "C" int t4k_conv_pool_relu_fwd_feed(const uint8_t *u8I, const uint8_t *u8
     return t4k_conv_pool_relu_fwd(data, F, B, Icopy, convO, poolO, actO, actF, flatO, N, H1, W1, C1, H0, W0, C0, KS, S, P, s);
 }
 
+// One-shot hook: the NEXT fused conv-block backward of this thread records `event` between its two launches — behind the machine-filling main
+// kernel, in front of the short finish launch.  A caller hangs side-stream work there that must not share the SMs with the main kernel (it
+// fills them in exactly one wave) but may overlap the finish: the data-parallel exchange of the rest of the arena (Model::backprop).
+static thread_local void *g_cpr_mid_event = nullptr;
+extern "C" int t4k_conv_pool_relu_bwd_mid_event(void *event) { g_cpr_mid_event = event; return 0; }
 extern "C" int t4k_conv_pool_relu_bwd(const float *dY, float *actO, const float *actF, float *poolO, float *convO, float *Iio, float *dXbuf,
                                       const float *F, float *dF, float *dB, int N, int H1, int W1, int C1, int H0, int W0, int C0,
                                       int KS, int S, int P, int train, t4k_stream_t s) {
@@ -623,6 +628,7 @@ extern "C" int t4k_conv_pool_relu_bwd_opt(const float *dY, float *actO, const fl
                               launch_std(k_cpr2_bwd<CM_, EX_>, dim3(N), dim3(threads), smem, STRM(s), p); }
     if (CM == 10) { if (ex) CPR2B(10, true) else CPR2B(10, false) } else { if (ex) CPR2B(16, true) else CPR2B(16, false) }
     int rc = check_launch(); if (rc || !train) return rc;
+    if (g_cpr_mid_event) { cudaEventRecord((cudaEvent_t)g_cpr_mid_event, STRM(s)); g_cpr_mid_event = nullptr; }   // t4k_conv_pool_relu_bwd_mid_event
     if (opt) return wgrad_fin_opt_launch(p.part, dF, dB, nF, C0, N, KS, S, opt, STRM(s));
     return wgrad_fin_launch(p.part, dF, dB, nF, C0, N, KS, S, STRM(s));
 }

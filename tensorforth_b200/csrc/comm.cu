@@ -47,6 +47,8 @@ struct t4k_comm {
     uint32_t *err_host, *err_dev;    // the same error word in mapped pinned host memory (host pointer / device alias): polled without a sync
     long long spin_limit;        // clock64 ticks a wait may go without progress
     size_t bytes;
+    cudaStream_t cs[COMM_MAXW];  // t4k_dp_push_dma: one copy stream per destination rank (the peer-to-peer copies of a push run side by side)
+    cudaEvent_t cfork, cdone[COMM_MAXW];
 };
 
 namespace t4k {
@@ -121,13 +123,15 @@ __global__ void __launch_bounds__(T4K_THREADS) k_dp_exchange(const __grid_consta
     if (tid < c.world) {
         const uint32_t *f = flag_of(c, c.rank, tid, b);
         const long long t0 = clock64();
-        while ((int32_t)(ld_acquire_sys(f) - ep) < 0)
+        while ((int32_t)(ld_acquire_sys(f) - ep) < 0) {
+            __nanosleep(32);                    // the waiting launch may share its SMs with the rest of backprop (side stream): leave the issue slots to it
             if (clock64() - t0 > c.spin_limit) {
                 atomicCAS(c.epoch + COMM_MAXB, 0u, 1u + (uint32_t)tid);           // first failure wins, never cleared
                 if (c.err_host) { *reinterpret_cast<volatile uint32_t*>(c.err_host) = 1u + (uint32_t)tid; __threadfence_system(); }
                 s_err = 1u + (uint32_t)tid;
                 break;
             }
+        }
     }
     __syncthreads();
     if (s_err) return;                          // no finish on incomplete data: G / M / V / DG stay as they are, the epoch is not advanced
@@ -175,6 +179,24 @@ __global__ void __launch_bounds__(T4K_THREADS) k_dp_exchange(const __grid_consta
     if (tid == 0) c.epoch[b] = ep;
 }
 
+// signal half of a push whose DATA travelled by copy engine (t4k_dp_push_dma): the chunks' epoch flags, stored to every rank (this one
+// included) once the copies of this stream have completed.  `par` is the slot parity the host addressed the copies with: it must be the
+// parity of the epoch the chunks are about to complete — a disagreement (an exchange the host did not count) raises the sticky error.
+__global__ void __launch_bounds__(T4K_THREADS) k_dp_signal(const __grid_constant__ CommDev c, int b0, int b1, int par) {
+    pdl_wait(); pdl_trigger();
+    if (c.epoch[COMM_MAXB]) return;
+    __threadfence_system();
+    for (int b = b0 + threadIdx.x; b < b1; b += blockDim.x) {
+        const uint32_t ep = c.epoch[b] + 1;
+        if ((int)(ep & 1u) != par) {
+            atomicCAS(c.epoch + COMM_MAXB, 0u, 1u + (uint32_t)c.rank);
+            if (c.err_host) { *reinterpret_cast<volatile uint32_t*>(c.err_host) = 1u + (uint32_t)c.rank; __threadfence_system(); }
+            continue;
+        }
+        for (int k = 1; k <= c.world; k++) *reinterpret_cast<volatile uint32_t*>(flag_of(c, (c.rank + k) % c.world, c.rank, b)) = ep;
+    }
+}
+
 static CommDev devview(const t4k_comm *c) {
     CommDev d;
     for (int i = 0; i < COMM_MAXW; i++) d.peer[i] = c->peer[i];
@@ -190,7 +212,7 @@ static void exchange_carveout() {
     static bool done[16];
     const int dev = cur_device();
     if (dev < 0 || dev >= 16 || done[dev]) return;
-    const void *k[] = {(const void*)k_dp_exchange<-1, true>, (const void*)k_dp_exchange<0, true>, (const void*)k_dp_exchange<0, false>,
+    const void *k[] = {(const void*)k_dp_signal, (const void*)k_dp_exchange<-1, true>, (const void*)k_dp_exchange<0, true>, (const void*)k_dp_exchange<0, false>,
                        (const void*)k_dp_exchange<1, true>, (const void*)k_dp_exchange<2, true>, (const void*)k_dp_exchange<3, true>};
     for (const void *f : k) if (cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) cudaGetLastError();
     done[dev] = true;
@@ -286,6 +308,10 @@ int t4k_comm_destroy(t4k_comm_t c) {
     if (c->base) cudaFree(c->base);
     if (c->epoch) cudaFree(c->epoch);
     if (c->err_host) cudaFreeHost(c->err_host);
+    if (c->cfork) {
+        cudaEventDestroy(c->cfork);
+        for (int p = 0; p < c->world; p++) { if (c->cs[p]) cudaStreamDestroy(c->cs[p]); if (c->cdone[p]) cudaEventDestroy(c->cdone[p]); }
+    }
     cudaGetLastError();
     delete c;
     return 0;
@@ -338,13 +364,73 @@ int64_t t4k_dp_push(t4k_comm_t c, const float *DG, int64_t from, int64_t total, 
     return rc ? (rc > 0 ? -(int64_t)rc - 1000 : rc) : b0 * chf;
 }
 
+int64_t t4k_comm_chunk_floats(t4k_comm_t c) { return c ? (int64_t)c->ch4 * 4 : 0; }
+
+static int optim_dp_launch(t4k_comm_t c, int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
+                           int64_t total, float lr, float b1, float b2, float wd, float *scal, int nscal, int64_t pushed_from, int b0, int grid, t4k_stream_t s);
+
+/* t4k_dp_push with the data moved by the COPY ENGINES (one peer-to-peer cudaMemcpyAsync per rank, own slot included) instead of SM stores: the
+ * push shares the machine with the rest of backprop without taking an SM from it; a one-block kernel then raises the chunks' flags.  Copy nodes
+ * carry fixed addresses, so the caller states the slot parity: `step` = number of exchanges this communicator has COMPLETED over these chunks
+ * (every exchange of a model's arena covers all of them, so the model counts its optimizer calls); a captured step is captured once per parity. */
+int64_t t4k_dp_push_dma(t4k_comm_t c, const float *DG, int64_t from, int64_t total, uint32_t step, t4k_stream_t s) {
+    if (!ready(c) || !DG || from < 0 || total < 0 || total > c->cap || (total & 3) || !aligned16(DG)) return T4K_EINVAL;
+    const int64_t chf = (int64_t)c->ch4 * 4;
+    const int64_t b0 = (from + chf - 1) / chf, nb = (total + chf - 1) / chf;
+    if (b0 >= nb) return total;
+    const int par = (int)((step + 1u) & 1u);
+    const int64_t off = b0 * chf, sstride = c->cap + COMM_NSCAL;
+    // fork: one copy stream per destination, joined back into `s` in front of the signal kernel (under stream capture: parallel copy nodes)
+    if (!c->cfork) {
+        if (cudaEventCreateWithFlags(&c->cfork, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return T4K_ENOMEM; }
+        for (int p = 0; p < c->world; p++)
+            if (cudaStreamCreateWithFlags(&c->cs[p], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->cdone[p], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError(); return T4K_ENOMEM;
+            }
+    }
+    cudaEventRecord(c->cfork, STRM(s));
+    for (int k = 1; k <= c->world; k++) {
+        const int p = (c->rank + k) % c->world;
+        float *dst = reinterpret_cast<float*>(c->peer[p] + COMM_FLAGB) + (int64_t)(par * c->world + c->rank) * sstride + off;
+        cudaStreamWaitEvent(c->cs[p], c->cfork, 0);
+        cudaError_t e = cudaMemcpyAsync(dst, DG + off, (size_t)(total - off) * sizeof(float), cudaMemcpyDeviceToDevice, c->cs[p]);
+        if (e != cudaSuccess) { cudaGetLastError(); return -(int64_t)e - 1000; }
+        cudaEventRecord(c->cdone[p], c->cs[p]);
+        cudaStreamWaitEvent(STRM(s), c->cdone[p], 0);
+    }
+    launch_pdl(k_dp_signal, dim3(1), dim3(T4K_THREADS), 0, STRM(s), devview(c), (int)b0, (int)nb, par);
+    const int rc = check_launch();
+    return rc ? (rc > 0 ? -(int64_t)rc - 1000 : rc) : off;
+}
+
 int t4k_optim_multi_dp(t4k_comm_t c, int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
                        int64_t total, float lr, float b1, float b2, float wd, float *scal, int nscal, int64_t pushed_from, t4k_stream_t s) {
-    if (!ready(c) || !G || !DG || !seg || nseg < 1 || total < 0 || total > c->cap || (total & 3) || !aligned16(DG) || !aligned16(G) ||
-        nscal < 0 || nscal > COMM_NSCAL || (nscal && !scal)) return T4K_EINVAL;
+    if (!ready(c) || total < 0 || total > c->cap) return T4K_EINVAL;
     if (total == 0) return 0;
-    const int grid = (int)(((total / 4) + c->ch4 - 1) / c->ch4);
-    DpOpt o{G, M, V, seg, nseg, true, OptP{lr, b1, b2, wd}, 0, (pushed_from > 0 && pushed_from <= total) ? pushed_from : total + 1};
+    return optim_dp_launch(c, kind, G, DG, M, V, seg, nseg, total, lr, b1, b2, wd, scal, nscal, pushed_from, 0, (int)(((total / 4) + c->ch4 - 1) / c->ch4), s);
+}
+
+/* the same exchange + optimizer on the chunks that START in [from, to) only (chunk = t4k_comm_chunk_floats floats, chunk k starts at k * that).
+ * A step may issue it twice on disjoint ranges — the part of the arena whose gradients are final early on a side stream, under the rest of
+ * backprop, and the first layers' chunks at the end — instead of one launch over everything: chunks carry their own epochs.  The scalars ride
+ * with chunk 0.  Every rank must split at the same offsets.  pushed_from as in t4k_optim_multi_dp (chunks at or beyond it were pushed early). */
+int t4k_optim_multi_dp_range(t4k_comm_t c, int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
+                             int64_t from, int64_t to, int64_t total, float lr, float b1, float b2, float wd, float *scal, int nscal,
+                             int64_t pushed_from, t4k_stream_t s) {
+    if (!ready(c) || total < 0 || total > c->cap || from < 0 || to < from || to > total) return T4K_EINVAL;
+    const int64_t chf = (int64_t)c->ch4 * 4;
+    const int64_t nb = (total + chf - 1) / chf;
+    int64_t c0 = (from + chf - 1) / chf, c1 = (to >= total) ? nb : (to + chf - 1) / chf;
+    if (c1 > nb) c1 = nb;
+    if (c0 >= c1) return 0;
+    return optim_dp_launch(c, kind, G, DG, M, V, seg, nseg, total, lr, b1, b2, wd, c0 == 0 ? scal : nullptr, c0 == 0 ? nscal : 0, pushed_from, (int)c0, (int)(c1 - c0), s);
+}
+
+static int optim_dp_launch(t4k_comm_t c, int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
+                           int64_t total, float lr, float b1, float b2, float wd, float *scal, int nscal, int64_t pushed_from, int b0, int grid, t4k_stream_t s) {
+    if (!G || !DG || !seg || nseg < 1 || (total & 3) || !aligned16(DG) || !aligned16(G) ||
+        nscal < 0 || nscal > COMM_NSCAL || (nscal && !scal)) return T4K_EINVAL;
+    DpOpt o{G, M, V, seg, nseg, true, OptP{lr, b1, b2, wd}, b0, (pushed_from > 0 && pushed_from <= total) ? pushed_from : total + 1};
     CommDev d = devview(c);
     switch (kind) {
     case 0: o.mom = !(fabsf(b1) < DU_EPS); if (o.mom && !M) return T4K_EINVAL;

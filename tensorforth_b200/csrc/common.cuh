@@ -72,14 +72,21 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // the grid starts unbalanced (linear_bwd 24.6 -> 33.9 us), while the short kernels gain 0.3-0.5 us each.  So only the
 // short, latency-bound kernels are launched with it (launch_pdl); machine-filling ones use launch_std (they still execute
 // pdl_trigger, so the short kernel behind them is scheduled early).
+// Shared-memory carve-out.  An SM changes its L1 / shared-memory split only when it is EMPTY: a short kernel that asks for no shared memory
+// gets the smallest split, and while its CTAs are resident the big-shared-memory kernels of another stream (fused conv blocks, layer GEMM) cannot
+// be placed on that SM — the side-stream branches of a step (loss, head gradients, optimizer) would push the critical path's kernels off the SMs
+// they touch.  The short kernels are therefore launched asking for the LARGEST shared-memory split (they stream through L2, L1 size is irrelevant
+// to them); T4K_CARVEOUT=-1 turns the attribute off, 0..100 picks another percentage.
+extern int g_carve;
 template<bool PDL, typename... KA, typename... A>
 static inline void launch_k(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = (PDL && g_pdl) ? 1 : 0;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (PDL && g_pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+    if (g_carve >= 0) { at[na].id = cudaLaunchAttributePreferredSharedMemoryCarveout; at[na].val.sharedMemCarveout = (unsigned)g_carve; na++; }
+    cfg.attrs = at; cfg.numAttrs = na;
     cudaLaunchKernelEx(&cfg, kern, KA(args)...);
 }
 template<typename... KA, typename... A>

@@ -17,14 +17,14 @@ namespace t4 {
 // =============================================================================== Runtime
 // per host thread: the lane the thread works on (every thread starts on lane 0, see Runtime::use_lane)
 static thread_local cudaStream_t g_stream = nullptr, g_stream2 = nullptr;      // library stream + side stream (forked work inside a step)
-static thread_local cudaEvent_t  g_fork = nullptr, g_join = nullptr, g_head = nullptr;
+static thread_local cudaEvent_t  g_fork = nullptr, g_join = nullptr, g_head = nullptr, g_mid = nullptr, g_push = nullptr;
 static bool  g_init = false;
 static int   g_device = 0;
 // Lanes: independent (stream, side stream, events, workspace banks) sets of ONE process.  Lane 0 is the default and the only one a
 // training process uses; the data-parallel tests run `world` ranks of one process on one device, each on its own lane, so that the ranks'
 // kernels can wait on one another exactly as they do across GPUs (Runtime::use_lane).
 #define T4_MAX_LANES 4
-static struct Lane { cudaStream_t s = nullptr, s2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, head = nullptr; } g_lanes[T4_MAX_LANES];
+static struct Lane { cudaStream_t s = nullptr, s2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr, head = nullptr, mid = nullptr, push = nullptr; } g_lanes[T4_MAX_LANES];
 static thread_local int g_lane = 0;
 #define WS_BANK_MAIN (2 * g_lane)
 #define WS_BANK_SIDE (2 * g_lane + 1)
@@ -35,13 +35,14 @@ int Runtime::init(int device) {
     if (cudaSetDevice(device) != cudaSuccess) { error("cudaSetDevice(%d) failed: no CUDA device (there is no CPU fallback)", device); cudaGetLastError(); return T4K_EINVAL; }
     if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) { error("cudaStreamCreate failed"); return T4K_EINVAL; }
     if (cudaStreamCreateWithFlags(&g_stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&g_head, cudaEventDisableTiming) != cudaSuccess) { error("cudaStreamCreate failed"); return T4K_EINVAL; }
+        cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&g_head, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_mid, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&g_push, cudaEventDisableTiming) != cudaSuccess) { error("cudaStreamCreate failed"); return T4K_EINVAL; }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t keep = UINT64_MAX;                     // keep freed blocks cached: alloc/free in `for @ drop next` loops stay cheap
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    g_lanes[0] = Lane{g_stream, g_stream2, g_fork, g_join, g_head};
+    g_lanes[0] = Lane{g_stream, g_stream2, g_fork, g_join, g_head, g_mid, g_push};
     g_device = device;
     g_init = true;
     return 0;
@@ -53,9 +54,12 @@ int Runtime::use_lane(int k) {
     if (!l.s) {
         if (cudaStreamCreateWithFlags(&l.s, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&l.s2, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&l.head, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); error("lane %d: stream creation failed", k); return T4K_EINVAL; }
+            cudaEventCreateWithFlags(&l.head, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&l.mid, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.push, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError(); error("lane %d: stream creation failed", k); return T4K_EINVAL;
+        }
     }
-    g_lane = k; g_stream = l.s; g_stream2 = l.s2; g_fork = l.fork; g_join = l.join; g_head = l.head;
+    g_lane = k; g_stream = l.s; g_stream2 = l.s2; g_fork = l.fork; g_join = l.join; g_head = l.head; g_mid = l.mid; g_push = l.push;
     t4k_set_workspace_bank(WS_BANK_MAIN);
     return 0;
 }
@@ -79,6 +83,13 @@ void Runtime::free(void *p) { if (p) cudaFreeAsync(p, (cudaStream_t)stream()); }
 
 #define ST         (Runtime::stream())
 #define KCHK(call) do { int _rc = (call); if (_rc) Runtime::error("%s -> %d (%s)", #call, _rc, t4k_strerror(_rc)); } while (0)
+// how the early half of the data-parallel exchange travels (T4K_DP_EARLY): "dma" copy engines (default), "sm" the push kernel, "range" the whole
+// exchange + optimizer of the finished part on the side stream (measured slower on 2 GPUs: its waiting CTAs sit on SMs the conv block's backward needs)
+static int dp_early_mode() {
+    static int m = -1;
+    if (m < 0) { const char *e = getenv("T4K_DP_EARLY"); m = !e ? 1 : (!strcmp(e, "sm") ? 0 : (!strcmp(e, "range") ? 2 : 1)); }
+    return m;
+}
 static inline DU SCALAR(DU v) { uint32_t u; memcpy(&u, &v, 4); u &= ~1u; memcpy(&v, &u, 4); return v; }   // src/t4base.h:33 (object tag bit cleared)
 
 // =============================================================================== Tensor
@@ -537,9 +548,24 @@ int Model::_bfused(int i) {                                // i = index of the b
                                         in.N(), in.H(), in.W(), in.C(), co.H(), co.W(), co.C(), f.H(), in.stride[0], in.stride[2], train, &fo, ST);
         if (rc == 0) _oe.first = true;
     }
-    if (rc == T4K_ENOSUP)
+    // data parallel, the block of the FIRST parameter layer, the rest of the arena already pushed to the peers (copy engines, _dp_push): the
+    // exchange + optimizer of that rest runs on the side stream from the moment the block's main kernel is done (it must not take SMs from it:
+    // one exact wave), under the block's finish launch — the end of the step then only exchanges the first chunk
+    const bool dp_rest = _comm && _dpo.on && !_dpo.rest && dp_early_mode() == 1 && _dp_pushed_from > 0 && _dp_pushed_from < (int64_t)_total && train && df.data == _DG;
+    if (rc == T4K_ENOSUP) {
+        if (dp_rest) t4k_conv_pool_relu_bwd_mid_event((void*)g_mid);
         rc = t4k_conv_pool_relu_bwd(dy.data, flat_dst, po.grad[4]->data, po.data, co.data, in.data, dx.data, f.data, df.data, db.data,
                                     in.N(), in.H(), in.W(), in.C(), co.H(), co.W(), co.C(), f.H(), in.stride[0], in.stride[2], train, ST);
+        t4k_conv_pool_relu_bwd_mid_event(nullptr);
+        if (dp_rest && rc == 0) {
+            cudaStreamWaitEvent(g_stream2, g_mid, 0);         // behind the block's main kernel — and behind the push itself (same side stream)
+            const int rr = t4k_optim_multi_dp_range((t4k_comm_t)_comm, _dpo.kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, _dp_pushed_from, (int64_t)_total,
+                                                    (int64_t)_total, _dpo.lr, _dpo.b1, _dpo.b2, _dpo.wd, nullptr, 0, _dp_pushed_from, (t4k_stream_t)g_stream2);
+            cudaEventRecord(g_join, g_stream2);
+            _side_join = true;
+            if (rr == 0) _dpo.rest = true; else Runtime::error("t4k_optim_multi_dp_range -> %d", rr);
+        }
+    }
     if (rc == T4K_ENOSUP) return 0;
     KCHK(rc);
     _skip_flat_copy = false;
@@ -661,7 +687,13 @@ Model &Model::backprop(Tensor &tgt) {
         else _bstep(*_layers[i], *_layers[i + 1], j == 0);
         i--;
     }
-    if (_side_join) { cudaStreamWaitEvent((cudaStream_t)ST, g_join, 0); _side_join = false; }      // side-stream branch of this backprop
+    if (_side_join) {                                                                               // side-stream branch of this backprop
+        if (_comm && _dpo.rest && dp_early_mode() == 1)
+            // data parallel: the exchange + optimizer of the rest of the arena is still running there and nothing at the end of the step reads what
+            // it writes — the optimizer call waits for the side stream's EARLIER work only (loss for the scalars), the step's end joins the rest
+            cudaStreamWaitEvent((cudaStream_t)ST, g_push, 0);
+        else { cudaStreamWaitEvent((cudaStream_t)ST, g_join, 0); _side_join = false; }
+    }
     return *this;
 }
 void Model::_opt_push() {
@@ -675,10 +707,33 @@ void Model::_opt_push() {
     _side_join = true; _oe.rest = true;
 }
 void Model::_dp_push() {
-    // Split exchange (comm.cu MODE -1): fork a side stream off the library stream, push the finished part of the gradient
-    // arena to the peers while the remaining backward kernels run; Model::_gradient joins it in front of the optimizer.
+    // Split exchange: fork a side stream off the library stream once every gradient but the first parameter layer's is final.
     cudaStream_t st = (cudaStream_t)ST;
     cudaEventRecord(g_fork, st); cudaStreamWaitEvent(g_stream2, g_fork, 0);
+    const int64_t chf = t4k_comm_chunk_floats((t4k_comm_t)_comm);
+    const int64_t split = chf > 0 ? ((_first_end + chf - 1) / chf) * chf : 0;          // first chunk boundary at or past the first layer's segments
+    if (dp_early_mode() == 2 && _dpo.on && split > 0 && split < (int64_t)_total) {
+        // (a) the whole exchange + optimizer of the chunks past the first layer runs THERE, under the first layer's backward (the peers reach
+        // this point at the same place of their step): what stays on the critical path at the end of the step is the first chunk's exchange alone
+        const int rc = t4k_optim_multi_dp_range((t4k_comm_t)_comm, _dpo.kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, split, (int64_t)_total, (int64_t)_total,
+                                                _dpo.lr, _dpo.b1, _dpo.b2, _dpo.wd, nullptr, 0, 0, (t4k_stream_t)g_stream2);
+        cudaEventRecord(g_join, g_stream2);
+        _side_join = true;
+        if (rc == 0) { _dp_pushed_from = split; _dpo.rest = true; return; }
+        Runtime::error("t4k_optim_multi_dp_range -> %d", rc);
+    }
+    // (b) push the finished part of the gradient arena to the peers while the remaining backward kernels run — by copy engine (no SM taken from
+    // the conv block's backward, which fills the machine in exactly one wave) or, T4K_DP_EARLY=sm, by the MODE -1 kernel of comm.cu;
+    // Model::_gradient joins it in front of the optimizer.
+    if (dp_early_mode() == 1) {
+        const int64_t r = t4k_dp_push_dma((t4k_comm_t)_comm, _DG, _first_end, (int64_t)_total, _dp_step, (t4k_stream_t)g_stream2);
+        cudaEventRecord(g_join, g_stream2);
+        cudaEventRecord(g_push, g_stream2);                 // everything the side stream holds up to here (loss, head gradients, the push)
+        _dp_join = true;
+        if (r < 0) { Runtime::error("t4k_dp_push_dma -> %ld", (long)r); _dp_pushed_from = (int64_t)_total; }
+        else _dp_pushed_from = r;
+        return;
+    }
     const int64_t r = t4k_dp_push((t4k_comm_t)_comm, _DG, _first_end, (int64_t)_total, (t4k_stream_t)g_stream2);
     cudaEventRecord(g_join, g_stream2);
     _dp_join = true;
@@ -944,11 +999,18 @@ Model &Model::_gradient(t4_optimizer op, DU lr, DU b1, DU b2, DU wd) {     // gr
     if (_iter++ == 0 && epoch == 0 && !_G) grad_alloc(op);
     if (!train || !_G) return *this;
     const int kind = (op == OPTI_SGD || op == OPTI_SGDM) ? 0 : (op == OPTI_ADAM ? 1 : 2);
-    if (_comm) {
+    if (_comm && _dpo.rest) {
+        // the side stream exchanged and stepped everything from `_dp_pushed_from` on (Model::_dp_push): the first chunks are what is left
+        _dp_join = false;                                                   // ordered by backprop's wait on the push event; the rest exchange is joined at the end of the step
+        KCHK(t4k_optim_multi_dp_range((t4k_comm_t)_comm, kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, 0, _dp_pushed_from, (int64_t)_total, lr, b1, b2, wd,
+                                      _dp_scal, _dp_nscal, _dp_pushed_from, ST));
+        _dp_pushed_from = -1; _dpo = DpOptEarly(); _dp_step++;
+    }
+    else if (_comm) {
         if (_dp_join) { cudaStreamWaitEvent((cudaStream_t)ST, g_join, 0); _dp_join = false; }     // the early push of this step (side stream)
         KCHK(t4k_optim_multi_dp((t4k_comm_t)_comm, kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, (int64_t)_total, lr, b1, b2, wd,
                                 _dp_scal, _dp_nscal, _dp_pushed_from > 0 ? _dp_pushed_from : (int64_t)_total, ST));
-        _dp_pushed_from = -1;
+        _dp_pushed_from = -1; _dp_step++;
     }
     else if (_oe.on && _oe.rest) {                                          // the side stream stepped [first_end, total) during backprop (_opt_push)
         if (!_oe.first) KCHK(t4k_optim_multi_range(kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, 0, _first_end, lr, b1, b2, wd, ST));
@@ -984,7 +1046,13 @@ static std::string layer_parm(Tensor &in, Tensor &out) {                  // AIO
     }
     return o.str();
 }
-int Model::save(const char *fname) {                                       // AIO::nsave + _nsave_model + _nsave_param
+// Optimizer state for resume (the reference's file has none: a reloaded model restarts Adam from m = v = 0).  It FOLLOWS the
+// reference's closing "---" line, where the reference's reader has already stopped (AIO::_nload_param reads one section per parametrised layer),
+// so a file with state still loads in the reference:
+//   "\ optimizer state iter=<calls> epoch=<n> floats=<arena length>\n--- m.arena\n" <raw FP32> "\n--- v.arena\n" <raw FP32> "\n---\n"
+// m / v are the flat moment arenas (grad_alloc: every parameter segment at its offset, 4-float aligned).
+static const char *OPT_TAG = "\\ optimizer state";
+int Model::save(const char *fname, bool opt_state) {                       // AIO::nsave + _nsave_model + _nsave_param
     std::ofstream fs(fname, std::ios_base::binary);
     if (!fs.is_open()) { Runtime::error("} => failed to open for output\n"); return 1; }
     fs << "\\ tensorForth v4.0 model\n";
@@ -1005,6 +1073,15 @@ int Model::save(const char *fname) {                                       // AI
         }
     }
     fs << "\n---" << std::endl;
+    if (opt_state && _G && _M && _V) {
+        h.resize(_total);
+        fs << OPT_TAG << " iter=" << _iter << " epoch=" << epoch << " floats=" << _total << "\n--- m.arena\n";
+        Runtime::sync();
+        cudaMemcpy(h.data(), _M, _total * sizeof(DU), cudaMemcpyDeviceToHost); fs.write((const char*)h.data(), _total * sizeof(DU));
+        fs << "\n--- v.arena\n";
+        cudaMemcpy(h.data(), _V, _total * sizeof(DU), cudaMemcpyDeviceToHost); fs.write((const char*)h.data(), _total * sizeof(DU));
+        fs << "\n---" << std::endl;
+    }
     return fs.good() ? 0 : 1;
 }
 int Model::load(const char *fname) {                                       // AIO::nload (parameter path) + _nload_param
@@ -1031,7 +1108,27 @@ int Model::load(const char *fname) {                                       // AI
         default: break;
         }
     }
-    return err;
+    if (err) return err;
+    // optional optimizer state behind the reference's sections (see save)
+    while (std::getline(fs, line)) {
+        if (line.compare(0, strlen(OPT_TAG), OPT_TAG) != 0) continue;
+        long it = 0, ep = 0; unsigned long long n = 0;
+        if (sscanf(line.c_str() + strlen(OPT_TAG), " iter=%ld epoch=%ld floats=%llu", &it, &ep, &n) != 3) { Runtime::error(" model format error (optimizer state)"); return 1; }
+        if (!_G) grad_alloc(OPTI_ADAM);
+        if (n != _total) { Runtime::error(" optimizer state of %llu floats does not fit this model (%llu)", n, (unsigned long long)_total); return 1; }
+        h.resize(_total);
+        for (DU *dst : {_M, _V}) {
+            if (!std::getline(fs, line) || line.compare(0, 3, "---") != 0) { Runtime::error(" model format error (optimizer state)"); return 1; }
+            fs.read((char*)h.data(), _total * sizeof(DU));
+            if ((U64)fs.gcount() != _total * sizeof(DU)) { Runtime::error(" model format error (optimizer state)"); return 1; }
+            cudaMemcpy(dst, h.data(), _total * sizeof(DU), cudaMemcpyHostToDevice);
+            std::getline(fs, line);                                        // the newline in front of the next "---"
+        }
+        _iter = (int)it; epoch = (int)ep;
+        _drop_graphs();                                                    // captured steps baked the first-call SGD momentum / arena pointers of the old state
+        break;
+    }
+    return 0;
 }
 int Model::arena(DU **G, DU **DG, int64_t *total) {
     if (!_G) grad_alloc(OPTI_ADAM);
@@ -1061,7 +1158,7 @@ int Model::dp_attach(void *comm, DU *scal, int nscal) {
         Runtime::error("nn#dp_attach: the model has batchnorm layers; give it a statistics communicator first (Model::dp_shard)\n");
         return T4K_ENOSUP;
     }
-    _comm = comm; _dp_scal = scal; _dp_nscal = comm ? nscal : 0;
+    _comm = comm; _dp_scal = scal; _dp_nscal = comm ? nscal : 0; _dp_step = 0;     // a fresh communicator: no exchange completed yet
     Runtime::sync(); _drop_graphs();                          // the captured optimizer node changes
     return 0;
 }
@@ -1104,6 +1201,13 @@ int Model::_step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4
             cudaEventRecord(g_join, g_stream2);
         }
         _dp_early = _comm && (int)op >= 0 && train && _G;  // forward -> backprop -> optimizer is one unit here: the exchange may start early
+        _dpo = DpOptEarly();
+        if (_dp_early && _iter > 0 && fuse) {              // ... and so may the optimizer of everything but the first chunks (see _dp_push); not on the first call (SGD forces its momentum to 0 there)
+            _dpo.on = true; _dpo.lr = lr; _dpo.b2 = b2; _dpo.wd = 0.0f;
+            if (op == OPTI_SGD || op == OPTI_SGDM) { _dpo.kind = 0; _dpo.b1 = fabsf(b1) < DU_EPS_H ? 0.0f : b1; _dpo.b2 = 0.0f; }
+            else if (op == OPTI_ADAM) { _dpo.kind = 1; _dpo.b1 = b1; }
+            else { _dpo.kind = 2; _dpo.b1 = b1; _dpo.wd = wd; }
+        }
         _oe = OptEarly();
         if (!_comm && (int)op >= 0 && train && _G && _iter > 0 && fuse) {     // single GPU: the optimizer may start early too (see OptEarly)
             _oe.on = true; _oe.lr = lr; _oe.b2 = b2; _oe.wd = 0.0f;
@@ -1130,7 +1234,8 @@ int Model::_step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4
             if (nf > 0) _hscratch = (DU*)Runtime::alloc((size_t)nf * sizeof(DU) + 64);
         }
     }
-    U64 key[12] = {0}; float f4[4] = {lr, b1, b2, wd};
+    U64 key[13] = {0}; float f4[4] = {lr, b1, b2, wd};
+    key[12] = _comm ? (U64)(_dp_step & 1u) : 0;           // data parallel: the early push's copy nodes address the exchange slots of one parity (t4k_dp_push_dma)
     key[0] = (U64)input.data; key[1] = (U64)tgt.data; key[2] = (U64)lop; key[3] = (U64)loss_dev; key[4] = (U64)op;
     memcpy(&key[5], f4, 16); key[7] = (U64)train; key[8] = (U64)x.simg; key[9] = (U64)x.slab; key[10] = (U64)x.n; key[11] = (U64)x.loss_pin;
     // SGD's first call forces momentum 0 (host state) and the first optimizer call builds the arenas: run those eagerly
@@ -1146,19 +1251,19 @@ int Model::_step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4
         if (slot->exec) { cudaGraphExecDestroy((cudaGraphExec_t)slot->exec); slot->exec = nullptr; }
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); run(); return 0; }
-        const int it = _iter;
+        const int it = _iter; const uint32_t ds = _dp_step;
         run();
         cudaError_t e = cudaStreamEndCapture(st, &graph);
-        if (e != cudaSuccess || !graph) { cudaGetLastError(); _iter = it; Runtime::error("graph capture failed: %s", cudaGetErrorString(e)); run(); return 0; }
+        if (e != cudaSuccess || !graph) { cudaGetLastError(); _iter = it; _dp_step = ds; Runtime::error("graph capture failed: %s", cudaGetErrorString(e)); run(); return 0; }
         cudaGraphExec_t ex = nullptr;
         e = cudaGraphInstantiate(&ex, graph, 0);
         cudaGraphDestroy(graph);
-        if (e != cudaSuccess) { cudaGetLastError(); _iter = it; run(); return 0; }
+        if (e != cudaSuccess) { cudaGetLastError(); _iter = it; _dp_step = ds; run(); return 0; }
         slot->exec = ex; memcpy(slot->key, key, sizeof(key));
-        _iter = it;                                   // the captured run did not execute; the launch below is the step
+        _iter = it; _dp_step = ds;                    // the captured run did not execute; the launch below is the step
     }
     slot->used = ++_graph_clock;
-    if ((int)op >= 0) _iter++;
+    if ((int)op >= 0) { _iter++; if (_comm) _dp_step++; }
     return (int)cudaGraphLaunch((cudaGraphExec_t)slot->exec, st);
 }
 
@@ -1318,6 +1423,7 @@ void *t4h_capture_end(void) {
 int   t4h_graph_launch(void *g) { return g ? (int)cudaGraphLaunch((cudaGraphExec_t)g, (cudaStream_t)Runtime::stream()) : T4K_EINVAL; }
 void  t4h_graph_free(void *g) { if (g) { Runtime::sync(); cudaGraphExecDestroy((cudaGraphExec_t)g); } }
 int   t4h_model_save(t4h_model m, const char *fname) { return MM(m).save(fname); }
+int   t4h_model_save_state(t4h_model m, const char *fname) { return MM(m).save(fname, true); }
 int   t4h_model_load(t4h_model m, const char *fname) { return MM(m).load(fname); }
 int   t4h_model_arena(t4h_model m, float **G, float **DG, int64_t *total) { return MM(m).arena(G, DG, total); }
 int   t4h_model_dp_attach(t4h_model m, void *comm, float *scal, int nscal) { return MM(m).dp_attach(comm, scal, nscal); }

@@ -156,7 +156,7 @@ class Model {
     void   *_seg_dev = nullptr; int _nseg = 0;
     t4_optimizer _arena_opt = OPTI_SGD;
     // captured train step
-    struct StepGraph { void *exec = nullptr; U64 key[12] = {0}; U64 used = 0; } _graphs[3];   // small LRU cache (dataset feeding alternates two staging buffers)
+    struct StepGraph { void *exec = nullptr; U64 key[13] = {0}; U64 used = 0; } _graphs[6];   // small LRU cache (dataset feeding alternates two staging buffers)
     U64     _graph_clock = 0;
     struct StepExtra { const uint8_t *simg = nullptr, *slab = nullptr; int n = 0; Dataset *ds = nullptr; DU *loss_pin = nullptr; };   // work folded into the captured step
     int     _step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4_optimizer op, DU lr, DU b1, DU b2, DU wd, const StepExtra &x);
@@ -166,6 +166,8 @@ class Model {
     int     _second_layer = 0; int64_t _first_end = 0;                    // arena layout: end of the first parameter layer's segments, index of the next parameter layer
     bool    _dp_early = false, _dp_join = false; int64_t _dp_pushed_from = -1;   // split exchange inside step_graph (early push on the side stream)
     void    _dp_push();
+    uint32_t _dp_step = 0;             // exchanges issued on _comm so far (= the epoch of every chunk of the arena: selects the slot parity of a DMA push)
+    struct DpOptEarly { bool on = false, rest = false; int kind = 0; DU lr = 0, b1 = 0, b2 = 0, wd = 0; } _dpo;   // data parallel, inside step_graph: optimizer arguments for the early exchange
     DU     *_pdup = nullptr; bool _want_pdup = false, _pdup_valid = false;   // step_graph: duplicate of the softmax output for the side-stream loss
     const StepExtra *_feed = nullptr; DU *_feed_hot = nullptr;   // step_graph: staged U8 batch still to be loaded (folded into the first fused block when there is one)
     void    _feed_fallback();
@@ -225,7 +227,7 @@ public:
     // 7-character layer name exactly as AIO::_nsave_model writes them), a blank line, then per parametrised layer
     // `\n--- w.<name>\n` + raw FP32 of the weight (and `b.` bias; batchnorm: w only), closed by `\n---\n`.
     // load() reads the parameter sections into an already built model of the same architecture (AIO::nload, numel > 2 path).
-    int    save(const char *fname);
+    int    save(const char *fname, bool opt_state = false);   ///< opt_state: + the optimizer's moment arenas and step count behind the reference's sections (resume)
     int    load(const char *fname);
     static const char *nname(int fn);                        ///< model.cpp:17-21 (LAYER_OP, ntypes.h:47-51)
     int    arena(DU **G, DU **DG, int64_t *total);

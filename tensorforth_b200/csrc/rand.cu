@@ -83,6 +83,9 @@ extern "C" int t4k_rand_tick(t4k_stream_t s) {
     uint64_t *e = epoch_ptr();
     if (!e) return T4K_ENOMEM;
     k_rand_tick<<<1, 32, 0, STRM(s)>>>(e);
+    // draws behind a tick are numbered from 0 again: a step's masks depend on (seed, step count, position inside the step) only — not on how many
+    // draws the process made before, nor on whether an earlier step ran eagerly or as a captured graph (whose host-side offsets never advance)
+    g_offset = 0;
     return check_launch();
 }
 /* Draw this rank's shard of a batch-major tensor exactly as ONE device holding the whole batch would draw it (per-rank Philox

@@ -8,6 +8,7 @@
 namespace t4k {
 
 long g_launches = 0;
+int  g_carve = []{ const char *e = getenv("T4K_CARVEOUT"); const int v = e ? atoi(e) : 100; return v > 100 ? 100 : v; }();   // common.cuh: shared-memory split asked for by the short kernels
 int  g_pdl = []{ const char *e = getenv("T4K_PDL"); return (e && e[0] == '1') ? 1 : 0; }();   // opt-in: no net gain measured on the MNIST step (common.cuh)
 
 int cur_device() {
@@ -115,6 +116,8 @@ int t4k_sync(t4k_stream_t s) { return (int)cudaStreamSynchronize((cudaStream_t)s
 long t4k_launch_count(void) { return t4k::g_launches; }
 
 int t4k_set_workspace_bank(int bank) { int was = t4k::g_ws_bank; t4k::g_ws_bank = bank & 7; return was; }
+
+int t4k_set_carveout(int pct) { int was = t4k::g_carve; t4k::g_carve = pct > 100 ? 100 : pct; return was; }
 
 int t4k_set_pdl(int on) { int was = t4k::g_pdl; t4k::g_pdl = on ? 1 : 0; return was; }
 

@@ -46,6 +46,7 @@ PROTOTYPES = {
     "t4h_use_lane": (_i, [_i]),
     "t4h_side_stream": (_p, []),
     "t4h_capture_begin": (_i, []), "t4h_capture_end": (_p, []), "t4h_graph_launch": (_i, [_p]), "t4h_graph_free": (None, [_p]),
+    "t4h_model_save_state": (_i, [_p, C.c_char_p]),
     "t4h_model_save": (_i, [_p, C.c_char_p]), "t4h_model_load": (_i, [_p, C.c_char_p]),
     "t4h_dataset_create": (_p, [_i, _i, _i, _i]), "t4h_dataset_destroy": (None, [_p]), "t4h_dataset_normalize": (None, [_p, _f, _f]),
     "t4h_dataset_stage": (_i, [_p, _p, _p, _i]), "t4h_dataset_commit": (_i, [_p]), "t4h_dataset_tensor": (_p, [_p]),
@@ -297,8 +298,8 @@ class Model:
         _k.check(load().t4h_model_arena(self.h, C.byref(g), C.byref(dg), C.byref(n)), "arena")
         return g.value, dg.value, n.value
 
-    def save(self, fname):              # word `save` ( N adr len -- N ): the reference's model file (src/io/aio_model.cpp)
-        if load().t4h_model_save(self.h, str(fname).encode()): raise T4KError(_err())
+    def save(self, fname, opt_state=False):              # word `save` ( N adr len -- N ): the reference's model file (src/io/aio_model.cpp)
+        if (load().t4h_model_save_state if opt_state else load().t4h_model_save)(self.h, str(fname).encode()): raise T4KError(_err())
         return self
 
     def load(self, fname):              # word `load`: parameters into an already built model

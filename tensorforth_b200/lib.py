@@ -63,6 +63,7 @@ PROTOTYPES = {
     "t4k_linear_bwd_ex": (_i, [_p] * 6 + [_i] * 5 + [_p]),
     "t4k_dconv2d_fwd": (_i, [_p] * 4 + [_i] * 10 + [_p]),
     "t4k_dconv2d_bwd": (_i, [_p] * 6 + [_i] * 11 + [_p]),
+    "t4k_set_carveout": (_i, [_i]),
     "t4k_rand_sharded": (_i, [_p, _l, _l, _l, _i, _f, _f, _p]),
     "t4k_batchnorm_fwd_dp": (_i, [_p] * 7 + [_i] * 4 + [_p]),
     "t4k_batchnorm_bwd_dp": (_i, [_p] * 8 + [_i] * 5 + [_p]),
@@ -101,6 +102,10 @@ PROTOTYPES = {
     "t4k_shard_info": (_i, [_l, _i, _i, C.POINTER(_l), C.POINTER(_l)]),
     "t4k_allreduce_sum": (_i, [_p, _p, _l, _p]),
     "t4k_optim_multi_dp": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _l, _f, _f, _f, _f, _p, _i, _l, _p]),
+    "t4k_optim_multi_dp_range": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _l, _l, _l, _f, _f, _f, _f, _p, _i, _l, _p]),
+    "t4k_conv_pool_relu_bwd_mid_event": (_i, [_p]),
+    "t4k_comm_chunk_floats": (_l, [_p]),
+    "t4k_dp_push_dma": (_l, [_p, _p, _l, _l, C.c_uint32, _p]),
     "t4k_dp_push": (_l, [_p, _p, _l, _l, _p]),
     "t4k_rand_seed": (_i, [_u64]),
     "t4k_rand": (_i, [_p, _l, _i, _f, _f, _p]),

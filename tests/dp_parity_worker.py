@@ -19,6 +19,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tensorforth_b200 import dp, host as th, lib as t4      # noqa: E402
 
 NG, K, LR = int(os.environ.get("DP_BATCH", "512")), int(os.environ.get("DP_STEPS", "12")), float(os.environ.get("DP_LR", "1e-3"))
+KIND = os.environ.get("DP_MODEL", "mnist")      # "bn": conv -> batchnorm -> relu -> dropout -> avgpool -> flatten -> linear -> softmax: batch statistics of
+                                                # the GLOBAL batch and the global batch's dropout masks (per-rank Philox offsets) are what make it follow rank 0's run
 
 
 def main():
@@ -29,14 +31,17 @@ def main():
     torch.cuda.set_stream(torch.cuda.ExternalStream(th.stream(), device=local))
     dev = torch.device("cuda", local)
     rng = np.random.default_rng(11)
-    Xg = (rng.random((NG, 28, 28, 1), dtype=np.float32) * 2 - 1).astype(np.float32)
+    shape = (NG, 28, 28, 1) if KIND == "mnist" else (NG, 8, 8, 3)
+    Xg = (rng.random(shape, dtype=np.float32) * 2 - 1).astype(np.float32)
     Yg = np.eye(10, dtype=np.float32)[rng.integers(0, 10, NG)]
     lo, hi = dp.shard_bounds(NG, world, rank)
     assert (hi - lo) * world == NG, "equal shards expected"
 
     def build(n):
         L.t4k_rand_seed(1234)                                   # identical initial weights on every rank / arm
-        return th.mnist_cnn(n)
+        if KIND == "mnist":
+            return th.mnist_cnn(n)
+        return th.Model(n, 8, 8, 3).conv2d(0.5, 6).batchnorm().relu().dropout(0.3).avgpool(2).flatten().linear(10).softmax()
 
     def run(arm):
         n = NG if arm == "single" else hi - lo

@@ -122,7 +122,7 @@ def test_allreduce_sum_mixed_lengths(world):
     ring.close()
 
 
-@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("split", [False, True, "range"])
 @pytest.mark.parametrize("world,big", [(4, 48000), (2, 196000)])
 @pytest.mark.parametrize("kind", [0, 1, 2])
 def test_fused_exchange_optimizer_equals_optimizer_on_summed_gradient(kind, world, big, split):
@@ -149,11 +149,25 @@ def test_fused_exchange_optimizer_equals_optimizer_on_summed_gradient(kind, worl
         ok(L.t4k_optim_multi(kind, ptr(Gr), ptr(DGr), ptr(Mr), ptr(Vr), ptr(seg), len(segs), total, lr, b1, b2, wd, st0), "optim_multi")
         torch.cuda.synchronize()
         pushed = [0] * world
-        if split:
+        if split == "range":
+            # the exchange + optimizer in two launches on disjoint chunk ranges (what Model::step_graph does: everything past the first layer's
+            # chunk early on a side stream, the first chunk — and the scalars — at the end)
+            chf = L.t4k_comm_chunk_floats(ring.h[0])
+            cut = ((104 + chf - 1) // chf) * chf
+            assert 0 < cut < total
+            for r in range(world):
+                ok(L.t4k_optim_multi_dp_range(ring.h[r], kind, ptr(G[r]), ptr(DG[r]), ptr(M[r]), ptr(V[r]), ptr(seg), len(segs), cut, total, total,
+                                              lr, b1, b2, wd, None, 0, 0, ring.st(r)), "range (rest)")
+            for r in range(world):
+                ok(L.t4k_optim_multi_dp_range(ring.h[r], kind, ptr(G[r]), ptr(DG[r]), ptr(M[r]), ptr(V[r]), ptr(seg), len(segs), 0, cut, total,
+                                              lr, b1, b2, wd, ptr(scal[r]), 3, 0, ring.st(r)), "range (first)")
+        elif split:
             for r in range(world):
                 pushed[r] = L.t4k_dp_push(ring.h[r], ptr(DG[r]), 104, total, ring.st(r))
                 assert 104 <= pushed[r] < total, pushed[r]
         for r in range(world):
+            if split == "range":
+                break
             ok(L.t4k_optim_multi_dp(ring.h[r], kind, ptr(G[r]), ptr(DG[r]), ptr(M[r]), ptr(V[r]), ptr(seg), len(segs), total,
                                     lr, b1, b2, wd, ptr(scal[r]), 3, pushed[r], ring.st(r)), "optim_multi_dp")
         ring.sync()

@@ -13,14 +13,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-def test_two_gpu_step_follows_single_gpu_trajectory():
+@pytest.mark.parametrize("kind,batch", [("mnist", 512), ("bn", 64)])
+def test_two_gpu_step_follows_single_gpu_trajectory(kind, batch):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs 2 GPUs")
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "tests", "dp_parity_worker.py")]
-    env = dict(os.environ, DP_LR="1e-4")
+    env = dict(os.environ, DP_LR="1e-4", DP_MODEL=kind, DP_BATCH=str(batch))
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     line = [l for l in p.stdout.splitlines() if l.startswith("DP_PARITY ")]
     assert line, p.stdout[-2000:] + p.stderr[-3000:]

@@ -696,3 +696,35 @@ def test_reference_program_golden_mlp_bn():
         m.forward(X); losses.append(m.loss(t4.LOSS_MSE, T))
     _close_printed(losses, _golden_numbers("mlp_bn_parity", "loss"), "loss trajectory")
     _close_printed([np.sqrt(float((m.w(1).numpy().astype(np.float64) ** 2).sum()))], _golden_numbers("mlp_bn_parity", "w1 norm"), "w1 norm")
+
+
+def test_model_file_carries_optimizer_state_for_resume(tmp_path):
+    """save(opt_state=True) appends Adam's moment arenas and the step count behind the reference's sections; a fresh model that
+    loads the file continues the run bit for bit, one that loads the parameters only (the reference's file) restarts from m = v = 0 and drifts;
+    the parameter part of both files is the same bytes."""
+    N = 16
+    rng = np.random.default_rng(12)
+    xs = [(rng.random((N, 28, 28, 1), dtype=np.float32) * 2 - 1).astype(np.float32) for _ in range(5)]
+    ys = [orc.onehot(rng.integers(0, 10, N), 10) for _ in range(5)]
+
+    def step(m, k):
+        m.forward(th.Tensor.from_numpy(xs[k])); m.backprop(th.Tensor.tensor(N, 1, 10, 1, ys[k])); m.adam(1e-3)
+    t4.load().t4k_rand_seed(5)
+    a = th.mnist_cnn(N)
+    for k in range(3):
+        step(a, k)
+    th.sync()
+    plain, full = str(tmp_path / "plain.t4"), str(tmp_path / "state.t4")
+    a.save(plain); a.save(full, opt_state=True)
+    dp, df = open(plain, "rb").read(), open(full, "rb").read()
+    assert df.startswith(dp) and b"\n\\ optimizer state iter=3 epoch=0 floats=" in df[len(dp) - 1:] and df.endswith(b"\n---\n")
+    b, c = th.mnist_cnn(N).load(full), th.mnist_cnn(N).load(plain)
+    for k in (3, 4):
+        step(a, k); step(b, k); step(c, k)
+    th.sync()
+    for i in (0, 4, 6):
+        assert np.array_equal(b.w(i).numpy(), a.w(i).numpy()) and np.array_equal(b.b(i).numpy(), a.b(i).numpy()), "resumed run diverged at layer %d" % i
+    assert not np.array_equal(c.w(4).numpy(), a.w(4).numpy())              # without the moments the continuation is another trajectory
+    # a state that does not fit the model is refused
+    with pytest.raises(Exception):
+        th.Model(N, 28, 28, 1).flatten().linear(10).softmax().load(full)
