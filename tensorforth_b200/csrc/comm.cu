@@ -380,23 +380,26 @@ int64_t t4k_dp_push_dma(t4k_comm_t c, const float *DG, int64_t from, int64_t tot
     if (b0 >= nb) return total;
     const int par = (int)((step + 1u) & 1u);
     const int64_t off = b0 * chf, sstride = c->cap + COMM_NSCAL;
-    // fork: one copy stream per destination, joined back into `s` in front of the signal kernel (under stream capture: parallel copy nodes)
-    if (!c->cfork) {
+    // more than one remote destination: one copy stream per destination, forked off `s` and joined back in front of the signal kernel (under
+    // stream capture: parallel copy nodes) — seven 0.8 MB copies in a row on ONE stream outlast the backward kernels they hide under
+    // (8 GPUs: 110.7 us per step against 96.1 with the push kernel)
+    const bool fan = c->world > 2;
+    if (fan && !c->cfork) {
         if (cudaEventCreateWithFlags(&c->cfork, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return T4K_ENOMEM; }
         for (int p = 0; p < c->world; p++)
             if (cudaStreamCreateWithFlags(&c->cs[p], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->cdone[p], cudaEventDisableTiming) != cudaSuccess) {
                 cudaGetLastError(); return T4K_ENOMEM;
             }
     }
-    cudaEventRecord(c->cfork, STRM(s));
+    if (fan) cudaEventRecord(c->cfork, STRM(s));
     for (int k = 1; k <= c->world; k++) {
         const int p = (c->rank + k) % c->world;
         float *dst = reinterpret_cast<float*>(c->peer[p] + COMM_FLAGB) + (int64_t)(par * c->world + c->rank) * sstride + off;
-        cudaStreamWaitEvent(c->cs[p], c->cfork, 0);
-        cudaError_t e = cudaMemcpyAsync(dst, DG + off, (size_t)(total - off) * sizeof(float), cudaMemcpyDeviceToDevice, c->cs[p]);
+        cudaStream_t cst = fan ? c->cs[p] : STRM(s);
+        if (fan) cudaStreamWaitEvent(cst, c->cfork, 0);
+        cudaError_t e = cudaMemcpyAsync(dst, DG + off, (size_t)(total - off) * sizeof(float), cudaMemcpyDeviceToDevice, cst);
         if (e != cudaSuccess) { cudaGetLastError(); return -(int64_t)e - 1000; }
-        cudaEventRecord(c->cdone[p], c->cs[p]);
-        cudaStreamWaitEvent(STRM(s), c->cdone[p], 0);
+        if (fan) { cudaEventRecord(c->cdone[p], cst); cudaStreamWaitEvent(STRM(s), c->cdone[p], 0); }
     }
     launch_pdl(k_dp_signal, dim3(1), dim3(T4K_THREADS), 0, STRM(s), devview(c), (int)b0, (int)nb, par);
     const int rc = check_launch();
