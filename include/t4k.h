@@ -370,6 +370,9 @@ int t4k_rand(float *d, int64_t n, int opt, float bias, float scale, t4k_stream_t
 /* this rank's shard [before, before + n) of a batch-major tensor of global_n elements, drawn with the counters a single device holding the
  * whole tensor would use (per-rank Philox offset = global element index); every rank advances the stream by global_n */
 int t4k_rand_sharded(float *d, int64_t n, int64_t before, int64_t global_n, int opt, float bias, float scale, t4k_stream_t s);
+/* dropout forward in ONE launch (Model::_fstep L_DROPOUT, src/nn/forward.cu:98-102 + k_activate, nmath.cu:66-68): draws the mask t4k_rand_sharded(F, n,
+ * before, global_n, UNIFORM) would draw (before = 0, global_n = n on one device), F <- (u > rate) ? 1 : 0, O <- I where kept else 0 (no rescaling) */
+int t4k_dropout_fwd(const float *I, float *O, float *F, float rate, int64_t n, int64_t before, int64_t global_n, t4k_stream_t s);
 int t4k_rand_at(float *d, int64_t n, int opt, float bias, float scale, uint64_t seed, uint64_t offset, t4k_stream_t s);
 /* CUDA-graph replays: a captured t4k_rand has its seed and offset baked in; t4k_rand adds a device-side replay epoch (x 2^40) to its
  * counter, and t4k_rand_tick — put once at the head of a captured sequence that draws — advances it, so that every replay draws

@@ -51,6 +51,7 @@ struct TlEpi {
 struct TlJob { const float *A, *B; float *O; float alpha, beta; int tA, tB, M, N, K; const TlEpi *epi; };
 // one launch for one or two independent problems (e.g. dW and dX of a layer): T4K_ENOSUP when they do not fit one co-resident wave
 int  gemm_tl_multi(const TlJob *jobs, int njobs, cudaStream_t st, int *ctas_out = nullptr);
+int  gemm_tl_pair_inplace(const TlJob *jobs, cudaStream_t st);   // two problems, jobs[0] stores over an operand jobs[1] reads (its stores wait for those reads)
 int  gemm_tl_ctas(const TlJob *jobs, int njobs);          // CTAs gemm_tl_multi would launch for these problems (<= 0: not supported)
 bool gemm_tl_ok(const float *A, const float *B, const float *O, int tA, int tB, int M, int N, int K, int C, int batch);
 int  gemm_tl(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB,

@@ -76,6 +76,10 @@ struct TlG {
     int mask_hi;                 // debug: store the masked hi back over the raw plane (does not rely on the MMA ignoring the low bits)
     uint32_t mn_type, mn_lbo, mn_sbo, mn_kstep;      // MN-major operand descriptor: layout type, LBO / SBO / start-address step per 8 k (bytes)
     long long *trace;            // bring-up: clock64 stamps of CTA 0's phases (t4k_gemm_tl_trace), nullptr in production
+    // in-place pair (problem 0 overwrites an operand of problem 1: dX = dY @ W stored over X while dW += dY^T @ X reads X): every CTA of problem 1
+    // counts itself in xsync[0] once its LAST operand tile has landed in shared memory; the CTAs of problem 0 hold their stores until all
+    // `nread` have (the grid is one co-resident wave, so nobody waits for a CTA that has not started); the last CTA out re-zeroes the counters
+    unsigned *xsync; unsigned nread;
 };
 #define TL_TRACE(ev) do { if (g.trace && blockIdx.x == 0) g.trace[ev] = clock64(); } while (0)
 
@@ -229,6 +233,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) TL_TRACE(1);
 
+    if (g.xsync && second && nkb == 0 && threadIdx.x == 0) atomicAdd(g.xsync, 1u);               // nothing to read: counted at once
     if (warp == 0) {
         // ===== TMA producer: raw FP32 tiles, four k-blocks in flight =====
         if (lane == 0) {
@@ -252,6 +257,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const __grid_constant_
             tc_fence_after();
             if (lane == 0 && i == 0) TL_TRACE(5);
             if (lane == 0 && i == nkb - 1) TL_TRACE(8);
+            if (g.xsync && second && i == nkb - 1 && lane == 0) { __threadfence(); atomicAdd(g.xsync, 1u); }      // this CTA's reads of the shared operand are over
             if (elect_one()) {
                 const uint32_t acc = tmem_base + (uint32_t)(b * L_BN);
                 const uint32_t sa = smem_u32(smem + (size_t)s * L_SLOT_B), sb = sa + L_PLANE_B;
@@ -402,6 +408,13 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const __grid_constant_
     if (S > 1) tl_cluster_sync();                                                     // every CTA's tile is parked / stored and visible cluster-wide
     if (threadIdx.x == 0) TL_TRACE(11);
 
+    if (g.xsync && !second) {                                                         // in-place pair: the operand this problem overwrites has been read
+        if (threadIdx.x == 0) {
+            unsigned v;
+            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(g.xsync) : "memory"); } while (v < g.nread);
+        }
+        __syncthreads();
+    }
     // ===== reduction over the tile's ranks + epilogue: rank `zs` finishes rows [zs*rpr, (zs+1)*rpr) of the tile, a warp per row, lane = 16-byte chunk =====
     if (active) {
         const int rpr = L_BM / split;
@@ -555,6 +568,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) k_gemm_tl(const __grid_constant_
     if (S > 1 && dsm_exit) tl_cluster_sync();
     if (threadIdx.x == 0) TL_TRACE(14);
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * L_BN); }
+    if (g.xsync && threadIdx.x == 0) {
+        const unsigned t = atomicAdd(g.xsync + 1, 1u);
+        if (t == gridDim.x - 1) { g.xsync[0] = 0u; __threadfence(); g.xsync[1] = 0u; }           // everybody is past its use of the counters
+    }
 }
 
 // ------------------------------------------------------------------ host side
@@ -587,6 +604,8 @@ static_assert(L_SMEM <= 227 * 1024, "shared memory budget");
 static_assert(L_NBAR * 8 + 8 <= 256, "barrier block");
 #define TL_MAX_DEV 16
 static int g_tl_maxcl[TL_MAX_DEV][5];                   // [device][log2 S]: co-resident clusters of size S (-1: unavailable)
+static unsigned *g_tl_xsync[TL_MAX_DEV];                // in-place pair counters (two words per ring slot, zero between launches)
+static unsigned g_tl_xslot[TL_MAX_DEV];
 
 static int tl_device() { const int d = cur_device(); return (d < 0 || d >= TL_MAX_DEV) ? -1 : d; }
 static int tl_prepare(int dev) {
@@ -606,6 +625,10 @@ static int tl_prepare(int dev) {
         if (S == 1) n = sm_count();
         else if (cudaOccupancyMaxActiveClusters(&n, k_gemm_tl, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
         g_tl_maxcl[dev][l] = n > 0 ? n : -1;
+    }
+    if (!g_tl_xsync[dev]) {                               // ring of 64 counter pairs: launches of different streams never share one
+        if (cudaMalloc((void**)&g_tl_xsync[dev], 64 * 2 * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return T4K_ENOMEM; }
+        cudaMemset(g_tl_xsync[dev], 0, 64 * 2 * sizeof(unsigned));
     }
     attr[dev] = true;
     return 0;
@@ -664,7 +687,7 @@ static int tl_fill(const TlJob &j, TlP &p, CUtensorMap *amap, CUtensorMap *bmap,
 
 // One launch for one or two problems.  Cluster size S and, per problem, K-split (split == S: a cluster is one tile) or none (split == 1: a
 // cluster is S tiles): the combination with the fewest k-blocks per CTA that keeps the whole grid co-resident (one wave).
-static int tl_launch(const TlJob *jobs, int njobs, cudaStream_t st, int *ctas_out, bool dry) {
+static int tl_launch(const TlJob *jobs, int njobs, cudaStream_t st, int *ctas_out, bool dry, bool inplace = false) {
     if (njobs < 1 || njobs > 2) return T4K_EINVAL;
     const int dev = tl_device();
     if (dev < 0) return T4K_EINVAL;
@@ -722,6 +745,7 @@ static int tl_launch(const TlJob *jobs, int njobs, cudaStream_t st, int *ctas_ou
     g.mask_hi = tl_knob(1);
     g.mn_type = (uint32_t)tl_knob(3); g.mn_lbo = (uint32_t)tl_knob(5); g.mn_sbo = (uint32_t)tl_knob(6); g.mn_kstep = (uint32_t)tl_knob(7);
     g.trace = g_tl_trace;
+    if (inplace && njobs == 2) { g.xsync = g_tl_xsync[dev] + 2 * (g_tl_xslot[dev]++ & 63u); g.nread = (unsigned)(ncl[1] * S); }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((ncl[0] + ncl[1]) * S)); cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = L_SMEM; cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -734,6 +758,8 @@ static int tl_launch(const TlJob *jobs, int njobs, cudaStream_t st, int *ctas_ou
 }
 
 int gemm_tl_multi(const TlJob *jobs, int njobs, cudaStream_t st, int *ctas_out) { return tl_launch(jobs, njobs, st, ctas_out, false); }
+// two problems, the FIRST of which stores over an operand the SECOND reads (see TlG::xsync)
+int gemm_tl_pair_inplace(const TlJob *jobs, cudaStream_t st) { return tl_launch(jobs, 2, st, nullptr, false, true); }
 int gemm_tl_ctas(const TlJob *jobs, int njobs) { int n = 0; const int rc = tl_launch(jobs, njobs, nullptr, &n, true); return rc ? rc : n; }
 int gemm_tl(const float *A, const float *B, float *O, float alpha, float beta, int tA, int tB, int M, int N, int K, cudaStream_t st, const TlEpi *epi) {
     TlJob j{A, B, O, alpha, beta, tA, tB, M, N, K, epi};

@@ -581,11 +581,10 @@ void Model::_fstep(Tensor &in, Tensor &out) {                             // for
     case T4K_L_RELU: case T4K_L_TANH: case T4K_L_SIGMOID: case T4K_L_SELU:
     case T4K_L_LEAKYRL: case T4K_L_ELU: _factivate(in, out, fn); break;
     case T4K_L_DROPOUT: {
+        // fresh mask every forward (forward.cu:98-102), drawn and applied in one launch; data parallel: the mask of THIS shard of the global batch (rand.cu)
         Tensor &t = *in.grad[4];
-        // fresh mask every forward (forward.cu:98-102); data parallel: the mask of THIS shard of the global batch (rand.cu)
-        if (_dp_world > 1) KCHK(t4k_rand_sharded(t.data, (int64_t)t.numel, (int64_t)_dp_rank * (int64_t)t.numel, (int64_t)_dp_world * (int64_t)t.numel, T4K_UNIFORM, 0.0f, 1.0f, ST));
-        else KCHK(t4k_rand(t.data, t.numel, T4K_UNIFORM, 0.0f, 1.0f, ST));
-        _factivate(in, out, fn);
+        const int64_t n = (int64_t)t.numel;
+        KCHK(t4k_dropout_fwd(in.data, out.data, t.data, in.xparm, n, _dp_world > 1 ? (int64_t)_dp_rank * n : 0, _dp_world > 1 ? (int64_t)_dp_world * n : n, ST));
     } break;
     case T4K_L_SOFTMAX: _fsoftmax(in, out);    break;
     case T4K_L_LOGSMAX: _flogsoftmax(in, out); break;

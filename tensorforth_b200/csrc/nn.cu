@@ -343,6 +343,8 @@ __global__ void __launch_bounds__(T4K_THREADS) k_head_grad_fin(const float *__re
 } // namespace t4k
 using namespace t4k;
 
+// dX and dW of a linear layer in one launch of the layer GEMM (T4K_TL_PAIR=0: two launches, as before)
+static int g_tl_pair = []{ const char *e = getenv("T4K_TL_PAIR"); return (e && e[0] == '0') ? 0 : 1; }();
 static bool head_train_ok(int layer, int N, int EH, int E1, int E0) {
     return (layer == T4K_L_RELU || layer == T4K_L_TANH || layer == T4K_L_SELU || layer == T4K_L_LEAKYRL || layer == T4K_L_ELU) &&
            E0 >= 1 && E0 <= 32 && EH <= 128 && (EH & 3) == 0 && (E1 & 3) == 0 && N >= 32;
@@ -419,6 +421,13 @@ extern "C" int t4k_linear_bwd_ex(const float *X, const float *W, const float *dY
         if (!dW || (!dB && !skip_db)) return T4K_EINVAL;
         int rc = 0;
         if (!skip_db) { rc = t4k_dbias(dY, dB, N, E0, s); if (rc) return rc; }       // dB[E0] += Σ_n dY
+        if (g_tl_pair && gemm_tl_ok(dY, W, dX, 0, 0, N, E1, E0, 1, 1) && gemm_tl_ok(dY, X, dW, 1, 0, E0, E1, N, 1, 1)) {
+            // dX and dW in ONE launch of the layer GEMM, also when dX is stored over X (Model::_blinear works in place): the dX tiles are held
+            // back until every CTA of the dW problem has its last X tile in shared memory
+            const TlJob jobs[2] = {{dY, W, dX, 1.0f, 0.0f, 0, 0, N, E1, E0, nullptr}, {dY, X, dW, 1.0f, 1.0f, 1, 0, E0, E1, N, nullptr}};
+            rc = (X == dX) ? gemm_tl_pair_inplace(jobs, STRM(s)) : gemm_tl_multi(jobs, 2, STRM(s));
+            if (rc != T4K_ENOSUP) return rc;
+        }
         rc = t4k_gemm(dY, X, dW, 1.0f, 1.0f, 1, 0, E0, E1, N, 1, 1, 0, 0, 0, s);      // dW[E0,E1] += dY^T[E0,N] @ X[N,E1]
         if (rc) return rc;
     }
@@ -432,14 +441,19 @@ extern "C" int t4k_linear_bwd_act(const float *X, const float *W, const float *d
         if (rc) return rc;
         return t4k_activate_bwd(dX, Fprev, dXprev, (int64_t)N * E1, s);
     }
+    TlEpi e{}; e.mode = 3; e.F = Fprev; e.O2 = dXprev;
     if (train) {
         if (!dW || (!dB && !skip_db)) return T4K_EINVAL;
         int rc = 0;
         if (!skip_db) { rc = t4k_dbias(dY, dB, N, E0, s); if (rc) return rc; }
+        if (g_tl_pair && gemm_tl_ok(dY, X, dW, 1, 0, E0, E1, N, 1, 1)) {               // dX (+ the activation backward in its epilogue) and dW in one launch, see t4k_linear_bwd_ex
+            const TlJob jobs[2] = {{dY, W, dX, 1.0f, 0.0f, 0, 0, N, E1, E0, &e}, {dY, X, dW, 1.0f, 1.0f, 1, 0, E0, E1, N, nullptr}};
+            rc = (X == dX || X == dXprev) ? gemm_tl_pair_inplace(jobs, STRM(s)) : gemm_tl_multi(jobs, 2, STRM(s));
+            if (rc != T4K_ENOSUP) return rc;
+        }
         rc = t4k_gemm(dY, X, dW, 1.0f, 1.0f, 1, 0, E0, E1, N, 1, 1, 0, 0, 0, s);
         if (rc) return rc;
     }
-    TlEpi e{}; e.mode = 3; e.F = Fprev; e.O2 = dXprev;
     return gemm_tl(dY, W, dX, 1.0f, 0.0f, 0, 0, N, E1, E0, STRM(s), &e);            // dX = dY @ W ; dXprev = dX * Fprev
 }
 extern "C" int t4k_linear_dx_from_head(const float *P, const float *T, const float *W2, const float *F1, const float *W1, float *dX,

@@ -63,8 +63,35 @@ k_rand(float *d, int64_t n, int opt, float bias, float scale, uint64_t seed, uin
         for (int k = 0; k < 4; k++) { const int64_t i = 4 * q + k; if (i < n) d[i] = scale * (bias + r[k]); }
     }
 }
+// dropout forward in one pass: the mask draw of k_rand (same counters, same U(0,1] conversion: bit-identical masks) and k_activate's L_DROPOUT
+// arithmetic (src/nn/nmath.cu:37-70: keep where u > rate, no rescaling) — one launch and 12 bytes per element instead of two launches and 20
+__global__ void __launch_bounds__(T4K_THREADS)
+k_dropout_fwd(const float *__restrict__ I, float *O, float *F, float rate, int64_t n, uint64_t seed, uint64_t offset, const uint64_t *__restrict__ epoch) {
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    if (epoch) offset += epoch[0] << 40;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t e = offset + (uint64_t)i;
+        const uint4 x = philox4x32_10(make_uint4((uint32_t)(e >> 2), (uint32_t)(e >> 34), 0u, 0u), key);
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+        const float u = 1.0f * (0.0f + u01(w[e & 3]));           // t4k_rand(..., bias 0, scale 1): the same two roundings
+        const bool keep = u > rate;
+        O[i] = keep ? I[i] : 0.0f; F[i] = keep ? 1.0f : 0.0f;
+    }
+}
 } // namespace t4k
 using namespace t4k;
+
+/* Model::_fstep L_DROPOUT (src/nn/forward.cu:98-102 + k_activate): F <- fresh U(0,1] mask draw, thresholded; O = I where kept, else 0.  Draws
+ * exactly what t4k_rand_sharded(F, n, before, global_n, UNIFORM) would (before = 0, global_n = n on a single device) and advances the stream alike. */
+extern "C" int t4k_dropout_fwd(const float *I, float *O, float *F, float rate, int64_t n, int64_t before, int64_t global_n, t4k_stream_t s) {
+    if (!I || !O || !F || n < 0 || before < 0 || global_n < before + n) return T4K_EINVAL;
+    if (n > 0) {
+        k_dropout_fwd<<<stream_grid(n), T4K_THREADS, 0, STRM(s)>>>(I, O, F, rate, n, g_seed, g_offset + (uint64_t)before, epoch_ptr());
+        const int rc = check_launch(); if (rc) return rc;
+    }
+    g_offset += (uint64_t)((global_n + 3) & ~3ll);
+    return 0;
+}
 
 extern "C" int t4k_rand_seed(uint64_t seed) {
     g_seed = seed; g_offset = 0;

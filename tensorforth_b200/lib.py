@@ -64,6 +64,7 @@ PROTOTYPES = {
     "t4k_dconv2d_fwd": (_i, [_p] * 4 + [_i] * 10 + [_p]),
     "t4k_dconv2d_bwd": (_i, [_p] * 6 + [_i] * 11 + [_p]),
     "t4k_set_carveout": (_i, [_i]),
+    "t4k_dropout_fwd": (_i, [_p, _p, _p, _f, _l, _l, _l, _p]),
     "t4k_rand_sharded": (_i, [_p, _l, _l, _l, _i, _f, _f, _p]),
     "t4k_batchnorm_fwd_dp": (_i, [_p] * 7 + [_i] * 4 + [_p]),
     "t4k_batchnorm_bwd_dp": (_i, [_p] * 8 + [_i] * 5 + [_p]),

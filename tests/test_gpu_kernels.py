@@ -570,10 +570,41 @@ def test_linear_fwd_bwd(N, E0, E1):
     assert_close(host(db), rdb, rtol=1e-4, what="dB")
     assert_close(host(dw), orc.gemm(dY, X, O=dW0, alpha=1.0, beta=1.0, tA=True), rtol=1e-4, what="dW")
     assert_close(host(dx), orc.gemm(dY, W), rtol=1e-4, what="dX")
+    # in place (dX stored over X, as Model::_blinear calls it): with the one-launch dX/dW pair the dX tiles are held back until the dW problem has
+    # read X — repeated, a lost ordering would show as a dW built from overwritten rows
+    for _ in range(4):
+        xio, dw3, db3 = dev(X), dev(dW0), dev(dB0)
+        ok(lib().t4k_linear_bwd(ptr(xio), ptr(dev(W)), ptr(dev(dY)), ptr(xio), ptr(dw3), ptr(db3), N, E0, E1, 1, None))
+        assert_exact(host(xio), host(dx), "dX in place"); assert_exact(host(dw3), host(dw), "dW with dX in place")
     # train == 0: parameters' gradients untouched
     dw2, db2 = dev(dW0), dev(dB0)
     ok(lib().t4k_linear_bwd(ptr(dev(X)), ptr(dev(W)), ptr(dev(dY)), ptr(dx), ptr(dw2), ptr(db2), N, E0, E1, 0, None))
     assert_exact(host(dw2), dW0); assert_exact(host(db2), dB0)
+
+
+@pytest.mark.parametrize("n,rate", [(7, 0.3), (4096, 0.5), (100352, 0.3), (1024 * 512, 0.3)])
+def test_dropout_fwd_equals_rand_then_activate(n, rate):
+    """the one-launch dropout forward draws the mask t4k_rand would draw and applies k_activate's L_DROPOUT rule: same bits, same stream position"""
+    L = lib()
+    x = dev(rnd(n))
+    L.t4k_rand_seed(123)
+    f1, o1, nx1 = zeros(n), zeros(n), zeros(64)
+    ok(L.t4k_rand(ptr(f1), n, t4.UNIFORM, 0.0, 1.0, None)); ok(L.t4k_activate_fwd(t4.L_DROPOUT, ptr(x), ptr(o1), ptr(f1), rate, n, None))
+    ok(L.t4k_rand(ptr(nx1), 64, t4.UNIFORM, 0.0, 1.0, None))
+    L.t4k_rand_seed(123)
+    f2, o2, nx2 = zeros(n), zeros(n), zeros(64)
+    ok(L.t4k_dropout_fwd(ptr(x), ptr(o2), ptr(f2), rate, n, 0, n, None)); ok(L.t4k_rand(ptr(nx2), 64, t4.UNIFORM, 0.0, 1.0, None))
+    assert_exact(host(f2), host(f1), "mask"); assert_exact(host(o2), host(o1), "output"); assert_exact(host(nx2), host(nx1), "next draw")
+    kept = float(host(f2).mean())
+    assert abs(kept - (1.0 - rate)) < 5.0 / np.sqrt(n) + 1e-9 or n < 100
+    # a shard of a larger batch-major tensor: the slice of the single-device mask
+    if n % 4 == 0 and n >= 4096:
+        L.t4k_rand_seed(123)
+        q = n // 4
+        f3, o3 = zeros(q), zeros(q)
+        xs = x[2 * q:3 * q].clone()
+        ok(L.t4k_dropout_fwd(ptr(xs), ptr(o3), ptr(f3), rate, q, 2 * q, n, None))
+        assert_exact(host(f3), host(f1)[2 * q:3 * q], "shard mask"); assert_exact(host(o3), host(o1)[2 * q:3 * q], "shard output")
 
 
 ACTS = [(t4.L_RELU, 0.0), (t4.L_TANH, 0.0), (t4.L_SIGMOID, 0.0), (t4.L_SELU, 0.0), (t4.L_LEAKYRL, 0.2),
