@@ -83,12 +83,16 @@ void Runtime::free(void *p) { if (p) cudaFreeAsync(p, (cudaStream_t)stream()); }
 
 #define ST         (Runtime::stream())
 #define KCHK(call) do { int _rc = (call); if (_rc) Runtime::error("%s -> %d (%s)", #call, _rc, t4k_strerror(_rc)); } while (0)
-// how the early half of the data-parallel exchange travels (T4K_DP_EARLY): "dma" copy engines (default), "sm" the push kernel, "range" the whole
-// exchange + optimizer of the finished part on the side stream (measured slower on 2 GPUs: its waiting CTAs sit on SMs the conv block's backward needs)
-static int dp_early_mode() {
-    static int m = -1;
-    if (m < 0) { const char *e = getenv("T4K_DP_EARLY"); m = !e ? 1 : (!strcmp(e, "sm") ? 0 : (!strcmp(e, "range") ? 2 : 1)); }
-    return m;
+// how the early half of the data-parallel exchange travels (T4K_DP_EARLY): "dma" copy engines + the exchange/optimizer of the rest of the arena
+// under the first layer's finish launch, "sm" the push kernel of comm.cu, "range" the whole exchange + optimizer of the finished part at once
+// (measured slower: its waiting CTAs sit on SMs the conv block's backward needs).  Default by world size, from the measured steps (MNIST CNN,
+// N=512 per GPU, us per step dma / sm): 2 GPUs 79.5 / 82.0, 8 GPUs 111.1 / 96.1 — seven peer-to-peer copies per rank, even on seven streams,
+// outlast the 25 us of backward they hide under, while the push kernel spreads them over the SMs' store paths.
+static int g_dp_early = -1;
+static int dp_early_mode(int world = 2) {
+    int &m = g_dp_early;
+    if (m < 0) { const char *e = getenv("T4K_DP_EARLY"); m = !e ? 3 : (!strcmp(e, "sm") ? 0 : (!strcmp(e, "range") ? 2 : (!strcmp(e, "dma") ? 1 : 3))); }
+    return m == 3 ? (world <= 4 ? 1 : 0) : m;
 }
 static inline DU SCALAR(DU v) { uint32_t u; memcpy(&u, &v, 4); u &= ~1u; memcpy(&v, &u, 4); return v; }   // src/t4base.h:33 (object tag bit cleared)
 
@@ -551,7 +555,7 @@ int Model::_bfused(int i) {                                // i = index of the b
     // data parallel, the block of the FIRST parameter layer, the rest of the arena already pushed to the peers (copy engines, _dp_push): the
     // exchange + optimizer of that rest runs on the side stream from the moment the block's main kernel is done (it must not take SMs from it:
     // one exact wave), under the block's finish launch — the end of the step then only exchanges the first chunk
-    const bool dp_rest = _comm && _dpo.on && !_dpo.rest && dp_early_mode() == 1 && _dp_pushed_from > 0 && _dp_pushed_from < (int64_t)_total && train && df.data == _DG;
+    const bool dp_rest = _comm && _dpo.on && !_dpo.rest && dp_early_mode(_dp_world) == 1 && _dp_pushed_from > 0 && _dp_pushed_from < (int64_t)_total && train && df.data == _DG;
     if (rc == T4K_ENOSUP) {
         if (dp_rest) t4k_conv_pool_relu_bwd_mid_event((void*)g_mid);
         rc = t4k_conv_pool_relu_bwd(dy.data, flat_dst, po.grad[4]->data, po.data, co.data, in.data, dx.data, f.data, df.data, db.data,
@@ -687,7 +691,7 @@ Model &Model::backprop(Tensor &tgt) {
         i--;
     }
     if (_side_join) {                                                                               // side-stream branch of this backprop
-        if (_comm && _dpo.rest && dp_early_mode() == 1)
+        if (_comm && _dpo.rest && dp_early_mode(_dp_world) == 1)
             // data parallel: the exchange + optimizer of the rest of the arena is still running there and nothing at the end of the step reads what
             // it writes — the optimizer call waits for the side stream's EARLIER work only (loss for the scalars), the step's end joins the rest
             cudaStreamWaitEvent((cudaStream_t)ST, g_push, 0);
@@ -711,7 +715,7 @@ void Model::_dp_push() {
     cudaEventRecord(g_fork, st); cudaStreamWaitEvent(g_stream2, g_fork, 0);
     const int64_t chf = t4k_comm_chunk_floats((t4k_comm_t)_comm);
     const int64_t split = chf > 0 ? ((_first_end + chf - 1) / chf) * chf : 0;          // first chunk boundary at or past the first layer's segments
-    if (dp_early_mode() == 2 && _dpo.on && split > 0 && split < (int64_t)_total) {
+    if (dp_early_mode(_dp_world) == 2 && _dpo.on && split > 0 && split < (int64_t)_total) {
         // (a) the whole exchange + optimizer of the chunks past the first layer runs THERE, under the first layer's backward (the peers reach
         // this point at the same place of their step): what stays on the critical path at the end of the step is the first chunk's exchange alone
         const int rc = t4k_optim_multi_dp_range((t4k_comm_t)_comm, _dpo.kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, split, (int64_t)_total, (int64_t)_total,
@@ -724,7 +728,7 @@ void Model::_dp_push() {
     // (b) push the finished part of the gradient arena to the peers while the remaining backward kernels run — by copy engine (no SM taken from
     // the conv block's backward, which fills the machine in exactly one wave) or, T4K_DP_EARLY=sm, by the MODE -1 kernel of comm.cu;
     // Model::_gradient joins it in front of the optimizer.
-    if (dp_early_mode() == 1) {
+    if (dp_early_mode(_dp_world) == 1) {
         const int64_t r = t4k_dp_push_dma((t4k_comm_t)_comm, _DG, _first_end, (int64_t)_total, _dp_step, (t4k_stream_t)g_stream2);
         cudaEventRecord(g_join, g_stream2);
         cudaEventRecord(g_push, g_stream2);                 // everything the side stream holds up to here (loss, head gradients, the push)
@@ -1429,6 +1433,7 @@ int   t4h_model_dp_attach(t4h_model m, void *comm, float *scal, int nscal) { ret
 int   t4h_model_dp_shard(t4h_model m, int rank, int world, void *comm_stat) { return MM(m).dp_shard(rank, world, comm_stat); }
 int   t4h_model_bn_channels(t4h_model m) { return MM(m).bn_channels(); }
 int   t4h_use_lane(int lane) { return Runtime::use_lane(lane); }
+int   t4h_set_dp_early(int mode) { const int was = g_dp_early; g_dp_early = (mode < 0 || mode > 3) ? 3 : mode; return was; }
 int   t4h_tensor_rand_sharded(t4h_tensor t, int opt, int rank, int world) {
     if (world < 1 || rank < 0 || rank >= world) return T4K_EINVAL;
     const int64_t n = (int64_t)TT(t).numel;

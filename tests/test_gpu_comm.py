@@ -179,6 +179,56 @@ def test_fused_exchange_optimizer_equals_optimizer_on_summed_gradient(kind, worl
     ring.close()
 
 
+@pytest.mark.parametrize("world,big", [(2, 196000), (4, 48000)])
+def test_dma_push_then_fused_exchange(world, big):
+    """the copy-engine push (t4k_dp_push_dma: peer-to-peer copies into the slots of the stated parity + a one-block signal kernel) followed by the
+    fused exchange + optimizer — in one launch, or split at the pushed offset into the rest of the arena and the first chunk (what the captured
+    step does) — equals the optimizer on the rank-summed gradient, step after step (the parity alternates)"""
+    L = lib()
+    warm(L)
+    segs = [(0, 92, 1), (92, 12, 1), (104, big, 1), (big + 104, 100, 1), (big + 204, 1000, 3), (big + 1204, 12, 1)]
+    total = big + 1216
+    seg = seg_table(segs)
+    ring = Ring(world, total)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    G0, M0, V0 = torch.randn(total, device="cuda", generator=gen) * 0.1, torch.randn(total, device="cuda", generator=gen) * 0.01, torch.rand(total, device="cuda", generator=gen) * 1e-3
+    lr, b1, b2, wd = 1e-2, 0.9, 0.999, 0.0
+    st0 = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    G = [G0.clone() for _ in range(world)]; M = [M0.clone() for _ in range(world)]; V = [V0.clone() for _ in range(world)]
+    Gr, Mr, Vr = G0.clone(), M0.clone(), V0.clone()
+    for step in range(4):
+        DG = [torch.randn(total, device="cuda", generator=gen) for _ in range(world)]
+        DGr = ranked_sum(DG)
+        ok(L.t4k_optim_multi(1, ptr(Gr), ptr(DGr), ptr(Mr), ptr(Vr), ptr(seg), len(segs), total, lr, b1, b2, wd, st0), "optim_multi")
+        torch.cuda.synchronize()
+        pushed = [0] * world
+        for r in range(world):
+            pushed[r] = L.t4k_dp_push_dma(ring.h[r], ptr(DG[r]), 104, total, step, ring.st(r))
+            assert 104 <= pushed[r] < total, pushed[r]
+        for r in range(world):
+            if step & 1:                                            # split at the pushed offset: rest of the arena, then the first chunk
+                ok(L.t4k_optim_multi_dp_range(ring.h[r], 1, ptr(G[r]), ptr(DG[r]), ptr(M[r]), ptr(V[r]), ptr(seg), len(segs), pushed[r], total, total,
+                                              lr, b1, b2, wd, None, 0, pushed[r], ring.st(r)), "rest")
+                ok(L.t4k_optim_multi_dp_range(ring.h[r], 1, ptr(G[r]), ptr(DG[r]), ptr(M[r]), ptr(V[r]), ptr(seg), len(segs), 0, pushed[r], total,
+                                              lr, b1, b2, wd, None, 0, pushed[r], ring.st(r)), "first chunk")
+            else:
+                ok(L.t4k_optim_multi_dp(ring.h[r], 1, ptr(G[r]), ptr(DG[r]), ptr(M[r]), ptr(V[r]), ptr(seg), len(segs), total,
+                                        lr, b1, b2, wd, None, 0, pushed[r], ring.st(r)), "optim_multi_dp")
+        ring.sync()
+        for r in range(world):
+            assert torch.equal(G[r], Gr), "G step %d rank %d" % (step, r)
+            assert torch.equal(M[r], Mr) and torch.equal(V[r], Vr)
+            assert float(DG[r].abs().max()) == 0.0
+    # a push addressed with the wrong parity is caught on the device (sticky error), not summed
+    DGx = [torch.ones(total, device="cuda") for _ in range(world)]
+    assert L.t4k_dp_push_dma(ring.h[0], ptr(DGx[0]), 104, total, 5, ring.st(0)) >= 104         # 4 exchanges completed: step 5 is the wrong parity
+    ring.streams[0].synchronize()
+    assert L.t4k_comm_status(ring.h[0]) == 1
+    torch.cuda.synchronize()
+    for r in range(world):
+        L.t4k_comm_destroy(ring.h[r])
+
+
 def test_exchange_replays_inside_cuda_graphs():
     L = lib()
     warm(L)
