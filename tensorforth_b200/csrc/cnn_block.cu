@@ -41,7 +41,7 @@ int wgrad_fin_opt_launch(const float *part, float *dF, float *dB, int nF, int C0
 struct Cpr2P {
     const float *I, *F, *B, *dY, *actFc;
     float *Icopy, *convO, *poolO, *actO, *actF, *flatO, *Iio, *dXbuf, *part;
-    int H, W, C1, C0, train;
+    int H, W, C1, C0, train, zero_all;
     // dataset feed folded into the forward block (t4k_conv_pool_relu_fwd_feed): samples n < feedN take their pixels from the staged
     // U8 block — d = ((float)u8 - mean) * scale as t4k_dataset_load — and write them to the dataset tensor (I) as well
     const uint8_t *u8I, *u8L; float mean, scale; int32_t *lab32; float *hot; int E, feedN;
@@ -322,9 +322,25 @@ __global__ void __launch_bounds__(256, 2) k_cpr2_bwd(Cpr2P p) {
     }
     for (int t = threadIdx.x; t < WP; t += blockDim.x) { sI[t] = 0.0f; sI[(HP - 1) * WP + t] = 0.0f; }
     for (int t = threadIdx.x; t < H; t += blockDim.x) { sI[(t + 1) * WP] = 0.0f; sI[(t + 1) * WP + W + 1] = 0.0f; }
-    {   // zero the whole routed tile (halo + padding stay zero; the interior is overwritten in phase A after the barrier)
+    if (p.zero_all) {   // A/B knob (T4K_CPR_ZERO=1): clear the whole routed tile, as before
         const int nq = (int)((((size_t)C0 * HP * RW + 3) & ~(size_t)3) >> 2);
         for (int t = threadIdx.x; t < nq; t += blockDim.x) *reinterpret_cast<float4*>(sR + 4 * t) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        // zero the HALO of the routed tile only: phase A writes all four pixels of every window, i.e. the whole interior, after the barrier —
+        // clearing it here as well was 9000 of the CTA's shared-memory stores for nothing.  Rows 0 and HP-1 as 64-bit stores (RW is even), then the
+        // left column and the right column (+ row padding) of the rows in between.
+        const int rq = RW >> 1;
+        for (int t = threadIdx.x; t < C0 * 2 * rq; t += blockDim.x) {
+            const int c = t / (2 * rq), k = t - c * 2 * rq;
+            float *row = sR + c * (HP * RW) + (k < rq ? 0 : (HP - 1) * RW);
+            *reinterpret_cast<float2*>(row + 2 * (k < rq ? k : k - rq)) = make_float2(0.f, 0.f);
+        }
+        for (int t = threadIdx.x; t < C0 * H; t += blockDim.x) {
+            const int c = t / H, y = t - c * H;
+            float *row = sR + c * (HP * RW) + (y + 1) * RW;
+            row[0] = 0.0f;
+            for (int x = WP - 1; x < RW; x++) row[x] = 0.0f;
+        }
     }
     cp_async_wait_all();                                // this thread's own copies have landed (it consumes only those before the barrier)
     if (alp) {                                          // coalesced 128-bit streams of the pooled-size tensors
@@ -622,6 +638,7 @@ extern "C" int t4k_conv_pool_relu_bwd_opt(const float *dY, float *actO, const fl
     const int nF = 9 * C0;
     Cpr2P p{}; p.F = F; p.dY = dY; p.actFc = actF; p.actO = actO; p.poolO = poolO; p.convO = convO; p.Iio = Iio; p.dXbuf = dXbuf;
     p.H = H1; p.W = W1; p.C1 = 1; p.C0 = C0; p.train = train;
+    { static int za = []{ const char *e = getenv("T4K_CPR_ZERO"); return (e && e[0] == '1') ? 1 : 0; }(); p.zero_all = za; }
     if (train) { p.part = (float*)workspace((size_t)N * (nF + C0) * sizeof(float), 4); if (!p.part) return T4K_ENOMEM; }
     const bool ex = (C0 == CM) && aligned16(convO);
     #define CPR2B(CM_, EX_) { static DevFlag attr; if (dev_first(attr)) { cudaFuncSetAttribute(k_cpr2_bwd<CM_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cudaFuncSetAttribute(k_cpr2_bwd<CM_, EX_>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); } \
