@@ -127,6 +127,8 @@ int   t4h_model_bn_channels(t4h_model m);        /* widest batchnorm layer (0: n
 int   t4h_tensor_rand_sharded(t4h_tensor t, int opt, int rank, int world);   /* t4k_rand_sharded on a batch-major tensor holding shard `rank` */
 void *t4h_side_stream(void);                     /* the side stream of the current lane (work forked inside a step) */
 int   t4h_use_lane(int lane);
+int   t4h_set_dp_rest(int on);                   /* 1 (default): the exchange + optimizer of everything past the first chunk runs on the side stream under the
+                                                  * first layer's finish launch; 0: one exchange launch at the end of the step (also T4K_DP_REST=0) */
 int   t4h_set_dp_early(int mode);                /* early half of the data-parallel exchange inside the captured step: 0 push kernel, 1 copy engines + early
                                                   * exchange of the rest of the arena, 2 whole early exchange, 3 by world size (default; also T4K_DP_EARLY=sm|dma|range) */                    /* tests: switch the process to stream set `lane` (0..3); lane 0 is the default */
 int   t4h_model_step_graph(t4h_model m, t4h_tensor input, t4h_tensor tgt, int loss_op, float *loss_dev,

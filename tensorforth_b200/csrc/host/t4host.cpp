@@ -88,6 +88,12 @@ void Runtime::free(void *p) { if (p) cudaFreeAsync(p, (cudaStream_t)stream()); }
 // (measured slower: its waiting CTAs sit on SMs the conv block's backward needs).  Default by world size, from the measured steps (MNIST CNN,
 // N=512 per GPU, us per step dma / sm): 2 GPUs 79.5 / 82.0, 8 GPUs 111.1 / 96.1 — seven peer-to-peer copies per rank, even on seven streams,
 // outlast the 25 us of backward they hide under, while the push kernel spreads them over the SMs' store paths.
+static int g_dp_rest = -1;
+static int dp_rest_on() {                                  // T4K_DP_REST=0: the end of the step exchanges the whole arena in one launch, as in round 1
+    int &v = g_dp_rest;
+    if (v < 0) { const char *e = getenv("T4K_DP_REST"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
 static int g_dp_early = -1;
 static int dp_early_mode(int world = 2) {
     int &m = g_dp_early;
@@ -555,7 +561,7 @@ int Model::_bfused(int i) {                                // i = index of the b
     // data parallel, the block of the FIRST parameter layer, the rest of the arena already pushed to the peers (copy engines, _dp_push): the
     // exchange + optimizer of that rest runs on the side stream from the moment the block's main kernel is done (it must not take SMs from it:
     // one exact wave), under the block's finish launch — the end of the step then only exchanges the first chunk
-    const bool dp_rest = _comm && _dpo.on && !_dpo.rest && dp_early_mode(_dp_world) == 1 && _dp_pushed_from > 0 && _dp_pushed_from < (int64_t)_total && train && df.data == _DG;
+    const bool dp_rest = _comm && _dpo.on && !_dpo.rest && dp_early_mode(_dp_world) <= 1 && dp_rest_on() && _dp_pushed_from > 0 && _dp_pushed_from < (int64_t)_total && train && df.data == _DG;
     if (rc == T4K_ENOSUP) {
         if (dp_rest) t4k_conv_pool_relu_bwd_mid_event((void*)g_mid);
         rc = t4k_conv_pool_relu_bwd(dy.data, flat_dst, po.grad[4]->data, po.data, co.data, in.data, dx.data, f.data, df.data, db.data,
@@ -691,7 +697,7 @@ Model &Model::backprop(Tensor &tgt) {
         i--;
     }
     if (_side_join) {                                                                               // side-stream branch of this backprop
-        if (_comm && _dpo.rest && dp_early_mode(_dp_world) == 1)
+        if (_comm && _dpo.rest && dp_early_mode(_dp_world) <= 1)
             // data parallel: the exchange + optimizer of the rest of the arena is still running there and nothing at the end of the step reads what
             // it writes — the optimizer call waits for the side stream's EARLIER work only (loss for the scalars), the step's end joins the rest
             cudaStreamWaitEvent((cudaStream_t)ST, g_push, 0);
@@ -739,6 +745,7 @@ void Model::_dp_push() {
     }
     const int64_t r = t4k_dp_push((t4k_comm_t)_comm, _DG, _first_end, (int64_t)_total, (t4k_stream_t)g_stream2);
     cudaEventRecord(g_join, g_stream2);
+    cudaEventRecord(g_push, g_stream2);
     _dp_join = true;
     if (r < 0) { Runtime::error("t4k_dp_push -> %ld", (long)r); _dp_pushed_from = (int64_t)_total; }
     else _dp_pushed_from = r;
@@ -1433,6 +1440,7 @@ int   t4h_model_dp_attach(t4h_model m, void *comm, float *scal, int nscal) { ret
 int   t4h_model_dp_shard(t4h_model m, int rank, int world, void *comm_stat) { return MM(m).dp_shard(rank, world, comm_stat); }
 int   t4h_model_bn_channels(t4h_model m) { return MM(m).bn_channels(); }
 int   t4h_use_lane(int lane) { return Runtime::use_lane(lane); }
+int   t4h_set_dp_rest(int on) { const int was = dp_rest_on(); g_dp_rest = on ? 1 : 0; return was; }
 int   t4h_set_dp_early(int mode) { const int was = g_dp_early; g_dp_early = (mode < 0 || mode > 3) ? 3 : mode; return was; }
 int   t4h_tensor_rand_sharded(t4h_tensor t, int opt, int rank, int world) {
     if (world < 1 || rank < 0 || rank >= world) return T4K_EINVAL;

@@ -45,6 +45,7 @@ PROTOTYPES = {
     "t4h_tensor_rand_sharded": (_i, [_p, _i, _i, _i]),
     "t4h_use_lane": (_i, [_i]),
     "t4h_set_dp_early": (_i, [_i]),
+    "t4h_set_dp_rest": (_i, [_i]),
     "t4h_side_stream": (_p, []),
     "t4h_capture_begin": (_i, []), "t4h_capture_end": (_p, []), "t4h_graph_launch": (_i, [_p]), "t4h_graph_free": (None, [_p]),
     "t4h_model_save_state": (_i, [_p, C.c_char_p]),

@@ -150,7 +150,7 @@ def test_mnist_cnn_dp_follows_the_single_rank_trajectory(world, N, graph):
     # stream, the first chunk at the end of the step), and the single device may fail to run them all at once.  The emulation therefore takes the
     # push kernel (one waiting kernel per rank, as the eager step); the copy-engine path is covered at the C-ABI level
     # (tests/test_gpu_comm.py::test_dma_push_...) and on two real GPUs (tests/test_gpu_dp_multi.py).
-    was = th.load().t4h_set_dp_early(0)
+    was, was_rest = th.load().t4h_set_dp_early(0), th.load().t4h_set_dp_rest(0)
     rk = Ranks(world, lambda: th.mnist_cnn(N), scal=True, warm_run=warm_run)
     th.use_lane(0)
     big = th.mnist_cnn(world * N)
@@ -190,7 +190,7 @@ def test_mnist_cnn_dp_follows_the_single_rank_trajectory(world, N, graph):
         d = (p0 - ref_params(big)).abs()
         assert float((d > 1e-6).float().mean()) < 2e-3 and float(d.max()) <= 2 * 1e-3 * 3.2, (step, float(d.max()))   # Adam's sign-like move near g = 0 (test_gpu_model.adam_slack)
     rk.close()
-    th.load().t4h_set_dp_early(was if was >= 0 else 3)
+    th.load().t4h_set_dp_early(was if was >= 0 else 3); th.load().t4h_set_dp_rest(was_rest)
 
 
 @pytest.mark.parametrize("world", [2, 4])
