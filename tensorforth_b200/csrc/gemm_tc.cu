@@ -335,6 +335,156 @@ __global__ void __launch_bounds__(320, 1) k_gemm_tc(TcP p) {
     }
 }
 
+
+// ------------------------------------------------------------------ CTA-pair variant (cta_group::2): 256 x 256 output tile per pair
+// Two CTAs of a cluster (one TPC) share every MMA: M = 256 (each CTA owns 128 rows of A and of the accumulator in its own TMEM), N = 256 with
+// each CTA holding 128 of the B tile's columns — per k-block a CTA stages A (hi+lo, 32 KiB) and HALF of B (hi+lo, 32 KiB): 64 KiB instead of the
+// 96 KiB of the single-CTA kernel, i.e. a third less L2 -> shared-memory traffic per flop and room for THREE stages.  The leader (cluster rank 0)
+// issues the MMAs; its full barrier says "my tiles landed", the follower's MMA-less warp 1 relays "mine too" into the leader's pfull barrier;
+// tcgen05.commit multicasts the stage-free and accumulator-ready arrivals to both CTAs; the follower's epilogue warps report "drained" to the leader.
+template<bool BF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1) k_gemm_tc2(TcP p) {
+    constexpr int BN = 256, STAGES = 3;
+    constexpr uint32_t PLANE_B = PLANE_FLTS * 4;                 // 16 KiB
+    constexpr uint32_t A_BYTES = 2 * PLANE_B, B_BYTES = 2 * PLANE_B, STAGE_BYTES = A_BYTES + B_BYTES;   // 64 KiB
+    constexpr int NEPI = 8, CW = BN / 2;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);   // full[S], pfull[S], empty[S], acc_full[2], acc_empty[2]
+    uint32_t *tmem_slot = (uint32_t*)(bars + 3 * STAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    int tile = blockIdx.x >> 1, kt0 = 0, kt1 = p.KT, tail_slot = -1;
+    if (p.tail_split > 0 && tile >= p.tail_first) {
+        const int r = tile - p.tail_first, z = r % p.tail_split;
+        tile = p.tail_first + r / p.tail_split;
+        kt0 = z * p.tail_kt_per; kt1 = min(p.KT, kt0 + p.tail_kt_per);
+        tail_slot = z * p.ntail + (tile - p.tail_first);
+    }
+    const int mp = tile / p.gx, nt = tile % p.gx;
+    const int mt = 2 * mp + (int)rank;                           // this CTA's 128-row tile of A / of the output
+    const int nkb = kt1 - kt0, nchunk = (nkb + DRAIN_KB - 1) / DRAIN_KB;
+    const uint32_t full0 = smem_u32(bars), pfull0 = full0 + 8 * STAGES, empty0 = pfull0 + 8 * STAGES;
+    const uint32_t afull0 = empty0 + 8 * STAGES, aempty0 = afull0 + 16;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(pfull0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(afull0 + 8 * b, 1); mbar_init(aempty0 + 8 * b, 2 * NEPI); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc_2cta(smem_u32(tmem_slot), 2 * BN);
+    tc_fence_before();
+    cluster_sync_aligned();                                      // both CTAs' barriers exist before anybody arrives on the peer's
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; i++) {
+                const int s = i % STAGES, it = i / STAGES;
+                mbar_wait(empty0 + 8 * s, (it & 1) ^ 1);
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+                mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+                const int kt = kt0 + i;
+                bulk_g2s(sa, p.PA + ((int64_t)mt * p.KT + kt) * TILE_FLTS, A_BYTES, full0 + 8 * s);                       // A rows: hi | lo
+                bulk_g2s(sb, p.PB + ((int64_t)(nt * 2 + (int)rank) * p.KT + kt) * TILE_FLTS, B_BYTES, full0 + 8 * s);    // this CTA's 128 columns of B: hi | lo
+            }
+        }
+    } else if (warp == 1 && rank != 0) {
+        // ===== follower: relay "my tiles of stage s landed" to the leader =====
+        for (int i = 0; i < nkb; i++) {
+            const int s = i % STAGES, it = i / STAGES;
+            mbar_wait(full0 + 8 * s, it & 1);
+            if (lane == 0) mbar_arrive_cluster(pfull0 + 8 * s, 0);
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===== leader: MMA issuer for the pair =====
+        constexpr uint32_t idesc = BF ? idesc_bf16(2 * TBM, BN) : idesc_tf32(2 * TBM, BN);
+        for (int i = 0; i < nkb; i++) {
+            const int s = i % STAGES, it = i / STAGES;
+            const int c = i / DRAIN_KB, ib = i % DRAIN_KB, b = c & 1;
+            if (ib == 0 && c >= 2) { mbar_wait(aempty0 + 8 * b, ((c >> 1) - 1) & 1); tc_fence_after(); }
+            mbar_wait(full0 + 8 * s, it & 1);
+            mbar_wait(pfull0 + 8 * s, it & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t acc = tmem_base + (uint32_t)(b * BN);
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+                const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + PLANE_B);
+                const uint64_t b_hi = smem_desc_sw128(sb), b_lo = smem_desc_sw128(sb + PLANE_B);
+                #pragma unroll
+                for (int k = 0; k < TBK / UK; k++) {
+                    const uint64_t ko = (uint64_t)((k * UK * 4) >> 4);
+                    if (BF) {
+                        tc_mma_bf16_2cta(acc, a_lo + ko, b_hi + ko, idesc, (ib | k) ? 1u : 0u);
+                        tc_mma_bf16_2cta(acc, a_hi + ko, b_lo + ko, idesc, 1u);
+                        tc_mma_bf16_2cta(acc, a_hi + ko, b_hi + ko, idesc, 1u);
+                    } else {
+                        tc_mma_tf32_2cta(acc, a_lo + ko, b_hi + ko, idesc, (ib | k) ? 1u : 0u);
+                        tc_mma_tf32_2cta(acc, a_hi + ko, b_lo + ko, idesc, 1u);
+                        tc_mma_tf32_2cta(acc, a_hi + ko, b_hi + ko, idesc, 1u);
+                    }
+                }
+            }
+            __syncwarp();
+            if (elect_one()) {
+                tc_commit_2cta(empty0 + 8 * s);
+                if (ib == DRAIN_KB - 1 || i == nkb - 1) tc_commit_2cta(afull0 + 8 * b);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue (both CTAs): own 128 rows; "drained" goes to the leader's barrier =====
+        const int q = warp & 3, h = (warp - 2) >> 2;
+        const int row = mt * TBM + q * 32 + lane;
+        float acc[CW];
+        #pragma unroll
+        for (int j = 0; j < CW; j++) acc[j] = 0.0f;
+        for (int c = 0; c < nchunk; c++) {
+            const int b = c & 1;
+            mbar_wait(afull0 + 8 * b, (c >> 1) & 1);
+            tc_fence_after();
+            #pragma unroll
+            for (int g = 0; g < CW / 16; g++) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + h * CW + g * 16), v);
+                tmem_ld_wait();
+                #pragma unroll
+                for (int j = 0; j < 16; j++) acc[g * 16 + j] += __uint_as_float(v[j]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (rank == 0) mbar_arrive(aempty0 + 8 * b); else mbar_arrive_cluster(aempty0 + 8 * b, 0); }
+        }
+        float *dst = p.O; float alpha = p.alpha, beta = p.beta;
+        int64_t ld = p.N; int orow = row, cbase = nt * BN, Mlim = p.M, Nlim = p.N;
+        if (tail_slot >= 0) { dst = p.tail_part + (int64_t)tail_slot * (2 * TBM) * BN; alpha = 1.0f; beta = 0.0f; ld = BN; orow = (int)rank * TBM + q * 32 + lane; cbase = 0; Mlim = 2 * TBM; Nlim = BN; }
+        const bool n_vec = ((ld & 3) == 0) && ((((uintptr_t)dst) & 15) == 0);
+        #pragma unroll
+        for (int g = 0; g < CW / 32; g++) {
+            const int col0 = cbase + h * CW + g * 32;
+            if (orow < Mlim && col0 < Nlim) {
+                float *o = dst + (int64_t)orow * ld + col0;
+                if (n_vec && col0 + 32 <= Nlim) {
+                    #pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 r = make_float4(acc[g * 32 + j] * alpha, acc[g * 32 + j + 1] * alpha, acc[g * 32 + j + 2] * alpha, acc[g * 32 + j + 3] * alpha);
+                        if (beta != 0.0f) { const float4 old = *reinterpret_cast<const float4*>(o + j); r.x += old.x * beta; r.y += old.y * beta; r.z += old.z * beta; r.w += old.w * beta; }
+                        stg4(o + j, r);
+                    }
+                } else {
+                    #pragma unroll
+                    for (int j = 0; j < 32; j++) if (col0 + j < Nlim) { float r = acc[g * 32 + j] * alpha; if (beta != 0.0f) r += o[j] * beta; o[j] = r; }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_aligned();                                      // nobody frees tensor memory / leaves while the pair's MMAs or remote arrivals are in flight
+    if (warp == 1) { tc_fence_after(); tmem_dealloc_2cta(tmem_base, 2 * BN); }
+}
+
 __global__ void k_splitk_fin_tc(const float *part, float *O, float alpha, float beta, int64_t MN, int splits);
 
 __global__ void __launch_bounds__(T4K_THREADS) k_splitk_fin_tc(const float *__restrict__ part, float *O,
@@ -348,12 +498,12 @@ __global__ void __launch_bounds__(T4K_THREADS) k_splitk_fin_tc(const float *__re
 
 // tail fix-up: O[tile] = alpha * Σ_slice tail_part[slice][tile] + beta * O[tile] for the tiles that were cut along K
 __global__ void __launch_bounds__(T4K_THREADS) k_tail_fin(const float *__restrict__ part, float *O, float alpha, float beta,
-                                                          int M, int N, int BN, int gx, int tail_first, int ntail, int nslice) {
+                                                          int M, int N, int BN, int gx, int tail_first, int ntail, int nslice, int TM) {
     const int t = blockIdx.y, tile = tail_first + t, mt = tile / gx, nt = tile % gx;
-    const int64_t tile_flts = (int64_t)TBM * BN;
+    const int64_t tile_flts = (int64_t)TM * BN;
     for (int e = (blockIdx.x * blockDim.x + threadIdx.x) * 4; e < tile_flts; e += gridDim.x * blockDim.x * 4) {
         const int r = e / BN, c = e % BN;
-        const int gm = mt * TBM + r, gn = nt * BN + c;
+        const int gm = mt * TM + r, gn = nt * BN + c;
         if (gm >= M || gn >= N) continue;
         float4 sum = ldg4(part + (int64_t)t * tile_flts + e);
         for (int z = 1; z < nslice; z++) { const float4 v = ldg4(part + ((int64_t)z * ntail + t) * tile_flts + e); sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w; }
@@ -404,6 +554,36 @@ int gemm_tc(const float *A, const float *B, float *O, float alpha, float beta, i
     const int gx = (N + BN - 1) / BN, gy = MT;
     int splits = 1;
     const int sms = sm_count();
+    // CTA pairs (k_gemm_tc2): large products with 256-wide N tiles and an even number of 128-row tiles; enough pair tiles to fill the machine
+    static int pair_on = -1;
+    if (pair_on < 0) { const char *e = getenv("T4K_GEMM_PAIR"); pair_on = e ? atoi(e) : 1; }           // T4K_GEMM_PAIR=0: the single-CTA kernel everywhere
+    if (pair_on && BN == 256 && (MT & 1) == 0 && KT >= 16 && gx * (MT / 2) >= sms / 2) {
+        const int slots = sms / 2, T2 = gx * (MT / 2), rem = T2 % slots;
+        TcP p{PA, PB, O, alpha, beta, M, N, KT, KT, 1, nullptr, gx, 0, 0, 0, 0, nullptr};
+        int npair = T2;
+        if (T2 > slots && rem > 0 && 2 * rem <= slots) {
+            int sl = slots / rem; if (sl > 4) sl = 4;
+            p.tail_first = T2 - rem; p.tail_kt_per = (KT + sl - 1) / sl; p.ntail = rem;
+            p.tail_split = (KT + p.tail_kt_per - 1) / p.tail_kt_per;
+            p.tail_part = (float*)workspace((size_t)p.tail_split * rem * 2 * TBM * BN * 4, 3);
+            if (!p.tail_part) return T4K_ENOMEM;
+            npair = p.tail_first + rem * p.tail_split;
+        }
+        constexpr size_t smem2 = (size_t)3 * 4 * PLANE_FLTS * 4 + 1024 + 256;
+        static DevFlag attr2[2];
+        if (dev_first(attr2[bf ? 1 : 0])) {
+            cudaError_t e = bf ? cudaFuncSetAttribute(k_gemm_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)
+                               : cudaFuncSetAttribute(k_gemm_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e != cudaSuccess) return (int)e;
+        }
+        if (bf) k_gemm_tc2<true><<<2 * npair, 320, smem2, st>>>(p); else k_gemm_tc2<false><<<2 * npair, 320, smem2, st>>>(p);
+        int rc = check_launch(); if (rc) return rc;
+        if (p.tail_split > 0) {
+            k_tail_fin<<<dim3(16, p.ntail), T4K_THREADS, 0, st>>>(p.tail_part, O, alpha, beta, M, N, BN, gx, p.tail_first, p.ntail, p.tail_split, 2 * TBM);
+            return check_launch();
+        }
+        return 0;
+    }
     if (gx * gy < sms && KT >= 8) {
         splits = (sms + gx * gy - 1) / (gx * gy);
         if (splits > KT / 4) splits = KT / 4;
@@ -434,7 +614,7 @@ int gemm_tc(const float *A, const float *B, float *O, float alpha, float beta, i
                 : ((BN == 256) ? launch_tc<256, 2, false>(p, grid, st) : launch_tc<128, 3, false>(p, grid, st));
     if (rc) return rc;
     if (p.tail_split > 0) {
-        k_tail_fin<<<dim3(8, p.ntail), T4K_THREADS, 0, st>>>(p.tail_part, O, alpha, beta, M, N, BN, gx, p.tail_first, p.ntail, p.tail_split);
+        k_tail_fin<<<dim3(8, p.ntail), T4K_THREADS, 0, st>>>(p.tail_part, O, alpha, beta, M, N, BN, gx, p.tail_first, p.ntail, p.tail_split, TBM);
         return check_launch();
     }
     if (splits == 1) return rc;

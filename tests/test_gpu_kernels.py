@@ -418,6 +418,29 @@ def test_linear_bwd_act(N, E0, E1):
     assert_exact(host(xio), host(dx)); assert_exact(host(dw2), host(dw))
 
 
+@pytest.mark.parametrize("engine", [t4.GEMM_TC, t4.GEMM_TC_BF16X3])
+@pytest.mark.parametrize("tA,tB,M,N,K", [(0, 0, 2200, 2400, 1024), (1, 1, 2304, 2100, 1100), (0, 1, 4096, 2048, 2048)])
+def test_gemm_tc_cta_pairs_ragged(engine, tA, tB, M, N, K):
+    """the CTA-pair kernel (k_gemm_tc2: cta_group::2, 256 x 256 tiles, three stages) on ragged M / N / K, transposed operands, alpha / beta,
+    with and without a K-split tail wave: FP32-grade against float64"""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A = torch.rand((K, M) if tA else (M, K), device="cuda", generator=g) * 2 - 1
+    B = torch.rand((N, K) if tB else (K, N), device="cuda", generator=g) * 2 - 1
+    O0 = torch.rand(M, N, device="cuda", generator=g)
+    o = O0.clone()
+    ok(lib().t4k_gemm_ex(engine, ptr(A), ptr(B), ptr(o), 0.5, 2.0, tA, tB, M, N, K, 1, 1, 0, 0, 0, None), "pair gemm")
+    idx = torch.cat([torch.arange(0, M, 97, device="cuda"), torch.tensor([M - 1], device="cuda")])
+    a = (A.t() if tA else A)[idx].double(); b = (B.t() if tB else B).double()
+    ref = 0.5 * (a @ b) + 2.0 * O0[idx].double()
+    got = o[idx].double()
+    rms = float((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    assert rms < (1.2e-5 if engine == t4.GEMM_TC_BF16X3 else 4e-6), rms
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-4
+    o2 = O0.clone()                                               # deterministic
+    ok(lib().t4k_gemm_ex(engine, ptr(A), ptr(B), ptr(o2), 0.5, 2.0, tA, tB, M, N, K, 1, 1, 0, 0, 0, None))
+    assert torch.equal(o, o2)
+
+
 @pytest.mark.parametrize("tA,tB", [(0, 0), (1, 1)])
 def test_gemm_tc_tail_split_ragged(tA, tB):
     """170 tiles on 148 SMs: the 22 tiles of the last wave are cut into K slices (gemm_tc.cu tail split); ragged M and N, alpha/beta"""
