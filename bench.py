@@ -534,6 +534,31 @@ def main():
                    "and the H2D copy + loss read-back overlap the step on their own streams",
            "window_ms": [round(w, 4) for w in wins_e2e]}
 
+    # ---- strong scaling: the SAME global batch of 512 cut into world shards of 512/world samples, one data-parallel step
+    strong = None
+    if world > 1 and fused and BATCH % world == 0 and BATCH // world >= 32:
+        try:
+            nb = BATCH // world
+            L.t4k_rand_seed(1234)
+            ms_ = th.mnist_cnn(nb)
+            Xs, Ys = th.Tensor.tensor(nb, 28, 28, 1), th.Tensor.tensor(nb, 1, 10, 1)
+            H.t4h_tensor_h2d(Xs.h, C.c_void_p(xh.data_ptr()), nb * 784); H.t4h_tensor_h2d(Ys.h, C.c_void_p(yh.data_ptr()), nb * 10)
+            ls_ = torch.zeros(8, device="cuda")
+            ms_.forward(Xs); ms_.backprop(Ys); ms_.adam(LR); th.sync()
+            dps = t4dp.DataParallel(ms_, torch.device("cuda", local), fused=True, scalars=ls_[:1])
+
+            def sstep():
+                t4.check(ms_.step_graph(Xs, Ys, t4.LOSS_CE, C.c_void_p(ls_.data_ptr()), optimizer=2, lr=LR), "step_graph (strong)")
+            for _ in range(6):
+                sstep()
+            wins_s = sorted(window(lambda: [sstep() for _ in range(100)]) for _ in range(3))
+            assert dps.comm.status() == 0
+            strong = {"global_batch": BATCH, "batch_per_gpu": nb, "ms_per_step": round(wins_s[1] / 100, 6), "samples_per_s": round(BATCH * 100 / (wins_s[1] / 1e3), 1),
+                      "scaling": "strong", "note": "the N=512 batch of the 1-GPU line cut into %d shards; same captured data-parallel step (exchange fused with Adam); "
+                                                   "compare with the 1-GPU ms_per_step of the same box session" % world}
+        except Exception as e:
+            strong = {"unavailable": repr(e)[:200]}
+            sys.stderr.write("strong-scaling extra failed: %r\n" % (e,))
     gan = conv = None
     if not args.no_extras:
         try:
@@ -684,6 +709,8 @@ def main():
         out.setdefault("extras", {})["conv2d_3x3_64"] = conv
     if gan is not None:
         out.setdefault("extras", {})["gan_t4_40b"] = gan
+    if strong is not None:
+        out.setdefault("extras", {})["mnist_strong_scaling"] = strong
     if not args.no_cpu_baseline:
         v, cores, sample = cpu_port_baseline()
         out["cpu_baseline"] = {"value": round(v, 1), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
