@@ -356,6 +356,15 @@ int64_t t4k_comm_chunk_floats(t4k_comm_t c);
  * t4k_optim_multi_dp as `pushed_from`; == total when nothing qualified), negative on error.  Exactly one
  * t4k_optim_multi_dp must follow before the next push; no other exchange on this communicator in between. */
 int64_t t4k_dp_push(t4k_comm_t c, const float *DG, int64_t from, int64_t total, t4k_stream_t s);
+/* reduce-scatter flavour for more than two ranks: chunk k has ONE owner (rank k % world).  t4k_dp_push_owner sends every chunk that starts at or beyond
+ * `from` to its owner only (1x the arena leaves the GPU instead of (world-1)x); t4k_optim_multi_dp_rs — one block per chunk on every rank — lets the owner
+ * sum the world pushes in rank order and store the SUM into every rank, after which every rank runs the optimizer on the chunk (state stays replicated).
+ * Two NVLink hops instead of one: for the part of the arena whose exchange is off the step's critical path. */
+int64_t t4k_dp_push_owner(t4k_comm_t c, const float *DG, int64_t from, int64_t total, t4k_stream_t s);
+int t4k_optim_multi_dp_rs(t4k_comm_t c, int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
+                          int64_t from, int64_t total, float lr, float b1, float b2, float wd, int phase, t4k_stream_t s);
+/* phase 0: both halves in one launch.  phase 1: the OWNERS' half only (wait for the pushes, sum, send the sums: ceil(chunks / world) blocks per
+ * rank — small enough to run next to backprop, right behind the push); phase 2: every rank's half (wait for the sums, optimizer). */
 /* the same push with the data moved by the copy engines (peer-to-peer cudaMemcpyAsync) and a one-block kernel raising the flags: no SM is taken
  * from the backward kernels it overlaps.  `step` = exchanges this communicator has completed so far (selects the slot parity the copies are
  * addressed with; a captured step is captured once per parity). */

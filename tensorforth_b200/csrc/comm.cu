@@ -33,7 +33,7 @@
 #define COMM_MAXW   8            // ranks (one NVSwitch domain)
 #define COMM_MAXB   512          // chunks (= blocks) per call
 #define COMM_NSCAL  64           // extra scalars riding in the same exchange (loss sum, hit count …)
-#define COMM_FLAGB  (COMM_MAXW * COMM_MAXB * 4)
+#define COMM_FLAGB  ((COMM_MAXW + 1) * COMM_MAXB * 4)       // [rank][chunk] push flags, then [chunk] flags of the owners' broadcasts (flag2)
 #define COMM_TIMEOUT_S_DEFAULT 60
 
 struct t4k_comm {
@@ -70,6 +70,13 @@ __device__ __forceinline__ float *slot_of(const CommDev &c, int where, int par, 
 }
 __device__ __forceinline__ uint32_t *flag_of(const CommDev &c, int where, int r, int b) {
     return reinterpret_cast<uint32_t*>(c.peer[where]) + r * COMM_MAXB + b;
+}
+__device__ __forceinline__ uint32_t *flag2_of(const CommDev &c, int where, int b) {
+    return reinterpret_cast<uint32_t*>(c.peer[where]) + COMM_MAXW * COMM_MAXB + b;
+}
+// landing zone of the owners' broadcasts: the rank-ordered SUM of a chunk, one copy per parity, behind the per-rank slots
+__device__ __forceinline__ float *gsum_of(const CommDev &c, int where, int par) {
+    return reinterpret_cast<float*>(c.peer[where] + COMM_FLAGB) + (int64_t)2 * c.world * (c.cap + COMM_NSCAL) + (int64_t)par * c.cap;
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
@@ -179,6 +186,113 @@ __global__ void __launch_bounds__(T4K_THREADS) k_dp_exchange(const __grid_consta
     if (tid == 0) c.epoch[b] = ep;
 }
 
+
+// ---- reduce-scatter + broadcast of the sums (world > 2).  The all-to-all push above sends every chunk to every rank: (world-1) x the arena
+// leaves each GPU through SM stores that share the machine with backprop (8 GPUs: 5.5 MB per rank and step).  Here chunk b has ONE owner,
+// rank b % world:
+//   k_dp_push_owner   every rank stores its chunk into slot[parity][rank] of the OWNER only and raises the owner's flag: 1 x the arena leaves
+//                     the GPU, early, on the side stream;
+//   k_dp_exchange_rs  later (rest of the arena: under the first layer's finish launch), one block per chunk on EVERY rank: the owner waits for
+//                     the world pushes, sums the slots in RANK ORDER and stores the sum into gsum[parity] of every rank (+ flag2); every rank
+//                     — the owner included — then waits for flag2, reads the sum from its own memory and runs the optimizer on the chunk.
+// One sum per chunk, computed once: the replicas receive identical bits by construction.  Optimizer state stays replicated (every rank steps
+// every chunk), so checkpoints and the single-GPU code paths are unchanged.  Two NVLink hops instead of one: used for the part of the arena
+// whose exchange is off the critical path; the first chunk keeps the one-hop all-to-all.
+__global__ void __launch_bounds__(T4K_THREADS) k_dp_push_owner(const __grid_constant__ CommDev c, const float *buf, int64_t n, int b0) {
+    __shared__ uint32_t s_ep, s_err;
+    pdl_wait(); pdl_trigger();
+    const int b = blockIdx.x + b0, tid = threadIdx.x;
+    if (tid == 0) { s_ep = c.epoch[b] + 1; s_err = c.epoch[COMM_MAXB]; }
+    __syncthreads();
+    if (s_err) return;
+    const uint32_t ep = s_ep;
+    const int par = (int)(ep & 1u), own = b % c.world;
+    const int64_t lo = (int64_t)b * c.ch4 * 4;
+    const int64_t hi = (lo + (int64_t)c.ch4 * 4 < n) ? lo + (int64_t)c.ch4 * 4 : n;
+    float *dst = slot_of(c, own, par, c.rank);
+    for (int64_t i = lo + 4 * tid; i < hi; i += 4 * T4K_THREADS) *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(buf + i);
+    __syncthreads();
+    if (tid == 0) { __threadfence_system(); *reinterpret_cast<volatile uint32_t*>(flag_of(c, own, c.rank, b)) = ep; }
+}
+
+// phase 0: both halves in one launch; phase 1: the owners' half only (wait for the pushes, sum, send the sums) — a few blocks per rank, launched
+// right behind the push so that the sums are already everywhere when phase 2 (everybody: optimizer on every chunk) runs at the end of backprop
+template<int KIND>
+__global__ void __launch_bounds__(T4K_THREADS) k_dp_exchange_rs(const __grid_constant__ CommDev c, float *buf, int64_t n, DpOpt o, int phase) {
+    __shared__ uint32_t s_ep, s_err;
+    pdl_wait(); pdl_trigger();
+    const int b = (phase == 1) ? o.b0 + ((c.rank - o.b0 % c.world + c.world) % c.world) + (int)blockIdx.x * c.world     // this rank's blockIdx.x-th own chunk at or past b0
+                               : (int)blockIdx.x + o.b0;
+    const int tid = threadIdx.x;
+    if (phase == 1 && (int64_t)b * c.ch4 * 4 >= n) return;
+    if (tid == 0) { s_ep = c.epoch[b] + 1; s_err = c.epoch[COMM_MAXB]; }
+    __syncthreads();
+    if (s_err) return;
+    const uint32_t ep = s_ep;
+    const int par = (int)(ep & 1u), own = b % c.world;
+    const int64_t lo = (int64_t)b * c.ch4 * 4;
+    const int64_t hi = (lo + (int64_t)c.ch4 * 4 < n) ? lo + (int64_t)c.ch4 * 4 : n;
+    auto timed_out = [&](int who) {
+        atomicCAS(c.epoch + COMM_MAXB, 0u, 1u + (uint32_t)who);
+        if (c.err_host) { *reinterpret_cast<volatile uint32_t*>(c.err_host) = 1u + (uint32_t)who; __threadfence_system(); }
+        s_err = 1u + (uint32_t)who;
+    };
+    if (own == c.rank && phase != 2) {
+        // ---- owner: the world pushes of this chunk -> rank-ordered sum -> every rank's gsum
+        if (tid < c.world) {
+            const uint32_t *f = flag_of(c, c.rank, tid, b);
+            const long long t0 = clock64();
+            while ((int32_t)(ld_acquire_sys(f) - ep) < 0) { __nanosleep(32); if (clock64() - t0 > c.spin_limit) { timed_out(tid); break; } }
+        }
+        __syncthreads();
+        if (s_err) return;
+        const float *mine = slot_of(c, c.rank, par, 0);
+        const int64_t sstride = c.cap + COMM_NSCAL;
+        for (int64_t i = lo + 4 * tid; i < hi; i += 4 * T4K_THREADS) {
+            float4 s = __ldcg(reinterpret_cast<const float4*>(mine + i));
+            for (int r = 1; r < c.world; r++) {
+                const float4 t = __ldcg(reinterpret_cast<const float4*>(mine + r * sstride + i));
+                s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+            }
+            #pragma unroll 1
+            for (int k = 1; k <= c.world; k++) *reinterpret_cast<float4*>(gsum_of(c, (c.rank + k) % c.world, par) + i) = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            for (int k = 1; k <= c.world; k++) *reinterpret_cast<volatile uint32_t*>(flag2_of(c, (c.rank + k) % c.world, b)) = ep;
+        }
+    }
+    if (phase == 1) return;
+    // ---- every rank: the owner's sum has landed here -> optimizer on the chunk
+    if (tid == 0) {
+        const uint32_t *f = flag2_of(c, c.rank, b);
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(f) - ep) < 0) { __nanosleep(32); if (clock64() - t0 > c.spin_limit) { timed_out(own); break; } }
+    }
+    __syncthreads();
+    if (s_err) return;
+    const float *sum = gsum_of(c, c.rank, par);
+    for (int64_t i = lo + 4 * tid; i < hi; i += 4 * T4K_THREADS) {
+        float4 s = __ldcg(reinterpret_cast<const float4*>(sum + i));
+        float4 g = *reinterpret_cast<const float4*>(o.G + i), m = make_float4(0, 0, 0, 0), v = m;
+        if (KIND == 0) {
+            int l = 0, h = o.nseg - 1;
+            while (l < h) { int mid = (l + h + 1) >> 1; if (o.seg[mid].off <= i) l = mid; else h = mid - 1; }
+            const float nw = (float)o.seg[l].Nw;
+            s.x = s.x / nw; s.y = s.y / nw; s.z = s.z / nw; s.w = s.w / nw;
+            if (o.mom) m = *reinterpret_cast<const float4*>(o.M + i);
+        } else { m = *reinterpret_cast<const float4*>(o.M + i); v = *reinterpret_cast<const float4*>(o.V + i); }
+        opt_step<KIND>(g.x, s.x, m.x, v.x, 1.0f, o.mom, o.p); opt_step<KIND>(g.y, s.y, m.y, v.y, 1.0f, o.mom, o.p);
+        opt_step<KIND>(g.z, s.z, m.z, v.z, 1.0f, o.mom, o.p); opt_step<KIND>(g.w, s.w, m.w, v.w, 1.0f, o.mom, o.p);
+        *reinterpret_cast<float4*>(o.G + i) = g;
+        *reinterpret_cast<float4*>(buf + i) = make_float4(0, 0, 0, 0);
+        if (KIND == 0) { if (o.mom) *reinterpret_cast<float4*>(o.M + i) = m; }
+        else { *reinterpret_cast<float4*>(o.M + i) = m; *reinterpret_cast<float4*>(o.V + i) = v; }
+    }
+    if (tid == 0) c.epoch[b] = ep;
+}
+
 // signal half of a push whose DATA travelled by copy engine (t4k_dp_push_dma): the chunks' epoch flags, stored to every rank (this one
 // included) once the copies of this stream have completed.  `par` is the slot parity the host addressed the copies with: it must be the
 // parity of the epoch the chunks are about to complete — a disagreement (an exchange the host did not count) raises the sticky error.
@@ -212,7 +326,7 @@ static void exchange_carveout() {
     static bool done[16];
     const int dev = cur_device();
     if (dev < 0 || dev >= 16 || done[dev]) return;
-    const void *k[] = {(const void*)k_dp_signal, (const void*)k_dp_exchange<-1, true>, (const void*)k_dp_exchange<0, true>, (const void*)k_dp_exchange<0, false>,
+    const void *k[] = {(const void*)k_dp_push_owner, (const void*)k_dp_exchange_rs<0>, (const void*)k_dp_exchange_rs<1>, (const void*)k_dp_exchange_rs<2>, (const void*)k_dp_signal, (const void*)k_dp_exchange<-1, true>, (const void*)k_dp_exchange<0, true>, (const void*)k_dp_exchange<0, false>,
                        (const void*)k_dp_exchange<1, true>, (const void*)k_dp_exchange<2, true>, (const void*)k_dp_exchange<3, true>};
     for (const void *f : k) if (cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) cudaGetLastError();
     done[dev] = true;
@@ -246,7 +360,7 @@ int t4k_comm_create(int rank, int world, int64_t cap_floats, t4k_comm_t *out, vo
     c->ch4 = (int)ch4;
     if (cudaGetDevice(&c->dev) != cudaSuccess) { cudaGetLastError(); delete c; return T4K_EINVAL; }
     exchange_carveout();
-    c->bytes = (size_t)COMM_FLAGB + (size_t)2 * world * (size_t)(c->cap + COMM_NSCAL) * 4;
+    c->bytes = (size_t)COMM_FLAGB + (size_t)2 * world * (size_t)(c->cap + COMM_NSCAL) * 4 + (size_t)2 * c->cap * 4;
     cudaError_t e = cudaMalloc((void**)&c->base, c->bytes);
     if (e != cudaSuccess) { cudaGetLastError(); delete c; return T4K_ENOMEM; }
     e = cudaMalloc((void**)&c->epoch, (COMM_MAXB + 8) * 4);
@@ -368,6 +482,42 @@ int64_t t4k_comm_chunk_floats(t4k_comm_t c) { return c ? (int64_t)c->ch4 * 4 : 0
 
 static int optim_dp_launch(t4k_comm_t c, int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
                            int64_t total, float lr, float b1, float b2, float wd, float *scal, int nscal, int64_t pushed_from, int b0, int grid, t4k_stream_t s);
+
+
+/* reduce-scatter flavour of the early push (world > 2): every chunk that STARTS at or beyond `from` goes to its owner (rank chunk % world) only.
+ * Must be followed, for the same chunks, by t4k_optim_multi_dp_rs — not by the all-to-all exchange.  Returns the first pushed float offset. */
+int64_t t4k_dp_push_owner(t4k_comm_t c, const float *DG, int64_t from, int64_t total, t4k_stream_t s) {
+    if (!ready(c) || !DG || from < 0 || total < 0 || total > c->cap || (total & 3) || !aligned16(DG)) return T4K_EINVAL;
+    const int64_t chf = (int64_t)c->ch4 * 4;
+    const int64_t b0 = (from + chf - 1) / chf, nb = (total + chf - 1) / chf;
+    if (b0 >= nb) return total;
+    launch_pdl(k_dp_push_owner, dim3((unsigned)(nb - b0)), dim3(T4K_THREADS), 0, STRM(s), devview(c), DG, total, (int)b0);
+    const int rc = check_launch();
+    return rc ? (rc > 0 ? -(int64_t)rc - 1000 : rc) : b0 * chf;
+}
+/* the owners sum, send the sums to every rank, every rank runs the optimizer: the chunks that start in [from, total), all pushed by t4k_dp_push_owner.
+ * phase 0: one launch; phase 1 then phase 2: the owners' half (a few blocks per rank: may run next to backprop) and the optimizer half apart */
+int t4k_optim_multi_dp_rs(t4k_comm_t c, int kind, float *G, float *DG, float *M, float *V, const t4k_seg_t *seg, int nseg,
+                          int64_t from, int64_t total, float lr, float b1, float b2, float wd, int phase, t4k_stream_t s) {
+    if (phase < 0 || phase > 2) return T4K_EINVAL;
+    if (!ready(c) || !G || !DG || !seg || nseg < 1 || total < 0 || total > c->cap || (total & 3) || from < 0 || from > total || !aligned16(DG) || !aligned16(G)) return T4K_EINVAL;
+    const int64_t chf = (int64_t)c->ch4 * 4;
+    const int64_t b0 = (from + chf - 1) / chf, nb = (total + chf - 1) / chf;
+    if (b0 >= nb) return 0;
+    DpOpt o{G, M, V, seg, nseg, true, OptP{lr, b1, b2, wd}, (int)b0, 0};
+    CommDev d = devview(c);
+    const dim3 grid(phase == 1 ? (unsigned)((nb - b0 + c->world - 1) / c->world) : (unsigned)(nb - b0));
+    switch (kind) {
+    case 0: o.mom = !(fabsf(b1) < DU_EPS); if (o.mom && !M) return T4K_EINVAL;
+            launch_pdl(k_dp_exchange_rs<0>, grid, dim3(T4K_THREADS), 0, STRM(s), d, DG, total, o, phase); break;
+    case 1: if (!M || !V || !aligned16(M) || !aligned16(V)) return T4K_EINVAL;
+            launch_pdl(k_dp_exchange_rs<1>, grid, dim3(T4K_THREADS), 0, STRM(s), d, DG, total, o, phase); break;
+    case 2: if (!M || !V || !aligned16(M) || !aligned16(V)) return T4K_EINVAL;
+            launch_pdl(k_dp_exchange_rs<2>, grid, dim3(T4K_THREADS), 0, STRM(s), d, DG, total, o, phase); break;
+    default: return T4K_EINVAL;
+    }
+    return check_launch();
+}
 
 /* t4k_dp_push with the data moved by the COPY ENGINES (one peer-to-peer cudaMemcpyAsync per rank, own slot included) instead of SM stores: the
  * push shares the machine with the rest of backprop without taking an SM from it; a one-block kernel then raises the chunks' flags.  Copy nodes

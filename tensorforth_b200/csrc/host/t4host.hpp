@@ -167,7 +167,7 @@ class Model {
     bool    _dp_early = false, _dp_join = false; int64_t _dp_pushed_from = -1;   // split exchange inside step_graph (early push on the side stream)
     void    _dp_push();
     uint32_t _dp_step = 0;             // exchanges issued on _comm so far (= the epoch of every chunk of the arena: selects the slot parity of a DMA push)
-    struct DpOptEarly { bool on = false, rest = false; int kind = 0; DU lr = 0, b1 = 0, b2 = 0, wd = 0; } _dpo;   // data parallel, inside step_graph: optimizer arguments for the early exchange
+    struct DpOptEarly { bool on = false, rest = false, rs = false; int kind = 0; DU lr = 0, b1 = 0, b2 = 0, wd = 0; } _dpo;   // data parallel, inside step_graph: optimizer arguments for the early exchange
     DU     *_pdup = nullptr; bool _want_pdup = false, _pdup_valid = false;   // step_graph: duplicate of the softmax output for the side-stream loss
     const StepExtra *_feed = nullptr; DU *_feed_hot = nullptr;   // step_graph: staged U8 batch still to be loaded (folded into the first fused block when there is one)
     void    _feed_fallback();

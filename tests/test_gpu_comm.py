@@ -229,6 +229,60 @@ def test_dma_push_then_fused_exchange(world, big):
         L.t4k_comm_destroy(ring.h[r])
 
 
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("world,big", [(4, 48000), (8, 20000), (3, 30000)])
+def test_reduce_scatter_exchange(kind, world, big):
+    """world > 2: every chunk past the first goes to ONE owner (t4k_dp_push_owner), the owners sum in rank order and send the sums to every rank,
+    every rank runs the optimizer (t4k_optim_multi_dp_rs); the first chunk keeps the one-hop all-to-all (t4k_optim_multi_dp_range).  Result: the
+    optimizer on the rank-summed gradient, bit for bit, replicas identical, step after step."""
+    L = lib()
+    warm(L)
+    segs = [(0, 92, 1), (92, 12, 1), (104, big, 1), (big + 104, 100, 1), (big + 204, 1000, 3), (big + 1204, 12, 1)]
+    total = big + 1216
+    seg = seg_table(segs)
+    ring = Ring(world, total)
+    # load the reduce-scatter kernels with nobody waiting (see warm())
+    r1 = Ring(1, total)
+    w_ = [torch.ones(total, device="cuda") for _ in range(4)]
+    assert L.t4k_dp_push_owner(r1.h[0], ptr(w_[1]), 104, total, r1.st(0)) >= 104
+    ok(L.t4k_optim_multi_dp_rs(r1.h[0], kind, ptr(w_[0]), ptr(w_[1]), ptr(w_[2]), ptr(w_[3]), ptr(seg), len(segs), L.t4k_comm_chunk_floats(r1.h[0]), total, 1e-3, 0.9, 0.999, 0.0, 0, r1.st(0)))
+    ok(L.t4k_optim_multi_dp_range(r1.h[0], kind, ptr(w_[0]), ptr(w_[1]), ptr(w_[2]), ptr(w_[3]), ptr(seg), len(segs), 0, L.t4k_comm_chunk_floats(r1.h[0]), total, 1e-3, 0.9, 0.999, 0.0, None, 0, 0, r1.st(0)))
+    r1.sync(); r1.close()
+    gen = torch.Generator(device="cuda").manual_seed(13 + kind)
+    G0, M0, V0 = torch.randn(total, device="cuda", generator=gen) * 0.1, torch.randn(total, device="cuda", generator=gen) * 0.01, torch.rand(total, device="cuda", generator=gen) * 1e-3
+    lr, b1, b2, wd = 1e-2, 0.9, 0.999, 1e-3
+    st0 = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    G = [G0.clone() for _ in range(world)]; M = [M0.clone() for _ in range(world)]; V = [V0.clone() for _ in range(world)]
+    Gr, Mr, Vr = G0.clone(), M0.clone(), V0.clone()
+    for step in range(3):
+        DG = [torch.randn(total, device="cuda", generator=gen) for _ in range(world)]
+        scal = [torch.tensor([1.0 + r], device="cuda") for r in range(world)]
+        DGr = ranked_sum(DG)
+        ok(L.t4k_optim_multi(kind, ptr(Gr), ptr(DGr), ptr(Mr), ptr(Vr), ptr(seg), len(segs), total, lr, b1, b2, wd, st0), "optim_multi")
+        torch.cuda.synchronize()
+        cut = [0] * world
+        for r in range(world):
+            cut[r] = L.t4k_dp_push_owner(ring.h[r], ptr(DG[r]), 104, total, ring.st(r))
+            assert 104 <= cut[r] < total
+        if step == 1:                                               # one launch per rank (phase 0)
+            for r in range(world):
+                ok(L.t4k_optim_multi_dp_rs(ring.h[r], kind, ptr(G[r]), ptr(DG[r]), ptr(M[r]), ptr(V[r]), ptr(seg), len(segs), cut[r], total, lr, b1, b2, wd, 0, ring.st(r)), "rs")
+        else:                                                       # the owners' half, then everybody's half (what the captured step does)
+            for ph in (1, 2):
+                for r in range(world):
+                    ok(L.t4k_optim_multi_dp_rs(ring.h[r], kind, ptr(G[r]), ptr(DG[r]), ptr(M[r]), ptr(V[r]), ptr(seg), len(segs), cut[r], total, lr, b1, b2, wd, ph, ring.st(r)), "rs phase %d" % ph)
+        for r in range(world):
+            ok(L.t4k_optim_multi_dp_range(ring.h[r], kind, ptr(G[r]), ptr(DG[r]), ptr(M[r]), ptr(V[r]), ptr(seg), len(segs), 0, cut[r], total,
+                                          lr, b1, b2, wd, ptr(scal[r]), 1, cut[r], ring.st(r)), "first chunk")
+        ring.sync()
+        for r in range(world):
+            assert torch.equal(G[r], Gr), "G step %d rank %d" % (step, r)
+            assert torch.equal(M[r], Mr) and (kind == 0 or torch.equal(V[r], Vr))
+            assert float(DG[r].abs().max()) == 0.0
+            assert scal[r].tolist() == [sum(1.0 + k for k in range(world))]
+    ring.close()
+
+
 def test_exchange_replays_inside_cuda_graphs():
     L = lib()
     warm(L)
