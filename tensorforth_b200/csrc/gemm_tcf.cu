@@ -357,8 +357,9 @@ bool gemm_tcf_ok(int tA, int tB, int M, int N, int K, int C, int batch) {
     // kernel wins when BOTH operands are K-contiguous (X @ W^T, the linear forward: 0.27 GFLOP 13 vs 16 us, 0.82 GFLOP 20 vs 33 us);
     // an operand that is contiguous along M/N goes through 4-byte scattered shared-memory stores and loses to the packed-plane
     // engine (dW, dX at 0.82 GFLOP: 24-28 vs 21 us), so those shapes are left to the other two engines.
-    // with the (opt-in, untimed) cluster variant the finish launch and the partial round trip are gone: let the 0.2-GFLOP class in too
-    return C == 1 && batch == 1 && tA == 0 && tB == 1 && M >= 32 && N >= 32 && K >= 32 && (double)M * N * K >= (tcf_cluster_on() ? 5.0e7 : 1.2e8);
+    // (the layer GEMM, gemm_tl.cu, now takes these shapes first; this engine stays for what it refuses.  The opt-in cluster variant below does not
+    // change the break-even: a shape that then fails cluster eligibility would run the plain path under its measured threshold — ADVICE r1)
+    return C == 1 && batch == 1 && tA == 0 && tB == 1 && M >= 32 && N >= 32 && K >= 32 && (double)M * N * K >= 1.2e8;
 }
 
 // defer: as gemm_simt — the caller runs its own split-K finish over defer->part [splits][M*N] (splits == 1: O holds the product)
@@ -403,10 +404,14 @@ int gemm_tcf(const float *A, const float *B, float *O, float alpha, float beta, 
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = (unsigned)splits;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, k_gemm_tcf<true>, ca);
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, k_gemm_tcf<true>, ca);
         int rc = check_launch();
-        if (defer) { defer->part = O; defer->splits = fused_epi ? 0 : 1; }
-        return rc;
+        if (le == cudaSuccess && rc == 0) {
+            if (defer) { defer->part = O; defer->splits = fused_epi ? 0 : 1; }
+            return 0;
+        }
+        cudaGetLastError();                                            // the cluster could not be co-scheduled (or the attribute is refused): the plain launch below
+        p.splits = splits;
     }
     if (splits > 1) {
         p.part = (float*)workspace((size_t)splits * M * N * sizeof(float), 7);
