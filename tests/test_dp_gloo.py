@@ -151,3 +151,50 @@ def test_c_abi_shard_info_matches_the_host_helper():
                 assert L.t4k_shard_info(n, world, r, C.byref(lo), C.byref(hi)) == 0
                 assert (lo.value, hi.value) == dp.shard_bounds(n, world, r)
     assert L.t4k_shard_info(8, 2, 2, C.byref(lo), C.byref(hi)) == lib.EINVAL
+
+
+class _FakeModel:
+    """what DataParallel touches of tensorforth_b200.host.Model, on the CPU: arena(), bn_channels(), dp_shard()"""
+
+    def __init__(self, bn):
+        self.bn, self.shard = bn, None
+
+    def arena(self):
+        return 0, 0, 16
+
+    def bn_channels(self):
+        return self.bn
+
+    def dp_shard(self, rank, world, comm_stat=None):
+        self.shard = (rank, world, comm_stat)
+
+
+def _dp_host_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plain = _FakeModel(0)
+        dp.DataParallel(plain, torch.device("cpu"))                 # every model learns which shard of the global batch it holds (dropout masks, BN statistics)
+        refused = False
+        try:
+            dp.DataParallel(_FakeModel(6), torch.device("cpu"))     # batch-norm statistics travel over CUDA peer memory: refused without a device, never silently per-shard
+        except NotImplementedError:
+            refused = True
+        if rank == 1:
+            q.put((plain.shard, refused))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_tells_the_model_its_shard_and_refuses_batchnorm_without_a_device():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_host_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    shard, refused = q.get()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert shard == (1, 2, None) and refused
