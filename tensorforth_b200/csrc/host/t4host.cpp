@@ -88,6 +88,11 @@ void Runtime::free(void *p) { if (p) cudaFreeAsync(p, (cudaStream_t)stream()); }
 // (measured slower: its waiting CTAs sit on SMs the conv block's backward needs).  Default by world size, from the measured steps (MNIST CNN,
 // N=512 per GPU, us per step dma / sm): 2 GPUs 79.5 / 82.0, 8 GPUs 111.1 / 96.1 — seven peer-to-peer copies per rank, even on seven streams,
 // outlast the 25 us of backward they hide under, while the push kernel spreads them over the SMs' store paths.
+static int opt_late_on() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("T4K_OPT_LATE"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v;
+}
 static int g_dp_rest = -1;
 static int dp_rest_on() {                                  // T4K_DP_REST=0: the end of the step exchanges the whole arena in one launch, as in round 1
     int &v = g_dp_rest;
@@ -564,9 +569,19 @@ int Model::_bfused(int i) {                                // i = index of the b
     if (_oe.on && _oe.rest && !_oe.first && train && df.data == _DG && db.data > _DG && db.data < _DG + _first_end) {
         // the block of the FIRST parameter layer, the rest of the arena already stepped on the side stream: its finish launch steps its own segments
         t4k_fused_opt_t fo{_oe.kind, _oe.lr, _oe.b1, _oe.b2, _oe.wd, _G, _M, _V, 0, (int64_t)(db.data - _DG), (int32_t)f.N(), (int32_t)in.grad[1]->N()};
+        if (_oe.late) t4k_conv_pool_relu_bwd_mid_event((void*)g_mid);
         rc = t4k_conv_pool_relu_bwd_opt(dy.data, flat_dst, po.grad[4]->data, po.data, co.data, in.data, dx.data, f.data, df.data, db.data,
                                         in.N(), in.H(), in.W(), in.C(), co.H(), co.W(), co.C(), f.H(), in.stride[0], in.stride[2], train, &fo, ST);
+        t4k_conv_pool_relu_bwd_mid_event(nullptr);
         if (rc == 0) _oe.first = true;
+        if (rc == 0 && _oe.late) {                          // the rest of the arena: stepped on the side stream from the end of the block's main kernel
+            _oe.late = false;
+            cudaStreamWaitEvent(g_stream2, g_mid, 0);
+            KCHK(t4k_optim_multi_range(_oe.kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, _first_end, (int64_t)_total, _oe.lr, _oe.b1, _oe.b2, _oe.wd,
+                                       (t4k_stream_t)g_stream2));
+            cudaEventRecord(g_join, g_stream2);
+            _side_join = true;
+        }
     }
     // data parallel, the block of the FIRST parameter layer, the rest of the arena already pushed to the peers (copy engines, _dp_push): the
     // exchange + optimizer of that rest runs on the side stream from the moment the block's main kernel is done (it must not take SMs from it:
@@ -684,7 +699,12 @@ Model &Model::backprop(Tensor &tgt) {
     for (; i >= 0; j++) {
         const t4_layer fn = _layers[i]->grad_fn;
         if (_dp_early && _dp_pushed_from < 0 && i < _second_layer) _dp_push();     // every gradient but the first parameter layer's is final
-        if (_oe.on && !_oe.rest && i < _second_layer && (int64_t)_total > _first_end) _opt_push();
+        if (_oe.on && !_oe.rest && i < _second_layer && (int64_t)_total > _first_end) {
+            // T4K_OPT_LATE=1: do not launch the rest-of-arena optimizer next to the conv block's main kernel (which fills the machine in exactly one
+            // wave: every CTA of another kernel resident on an SM displaces one of its CTAs) but from the block's mid event, under its finish launch
+            if (opt_late_on() && j > 0 && (fn == T4K_L_FLATTEN || fn == T4K_L_RELU)) { _oe.rest = true; _oe.late = true; }
+            else _opt_push();
+        }
         const int adv = (j > 0 && (fn == T4K_L_FLATTEN || fn == T4K_L_RELU)) ? _bfused(i) : 0;
         if (adv) { i -= adv; continue; }
         if (_skip_flat_copy) {                              // the fused block did not take the flatten: rejoin before the per-layer path touches it
@@ -1046,6 +1066,9 @@ Model &Model::_gradient(t4_optimizer op, DU lr, DU b1, DU b2, DU wd) {     // gr
         KCHK(t4k_optim_multi_dp((t4k_comm_t)_comm, kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, (int64_t)_total, lr, b1, b2, wd,
                                 _dp_scal, _dp_nscal, _dp_pushed_from > 0 ? _dp_pushed_from : (int64_t)_total, ST));
         _dp_pushed_from = -1; _dp_step++;
+    }
+    else if (_oe.on && _oe.rest && _oe.late) {                              // deferred and never picked up by a fused first block: the whole arena here
+        KCHK(t4k_optim_multi(kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, (int64_t)_total, lr, b1, b2, wd, ST));
     }
     else if (_oe.on && _oe.rest) {                                          // the side stream stepped [first_end, total) during backprop (_opt_push)
         if (!_oe.first) KCHK(t4k_optim_multi_range(kind, _G, _DG, _M, _V, (const t4k_seg_t*)_seg_dev, _nseg, 0, _first_end, lr, b1, b2, wd, ST));

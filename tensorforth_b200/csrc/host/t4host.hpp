@@ -180,7 +180,7 @@ class Model {
     // optimizer split inside step_graph (single GPU): once every gradient but the first parameter layer's is final, the optimizer of the rest of
     // the arena runs on the side stream under the first layers' backward (_opt_push); the fused conv block applies the step to its own filter /
     // bias in the launch that finishes them (t4k_conv_pool_relu_bwd_opt), so the critical path ends one launch earlier
-    struct OptEarly { bool on = false, rest = false, first = false; int kind = 0; DU lr = 0, b1 = 0, b2 = 0, wd = 0; } _oe;
+    struct OptEarly { bool on = false, rest = false, first = false, late = false; int kind = 0; DU lr = 0, b1 = 0, b2 = 0, wd = 0; } _oe;
     void    _opt_push();
     bool    _side_join = false, _skip_flat_copy = false;   // backprop: work pending on the side stream / flatten copy already issued there
     DU     *_loss_pin = nullptr; void *_loss_ev[2] = {nullptr, nullptr}; unsigned _tstep = 0;   // train_step read-back ring
