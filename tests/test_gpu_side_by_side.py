@@ -47,3 +47,26 @@ def test_object_store_beyond_2gib_from_forth():
     assert abs(val("conv out max=") - 9 * 64 * 0.5 * 0.001) < 1e-4          # interior pixel: all nine taps in the image
     assert abs(val("conv out min=") - 4 * 64 * 0.5 * 0.001) < 1e-4          # corner pixel: four taps
     assert val("dw sum/1e6=") > 0
+
+
+@pytest.mark.gpu
+def test_dconv2d_word_through_the_reference_vm():
+    """the conv-transpose layer driven from Forth text: the reference's VM and Model::add (unmodified) on integration/model_shim.cu's L_DCONV cases
+    (t4k_dconv2d_fwd / _bwd); closed-form values for constant tensors (see the script's header)"""
+    if not os.path.exists(NEW):
+        pytest.skip("integration/_build/ten4_b200 not built")
+    src = open(os.path.join(ROOT, "integration", "scripts_b200", "dconv2d.4th")).read()
+    p = subprocess.run([NEW], input=src, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    out = p.stdout
+    sys.stdout.write(out[-800:])
+    import re
+
+    def val(tag):
+        m = re.search(re.escape(tag) + r"\s*(-?[0-9.]+(?:e[-+]?\d+)?)", out)
+        assert m, (tag, out[-800:], p.stderr[-300:])
+        return float(m.group(1))
+    assert abs(val("out max=") - 0.16) < 1e-4 and abs(val("out min=") - 0.04) < 1e-4
+    # every input element reaches 16 taps (4 x 4), minus those that fall outside the 8 x 8 output: sum over the output = 0.005 * 6 * sum over inputs of its taps inside
+    assert abs(val("out sum=") - 2 * 6 * 8 * 0.005 * (4 * 9 + 8 * 12 + 4 * 16)) < 1e-2
+    assert abs(val("dx max=") - 16 * 6 * 0.01) < 1e-4
+    assert abs(val("db sum=") - 2 * 8 * 8 * 6) < 1e-2
