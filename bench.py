@@ -524,6 +524,7 @@ def main():
         losses_seen.clear()
         wins_e2e.append(window(lambda: e2e_run(args.steps)))
         assert len(losses_seen) == args.steps
+    e2e_last_loss = (losses_seen[-1] / (world if fused else 1)) if losses_seen else None      # what the host read for the last step of the last window
     wins_e2e.sort()
     ms_e2e = wins_e2e[len(wins_e2e) // 2] if len(wins_e2e) & 1 else 0.5 * (wins_e2e[len(wins_e2e) // 2 - 1] + wins_e2e[len(wins_e2e) // 2])
     e2e = {"value": BATCH * world * args.steps / (ms_e2e / 1e3), "unit": "samples/s",
@@ -532,7 +533,7 @@ def main():
                    "(u8-128)/128 + one-hot, folded into the step's first kernel (t4k_conv_pool_relu_fwd_feed) -> train step -> loss D2H read on the host (pipelined by one step); one host call per iteration.  "
                    "It can come out a hair ABOVE `value`: the feed kernel reads 0.4 MB of U8 where the resident-input step copies 1.6 MB of FP32 into the model's input layer, "
                    "and the H2D copy + loss read-back overlap the step on their own streams",
-           "window_ms": [round(w, 4) for w in wins_e2e]}
+           "window_ms": [round(w, 4) for w in wins_e2e], "last_loss_read_on_host": e2e_last_loss}
 
     # ---- strong scaling: the SAME global batch of 512 cut into world shards of 512/world samples, one data-parallel step
     strong = None

@@ -334,6 +334,8 @@ int t4k_comm_status(t4k_comm_t c);      /* 0 healthy; k>0: a wait for rank k-1 t
                                          * step on a half-summed gradient) and every later exchange on this communicator is a no-op */
 int t4k_comm_poll(t4k_comm_t c);        /* the same word read from mapped host memory, no synchronisation (cheap enough for every step) */
 int64_t t4k_comm_capacity(t4k_comm_t c);
+int t4k_comm_scalar_mirror(t4k_comm_t c, float *pinned);   /* exchanges launched / captured from now on also store the summed scalars into this page-locked host
+                                                             * buffer (unified addressing): the host reads the global loss with no copy node behind the step; NULL = off */
 int t4k_shard_info(int64_t n, int world, int rank, int64_t *lo, int64_t *hi);   /* batch shard of a rank: samples [lo, hi) (no device needed) */
 /* buf[i] = sum over ranks of buf[i], in place, n <= capacity */
 int t4k_allreduce_sum(t4k_comm_t c, float *buf, int64_t n, t4k_stream_t s);

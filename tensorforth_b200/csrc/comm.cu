@@ -45,6 +45,7 @@ struct t4k_comm {
     bool ipc[COMM_MAXW];
     uint32_t *epoch;             // [COMM_MAXB] per-chunk epoch counters + [COMM_MAXB] sticky error word (local device memory)
     uint32_t *err_host, *err_dev;    // the same error word in mapped pinned host memory (host pointer / device alias): polled without a sync
+    float *scal_mirror;              // t4k_comm_scalar_mirror: pinned host floats that receive the summed scalars straight from the exchange kernel
     long long spin_limit;        // clock64 ticks a wait may go without progress
     size_t bytes;
     cudaStream_t cs[COMM_MAXW];  // t4k_dp_push_dma: one copy stream per destination rank (the peer-to-peer copies of a push run side by side)
@@ -60,6 +61,7 @@ struct CommDev {
     long long spin_limit;
     int64_t cap;
     int rank, world, ch4;
+    float *scal_mirror;          // pinned host memory (unified addressing): the summed scalars are ALSO stored here — no copy node behind the step
 };
 struct DpOpt { float *G, *M, *V; const t4k_seg_t *seg; int nseg; bool mom; OptP p;
                int b0;                  // first chunk of this launch (push-only launches start past the late chunks)
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(T4K_THREADS) k_dp_exchange(const __grid_consta
         float s = __ldcg(mine + c.cap + tid);
         for (int r = 1; r < c.world; r++) s += __ldcg(mine + r * sstride + c.cap + tid);
         scal[tid] = s;
+        if (c.scal_mirror) c.scal_mirror[tid] = s;
     }
     if (tid == 0) c.epoch[b] = ep;
 }
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(T4K_THREADS) k_dp_signal(const __grid_constant
 static CommDev devview(const t4k_comm *c) {
     CommDev d;
     for (int i = 0; i < COMM_MAXW; i++) d.peer[i] = c->peer[i];
-    d.epoch = c->epoch; d.err_host = c->err_dev; d.spin_limit = c->spin_limit; d.cap = c->cap; d.rank = c->rank; d.world = c->world; d.ch4 = c->ch4;
+    d.epoch = c->epoch; d.err_host = c->err_dev; d.spin_limit = c->spin_limit; d.cap = c->cap; d.rank = c->rank; d.world = c->world; d.ch4 = c->ch4; d.scal_mirror = c->scal_mirror;
     return d;
 }
 // An SM changes its L1 / shared-memory split only when it is empty.  Exchange kernels WAIT — resident on every SM — and would pin the split
@@ -447,6 +450,10 @@ int t4k_comm_poll(t4k_comm_t c) {
 }
 
 int64_t t4k_comm_capacity(t4k_comm_t c) { return c ? c->cap : 0; }
+
+/* the exchanges launched (or captured) from now on also store the summed scalars into `pinned` — page-locked host memory, reachable from the device
+ * under unified addressing — so that a training loop reads the global loss on the host without a copy node behind the step (NULL: off) */
+int t4k_comm_scalar_mirror(t4k_comm_t c, float *pinned) { if (!c) return T4K_EINVAL; c->scal_mirror = pinned; return 0; }
 
 /* samples [lo, hi) of a batch of n owned by `rank` of `world`: contiguous, sizes differ by at most one, first ranks larger (host-only) */
 int t4k_shard_info(int64_t n, int world, int rank, int64_t *lo, int64_t *hi) {

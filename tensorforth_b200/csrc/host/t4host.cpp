@@ -93,6 +93,11 @@ static int opt_late_on() {
     if (v < 0) { const char *e = getenv("T4K_OPT_LATE"); v = (e && e[0] == '1') ? 1 : 0; }
     return v;
 }
+static int dp_mirror_on() {                                // T4K_DP_MIRROR=0: the loss read-back of a data-parallel step is a copy node behind the exchange, as before
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("T4K_DP_MIRROR"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
 static int g_dp_rest = -1;
 static int dp_rest_on() {                                  // T4K_DP_REST=0: the end of the step exchanges the whole arena in one launch, as in round 1
     int &v = g_dp_rest;
@@ -1275,12 +1280,16 @@ int Model::_step_graph(Tensor &input, Tensor &tgt, t4_loss lop, DU *loss_dev, t4
         }
         backprop(tgt);
         _dp_early = false;
+        // data parallel with a pinned loss slot: the exchange kernel itself stores the summed loss there (no copy node behind the step)
+        const bool mirror = _comm && (int)op >= 0 && x.loss_pin && loss_dev && _dp_scal == loss_dev && _dp_nscal >= 1 && dp_mirror_on();
+        if (_comm) t4k_comm_scalar_mirror((t4k_comm_t)_comm, mirror ? x.loss_pin : nullptr);
         if ((int)op >= 0) {                                // op < 0 — data parallel over NCCL: the caller all-reduces DG, then calls the optimizer
             switch (op) { case OPTI_SGD: case OPTI_SGDM: sgd(lr, b1); break; case OPTI_ADAM: adam(lr, b1, b2); break; default: adamw(lr, wd, b1, b2); }
         }
         if (_side_join) { cudaStreamWaitEvent((cudaStream_t)ST, g_join, 0); _side_join = false; }   // side-stream work of this step (backprop joins its own)
         if (early_loss) cudaStreamWaitEvent((cudaStream_t)ST, g_join, 0);
-        else if (x.loss_pin && loss_dev && !(side_loss && !_comm)) cudaMemcpyAsync(x.loss_pin, loss_dev, sizeof(DU), cudaMemcpyDeviceToHost, (cudaStream_t)ST);
+        else if (x.loss_pin && loss_dev && !(side_loss && !_comm) && !mirror) cudaMemcpyAsync(x.loss_pin, loss_dev, sizeof(DU), cudaMemcpyDeviceToHost, (cudaStream_t)ST);
+        if (_comm && mirror) t4k_comm_scalar_mirror((t4k_comm_t)_comm, nullptr);
     };
     if (loss_dev && !_pdup) _pdup = (DU*)Runtime::alloc((size_t)(*this)[-1].numel * sizeof(DU) + 64);   // not inside the capture below
     if (!_hscratch && fuse && train) {                    // train tail: linear -> mask activation -> small linear -> softmax at the end of the model

@@ -106,6 +106,7 @@ PROTOTYPES = {
     "t4k_optim_multi_dp_range": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _l, _l, _l, _f, _f, _f, _f, _p, _i, _l, _p]),
     "t4k_conv_pool_relu_bwd_mid_event": (_i, [_p]),
     "t4k_comm_chunk_floats": (_l, [_p]),
+    "t4k_comm_scalar_mirror": (_i, [_p, _p]),
     "t4k_dp_push_owner": (_l, [_p, _p, _l, _l, _p]),
     "t4k_optim_multi_dp_rs": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _l, _l, _f, _f, _f, _f, _i, _p]),
     "t4k_dp_push_dma": (_l, [_p, _p, _l, _l, C.c_uint32, _p]),
