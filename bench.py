@@ -9,6 +9,9 @@ Metric (BASELINE.json): MNIST-CNN training samples/s — the CNN of examples/t4_
 one step = forward + loss.ce + backprop + nn.adam on synthetic 28x28x1 data.  One JSON line on stdout (rank 0).
 
 `value`   : device-timed (CUDA events on the launching stream, max over ranks), inputs resident in HBM, one CUDA-graph launch per step.
+            The timed region is EXACTLY --steps steps between two events (barrier + synchronize on both sides); a 20-step window of this
+            workload is 1.4 ms, so the window is repeated (up to 15 times) and the MEDIAN window is reported — every window is listed
+            under `timing`.
 `e2e`     : the same step through the public host API the way a training loop over a dataset runs: every step's mini-batch starts in
             pinned host memory as U8 pixels + U8 labels (what an MNIST loader holds), Dataset.stage() copies the bytes, the device
             normalises and one-hots them (inside the step's first kernel), and every step's loss is read back on the host (Model.train_step).
@@ -16,7 +19,8 @@ one step = forward + loss.ce + backprop + nn.adam on synthetic 28x28x1 data.  On
             profiles/ncu_traffic.json), timed live (graph of 20 launches replayed between two events on its stream), against the
             measured HBM bandwidth; `calls` lists every call of the step the same way.
 `extras`  : the other headline numbers — GEMM 4096^3 (both tensor-core engines, with their measured error), conv2d 3x3 64->64 @56x56 at
-            the full N=8192 sharded over the ranks, one GAN iteration of examples/t4_40b.4th at N=1024 per GPU.
+            the full N=8192 sharded over the ranks, one GAN iteration of examples/t4_40b.4th at N=1024 per GPU; N > 1: a strong-scaling
+            line (the same global batch of 512 cut into N shards).
 `cpu_baseline`: the C oracle (oracle/, "port") timed on the host cores on a bounded sample — reported, not a target.
 N > 1     : one rank per GPU (torchrun); the gradient exchange is fused into the optimizer kernel over NVLink peer memory
             (`--exchange nccl` selects the NCCL all-reduce arm).
