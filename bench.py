@@ -641,7 +641,8 @@ def main():
     for name, fn, nbytes in kernels:
         n0 = L.t4k_launch_count(); fn(None); nl = L.t4k_launch_count() - n0
         us = gtime(fn)
-        ktab.append({"call": name, "launches": int(nl), "us": round(us, 2), "alg_MB": round(nbytes / 1e6, 2), "GBps": round(nbytes / us / 1e3, 1)})
+        ktab.append({"call": name, "launches": int(nl), "us": round(us, 2), "alg_MB": round(nbytes / 1e6, 2), "GBps": round(nbytes / us / 1e3, 1),
+                     "hbm_frac": round(nbytes / us / 1e3 / pk["hbm_gbs"], 4)})
     # The dominant KERNEL of the step is the largest single launch of the committed ncu launch list (profiles/: k_cpr2_bwd, 18 % of the
     # step; each of the three GEMM launches is 11-12 %), named with its call in profiles/ncu_traffic.json; the calls of this table that
     # take several launches (linear_bwd: dW GEMM + split-K finish + dX GEMM, the first two on a side stream in the real step) are not
@@ -661,7 +662,18 @@ def main():
                 "frac": round(dom["GBps"] / pk["hbm_gbs"], 4), "traffic": traffic, "traffic_src": traffic_src, "peak_src": pk["src"] + " (burst copy bandwidth)",
                 "alg_bytes_per_launch": int(dom["alg_MB"] * 1e6), "us_per_launch": dom["us"],
                 "step_call_sum_us": round(sum(r["us"] for r in ktab), 1),
-                "step_hbm_floor_us": round(sum(r["alg_MB"] for r in ktab) * 1e6 / (pk["hbm_gbs"] * 1e9) * 1e6, 1)}
+                "step_hbm_floor_us": round(sum(r["alg_MB"] for r in ktab) * 1e6 / (pk["hbm_gbs"] * 1e9) * 1e6, 1),
+                "note": "dominant = the largest call of the step in this live, warm, graph-replayed timing (the conv block's backward: k_cpr2_bwd + its short finish "
+                        "launch, timed together, so `achieved` is conservative for the kernel alone).  In the cold-cache serialised ncu list (profiles/r02_launches_step.txt) "
+                        "the train-tail launch of the layer GEMM is the larger single kernel (24.7 % vs 20.3 %); it is latency-bound, not throughput-bound — its line is `layer_gemm`"}
+    # the two layer-GEMM launches of the step against the tensor roofline (3xTF32: three TF32 MMAs per FP32 product): latency-bound by design
+    tf32x3_peak = pk["bf16_tflops"] / 2 / 3
+    lg = []
+    for row, gflop in ((ktab[1], 2.0 * N * (1960 * 100 + 2 * 100 * 10) / 1e9), (ktab[4], 2.0 * 2.0 * N * 1960 * 100 / 1e9)):
+        tf = gflop / row["us"] * 1e3                 # GFLOP per us = PFLOP/s; x 1e3 = TFLOP/s
+        lg.append({"call": row["call"], "us": row["us"], "gflop": round(gflop, 4), "tflops": round(tf, 2), "peak": round(tf32x3_peak, 1),
+                   "frac": round(tf / tf32x3_peak, 4), "hbm_frac": row["hbm_frac"]})
+    roofline["layer_gemm"] = lg
 
     out = {"metric": "mnist_cnn_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
