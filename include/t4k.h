@@ -143,20 +143,21 @@ int t4k_gemm_tl_trace(long long *dev16);
 int t4k_bias(const float *B, float *Y, int N, int E0, t4k_stream_t s);
 /* Model::_flinear (forward.cu:158-198): Y[N,E0] = X[N,E1] @ W[E0,E1]^T + B[E0]  (GEMM + fused bias) */
 int t4k_linear_fwd(const float *X, const float *W, const float *B, float *Y, int N, int E0, int E1, t4k_stream_t s);
-/* _flinear + the following _factivate in one pass (the bias, activation and mask ride in the GEMM's split-K finish):
+/* _flinear + the following _factivate (forward.cu:158-209) in one pass (the bias, activation and mask ride in the GEMM's split-K finish):
  * Y = X @ W^T + B (the linear layer's output tensor), A = act(Y), F = saved derivative / mask; layer as t4k_activate_fwd */
 int t4k_linear_act_fwd(int layer, const float *X, const float *W, const float *B, float *Y, float *A, float *F, float alpha,
                        int N, int E0, int E1, t4k_stream_t s);
 /* classifier head, forward: small linear (E0 <= 32, W <= 40 KB) + bias + row softmax in one launch (forward.cu:158-198,231-243):
  * Y = X @ W^T + B, P = softmax(Y).  T4K_ENOSUP when the head is not small (caller: t4k_linear_fwd + t4k_softmax_fwd) */
 int t4k_mlp_head_fwd(const float *X, const float *W, const float *B, float *Y, float *P, int N, int E0, int E1, t4k_stream_t s);
-/* hidden linear + activation + classifier head in two launches (GEMM, then split-K finish + bias + activation + small linear + softmax):
+/* hidden linear + activation + classifier head (forward.cu:158-243) in two launches (GEMM, then split-K finish + bias + activation + small linear + softmax):
  * X [N,E1] -> Y1 = X @ W1^T + B1 [N,EH], A1 = act(Y1), F1 = saved derivative -> Y2 = A1 @ W2^T + B2 [N,E0], P = softmax(Y2) (+ Pdup).
  * Same tensors, same bits as t4k_linear_act_fwd followed by t4k_mlp_head_fwd.  T4K_ENOSUP when EH > 128, E0 > 32 or the layer is
  * not relu / tanh / sigmoid / selu / leakyrelu / elu: use the two calls. */
 int t4k_linear_act_head_fwd(int layer, const float *X, const float *W1, const float *B1, float *Y1, float *A1, float *F1, float alpha,
                             const float *W2, const float *B2, float *Y2, float *P, float *Pdup, int N, int EH, int E1, int E0, t4k_stream_t s);
-/* the same, with the probabilities also written to Pdup [N,E0] (may be NULL): Model::backprop turns P into p - y in place, so a
+/* the same (forward.cu:158-198,231-243), with the probabilities also written to Pdup [N,E0] (may be NULL; the reference's Model::loss works on a
+ * duplicate too, loss.cpp:129-132): Model::backprop turns P into p - y in place, so a
  * caller that wants the loss kernel to overlap the backward pass (second stream) lets it read the duplicate */
 int t4k_mlp_head_fwd_dup(const float *X, const float *W, const float *B, float *Y, float *P, float *Pdup, int N, int E0, int E1, t4k_stream_t s);
 /* k_activate (nmath.cu:37-70, forward.cu:201-209): writes O and the saved derivative/mask F.
@@ -190,7 +191,7 @@ int t4k_dbias(const float *dY, float *dB, int N, int E0, t4k_stream_t s);
  * dX may alias X's buffer?  NO — dW needs X; pass distinct buffers or dX==X (handled: dW first). */
 int t4k_linear_bwd(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
                    int N, int E0, int E1, int train, t4k_stream_t s);
-/* as t4k_linear_bwd; skip_db != 0 leaves dB alone (it was accumulated by t4k_mlp_head_bwd) */
+/* as t4k_linear_bwd (backprop.cu:194-254); skip_db != 0 leaves dB alone (it was accumulated by t4k_mlp_head_bwd) */
 int t4k_linear_bwd_ex(const float *X, const float *W, const float *dY, float *dX, float *dW, float *dB,
                       int N, int E0, int E1, int train, int skip_db, t4k_stream_t s);
 /* _blinear followed by the _bactivate of the activation layer in front of it (backprop.cu:194-263) with the mask multiply in the dX
@@ -206,7 +207,7 @@ int t4k_linear_bwd_act(const float *X, const float *W, const float *dY, float *d
  * concurrently with t4k_mlp_head_bwd.  T4K_ENOSUP: E2 > 32, EH > 128, EH % 4, or a shape the layer GEMM does not take. */
 int t4k_linear_dx_from_head(const float *P, const float *T, const float *W2, const float *F1, const float *W1, float *dX,
                             int N, int E2, int EH, int E1, t4k_stream_t s);
-/* the same for BOTH products of the hidden layer, ONE launch: dX = A @ W1 and dW1 += A^T @ X with A generated K-major for the one and
+/* the same (backprop.cu:76-140,194-263) for BOTH products of the hidden layer, ONE launch: dX = A @ W1 and dW1 += A^T @ X with A generated K-major for the one and
  * M-major for the other (two problems share the grid of the layer GEMM).  X must not alias dX (Model::backprop passes the flatten layer's
  * duplicate of X).  T4K_ENOSUP: as above, or the two problems do not fit one co-resident wave. */
 int t4k_linear_bwd_from_head(const float *P, const float *T, const float *W2, const float *F1, const float *X, const float *W1,
@@ -222,7 +223,7 @@ int t4k_linear_act_head_train(int layer, const float *X, const float *W1, const 
                               const float *W2, const float *B2, float *Ylin, float *P, float *Pdup, const float *T,
                               float *scratch, int *ncta, int N, int EH, int E1, int E0, t4k_stream_t s);
 int t4k_head_grad_finish(const float *scratch, int ncta, int E0, int EH, float *dW2, float *dB2, float *dB1, t4k_stream_t s);
-/* dX = dY @ W and dW += dY^T @ X of Model::_blinear in ONE launch (two problems share the layer GEMM's grid); X must not alias dX.
+/* dX = dY @ W and dW += dY^T @ X of Model::_blinear (backprop.cu:239-247) in ONE launch (two problems share the layer GEMM's grid); X must not alias dX.
  * T4K_ENOSUP when a product is outside the layer GEMM's class or the pair does not fit one co-resident wave: use t4k_linear_bwd_ex */
 int t4k_linear_bwd_pair(const float *X, const float *W, const float *dY, float *dX, float *dW, int N, int E0, int E1, t4k_stream_t s);
 /* classifier head, backward, one launch (backprop.cu:76-140,194-263), E0 <= 32, E1 <= 128 else T4K_ENOSUP:

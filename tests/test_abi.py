@@ -77,3 +77,24 @@ def test_host_library_exports_every_symbol_of_t4host_h():
     from tensorforth_b200 import host
     unknown = [s for s in host.PROTOTYPES if s not in syms]
     assert not unknown, unknown
+
+
+def test_integration_index_matches_header():
+    """INTEGRATION.md §8 lists every function include/t4k.h declares, with the reference lines the header cites for it
+    (regenerate with `python bench_scripts/abi_index.py --write`); only library plumbing may be without a reference counterpart"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("abi_index", os.path.join(ROOT, "bench_scripts", "abi_index.py"))
+    ai = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ai)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = doc[doc.index(ai.BEGIN) + len(ai.BEGIN):doc.index(ai.END)].strip()
+    assert block == ai.table().strip(), "INTEGRATION.md §8 is stale: python bench_scripts/abi_index.py --write"
+    ents = ai.entries()
+    funcs = [s for s in header_symbols() if s not in ("t4k_comm",)]
+    listed = {e[0] for e in ents}
+    missing = [s for s in funcs if s not in listed and not s.endswith("_t")]
+    assert not missing, missing
+    uncited = sorted(e[0] for e in ents if not e[2])
+    plumbing = {"t4k_version", "t4k_strerror", "t4k_device_count", "t4k_sm_count", "t4k_sync", "t4k_launch_count", "t4k_set_workspace_bank",
+                "t4k_set_carveout", "t4k_set_pdl", "t4k_set_conv_engine"}
+    assert set(uncited) <= plumbing, set(uncited) - plumbing
