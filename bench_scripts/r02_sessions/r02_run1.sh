@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 1: first contact of the layer GEMM + the evidence the round-1 verdict asked for (GEMM 4096^3 ncu, GAN launch list)
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out && O=gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out && O=gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/r02_run1_smi.txt 2>&1
 timeout 180 python bench_scripts/tl_smoke.py > $O/r02_tl_smoke.txt 2>&1; rc=$?; echo "tl_smoke rc=$rc" | tee -a $O/r02_tl_smoke.txt
 if [ $rc -ne 0 ]; then export T4K_GEMM_TL=0; echo "TL engine disabled for the rest of this run"; fi

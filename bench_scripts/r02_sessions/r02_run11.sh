@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out && O=gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out && O=gpurun_out
 timeout 900 python -m pytest tests/test_gpu_dp_multi.py tests/test_gpu_comm.py tests/test_gpu_dp_lanes.py tests/test_gpu_model.py -m gpu -q 2>&1 | grep -v "^$" > $O/r02_t17.log; grep -n "^E  .*Error\|^E   .*assert\|^FAILED\|passed\|failed" $O/r02_t17.log | head -20
 for c in 100 -1; do
 T4K_CARVEOUT=$c timeout 300 python bench.py --steps 100 --no-extras --no-cpu-baseline > $O/r02_b1_c$c.json 2> $O/r02_b1.err

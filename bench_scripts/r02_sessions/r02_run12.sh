@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out && O=gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out && O=gpurun_out
 timeout 900 python -m pytest tests/test_gpu_dp_multi.py tests/test_gpu_comm.py tests/test_gpu_dp_lanes.py -m gpu -q 2>&1 | grep -v "^$" > $O/r02_t18.log; grep -n "^E  .*Error\|^E   .*assert\|^FAILED\|passed\|failed" $O/r02_t18.log | head -20
 for m in dma sm range; do
 T4K_DP_EARLY=$m timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 100 --no-extras --no-cpu-baseline > $O/r02_b2_$m.json 2> $O/r02_b2.err

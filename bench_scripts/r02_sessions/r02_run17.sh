@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out && O=gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out && O=gpurun_out
 for z in 0 1 0 1; do
 T4K_CPR_ZERO=$z timeout 600 python bench.py --steps 100 --no-cpu-baseline --no-extras > $O/r02_b1_z$z.json 2> $O/r02_b1.err
 python -c "

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out && O=gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out && O=gpurun_out
 timeout 120 python bench_scripts/tl_trace.py > $O/r02_tl_trace2.txt 2>&1; cat $O/r02_tl_trace2.txt
 timeout 1500 python -m pytest tests/test_gpu_kernels.py -x -q > $O/r02_t5.log 2>&1; echo "rc=$?" >> $O/r02_t5.log; tail -4 $O/r02_t5.log
 timeout 1200 python -m pytest tests/test_gpu_model.py -x -q > $O/r02_t6.log 2>&1; echo "rc=$?" >> $O/r02_t6.log; tail -4 $O/r02_t6.log

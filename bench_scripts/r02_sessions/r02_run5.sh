@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." && mkdir -p gpurun_out && O=gpurun_out
+cd "$(dirname "$0")/../.." && mkdir -p gpurun_out && O=gpurun_out
 timeout 200 python bench_scripts/tl_smoke.py > $O/r02_tl_smoke3.txt 2>&1; tail -2 $O/r02_tl_smoke3.txt
 timeout 1500 python -m pytest tests/test_gpu_kernels.py -x -q -k "gemm or linear or head or optim or conv_pool or step_graph" > $O/r02_t7.log 2>&1; echo "rc=$?" >> $O/r02_t7.log; tail -4 $O/r02_t7.log
 timeout 1200 python -m pytest tests/test_gpu_model.py -x -q > $O/r02_t8.log 2>&1; echo "rc=$?" >> $O/r02_t8.log; tail -4 $O/r02_t8.log
