@@ -98,3 +98,16 @@ def test_integration_index_matches_header():
     plumbing = {"t4k_version", "t4k_strerror", "t4k_device_count", "t4k_sm_count", "t4k_sync", "t4k_launch_count", "t4k_set_workspace_bank",
                 "t4k_set_carveout", "t4k_set_pdl", "t4k_set_conv_engine"}
     assert set(uncited) <= plumbing, set(uncited) - plumbing
+
+
+def test_host_mirror_fails_loudly_without_a_gpu():
+    """the Tensor / Model mirror (libt4host.so) has no CPU path either: init raises, nothing is computed on the host"""
+    import torch
+    if torch.cuda.is_available():
+        return
+    from tensorforth_b200 import host as th
+    from tensorforth_b200 import lib
+    import pytest
+    with pytest.raises(lib.T4KError) as e:
+        th.init(0)
+    assert "no CUDA device" in str(e.value) and "no CPU fallback" in str(e.value)
